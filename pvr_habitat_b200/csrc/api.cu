@@ -1,0 +1,323 @@
+// C ABI (include/pvr_b200.h): error reporting, encoder program executor, plain GEMM entry point.
+#include "pvr_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "conv_gemm.cuh"
+#include "kernels.cuh"
+
+namespace {
+thread_local char g_err[512] = "";
+}
+
+void pvr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* pvr_last_error(void) { return g_err; }
+extern "C" int pvr_abi_version(void) { return 1; }
+
+namespace {
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+  }
+  return sms;
+}
+
+int pick_block_n(int n_pad, long long m_tiles, int sms, int hint) {
+  if (hint) return hint;
+  if (n_pad % 64) return 32;
+  // Largest tile that still gives every SM work; wide tiles amortise the A-operand traffic.
+  const int cand[3] = {256, 128, 64};
+  for (int bn : cand)
+    if (n_pad % bn == 0 && m_tiles * (n_pad / bn) >= sms) return bn;
+  return 64;
+}
+
+struct BoundConv {
+  CUtensorMap ta, tb;
+  pvr::ConvGemmParams p;
+  int block_n, a_mode;
+};
+
+}  // namespace
+
+struct pvr_encoder {
+  std::vector<pvr_op> ops;
+  std::vector<pvr_slot> slots;
+  int emb_width = 0;
+  int n_images = 0;
+  int sms = 0;
+  std::vector<char*> slot_ptr;
+  std::vector<BoundConv> bound;  // one per op (unused for non-conv ops)
+};
+
+extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* slots, int n_slots, int emb_width,
+                                  pvr_encoder** out) {
+  if (!ops || n_ops <= 0 || !slots || n_slots <= 0 || !out || emb_width <= 0) {
+    pvr_set_error("pvr_encoder_create: invalid argument");
+    return PVR_ERR_ARG;
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    const pvr_op& o = ops[i];
+    const bool emb_out = (o.kind == PVR_OP_AVGPOOL || o.kind == PVR_OP_HEAD);
+    if (o.in_slot < 0 || o.in_slot >= n_slots || (!emb_out && (o.out_slot < 0 || o.out_slot >= n_slots)) ||
+        o.res_slot >= n_slots) {
+      pvr_set_error("pvr_encoder_create: op %d references a slot out of range", i);
+      return PVR_ERR_ARG;
+    }
+    if (o.kind == PVR_OP_CONV) {
+      if (!o.weight || !o.scale || !o.bias || o.k_pad <= 0 || o.k_pad % 64 || o.n_pad <= 0 || o.n_pad % 32 ||
+          o.c_out > o.n_pad || (o.in_pitch % 8) || (o.out_pitch % 8) || (o.out_coff % 8)) {
+        pvr_set_error("pvr_encoder_create: op %d has an invalid conv description", i);
+        return PVR_ERR_ARG;
+      }
+      if (!(o.c_in == 8 || o.c_in % 64 == 0)) {
+        pvr_set_error("pvr_encoder_create: op %d: c_in must be 8 or a multiple of 64 (got %d)", i, o.c_in);
+        return PVR_ERR_ARG;
+      }
+    } else if (o.kind != PVR_OP_MAXPOOL && o.kind != PVR_OP_AVGPOOL && o.kind != PVR_OP_HEAD) {
+      pvr_set_error("pvr_encoder_create: op %d has unknown kind %d", i, o.kind);
+      return PVR_ERR_ARG;
+    }
+  }
+  pvr_encoder* e = new (std::nothrow) pvr_encoder();
+  if (!e) {
+    pvr_set_error("pvr_encoder_create: out of memory");
+    return PVR_ERR_STATE;
+  }
+  e->ops.assign(ops, ops + n_ops);
+  e->slots.assign(slots, slots + n_slots);
+  e->emb_width = emb_width;
+  *out = e;
+  return PVR_OK;
+}
+
+static int64_t slot_offset(const pvr_encoder* enc, int slot, int n_images) {
+  int64_t off = 0;
+  for (int s = 0; s < slot; ++s) {
+    int64_t b = enc->slots[s].elems_per_image * 2 * (int64_t)n_images;
+    off += (b + 1023) & ~int64_t(1023);
+  }
+  return off;
+}
+
+extern "C" int64_t pvr_encoder_workspace_bytes(const pvr_encoder* enc, int n_images) {
+  if (!enc || n_images <= 0) return PVR_ERR_ARG;
+  return slot_offset(enc, (int)enc->slots.size(), n_images);
+}
+
+extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace, int64_t workspace_bytes,
+                                void** slot0) {
+  if (!enc || n_images <= 0 || !workspace || (reinterpret_cast<uintptr_t>(workspace) & 1023)) {
+    pvr_set_error("pvr_encoder_bind: invalid argument (workspace must be 1024-byte aligned)");
+    return PVR_ERR_ARG;
+  }
+  if (workspace_bytes < pvr_encoder_workspace_bytes(enc, n_images)) {
+    pvr_set_error("pvr_encoder_bind: workspace too small");
+    return PVR_ERR_ARG;
+  }
+  enc->sms = device_sm_count();
+  if (enc->sms <= 0) {
+    pvr_set_error("pvr_encoder_bind: no CUDA device (%s)", cudaGetErrorString(cudaGetLastError()));
+    return PVR_ERR_CUDA;
+  }
+  enc->n_images = 0;
+  enc->slot_ptr.resize(enc->slots.size());
+  for (size_t s = 0; s < enc->slots.size(); ++s)
+    enc->slot_ptr[s] = static_cast<char*>(workspace) + slot_offset(enc, (int)s, n_images);
+  enc->bound.assign(enc->ops.size(), BoundConv());
+  for (size_t i = 0; i < enc->ops.size(); ++i) {
+    const pvr_op& o = enc->ops[i];
+    if (o.kind != PVR_OP_CONV) continue;
+    BoundConv& b = enc->bound[i];
+    pvr::ConvGemmParams& p = b.p;
+    memset(&p, 0, sizeof(p));
+    const long long M = (long long)n_images * o.h_out * o.w_out;
+    if (M > 0x7fffffffll) {
+      pvr_set_error("pvr_encoder_bind: batch too large");
+      return PVR_ERR_ARG;
+    }
+    p.M = (int)M;
+    p.P = o.h_out;
+    p.Q = o.w_out;
+    p.num_m_tiles = (int)((M + 127) / 128);
+    b.block_n = pick_block_n(o.n_pad, p.num_m_tiles, enc->sms, o.block_n);
+    if (o.n_pad % b.block_n) {
+      pvr_set_error("pvr_encoder_bind: op %zu: n_pad %d not a multiple of the N tile %d", i, o.n_pad, b.block_n);
+      return PVR_ERR_ARG;
+    }
+    p.num_n_tiles = o.n_pad / b.block_n;
+    p.num_k_chunks = o.k_pad / 64;
+    p.S = o.s;
+    p.taps = o.r * o.s;
+    p.stride_w = o.stride_w;
+    p.stride_h = o.stride_h;
+    p.lower_w = o.lower_w;
+    p.lower_h = o.lower_h;
+    p.n_valid = o.c_out;
+    p.relu_n = o.relu_n;
+    p.ldo = o.out_pitch;
+    p.out = reinterpret_cast<__nv_bfloat16*>(enc->slot_ptr[o.out_slot]) + o.out_coff;
+    if (o.res_slot >= 0) {
+      p.res = reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.res_slot]) + o.res_coff;
+      p.ldr = o.res_pitch;
+    }
+    p.scale = o.scale;
+    p.bias = o.bias;
+    const char* err = "";
+    const void* in = enc->slot_ptr[o.in_slot];
+    const bool pointwise = (o.r == 1 && o.s == 1 && o.stride_h == 1 && o.stride_w == 1 && o.lower_h == 0 &&
+                            o.lower_w == 0 && o.h_in == o.h_out && o.w_in == o.w_out);
+    bool ok;
+    if (pointwise && o.c_in % 64 == 0) {
+      b.a_mode = pvr::A_TILED;
+      if (o.k_pad != o.c_in) {
+        pvr_set_error("pvr_encoder_bind: op %zu: k_pad must equal c_in for 1x1 convs", i);
+        return PVR_ERR_ARG;
+      }
+      ok = pvr::make_tmap_2d(&b.ta, in, (uint64_t)o.c_in, (uint64_t)M, (uint64_t)o.in_pitch, 128, &err);
+    } else {
+      const int upper_w = o.lower_w + (o.w_out - 1) * o.stride_w - (o.w_in - 1);
+      const int upper_h = o.lower_h + (o.h_out - 1) * o.stride_h - (o.h_in - 1);
+      if (o.c_in == 8) {
+        b.a_mode = pvr::A_IM2COL8;
+        if (o.k_pad < o.r * o.s * 8) {
+          pvr_set_error("pvr_encoder_bind: op %zu: k_pad too small", i);
+          return PVR_ERR_ARG;
+        }
+        ok = pvr::make_tmap_im2col(&b.ta, in, 8, o.in_pitch, o.w_in, o.h_in, n_images, o.lower_w, o.lower_h, upper_w,
+                                   upper_h, o.stride_w, o.stride_h, 8, 128, false, &err);
+      } else {
+        b.a_mode = pvr::A_IM2COL64;
+        p.cin_chunks = o.c_in / 64;
+        if (o.k_pad != o.r * o.s * o.c_in) {
+          pvr_set_error("pvr_encoder_bind: op %zu: k_pad must equal r*s*c_in", i);
+          return PVR_ERR_ARG;
+        }
+        ok = pvr::make_tmap_im2col(&b.ta, in, o.c_in, o.in_pitch, o.w_in, o.h_in, n_images, o.lower_w, o.lower_h,
+                                   upper_w, upper_h, o.stride_w, o.stride_h, 64, 128, true, &err);
+      }
+    }
+    if (!ok) {
+      pvr_set_error("pvr_encoder_bind: op %zu: activation tensor map: %s", i, err);
+      return PVR_ERR_CUDA;
+    }
+    if (!pvr::make_tmap_2d(&b.tb, o.weight, (uint64_t)o.k_pad, (uint64_t)o.n_pad, (uint64_t)o.k_pad,
+                           (uint32_t)b.block_n, &err)) {
+      pvr_set_error("pvr_encoder_bind: op %zu: weight tensor map: %s", i, err);
+      return PVR_ERR_CUDA;
+    }
+  }
+  enc->n_images = n_images;
+  if (slot0) *slot0 = enc->slot_ptr[0];
+  return PVR_OK;
+}
+
+extern "C" int pvr_encoder_forward(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream_) {
+  if (!enc || enc->n_images <= 0) {
+    pvr_set_error("pvr_encoder_forward: encoder is not bound");
+    return PVR_ERR_STATE;
+  }
+  if (!emb || emb_ld < enc->emb_width) {
+    pvr_set_error("pvr_encoder_forward: invalid embedding buffer");
+    return PVR_ERR_ARG;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int n = enc->n_images;
+  for (size_t i = 0; i < enc->ops.size(); ++i) {
+    const pvr_op& o = enc->ops[i];
+    cudaError_t e = cudaSuccess;
+    switch (o.kind) {
+      case PVR_OP_CONV: {
+        const BoundConv& b = enc->bound[i];
+        e = pvr::launch_conv_gemm(b.block_n, b.a_mode, b.ta, b.tb, b.p, enc->sms, stream);
+        break;
+      }
+      case PVR_OP_MAXPOOL:
+        e = pvr::launch_maxpool(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]),
+                                reinterpret_cast<__nv_bfloat16*>(enc->slot_ptr[o.out_slot]), n, o.h_in, o.w_in,
+                                o.c_in, o.h_out, o.w_out, stream);
+        break;
+      case PVR_OP_AVGPOOL:
+        e = pvr::launch_avgpool(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), emb, emb_ld,
+                                o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
+        break;
+      case PVR_OP_HEAD:
+        e = pvr::launch_head_tail(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), o.in_pitch,
+                                  static_cast<const float*>(o.aux), emb, emb_ld, o.emb_offset, n, o.h_in, o.w_in,
+                                  o.c_out, stream);
+        break;
+    }
+    if (e != cudaSuccess) {
+      pvr_set_error("pvr_encoder_forward: op %zu (kind %d): %s", i, o.kind, cudaGetErrorString(e));
+      return PVR_ERR_CUDA;
+    }
+  }
+  return PVR_OK;
+}
+
+extern "C" void* pvr_encoder_slot_ptr(const pvr_encoder* enc, int slot) {
+  if (!enc || enc->n_images <= 0 || slot < 0 || slot >= (int)enc->slot_ptr.size()) return nullptr;
+  return enc->slot_ptr[slot];
+}
+
+extern "C" int pvr_encoder_launch_count(const pvr_encoder* enc) { return enc ? (int)enc->ops.size() : 0; }
+
+extern "C" void pvr_encoder_destroy(pvr_encoder* enc) { delete enc; }
+
+extern "C" int pvr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo,
+                             const float* scale, const float* bias, const void* res, int64_t ldr, int m, int n,
+                             int n_pad, int k, int relu, void* stream) {
+  if (!a || !b || !out || !scale || !bias || m <= 0 || n <= 0 || n > n_pad || n_pad % 32 || k <= 0 || k % 64 ||
+      lda % 8 || ldb % 8 || ldo % 8 || (res && ldr % 8)) {
+    pvr_set_error("pvr_gemm_bf16: invalid argument");
+    return PVR_ERR_ARG;
+  }
+  const int sms = device_sm_count();
+  if (sms <= 0) {
+    pvr_set_error("pvr_gemm_bf16: no CUDA device");
+    return PVR_ERR_CUDA;
+  }
+  pvr::ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = m;
+  p.num_m_tiles = (m + 127) / 128;
+  const int block_n = pick_block_n(n_pad, p.num_m_tiles, sms, 0);
+  p.num_n_tiles = n_pad / block_n;
+  p.num_k_chunks = k / 64;
+  p.n_valid = n;
+  p.relu_n = relu ? n : 0;
+  p.ldo = ldo;
+  p.ldr = ldr;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.res = static_cast<const __nv_bfloat16*>(res);
+  p.scale = scale;
+  p.bias = bias;
+  CUtensorMap ta, tb;
+  const char* err = "";
+  if (!pvr::make_tmap_2d(&ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 128, &err) ||
+      !pvr::make_tmap_2d(&tb, b, (uint64_t)k, (uint64_t)n_pad, (uint64_t)ldb, (uint32_t)block_n, &err)) {
+    pvr_set_error("pvr_gemm_bf16: %s", err);
+    return PVR_ERR_CUDA;
+  }
+  cudaError_t e = pvr::launch_conv_gemm(block_n, pvr::A_TILED, ta, tb, p, sms, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) {
+    pvr_set_error("pvr_gemm_bf16: %s", cudaGetErrorString(e));
+    return PVR_ERR_CUDA;
+  }
+  return PVR_OK;
+}

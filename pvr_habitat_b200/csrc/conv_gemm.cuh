@@ -1,0 +1,50 @@
+// Host-visible declarations of the tcgen05 implicit-GEMM convolution / GEMM kernel.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pvr {
+
+// How the A operand (activations) reaches shared memory.
+enum AMode : int {
+  A_TILED = 0,     // plain (M x K) row-major matrix: 2-D tiled TMA, 128B swizzle (1x1 stride-1 convs, GEMMs)
+  A_IM2COL64 = 1,  // NHWC tensor, C_in % 64 == 0: one im2col TMA (64 channels x 128 pixels) per K chunk, 128B swizzle
+  A_IM2COL8 = 2,   // NHWC tensor with 8-element pixels (stem): 8 im2col TMAs (8 ch x 128 px) per K chunk, no swizzle
+};
+
+struct ConvGemmParams {
+  int M;             // GEMM rows = images * P * Q (output pixels)
+  int P, Q;          // output height / width per image (im2col modes)
+  int num_m_tiles;   // ceil(M / 128)
+  int num_n_tiles;   // n_pad / BLOCK_N
+  int num_k_chunks;  // k_pad / 64
+  int cin_chunks;    // A_IM2COL64: C_in / 64
+  int S;             // filter taps per row
+  int taps;          // R * S (real taps; chunks may be padded with repeats of tap 0 against zero weights)
+  int stride_w, stride_h;
+  int lower_w, lower_h;
+  int n_valid;       // real output channels (columns >= n_valid are not stored)
+  int relu_n;        // ReLU is applied to output columns < relu_n (0: none, >= n_valid: all)
+  long long ldo, ldr;  // output / residual row pitch in elements
+  __nv_bfloat16* out;
+  const __nv_bfloat16* res;  // may be null
+  const float* scale;        // (n_pad)
+  const float* bias;         // (n_pad)
+};
+
+// Launch on `stream`; block_n in {32, 64, 128, 256}. Returns cudaError_t of the launch.
+cudaError_t launch_conv_gemm(int block_n, int a_mode, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
+                             const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+
+// Tensor-map builders (driver entry points resolved through cudaGetDriverEntryPoint; no -lcuda needed).
+// 2-D K-major bf16 matrix (rows x k), row pitch ld elements, box = (64 x box_rows), 128B swizzle.
+bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                  const char** err);
+// im2col map over an NHWC bf16 tensor (N, H, W, pitch) exposing `c` channels per pixel.
+bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int lower_w,
+                      int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int channels_per_pixel,
+                      int pixels_per_column, bool swizzle128, const char** err);
+
+}  // namespace pvr

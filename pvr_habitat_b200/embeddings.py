@@ -1,0 +1,262 @@
+"""Drop-in for the reference's src/embeddings.py (EmbeddingNet / _get_embedding / UberModel / EmbeddingWrapper).
+
+Same constructor arguments, attributes (`embedding_name, in_channels, embedding, transforms, in_shape, out_size,
+device, training`), state_dict keys (`embedding.*`, empty for uber models — reference quirk D8, src/embeddings.py:45-53)
+and return types (`numpy (N, O)` float32 in eval mode, squeezed when N == 1, src/embeddings.py:398-402). The arithmetic
+runs in libpvr_b200: the fused uint8 preprocessing kernel and the tcgen05 encoder program. There is no CPU path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from . import program as prg
+from .vision_models.moco import moco_conv3_compressed, moco_conv4_compressed, moco_conv5
+from .vision_models.resnet import resnet_conv3_compressed, resnet_conv4_compressed, resnet_conv5
+from .vision_models.resnet_params import ResNet50Params
+
+IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+CLIP_MEAN, CLIP_STD = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+
+
+def resize_geometry(h, w, size=256, crop=224):
+    """torchvision Resize(int) + CenterCrop geometry (transforms/functional.py:368-384, 592-594)."""
+    if h <= w:
+        rh, rw = size, int(size * w / h)
+    else:
+        rh, rw = int(size * h / w), size
+    top = int(round((rh - crop) / 2.0))
+    left = int(round((rw - crop) / 2.0))
+    return rh, rw, top, left
+
+
+class Transforms(nn.Module):
+    """Resize(256) -> CenterCrop(224) -> ConvertImageDtype(float) -> Normalize (src/embeddings.py:80-85) as ONE kernel.
+
+    Calling it on an NCHW uint8 tensor (the reference's calling convention, src/embeddings.py:393) returns the
+    NCHW float32 tensor the reference's nn.Sequential of torchvision transforms returns, bit for bit.
+    """
+
+    def __init__(self, mean=IMAGENET_MEAN, std=IMAGENET_STD, size=256, crop=224):
+        super().__init__()
+        self.mean, self.std, self.size, self.crop = list(mean), list(std), size, crop
+
+    def run(self, obs_nhwc_u8, n_frames, out_ptr, fmt, sample_major):
+        """obs: CUDA uint8 (N, H, W, 3*n_frames) contiguous; writes n_frames*N images at `out_ptr`."""
+        n, h, w, ch = obs_nhwc_u8.shape
+        assert ch == 3 * n_frames and obs_nhwc_u8.dtype == torch.uint8 and obs_nhwc_u8.is_contiguous()
+        rh, rw, top, left = resize_geometry(h, w, self.size, self.crop)
+        mean = (ctypes.c_float * 3)(*self.mean)
+        std = (ctypes.c_float * 3)(*self.std)
+        with torch.cuda.device(obs_nhwc_u8.device):
+            _lib.check(_lib.lib().pvr_preprocess_u8(obs_nhwc_u8.data_ptr(), n, h, w, n_frames, rh, rw, top, left,
+                                                    self.crop, mean, std, out_ptr, fmt, int(sample_major),
+                                                    _lib.current_stream_ptr()), "pvr_preprocess_u8")
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise _lib.PvrError("pvr_habitat_b200 transforms run on CUDA only (no CPU fallback)")
+        if x.dtype != torch.uint8:
+            raise _lib.PvrError("transforms expect the uint8 frames the reference feeds them")
+        nhwc = x.permute(0, 2, 3, 1).contiguous()
+        out = torch.empty(x.shape[0], 3, self.crop, self.crop, dtype=torch.float32, device=x.device)
+        self.run(nhwc, 1, out.data_ptr(), _lib.PVR_FMT_NCHW_F32, False)
+        return out
+
+
+class UberModel(nn.Module):
+    """Concatenation of several encoders (src/embeddings.py:44-57). `models` is a plain list, as in the reference,
+    so an uber EmbeddingNet has an empty state_dict."""
+
+    def __init__(self, models):
+        super(UberModel, self).__init__()
+        self.models = models
+        assert all(models[0].training == m.training for m in models)
+        self.training = models[0].training
+        self.out_size = sum(m.out_size for m in models)
+
+    def to(self, device):
+        self.models = [m.to(device=device) for m in self.models]
+        return self
+
+
+_MOCO_CONV5 = {
+    'demy': 'demy.pth', 'moco_aug': 'moco_aug.pth.tar', 'moco_aug_habitat': 'moco_aug_habitat_64.pth',
+    'moco_aug_mujoco': 'moco_aug_mujoco.pth', 'moco_aug_uber': 'moco_aug_uber.pth',
+    'moco_aug_places': 'moco_aug_places.pth.tar', 'moco_croponly': 'moco_croponly.pth',
+    'moco_croponly_places': 'moco_croponly_places.pth', 'moco_croponly_habitat': 'moco_croponly_habitat_64.pth',
+    'moco_croponly_mujoco': 'moco_croponly_mujoco.pth', 'moco_croponly_uber': 'moco_croponly_uber.pth',
+    'moco_coloronly': 'moco_coloronly.pth',
+}
+_MOCO_L4 = {n: n + '.pth' for n in ('moco_aug_l4', 'moco_aug_places_l4', 'moco_croponly_l4',
+                                    'moco_croponly_places_l4')}
+_MOCO_L3 = {n: n + '.pth' for n in ('moco_aug_l3', 'moco_aug_places_l3', 'moco_croponly_l3',
+                                    'moco_croponly_places_l3')}
+_RESNET = {
+    'resnet50_places': (resnet_conv5, 'resnet50_places.pth.tar'),
+    'resnet50_l4': (resnet_conv4_compressed, 'resnet50_l4.pth.tar'),
+    'resnet50_l3': (resnet_conv3_compressed, 'resnet50_l3.tar'),
+    'resnet50_places_l4': (resnet_conv4_compressed, 'resnet50_places_l4.tar'),
+    'resnet50_places_l3': (resnet_conv3_compressed, 'resnet50_places_l3.tar'),
+}
+_UBER_PARTS = {'3': '_l3', '4': '_l4', '5': ''}
+
+
+def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, train=False):
+    """Same names and return convention as src/embeddings.py:60-332: `(model, transforms)`."""
+    transforms = Transforms(IMAGENET_MEAN, IMAGENET_STD)
+    assert in_channels == 3, 'Current models accept 3-channel inputs only.'
+
+    if embedding_name == 'resnet50':
+        # torchvision.models.resnet50(pretrained=...), fc -> Identity (src/embeddings.py:118-120). Offline there is no
+        # download: pretrained weights must already be loaded by the caller through load_state_dict.
+        model = ResNet50Params('conv5')
+    elif embedding_name in _MOCO_CONV5:
+        model = moco_conv5(checkpoint_path=_MOCO_CONV5[embedding_name])
+    elif embedding_name in _MOCO_L4:
+        model = moco_conv4_compressed(checkpoint_path=_MOCO_L4[embedding_name])
+    elif embedding_name in _MOCO_L3:
+        model = moco_conv3_compressed(checkpoint_path=_MOCO_L3[embedding_name])
+    elif embedding_name in _RESNET:
+        fn, path = _RESNET[embedding_name]
+        model = fn(checkpoint_path=path)
+    elif '_uber_' in embedding_name and embedding_name.startswith('moco_'):
+        # e.g. moco_aug_places_uber_345 -> [moco_aug_places_l3, moco_aug_places_l4, moco_aug_places]
+        base, taps = embedding_name.split('_uber_')
+        if base not in ('moco_aug', 'moco_aug_places', 'moco_croponly', 'moco_croponly_places') or \
+                taps not in ('345', '35', '34', '45'):
+            raise NotImplementedError("Requested model not available.")
+        model = UberModel([_get_embedding(base + _UBER_PARTS[t])[0] for t in taps])
+    elif embedding_name == 'true_state':
+        return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
+    else:
+        # 'random', 'clip_vit', mae_*, resnet18/34, clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
+        raise NotImplementedError("Requested model not available.")
+
+    if train:
+        raise NotImplementedError("pvr_habitat_b200 runs the frozen-encoder path only (train=False).")
+    model.eval()
+    for p in model.parameters():
+        p.requires_grad = False
+    return model, transforms
+
+
+def build_encoder(model, device, hw=224):
+    """Compile `model` (ResNet50Params or UberModel of them) into one pvr_encoder program on `device`."""
+    prog = prg.Program()
+    in_slot = prog.new_slot(hw * hw * 4)  # slot 0: NHWC4 bf16 frames written by the preprocessing kernel
+    parts = model.models if isinstance(model, UberModel) else [model]
+    off = 0
+    for m in parts:
+        sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        off += prg.add_resnet50(prog, sd, m.variant, in_slot, off, hw)
+    prog.emb_width = off
+    return prog.finish(device)
+
+
+class EmbeddingNet(nn.Module):
+    """
+    Input shape must be (N, H, W, 3), where N is the number of frames.
+    The output shape will be (N, O), where O is the embedding size.  (src/embeddings.py:339-402)
+    """
+
+    def __init__(self, embedding_name, in_channels=3, pretrained=True, train=False, disable_cuda=False):
+        super(EmbeddingNet, self).__init__()
+        self.embedding_name = embedding_name
+        if self.embedding_name == 'true_state':
+            return
+        self.in_channels = in_channels
+        self.embedding, self.transforms = _get_embedding(embedding_name, in_channels, pretrained, train)
+        self.in_shape = torch.Size([in_channels, self.transforms.crop, self.transforms.crop])
+        self.out_size = int(self.embedding.out_size)
+        if torch.cuda.is_available() and not disable_cuda:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        else:
+            self.device = torch.device('cpu')
+        self.embedding = self.embedding.to(device=self.device)
+        self.training = self.embedding.training
+        self._encoder = None
+        self._emb = None
+
+    # ---- weights changed -> recompile the program lazily
+    def load_state_dict(self, *args, **kwargs):
+        self._encoder = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def invalidate(self):
+        """Call after mutating `self.embedding` parameters in place."""
+        self._encoder = None
+
+    def _require_cuda(self):
+        if self.device.type != 'cuda':
+            raise _lib.PvrError("EmbeddingNet: CUDA device required — pvr_habitat_b200 has no CPU fallback "
+                                "(disable_cuda=True is only meaningful for the reference implementation).")
+
+    def encoder(self):
+        self._require_cuda()
+        if self._encoder is None:
+            self._encoder = build_encoder(self.embedding, self.device, self.transforms.crop)
+        return self._encoder
+
+    def preprocess(self, observation):
+        """(N, H, W, 3) uint8 -> (N, 3, 224, 224) float32 CUDA tensor, bit-identical to the reference transforms."""
+        self._require_cuda()
+        obs = observation.to(device=self.device).contiguous()
+        out = torch.empty(obs.shape[0], 3, self.transforms.crop, self.transforms.crop, dtype=torch.float32,
+                          device=self.device)
+        self.transforms.run(obs, 1, out.data_ptr(), _lib.PVR_FMT_NCHW_F32, False)
+        return out
+
+    def embed(self, observation, n_frames=1, out=None):
+        """Fused path: (N, H, W, 3*n_frames) uint8 -> CUDA float32 (N, n_frames*O).
+
+        Covers the host-side frame split / regroup of main_bc_1.py:128-136 and save_embedded_obs.py:149-155:
+        frame f of sample i lands in out[i, f*O:(f+1)*O].
+        """
+        self._require_cuda()
+        obs = observation.to(device=self.device)
+        if not obs.is_contiguous():
+            obs = obs.contiguous()
+        n = obs.shape[0]
+        enc = self.encoder()
+        enc.bind(n * n_frames)
+        self.transforms.run(obs, n_frames, enc.slot0, _lib.PVR_FMT_NHWC4_BF16, True)
+        if out is None:
+            out = torch.empty(n, n_frames * self.out_size, dtype=torch.float32, device=self.device)
+        enc.forward(out, self.out_size)
+        return out
+
+    def forward(self, observation):
+        if self.embedding_name == 'true_state':
+            return observation.squeeze().cpu().numpy()
+        # observation.shape -> (N, H, W, 3)
+        out = self.embed(observation, 1)
+        return out.view(-1, self.out_size).squeeze().cpu().numpy()
+
+
+try:  # the gym adaptor exists only where gym does (simulator side; not on the embedding/BC hot path)
+    import gym
+    from gym.spaces.box import Box
+
+    class EmbeddingWrapper(gym.ObservationWrapper):
+        """src/embeddings.py:409-444: (H, W, 3n) frames -> flat (n*O,) embedding."""
+
+        def __init__(self, env, embedding):
+            gym.ObservationWrapper.__init__(self, env)
+            in_channels = env.observation_space.shape[2]
+            assert in_channels % 3 == 0, "Only RGB images are supported."
+            self.in_channels = 3
+            self.n_frames = in_channels // 3
+            self.embedding = embedding
+            self.observation_space = Box(low=-np.inf, high=np.inf,
+                                         shape=(self.embedding.out_size * self.n_frames,))
+
+        def observation(self, observation):
+            obs = torch.from_numpy(np.ascontiguousarray(observation))[None]
+            return self.embedding.embed(obs, self.n_frames).flatten().cpu().numpy()
+except ImportError:  # pragma: no cover
+    class EmbeddingWrapper(object):
+        def __init__(self, *a, **k):
+            raise ImportError("EmbeddingWrapper needs `gym` (the reference's simulator stack)")

@@ -1,0 +1,302 @@
+"""Host-side compiler from a (torchvision-named) ResNet-50 state_dict to the flat op program executed by
+libpvr_b200 (include/pvr_b200.h: pvr_op / pvr_encoder_*).
+
+What the program computes is what the reference builds in src/vision_models/moco.py:6-113 out of
+torchvision's ResNet (torchvision/models/resnet.py:108-166 Bottleneck, :59-105 BasicBlock, :266-282 forward):
+eval-mode BatchNorm is folded into a per-channel fp32 scale/bias applied in the GEMM epilogue, activations are NHWC
+bf16, weights are bf16 (C_out, K) with K ordered (tap_row, tap_col, channel).
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+from ._lib import pvr_op, pvr_slot
+
+BN_EPS = 1e-5
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def fold_bn(sd, prefix, conv_bias=None):
+    """eval-mode BN(x) = (x - mean) / sqrt(var + eps) * gamma + beta  ->  x * scale + bias (fp32)."""
+    g, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
+    m, v = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
+    scale = g / torch.sqrt(v + BN_EPS)
+    bias = b - m * scale
+    if conv_bias is not None:
+        bias = bias + conv_bias.double() * scale
+    return scale.float(), bias.float()
+
+
+def pack_conv_weight(w, n_pad):
+    """(C_out, C_in, R, S) fp32 -> bf16 (n_pad, R*S*C_in), K ordered (r, s, c)."""
+    co, ci, r, s = w.shape
+    k = r * s * ci
+    out = torch.zeros(n_pad, k, dtype=torch.bfloat16)
+    out[:co] = w.permute(0, 2, 3, 1).reshape(co, k).to(torch.bfloat16)
+    return out
+
+
+def pack_stem_weight(w, n_pad):
+    """7x7 stride-2 stem over NHWC4 input seen as (H, W/2, 8): the filter becomes 7 x 4 taps of 8 values.
+
+    Output column q reads input columns 2q-3 .. 2q+3 = pixel pairs q-2 .. q+1; in pair sp the element e holds
+    input column 2(q-2+sp)+e, i.e. filter column j = 2*sp + e - 1 (j = -1 does not exist -> zero).
+    K index = ((r*4 + sp)*8 + e*4 + c); 28 taps padded to 32 (k_pad = 256).
+    """
+    co, ci, r, s = w.shape
+    assert (ci, r, s) == (3, 7, 7)
+    out = torch.zeros(n_pad, 32, 8, dtype=torch.float32)
+    for rr in range(7):
+        for sp in range(4):
+            for e in range(2):
+                j = 2 * sp + e - 1
+                if 0 <= j < 7:
+                    out[:co, rr * 4 + sp, e * 4:e * 4 + 3] = w[:, :, rr, j]
+    return out.reshape(n_pad, 256).to(torch.bfloat16)
+
+
+class Program:
+    """Accumulates ops/slots; `finish(device)` uploads the packed weights and creates the pvr_encoder."""
+
+    def __init__(self):
+        self.ops = []          # dicts of pvr_op fields + host tensors
+        self.slot_elems = []   # per-slot bf16 elements per image
+        self.free = []
+        self.emb_width = 0
+
+    # ---- slots
+    def new_slot(self, elems):
+        self.slot_elems.append(int(elems))
+        return len(self.slot_elems) - 1
+
+    def alloc(self, elems):
+        if self.free:
+            s = self.free.pop()
+            self.slot_elems[s] = max(self.slot_elems[s], int(elems))
+            return s
+        return self.new_slot(elems)
+
+    def release(self, s):
+        if s not in self.free:
+            self.free.append(s)
+
+    # ---- ops
+    def conv(self, in_slot, in_chw, w_packed, k_pad, c_out, r, s, stride, lower, out_hw, scale, bias, relu_n,
+             in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0):
+        c_in, h_in, w_in = in_chw
+        n_pad = w_packed.shape[0]
+        p, q = out_hw
+        if out_pitch is None:
+            out_pitch = _round_up(c_out, 8)
+        if out_slot is None:
+            out_slot = self.alloc(p * q * out_pitch)
+        sc = torch.zeros(n_pad, dtype=torch.float32)
+        bi = torch.zeros(n_pad, dtype=torch.float32)
+        sc[:c_out] = scale
+        bi[:c_out] = bias
+        op = dict(kind=_lib.PVR_OP_CONV, in_slot=in_slot, out_slot=out_slot, res_slot=-1, c_in=c_in, h_in=h_in,
+                  w_in=w_in, in_pitch=in_pitch if in_pitch is not None else c_in, c_out=c_out, h_out=p, w_out=q,
+                  out_pitch=out_pitch, res_pitch=0, out_coff=out_coff, res_coff=0, r=r, s=s,
+                  stride_h=stride[0], stride_w=stride[1], lower_h=lower[0], lower_w=lower[1], relu_n=relu_n,
+                  block_n=block_n, k_pad=k_pad, n_pad=n_pad, emb_offset=0,
+                  _weight=w_packed.contiguous(), _scale=sc, _bias=bi)
+        if res is not None:
+            op.update(res_slot=res[0], res_pitch=res[1], res_coff=res[2])
+        self.ops.append(op)
+        return out_slot
+
+    def maxpool(self, in_slot, c, h, w):
+        p, q = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        out_slot = self.alloc(p * q * c)
+        self.ops.append(dict(kind=_lib.PVR_OP_MAXPOOL, in_slot=in_slot, out_slot=out_slot, res_slot=-1, c_in=c,
+                             h_in=h, w_in=w, in_pitch=c, c_out=c, h_out=p, w_out=q, out_pitch=c))
+        return out_slot, p, q
+
+    def avgpool(self, in_slot, c, h, w, emb_offset):
+        self.ops.append(dict(kind=_lib.PVR_OP_AVGPOOL, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=c, h_in=h,
+                             w_in=w, in_pitch=c, c_out=c, emb_offset=emb_offset))
+
+    def head_tail(self, in_slot, pitch, c, h, w, aux, emb_offset):
+        self.ops.append(dict(kind=_lib.PVR_OP_HEAD, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=2 * c, h_in=h,
+                             w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset, _aux=aux.contiguous()))
+
+    # ---- finalise
+    def finish(self, device):
+        return Encoder(self, device)
+
+
+class Encoder:
+    """Owns the device copies of the packed weights, the pvr_encoder handle and the bound workspace."""
+
+    def __init__(self, prog, device):
+        self.lib = _lib.lib()
+        self.device = torch.device(device)
+        self.emb_width = prog.emb_width
+        self._keep = []
+        ops = (pvr_op * len(prog.ops))()
+        for i, d in enumerate(prog.ops):
+            o = ops[i]
+            for k, v in d.items():
+                if not k.startswith("_"):
+                    setattr(o, k, int(v))
+            for key, field in (("_weight", "weight"), ("_scale", "scale"), ("_bias", "bias"), ("_aux", "aux")):
+                if key in d:
+                    t = d[key].to(self.device)
+                    self._keep.append(t)
+                    setattr(o, field, t.data_ptr())
+        slots = (pvr_slot * len(prog.slot_elems))()
+        for i, e in enumerate(prog.slot_elems):
+            slots[i].elems_per_image = e
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.pvr_encoder_create(ops, len(prog.ops), slots, len(prog.slot_elems), prog.emb_width,
+                                               ctypes.byref(handle)), "pvr_encoder_create")
+        self.handle = handle
+        self.n_ops = len(prog.ops)
+        self.n_images = 0
+        self.workspace = None
+        self.slot0 = None
+        self.op_meta = [{k: v for k, v in d.items() if not k.startswith("_")} for d in prog.ops]
+
+    def bind(self, n_images):
+        if n_images == self.n_images:
+            return
+        need = self.lib.pvr_encoder_workspace_bytes(self.handle, n_images)
+        if need < 0:
+            raise _lib.PvrError("pvr_encoder_workspace_bytes failed")
+        if self.workspace is None or self.workspace.numel() < need + 1024:
+            self.workspace = None
+            self.workspace = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        base = (self.workspace.data_ptr() + 1023) // 1024 * 1024
+        slot0 = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pvr_encoder_bind(self.handle, n_images, base, need, ctypes.byref(slot0)),
+                       "pvr_encoder_bind")
+        self.slot0 = slot0.value
+        self.n_images = n_images
+
+    def forward(self, emb, emb_ld=None):
+        """emb: float32 CUDA tensor with at least n_images rows of emb_ld floats."""
+        if emb_ld is None:
+            emb_ld = emb.stride(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pvr_encoder_forward(self.handle, emb.data_ptr(), emb_ld, _lib.current_stream_ptr()),
+                       "pvr_encoder_forward")
+
+    def slot_ptr(self, slot):
+        return self.lib.pvr_encoder_slot_ptr(self.handle, slot)
+
+    def slot_tensor(self, slot, shape):
+        """View a slot as a bf16 tensor (tests / per-layer parity). Copies out of the workspace."""
+        ptr = self.slot_ptr(slot)
+        off = ptr - self.workspace.data_ptr()
+        n = math.prod(shape)
+        return self.workspace[off:off + 2 * n].view(torch.bfloat16).view(*shape).clone()
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.pvr_encoder_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------------------------------------ ResNet-50
+RESNET50_LAYERS = (("layer1", 64, 3, 1), ("layer2", 128, 4, 2), ("layer3", 256, 6, 2), ("layer4", 512, 3, 2))
+
+
+def _conv_bn(prog, sd, conv_key, bn_key, in_slot, in_chw, stride, pad, relu, res=None, block_n=0):
+    w = sd[conv_key + ".weight"].float()
+    co, ci, r, s = w.shape
+    assert ci == in_chw[0], (conv_key, ci, in_chw)
+    scale, bias = fold_bn(sd, bn_key, sd.get(conv_key + ".bias"))
+    n_pad = _round_up(co, 64)
+    h, wd = in_chw[1], in_chw[2]
+    p = (h + 2 * pad - r) // stride + 1
+    q = (wd + 2 * pad - s) // stride + 1
+    out = prog.conv(in_slot, in_chw, pack_conv_weight(w, n_pad), r * s * ci, co, r, s, (stride, stride),
+                    (-pad, -pad), (p, q), scale, bias, co if relu else 0, res=res, block_n=block_n)
+    return out, (co, p, q)
+
+
+def _bottleneck(prog, sd, prefix, x_slot, x_chw, stride, has_ds):
+    """torchvision Bottleneck (resnet.py:143-166), stride on the 3x3 conv (v1.5)."""
+    t1, s1 = _conv_bn(prog, sd, prefix + ".conv1", prefix + ".bn1", x_slot, x_chw, 1, 0, True)
+    t2, s2 = _conv_bn(prog, sd, prefix + ".conv2", prefix + ".bn2", t1, s1, stride, 1, True)
+    prog.release(t1)
+    if has_ds:
+        idn, sidn = _conv_bn(prog, sd, prefix + ".downsample.0", prefix + ".downsample.1", x_slot, x_chw, stride, 0,
+                             False)
+        prog.release(x_slot)
+    else:
+        idn, sidn = x_slot, x_chw
+    y, sy = _conv_bn(prog, sd, prefix + ".conv3", prefix + ".bn3", t2, s2, 1, 0, True, res=(idn, sidn[0], 0))
+    prog.release(t2)
+    prog.release(idn)
+    return y, sy
+
+
+def _compress_head(prog, sd, prefix, x_slot, x_chw, emb_offset):
+    """BasicBlock(C, c, downsample=Sequential(Conv2d(C, c, 3, padding=1, bias=True), BN)) of moco.py:34-50/:78-94.
+
+    conv1 (-> bn1 -> ReLU) and the biased downsample conv (-> BN) read the same input: one GEMM with 2c output
+    columns (ReLU on the first c only); conv2 -> bn2 -> += identity -> ReLU runs in the head-tail kernel, which
+    writes the NCHW-flattened float32 embedding columns.
+    """
+    w1 = sd[prefix + ".conv1.weight"].float()
+    wd = sd[prefix + ".downsample.0.weight"].float()
+    c = w1.shape[0]
+    C, h, w = x_chw
+    s1, b1 = fold_bn(sd, prefix + ".bn1")
+    sdn, bdn = fold_bn(sd, prefix + ".downsample.1", sd[prefix + ".downsample.0.bias"])
+    n_pad = _round_up(2 * c, 32)
+    pitch = n_pad
+    wcat = torch.cat([w1, wd], 0)
+    t = prog.conv(x_slot, x_chw, pack_conv_weight(wcat, n_pad), 9 * C, 2 * c, 3, 3, (1, 1), (-1, -1), (h, w),
+                  torch.cat([s1, sdn]), torch.cat([b1, bdn]), c, out_pitch=pitch)
+    w2 = sd[prefix + ".conv2.weight"].float()  # (c, c, 3, 3) -> (co, r, s, ci)
+    s2, b2 = fold_bn(sd, prefix + ".bn2")
+    aux = torch.cat([w2.permute(0, 2, 3, 1).reshape(-1), s2, b2]).float()
+    prog.head_tail(t, pitch, c, h, w, aux, emb_offset)
+    prog.release(t)
+    return c * h * w
+
+
+def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
+    """Append one ResNet-50 trunk reading the NHWC4 bf16 frames in `in_slot`.
+
+    variant: 'conv5' (moco_conv5 / resnet50: avg-pooled 2048), 'l4' (moco_conv4_compressed: 42*7*7 = 2058),
+             'l3' (moco_conv3_compressed: 11*14*14 = 2156). Returns the number of embedding columns written.
+    """
+    pre = {"conv5": ("layer3.", "layer4."), "l4": ("layer3.", "layer4.0."), "l3": ("layer3.0.", None)}[variant]
+    # stem: 7x7/2 as a 7x4-tap conv over pixel pairs (see pack_stem_weight)
+    scale, bias = fold_bn(sd, "bn1")
+    p = (hw + 6 - 7) // 2 + 1
+    stem = prog.conv(in_slot, (8, hw, hw // 2), pack_stem_weight(sd["conv1.weight"].float(), 64), 256, 64, 7, 4,
+                     (2, 1), (-3, -2), (p, p), scale, bias, 64)
+    x, h, w = prog.maxpool(stem, 64, p, p)
+    prog.release(stem)
+    chw = (64, h, w)
+    for name, planes, blocks, stride in RESNET50_LAYERS:
+        if name == "layer4" and pre[1] is None:
+            break
+        key = name + "."
+        if name == "layer3":
+            key = pre[0]
+        elif name == "layer4":
+            key = pre[1]
+        for b in range(blocks):
+            x, chw = _bottleneck(prog, sd, f"{key}{b}", x, chw, stride if b == 0 else 1, b == 0)
+    if variant == "conv5":
+        prog.avgpool(x, chw[0], chw[1], chw[2], emb_offset)
+        prog.release(x)
+        return chw[0]
+    head_prefix = "layer4.1" if variant == "l4" else "layer3.1"
+    n = _compress_head(prog, sd, head_prefix, x, chw, emb_offset)
+    prog.release(x)
+    return n

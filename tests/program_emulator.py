@@ -1,0 +1,77 @@
+"""CPU emulation of the op program that pvr_habitat_b200.program emits (test infrastructure only).
+
+It interprets the very fields libpvr_b200 consumes (packed bf16 weights, lower corner, traversal strides, pitches,
+channel offsets), in fp32 torch, so host-side packing / slot planning is verified without a GPU.
+"""
+import torch
+import torch.nn.functional as F
+
+from pvr_habitat_b200 import _lib
+
+
+def emulate(prog, frames_nhwc4, round_bf16=True):
+    """frames_nhwc4: (N, H, W, 4) float tensor (slot 0 contents). Returns (N, emb_width) float32."""
+    n = frames_nhwc4.shape[0]
+    slots = {0: frames_nhwc4.reshape(n, -1).float()}
+    emb = torch.zeros(n, prog.emb_width)
+
+    def rb(t):
+        return t.to(torch.bfloat16).float() if round_bf16 else t
+
+    slots[0] = rb(slots[0])
+    for op in prog.ops:
+        k = op["kind"]
+        if k == _lib.PVR_OP_CONV:
+            ci, hi, wi, pitch = op["c_in"], op["h_in"], op["w_in"], op["in_pitch"]
+            x = slots[op["in_slot"]][:, :hi * wi * pitch].reshape(n, hi, wi, pitch)[..., :ci].permute(0, 3, 1, 2)
+            r, s = op["r"], op["s"]
+            w = op["_weight"].float()
+            co, npad = op["c_out"], op["n_pad"]
+            kk = r * s * ci
+            wt = w[:, :kk].reshape(npad, r, s, ci).permute(0, 3, 1, 2)
+            assert torch.all(w[:, kk:] == 0), "padded K columns must carry zero weights"
+            p, q = op["h_out"], op["w_out"]
+            pl, pt = -op["lower_w"], -op["lower_h"]
+            pr = (q - 1) * op["stride_w"] + s - wi - pl
+            pb = (p - 1) * op["stride_h"] + r - hi - pt
+            xp = F.pad(x, (pl, max(pr, 0), pt, max(pb, 0)))
+            y = F.conv2d(xp, wt, stride=(op["stride_h"], op["stride_w"]))[:, :, :p, :q]
+            y = y * op["_scale"][None, :, None, None] + op["_bias"][None, :, None, None]
+            y = y[:, :co]
+            if op["res_slot"] >= 0:
+                rp = op["res_pitch"]
+                res = slots[op["res_slot"]][:, :p * q * rp].reshape(n, p, q, rp)
+                y = y + res[..., op["res_coff"]:op["res_coff"] + co].permute(0, 3, 1, 2)
+            rn = op["relu_n"]
+            if rn > 0:
+                y = torch.cat([y[:, :rn].relu(), y[:, rn:]], 1)
+            op_ = op["out_pitch"]
+            buf = slots.get(op["out_slot"])
+            need = p * q * op_
+            if buf is None or buf.shape[1] < need:
+                buf = torch.zeros(n, need)
+            view = buf[:, :need].reshape(n, p, q, op_).clone()
+            view[..., op["out_coff"]:op["out_coff"] + co] = rb(y.permute(0, 2, 3, 1))
+            nb = torch.zeros(n, max(need, buf.shape[1]))
+            nb[:, :need] = view.reshape(n, -1)
+            slots[op["out_slot"]] = nb
+        elif k == _lib.PVR_OP_MAXPOOL:
+            c, h, w = op["c_in"], op["h_in"], op["w_in"]
+            x = slots[op["in_slot"]][:, :h * w * c].reshape(n, h, w, c).permute(0, 3, 1, 2)
+            y = F.max_pool2d(x, 3, 2, 1)
+            slots[op["out_slot"]] = y.permute(0, 2, 3, 1).reshape(n, -1).contiguous()
+        elif k == _lib.PVR_OP_AVGPOOL:
+            c, h, w = op["c_in"], op["h_in"], op["w_in"]
+            x = slots[op["in_slot"]][:, :h * w * c].reshape(n, h * w, c)
+            emb[:, op["emb_offset"]:op["emb_offset"] + c] = x.mean(1)
+        elif k == _lib.PVR_OP_HEAD:
+            c, h, w, pitch = op["c_out"], op["h_in"], op["w_in"], op["in_pitch"]
+            t = slots[op["in_slot"]][:, :h * w * pitch].reshape(n, h, w, pitch)
+            a = t[..., :c].permute(0, 3, 1, 2)
+            idn = t[..., c:2 * c].permute(0, 3, 1, 2)
+            aux = op["_aux"]
+            w2 = aux[:c * 9 * c].reshape(c, 3, 3, c).permute(0, 3, 1, 2)
+            s2, b2 = aux[c * 9 * c:c * 9 * c + c], aux[c * 9 * c + c:]
+            y = F.conv2d(a, w2, padding=1) * s2[None, :, None, None] + b2[None, :, None, None] + idn
+            emb[:, op["emb_offset"]:op["emb_offset"] + c * h * w] = y.relu().reshape(n, -1)
+    return emb

@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py — PVR frames/sec embedded (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload uber34x3|conv5]
+
+One step = one pass of the embedding hot path over one batch of synthetic observations:
+uint8 (B, 224, 224, 3n) -> fused preprocessing kernel -> ResNet-50 trunk(s) (tcgen05 implicit GEMM) -> (B, n*O) fp32.
+Default workload = BASELINE.json configs[1]: moco_aug_uber_34 (layer3 + layer4 compressed taps, two independent
+ResNet-50 trunks as the reference computes them, src/embeddings.py:44-57,225-229), 3-frame observations, bf16.
+
+`value`   frames/s with the batch already resident in HBM (frames = B * n per step, summed over ranks).
+`e2e`     the same metric through the public API with HOST buffers: pinned uint8 observations -> H2D ->
+          EmbeddingNet.embed -> D2H of the embeddings, every step inside the timed region.
+`roofline` dominant kernel = conv_gemm_kernel (all tcgen05 conv launches of a step): algorithmic conv FLOPs of the
+          step / summed device time of those launches (CUDA events between ops on the launch stream, measured here).
+`cpu_baseline` the oracle's CPU port of the same workload on this host's cores (bounded sample), rank 0, N=1 only.
+--impl reference: the reference's own CPU implementation of the path (oracle port: the reference is Python and does
+          not travel to the GPU box) on all host threads, same JSON schema.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (embedding name, frames per observation, observations per step per GPU)
+    "uber34x3": ("moco_aug_uber_34", 3, 96),
+    "conv5": ("moco_aug", 1, 256),
+}
+VARIANTS = {"moco_aug": ["conv5"], "moco_aug_uber_34": ["l3", "l4"]}
+GFLOP_PER_FRAME = {"moco_aug": 8.174, "moco_aug_uber_34": 14.96}  # SURVEY.md §8(d), convs only
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_observations(n, n_frames, seed):
+    """Structured synthetic frames (not iid noise), tiled from a small seeded set to bound generation time."""
+    from oracle import restate  # synthetic-input generator only (inputs, not the measured path)
+    base = restate.structured_frames(16, 224, 224, 3 * n_frames, seed)
+    reps = (n + 15) // 16
+    obs = np.concatenate([np.roll(base, shift=7 * r, axis=2) for r in range(reps)])[:n]
+    return np.ascontiguousarray(obs)
+
+
+def oracle_parts(name, seed=1):
+    from oracle import restate
+    return [(v, restate.resnet50_state(v, seed + i)) for i, v in enumerate(VARIANTS[name])]
+
+
+def build_net(name, device):
+    from pvr_habitat_b200.embeddings import EmbeddingNet
+    from pvr_habitat_b200.vision_models.moco import allow_random_init
+    with allow_random_init():
+        net = EmbeddingNet(name)
+    parts = net.embedding.models if hasattr(net.embedding, "models") else [net.embedding]
+    for m, (v, sd) in zip(parts, oracle_parts(name)):
+        m.load_state_dict(sd, strict=True)
+    net.invalidate()
+    return net
+
+
+def cpu_port_frames_per_s(name, n_frames, n_obs, threads):
+    """Oracle (CPU port of the reference path) on a bounded sample: returns (frames/s, seconds)."""
+    from oracle import restate
+    torch.set_num_threads(threads)
+    parts = oracle_parts(name)
+    obs = make_observations(n_obs, n_frames, 5)
+    restate.embed_observations(parts, obs[:2], batch_size=64)  # warm-up
+    t0 = time.perf_counter()
+    restate.embed_observations(parts, obs, batch_size=64)  # mini-batches of 64 like main_bc_1.py:130
+    dt = time.perf_counter() - t0
+    return n_obs * n_frames / dt, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, all host threads, same schema."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name, n_frames, _ = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    from oracle import restate
+    torch.set_num_threads(threads)
+    parts = oracle_parts(name)
+    per_step = 8  # observations per step: bounded so that K steps end within minutes
+    obs = make_observations(per_step, n_frames, 5)
+    for _ in range(max(1, min(args.warmup, 1))):
+        restate.embed_observations(parts, obs[:2], batch_size=64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        restate.embed_observations(parts, obs, batch_size=64)
+    dt = time.perf_counter() - t0
+    v = args.steps * per_step * n_frames / dt
+    line = {
+        "impl": "reference", "metric": "pvr_frames_per_sec_embedded", "value": v, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name} x {n_frames}-frame 224x224 uint8 observations (BASELINE configs[1])"
+                   if args.workload == "uber34x3" else f"{name} 224x224 uint8 frames",
+                   "obs_per_step": per_step, "frames_per_step": per_step * n_frames},
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x {per_step} observations x {n_frames} frames, torch CPU fp32, "
+                                   "oracle/restate.py (the reference is Python and is not present on the GPU box)"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="uber34x3", choices=list(WORKLOADS))
+    ap.add_argument("--obs-per-step", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    name, n_frames, obs_per_step = WORKLOADS[args.workload]
+    if args.obs_per_step:
+        obs_per_step = args.obs_per_step
+    frames_per_step = obs_per_step * n_frames
+    net = build_net(name, torch.device("cuda", local))
+    width = n_frames * net.out_size
+
+    # Inputs: a rotation of distinct batches larger than L2 in total (126 MB), so no step re-reads its input from L2.
+    bytes_per_batch = obs_per_step * 224 * 224 * 3 * n_frames
+    n_rot = max(2, -(-3 * 126 * 2 ** 20 // bytes_per_batch))
+    host = [torch.from_numpy(make_observations(obs_per_step, n_frames, 100 + rank * 16 + i)).pin_memory()
+            for i in range(min(n_rot, 4))]
+    while len(host) < n_rot:
+        host.append(host[len(host) % 4].clone().pin_memory())
+    dev = [h.cuda(non_blocking=True) for h in host]
+    out = torch.empty(obs_per_step, width, dtype=torch.float32, device="cuda")
+    out_host = torch.empty(obs_per_step, width, dtype=torch.float32).pin_memory()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- device-resident throughput
+    def step_resident(i):
+        net.embed(dev[i % n_rot], n_frames, out=out)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = timed(step_resident, args.steps, args.warmup)
+    clocks = sampler.stop() if sampler else None
+    value = world * frames_per_step * args.steps / (ms / 1e3)
+
+    # ---- end to end: pinned host -> H2D -> embed -> D2H, every step
+    def step_e2e(i):
+        d = host[i % n_rot].cuda(non_blocking=True)
+        net.embed(d, n_frames, out=out)
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the embeddings (numpy) every step
+
+    ms_e2e = timed(step_e2e, args.steps, 3)
+    e2e_value = world * frames_per_step * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel roofline (rank 0): CUDA events between ops on the launch stream
+    enc = net.encoder()
+    peaks = load_peaks()
+    conv_ms, conv_flops, other_ms = [], 0.0, []
+    reps = 5
+    for r in range(reps + 1):
+        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, 1, True)
+        op_ms = enc.forward_timed(out, net.out_size)
+        if r == 0:
+            continue  # warm
+        conv_ms.append(sum(t for t, m in zip(op_ms, enc.op_meta) if m["kind"] == 1))
+        other_ms.append(sum(t for t, m in zip(op_ms, enc.op_meta) if m["kind"] != 1))
+    conv_flops = sum(m["flops_per_image"] for m in enc.op_meta if m["kind"] == 1) * frames_per_step
+    n_conv = sum(1 for m in enc.op_meta if m["kind"] == 1)
+    conv_t = float(np.mean(conv_ms)) / 1e3
+    achieved = conv_flops / conv_t / 1e12
+    # preprocessing kernel timed alone (HBM bound)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(10):
+        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, 1, True)
+    e1.record()
+    torch.cuda.synchronize()
+    pre_ms = e0.elapsed_time(e1) / 10
+    pre_bytes = frames_per_step * (224 * 224 * 3 + 224 * 224 * 4 * 2)
+    roofline = {
+        "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % n_conv,
+        "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+        "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+        "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
+        "algorithmic_gflop_per_frame": conv_flops / frames_per_step / 1e9,
+        "conv_ms_per_step": conv_t * 1e3, "conv_share_of_step": conv_t * 1e3 / (ms / args.steps),
+        "other_ops_ms_per_step": float(np.mean(other_ms)),
+        "preprocess": {"bound": "hbm", "ms_per_step": pre_ms, "achieved": pre_bytes / (pre_ms / 1e3) / 1e9,
+                       "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                       "frac": pre_bytes / (pre_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                       "algorithmic_bytes_per_frame": 224 * 224 * 3 + 224 * 224 * 4 * 2},
+    }
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_obs = 24 if n_frames == 3 else 96
+        v, dt = cpu_port_frames_per_s(name, n_frames, n_obs, threads)
+        cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+                        "sample": f"{n_obs} observations x {n_frames} frames of the same workload, mini-batch 64, "
+                                  f"torch CPU fp32 oracle port, {dt:.1f} s"}
+
+    line = {
+        "metric": "pvr_frames_per_sec_embedded", "value": value, "unit": "frames/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": (f"{name}: ResNet-50 MoCo layer3+layer4 compressed taps (2 trunks), {n_frames}-frame "
+                         "224x224 uint8 observations, random-init weights (BASELINE configs[1])")
+            if args.workload == "uber34x3" else f"{name}: ResNet-50 conv5, 224x224 uint8 frames, random-init weights",
+            "obs_per_step_per_gpu": obs_per_step, "frames_per_step_per_gpu": frames_per_step,
+            "embedding_width": width, "sharding": "observations split over ranks, no data-path collective",
+            "l2": f"inputs rotate over {n_rot} distinct batches ({n_rot * bytes_per_batch / 2**20:.0f} MiB > 126 MB L2); "
+                  "activations (>1 GB/step) are rewritten every step",
+        },
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_per_batch,
+                "d2h_bytes_per_step": obs_per_step * width * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": args.steps * (1 + enc.n_ops),
+        "tflops_effective": value * GFLOP_PER_FRAME[name] / 1e3,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

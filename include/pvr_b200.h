@@ -99,6 +99,9 @@ int64_t pvr_encoder_workspace_bytes(const pvr_encoder* enc, int n_images);
 int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace, int64_t workspace_bytes, void** slot0);
 /* Run all ops for the bound batch. Embedding rows are written to emb[i*emb_ld + ...] (float32, device). */
 int pvr_encoder_forward(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream);
+/* Same, with a CUDA event between ops; synchronises at the end and writes the device time of each op (ms) to the
+ * host array op_ms[n_ops]. Used by bench.py for the per-kernel roofline numbers, not on the product path. */
+int pvr_encoder_forward_timed(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream, float* op_ms);
 /* Device address of a slot after bind (tests / per-layer parity). */
 void* pvr_encoder_slot_ptr(const pvr_encoder* enc, int slot);
 /* Number of kernel launches one forward issues (for bench.py's gpu_launches). */

@@ -1,0 +1,91 @@
+"""ORACLE (build container only) — import the UNMODIFIED reference from /root/reference.
+
+The reference needs gym / detectron2 / timm / habitat at import time (src/embeddings.py:2-3,
+src/vision_models/maskrcnn.py:2-20, src/vision_models/mae.py:20); none is installed and none is on the hot path, so
+they are replaced by inert stub modules. Checkpoint-backed encoders (src/embeddings.py:151-236) read hard-coded
+relative paths: `write_checkpoints` writes synthetic checkpoints under those names into a scratch directory and the
+constructors run from there, so no reference code is patched.
+This file is never imported on the GPU box (/root/reference does not exist there).
+"""
+import contextlib
+import os
+import sys
+import types
+
+REFERENCE = "/root/reference"
+
+
+class _Anything(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return type(name, (), {"__init__": lambda self, *a, **k: None})
+
+
+def install_stubs():
+    if REFERENCE not in sys.path:
+        sys.path.insert(0, REFERENCE)
+    if "gym" not in sys.modules:
+        gym = types.ModuleType("gym")
+
+        class _W(object):
+            def __init__(self, env=None):
+                self.env = env
+
+        gym.ObservationWrapper = gym.Wrapper = gym.Env = _W
+        spaces = types.ModuleType("gym.spaces")
+        box = types.ModuleType("gym.spaces.box")
+
+        class Box(object):
+            def __init__(self, low=None, high=None, shape=None, dtype=None):
+                self.low, self.high, self.shape, self.dtype = low, high, shape, dtype
+
+        box.Box = spaces.Box = Box
+        gym.spaces = spaces
+        spaces.box = box
+        sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.spaces.box": box})
+    for name in ("detectron2", "detectron2.layers", "detectron2.config", "detectron2.modeling",
+                 "detectron2.modeling.meta_arch", "detectron2.modeling.anchor_generator",
+                 "detectron2.modeling.backbone", "detectron2.modeling.backbone.resnet",
+                 "detectron2.modeling.box_regression", "detectron2.modeling.matcher", "detectron2.modeling.poolers",
+                 "detectron2.modeling.proposal_generator", "detectron2.modeling.roi_heads", "timm", "timm.models",
+                 "timm.models.vision_transformer"):
+        sys.modules.setdefault(name, _Anything(name))
+
+
+def reference_embeddings():
+    install_stubs()
+    import src.embeddings as E
+    return E
+
+
+def reference_models():
+    install_stubs()
+    import src.models as M
+    return M
+
+
+CHECKPOINT_FILES = {  # src/embeddings.py:151-236
+    "moco_aug": "moco_aug.pth.tar", "moco_aug_l4": "moco_aug_l4.pth", "moco_aug_l3": "moco_aug_l3.pth",
+    "moco_croponly": "moco_croponly.pth", "moco_croponly_l4": "moco_croponly_l4.pth",
+    "moco_croponly_l3": "moco_croponly_l3.pth",
+}
+
+
+def write_checkpoints(directory, states):
+    """states: {embedding_name: torchvision-named state_dict}. Keys get the MoCo `module.encoder_q.` prefix
+    (src/vision_models/moco.py:14-21)."""
+    import torch
+    for name, sd in states.items():
+        ck = {"state_dict": {"module.encoder_q." + k: v.clone() for k, v in sd.items()}}
+        torch.save(ck, os.path.join(directory, CHECKPOINT_FILES[name]))
+
+
+@contextlib.contextmanager
+def chdir(path):
+    old = os.getcwd()
+    os.chdir(path)
+    try:
+        yield
+    finally:
+        os.chdir(old)

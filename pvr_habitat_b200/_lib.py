@@ -40,6 +40,8 @@ _SIGNATURES = {
     "pvr_encoder_bind": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
                                         ctypes.POINTER(ctypes.c_void_p)]),
     "pvr_encoder_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "pvr_encoder_forward_timed": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                                 ctypes.POINTER(ctypes.c_float)]),
     "pvr_encoder_slot_ptr": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
     "pvr_encoder_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
     "pvr_encoder_destroy": (None, [ctypes.c_void_p]),

@@ -227,20 +227,12 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
   return PVR_OK;
 }
 
-extern "C" int pvr_encoder_forward(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream_) {
-  if (!enc || enc->n_images <= 0) {
-    pvr_set_error("pvr_encoder_forward: encoder is not bound");
-    return PVR_ERR_STATE;
-  }
-  if (!emb || emb_ld < enc->emb_width) {
-    pvr_set_error("pvr_encoder_forward: invalid embedding buffer");
-    return PVR_ERR_ARG;
-  }
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_t stream, cudaEvent_t* ev) {
   const int n = enc->n_images;
   for (size_t i = 0; i < enc->ops.size(); ++i) {
     const pvr_op& o = enc->ops[i];
     cudaError_t e = cudaSuccess;
+    if (ev) cudaEventRecord(ev[i], stream);
     switch (o.kind) {
       case PVR_OP_CONV: {
         const BoundConv& b = enc->bound[i];
@@ -267,7 +259,51 @@ extern "C" int pvr_encoder_forward(pvr_encoder* enc, float* emb, int64_t emb_ld,
       return PVR_ERR_CUDA;
     }
   }
+  if (ev) cudaEventRecord(ev[enc->ops.size()], stream);
   return PVR_OK;
+}
+
+static int encoder_check(pvr_encoder* enc, float* emb, int64_t emb_ld) {
+  if (!enc || enc->n_images <= 0) {
+    pvr_set_error("pvr_encoder_forward: encoder is not bound");
+    return PVR_ERR_STATE;
+  }
+  if (!emb || emb_ld < enc->emb_width) {
+    pvr_set_error("pvr_encoder_forward: invalid embedding buffer");
+    return PVR_ERR_ARG;
+  }
+  return PVR_OK;
+}
+
+extern "C" int pvr_encoder_forward(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream_) {
+  int rc = encoder_check(enc, emb, emb_ld);
+  if (rc != PVR_OK) return rc;
+  return encoder_run(enc, emb, emb_ld, static_cast<cudaStream_t>(stream_), nullptr);
+}
+
+extern "C" int pvr_encoder_forward_timed(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream_, float* op_ms) {
+  int rc = encoder_check(enc, emb, emb_ld);
+  if (rc != PVR_OK) return rc;
+  if (!op_ms) {
+    pvr_set_error("pvr_encoder_forward_timed: op_ms is null");
+    return PVR_ERR_ARG;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const size_t n = enc->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) cudaEventCreate(&e);
+  rc = encoder_run(enc, emb, emb_ld, stream, ev.data());
+  if (rc == PVR_OK) {
+    cudaError_t e = cudaEventSynchronize(ev[n]);
+    if (e != cudaSuccess) {
+      pvr_set_error("pvr_encoder_forward_timed: %s", cudaGetErrorString(e));
+      rc = PVR_ERR_CUDA;
+    } else {
+      for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]);
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
 }
 
 extern "C" void* pvr_encoder_slot_ptr(const pvr_encoder* enc, int slot) {

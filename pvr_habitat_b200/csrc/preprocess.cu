@@ -31,8 +31,9 @@ struct PreParams {
 };
 
 __device__ __forceinline__ void src_index(float scale, int dst, int size, int& i0, int& i1, float& l) {
-  // ATen area_pixel_compute_source_index(align_corners=false) + guard_index_and_lambda
-  float s = __fsub_rn(__fmul_rn(scale, (float)dst + 0.5f), 0.5f);
+  // ATen area_pixel_compute_source_index(align_corners=false) + guard_index_and_lambda. The x86 build of ATen
+  // contracts scale*(dst+0.5)-0.5 into one FMA (probed bit-exact, oracle/restate.py:_src_index).
+  float s = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);
   if (s < 0.f) s = 0.f;
   i0 = (int)s;
   if (i0 > size - 1) i0 = size - 1;
@@ -103,9 +104,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int ch = 3 * f + c;
-        const float top = __fadd_rn(__fmul_rn(hx, (float)q00[ch]), __fmul_rn(lx, (float)q01[ch]));
-        const float bot = __fadd_rn(__fmul_rn(hx, (float)q10[ch]), __fmul_rn(lx, (float)q11[ch]));
-        const float v = __fadd_rn(__fmul_rn(hy, top), __fmul_rn(ly, bot));
+        // ATen Interpolate<>::eval as compiled for x86: fma(t0, w0, round(t1 * w1)) per dimension
+        const float top = __fmaf_rn((float)q00[ch], hx, __fmul_rn((float)q01[ch], lx));
+        const float bot = __fmaf_rn((float)q10[ch], hx, __fmul_rn((float)q11[ch], lx));
+        const float v = __fmaf_rn(top, hy, __fmul_rn(bot, ly));
         int u = (int)rintf(v);  // half to even, as torch.round
         u = min(max(u, 0), 255);
         o[c] = lut[c * 256 + u];

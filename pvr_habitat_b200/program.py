@@ -87,7 +87,7 @@ class Program:
 
     # ---- ops
     def conv(self, in_slot, in_chw, w_packed, k_pad, c_out, r, s, stride, lower, out_hw, scale, bias, relu_n,
-             in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0):
+             in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0, flops=None):
         c_in, h_in, w_in = in_chw
         n_pad = w_packed.shape[0]
         p, q = out_hw
@@ -104,7 +104,8 @@ class Program:
                   out_pitch=out_pitch, res_pitch=0, out_coff=out_coff, res_coff=0, r=r, s=s,
                   stride_h=stride[0], stride_w=stride[1], lower_h=lower[0], lower_w=lower[1], relu_n=relu_n,
                   block_n=block_n, k_pad=k_pad, n_pad=n_pad, emb_offset=0,
-                  _weight=w_packed.contiguous(), _scale=sc, _bias=bi)
+                  _weight=w_packed.contiguous(), _scale=sc, _bias=bi,
+                  flops_per_image=int(flops if flops is not None else 2 * p * q * c_out * r * s * c_in))
         if res is not None:
             op.update(res_slot=res[0], res_pitch=res[1], res_coff=res[2])
         self.ops.append(op)
@@ -142,7 +143,7 @@ class Encoder:
         for i, d in enumerate(prog.ops):
             o = ops[i]
             for k, v in d.items():
-                if not k.startswith("_"):
+                if not k.startswith("_") and k != "flops_per_image":
                     setattr(o, k, int(v))
             for key, field in (("_weight", "weight"), ("_scale", "scale"), ("_bias", "bias"), ("_aux", "aux")):
                 if key in d:
@@ -186,6 +187,16 @@ class Encoder:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.pvr_encoder_forward(self.handle, emb.data_ptr(), emb_ld, _lib.current_stream_ptr()),
                        "pvr_encoder_forward")
+
+    def forward_timed(self, emb, emb_ld=None):
+        """Like forward, returns the per-op device time in ms (synchronises)."""
+        if emb_ld is None:
+            emb_ld = emb.stride(0)
+        ms = (ctypes.c_float * self.n_ops)()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.pvr_encoder_forward_timed(self.handle, emb.data_ptr(), emb_ld,
+                                                          _lib.current_stream_ptr(), ms), "pvr_encoder_forward_timed")
+        return list(ms)
 
     def slot_ptr(self, slot):
         return self.lib.pvr_encoder_slot_ptr(self.handle, slot)
@@ -278,7 +289,7 @@ def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
     scale, bias = fold_bn(sd, "bn1")
     p = (hw + 6 - 7) // 2 + 1
     stem = prog.conv(in_slot, (8, hw, hw // 2), pack_stem_weight(sd["conv1.weight"].float(), 64), 256, 64, 7, 4,
-                     (2, 1), (-3, -2), (p, p), scale, bias, 64)
+                     (2, 1), (-3, -2), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147)
     x, h, w = prog.maxpool(stem, 64, p, p)
     prog.release(stem)
     chw = (64, h, w)

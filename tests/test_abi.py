@@ -1,0 +1,53 @@
+"""The C-ABI library loads and exports every symbol include/pvr_b200.h declares (no compute calls: CPU only)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from pvr_habitat_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "pvr_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pvr_[a-z0-9_]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__
+    __graft_entry__.build()
+    return _lib.lib()
+
+
+def test_header_and_binding_agree():
+    assert header_symbols() == _lib.declared_symbols()
+
+
+def test_library_exports_every_declared_symbol(built):
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_symbols():
+        assert hasattr(raw, name), name
+
+
+def test_abi_version_and_error_string(built):
+    assert built.pvr_abi_version() == 1
+    assert isinstance(built.pvr_last_error(), bytes)
+
+
+def test_argument_errors_do_not_need_a_gpu(built):
+    rc = built.pvr_preprocess_u8(None, 1, 64, 64, 1, 256, 256, 16, 16, 224, None, None, None, 0, 0, None)
+    assert rc == -1 and b"invalid argument" in built.pvr_last_error()
+    h = ctypes.c_void_p()
+    assert built.pvr_encoder_create(None, 0, None, 0, 0, ctypes.byref(h)) == -1
+    assert built.pvr_encoder_workspace_bytes(None, 4) < 0
+    assert built.pvr_gemm_bf16(None, 0, None, 0, None, 0, None, None, None, 0, 1, 1, 64, 64, 0, None) == -1
+
+
+def test_op_struct_layout_matches_header():
+    """pvr_op: 26 int32 fields then 4 pointers (ctypes mirror of the C struct)."""
+    assert ctypes.sizeof(_lib.pvr_op) == 26 * 4 + 4 * 8
+    assert _lib.pvr_op.weight.offset == 104

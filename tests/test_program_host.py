@@ -1,0 +1,93 @@
+"""Host-side logic on CPU: the op program compiled from a state_dict computes the reference network (checked by
+interpreting the exact fields the CUDA library consumes), names / sizes / state_dict keys mirror the reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate
+from program_emulator import emulate
+from pvr_habitat_b200 import program as prg
+from pvr_habitat_b200.embeddings import EmbeddingNet, UberModel, _get_embedding, resize_geometry
+from pvr_habitat_b200.vision_models.moco import allow_random_init
+from pvr_habitat_b200.vision_models.resnet_params import ResNet50Params
+
+
+@pytest.mark.parametrize("variant,width", [("conv5", 2048), ("l4", 42 * 2 * 2), ("l3", 11 * 4 * 4)])
+def test_program_equals_oracle_network(variant, width):
+    sd = restate.resnet50_state(variant, 7)
+    sd = {k: (v.to(torch.bfloat16).float() if k.endswith("conv1.weight") or "conv" in k or "downsample.0.weight" in k
+              else v) for k, v in sd.items()}  # weights the program will round to bf16 anyway
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 64 * 4)
+    prog.emb_width = prg.add_resnet50(prog, sd, variant, s0, 0, hw=64)
+    assert prog.emb_width == width
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    x4 = torch.zeros(2, 64, 64, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    got = emulate(prog, x4, round_bf16=False)
+    ref = restate.resnet50_forward(sd, variant, x)
+    assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+
+
+def test_stem_packing_is_the_7x7_stride2_conv():
+    w = torch.randn(64, 3, 7, 7)
+    full = prg.pack_stem_weight(w, 64).float()
+    assert torch.all(full[:, 224:] == 0)  # taps 28..31 pad K to 256
+    packed = full[:, :224].reshape(64, 7, 4, 2, 4)
+    assert torch.all(packed[..., 3] == 0)  # padded channel
+    assert torch.all(packed[:, :, 0, 0, :] == 0)  # filter column -1 does not exist
+    for j in range(7):
+        sp, e = (j + 1) // 2, (j + 1) % 2
+        assert torch.equal(packed[:, :, sp, e, :3], w[:, :, :, j].permute(0, 2, 1).to(torch.bfloat16).float())
+
+
+def test_slot_planning_never_aliases_live_tensors():
+    sd = restate.resnet50_state("conv5", 3)
+    prog = prg.Program()
+    s0 = prog.new_slot(224 * 224 * 4)
+    prg.add_resnet50(prog, sd, "conv5", s0, 0)
+    for op in prog.ops:
+        if op["kind"] == 1:
+            assert op["out_slot"] != op["in_slot"] and op["out_slot"] != 0
+            if op["res_slot"] >= 0:
+                assert op["res_slot"] != op["in_slot"]
+    assert len(prog.ops) == 53 + 2  # 53 convs + maxpool + avgpool
+    assert len(prog.slot_elems) <= 6
+
+
+def test_names_sizes_and_state_dict_keys():
+    with allow_random_init():
+        for name, size, nkeys in (("moco_aug", 2048, 318), ("moco_aug_l4", 2058, 337), ("moco_aug_l3", 2156, 277),
+                                  ("moco_aug_uber_34", 4214, 0), ("moco_aug_uber_345", 6262, 0),
+                                  ("moco_croponly_places_uber_45", 2058 + 2048, 0), ("resnet50", 2048, 318),
+                                  ("resnet50_l3", 2156, 277)):
+            net = EmbeddingNet(name, disable_cuda=True)
+            assert net.out_size == size and tuple(net.in_shape) == (3, 224, 224)
+            assert len(net.state_dict()) == nkeys  # uber: reference quirk D8 (plain list -> empty state_dict)
+            assert all(k.startswith("embedding.") for k in net.state_dict())
+    with pytest.raises(NotImplementedError, match="Requested model not available."):
+        _get_embedding("no_such_model")
+
+
+def test_state_dict_interchanges_with_reference_key_names():
+    sd = restate.resnet50_state("l3", 5)
+    m = ResNet50Params("l3")
+    msg = m.load_state_dict(sd, strict=True)
+    assert not msg.missing_keys and not msg.unexpected_keys
+
+
+def test_missing_checkpoint_raises_like_reference():
+    with pytest.raises(FileNotFoundError):
+        EmbeddingNet("moco_aug", disable_cuda=True)
+
+
+def test_cpu_forward_fails_loudly():
+    with allow_random_init():
+        net = EmbeddingNet("moco_aug", disable_cuda=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(torch.zeros(1, 64, 64, 3, dtype=torch.uint8))
+
+
+def test_resize_geometry_matches_oracle():
+    for hw in ((64, 64), (224, 224), (96, 128), (480, 640), (640, 480), (100, 75)):
+        assert resize_geometry(*hw) == restate.resize_geometry(*hw)

@@ -48,9 +48,10 @@ int pick_block_n(int n_pad, long long m_tiles, int sms, int hint) {
 }
 
 struct BoundConv {
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to, tr;
   pvr::ConvGemmParams p;
   int block_n, a_mode;
+  bool epi_tma;
 };
 
 }  // namespace
@@ -221,6 +222,22 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       pvr_set_error("pvr_encoder_bind: op %zu: weight tensor map: %s", i, err);
       return PVR_ERR_CUDA;
     }
+    // Output / residual staged through shared memory + TMA when the channel count allows full 64-column sub-tiles.
+    b.epi_tma = (b.block_n >= 64 && o.c_out % 64 == 0);
+    b.to = b.ta;
+    b.tr = b.ta;
+    if (b.epi_tma) {
+      p.has_res = o.res_slot >= 0;
+      p.out_coff = o.out_coff;
+      p.res_coff = o.res_coff;
+      if (!pvr::make_tmap_2d(&b.to, enc->slot_ptr[o.out_slot], (uint64_t)o.out_pitch, (uint64_t)M,
+                             (uint64_t)o.out_pitch, 128, &err) ||
+          (p.has_res && !pvr::make_tmap_2d(&b.tr, enc->slot_ptr[o.res_slot], (uint64_t)o.res_pitch, (uint64_t)M,
+                                           (uint64_t)o.res_pitch, 128, &err))) {
+        pvr_set_error("pvr_encoder_bind: op %zu: output/residual tensor map: %s", i, err);
+        return PVR_ERR_CUDA;
+      }
+    }
   }
   enc->n_images = n_images;
   if (slot0) *slot0 = enc->slot_ptr[0];
@@ -236,7 +253,7 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
     switch (o.kind) {
       case PVR_OP_CONV: {
         const BoundConv& b = enc->bound[i];
-        e = pvr::launch_conv_gemm(b.block_n, b.a_mode, b.ta, b.tb, b.p, enc->sms, stream);
+        e = pvr::launch_conv_gemm(b.block_n, b.a_mode, b.epi_tma, b.ta, b.tb, b.to, b.tr, b.p, enc->sms, stream);
         break;
       }
       case PVR_OP_MAXPOOL:
@@ -343,14 +360,26 @@ extern "C" int pvr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t 
   p.res = static_cast<const __nv_bfloat16*>(res);
   p.scale = scale;
   p.bias = bias;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to, tr;
   const char* err = "";
   if (!pvr::make_tmap_2d(&ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 128, &err) ||
       !pvr::make_tmap_2d(&tb, b, (uint64_t)k, (uint64_t)n_pad, (uint64_t)ldb, (uint32_t)block_n, &err)) {
     pvr_set_error("pvr_gemm_bf16: %s", err);
     return PVR_ERR_CUDA;
   }
-  cudaError_t e = pvr::launch_conv_gemm(block_n, pvr::A_TILED, ta, tb, p, sms, static_cast<cudaStream_t>(stream));
+  const bool epi_tma = (block_n >= 64 && n % 64 == 0);
+  to = ta;
+  tr = ta;
+  if (epi_tma) {
+    p.has_res = res != nullptr;
+    if (!pvr::make_tmap_2d(&to, out, (uint64_t)n, (uint64_t)m, (uint64_t)ldo, 128, &err) ||
+        (res && !pvr::make_tmap_2d(&tr, res, (uint64_t)n, (uint64_t)m, (uint64_t)ldr, 128, &err))) {
+      pvr_set_error("pvr_gemm_bf16: %s", err);
+      return PVR_ERR_CUDA;
+    }
+  }
+  cudaError_t e = pvr::launch_conv_gemm(block_n, pvr::A_TILED, epi_tma, ta, tb, to, tr, p, sms,
+                                        static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) {
     pvr_set_error("pvr_gemm_bf16: %s", cudaGetErrorString(e));
     return PVR_ERR_CUDA;

@@ -6,14 +6,20 @@
 // The reference computes the same thing through torchvision's Bottleneck / BasicBlock (conv -> BN -> ReLU [-> add]),
 // src/vision_models/moco.py:11,34-50,78-94 on top of torchvision/models/resnet.py:89-166.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 224 threads, warp-specialised):
 //   warp 0 / lane 0 : TMA producer. A tile (128 pixels x 64 K) by im2col-mode TMA straight from the NHWC tensor
 //                     (padding = hardware zero fill, stride = traversal stride), W tile (BLOCK_N x 64) by tiled TMA.
 //   warp 1 / lane 0 : tcgen05.mma issuer, 128 x BLOCK_N x 16 per instruction, fp32 accumulators in TMEM,
 //                     two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
 //   warps 2..5      : epilogue. tcgen05.ld (one TMEM lane = one output pixel per thread), folded-BN scale/bias,
-//                     residual add, ReLU, bf16 round, 16-byte stores into the NHWC output.
-// Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator stage.
+//                     residual add, ReLU, bf16 round. EPI_TMA: results are staged in 128B-swizzled shared memory in
+//                     128 x 64 sub-tiles and written with TMA stores (full-line, clipped at the M tail); the residual
+//                     sub-tiles are prefetched by warp 6 with TMA loads (3 stages). The v0 epilogue issued 16-byte
+//                     global accesses at a 512-byte stride per thread and was L1TEX-bound (profiles/r01_*_v0).
+//                     !EPI_TMA: direct 16-byte stores, used for ragged channel counts (compression heads).
+//   warp 6 / lane 0 : residual prefetch (EPI_TMA).
+// Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator stage,
+//            res_full/res_empty per residual stage.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 
@@ -26,15 +32,22 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 224;  // 7 warps: TMA, MMA, 4 x epilogue, residual prefetch
+constexpr int EPI_N = 64;         // epilogue sub-tile: 64 bf16 columns = one 128-byte swizzle row
+constexpr int RES_STAGES = 3;
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr uint32_t EPI_TILE_BYTES = BLOCK_M * EPI_N * 2;   // 16 KiB
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool EPI_TMA>
 struct Cfg {
   static constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int STAGES = EPI_TMA ? (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6))
+                                        : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr uint32_t EPI_BYTES = EPI_TMA ? (RES_STAGES + 2) * EPI_TILE_BYTES : 0;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 64 / 128 / 256 / 512: all powers of two >= 32
-  static constexpr uint32_t SMEM_BYTES = 1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256;
+  static constexpr uint32_t SMEM_BYTES =
+      1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_BYTES + 256;
+  static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KiB shared memory of one CTA");
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -42,22 +55,59 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int BLOCK_N, int A_MODE>
+// scale/bias + (optional) residual + ReLU on 32 accumulator columns starting at column n.
+__device__ __forceinline__ void epilogue_math(const uint32_t* v, float* f, const ConvGemmParams& p, int n) {
+  const float4* sc4 = reinterpret_cast<const float4*>(p.scale + n);
+  const float4* bi4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 s4 = __ldg(sc4 + j);
+    const float4 b4 = __ldg(bi4 + j);
+    f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), s4.x, b4.x);
+    f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), s4.y, b4.y);
+    f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), s4.z, b4.z);
+    f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), s4.w, b4.w);
+  }
+}
+__device__ __forceinline__ void add_bf16x8(float* f, const uint4& rv) {
+  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    f[2 * t + 0] += __uint_as_float(w[t] << 16);
+    f[2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ void relu_cols(float* f, int n, int relu_n) {
+  if (n + 32 <= relu_n) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (n < relu_n) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = (n + j < relu_n) ? fmaxf(f[j], 0.0f) : f[j];
+  }
+}
+
+template <int BLOCK_N, int A_MODE, bool EPI_TMA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const ConvGemmParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, EPI_TMA>;
   constexpr int STAGES = C::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * C::B_STAGE_BYTES);
+  uint8_t* sRes = sB + STAGES * C::B_STAGE_BYTES;       // RES_STAGES x 16 KiB (EPI_TMA only)
+  uint8_t* sOut = sRes + RES_STAGES * EPI_TILE_BYTES;   // 2 x 16 KiB          (EPI_TMA only)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * C::B_STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;
+  uint64_t* res_empty_bar = res_full_bar + RES_STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + RES_STAGES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -66,6 +116,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (EPI_TMA) {
+      prefetch_tmap(&tmap_out);
+      if (p.has_res) prefetch_tmap(&tmap_res);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -73,6 +127,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 128);
+    }
+    for (int s = 0; s < RES_STAGES; ++s) {
+      mbar_init(&res_full_bar[s], 1);
+      mbar_init(&res_empty_bar[s], 128);
     }
     fence_barrier_init();
   }
@@ -86,7 +144,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
+    // ===================================================== TMA producer (A and W tiles)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -160,11 +218,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
+  } else if (warp == 6) {
+    // ===================================================== residual prefetch (TMA, 128 rows x 64 columns per sub-tile)
+    if (EPI_TMA && lane == 0 && p.has_res) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        for (int c = 0; c < BLOCK_N / EPI_N; ++c, ++it) {
+          const uint32_t s = it % RES_STAGES, ph = (it / RES_STAGES) & 1;
+          mbar_wait(&res_empty_bar[s], ph ^ 1);
+          mbar_expect_tx(&res_full_bar[s], EPI_TILE_BYTES);
+          tma_load_2d(&tmap_res, &res_full_bar[s], sRes + s * EPI_TILE_BYTES, p.res_coff + n_tile * BLOCK_N + c * EPI_N,
+                      m_tile * BLOCK_M);
+        }
+      }
+    }
   } else {
     // ===================================================== epilogue (warps 2..5; TMEM lane quarter = warp % 4)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    uint32_t acc = 0, acc_phase = 0;
+    const bool leader = (threadIdx.x == 64);  // warp 2, lane 0: issues the TMA stores
+    uint32_t acc = 0, acc_phase = 0, it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -173,75 +248,96 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
-      const bool row_ok = m < p.M;
-      __nv_bfloat16* out_row = p.out + m * p.ldo;
-      const __nv_bfloat16* res_row = p.res ? p.res + m * p.ldr : nullptr;
+      if (EPI_TMA) {
+        const uint32_t swz = (uint32_t)(row & 7);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated store path of the last chunk
-        tmem_ld_32x32b_x32(taddr + c * 32, v);
-        tmem_wait_ld();
-        const int n = n0 + c * 32;
-        if (!row_ok || n >= p.n_valid) continue;
-        float f[32];
-        const float4* sc4 = reinterpret_cast<const float4*>(p.scale + n);
-        const float4* bi4 = reinterpret_cast<const float4*>(p.bias + n);
+        for (int c = 0; c < BLOCK_N / EPI_N; ++c, ++it) {
+          const uint32_t s = it % RES_STAGES, ph = (it / RES_STAGES) & 1, ob = it & 1;
+          // the TMA store that last used staging buffer `ob` (two sub-tiles ago) must have drained it
+          if (leader) bulk_wait_group_read<1>();
+          named_bar_sync(1, 128);
+          if (p.has_res) mbar_wait(&res_full_bar[s], ph);
+          const uint32_t res_row = smem_u32(sRes + s * EPI_TILE_BYTES) + row * 128;
+          const uint32_t out_row = smem_u32(sOut + ob * EPI_TILE_BYTES) + row * 128;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 s4 = __ldg(sc4 + j);
-          const float4 b4 = __ldg(bi4 + j);
-          f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), s4.x, b4.x);
-          f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), s4.y, b4.y);
-          f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), s4.z, b4.z);
-          f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), s4.w, b4.w);
-        }
-        if (n + 32 <= p.n_valid) {
-          if (res_row) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(res_row + n);
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(taddr + c * EPI_N + h * 32, v);
+            tmem_wait_ld();
+            const int n = n0 + c * EPI_N + h * 32;
+            float f[32];
+            epilogue_math(v, f, p, n);
+            if (p.has_res) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) add_bf16x8(f + 8 * j, ld_shared_v4(res_row + (((h * 4 + j) ^ swz) << 4)));
+            }
+            relu_cols(f, n, p.relu_n);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const uint4 rv = __ldg(r4 + j);
-              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                f[8 * j + 2 * t + 0] += __uint_as_float(w[t] << 16);
-                f[8 * j + 2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
-              }
+              uint4 ov;
+              ov.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              ov.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              ov.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              ov.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              st_shared_v4(out_row + (((h * 4 + j) ^ swz) << 4), ov);
             }
           }
-          if (n + 32 <= p.relu_n) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          } else if (n < p.relu_n) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = (n + j < p.relu_n) ? fmaxf(f[j], 0.0f) : f[j];
-          }
-          uint4* o4 = reinterpret_cast<uint4*>(out_row + n);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 ov;
-            ov.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-            ov.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            ov.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            ov.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            o4[j] = ov;
-          }
-        } else {
-          const int nv = p.n_valid - n;  // ragged channel tail (compression heads)
-          for (int j = 0; j < nv; ++j) {
-            float x = f[j];
-            if (res_row) x += __bfloat162float(res_row[n + j]);
-            if (n + j < p.relu_n) x = fmaxf(x, 0.0f);
-            out_row[n + j] = __float2bfloat16_rn(x);
+          if (p.has_res) mbar_arrive(&res_empty_bar[s]);
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+          named_bar_sync(1, 128);
+          if (leader) {
+            tma_store_2d(&tmap_out, sOut + ob * EPI_TILE_BYTES, p.out_coff + n0 + c * EPI_N, m_tile * BLOCK_M);
+            bulk_commit_group();
           }
         }
+      } else {
+        const bool row_ok = m < p.M;
+        __nv_bfloat16* out_row = p.out + m * p.ldo;
+        const __nv_bfloat16* res_row = p.res ? p.res + m * p.ldr : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated store path
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_wait_ld();
+          const int n = n0 + c * 32;
+          if (!row_ok || n >= p.n_valid) continue;
+          float f[32];
+          epilogue_math(v, f, p, n);
+          if (n + 32 <= p.n_valid) {
+            if (res_row) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(res_row + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) add_bf16x8(f + 8 * j, __ldg(r4 + j));
+            }
+            relu_cols(f, n, p.relu_n);
+            uint4* o4 = reinterpret_cast<uint4*>(out_row + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 ov;
+              ov.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+              ov.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+              ov.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+              ov.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+              o4[j] = ov;
+            }
+          } else {
+            const int nv = p.n_valid - n;  // ragged channel tail (compression heads)
+            for (int j = 0; j < nv; ++j) {
+              float x = f[j];
+              if (res_row) x += __bfloat162float(res_row[n + j]);
+              if (n + j < p.relu_n) x = fmaxf(x, 0.0f);
+              out_row[n + j] = __float2bfloat16_rn(x);
+            }
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (EPI_TMA && leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires its smem
   }
 
   tc_fence_before();
@@ -252,42 +348,52 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int BLOCK_N, int A_MODE>
-cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p, int num_sms,
-                       cudaStream_t stream) {
-  auto kern = conv_gemm_kernel<BLOCK_N, A_MODE>;
+template <int BLOCK_N, int A_MODE, bool EPI_TMA>
+cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                       const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = conv_gemm_kernel<BLOCK_N, A_MODE, EPI_TMA>;
+  using C = Cfg<BLOCK_N, EPI_TMA>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, stream>>>(ta, tb, p);
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, p);
   return cudaGetLastError();
 }
 
-template <int BLOCK_N>
-cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb, const ConvGemmParams& p,
-                        int num_sms, cudaStream_t stream) {
+template <int BLOCK_N, bool EPI_TMA>
+cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
+                        const CUtensorMap& tr, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   switch (a_mode) {
-    case A_TILED: return launch_one<BLOCK_N, A_TILED>(ta, tb, p, num_sms, stream);
-    case A_IM2COL64: return launch_one<BLOCK_N, A_IM2COL64>(ta, tb, p, num_sms, stream);
-    case A_IM2COL8: return launch_one<BLOCK_N, A_IM2COL8>(ta, tb, p, num_sms, stream);
+    case A_TILED: return launch_one<BLOCK_N, A_TILED, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
+    case A_IM2COL64: return launch_one<BLOCK_N, A_IM2COL64, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
+    case A_IM2COL8: return launch_one<BLOCK_N, A_IM2COL8, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
 
 }  // namespace
 
-cudaError_t launch_conv_gemm(int block_n, int a_mode, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
+cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtensorMap& tmap_a,
+                             const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  if (epi_tma) {
+    switch (block_n) {
+      case 64: return launch_mode<64, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      case 128: return launch_mode<128, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      case 256: return launch_mode<256, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   switch (block_n) {
-    case 32: return launch_mode<32>(a_mode, tmap_a, tmap_b, p, num_sms, stream);
-    case 64: return launch_mode<64>(a_mode, tmap_a, tmap_b, p, num_sms, stream);
-    case 128: return launch_mode<128>(a_mode, tmap_a, tmap_b, p, num_sms, stream);
-    case 256: return launch_mode<256>(a_mode, tmap_a, tmap_b, p, num_sms, stream);
+    case 32: return launch_mode<32, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+    case 64: return launch_mode<64, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+    case 128: return launch_mode<128, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+    case 256: return launch_mode<256, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -27,6 +27,8 @@ struct ConvGemmParams {
   int lower_w, lower_h;
   int n_valid;       // real output channels (columns >= n_valid are not stored)
   int relu_n;        // ReLU is applied to output columns < relu_n (0: none, >= n_valid: all)
+  int has_res;       // residual present (EPI_TMA path reads it through tmap_res)
+  int out_coff, res_coff;  // channel offsets of the output / residual tile inside their pixel rows (EPI_TMA)
   long long ldo, ldr;  // output / residual row pitch in elements
   __nv_bfloat16* out;
   const __nv_bfloat16* res;  // may be null
@@ -35,7 +37,10 @@ struct ConvGemmParams {
 };
 
 // Launch on `stream`; block_n in {32, 64, 128, 256}. Returns cudaError_t of the launch.
-cudaError_t launch_conv_gemm(int block_n, int a_mode, const CUtensorMap& tmap_a, const CUtensorMap& tmap_b,
+// epi_tma: stage the output through shared memory + TMA store (needs n_valid % 64 == 0, block_n >= 64); tmap_out /
+// tmap_res are (pitch x M) bf16 maps with a (64 x 128) box over the output / residual pixel rows.
+cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtensorMap& tmap_a,
+                             const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const ConvGemmParams& p, int num_sms, cudaStream_t stream);
 
 // Tensor-map builders (driver entry points resolved through cudaGetDriverEntryPoint; no -lcuda needed).

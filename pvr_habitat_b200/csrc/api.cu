@@ -37,13 +37,14 @@ int device_sm_count() {
   return sms;
 }
 
-int pick_block_n(int n_pad, long long m_tiles, int sms, int hint) {
+int pick_block_n(int n_pad, long long m_tiles, int sms, int hint, bool has_res) {
   if (hint) return hint;
   if (n_pad % 64) return 32;
-  // Largest tile that still gives every SM work; wide tiles amortise the A-operand traffic.
+  // Largest tile that still gives every SM work; wide tiles amortise the A-operand traffic. Residual layers stay at
+  // N <= 128: their epilogue needs 3 in-flight buffers per group (residual prefetch) and the smem for it.
   const int cand[3] = {256, 128, 64};
   for (int bn : cand)
-    if (n_pad % bn == 0 && m_tiles * (n_pad / bn) >= sms) return bn;
+    if (n_pad % bn == 0 && m_tiles * (n_pad / bn) >= sms && !(has_res && bn == 256)) return bn;
   return 64;
 }
 
@@ -156,7 +157,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     p.P = o.h_out;
     p.Q = o.w_out;
     p.num_m_tiles = (int)((M + 127) / 128);
-    b.block_n = pick_block_n(o.n_pad, p.num_m_tiles, enc->sms, o.block_n);
+    b.block_n = pick_block_n(o.n_pad, p.num_m_tiles, enc->sms, o.block_n, o.res_slot >= 0);
     if (o.n_pad % b.block_n) {
       pvr_set_error("pvr_encoder_bind: op %zu: n_pad %d not a multiple of the N tile %d", i, o.n_pad, b.block_n);
       return PVR_ERR_ARG;
@@ -349,7 +350,7 @@ extern "C" int pvr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t 
   memset(&p, 0, sizeof(p));
   p.M = m;
   p.num_m_tiles = (m + 127) / 128;
-  const int block_n = pick_block_n(n_pad, p.num_m_tiles, sms, 0);
+  const int block_n = pick_block_n(n_pad, p.num_m_tiles, sms, 0, res != nullptr);
   p.num_n_tiles = n_pad / block_n;
   p.num_k_chunks = k / 64;
   p.n_valid = n;

@@ -6,20 +6,21 @@
 // The reference computes the same thing through torchvision's Bottleneck / BasicBlock (conv -> BN -> ReLU [-> add]),
 // src/vision_models/moco.py:11,34-50,78-94 on top of torchvision/models/resnet.py:89-166.
 //
-// Structure (one persistent CTA per SM, 224 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 352 threads, warp-specialised):
 //   warp 0 / lane 0 : TMA producer. A tile (128 pixels x 64 K) by im2col-mode TMA straight from the NHWC tensor
 //                     (padding = hardware zero fill, stride = traversal stride), W tile (BLOCK_N x 64) by tiled TMA.
 //   warp 1 / lane 0 : tcgen05.mma issuer, 128 x BLOCK_N x 16 per instruction, fp32 accumulators in TMEM,
 //                     two accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1.
-//   warps 2..5      : epilogue. tcgen05.ld (one TMEM lane = one output pixel per thread), folded-BN scale/bias,
-//                     residual add, ReLU, bf16 round. EPI_TMA: results are staged in 128B-swizzled shared memory in
-//                     128 x 64 sub-tiles and written with TMA stores (full-line, clipped at the M tail); the residual
-//                     sub-tiles are prefetched by warp 6 with TMA loads (3 stages). The v0 epilogue issued 16-byte
-//                     global accesses at a 512-byte stride per thread and was L1TEX-bound (profiles/r01_*_v0).
-//                     !EPI_TMA: direct 16-byte stores, used for ragged channel counts (compression heads).
-//   warp 6 / lane 0 : residual prefetch (EPI_TMA).
+//   warps 2..9      : epilogue, two groups of 4 warps that take alternate 128 x 64 sub-tiles. tcgen05.ld (one TMEM
+//                     lane = one output pixel per thread), folded-BN scale/bias (staged in smem), residual add, ReLU,
+//                     bf16 round. EPI_TMA: the result overwrites the residual in a 128B-swizzled 16 KiB shared-memory
+//                     buffer and leaves through a TMA store (full lines, clipped at the M tail). The v0 epilogue
+//                     issued 16-byte global accesses at a 512-byte stride per thread and was L1TEX-bound
+//                     (profiles/r01_*_v0). !EPI_TMA: direct stores for ragged channel counts (compression heads).
+//   warp 10 / lane 0: epilogue-buffer manager: recycles the buffers in sub-tile order and prefetches the residual
+//                     sub-tile into them with TMA loads.
 // Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator stage,
-//            res_full/res_empty per residual stage.
+//            eb_full/eb_empty per epilogue buffer.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 
@@ -32,18 +33,21 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 224;  // 7 warps: TMA, MMA, 4 x epilogue, residual prefetch
-constexpr int EPI_N = 64;         // epilogue sub-tile: 64 bf16 columns = one 128-byte swizzle row
-constexpr int RES_STAGES = 3;
+// 11 warps: 0 = TMA producer, 1 = MMA issuer, 2..9 = two epilogue groups of 4 warps, 10 = epilogue-buffer manager
+constexpr int NUM_THREADS = 352;
+constexpr int EPI_N = 64;                                  // epilogue sub-tile: 64 bf16 columns = one 128-byte row
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr uint32_t EPI_TILE_BYTES = BLOCK_M * EPI_N * 2;   // 16 KiB
 
 template <int BLOCK_N, bool EPI_TMA>
 struct Cfg {
   static constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGES = EPI_TMA ? (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 6))
+  static constexpr int STAGES = EPI_TMA ? (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5))
                                         : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
-  static constexpr uint32_t EPI_BYTES = EPI_TMA ? (RES_STAGES + 2) * EPI_TILE_BYTES : 0;
+  // epilogue buffers (residual in -> result out, in place), handed out in sub-tile order: 4 at N=256 (residual layers
+  // use N<=128), 5 at N=128, 6 at N=64 — what fits beside the A/W stages in 227 KiB
+  static constexpr int NB = EPI_TMA ? (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 5 : 6)) : 0;
+  static constexpr uint32_t EPI_BYTES = NB * EPI_TILE_BYTES + (EPI_TMA ? 2048 : 0);  // + scale/bias staging
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 64 / 128 / 256 / 512: all powers of two >= 32
   static constexpr uint32_t SMEM_BYTES =
       1024 /*align slack*/ + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + EPI_BYTES + 256;
@@ -55,7 +59,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// scale/bias + (optional) residual + ReLU on 32 accumulator columns starting at column n.
+// scale/bias (global, uniform addresses) on 32 accumulator columns starting at column n.
 __device__ __forceinline__ void epilogue_math(const uint32_t* v, float* f, const ConvGemmParams& p, int n) {
   const float4* sc4 = reinterpret_cast<const float4*>(p.scale + n);
   const float4* bi4 = reinterpret_cast<const float4*>(p.bias + n);
@@ -94,20 +98,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const ConvGemmParams p) {
   using C = Cfg<BLOCK_N, EPI_TMA>;
   constexpr int STAGES = C::STAGES;
+  constexpr int NB = C::NB > 0 ? C::NB : 1;
+  constexpr int SUBS = BLOCK_N / EPI_N > 0 ? BLOCK_N / EPI_N : 1;  // epilogue sub-tiles per tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* sRes = sB + STAGES * C::B_STAGE_BYTES;       // RES_STAGES x 16 KiB (EPI_TMA only)
-  uint8_t* sOut = sRes + RES_STAGES * EPI_TILE_BYTES;   // 2 x 16 KiB          (EPI_TMA only)
+  uint8_t* sEB = sB + STAGES * C::B_STAGE_BYTES;                      // NB x 16 KiB epilogue buffers
+  float* sSB = reinterpret_cast<float*>(sEB + C::NB * EPI_TILE_BYTES);  // [group][2][scale 64 | bias 64]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + STAGES * C::B_STAGE_BYTES + C::EPI_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* res_full_bar = tmem_empty_bar + 2;
-  uint64_t* res_empty_bar = res_full_bar + RES_STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_empty_bar + RES_STAGES);
+  uint64_t* eb_full_bar = tmem_empty_bar + 2;
+  uint64_t* eb_empty_bar = eb_full_bar + NB;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(eb_empty_bar + NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,11 +132,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], 128);
+      mbar_init(&tmem_empty_bar[s], EPI_TMA ? 256 : 128);
     }
-    for (int s = 0; s < RES_STAGES; ++s) {
-      mbar_init(&res_full_bar[s], 1);
-      mbar_init(&res_empty_bar[s], 128);
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&eb_full_bar[s], 1);
+      mbar_init(&eb_empty_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -218,79 +224,124 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp == 6) {
-    // ===================================================== residual prefetch (TMA, 128 rows x 64 columns per sub-tile)
-    if (EPI_TMA && lane == 0 && p.has_res) {
-      uint32_t it = 0;
+  } else if (warp == 10) {
+    // ===================================================== epilogue-buffer manager: hands out the 16 KiB buffers in
+    // sub-tile order, pre-filled with the residual sub-tile by TMA when the layer has one.
+    if (EPI_TMA && lane == 0) {
+      uint32_t q = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.num_n_tiles;
         const int n_tile = tile - m_tile * p.num_n_tiles;
-        for (int c = 0; c < BLOCK_N / EPI_N; ++c, ++it) {
-          const uint32_t s = it % RES_STAGES, ph = (it / RES_STAGES) & 1;
-          mbar_wait(&res_empty_bar[s], ph ^ 1);
-          mbar_expect_tx(&res_full_bar[s], EPI_TILE_BYTES);
-          tma_load_2d(&tmap_res, &res_full_bar[s], sRes + s * EPI_TILE_BYTES, p.res_coff + n_tile * BLOCK_N + c * EPI_N,
-                      m_tile * BLOCK_M);
+        for (int c = 0; c < SUBS; ++c, ++q) {
+          const uint32_t s = q % NB, ph = (q / NB) & 1;
+          mbar_wait(&eb_empty_bar[s], ph ^ 1);
+          if (p.has_res) {
+            mbar_expect_tx(&eb_full_bar[s], EPI_TILE_BYTES);
+            tma_load_2d(&tmap_res, &eb_full_bar[s], sEB + s * EPI_TILE_BYTES,
+                        p.res_coff + n_tile * BLOCK_N + c * EPI_N, m_tile * BLOCK_M);
+          } else {
+            mbar_arrive(&eb_full_bar[s]);
+          }
         }
       }
     }
   } else {
-    // ===================================================== epilogue (warps 2..5; TMEM lane quarter = warp % 4)
+    // ===================================================== epilogue (warps 2..9; TMEM lane quarter = warp % 4)
+    const int group = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const bool leader = (threadIdx.x == 64);  // warp 2, lane 0: issues the TMA stores
-    uint32_t acc = 0, acc_phase = 0, it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles;
-      const int n_tile = tile - m_tile * p.num_n_tiles;
-      const long long m = (long long)m_tile * BLOCK_M + row;
-      const int n0 = n_tile * BLOCK_N;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
-      if (EPI_TMA) {
-        const uint32_t swz = (uint32_t)(row & 7);
+    const int gtid = (warp - 2 - group * 4) * 32 + lane;  // 0..127 inside the group
+    uint32_t acc = 0, acc_phase = 0;
+    if (EPI_TMA) {
+      const bool leader = (gtid == 0);
+      const uint32_t swz = (uint32_t)(row & 7);
+      float* sb = sSB + group * 256;  // two 128-float buffers: scale[64] | bias[64]
+      auto stage_scale_bias = [&](uint32_t qq, uint32_t buf) {
+        const int t_it = qq / SUBS, c = qq - t_it * SUBS;
+        const long long tile = (long long)blockIdx.x + (long long)t_it * gridDim.x;
+        if (tile < num_tiles) {
+          const int n = (int)(tile % p.num_n_tiles) * BLOCK_N + c * EPI_N;
+          sb[buf * 128 + gtid] = gtid < 64 ? __ldg(p.scale + n + gtid) : __ldg(p.bias + n + gtid - 64);
+        }
+      };
+      uint32_t q = 0, j = 0, prev_s = 0;
+      stage_scale_bias(group, 0);
+      named_bar_sync(1 + group, 128);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int n0 = n_tile * BLOCK_N;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / EPI_N; ++c, ++it) {
-          const uint32_t s = it % RES_STAGES, ph = (it / RES_STAGES) & 1, ob = it & 1;
-          // the TMA store that last used staging buffer `ob` (two sub-tiles ago) must have drained it
-          if (leader) bulk_wait_group_read<1>();
-          named_bar_sync(1, 128);
-          if (p.has_res) mbar_wait(&res_full_bar[s], ph);
-          const uint32_t res_row = smem_u32(sRes + s * EPI_TILE_BYTES) + row * 128;
-          const uint32_t out_row = smem_u32(sOut + ob * EPI_TILE_BYTES) + row * 128;
+        for (int c = 0; c < SUBS; ++c, ++q) {
+          if ((q & 1) != (uint32_t)group) continue;
+          const uint32_t s = q % NB, ph = (q / NB) & 1;
+          uint32_t v[64];
+          tmem_ld_32x32b_x32(taddr + c * EPI_N, v);
+          tmem_ld_32x32b_x32(taddr + c * EPI_N + 32, v + 32);
+          stage_scale_bias(q + 2, (j + 1) & 1);  // next sub-tile of this group; published by this iteration's barrier
+          mbar_wait(&eb_full_bar[s], ph);
+          tmem_wait_ld();
+          const uint32_t eb_row = smem_u32(sEB + s * EPI_TILE_BYTES) + row * 128;
+          const uint32_t sb_addr = smem_u32(sb + (j & 1) * 128);
+          const int n = n0 + c * EPI_N;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld_32x32b_x32(taddr + c * EPI_N + h * 32, v);
-            tmem_wait_ld();
-            const int n = n0 + c * EPI_N + h * 32;
             float f[32];
-            epilogue_math(v, f, p, n);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const uint4 s4 = ld_shared_v4(sb_addr + (h * 8 + jj) * 16);
+              const uint4 b4 = ld_shared_v4(sb_addr + 256 + (h * 8 + jj) * 16);
+              f[4 * jj + 0] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 0]), __uint_as_float(s4.x), __uint_as_float(b4.x));
+              f[4 * jj + 1] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 1]), __uint_as_float(s4.y), __uint_as_float(b4.y));
+              f[4 * jj + 2] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 2]), __uint_as_float(s4.z), __uint_as_float(b4.z));
+              f[4 * jj + 3] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 3]), __uint_as_float(s4.w), __uint_as_float(b4.w));
+            }
             if (p.has_res) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) add_bf16x8(f + 8 * j, ld_shared_v4(res_row + (((h * 4 + j) ^ swz) << 4)));
+              for (int jj = 0; jj < 4; ++jj)
+                add_bf16x8(f + 8 * jj, ld_shared_v4(eb_row + (((h * 4 + jj) ^ swz) << 4)));
             }
-            relu_cols(f, n, p.relu_n);
+            relu_cols(f, n + h * 32, p.relu_n);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int jj = 0; jj < 4; ++jj) {
               uint4 ov;
-              ov.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              ov.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              ov.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              ov.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              st_shared_v4(out_row + (((h * 4 + j) ^ swz) << 4), ov);
+              ov.x = pack_bf16x2(f[8 * jj + 0], f[8 * jj + 1]);
+              ov.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
+              ov.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
+              ov.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
+              st_shared_v4(eb_row + (((h * 4 + jj) ^ swz) << 4), ov);
             }
           }
-          if (p.has_res) mbar_arrive(&res_empty_bar[s]);
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-          named_bar_sync(1, 128);
+          named_bar_sync(1 + group, 128);
           if (leader) {
-            tma_store_2d(&tmap_out, sOut + ob * EPI_TILE_BYTES, p.out_coff + n0 + c * EPI_N, m_tile * BLOCK_M);
+            tma_store_2d(&tmap_out, sEB + s * EPI_TILE_BYTES, p.out_coff + n, m_tile * BLOCK_M);
             bulk_commit_group();
+            if (j > 0) {  // the previous store of this group has drained its buffer: hand it back to the manager
+              bulk_wait_group_read<1>();
+              mbar_arrive(&eb_empty_bar[prev_s]);
+            }
           }
+          prev_s = s;
+          ++j;
         }
-      } else {
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires its smem
+    } else if (group == 0) {
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const long long m = (long long)m_tile * BLOCK_M + row;
+        const int n0 = n_tile * BLOCK_N;
+        mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + acc * BLOCK_N + ((uint32_t)(quarter * 32) << 16);
         const bool row_ok = m < p.M;
         __nv_bfloat16* out_row = p.out + m * p.ldo;
         const __nv_bfloat16* res_row = p.res ? p.res + m * p.ldr : nullptr;
@@ -308,36 +359,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (res_row) {
               const uint4* r4 = reinterpret_cast<const uint4*>(res_row + n);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) add_bf16x8(f + 8 * j, __ldg(r4 + j));
+              for (int jj = 0; jj < 4; ++jj) add_bf16x8(f + 8 * jj, __ldg(r4 + jj));
             }
             relu_cols(f, n, p.relu_n);
             uint4* o4 = reinterpret_cast<uint4*>(out_row + n);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int jj = 0; jj < 4; ++jj) {
               uint4 ov;
-              ov.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-              ov.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-              ov.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-              ov.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-              o4[j] = ov;
+              ov.x = pack_bf16x2(f[8 * jj + 0], f[8 * jj + 1]);
+              ov.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
+              ov.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
+              ov.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
+              o4[jj] = ov;
             }
           } else {
             const int nv = p.n_valid - n;  // ragged channel tail (compression heads)
-            for (int j = 0; j < nv; ++j) {
-              float x = f[j];
-              if (res_row) x += __bfloat162float(res_row[n + j]);
-              if (n + j < p.relu_n) x = fmaxf(x, 0.0f);
-              out_row[n + j] = __float2bfloat16_rn(x);
+            for (int jj = 0; jj < nv; ++jj) {
+              float x = f[jj];
+              if (res_row) x += __bfloat162float(res_row[n + jj]);
+              if (n + jj < p.relu_n) x = fmaxf(x, 0.0f);
+              out_row[n + jj] = __float2bfloat16_rn(x);
             }
           }
         }
         __syncwarp();
+        tc_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      tc_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (EPI_TMA && leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires its smem
   }
 
   tc_fence_before();

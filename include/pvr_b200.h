@@ -40,6 +40,9 @@ int pvr_abi_version(void);
  *          i*n_frames + f (so that an (N, n_frames*O) embedding row is contiguous):
  *          PVR_FMT_NCHW_F32       (n_frames*N, 3, crop, crop) float32 — bit-exact with the reference transforms
  *          PVR_FMT_NHWC4_BF16     (n_frames*N, crop, crop, 4) bf16, channel 3 = 0 — round-to-nearest of the above
+ *          PVR_FMT_STEM_BF16      (n_frames*N, crop, crop/2, 8, 4) bf16: for output column q of the 7x7/2 stem the
+ *                                 8 input columns 2q-3..2q+4 (zeros outside the image) x 4 channels = 64 B, so the
+ *                                 stem is a 7x1-tap implicit GEMM fed by 64-byte TMA rows
  *   rh,rw: size after Resize (short side -> 256: rh = 256, rw = int(256*W/H) for H <= W), bilinear,
  *          align_corners=False, no antialias, rounded half-to-even back to uint8 (torchvision semantics)
  *   top,left: CenterCrop offsets inside the resized image; crop = 224
@@ -47,6 +50,7 @@ int pvr_abi_version(void);
  */
 #define PVR_FMT_NCHW_F32 0
 #define PVR_FMT_NHWC4_BF16 1
+#define PVR_FMT_STEM_BF16 2
 int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int rh, int rw, int top, int left,
                       int crop, const float* mean, const float* stdv, void* out, int out_fmt, int sample_major,
                       void* stream);

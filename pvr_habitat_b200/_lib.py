@@ -7,6 +7,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpvr_b200.so")
 
 PVR_FMT_NCHW_F32 = 0
 PVR_FMT_NHWC4_BF16 = 1
+PVR_FMT_STEM_BF16 = 2
 PVR_OP_CONV, PVR_OP_MAXPOOL, PVR_OP_AVGPOOL, PVR_OP_HEAD = 1, 2, 3, 4
 
 

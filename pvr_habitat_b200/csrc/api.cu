@@ -87,8 +87,8 @@ extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* 
         pvr_set_error("pvr_encoder_create: op %d has an invalid conv description", i);
         return PVR_ERR_ARG;
       }
-      if (!(o.c_in == 8 || o.c_in % 64 == 0)) {
-        pvr_set_error("pvr_encoder_create: op %d: c_in must be 8 or a multiple of 64 (got %d)", i, o.c_in);
+      if (!(o.c_in == 8 || o.c_in == 32 || o.c_in % 64 == 0)) {
+        pvr_set_error("pvr_encoder_create: op %d: c_in must be 8, 32 or a multiple of 64 (got %d)", i, o.c_in);
         return PVR_ERR_ARG;
       }
     } else if (o.kind != PVR_OP_MAXPOOL && o.kind != PVR_OP_AVGPOOL && o.kind != PVR_OP_HEAD) {
@@ -202,7 +202,15 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
           return PVR_ERR_ARG;
         }
         ok = pvr::make_tmap_im2col(&b.ta, in, 8, o.in_pitch, o.w_in, o.h_in, n_images, o.lower_w, o.lower_h, upper_w,
-                                   upper_h, o.stride_w, o.stride_h, 8, 128, false, &err);
+                                   upper_h, o.stride_w, o.stride_h, 8, 128, 0, &err);
+      } else if (o.c_in == 32) {
+        b.a_mode = pvr::A_IM2COL32;
+        if (o.k_pad < o.r * o.s * 32) {
+          pvr_set_error("pvr_encoder_bind: op %zu: k_pad too small", i);
+          return PVR_ERR_ARG;
+        }
+        ok = pvr::make_tmap_im2col(&b.ta, in, 32, o.in_pitch, o.w_in, o.h_in, n_images, o.lower_w, o.lower_h, upper_w,
+                                   upper_h, o.stride_w, o.stride_h, 32, 128, 64, &err);
       } else {
         b.a_mode = pvr::A_IM2COL64;
         p.cin_chunks = o.c_in / 64;
@@ -211,7 +219,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
           return PVR_ERR_ARG;
         }
         ok = pvr::make_tmap_im2col(&b.ta, in, o.c_in, o.in_pitch, o.w_in, o.h_in, n_images, o.lower_w, o.lower_h,
-                                   upper_w, upper_h, o.stride_w, o.stride_h, 64, 128, true, &err);
+                                   upper_w, upper_h, o.stride_w, o.stride_h, 64, 128, 128, &err);
       }
     }
     if (!ok) {

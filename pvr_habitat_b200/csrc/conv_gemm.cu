@@ -181,6 +181,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const int r = tap / p.S;
             const int s = tap - r * p.S;
             tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst, c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+          } else if (A_MODE == A_IM2COL32) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              int tap = kc * 2 + j;
+              if (tap >= p.taps) tap = 0;  // padded K: finite data against zero weights
+              const int r = tap / p.S;
+              const int s = tap - r * p.S;
+              tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst + j * 8192, 0, w0, h0, img, (uint16_t)s,
+                                 (uint16_t)r);
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -212,8 +222,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t b_base = smem_u32(sB + stage * C::B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = (A_MODE == A_IM2COL8) ? umma_desc_nosw(a_base + k * 4096, 2048, 128)
-                                                          : umma_desc_sw128(a_base + k * (UMMA_K * 2));
+            const uint64_t adesc =
+                (A_MODE == A_IM2COL8)    ? umma_desc_nosw(a_base + k * 4096, 2048, 128)
+                : (A_MODE == A_IM2COL32) ? umma_desc_sw64(a_base + (k >> 1) * 8192 + (k & 1) * (UMMA_K * 2))
+                                         : umma_desc_sw128(a_base + k * (UMMA_K * 2));
             const uint64_t bdesc = umma_desc_sw128(b_base + k * (UMMA_K * 2));
             umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
           }
@@ -422,6 +434,7 @@ cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb
     case A_TILED: return launch_one<BLOCK_N, A_TILED, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
     case A_IM2COL64: return launch_one<BLOCK_N, A_IM2COL64, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
     case A_IM2COL8: return launch_one<BLOCK_N, A_IM2COL8, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
+    case A_IM2COL32: return launch_one<BLOCK_N, A_IM2COL32, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -486,7 +499,7 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows,
 
 bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int lower_w,
                       int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int channels_per_pixel,
-                      int pixels_per_column, bool swizzle128, const char** err) {
+                      int pixels_per_column, int swizzle_bytes, const char** err) {
   static EncodeIm2colFn fn = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));
   if (!fn) { *err = "cuTensorMapEncodeIm2col not available"; return false; }
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
@@ -496,7 +509,10 @@ bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int 
   cuuint32_t estr[4] = {1, (cuuint32_t)stride_w, (cuuint32_t)stride_h, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower, upper,
                   (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels_per_column, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 128  ? CU_TENSOR_MAP_SWIZZLE_128B
+                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                        : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeIm2col failed"; return false; }
   // Driver <= 13.1 sets a descriptor bit that mis-handles im2col tensors smaller than 128 KiB; clear it.

@@ -11,7 +11,9 @@ namespace pvr {
 enum AMode : int {
   A_TILED = 0,     // plain (M x K) row-major matrix: 2-D tiled TMA, 128B swizzle (1x1 stride-1 convs, GEMMs)
   A_IM2COL64 = 1,  // NHWC tensor, C_in % 64 == 0: one im2col TMA (64 channels x 128 pixels) per K chunk, 128B swizzle
-  A_IM2COL8 = 2,   // NHWC tensor with 8-element pixels (stem): 8 im2col TMAs (8 ch x 128 px) per K chunk, no swizzle
+  A_IM2COL8 = 2,   // NHWC tensor with 8-element pixels: 8 im2col TMAs (8 ch x 128 px) per K chunk, no swizzle
+  A_IM2COL32 = 3,  // NHWC tensor with 32-element pixels (W-expanded stem input): 2 im2col TMAs (32 ch x 128 px)
+                   // per K chunk, 64B swizzle
 };
 
 struct ConvGemmParams {
@@ -50,6 +52,6 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows,
 // im2col map over an NHWC bf16 tensor (N, H, W, pitch) exposing `c` channels per pixel.
 bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int lower_w,
                       int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int channels_per_pixel,
-                      int pixels_per_column, bool swizzle128, const char** err);
+                      int pixels_per_column, int swizzle_bytes, const char** err);
 
 }  // namespace pvr

@@ -28,6 +28,7 @@ struct PreParams {
   float mean[3], stdv[3];
   int fmt;
   int sample_major;  // image index of (sample i, frame f): i*nf + f instead of f*N + i
+  int pix_off;       // byte offset of the bf16 pixel buffer inside dynamic smem (PVR_FMT_STEM_BF16)
 };
 
 __device__ __forceinline__ void src_index(float scale, int dst, int size, int& i0, int& i1, float& l) {
@@ -86,6 +87,59 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
   const uint8_t* s = stage + head;
   const int npix = y_count * p.crop;
   const long long plane = (long long)p.crop * p.crop;
+  if (p.fmt == PVR_FMT_STEM_BF16) {
+    // W-expanded stem input: out[image][y][q][8 columns 2q-3..2q+4][4 ch] bf16 (64 B per output column of the 7x7/2
+    // stem), so that the stem conv is a 7x1-tap implicit GEMM with 64-byte TMA rows. Pixels are first written to a
+    // zero-margined bf16 row buffer in smem, then copied out 16 B per thread, fully coalesced.
+    uint2* pix = reinterpret_cast<uint2*>(smem + p.pix_off);
+    const int prow = p.crop + 8;  // entry x+4 holds column x; 4 zero entries on each side
+    const int Q = p.crop >> 1;
+    for (int t = threadIdx.x; t < y_count * 8; t += blockDim.x) {
+      const int yy = t >> 3, e = t & 7;
+      pix[yy * prow + (e < 4 ? e : p.crop + e)] = make_uint2(0u, 0u);
+    }
+    for (int f = 0; f < p.nf; ++f) {
+      for (int idx = threadIdx.x; idx < npix; idx += blockDim.x) {
+        const int yy = idx / p.crop;
+        const int x = idx - yy * p.crop;
+        int r0, r1, c0, c1;
+        float ly, lx;
+        src_index(p.scale_y, y_first + yy + p.top, p.H, r0, r1, ly);
+        src_index(p.scale_x, x + p.left, p.W, c0, c1, lx);
+        const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+        const uint8_t* q00 = s + (long long)(r0 - r_lo) * row_bytes + c0 * p.CH + 3 * f;
+        const uint8_t* q01 = s + (long long)(r0 - r_lo) * row_bytes + c1 * p.CH + 3 * f;
+        const uint8_t* q10 = s + (long long)(r1 - r_lo) * row_bytes + c0 * p.CH + 3 * f;
+        const uint8_t* q11 = s + (long long)(r1 - r_lo) * row_bytes + c1 * p.CH + 3 * f;
+        float o[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float top = __fmaf_rn((float)q00[c], hx, __fmul_rn((float)q01[c], lx));
+          const float bot = __fmaf_rn((float)q10[c], hx, __fmul_rn((float)q11[c], lx));
+          const float v = __fmaf_rn(top, hy, __fmul_rn(bot, ly));
+          int u = (int)rintf(v);
+          u = min(max(u, 0), 255);
+          o[c] = lut[c * 256 + u];
+        }
+        __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(o[2], 0.f);
+        pix[yy * prow + x + 4] = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+      }
+      __syncthreads();
+      const long long image = p.sample_major ? (long long)img * p.nf + f : (long long)f * p.N + img;
+      uint4* dst = reinterpret_cast<uint4*>(p.out) + (image * p.crop + y_first) * (long long)Q * 4;
+      for (int t = threadIdx.x; t < y_count * Q * 4; t += blockDim.x) {
+        const int yy = t / (Q * 4);
+        const int rem = t - yy * Q * 4;
+        const int q = rem >> 2, k = rem & 3;
+        const uint2 e0 = pix[yy * prow + 2 * q + 1 + 2 * k];
+        const uint2 e1 = pix[yy * prow + 2 * q + 2 + 2 * k];
+        dst[t] = make_uint4(e0.x, e0.y, e1.x, e1.y);
+      }
+      __syncthreads();
+    }
+    return;
+  }
   for (int idx = threadIdx.x; idx < npix; idx += blockDim.x) {
     const int yy = idx / p.crop;
     const int x = idx - yy * p.crop;
@@ -142,7 +196,8 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   using namespace pvr;
   if (!in || !out || N <= 0 || H <= 0 || W <= 0 || n_frames <= 0 || rh <= 0 || rw <= 0 || crop <= 0 || top < 0 ||
       left < 0 || top + crop > rh || left + crop > rw || !mean || !stdv ||
-      (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16)) {
+      (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16 && out_fmt != PVR_FMT_STEM_BF16) ||
+      (out_fmt == PVR_FMT_STEM_BF16 && (crop & 1))) {
     pvr_set_error("pvr_preprocess_u8: invalid argument");
     return PVR_ERR_ARG;
   }
@@ -166,7 +221,12 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   int rows = 16;
   auto stage_bytes = [&](int r) { return ((long long)(p.scale_y * r) + 3) * row_bytes + 48; };
   while (rows > 1 && stage_bytes(rows) > 48 * 1024) rows >>= 1;
-  const long long smem = 16 + 3072 + stage_bytes(rows);
+  long long smem = 16 + 3072 + stage_bytes(rows);
+  p.pix_off = 0;
+  if (out_fmt == PVR_FMT_STEM_BF16) {
+    p.pix_off = (int)((smem + 15) & ~15ll);
+    smem = p.pix_off + (long long)rows * (crop + 8) * 8;
+  }
   if (smem > 200 * 1024) {
     pvr_set_error("pvr_preprocess_u8: input rows too wide for shared-memory staging (%lld bytes)", smem);
     return PVR_ERR_ARG;

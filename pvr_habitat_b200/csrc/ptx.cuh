@@ -191,6 +191,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// K-major, 64-byte swizzle: rows are 64 B (32 bf16) apart, 8-row groups SBO = 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
 // K-major, no swizzle ("interleave"): 8x16-byte core matrices; LBO = byte distance between the two K-halves of
 // one K=16 slice, SBO = byte distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {

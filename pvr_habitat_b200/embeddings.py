@@ -146,7 +146,7 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
 def build_encoder(model, device, hw=224):
     """Compile `model` (ResNet50Params or UberModel of them) into one pvr_encoder program on `device`."""
     prog = prg.Program()
-    in_slot = prog.new_slot(hw * hw * 4)  # slot 0: NHWC4 bf16 frames written by the preprocessing kernel
+    in_slot = prog.new_slot(hw * (hw // 2) * 32)  # slot 0: W-expanded bf16 frames from the preprocessing kernel
     parts = model.models if isinstance(model, UberModel) else [model]
     off = 0
     for m in parts:
@@ -222,7 +222,7 @@ class EmbeddingNet(nn.Module):
         n = obs.shape[0]
         enc = self.encoder()
         enc.bind(n * n_frames)
-        self.transforms.run(obs, n_frames, enc.slot0, _lib.PVR_FMT_NHWC4_BF16, True)
+        self.transforms.run(obs, n_frames, enc.slot0, _lib.PVR_FMT_STEM_BF16, True)
         if out is None:
             out = torch.empty(n, n_frames * self.out_size, dtype=torch.float32, device=self.device)
         enc.forward(out, self.out_size)

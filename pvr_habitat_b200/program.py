@@ -42,22 +42,26 @@ def pack_conv_weight(w, n_pad):
 
 
 def pack_stem_weight(w, n_pad):
-    """7x7 stride-2 stem over NHWC4 input seen as (H, W/2, 8): the filter becomes 7 x 4 taps of 8 values.
+    """7x7 stride-2 stem over the W-expanded input (PVR_FMT_STEM_BF16): per output column q the input row holds the
+    8 columns 2q-3 .. 2q+4 x 4 channels, so the filter is 7 row taps of 32 values.
 
-    Output column q reads input columns 2q-3 .. 2q+3 = pixel pairs q-2 .. q+1; in pair sp the element e holds
-    input column 2(q-2+sp)+e, i.e. filter column j = 2*sp + e - 1 (j = -1 does not exist -> zero).
-    K index = ((r*4 + sp)*8 + e*4 + c); 28 taps padded to 32 (k_pad = 256).
+    K index = r*32 + j*4 + c with j = filter column (j = 7 and c = 3 carry zero weights); 7 taps padded to 8
+    (k_pad = 256).
     """
     co, ci, r, s = w.shape
     assert (ci, r, s) == (3, 7, 7)
-    out = torch.zeros(n_pad, 32, 8, dtype=torch.float32)
-    for rr in range(7):
-        for sp in range(4):
-            for e in range(2):
-                j = 2 * sp + e - 1
-                if 0 <= j < 7:
-                    out[:co, rr * 4 + sp, e * 4:e * 4 + 3] = w[:, :, rr, j]
+    out = torch.zeros(n_pad, 8, 8, 4, dtype=torch.float32)  # (co, r, j, c)
+    out[:co, :7, :7, :3] = w.permute(0, 2, 3, 1)
     return out.reshape(n_pad, 256).to(torch.bfloat16)
+
+
+def expand_stem_input(x4):
+    """(N, H, W, 4) -> (N, H, W/2, 32): the PVR_FMT_STEM_BF16 layout, in torch (tests / NCHW entry point only)."""
+    n, h, w, c = x4.shape
+    pad = torch.zeros(n, h, w + 8, c, dtype=x4.dtype, device=x4.device)
+    pad[:, :, 4:4 + w] = x4
+    cols = [pad[:, :, 1 + e:1 + e + w:2] for e in range(8)]  # entry 2q+1+e = column 2q-3+e
+    return torch.stack(cols, 3).reshape(n, h, w // 2, 8 * c)
 
 
 class Program:
@@ -279,17 +283,17 @@ def _compress_head(prog, sd, prefix, x_slot, x_chw, emb_offset):
 
 
 def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
-    """Append one ResNet-50 trunk reading the NHWC4 bf16 frames in `in_slot`.
+    """Append one ResNet-50 trunk reading the W-expanded bf16 frames (PVR_FMT_STEM_BF16) in `in_slot`.
 
     variant: 'conv5' (moco_conv5 / resnet50: avg-pooled 2048), 'l4' (moco_conv4_compressed: 42*7*7 = 2058),
              'l3' (moco_conv3_compressed: 11*14*14 = 2156). Returns the number of embedding columns written.
     """
     pre = {"conv5": ("layer3.", "layer4."), "l4": ("layer3.", "layer4.0."), "l3": ("layer3.0.", None)}[variant]
-    # stem: 7x7/2 as a 7x4-tap conv over pixel pairs (see pack_stem_weight)
+    # stem: 7x7/2 as a 7x1-tap conv over the W-expanded input (see pack_stem_weight)
     scale, bias = fold_bn(sd, "bn1")
     p = (hw + 6 - 7) // 2 + 1
-    stem = prog.conv(in_slot, (8, hw, hw // 2), pack_stem_weight(sd["conv1.weight"].float(), 64), 256, 64, 7, 4,
-                     (2, 1), (-3, -2), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147)
+    stem = prog.conv(in_slot, (32, hw, hw // 2), pack_stem_weight(sd["conv1.weight"].float(), 64), 256, 64, 7, 1,
+                     (2, 1), (-3, 0), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147)
     x, h, w = prog.maxpool(stem, 64, p, p)
     prog.release(stem)
     chw = (64, h, w)

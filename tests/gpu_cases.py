@@ -68,9 +68,10 @@ def run_conv_op(x_nhwc, w, scale, bias, stride, pad, relu, res_nhwc=None, stem=F
     q = (wd + 2 * pad - s) // stride + 1
     n_pad = (co + 63) // 64 * 64
     if stem:
-        in_slot = prog.new_slot(h * wd * 4)
+        x_nhwc = prg.expand_stem_input(x_nhwc)
+        in_slot = prog.new_slot(h * (wd // 2) * 32)
         res = None
-        out_slot = prog.conv(in_slot, (8, h, wd // 2), prg.pack_stem_weight(w, n_pad), 256, co, 7, 4, (2, 1), (-3, -2),
+        out_slot = prog.conv(in_slot, (32, h, wd // 2), prg.pack_stem_weight(w, n_pad), 256, co, 7, 1, (2, 1), (-3, 0),
                              (p, q), scale, bias, co if relu else 0, block_n=block_n)
     else:
         in_slot = prog.new_slot(h * wd * c)

@@ -10,7 +10,7 @@ from pvr_habitat_b200 import _lib
 
 
 def emulate(prog, frames_nhwc4, round_bf16=True):
-    """frames_nhwc4: (N, H, W, 4) float tensor (slot 0 contents). Returns (N, emb_width) float32."""
+    """frames_nhwc4: slot-0 contents, (N, H, W/2, 32) W-expanded frames (program.expand_stem_input). Returns (N, emb_width)."""
     n = frames_nhwc4.shape[0]
     slots = {0: frames_nhwc4.reshape(n, -1).float()}
     emb = torch.zeros(n, prog.emb_width)

@@ -80,6 +80,21 @@ def test_preprocess_bf16_nhwc4_sample_major():
     assert torch.equal(got[..., :3], ref) and torch.all(got[..., 3] == 0)
 
 
+def test_preprocess_stem_layout_sample_major():
+    """PVR_FMT_STEM_BF16: per stem output column q, the 8 input columns 2q-3..2q+4 x 4 channels (zeros outside)."""
+    from pvr_habitat_b200.program import expand_stem_input
+    obs = restate.structured_frames(3, 64, 64, 6, 6)
+    t = Transforms()
+    out = torch.full((6, 224, 112, 32), float("nan"), dtype=torch.bfloat16, device="cuda")
+    t.run(torch.from_numpy(obs).cuda(), 2, out.data_ptr(), _lib.PVR_FMT_STEM_BF16, True)
+    frames, _ = restate.split_frames(obs)
+    ref = torch.from_numpy(restate.transforms(np.ascontiguousarray(frames.transpose(0, 3, 1, 2))))
+    ref = ref.view(2, 3, 3, 224, 224).permute(1, 0, 3, 4, 2).reshape(6, 224, 224, 3).to(torch.bfloat16)
+    ref4 = torch.zeros(6, 224, 224, 4, dtype=torch.bfloat16)
+    ref4[..., :3] = ref
+    assert torch.equal(out.cpu(), expand_stem_input(ref4))
+
+
 def test_transforms_module_keeps_reference_calling_convention(tf):
     frames = tf["in_structured_64"]
     x = torch.from_numpy(frames).permute(0, 3, 1, 2).contiguous().cuda()  # NCHW uint8, as src/embeddings.py:392-393

@@ -18,33 +18,36 @@ def test_program_equals_oracle_network(variant, width):
     sd = {k: (v.to(torch.bfloat16).float() if k.endswith("conv1.weight") or "conv" in k or "downsample.0.weight" in k
               else v) for k, v in sd.items()}  # weights the program will round to bf16 anyway
     prog = prg.Program()
-    s0 = prog.new_slot(64 * 64 * 4)
+    s0 = prog.new_slot(64 * 32 * 32)
     prog.emb_width = prg.add_resnet50(prog, sd, variant, s0, 0, hw=64)
     assert prog.emb_width == width
     x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(0))
     x4 = torch.zeros(2, 64, 64, 4)
     x4[..., :3] = x.permute(0, 2, 3, 1)
-    got = emulate(prog, x4, round_bf16=False)
+    got = emulate(prog, prg.expand_stem_input(x4), round_bf16=False)
     ref = restate.resnet50_forward(sd, variant, x)
     assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
 
 
 def test_stem_packing_is_the_7x7_stride2_conv():
     w = torch.randn(64, 3, 7, 7)
-    full = prg.pack_stem_weight(w, 64).float()
-    assert torch.all(full[:, 224:] == 0)  # taps 28..31 pad K to 256
-    packed = full[:, :224].reshape(64, 7, 4, 2, 4)
-    assert torch.all(packed[..., 3] == 0)  # padded channel
-    assert torch.all(packed[:, :, 0, 0, :] == 0)  # filter column -1 does not exist
-    for j in range(7):
-        sp, e = (j + 1) // 2, (j + 1) % 2
-        assert torch.equal(packed[:, :, sp, e, :3], w[:, :, :, j].permute(0, 2, 1).to(torch.bfloat16).float())
+    packed = prg.pack_stem_weight(w, 64).float().reshape(64, 8, 8, 4)  # (co, r, j, c)
+    assert torch.all(packed[:, 7] == 0) and torch.all(packed[:, :, 7] == 0) and torch.all(packed[..., 3] == 0)
+    assert torch.equal(packed[:, :7, :7, :3], w.permute(0, 2, 3, 1).to(torch.bfloat16).float())
+    # the expanded input layout: column e of output position q is input column 2q-3+e
+    x4 = torch.arange(2 * 6 * 8 * 4, dtype=torch.float32).reshape(2, 6, 8, 4)
+    ex = prg.expand_stem_input(x4).reshape(2, 6, 4, 8, 4)
+    for q in range(4):
+        for e in range(8):
+            col = 2 * q - 3 + e
+            want = x4[:, :, col] if 0 <= col < 8 else torch.zeros(2, 6, 4)
+            assert torch.equal(ex[:, :, q, e], want)
 
 
 def test_slot_planning_never_aliases_live_tensors():
     sd = restate.resnet50_state("conv5", 3)
     prog = prg.Program()
-    s0 = prog.new_slot(224 * 224 * 4)
+    s0 = prog.new_slot(224 * 112 * 32)
     prg.add_resnet50(prog, sd, "conv5", s0, 0)
     for op in prog.ops:
         if op["kind"] == 1:

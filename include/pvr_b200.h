@@ -121,6 +121,113 @@ int pvr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* 
                   const float* bias, const void* res, int64_t ldr, int m, int n, int n_pad, int k, int relu,
                   void* stream);
 
+/* General form used by the policy network (nn.Linear / nn.LSTM call sites of src/models.py:22-44 and their
+ * backward): out = epilogue(a (m x k) * b^T (n x k)), a and b bf16 row-major (K contiguous). */
+typedef struct pvr_gemm_desc {
+  const void* a;      /* bf16 (m, k), row pitch lda */
+  const void* b;      /* bf16 (n_pad, k), row pitch ldb; rows >= n must be zero */
+  void* out;          /* bf16 or fp32 (m, n), row pitch ldo */
+  const float* scale; /* (n_pad) per-column scale or NULL (= 1) */
+  const float* bias;  /* (n_pad) per-column bias or NULL (= 0) */
+  const void* res;    /* optional bf16 (m, n), row pitch ldr */
+  int64_t lda, ldb, ldo, ldr;
+  int32_t m, n, n_pad, k;
+  int32_t relu;       /* ReLU on the result */
+  int32_t res_mode;   /* 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward against the saved activation) */
+  int32_t out_f32;    /* 0: bf16 out; 1: fp32 out; 2: fp32 out, atomically accumulated (out must hold the addend) */
+  int32_t split_k;    /* out_f32 == 2 only: number of K slices computed by separate CTAs */
+} pvr_gemm_desc;
+int pvr_gemm(const pvr_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * BC policy network pieces (src/models.py:13-89 PolicyNet, main_bc_2.py:206-227 loss / clip / RMSprop).
+ * All matrices are row-major; "bf16" pointers are void*.
+ */
+/* BatchNorm1d, train mode (src/models.py:30-34): phase 1 accumulates per-feature sum / sum of squares in double
+ * (sums: 2*d doubles, zeroed inside) — all-reduce `sums` across ranks for data-parallel training — phase 2 turns them
+ * into mean / rstd (biased variance, eps), updates the running statistics (momentum, unbiased variance over `count`
+ * rows) and writes y = (x - mean) * rstd * gamma + beta as bf16. */
+int pvr_bn1d_stats(const float* x, int64_t ldx, int m, int d, double* sums, void* stream);
+int pvr_bn1d_normalize(const float* x, int64_t ldx, int m, int d, const double* sums, double count, float eps,
+                       float momentum, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                       float* mean, float* rstd, void* y_bf16, int64_t ldy, void* stream);
+/* eval mode: running statistics. */
+int pvr_bn1d_eval(const float* x, int64_t ldx, int m, int d, const float* running_mean, const float* running_var,
+                  float eps, const float* gamma, const float* beta, float* mean, float* rstd, void* y_bf16,
+                  int64_t ldy, void* stream);
+/* dgamma += sum dy * xhat, dbeta += sum dy (dy bf16 = gradient w.r.t. the BN output; outputs must be zeroed). */
+int pvr_bn1d_backward(const void* dy_bf16, int64_t lddy, const float* x, int64_t ldx, int m, int d, const float* mean,
+                      const float* rstd, float* dgamma, float* dbeta, void* stream);
+/* fp32 rows -> bf16 rows (policy input without BatchNorm; `x.float()` of src/models.py:60). */
+int pvr_cast_rows_bf16(const float* x, int64_t ldx, int m, int d, void* y_bf16, int64_t ldy, void* stream);
+
+/* One LSTM step (gate order i,f,g,o; state masked by notdone before the step, src/models.py:67-72). */
+int pvr_lstm_cell_forward(const float* G, const float* XP, const float* c_prev, const float* nd, const float* nd_next,
+                          int B, int H, float* gates, float* c_out, float* h_out_f32, void* h_out_bf16,
+                          void* hm_next_bf16, void* stream);
+int pvr_lstm_cell_backward(const float* dh_out, float* dh_rec, float* dc_rec, const float* gates, const float* c_prev,
+                           const float* c_cur, const float* nd, const float* nd_next, int B, int H, void* dG_bf16,
+                           void* stream);
+
+/* All T steps of one LSTM layer (recurrent GEMM on tcgen05 + fused cell kernel per step). */
+typedef struct pvr_lstm_fwd {
+  int32_t T, B, H, reserved;
+  const void* w_hh;   /* bf16 (4H, H) */
+  const float* xp;    /* (T*B, 4H) fp32: x_t W_ih^T + b_ih + b_hh for every step (one big GEMM) */
+  const float* nd;    /* (T, B) fp32 notdone = |1 - done| */
+  const float* h0;    /* (B, H) fp32 initial hidden state; the initial cell state is c_all[0] */
+  float* c_all;       /* ((T+1)*B, H) fp32: c_all[0] = c0 on entry, c_all[t+1] = c_t on exit (saved for backward) */
+  void* hm;           /* bf16 (T*B, H) workspace: hm[t] = nd[t] * h[t-1], the recurrent GEMM operand */
+  void* h_out;        /* bf16 (T*B, H): layer output */
+  float* gates;       /* (T*B, 4H) fp32 activated gates, saved for backward */
+  float* g_tmp;       /* (B, 4H) fp32 scratch */
+  float* h_last;      /* (B, H) fp32: h_{T-1} */
+} pvr_lstm_fwd;
+int pvr_lstm_forward(const pvr_lstm_fwd* layer, void* stream);
+
+typedef struct pvr_lstm_bwd {
+  int32_t T, B, H, reserved;
+  const void* w_hh_t;   /* bf16 (H, 4H): W_hh transposed */
+  const float* nd;      /* (T, B) */
+  const float* gates;   /* saved by the forward */
+  const float* c_all;   /* saved by the forward */
+  const float* dh_out;  /* (T*B, H) fp32 gradient w.r.t. the layer output, or NULL */
+  float* dh_rec;        /* (B, H) fp32: gradient of the final hidden state on entry (zeros in BC) */
+  float* dc_rec;        /* (B, H) fp32: gradient of the final cell state on entry (zeros in BC) */
+  void* dG;             /* bf16 (T*B, 4H) out: gradient w.r.t. the gate pre-activations */
+} pvr_lstm_bwd;
+int pvr_lstm_backward(const pvr_lstm_bwd* layer, void* stream);
+
+/* Heads (src/models.py:75-76): logits = h Wp^T + bp (A <= 8 actions), baseline = h Wb^T + bb; h bf16 (m, K). */
+int pvr_heads_forward(const void* h_bf16, int m, int K, const float* Wp, const float* bp, const float* Wb,
+                      const float* bb, int A, float* logits, float* baseline, void* stream);
+/* dh = scale * dlogits Wp (fp32), dWp += scale * dlogits^T h, dbp += scale * sum dlogits (outputs zeroed by caller). */
+int pvr_heads_backward(const float* dlogits, const void* h_bf16, const float* Wp, int m, int K, int A, float scale,
+                       float* dh, float* dWp, float* dbp, void* stream);
+/* loss = inv_count * sum_m nll(log_softmax(logits[m]), targets[m]) (main_bc_2.py:211-214; inv_count = 1/(T*B) of
+ * the GLOBAL batch), dlogits = inv_count * (softmax - onehot). `loss` is a device float. */
+int pvr_ce_loss(const float* logits, const int64_t* targets, int m, int A, float inv_count, float* loss, float* dlogits,
+                void* stream);
+
+/* out[n] += sum_m y[m][n] (bias gradients), y bf16. */
+int pvr_colsum_bf16(const void* y_bf16, int64_t ldy, int m, int n, float* out, void* stream);
+/* out (cols x rows) = in (rows x cols)^T, bf16. */
+int pvr_transpose_bf16(const void* in, int64_t ldi, int rows, int cols, void* out, int64_t ldo, void* stream);
+/* fp32 weight (rows x cols) -> bf16 copy and/or bf16 transposed copy (either may be NULL). */
+int pvr_cast_weight(const float* w, int rows, int cols, void* w_bf16, int64_t ldb, void* wt_bf16, int64_t ldt,
+                    void* stream);
+
+/* Fused optimizer (main_bc_2.py:220-227): sumsq = sum of squared gradients over <= 24 tensors (device double, zeroed
+ * inside); step = clip by the global norm sqrt(sumsq) (max_norm <= 0: no clipping; coefficient
+ * min(1, max_norm / (norm + 1e-6)) like torch.nn.utils.clip_grad_norm_) and RMSprop (torch semantics: eps outside the
+ * sqrt) or Adam update. The pre-clip norm is written to norm_out (device float) — the reference's gradient_norm stat. */
+#define PVR_OPT_RMSPROP 0
+#define PVR_OPT_ADAM 1
+int pvr_optim_sumsq(const float* const* grads, const int64_t* sizes, int count, double* sumsq, void* stream);
+int pvr_optim_step(int mode, float* const* params, float* const* grads, float* const* state1, float* const* state2,
+                   const int64_t* sizes, int count, const double* sumsq, float grad_scale, float max_norm, float lr,
+                   float alpha_or_beta1, float beta2, float eps, int step, float* norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

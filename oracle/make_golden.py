@@ -83,12 +83,107 @@ def golden_embeddings(E):
     np.savez_compressed(os.path.join(GOLDEN, "embeddings.npz"), **out)
 
 
+def golden_policy():
+    """Reference PolicyNet (src/models.py) forward/backward, and the per-step training trace of the UNMODIFIED
+    main_bc_2.run() on a synthetic embedded-observation pickle (fake env / test modules)."""
+    import pickle
+    import random
+    import types
+    from oracle import restate_policy as rp
+    M = refshim.reference_models()
+    out = {}
+    # ---- (a) one forward/backward of the reference module
+    T, B, D, A = 6, 5, 64, 3
+    torch.manual_seed(7)
+    net = M.PolicyNet((D,), A, batch_norm=True)
+    net.train()
+    rng = np.random.default_rng(3)
+    obs = rng.standard_normal((T, B, D)).astype(np.float32)
+    done = rng.random((T, B)) < 0.25
+    act = rng.integers(0, A, (T, B))
+    state = tuple(torch.from_numpy(rng.standard_normal((2, B, 1024)).astype(np.float32)) * 0.1 for _ in range(2))
+    o, st = net(dict(obs=torch.from_numpy(obs), done=torch.from_numpy(done)), state)
+    loss = torch.nn.functional.nll_loss(torch.nn.functional.log_softmax(torch.flatten(o["policy_logits"], 0, 1), -1),
+                                        torch.flatten(torch.from_numpy(act), 0, 1).long())
+    loss.backward()
+    out.update(fb_obs=obs, fb_done=done, fb_act=act, fb_h0=state[0].numpy(), fb_c0=state[1].numpy(),
+               fb_logits=o["policy_logits"].detach().numpy(), fb_baseline=o["baseline"].detach().numpy(),
+               fb_hn=st[0].detach().numpy(), fb_cn=st[1].detach().numpy(), fb_loss=np.float32(loss.item()))
+    names, norms, none = [], [], []
+    for k, p in net.named_parameters():
+        names.append(k)
+        norms.append(float(p.grad.norm()) if p.grad is not None else -1.0)
+        if p.grad is None:
+            none.append(k)
+    out.update(fb_param_names=np.array(names), fb_grad_norms=np.array(norms, dtype=np.float64),
+               fb_param_sums=np.array([float(p.double().sum()) for p in net.parameters()]),
+               fb_grad_bias_ih_l1=net.core.bias_ih_l1.grad.numpy(), fb_grad_policy_w=net.policy.weight.grad.numpy(),
+               fb_grad_bn_w=net.fc[0].weight.grad.numpy(), fb_running_var=net.fc[0].running_var.numpy())
+    print("policy fwd/bwd: loss", loss.item(), "params without grad:", none)
+
+    # ---- (b) main_bc_2.run() unmodified
+    n, D, T, B, steps = 512, 128, 8, 4, 12
+    obs, action, done, reward = rp.synthetic_bc_data(n, D, 3, 11)
+    fake_env = types.ModuleType("src.env_utils")
+
+    class _Space:
+        def __init__(self, shape=None, n=None):
+            self.shape, self.n = shape, n
+
+    class _Env:
+        def __init__(self):
+            self.gym_env = types.SimpleNamespace(observation_space=_Space(shape=(D,)), action_space=_Space(n=3))
+
+        def close(self):
+            pass
+
+    fake_env.make_environment = lambda flags, embedding_model, actor_id=1: _Env()
+    fake_test = types.ModuleType("src.test_model")
+    fake_test.test = lambda model, env, stat_keys, n_episodes: {k: [0.0] for k in stat_keys}
+    sys.modules["src.env_utils"], sys.modules["src.test_model"] = fake_env, fake_test
+    refshim.install_stubs()
+    import src.embeddings as E
+    E.EmbeddingNet = lambda *a, **k: torch.nn.Identity()
+    import main_bc_2
+    main_bc_2.EmbeddingNet = E.EmbeddingNet
+    from src.arguments import parser
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, "fakeenv_fakeemb.pickle"), "wb") as f:
+            pickle.dump(dict(obs=obs, action=action, reward=reward, done=done, true_state=np.zeros((n, 12))), f)
+        flags = parser.parse_args([
+            "--env", "fakeenv", "--to_env", "fakeenv", "--embedding_name", "fakeemb", "--data_path", d,
+            "--save_path", os.path.join(d, "out"), "--batch_size", str(B), "--unroll_length", str(T),
+            "--max_frames", str(steps * T * B), "--eval_frequency", "1", "--batch_norm", "--disable_cuda",
+            "--disable_save", "--run_id", "5", "--n_episodes_test", "1"])
+        stats = {}
+        orig_dump = pickle.dump
+        main_bc_2.pickle.dump = lambda obj, fh, protocol=None: stats.update(obj)  # unused (disable_save)
+        # capture the stats dict: run() keeps it local, so re-enable saving into the temp dir instead
+        flags.disable_save = False
+        main_bc_2.pickle.dump = orig_dump
+        main_bc_2.run(flags)
+        st = pickle.load(open(os.path.join(d, "out", "fakeenv_emfakeemb_s5_fakeenv.pickle"), "rb"))["fakeenv"]
+    out.update(bc_obs=obs, bc_action=action, bc_done=done, bc_T=np.array(T), bc_B=np.array(B),
+               bc_steps=np.array(steps), bc_seed=np.array(5), bc_max_frames=np.array(steps * T * B),
+               bc_loss=np.array(st["training_loss"][1:], dtype=np.float64),
+               bc_grad_norm=np.array(st["gradient_norm"][1:], dtype=np.float64),
+               bc_frames=np.array(st["frames"][1:]))
+    print("main_bc_2.run trace:", np.round(out["bc_loss"], 4))
+    np.savez_compressed(os.path.join(GOLDEN, "policy.npz"), **out)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
-    E = refshim.reference_embeddings()
-    golden_transforms(E)
-    golden_embeddings(E)
+    which = sys.argv[1:] or ["transforms", "embeddings", "policy"]
+    if "transforms" in which or "embeddings" in which:
+        E = refshim.reference_embeddings()
+        if "transforms" in which:
+            golden_transforms(E)
+        if "embeddings" in which:
+            golden_embeddings(E)
+    if "policy" in which:
+        golden_policy()
 
 
 if __name__ == "__main__":

@@ -23,11 +23,30 @@ class pvr_op(ctypes.Structure):
         ("weight", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("aux", ctypes.c_void_p)]
 
 
+class pvr_gemm_desc(ctypes.Structure):
+    _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("out", ctypes.c_void_p), ("scale", ctypes.c_void_p),
+                ("bias", ctypes.c_void_p), ("res", ctypes.c_void_p), ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64),
+                ("ldo", ctypes.c_int64), ("ldr", ctypes.c_int64), ("m", ctypes.c_int32), ("n", ctypes.c_int32),
+                ("n_pad", ctypes.c_int32), ("k", ctypes.c_int32), ("relu", ctypes.c_int32),
+                ("res_mode", ctypes.c_int32), ("out_f32", ctypes.c_int32), ("split_k", ctypes.c_int32)]
+
+
+class pvr_lstm_fwd(ctypes.Structure):
+    _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("reserved", ctypes.c_int32)] + [
+        (n, ctypes.c_void_p) for n in ("w_hh", "xp", "nd", "h0", "c_all", "hm", "h_out", "gates", "g_tmp", "h_last")]
+
+
+class pvr_lstm_bwd(ctypes.Structure):
+    _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("reserved", ctypes.c_int32)] + [
+        (n, ctypes.c_void_p) for n in ("w_hh_t", "nd", "gates", "c_all", "dh_out", "dh_rec", "dc_rec", "dG")]
+
+
 class pvr_slot(ctypes.Structure):
     _fields_ = [("elems_per_image", ctypes.c_int64)]
 
 
 _lib = None
+_vp, _i, _i64, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
 
 _SIGNATURES = {
     "pvr_last_error": (ctypes.c_char_p, []),
@@ -46,6 +65,27 @@ _SIGNATURES = {
     "pvr_encoder_slot_ptr": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_int]),
     "pvr_encoder_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
     "pvr_encoder_destroy": (None, [ctypes.c_void_p]),
+    "pvr_gemm": (ctypes.c_int, [ctypes.POINTER(pvr_gemm_desc), ctypes.c_void_p]),
+    "pvr_bn1d_stats": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp]),
+    "pvr_bn1d_normalize": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, ctypes.c_double, _f, _f, _vp, _vp, _vp, _vp, _vp,
+                                          _vp, _vp, _i64, _vp]),
+    "pvr_bn1d_eval": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "pvr_bn1d_backward": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "pvr_cast_rows_bf16": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _i64, _vp]),
+    "pvr_lstm_cell_forward": (ctypes.c_int, [_vp] * 5 + [_i, _i] + [_vp] * 6),
+    "pvr_lstm_cell_backward": (ctypes.c_int, [_vp] * 8 + [_i, _i, _vp, _vp]),
+    "pvr_lstm_forward": (ctypes.c_int, [ctypes.POINTER(pvr_lstm_fwd), _vp]),
+    "pvr_lstm_backward": (ctypes.c_int, [ctypes.POINTER(pvr_lstm_bwd), _vp]),
+    "pvr_heads_forward": (ctypes.c_int, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "pvr_heads_backward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
+    "pvr_ce_loss": (ctypes.c_int, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp]),
+    "pvr_colsum_bf16": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp]),
+    "pvr_transpose_bf16": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _i64, _vp]),
+    "pvr_cast_weight": (ctypes.c_int, [_vp, _i, _i, _vp, _i64, _vp, _i64, _vp]),
+    "pvr_optim_sumsq": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _vp]),
+    "pvr_optim_step": (ctypes.c_int, [_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                      ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _f, _f, _f, _f, _f, _f, _i,
+                                      _vp, _vp]),
     "pvr_gemm_bf16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -164,6 +164,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     }
     p.num_n_tiles = o.n_pad / b.block_n;
     p.num_k_chunks = o.k_pad / 64;
+    p.split_k = 1;
     p.S = o.s;
     p.taps = o.r * o.s;
     p.stride_w = o.stride_w;
@@ -341,57 +342,122 @@ extern "C" int pvr_encoder_launch_count(const pvr_encoder* enc) { return enc ? (
 
 extern "C" void pvr_encoder_destroy(pvr_encoder* enc) { delete enc; }
 
-extern "C" int pvr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo,
-                             const float* scale, const float* bias, const void* res, int64_t ldr, int m, int n,
-                             int n_pad, int k, int relu, void* stream) {
-  if (!a || !b || !out || !scale || !bias || m <= 0 || n <= 0 || n > n_pad || n_pad % 32 || k <= 0 || k % 64 ||
-      lda % 8 || ldb % 8 || ldo % 8 || (res && ldr % 8)) {
-    pvr_set_error("pvr_gemm_bf16: invalid argument");
+namespace {
+// Device constants for GEMMs called without scale / bias (ones / zeros), allocated once per process and device.
+const float* unit_vector(bool ones) {
+  static float* bufs[16][2] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!bufs[dev][0]) {
+    const size_t n = 16384;
+    float* z = nullptr;
+    float* o = nullptr;
+    if (cudaMalloc(&z, n * sizeof(float)) != cudaSuccess || cudaMalloc(&o, n * sizeof(float)) != cudaSuccess)
+      return nullptr;
+    std::vector<float> h(n, 1.0f);
+    cudaMemset(z, 0, n * sizeof(float));
+    cudaMemcpy(o, h.data(), n * sizeof(float), cudaMemcpyHostToDevice);
+    bufs[dev][0] = z;
+    bufs[dev][1] = o;
+  }
+  return bufs[dev][ones ? 1 : 0];
+}
+}  // namespace
+
+extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
+  if (!d || !d->a || !d->b || !d->out || d->m <= 0 || d->n <= 0 || d->n > d->n_pad || d->n_pad % 32 || d->k <= 0 ||
+      d->k % 64 || d->lda % 8 || d->ldb % 8 || (d->res && d->ldr % 8) || d->n_pad > 16384 || d->out_f32 < 0 ||
+      d->out_f32 > 2 || (d->out_f32 ? d->ldo % 4 : d->ldo % 8)) {
+    pvr_set_error("pvr_gemm: invalid argument");
+    return PVR_ERR_ARG;
+  }
+  const int split_k = d->split_k > 1 ? d->split_k : 1;
+  if ((split_k > 1 && d->out_f32 != 2) || (d->k / 64) % split_k || (d->out_f32 && d->res)) {
+    pvr_set_error("pvr_gemm: split_k needs out_f32 == 2 and must divide k/64; fp32 output takes no residual");
     return PVR_ERR_ARG;
   }
   const int sms = device_sm_count();
-  if (sms <= 0) {
-    pvr_set_error("pvr_gemm_bf16: no CUDA device");
+  const float* scale = d->scale ? d->scale : unit_vector(true);
+  const float* bias = d->bias ? d->bias : unit_vector(false);
+  if (sms <= 0 || !scale || !bias) {
+    pvr_set_error("pvr_gemm: no CUDA device");
     return PVR_ERR_CUDA;
   }
   pvr::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
-  p.M = m;
-  p.num_m_tiles = (m + 127) / 128;
-  const int block_n = pick_block_n(n_pad, p.num_m_tiles, sms, 0, res != nullptr);
-  p.num_n_tiles = n_pad / block_n;
-  p.num_k_chunks = k / 64;
-  p.n_valid = n;
-  p.relu_n = relu ? n : 0;
-  p.ldo = ldo;
-  p.ldr = ldr;
-  p.out = static_cast<__nv_bfloat16*>(out);
-  p.res = static_cast<const __nv_bfloat16*>(res);
+  p.M = d->m;
+  p.num_m_tiles = (d->m + 127) / 128;
+  int block_n = pick_block_n(d->n_pad, (long long)p.num_m_tiles * split_k, sms, 0, d->res != nullptr);
+  if (d->out_f32 == 2 && block_n > 128) block_n = 128;
+  p.num_n_tiles = d->n_pad / block_n;
+  p.split_k = split_k;
+  p.num_k_chunks = d->k / 64 / split_k;
+  p.n_valid = d->n;
+  p.relu_n = d->relu ? d->n : 0;
+  p.ldo = d->ldo;
+  p.ldr = d->ldr;
+  p.res_mode = d->res_mode;
+  p.out_is_f32 = d->out_f32 != 0;
+  p.out = static_cast<__nv_bfloat16*>(d->out);
+  p.out_f32 = static_cast<float*>(d->out);
+  p.res = static_cast<const __nv_bfloat16*>(d->res);
   p.scale = scale;
   p.bias = bias;
   CUtensorMap ta, tb, to, tr;
   const char* err = "";
-  if (!pvr::make_tmap_2d(&ta, a, (uint64_t)k, (uint64_t)m, (uint64_t)lda, 128, &err) ||
-      !pvr::make_tmap_2d(&tb, b, (uint64_t)k, (uint64_t)n_pad, (uint64_t)ldb, (uint32_t)block_n, &err)) {
-    pvr_set_error("pvr_gemm_bf16: %s", err);
+  if (!pvr::make_tmap_2d(&ta, d->a, (uint64_t)d->k, (uint64_t)d->m, (uint64_t)d->lda, 128, &err) ||
+      !pvr::make_tmap_2d(&tb, d->b, (uint64_t)d->k, (uint64_t)d->n_pad, (uint64_t)d->ldb, (uint32_t)block_n, &err)) {
+    pvr_set_error("pvr_gemm: %s", err);
     return PVR_ERR_CUDA;
   }
-  const bool epi_tma = (block_n >= 64 && n % 64 == 0);
+  bool epi_tma;
   to = ta;
   tr = ta;
-  if (epi_tma) {
-    p.has_res = res != nullptr;
-    if (!pvr::make_tmap_2d(&to, out, (uint64_t)n, (uint64_t)m, (uint64_t)ldo, 128, &err) ||
-        (res && !pvr::make_tmap_2d(&tr, res, (uint64_t)n, (uint64_t)m, (uint64_t)ldr, 128, &err))) {
-      pvr_set_error("pvr_gemm_bf16: %s", err);
+  if (d->out_f32 == 0) {
+    epi_tma = (block_n >= 64 && d->n % 64 == 0);
+    if (epi_tma) {
+      p.has_res = d->res != nullptr;
+      if (!pvr::make_tmap_2d(&to, d->out, (uint64_t)d->n, (uint64_t)d->m, (uint64_t)d->ldo, 128, &err) ||
+          (d->res && !pvr::make_tmap_2d(&tr, d->res, (uint64_t)d->n, (uint64_t)d->m, (uint64_t)d->ldr, 128, &err))) {
+        pvr_set_error("pvr_gemm: %s", err);
+        return PVR_ERR_CUDA;
+      }
+    }
+  } else if (d->out_f32 == 1) {
+    epi_tma = true;
+    if (block_n < 64 || d->n % 32) {
+      pvr_set_error("pvr_gemm: fp32 output needs n %% 32 == 0 and n_pad %% 64 == 0");
+      return PVR_ERR_ARG;
+    }
+    if (!pvr::make_tmap_2d_f32(&to, d->out, (uint64_t)d->n, (uint64_t)d->m, (uint64_t)d->ldo, 128, &err)) {
+      pvr_set_error("pvr_gemm: %s", err);
       return PVR_ERR_CUDA;
     }
+  } else {
+    epi_tma = false;
   }
   cudaError_t e = pvr::launch_conv_gemm(block_n, pvr::A_TILED, epi_tma, ta, tb, to, tr, p, sms,
                                         static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) {
-    pvr_set_error("pvr_gemm_bf16: %s", cudaGetErrorString(e));
+    pvr_set_error("pvr_gemm: %s", cudaGetErrorString(e));
     return PVR_ERR_CUDA;
   }
   return PVR_OK;
+}
+
+extern "C" int pvr_gemm_bf16(const void* a, int64_t lda, const void* b, int64_t ldb, void* out, int64_t ldo,
+                             const float* scale, const float* bias, const void* res, int64_t ldr, int m, int n,
+                             int n_pad, int k, int relu, void* stream) {
+  pvr_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.a = a; d.lda = lda; d.b = b; d.ldb = ldb; d.out = out; d.ldo = ldo;
+  d.scale = scale; d.bias = bias; d.res = res; d.ldr = ldr;
+  d.m = m; d.n = n; d.n_pad = n_pad; d.k = k; d.relu = relu; d.split_k = 1;
+  if (!scale || !bias) {
+    pvr_set_error("pvr_gemm_bf16: invalid argument");
+    return PVR_ERR_ARG;
+  }
+  int rc = pvr_gemm(&d, stream);
+  if (rc == PVR_ERR_ARG) pvr_set_error("pvr_gemm_bf16: invalid argument");
+  return rc;
 }

@@ -81,6 +81,15 @@ __device__ __forceinline__ void add_bf16x8(float* f, const uint4& rv) {
     f[2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
   }
 }
+// ReLU backward: zero the gradient where the saved forward activation is not positive.
+__device__ __forceinline__ void mask_bf16x8(float* f, const uint4& rv) {
+  const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    if (!(__uint_as_float(w[t] << 16) > 0.f)) f[2 * t + 0] = 0.f;
+    if (!(__uint_as_float(w[t] & 0xFFFF0000u) > 0.f)) f[2 * t + 1] = 0.f;
+  }
+}
 __device__ __forceinline__ void relu_cols(float* f, int n, int relu_n) {
   if (n + 32 <= relu_n) {
 #pragma unroll
@@ -91,7 +100,7 @@ __device__ __forceinline__ void relu_cols(float* f, int n, int relu_n) {
   }
 }
 
-template <int BLOCK_N, int A_MODE, bool EPI_TMA>
+template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
@@ -99,7 +108,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   using C = Cfg<BLOCK_N, EPI_TMA>;
   constexpr int STAGES = C::STAGES;
   constexpr int NB = C::NB > 0 ? C::NB : 1;
-  constexpr int SUBS = BLOCK_N / EPI_N > 0 ? BLOCK_N / EPI_N : 1;  // epilogue sub-tiles per tile
+  constexpr int EPI_COLS = OUT_F32 ? 32 : EPI_N;  // columns of one 128-byte staging row (fp32 / bf16 output)
+  constexpr int SUBS = BLOCK_N / EPI_COLS > 0 ? BLOCK_N / EPI_COLS : 1;  // epilogue sub-tiles per tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -117,7 +127,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;  // split-K slices are separate tiles
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
@@ -154,8 +164,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int mn = tile / p.split_k;
+        const int kc0 = (tile - mn * p.split_k) * p.num_k_chunks;  // first K chunk of this split-K slice
+        const int m_tile = mn / p.num_n_tiles;
+        const int n_tile = mn - m_tile * p.num_n_tiles;
         const int m0 = m_tile * BLOCK_M;
         const int n0 = n_tile * BLOCK_N;
         int img = 0, w0 = 0, h0 = 0;
@@ -168,7 +180,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           w0 = p.lower_w + qq * p.stride_w;
           h0 = p.lower_h + pp * p.stride_h;
         }
-        for (int kc = 0; kc < p.num_k_chunks; ++kc) {
+        for (int kc = kc0; kc < kc0 + p.num_k_chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
           uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
@@ -227,7 +239,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 : (A_MODE == A_IM2COL32) ? umma_desc_sw64(a_base + (k >> 1) * 8192 + (k & 1) * (UMMA_K * 2))
                                          : umma_desc_sw128(a_base + k * (UMMA_K * 2));
             const uint64_t bdesc = umma_desc_sw128(b_base + k * (UMMA_K * 2));
-            umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, (kc | k) != 0);  // kc counts from 0 inside the slice
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -242,15 +254,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (EPI_TMA && lane == 0) {
       uint32_t q = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int mn = tile / p.split_k;
+        const int m_tile = mn / p.num_n_tiles;
+        const int n_tile = mn - m_tile * p.num_n_tiles;
         for (int c = 0; c < SUBS; ++c, ++q) {
           const uint32_t s = q % NB, ph = (q / NB) & 1;
           mbar_wait(&eb_empty_bar[s], ph ^ 1);
-          if (p.has_res) {
+          if (!OUT_F32 && p.has_res) {
             mbar_expect_tx(&eb_full_bar[s], EPI_TILE_BYTES);
             tma_load_2d(&tmap_res, &eb_full_bar[s], sEB + s * EPI_TILE_BYTES,
-                        p.res_coff + n_tile * BLOCK_N + c * EPI_N, m_tile * BLOCK_M);
+                        p.res_coff + n_tile * BLOCK_N + c * EPI_COLS, m_tile * BLOCK_M);
           } else {
             mbar_arrive(&eb_full_bar[s]);
           }
@@ -267,21 +280,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (EPI_TMA) {
       const bool leader = (gtid == 0);
       const uint32_t swz = (uint32_t)(row & 7);
-      float* sb = sSB + group * 256;  // two 128-float buffers: scale[64] | bias[64]
+      float* sb = sSB + group * 256;  // two 128-float buffers: scale[EPI_COLS] | bias[EPI_COLS] (bias at +64)
       auto stage_scale_bias = [&](uint32_t qq, uint32_t buf) {
         const int t_it = qq / SUBS, c = qq - t_it * SUBS;
         const long long tile = (long long)blockIdx.x + (long long)t_it * gridDim.x;
         if (tile < num_tiles) {
-          const int n = (int)(tile % p.num_n_tiles) * BLOCK_N + c * EPI_N;
-          sb[buf * 128 + gtid] = gtid < 64 ? __ldg(p.scale + n + gtid) : __ldg(p.bias + n + gtid - 64);
+          const int n = (int)((tile / p.split_k) % p.num_n_tiles) * BLOCK_N + c * EPI_COLS;
+          const int col = gtid & 63;
+          if (col < EPI_COLS) sb[buf * 128 + gtid] = gtid < 64 ? __ldg(p.scale + n + col) : __ldg(p.bias + n + col);
         }
       };
       uint32_t q = 0, j = 0, prev_s = 0;
       stage_scale_bias(group, 0);
       named_bar_sync(1 + group, 128);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int mn = tile / p.split_k;
+        const int m_tile = mn / p.num_n_tiles;
+        const int n_tile = mn - m_tile * p.num_n_tiles;
         const int n0 = n_tile * BLOCK_N;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
@@ -290,17 +305,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int c = 0; c < SUBS; ++c, ++q) {
           if ((q & 1) != (uint32_t)group) continue;
           const uint32_t s = q % NB, ph = (q / NB) & 1;
-          uint32_t v[64];
-          tmem_ld_32x32b_x32(taddr + c * EPI_N, v);
-          tmem_ld_32x32b_x32(taddr + c * EPI_N + 32, v + 32);
+          uint32_t v[EPI_COLS];
+          tmem_ld_32x32b_x32(taddr + c * EPI_COLS, v);
+          if (!OUT_F32) tmem_ld_32x32b_x32(taddr + c * EPI_COLS + 32, v + (OUT_F32 ? 0 : 32));
           stage_scale_bias(q + 2, (j + 1) & 1);  // next sub-tile of this group; published by this iteration's barrier
           mbar_wait(&eb_full_bar[s], ph);
           tmem_wait_ld();
           const uint32_t eb_row = smem_u32(sEB + s * EPI_TILE_BYTES) + row * 128;
           const uint32_t sb_addr = smem_u32(sb + (j & 1) * 128);
-          const int n = n0 + c * EPI_N;
+          const int n = n0 + c * EPI_COLS;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < EPI_COLS / 32; ++h) {
             float f[32];
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj) {
@@ -311,20 +326,36 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               f[4 * jj + 2] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 2]), __uint_as_float(s4.z), __uint_as_float(b4.z));
               f[4 * jj + 3] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 3]), __uint_as_float(s4.w), __uint_as_float(b4.w));
             }
-            if (p.has_res) {
+            if (OUT_F32) {
+              relu_cols(f, n, p.relu_n);
 #pragma unroll
-              for (int jj = 0; jj < 4; ++jj)
-                add_bf16x8(f + 8 * jj, ld_shared_v4(eb_row + (((h * 4 + jj) ^ swz) << 4)));
-            }
-            relu_cols(f, n + h * 32, p.relu_n);
+              for (int jj = 0; jj < 8; ++jj) {  // 32 fp32 = 8 x 16 B = one swizzled 128-byte row
+                uint4 ov;
+                ov.x = __float_as_uint(f[4 * jj + 0]);
+                ov.y = __float_as_uint(f[4 * jj + 1]);
+                ov.z = __float_as_uint(f[4 * jj + 2]);
+                ov.w = __float_as_uint(f[4 * jj + 3]);
+                st_shared_v4(eb_row + ((jj ^ swz) << 4), ov);
+              }
+            } else {
+              if (p.has_res) {
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              uint4 ov;
-              ov.x = pack_bf16x2(f[8 * jj + 0], f[8 * jj + 1]);
-              ov.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
-              ov.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
-              ov.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
-              st_shared_v4(eb_row + (((h * 4 + jj) ^ swz) << 4), ov);
+                for (int jj = 0; jj < 4; ++jj) {
+                  const uint4 rv = ld_shared_v4(eb_row + (((h * 4 + jj) ^ swz) << 4));
+                  if (p.res_mode == 0) add_bf16x8(f + 8 * jj, rv);
+                  else mask_bf16x8(f + 8 * jj, rv);
+                }
+              }
+              relu_cols(f, n + h * 32, p.relu_n);
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj) {
+                uint4 ov;
+                ov.x = pack_bf16x2(f[8 * jj + 0], f[8 * jj + 1]);
+                ov.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
+                ov.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
+                ov.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
+                st_shared_v4(eb_row + (((h * 4 + jj) ^ swz) << 4), ov);
+              }
             }
           }
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -347,8 +378,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires its smem
     } else if (group == 0) {
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.num_n_tiles;
-        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int mn = tile / p.split_k;
+        const int m_tile = mn / p.num_n_tiles;
+        const int n_tile = mn - m_tile * p.num_n_tiles;
         const long long m = (long long)m_tile * BLOCK_M + row;
         const int n0 = n_tile * BLOCK_N;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -365,6 +397,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_wait_ld();
           const int n = n0 + c * 32;
           if (!row_ok || n >= p.n_valid) continue;
+          if (OUT_F32) {
+            // fp32 accumulate into global memory (split-K partial sums): 16-byte vector reductions
+            float* orow = p.out_f32 + m * p.ldo + n;
+            if (n + 32 <= p.n_valid) {
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj)
+                atomicAdd(reinterpret_cast<float4*>(orow) + jj,
+                          make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]),
+                                      __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3])));
+            } else {
+              for (int jj = 0; jj < p.n_valid - n; ++jj) atomicAdd(orow + jj, __uint_as_float(v[jj]));
+            }
+            continue;
+          }
           float f[32];
           epilogue_math(v, f, p, n);
           if (n + 32 <= p.n_valid) {
@@ -410,10 +456,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <int BLOCK_N, int A_MODE, bool EPI_TMA>
+template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32>
 cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                        const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = conv_gemm_kernel<BLOCK_N, A_MODE, EPI_TMA>;
+  auto kern = conv_gemm_kernel<BLOCK_N, A_MODE, EPI_TMA, OUT_F32>;
   using C = Cfg<BLOCK_N, EPI_TMA>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
@@ -421,7 +467,7 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, p);
   return cudaGetLastError();
@@ -431,10 +477,10 @@ template <int BLOCK_N, bool EPI_TMA>
 cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                         const CUtensorMap& tr, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   switch (a_mode) {
-    case A_TILED: return launch_one<BLOCK_N, A_TILED, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
-    case A_IM2COL64: return launch_one<BLOCK_N, A_IM2COL64, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
-    case A_IM2COL8: return launch_one<BLOCK_N, A_IM2COL8, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
-    case A_IM2COL32: return launch_one<BLOCK_N, A_IM2COL32, EPI_TMA>(ta, tb, to, tr, p, num_sms, stream);
+    case A_TILED: return launch_one<BLOCK_N, A_TILED, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
+    case A_IM2COL64: return launch_one<BLOCK_N, A_IM2COL64, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
+    case A_IM2COL8: return launch_one<BLOCK_N, A_IM2COL8, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
+    case A_IM2COL32: return launch_one<BLOCK_N, A_IM2COL32, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -444,6 +490,24 @@ cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb
 cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtensorMap& tmap_a,
                              const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  if (p.split_k < 1) return cudaErrorInvalidValue;
+  if (p.out_is_f32) {  // plain GEMMs only (policy network): fp32 result, TMA-staged or split-K atomic
+    if (a_mode != A_TILED) return cudaErrorInvalidValue;
+    if (epi_tma) {
+      switch (block_n) {
+        case 64: return launch_one<64, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+        case 128: return launch_one<128, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+        case 256: return launch_one<256, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+        default: return cudaErrorInvalidValue;
+      }
+    }
+    switch (block_n) {
+      case 32: return launch_one<32, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      case 64: return launch_one<64, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      case 128: return launch_one<128, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (epi_tma) {
     switch (block_n) {
       case 64: return launch_mode<64, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
@@ -494,6 +558,21 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed"; return false; }
+  return true;
+}
+
+bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                      uint32_t box_rows, const char** err) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
+  if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (fp32) failed"; return false; }
   return true;
 }
 

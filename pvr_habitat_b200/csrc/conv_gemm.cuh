@@ -21,7 +21,7 @@ struct ConvGemmParams {
   int P, Q;          // output height / width per image (im2col modes)
   int num_m_tiles;   // ceil(M / 128)
   int num_n_tiles;   // n_pad / BLOCK_N
-  int num_k_chunks;  // k_pad / 64
+  int num_k_chunks;  // K chunks of 64 per tile (= k_pad / 64 / split_k)
   int cin_chunks;    // A_IM2COL64: C_in / 64
   int S;             // filter taps per row
   int taps;          // R * S (real taps; chunks may be padded with repeats of tap 0 against zero weights)
@@ -30,6 +30,10 @@ struct ConvGemmParams {
   int n_valid;       // real output channels (columns >= n_valid are not stored)
   int relu_n;        // ReLU is applied to output columns < relu_n (0: none, >= n_valid: all)
   int has_res;       // residual present (EPI_TMA path reads it through tmap_res)
+  int res_mode;      // 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward with the saved activation)
+  int split_k;       // >= 1; K is cut into split_k slices of num_k_chunks chunks, each its own tile (fp32 atomics)
+  int out_is_f32;    // fp32 output: TMA-staged (tmap_out is an fp32 map) or, with !epi_tma, atomically accumulated
+  float* out_f32;    // direct fp32 accumulate target (split-K)
   int out_coff, res_coff;  // channel offsets of the output / residual tile inside their pixel rows (EPI_TMA)
   long long ldo, ldr;  // output / residual row pitch in elements
   __nv_bfloat16* out;
@@ -49,6 +53,9 @@ cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtens
 // 2-D K-major bf16 matrix (rows x k), row pitch ld elements, box = (64 x box_rows), 128B swizzle.
 bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
                   const char** err);
+// 2-D fp32 matrix (rows x cols), row pitch ld elements, box = (32 x box_rows) = 128-byte rows, 128B swizzle.
+bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
+                      uint32_t box_rows, const char** err);
 // im2col map over an NHWC bf16 tensor (N, H, W, pitch) exposing `c` channels per pixel.
 bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int lower_w,
                       int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int channels_per_pixel,

@@ -1,0 +1,386 @@
+"""Drop-in for the reference's src/models.py: PolicyNet (and the fused BC loss).
+
+Same constructor, attributes, state_dict keys (`fc.*`, `core.weight_ih_l0` ..., `policy.*`, `baseline.*`), initial
+values (the constructor consumes the torch RNG exactly like the reference: orthogonal init for the Linear layers,
+nn.LSTM default init) and forward signature `forward(inputs: {'obs','done'}, core_state) -> (dict, core_state)`
+(src/models.py:57-89). The arithmetic runs in libpvr_b200: tcgen05 GEMMs for the Linear layers, the LSTM input
+projections and the recurrent matmuls, fused cell / BatchNorm / heads / loss kernels. Parameters stay fp32 (master
+copies); GEMM operands are bf16 with fp32 accumulation. There is no CPU path.
+
+Layer-wise execution: the done masks depend only on t, so running all T steps of LSTM layer 0 and then layer 1 equals
+the reference's per-timestep two-layer call and lets x_t W_ih^T be one (T*B) x 4096 GEMM per layer.
+"""
+import ctypes
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib
+from ._lib import pvr_gemm_desc, pvr_lstm_bwd, pvr_lstm_fwd
+
+
+def init(module, weight_init, bias_init, gain=1):
+    weight_init(module.weight.data, gain=gain)
+    bias_init(module.bias.data)
+    return module
+
+
+def _r64(x):
+    return (x + 63) // 64 * 64
+
+
+def _stream():
+    return _lib.current_stream_ptr()
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def gemm(a, b, out, m, n, k, bias=None, relu=False, res=None, res_mode=0, out_f32=0, split_k=1, n_pad=None):
+    """out (m x n) = epilogue(a (m x k) @ b (n x k)^T); a, b bf16 row-major with K contiguous."""
+    d = pvr_gemm_desc()
+    d.a, d.lda = a.data_ptr(), a.stride(0)
+    d.b, d.ldb = b.data_ptr(), b.stride(0)
+    d.out, d.ldo = out.data_ptr(), out.stride(0)
+    d.scale = None
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.res, d.ldr = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
+    d.m, d.n, d.n_pad, d.k = m, n, n_pad if n_pad is not None else b.shape[0], k
+    d.relu, d.res_mode, d.out_f32, d.split_k = int(relu), res_mode, out_f32, split_k
+    _lib.check(_lib.lib().pvr_gemm(ctypes.byref(d), _stream()), "pvr_gemm")
+
+
+class _Workspace:
+    """Device buffers of one (T, B, D) problem, reused across steps."""
+
+    def __init__(self, T, B, D, H, A, device, batch_norm):
+        M, Mp, Dp = T * B, _r64(T * B), _r64(D)
+        bf, f32 = torch.bfloat16, torch.float32
+        z = lambda *s, dtype=f32: torch.zeros(*s, dtype=dtype, device=device)  # noqa: E731
+        self.T, self.B, self.D, self.H, self.A, self.M, self.Mp, self.Dp = T, B, D, H, A, M, Mp, Dp
+        self.X0 = z(M, Dp, dtype=bf)          # BatchNorm output / cast input (K padded with zeros)
+        self.H1, self.H2 = z(M, H, dtype=bf), z(M, H, dtype=bf)
+        self.XP = [z(M, 4 * H), z(M, 4 * H)]
+        self.HL = [z(M, H, dtype=bf), z(M, H, dtype=bf)]
+        self.hm = [z(M, H, dtype=bf), z(M, H, dtype=bf)]
+        self.gates = [z(M, 4 * H), z(M, 4 * H)]
+        self.c_all = [z(M + B, H), z(M + B, H)]
+        self.g_tmp = z(B, 4 * H)
+        self.h_last = [z(B, H), z(B, H)]
+        self.nd = z(T, B)
+        self.logits, self.baseline = z(M, A), z(M)
+        self.mean, self.rstd = z(D), z(D)
+        self.sums = torch.zeros(2 * D, dtype=torch.float64, device=device)
+        # backward
+        self.dHL = [z(M, H), z(M, H)]         # fp32 gradients w.r.t. the LSTM layer outputs
+        self.dG = [z(M, 4 * H, dtype=bf), z(M, 4 * H, dtype=bf)]
+        self.dh_rec, self.dc_rec = z(B, H), z(B, H)
+        self.dZ2, self.dZ1 = z(M, H, dtype=bf), z(M, H, dtype=bf)
+        self.dX0 = z(M, Dp, dtype=bf) if batch_norm else None
+        # transposed operands for the weight-gradient GEMMs (batch dimension padded to 64 with zeros)
+        self.dGT = z(4 * H, Mp, dtype=bf)
+        self.actT = z(max(H, Dp), Mp, dtype=bf)
+        self.dZT = z(H, Mp, dtype=bf)
+        self.dW1p = z(H, Dp) if Dp != D else None
+
+
+class _PolicyFn(torch.autograd.Function):
+    """forward + backward of the whole PolicyNet as one autograd node (the CUDA kernels do not build a graph)."""
+
+    @staticmethod
+    def forward(ctx, net, x, notdone, h0, c0, *params):
+        ctx.set_materialize_grads(False)
+        out = net._forward_cuda(x, notdone, h0, c0)
+        ctx.net = net
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(out[2], out[3])
+        return out
+
+    @staticmethod
+    def backward(ctx, dlogits, dbaseline, dh, dc):
+        if dbaseline is not None:
+            raise NotImplementedError("PolicyNet backward: a loss on `baseline` is not part of the BC path "
+                                      "(main_bc_2.py:211-214 uses policy_logits only)")
+        if dlogits is None:
+            return (None,) * (5 + ctx.n_params)
+        grads = ctx.net._backward_cuda(dlogits.contiguous())
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class PolicyNet(nn.Module):
+    def __init__(self, observation_shape, num_actions, batch_norm=False):
+        super(PolicyNet, self).__init__()
+
+        init_ = lambda m: init(m, nn.init.orthogonal_,  # noqa: E731
+                               lambda x: nn.init.constant_(x, 0), nn.init.calculate_gain('relu'))
+        # identical module structure / construction order to src/models.py:22-44 (same RNG stream, same keys)
+        self.fc = nn.Sequential(
+            init_(nn.Linear(observation_shape[0], 1024)),
+            nn.ReLU(),
+            init_(nn.Linear(1024, 1024)),
+            nn.ReLU(),
+        )
+        if batch_norm:
+            self.fc = nn.Sequential(nn.BatchNorm1d(observation_shape[0]), *list(self.fc))
+        self.core = nn.LSTM(1024, 1024, 2)
+        init_ = lambda m: init(m, nn.init.orthogonal_, lambda x: nn.init.constant_(x, 0))  # noqa: E731
+        self.policy = init_(nn.Linear(1024, num_actions))
+        self.baseline = init_(nn.Linear(1024, 1))
+
+        self.batch_norm = bool(batch_norm)
+        self.num_actions = num_actions
+        self.obs_size = observation_shape[0]
+        self._ws = {}
+        self._wb = None          # bf16 weight copies
+        self._saved = None
+        # data-parallel hooks (set by pvr_habitat_b200.parallel): all-reduce of the BatchNorm sums
+        self.process_group = None
+        self.global_rows = None  # T*B of the GLOBAL batch (BatchNorm count); None = local
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def initial_state(self, batch_size):
+        return tuple(torch.zeros(self.core.num_layers, batch_size, self.core.hidden_size) for _ in range(2))
+
+    # ------------------------------------------------------------------------------------------ parameters
+    def _linears(self):
+        off = 1 if self.batch_norm else 0
+        return self.fc[off], self.fc[off + 2]
+
+    def _param_list(self):
+        """Order of the gradients returned by the backward."""
+        l1, l2 = self._linears()
+        ps = []
+        if self.batch_norm:
+            ps += [self.fc[0].weight, self.fc[0].bias]
+        ps += [l1.weight, l1.bias, l2.weight, l2.bias]
+        for l in range(2):
+            ps += [getattr(self.core, f"weight_ih_l{l}"), getattr(self.core, f"weight_hh_l{l}"),
+                   getattr(self.core, f"bias_ih_l{l}"), getattr(self.core, f"bias_hh_l{l}")]
+        ps += [self.policy.weight, self.policy.bias]
+        return ps
+
+    def _refresh_weights(self):
+        """bf16 (and transposed bf16) copies of the fp32 master weights; called at the start of every forward."""
+        dev, bf = self.device, torch.bfloat16
+        lib = _lib.lib()
+        l1, l2 = self._linears()
+        H, D, Dp = 1024, self.obs_size, _r64(self.obs_size)
+        if self._wb is None or self._wb["dev"] != dev:
+            z = lambda *s: torch.zeros(*s, dtype=bf, device=dev)  # noqa: E731
+            self._wb = dict(dev=dev, W1=z(H, Dp), W1T=z(Dp, H), W2=z(H, H), W2T=z(H, H),
+                            Wih=[z(4 * H, H), z(4 * H, H)], WihT=[z(H, 4 * H), z(H, 4 * H)],
+                            Whh=[z(4 * H, H), z(4 * H, H)], WhhT=[z(H, 4 * H), z(H, 4 * H)])
+        w = self._wb
+
+        def cast(src, dst, dstT):
+            r, c = src.shape
+            _lib.check(lib.pvr_cast_weight(src.data_ptr(), r, c, dst.data_ptr(), dst.stride(0),
+                                           dstT.data_ptr() if dstT is not None else None,
+                                           dstT.stride(0) if dstT is not None else 0, _stream()), "pvr_cast_weight")
+
+        cast(l1.weight.data, w["W1"], w["W1T"] if self.batch_norm else None)
+        cast(l2.weight.data, w["W2"], w["W2T"])
+        for l in range(2):
+            cast(getattr(self.core, f"weight_ih_l{l}").data, w["Wih"][l], w["WihT"][l])
+            cast(getattr(self.core, f"weight_hh_l{l}").data, w["Whh"][l], w["WhhT"][l])
+        w["b_l"] = [getattr(self.core, f"bias_ih_l{l}").data + getattr(self.core, f"bias_hh_l{l}").data
+                    for l in range(2)]
+
+    def _workspace(self, T, B):
+        key = (T, B, str(self.device))
+        if key not in self._ws:
+            if len(self._ws) > 4:
+                self._ws.clear()
+            self._ws[key] = _Workspace(T, B, self.obs_size, 1024, self.num_actions, self.device, self.batch_norm)
+        return self._ws[key]
+
+    # ------------------------------------------------------------------------------------------ forward (CUDA)
+    def _forward_cuda(self, x, notdone, h0, c0):
+        lib = _lib.lib()
+        T, B = notdone.shape
+        ws = self._workspace(T, B)
+        M, H, D = ws.M, ws.H, ws.D
+        self._refresh_weights()
+        w = self._wb
+        l1, l2 = self._linears()
+        ws.nd.copy_(notdone)
+        x = x.contiguous()
+        if self.batch_norm:
+            bn = self.fc[0]
+            if self.training:
+                _lib.check(lib.pvr_bn1d_stats(x.data_ptr(), x.stride(0), M, D, ws.sums.data_ptr(), _stream()),
+                           "pvr_bn1d_stats")
+                count = float(M)
+                if self.process_group is not None:
+                    torch.distributed.all_reduce(ws.sums, group=self.process_group)
+                    count = float(self.global_rows)
+                _lib.check(lib.pvr_bn1d_normalize(x.data_ptr(), x.stride(0), M, D, ws.sums.data_ptr(), count, bn.eps,
+                                                  bn.momentum, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                                  bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+                                                  ws.mean.data_ptr(), ws.rstd.data_ptr(), ws.X0.data_ptr(),
+                                                  ws.X0.stride(0), _stream()), "pvr_bn1d_normalize")
+                bn.num_batches_tracked += 1
+            else:
+                _lib.check(lib.pvr_bn1d_eval(x.data_ptr(), x.stride(0), M, D, bn.running_mean.data_ptr(),
+                                             bn.running_var.data_ptr(), bn.eps, bn.weight.data_ptr(),
+                                             bn.bias.data_ptr(), ws.mean.data_ptr(), ws.rstd.data_ptr(),
+                                             ws.X0.data_ptr(), ws.X0.stride(0), _stream()), "pvr_bn1d_eval")
+        else:
+            _lib.check(lib.pvr_cast_rows_bf16(x.data_ptr(), x.stride(0), M, D, ws.X0.data_ptr(), ws.X0.stride(0),
+                                              _stream()), "pvr_cast_rows_bf16")
+        gemm(ws.X0, w["W1"], ws.H1, M, H, ws.Dp, bias=l1.bias.data, relu=True)
+        gemm(ws.H1, w["W2"], ws.H2, M, H, H, bias=l2.bias.data, relu=True)
+        inp = ws.H2
+        hn, cn = [], []
+        for l in range(2):
+            gemm(inp, w["Wih"][l], ws.XP[l], M, 4 * H, H, bias=w["b_l"][l], out_f32=1)
+            ws.c_all[l][:B].copy_(c0[l])
+            h0l = h0[l].contiguous()
+            L = pvr_lstm_fwd(T=T, B=B, H=H, reserved=0, w_hh=w["Whh"][l].data_ptr(), xp=ws.XP[l].data_ptr(),
+                             nd=ws.nd.data_ptr(), h0=h0l.data_ptr(), c_all=ws.c_all[l].data_ptr(),
+                             hm=ws.hm[l].data_ptr(), h_out=ws.HL[l].data_ptr(), gates=ws.gates[l].data_ptr(),
+                             g_tmp=ws.g_tmp.data_ptr(), h_last=ws.h_last[l].data_ptr())
+            _lib.check(lib.pvr_lstm_forward(ctypes.byref(L), _stream()), "pvr_lstm_forward")
+            inp = ws.HL[l]
+            hn.append(ws.h_last[l].clone())
+            cn.append(ws.c_all[l][M:M + B].clone())
+        _lib.check(lib.pvr_heads_forward(ws.HL[1].data_ptr(), M, H, self.policy.weight.data_ptr(),
+                                         self.policy.bias.data_ptr(), self.baseline.weight.data_ptr(),
+                                         self.baseline.bias.data_ptr(), self.num_actions, ws.logits.data_ptr(),
+                                         ws.baseline.data_ptr(), _stream()), "pvr_heads_forward")
+        self._saved = (ws, x)
+        return ws.logits.clone(), ws.baseline.clone(), torch.stack(hn), torch.stack(cn)
+
+    # ------------------------------------------------------------------------------------------ backward (CUDA)
+    def _backward_cuda(self, dlogits):
+        lib = _lib.lib()
+        ws, x = self._saved
+        w = self._wb
+        T, B, M, Mp, H, D, Dp, A = ws.T, ws.B, ws.M, ws.Mp, ws.H, ws.D, ws.Dp, ws.A
+        dev = self.device
+        params = self._param_list()
+        # one flat, zero-initialised gradient buffer (a single all-reduce under data parallelism); every view starts on
+        # a 256-byte boundary so the fp32 TMA stores of the weight-gradient GEMMs are aligned
+        sizes = [(p.numel() + 63) // 64 * 64 for p in params]
+        flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        grads, off = [], 0
+        for p, sz in zip(params, sizes):
+            grads.append(flat[off:off + p.numel()].view_as(p))
+            off += sz
+        g = dict(zip(["bn_w", "bn_b"] if self.batch_norm else [], grads[:2]))
+        names = ["W1", "b1", "W2", "b2", "Wih0", "Whh0", "bih0", "bhh0", "Wih1", "Whh1", "bih1", "bhh1", "Wp", "bp"]
+        g.update(zip(names, grads[2 if self.batch_norm else 0:]))
+
+        def transpose(src, rows, cols, dst):
+            _lib.check(lib.pvr_transpose_bf16(src.data_ptr(), src.stride(0), rows, cols, dst.data_ptr(),
+                                              dst.stride(0), _stream()), "pvr_transpose_bf16")
+
+        def colsum(src, n, out):
+            _lib.check(lib.pvr_colsum_bf16(src.data_ptr(), src.stride(0), M, n, out.data_ptr(), _stream()),
+                       "pvr_colsum_bf16")
+
+        # heads: dHL1 = dlogits Wp, dWp, dbp
+        _lib.check(lib.pvr_heads_backward(dlogits.data_ptr(), ws.HL[1].data_ptr(), self.policy.weight.data_ptr(), M, H,
+                                          A, 1.0, ws.dHL[1].data_ptr(), g["Wp"].data_ptr(), g["bp"].data_ptr(),
+                                          _stream()), "pvr_heads_backward")
+        below = [ws.H2, ws.HL[0]]  # input of LSTM layer l
+        for l in (1, 0):
+            ws.dh_rec.zero_()
+            ws.dc_rec.zero_()
+            L = pvr_lstm_bwd(T=T, B=B, H=H, reserved=0, w_hh_t=w["WhhT"][l].data_ptr(), nd=ws.nd.data_ptr(),
+                             gates=ws.gates[l].data_ptr(), c_all=ws.c_all[l].data_ptr(),
+                             dh_out=ws.dHL[l].data_ptr(), dh_rec=ws.dh_rec.data_ptr(), dc_rec=ws.dc_rec.data_ptr(),
+                             dG=ws.dG[l].data_ptr())
+            _lib.check(lib.pvr_lstm_backward(ctypes.byref(L), _stream()), "pvr_lstm_backward")
+            dG = ws.dG[l]
+            colsum(dG, 4 * H, g[f"bih{l}"])
+            g[f"bhh{l}"].copy_(g[f"bih{l}"])
+            transpose(dG, M, 4 * H, ws.dGT)
+            transpose(ws.hm[l], M, H, ws.actT)
+            gemm(ws.dGT, ws.actT, g[f"Whh{l}"], 4 * H, H, Mp, out_f32=1, n_pad=H)
+            transpose(below[l], M, H, ws.actT)
+            gemm(ws.dGT, ws.actT, g[f"Wih{l}"], 4 * H, H, Mp, out_f32=1, n_pad=H)
+            if l == 1:   # gradient w.r.t. layer-0 outputs (fp32, consumed by the layer-0 cell backward)
+                gemm(dG, w["WihT"][1], ws.dHL[0], M, H, 4 * H, out_f32=1)
+            else:        # through ReLU of fc2: dZ2 = (dG0 W_ih0) * (H2 > 0)
+                gemm(dG, w["WihT"][0], ws.dZ2, M, H, 4 * H, res=ws.H2, res_mode=1)
+        colsum(ws.dZ2, H, g["b2"])
+        transpose(ws.dZ2, M, H, ws.dZT)
+        transpose(ws.H1, M, H, ws.actT)
+        gemm(ws.dZT, ws.actT, g["W2"], H, H, Mp, out_f32=1, n_pad=H)
+        gemm(ws.dZ2, w["W2T"], ws.dZ1, M, H, H, res=ws.H1, res_mode=1)
+        colsum(ws.dZ1, H, g["b1"])
+        transpose(ws.dZ1, M, H, ws.dZT)
+        transpose(ws.X0, M, Dp, ws.actT)
+        if Dp == D:
+            gemm(ws.dZT, ws.actT, g["W1"], H, D, Mp, out_f32=1, n_pad=Dp)
+        else:
+            gemm(ws.dZT, ws.actT, ws.dW1p, H, Dp, Mp, out_f32=1, n_pad=Dp)
+            g["W1"].copy_(ws.dW1p[:, :D])
+        if self.batch_norm:
+            gemm(ws.dZ1, w["W1T"], ws.dX0, M, Dp, H)
+            _lib.check(lib.pvr_bn1d_backward(ws.dX0.data_ptr(), ws.dX0.stride(0), x.data_ptr(), x.stride(0), M, D,
+                                             ws.mean.data_ptr(), ws.rstd.data_ptr(), g["bn_w"].data_ptr(),
+                                             g["bn_b"].data_ptr(), _stream()), "pvr_bn1d_backward")
+        if self.process_group is not None:  # data parallel: SUM over ranks (the loss is pre-scaled by 1/global rows)
+            torch.distributed.all_reduce(flat, group=self.process_group)
+        return grads
+
+    # ------------------------------------------------------------------------------------------ public forward
+    def forward(self, inputs, core_state=()):
+        x = inputs['obs']  # (unroll_length, batch_size, obs_size)
+        T, B, *_ = x.shape
+        dev = self.device
+        if dev.type != 'cuda':
+            raise _lib.PvrError("PolicyNet: CUDA device required — pvr_habitat_b200 has no CPU fallback")
+        x = torch.flatten(x, 0, 1).float().to(device=dev)
+        notdone = (1 - inputs['done'].float()).abs().to(device=dev)
+        if len(core_state) == 0:
+            core_state = self.initial_state(B)
+        h0, c0 = (s.to(device=dev, dtype=torch.float32) for s in core_state)
+        params = self._param_list()
+        with torch.cuda.device(dev):
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                logits, baseline, hn, cn = _PolicyFn.apply(self, x, notdone, h0, c0, *params)
+            else:
+                logits, baseline, hn, cn = self._forward_cuda(x, notdone, h0, c0)
+        if self.training:
+            action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1)
+        else:
+            action = torch.argmax(logits, dim=1)
+        return dict(policy_logits=logits.view(T, B, -1), baseline=baseline.view(T, B),
+                    action=action.view(T, B)), (hn, cn)
+
+
+class _CELossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, inv_count):
+        m, a = logits.shape
+        loss = torch.zeros((), dtype=torch.float32, device=logits.device)
+        dl = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            _lib.check(_lib.lib().pvr_ce_loss(logits.data_ptr(), targets.data_ptr(), m, a, inv_count, loss.data_ptr(),
+                                              dl.data_ptr(), _stream()), "pvr_ce_loss")
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad):
+        (dl,) = ctx.saved_tensors
+        return dl * grad, None, None
+
+
+def bc_loss(policy_logits, actions, global_rows=None):
+    """F.nll_loss(F.log_softmax(flatten(policy_logits), -1), flatten(actions).long()) of main_bc_2.py:211-214 as one
+    kernel (warp-shuffle reduction); `global_rows` = T*B of the global batch under data parallelism (loss and
+    gradients are then pre-scaled so that a SUM all-reduce over ranks gives the reference's mean)."""
+    logits = torch.flatten(policy_logits, 0, 1).contiguous().float()
+    targets = torch.flatten(actions, 0, 1).contiguous().long()
+    rows = logits.shape[0] if global_rows is None else global_rows
+    return _CELossFn.apply(logits, targets, 1.0 / rows)

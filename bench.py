@@ -127,6 +127,62 @@ def cpu_port_frames_per_s(name, n_frames, n_obs, threads):
     return n_obs * n_frames / dt, dt
 
 
+BC_CFG = dict(n=65536, D=2048, T=64, B=128, A=3)  # BASELINE configs[4]: global batch T*B = 8192, batch_norm=True
+BC_GFLOP_PER_STEP = 979.0  # fwd+bwd 119.6 MFLOP/sample x 8192
+
+
+def bc_dataset(seed=7):
+    from oracle import restate_policy as rp  # synthetic-input generator only
+    return rp.synthetic_bc_data(BC_CFG["n"], BC_CFG["D"], BC_CFG["A"], seed)
+
+
+def bench_bc(steps, warmup, world, dist, host_batches):
+    """BC train steps/s on the CUDA policy path (strong scaling: the global batch T*B = 8192 is split over ranks)."""
+    import random
+    from pvr_habitat_b200.bc import BCTrainer
+    from pvr_habitat_b200.models import PolicyNet
+    obs, action, done, _ = bc_dataset()
+    torch.manual_seed(1)
+    random.seed(1)
+    net = PolicyNet((BC_CFG["D"],), BC_CFG["A"], batch_norm=True).cuda().train()
+    tr = BCTrainer(net, obs, action, done, BC_CFG["B"], BC_CFG["T"], 10 ** 9, host_batches=host_batches,
+                   process_group=dist.group.WORLD if dist is not None else None)
+    for _ in range(warmup):
+        tr.step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.step()
+        if host_batches:
+            loss.item()  # the reference reads the loss on the host (main_bc_2.py:245)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return steps / (ms / 1e3), ms / steps, float(loss)
+
+
+def cpu_port_bc_steps_per_s(threads):
+    """Oracle CPU port of one BC step at the same shape (bounded sample: 1 step after a small warm-up)."""
+    from oracle import restate_policy as rp
+    torch.set_num_threads(threads)
+    obs, action, done, _ = bc_dataset()
+    sd = rp.init_policy_state(BC_CFG["D"], BC_CFG["A"], True, 1)
+    rp.bc_train(sd, obs, action, done, 4, 8, 1, 10 ** 9, True)  # warm-up at a tiny shape
+    t0 = time.perf_counter()
+    rp.bc_train(sd, obs, action, done, BC_CFG["T"], BC_CFG["B"], 1, 10 ** 9, True)
+    dt = time.perf_counter() - t0
+    return 1.0 / dt, dt
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path, all host threads, same schema."""
     rank = int(os.environ.get("RANK", "0"))
@@ -171,6 +227,7 @@ def main():
     ap.add_argument("--workload", default="uber34x3", choices=list(WORKLOADS))
     ap.add_argument("--obs-per-step", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bc", action="store_true", help="skip the BC steps/s measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -247,6 +304,26 @@ def main():
     ms_e2e = timed(step_e2e, args.steps, 3)
     e2e_value = world * frames_per_step * args.steps / (ms_e2e / 1e3)
 
+    # ---- second headline metric: BC train steps/s (all ranks: data parallel, NCCL gradient all-reduce)
+    bc = None
+    if not args.no_bc:
+        bc_steps = max(10, args.steps)
+        v, ms_bc, last_loss = bench_bc(bc_steps, 3, world, dist, host_batches=False)
+        v_e2e, ms_bc_e2e, _ = bench_bc(bc_steps, 3, world, dist, host_batches=True)
+        bc = {"metric": "bc_train_steps_per_sec", "value": v, "unit": "steps/s", "ms_per_step": ms_bc,
+              "scaling": "strong", "steps": bc_steps,
+              "config": {"workload": "PolicyNet((2048,), 3, batch_norm=True) on pre-embedded observations "
+                                     "(BASELINE configs[4]), RMSprop + clip 40, LambdaLR",
+                         "global_batch_rows": BC_CFG["T"] * BC_CFG["B"], "unroll_length": BC_CFG["T"],
+                         "batch_size": BC_CFG["B"], "dataset_rows": BC_CFG["n"],
+                         "parallelism": f"dp{world}: sequences split over ranks, BN sums + gradients all-reduced"},
+              "tflops_effective": v * BC_GFLOP_PER_STEP / 1e3,
+              "frac_of_bf16_sustained": v * BC_GFLOP_PER_STEP / 1e3 / load_peaks()["bf16_sustained"],
+              "e2e": {"value": v_e2e, "unit": "steps/s", "ms_per_step": ms_bc_e2e,
+                      "h2d_bytes_per_step": BC_CFG["T"] * BC_CFG["B"] // world * (BC_CFG["D"] * 4 + 8 + 1),
+                      "d2h_bytes_per_step": 4},
+              "last_loss": last_loss}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -299,6 +376,11 @@ def main():
         cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
                         "sample": f"{n_obs} observations x {n_frames} frames of the same workload, mini-batch 64, "
                                   f"torch CPU fp32 oracle port, {dt:.1f} s"}
+        if bc is not None:
+            v_bc, dt_bc = cpu_port_bc_steps_per_s(threads)
+            bc["cpu_baseline"] = {"value": v_bc, "unit": "steps/s", "cores": threads, "kind": "port",
+                                  "sample": f"1 step at the same shape (T=64, B=128, D=2048), torch CPU fp32 oracle "
+                                            f"port, {dt_bc:.1f} s"}
 
     line = {
         "metric": "pvr_frames_per_sec_embedded", "value": value, "unit": "frames/s", "n_gpus": world,
@@ -317,7 +399,7 @@ def main():
                 "d2h_bytes_per_step": obs_per_step * width * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": args.steps * (1 + enc.n_ops),
         "tflops_effective": value * GFLOP_PER_FRAME[name] / 1e3,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "bc": bc,
     }
     print(json.dumps(line))
     if dist is not None:

@@ -118,6 +118,23 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
   }
 }
 
+// scalar variants for feature counts / pitches that are not multiples of 4
+__global__ void __launch_bounds__(256) bn_apply_scalar_kernel(const float* __restrict__ x, long long ldx, int m, int d,
+                                                               const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd,
+                                                               const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta,
+                                                               __nv_bfloat16* __restrict__ y, long long ldy) {
+  const long long total = (long long)m * d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / d), c = (int)(i - (long long)r * d);
+    const float v = x[(long long)r * ldx + c];
+    const float o = gamma ? (v - mean[c]) * rstd[c] * gamma[c] + beta[c] : v;
+    y[(long long)r * ldy + c] = __float2bfloat16_rn(o);
+  }
+}
+
 // float -> bf16 cast of a (m x d) matrix (policy input without BatchNorm).
 __global__ void __launch_bounds__(256) cast_rows_kernel(const float* __restrict__ x, long long ldx, int m, int d,
                                                          __nv_bfloat16* __restrict__ y, long long ldy) {
@@ -479,15 +496,19 @@ extern "C" int pvr_bn1d_normalize(const float* x, int64_t ldx, int m, int d, con
                                   float* running_mean, float* running_var, float* mean, float* rstd, void* y_bf16,
                                   int64_t ldy, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (!x || m <= 0 || d <= 0 || d % 4 || !sums || !gamma || !beta || !mean || !rstd || !y_bf16 || count <= 0) {
+  if (!x || m <= 0 || d <= 0 || !sums || !gamma || !beta || !mean || !rstd || !y_bf16 || count <= 0) {
     pvr_set_error("pvr_bn1d_normalize: invalid argument");
     return PVR_ERR_ARG;
   }
   bn_finalize_kernel<<<(d + 255) / 256, 256, 0, st>>>(sums, d, count, eps, momentum, running_mean, running_var, mean,
                                                       rstd);
   PVR_LAUNCH_CHECK("pvr_bn1d_normalize(finalize)");
-  bn_apply_kernel<<<148 * 8, 256, 0, st>>>(x, ldx, m, d, mean, rstd, gamma, beta,
-                                           static_cast<__nv_bfloat16*>(y_bf16), ldy);
+  if (d % 4 || ldx % 4 || ldy % 4)
+    bn_apply_scalar_kernel<<<148 * 8, 256, 0, st>>>(x, ldx, m, d, mean, rstd, gamma, beta,
+                                                    static_cast<__nv_bfloat16*>(y_bf16), ldy);
+  else
+    bn_apply_kernel<<<148 * 8, 256, 0, st>>>(x, ldx, m, d, mean, rstd, gamma, beta,
+                                             static_cast<__nv_bfloat16*>(y_bf16), ldy);
   PVR_LAUNCH_CHECK("pvr_bn1d_normalize(apply)");
   return PVR_OK;
 }
@@ -496,27 +517,34 @@ extern "C" int pvr_bn1d_eval(const float* x, int64_t ldx, int m, int d, const fl
                              const float* running_var, float eps, const float* gamma, const float* beta, float* mean,
                              float* rstd, void* y_bf16, int64_t ldy, void* stream_) {
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  if (!x || m <= 0 || d <= 0 || d % 4 || !running_mean || !running_var || !gamma || !beta || !mean || !rstd ||
-      !y_bf16) {
+  if (!x || m <= 0 || d <= 0 || !running_mean || !running_var || !gamma || !beta || !mean || !rstd || !y_bf16) {
     pvr_set_error("pvr_bn1d_eval: invalid argument");
     return PVR_ERR_ARG;
   }
   bn_eval_stats_kernel<<<(d + 255) / 256, 256, 0, st>>>(running_mean, running_var, eps, d, mean, rstd);
   PVR_LAUNCH_CHECK("pvr_bn1d_eval(stats)");
-  bn_apply_kernel<<<148 * 8, 256, 0, st>>>(x, ldx, m, d, mean, rstd, gamma, beta,
-                                           static_cast<__nv_bfloat16*>(y_bf16), ldy);
+  if (d % 4 || ldx % 4 || ldy % 4)
+    bn_apply_scalar_kernel<<<148 * 8, 256, 0, st>>>(x, ldx, m, d, mean, rstd, gamma, beta,
+                                                    static_cast<__nv_bfloat16*>(y_bf16), ldy);
+  else
+    bn_apply_kernel<<<148 * 8, 256, 0, st>>>(x, ldx, m, d, mean, rstd, gamma, beta,
+                                             static_cast<__nv_bfloat16*>(y_bf16), ldy);
   PVR_LAUNCH_CHECK("pvr_bn1d_eval(apply)");
   return PVR_OK;
 }
 
 extern "C" int pvr_cast_rows_bf16(const float* x, int64_t ldx, int m, int d, void* y_bf16, int64_t ldy,
                                   void* stream_) {
-  if (!x || !y_bf16 || m <= 0 || d <= 0 || d % 4) {
+  if (!x || !y_bf16 || m <= 0 || d <= 0) {
     pvr_set_error("pvr_cast_rows_bf16: invalid argument");
     return PVR_ERR_ARG;
   }
-  cast_rows_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(x, ldx, m, d,
-                                                                            static_cast<__nv_bfloat16*>(y_bf16), ldy);
+  if (d % 4 || ldx % 4 || ldy % 4)
+    bn_apply_scalar_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        x, ldx, m, d, nullptr, nullptr, nullptr, nullptr, static_cast<__nv_bfloat16*>(y_bf16), ldy);
+  else
+    cast_rows_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        x, ldx, m, d, static_cast<__nv_bfloat16*>(y_bf16), ldy);
   PVR_LAUNCH_CHECK("pvr_cast_rows_bf16");
   return PVR_OK;
 }

@@ -17,7 +17,8 @@ def test_initial_weights_match_reference_constructor(gold):
     sd = rp.init_policy_state(64, 3, True, 7)
     names = [str(n) for n in gold["fb_param_names"]]
     sums = np.array([float(sd[n].double().sum()) for n in names])
-    np.testing.assert_allclose(sums, gold["fb_param_sums"], rtol=0, atol=1e-9)
+    # orthogonal_ runs a LAPACK QR: the last bits depend on the host CPU / thread count
+    np.testing.assert_allclose(sums, gold["fb_param_sums"], rtol=1e-5, atol=1e-4)
 
 
 def test_forward_backward_matches_reference_module(gold):

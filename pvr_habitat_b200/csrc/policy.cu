@@ -721,14 +721,36 @@ extern "C" int pvr_optim_step(int mode, float* const* params, float* const* grad
 }
 
 // ---------------------------------------------------------------------------------------------- LSTM time loops
-// The T sequential steps of one layer, issued from C so the host cost per step is two kernel launches.
-extern "C" int pvr_lstm_forward(const pvr_lstm_fwd* L, void* stream_) {
-  if (!L || L->T <= 0 || L->B <= 0 || L->H <= 0 || L->H % 64 || !L->w_hh || !L->xp || !L->nd || !L->h0 || !L->c_all ||
-      !L->hm || !L->h_out || !L->gates || !L->g_tmp || !L->h_last) {
-    pvr_set_error("pvr_lstm_forward: invalid argument");
-    return PVR_ERR_ARG;
+// The T sequential steps of one layer are issued from C. The launch sequence of a (layer, shape, buffers) tuple is
+// captured once into a CUDA graph and replayed afterwards: 2T launches become one cudaGraphLaunch (the per-step
+// kernels are a few microseconds each, so per-launch host cost would otherwise bound the step).
+namespace {
+
+struct GraphCacheEntry {
+  unsigned char key[160];
+  size_t key_len;
+  int seen;  // number of eager executions so far (the first run stays eager: lazy one-time attribute setup)
+  cudaGraphExec_t exec;
+};
+GraphCacheEntry g_graphs[32];
+int g_num_graphs = 0;
+
+GraphCacheEntry* graph_lookup(const void* key, size_t len) {
+  for (int i = 0; i < g_num_graphs; ++i)
+    if (g_graphs[i].key_len == len && memcmp(g_graphs[i].key, key, len) == 0) return &g_graphs[i];
+  if (g_num_graphs == 32) {  // recycle everything (shapes changed many times)
+    for (int i = 0; i < 32; ++i)
+      if (g_graphs[i].exec) cudaGraphExecDestroy(g_graphs[i].exec);
+    g_num_graphs = 0;
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  GraphCacheEntry* e = &g_graphs[g_num_graphs++];
+  memset(e, 0, sizeof(*e));
+  memcpy(e->key, key, len);
+  e->key_len = len;
+  return e;
+}
+
+int lstm_forward_issue(const pvr_lstm_fwd* L, cudaStream_t st) {
   const int T = L->T, B = L->B, H = L->H;
   const long long BH = (long long)B * H;
   __nv_bfloat16* hm = static_cast<__nv_bfloat16*>(L->hm);
@@ -741,7 +763,7 @@ extern "C" int pvr_lstm_forward(const pvr_lstm_fwd* L, void* stream_) {
   d.m = B; d.n = 4 * H; d.n_pad = 4 * H; d.k = H; d.out_f32 = 1; d.split_k = 1;
   for (int t = 0; t < T; ++t) {
     d.a = hm + t * BH;
-    int rc = pvr_gemm(&d, stream_);
+    int rc = pvr_gemm(&d, st);
     if (rc != PVR_OK) return rc;
     lstm_cell_fwd_kernel<<<(int)((BH + 255) / 256), 256, 0, st>>>(
         L->g_tmp, L->xp + (long long)t * B * 4 * H, L->c_all + t * BH, L->nd + (long long)t * B,
@@ -752,13 +774,7 @@ extern "C" int pvr_lstm_forward(const pvr_lstm_fwd* L, void* stream_) {
   return PVR_OK;
 }
 
-extern "C" int pvr_lstm_backward(const pvr_lstm_bwd* L, void* stream_) {
-  if (!L || L->T <= 0 || L->B <= 0 || L->H <= 0 || L->H % 64 || !L->w_hh_t || !L->nd || !L->gates || !L->c_all ||
-      !L->dh_rec || !L->dc_rec || !L->dG) {
-    pvr_set_error("pvr_lstm_backward: invalid argument");
-    return PVR_ERR_ARG;
-  }
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+int lstm_backward_issue(const pvr_lstm_bwd* L, cudaStream_t st) {
   const int T = L->T, B = L->B, H = L->H;
   const long long BH = (long long)B * H;
   __nv_bfloat16* dG = static_cast<__nv_bfloat16*>(L->dG);
@@ -775,9 +791,87 @@ extern "C" int pvr_lstm_backward(const pvr_lstm_bwd* L, void* stream_) {
     PVR_LAUNCH_CHECK("pvr_lstm_backward(cell)");
     if (t > 0) {
       d.a = dG + (long long)t * B * 4 * H;
-      int rc = pvr_gemm(&d, stream_);
+      int rc = pvr_gemm(&d, st);
       if (rc != PVR_OK) return rc;
     }
   }
   return PVR_OK;
+}
+
+// Run `issue` through the graph cache: eager the first time a key is seen (and whenever the stream is already being
+// captured by the caller), captured + instantiated the second time, replayed afterwards.
+template <class Desc, class Fn>
+int run_cached(const Desc* L, cudaStream_t st, Fn issue, const char* name) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return issue(L, st);
+  unsigned char key[160];
+  static_assert(sizeof(Desc) + sizeof(cudaStream_t) + sizeof(void*) <= sizeof(key), "graph key too small");
+  memset(key, 0, sizeof(key));
+  memcpy(key, L, sizeof(Desc));
+  memcpy(key + sizeof(Desc), &st, sizeof(st));
+  const void* tag = name;
+  memcpy(key + sizeof(Desc) + sizeof(st), &tag, sizeof(tag));
+  GraphCacheEntry* e = graph_lookup(key, sizeof(Desc) + sizeof(st) + sizeof(tag));
+  if (e->exec) {
+    cudaError_t err = cudaGraphLaunch(e->exec, st);
+    if (err != cudaSuccess) {
+      pvr_set_error("%s: cudaGraphLaunch: %s", name, cudaGetErrorString(err));
+      return PVR_ERR_CUDA;
+    }
+    return PVR_OK;
+  }
+  if (e->seen++ == 0) return issue(L, st);
+  // Capture on a private stream (the caller's may be the legacy default stream, which cannot be captured); the
+  // instantiated graph is then launched on the caller's stream.
+  static cudaStream_t cap = nullptr;
+  if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    return issue(L, st);
+  }
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return issue(L, st);
+  }
+  const int rc = issue(L, cap);
+  cudaError_t err = cudaStreamEndCapture(cap, &graph);
+  if (rc != PVR_OK || err != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != PVR_OK) return rc;
+    return issue(L, st);  // capture unavailable: stay eager
+  }
+  err = cudaGraphInstantiate(&e->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (err != cudaSuccess) {
+    e->exec = nullptr;
+    cudaGetLastError();
+    return issue(L, st);
+  }
+  err = cudaGraphLaunch(e->exec, st);
+  if (err != cudaSuccess) {
+    pvr_set_error("%s: cudaGraphLaunch: %s", name, cudaGetErrorString(err));
+    return PVR_ERR_CUDA;
+  }
+  return PVR_OK;
+}
+
+}  // namespace
+
+extern "C" int pvr_lstm_forward(const pvr_lstm_fwd* L, void* stream_) {
+  if (!L || L->T <= 0 || L->B <= 0 || L->H <= 0 || L->H % 64 || !L->w_hh || !L->xp || !L->nd || !L->h0 || !L->c_all ||
+      !L->hm || !L->h_out || !L->gates || !L->g_tmp || !L->h_last) {
+    pvr_set_error("pvr_lstm_forward: invalid argument");
+    return PVR_ERR_ARG;
+  }
+  return run_cached(L, static_cast<cudaStream_t>(stream_), lstm_forward_issue, "pvr_lstm_forward");
+}
+
+extern "C" int pvr_lstm_backward(const pvr_lstm_bwd* L, void* stream_) {
+  if (!L || L->T <= 0 || L->B <= 0 || L->H <= 0 || L->H % 64 || !L->w_hh_t || !L->nd || !L->gates || !L->c_all ||
+      !L->dh_rec || !L->dc_rec || !L->dG) {
+    pvr_set_error("pvr_lstm_backward: invalid argument");
+    return PVR_ERR_ARG;
+  }
+  return run_cached(L, static_cast<cudaStream_t>(stream_), lstm_backward_issue, "pvr_lstm_backward");
 }

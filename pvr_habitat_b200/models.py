@@ -70,6 +70,7 @@ class _Workspace:
         self.c_all = [z(M + B, H), z(M + B, H)]
         self.g_tmp = z(B, 4 * H)
         self.h_last = [z(B, H), z(B, H)]
+        self.h0 = [z(B, H), z(B, H)]          # persistent copies: stable pointers keep the CUDA-graph cache warm
         self.nd = z(T, B)
         self.logits, self.baseline = z(M, A), z(M)
         self.mean, self.rstd = z(D), z(D)
@@ -241,9 +242,9 @@ class PolicyNet(nn.Module):
         for l in range(2):
             gemm(inp, w["Wih"][l], ws.XP[l], M, 4 * H, H, bias=w["b_l"][l], out_f32=1)
             ws.c_all[l][:B].copy_(c0[l])
-            h0l = h0[l].contiguous()
+            ws.h0[l].copy_(h0[l])
             L = pvr_lstm_fwd(T=T, B=B, H=H, reserved=0, w_hh=w["Whh"][l].data_ptr(), xp=ws.XP[l].data_ptr(),
-                             nd=ws.nd.data_ptr(), h0=h0l.data_ptr(), c_all=ws.c_all[l].data_ptr(),
+                             nd=ws.nd.data_ptr(), h0=ws.h0[l].data_ptr(), c_all=ws.c_all[l].data_ptr(),
                              hm=ws.hm[l].data_ptr(), h_out=ws.HL[l].data_ptr(), gates=ws.gates[l].data_ptr(),
                              g_tmp=ws.g_tmp.data_ptr(), h_last=ws.h_last[l].data_ptr())
             _lib.check(lib.pvr_lstm_forward(ctypes.byref(L), _stream()), "pvr_lstm_forward")

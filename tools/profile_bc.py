@@ -1,0 +1,29 @@
+"""Tiny driver for ncu / timing: a few BC steps at the bench shape. Usage: profile_bc.py STEPS"""
+import os
+import random
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from pvr_habitat_b200.bc import BCTrainer  # noqa: E402
+from pvr_habitat_b200.models import PolicyNet  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
+obs, action, done, _ = bench.bc_dataset()
+torch.manual_seed(1)
+random.seed(1)
+net = PolicyNet((2048,), 3, batch_norm=True).cuda().train()
+tr = BCTrainer(net, obs, action, done, 128, 64, 10 ** 9)
+for _ in range(2):
+    tr.step()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(steps):
+    tr.step()
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+t2 = time.perf_counter()
+print(f"host issue {1e3 * (t1 - t0) / steps:.2f} ms/step, wall {1e3 * (t2 - t0) / steps:.2f} ms/step")

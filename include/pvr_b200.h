@@ -129,15 +129,32 @@ typedef struct pvr_gemm_desc {
   void* out;          /* bf16 or fp32 (m, n), row pitch ldo */
   const float* scale; /* (n_pad) per-column scale or NULL (= 1) */
   const float* bias;  /* (n_pad) per-column bias or NULL (= 0) */
-  const void* res;    /* optional bf16 (m, n), row pitch ldr */
+  const void* res;    /* optional residual (m, n), row pitch ldr: bf16, or fp32 when out_f32 == 1 (may alias out) */
   int64_t lda, ldb, ldo, ldr;
   int32_t m, n, n_pad, k;
   int32_t relu;       /* ReLU on the result */
   int32_t res_mode;   /* 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward against the saved activation) */
   int32_t out_f32;    /* 0: bf16 out; 1: fp32 out; 2: fp32 out, atomically accumulated (out must hold the addend) */
   int32_t split_k;    /* out_f32 == 2 only: number of K slices computed by separate CTAs */
+  int32_t act;        /* 0: none (or `relu`), 1: ReLU, 2: QuickGELU x*sigmoid(1.702x) (bf16 output) */
+  int32_t reserved;
 } pvr_gemm_desc;
 int pvr_gemm(const pvr_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * CLIP-architecture ViT pieces (src/embeddings.py:303-304,375-376 -> openai/CLIP VisionTransformer.forward). The
+ * patch embedding, QKV / projection / MLP matmuls go through pvr_gemm (QuickGELU and the fp32 residual stream are
+ * GEMM epilogues); width must be 768 (ViT-B), head_dim 64.
+ */
+/* y (rows, width) bf16 = LayerNorm(x[r * row_step]) * gamma + beta; x fp32 (row_step = tokens picks the class token). */
+int pvr_layernorm(const float* x, int64_t row_step, int64_t rows, int width, const float* gamma, const float* beta,
+                  float eps, void* y_bf16, void* stream);
+/* x_out (n_img*tokens, width) fp32 = ln_pre([class_embedding | patches] + positional_embedding). */
+int pvr_vit_embed(const void* patches_bf16, const float* cls, const float* pos, int n_img, int tokens, int width,
+                  const float* gamma, const float* beta, float eps, float* x_out, void* stream);
+/* out (n_img*tokens, width) bf16 = softmax(q k^T / sqrt(64)) v per image and head; qkv (n_img*tokens, 3*width) bf16
+ * laid out [q | k | v] with heads contiguous inside each (nn.MultiheadAttention in_proj order). tcgen05 kernel. */
+int pvr_attention(const void* qkv_bf16, int n_img, int tokens, int width, int heads, void* out_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BC policy network pieces (src/models.py:13-89 PolicyNet, main_bc_2.py:206-227 loss / clip / RMSprop).

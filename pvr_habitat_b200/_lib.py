@@ -28,7 +28,8 @@ class pvr_gemm_desc(ctypes.Structure):
                 ("bias", ctypes.c_void_p), ("res", ctypes.c_void_p), ("lda", ctypes.c_int64), ("ldb", ctypes.c_int64),
                 ("ldo", ctypes.c_int64), ("ldr", ctypes.c_int64), ("m", ctypes.c_int32), ("n", ctypes.c_int32),
                 ("n_pad", ctypes.c_int32), ("k", ctypes.c_int32), ("relu", ctypes.c_int32),
-                ("res_mode", ctypes.c_int32), ("out_f32", ctypes.c_int32), ("split_k", ctypes.c_int32)]
+                ("res_mode", ctypes.c_int32), ("out_f32", ctypes.c_int32), ("split_k", ctypes.c_int32),
+                ("act", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 class pvr_lstm_fwd(ctypes.Structure):
@@ -66,6 +67,9 @@ _SIGNATURES = {
     "pvr_encoder_launch_count": (ctypes.c_int, [ctypes.c_void_p]),
     "pvr_encoder_destroy": (None, [ctypes.c_void_p]),
     "pvr_gemm": (ctypes.c_int, [ctypes.POINTER(pvr_gemm_desc), ctypes.c_void_p]),
+    "pvr_layernorm": (ctypes.c_int, [_vp, _i64, _i64, _i, _vp, _vp, _f, _vp, _vp]),
+    "pvr_vit_embed": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp]),
+    "pvr_attention": (ctypes.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "pvr_bn1d_stats": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp]),
     "pvr_bn1d_normalize": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, ctypes.c_double, _f, _f, _vp, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _i64, _vp]),

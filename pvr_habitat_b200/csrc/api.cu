@@ -366,14 +366,15 @@ const float* unit_vector(bool ones) {
 
 extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   if (!d || !d->a || !d->b || !d->out || d->m <= 0 || d->n <= 0 || d->n > d->n_pad || d->n_pad % 32 || d->k <= 0 ||
-      d->k % 64 || d->lda % 8 || d->ldb % 8 || (d->res && d->ldr % 8) || d->n_pad > 16384 || d->out_f32 < 0 ||
+      d->k % 64 || d->lda % 8 || d->ldb % 8 || (d->res && !d->out_f32 && d->ldr % 8) || d->n_pad > 16384 || d->out_f32 < 0 ||
       d->out_f32 > 2 || (d->out_f32 ? d->ldo % 4 : d->ldo % 8)) {
     pvr_set_error("pvr_gemm: invalid argument");
     return PVR_ERR_ARG;
   }
   const int split_k = d->split_k > 1 ? d->split_k : 1;
-  if ((split_k > 1 && d->out_f32 != 2) || (d->k / 64) % split_k || (d->out_f32 && d->res)) {
-    pvr_set_error("pvr_gemm: split_k needs out_f32 == 2 and must divide k/64; fp32 output takes no residual");
+  if ((split_k > 1 && d->out_f32 != 2) || (d->k / 64) % split_k || (d->out_f32 == 2 && d->res) ||
+      (d->out_f32 == 1 && d->res && (d->ldr % 4 || d->res_mode != 0))) {
+    pvr_set_error("pvr_gemm: split_k needs out_f32 == 2 and must divide k/64; fp32 residuals only with out_f32 == 1");
     return PVR_ERR_ARG;
   }
   const int sms = device_sm_count();
@@ -393,10 +394,11 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   p.split_k = split_k;
   p.num_k_chunks = d->k / 64 / split_k;
   p.n_valid = d->n;
-  p.relu_n = d->relu ? d->n : 0;
+  p.relu_n = (d->relu || d->act == 1) ? d->n : 0;
   p.ldo = d->ldo;
   p.ldr = d->ldr;
   p.res_mode = d->res_mode;
+  p.quick_gelu = d->act == 2;
   p.out_is_f32 = d->out_f32 != 0;
   p.out = static_cast<__nv_bfloat16*>(d->out);
   p.out_f32 = static_cast<float*>(d->out);
@@ -429,7 +431,9 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
       pvr_set_error("pvr_gemm: fp32 output needs n %% 32 == 0 and n_pad %% 64 == 0");
       return PVR_ERR_ARG;
     }
-    if (!pvr::make_tmap_2d_f32(&to, d->out, (uint64_t)d->n, (uint64_t)d->m, (uint64_t)d->ldo, 128, &err)) {
+    p.has_res = d->res != nullptr;  // fp32 residual (same layout as the output; in place allowed)
+    if (!pvr::make_tmap_2d_f32(&to, d->out, (uint64_t)d->n, (uint64_t)d->m, (uint64_t)d->ldo, 128, &err) ||
+        (d->res && !pvr::make_tmap_2d_f32(&tr, d->res, (uint64_t)d->n, (uint64_t)d->m, (uint64_t)d->ldr, 128, &err))) {
       pvr_set_error("pvr_gemm: %s", err);
       return PVR_ERR_CUDA;
     }

@@ -260,7 +260,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int c = 0; c < SUBS; ++c, ++q) {
           const uint32_t s = q % NB, ph = (q / NB) & 1;
           mbar_wait(&eb_empty_bar[s], ph ^ 1);
-          if (!OUT_F32 && p.has_res) {
+          if (p.has_res) {
             mbar_expect_tx(&eb_full_bar[s], EPI_TILE_BYTES);
             tma_load_2d(&tmap_res, &eb_full_bar[s], sEB + s * EPI_TILE_BYTES,
                         p.res_coff + n_tile * BLOCK_N + c * EPI_COLS, m_tile * BLOCK_M);
@@ -327,6 +327,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               f[4 * jj + 3] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 3]), __uint_as_float(s4.w), __uint_as_float(b4.w));
             }
             if (OUT_F32) {
+              if (p.has_res) {  // fp32 residual stream (ViT): out = res + acc * scale + bias, may be in place
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const uint4 rv = ld_shared_v4(eb_row + ((jj ^ swz) << 4));
+                  f[4 * jj + 0] += __uint_as_float(rv.x);
+                  f[4 * jj + 1] += __uint_as_float(rv.y);
+                  f[4 * jj + 2] += __uint_as_float(rv.z);
+                  f[4 * jj + 3] += __uint_as_float(rv.w);
+                }
+              }
               relu_cols(f, n, p.relu_n);
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {  // 32 fp32 = 8 x 16 B = one swizzled 128-byte row
@@ -347,6 +357,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 }
               }
               relu_cols(f, n + h * 32, p.relu_n);
+              if (p.quick_gelu) {  // CLIP's QuickGELU: x * sigmoid(1.702 x)
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) f[jj] = f[jj] / (1.f + __expf(-1.702f * f[jj]));
+              }
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {
                 uint4 ov;

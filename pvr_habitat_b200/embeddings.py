@@ -13,6 +13,7 @@ from torch import nn
 
 from . import _lib
 from . import program as prg
+from .vision_models import clip_vit
 from .vision_models.moco import moco_conv3_compressed, moco_conv4_compressed, moco_conv5
 from .vision_models.resnet import resnet_conv3_compressed, resnet_conv4_compressed, resnet_conv5
 from .vision_models.resnet_params import ResNet50Params
@@ -42,11 +43,15 @@ class Transforms(nn.Module):
     def __init__(self, mean=IMAGENET_MEAN, std=IMAGENET_STD, size=256, crop=224):
         super().__init__()
         self.mean, self.std, self.size, self.crop = list(mean), list(std), size, crop
+        self.identity_resize_only = False  # CLIP: bicubic antialiased Resize is only supported when it is a no-op
 
     def run(self, obs_nhwc_u8, n_frames, out_ptr, fmt, sample_major):
         """obs: CUDA uint8 (N, H, W, 3*n_frames) contiguous; writes n_frames*N images at `out_ptr`."""
         n, h, w, ch = obs_nhwc_u8.shape
         assert ch == 3 * n_frames and obs_nhwc_u8.dtype == torch.uint8 and obs_nhwc_u8.is_contiguous()
+        if self.identity_resize_only and (h != self.size or w != self.size):
+            raise NotImplementedError(f"CLIP preprocessing of {h}x{w} frames needs the antialiased bicubic resize; "
+                                      f"only {self.size}x{self.size} frames (identity resize) are supported")
         rh, rw, top, left = resize_geometry(h, w, self.size, self.crop)
         mean = (ctypes.c_float * 3)(*self.mean)
         std = (ctypes.c_float * 3)(*self.std)
@@ -129,10 +134,23 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
                 taps not in ('345', '35', '34', '45'):
             raise NotImplementedError("Requested model not available.")
         model = UberModel([_get_embedding(base + _UBER_PARTS[t])[0] for t in taps])
+    elif 'clip' in embedding_name:
+        # src/embeddings.py:298-314: clip.load("ViT-B/32") + CLIP's own normalisation. Resize(224, bicubic) and
+        # CenterCrop(224) are the identity for the 224x224 frames of the north-star configs; other sizes would need
+        # the antialiased bicubic resize and are rejected at call time.
+        if embedding_name == 'clip_vit':
+            model, _ = clip_vit.load("ViT-B/32", device='cpu')
+        elif embedding_name == 'clip_vit_b16':  # BASELINE configs[2] geometry (CLIP block structure, patch 16)
+            model, _ = clip_vit.load("ViT-B/16", device='cpu')
+        else:
+            raise NotImplementedError("Requested model not available.")
+        transforms = Transforms(CLIP_MEAN, CLIP_STD, size=model.visual.input_resolution,
+                                crop=model.visual.input_resolution)
+        transforms.identity_resize_only = True
     elif embedding_name == 'true_state':
         return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
     else:
-        # 'random', 'clip_vit', mae_*, resnet18/34, clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
+        # 'random', mae_*, resnet18/34, clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
         raise NotImplementedError("Requested model not available.")
 
     if train:
@@ -197,7 +215,11 @@ class EmbeddingNet(nn.Module):
     def encoder(self):
         self._require_cuda()
         if self._encoder is None:
-            self._encoder = build_encoder(self.embedding, self.device, self.transforms.crop)
+            if isinstance(self.embedding, clip_vit.CLIPImageModel):
+                self.embedding.invalidate()
+                self._encoder = self.embedding.runner(self.device)
+            else:
+                self._encoder = build_encoder(self.embedding, self.device, self.transforms.crop)
         return self._encoder
 
     def preprocess(self, observation):
@@ -222,7 +244,8 @@ class EmbeddingNet(nn.Module):
         n = obs.shape[0]
         enc = self.encoder()
         enc.bind(n * n_frames)
-        self.transforms.run(obs, n_frames, enc.slot0, _lib.PVR_FMT_STEM_BF16, True)
+        fmt = _lib.PVR_FMT_NHWC4_BF16 if isinstance(enc, clip_vit.ViTRunner) else _lib.PVR_FMT_STEM_BF16
+        self.transforms.run(obs, n_frames, enc.slot0, fmt, True)
         if out is None:
             out = torch.empty(n, n_frames * self.out_size, dtype=torch.float32, device=self.device)
         enc.forward(out, self.out_size)

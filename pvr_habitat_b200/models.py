@@ -39,7 +39,7 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def gemm(a, b, out, m, n, k, bias=None, relu=False, res=None, res_mode=0, out_f32=0, split_k=1, n_pad=None):
+def gemm(a, b, out, m, n, k, bias=None, relu=False, res=None, res_mode=0, out_f32=0, split_k=1, n_pad=None, act=0):
     """out (m x n) = epilogue(a (m x k) @ b (n x k)^T); a, b bf16 row-major with K contiguous."""
     d = pvr_gemm_desc()
     d.a, d.lda = a.data_ptr(), a.stride(0)
@@ -49,7 +49,7 @@ def gemm(a, b, out, m, n, k, bias=None, relu=False, res=None, res_mode=0, out_f3
     d.bias = bias.data_ptr() if bias is not None else None
     d.res, d.ldr = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
     d.m, d.n, d.n_pad, d.k = m, n, n_pad if n_pad is not None else b.shape[0], k
-    d.relu, d.res_mode, d.out_f32, d.split_k = int(relu), res_mode, out_f32, split_k
+    d.relu, d.res_mode, d.out_f32, d.split_k, d.act = int(relu), res_mode, out_f32, split_k, act
     _lib.check(_lib.lib().pvr_gemm(ctypes.byref(d), _stream()), "pvr_gemm")
 
 

@@ -1,0 +1,228 @@
+"""CLIP-architecture ViT-B image encoder — drop-in for what the reference gets from `clip.load("ViT-B/32")`
+(src/embeddings.py:298-314) and calls through `encode_image` (src/embeddings.py:375-376).
+
+The parameter container uses openai/CLIP's key names (`visual.conv1.weight`, `visual.class_embedding`,
+`visual.transformer.resblocks.N.attn.in_proj_weight`, ..., `visual.proj`) so CLIP checkpoints interchange; the text
+tower is not on the path and is not instantiated. The forward runs in libpvr_b200: patch embedding as an implicit GEMM
+straight from the NHWC4 frames (im2col TMA: one "pixel" = one patch row), fused token assembly + ln_pre, LayerNorm,
+tcgen05 attention, tcgen05 GEMMs with bias / QuickGELU / fp32-residual epilogues.
+"""
+import ctypes
+import os
+
+import torch
+from torch import nn
+
+from .. import _lib
+from .. import program as prg
+from ..models import gemm
+from .moco import _ALLOW_RANDOM_INIT
+
+_CONFIGS = {"ViT-B/32": 32, "ViT-B/16": 16}
+
+
+class _LN(nn.Module):
+    def __init__(self, w):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(w))
+        self.bias = nn.Parameter(torch.zeros(w))
+
+
+class _Lin(nn.Module):
+    def __init__(self, i, o, std):
+        super().__init__()
+        self.weight = nn.Parameter(torch.randn(o, i) * std)
+        self.bias = nn.Parameter(torch.zeros(o))
+
+
+class _Attn(nn.Module):
+    def __init__(self, w, attn_std, proj_std):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.randn(3 * w, w) * attn_std)
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * w))
+        self.out_proj = _Lin(w, w, proj_std)
+
+
+class _MLP(nn.Module):
+    def __init__(self, w, fc_std, proj_std):
+        super().__init__()
+        self.c_fc = _Lin(w, 4 * w, fc_std)
+        self.c_proj = _Lin(4 * w, w, proj_std)
+
+
+class _Block(nn.Module):
+    def __init__(self, w, attn_std, proj_std, fc_std):
+        super().__init__()
+        self.attn = _Attn(w, attn_std, proj_std)
+        self.ln_1 = _LN(w)
+        self.mlp = _MLP(w, fc_std, proj_std)
+        self.ln_2 = _LN(w)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, w, layers):
+        super().__init__()
+        proj_std = (w ** -0.5) * ((2 * layers) ** -0.5)  # CLIP.initialize_parameters
+        self.resblocks = nn.Sequential(*[_Block(w, w ** -0.5, proj_std, (2 * w) ** -0.5) for _ in range(layers)])
+
+
+class _Conv1(nn.Module):
+    def __init__(self, w, patch):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(w, 3, patch, patch))
+        nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+
+
+class VisionTransformerParams(nn.Module):
+    def __init__(self, input_resolution=224, patch_size=32, width=768, layers=12, heads=12, output_dim=512):
+        super().__init__()
+        assert width == 768 and heads * 64 == width, "libpvr_b200 ViT kernels are built for ViT-B (width 768)"
+        self.input_resolution, self.patch_size, self.width = input_resolution, patch_size, width
+        self.layers, self.heads, self.output_dim = layers, heads, output_dim
+        scale = width ** -0.5
+        self.conv1 = _Conv1(width, patch_size)
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = _LN(width)
+        self.transformer = _Transformer(width, layers)
+        self.ln_post = _LN(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+
+
+class CLIPImageModel(nn.Module):
+    """`clip.load(...)[0]` as far as the reference uses it: `.visual.input_resolution`, `.encode_image(x)`,
+    `.parameters()`, `.eval()`, `.to()`."""
+
+    def __init__(self, name="ViT-B/32"):
+        super().__init__()
+        self.name = name
+        self.visual = VisionTransformerParams(patch_size=_CONFIGS[name])
+        self.out_size = self.visual.output_dim
+        self._runner = None
+
+    def invalidate(self):
+        self._runner = None
+
+    def runner(self, device):
+        if self._runner is None or self._runner.device != torch.device(device):
+            self._runner = ViTRunner(self.visual, device)
+        return self._runner
+
+
+def load(name, device="cpu", checkpoint_path=None):
+    """Stand-in for `clip.load(name, device)`: returns (model, None). openai's checkpoints are downloaded TorchScript
+    archives; offline a state_dict file may be given, otherwise (inside `allow_random_init()`) the weights stay at
+    CLIP's random initialisation."""
+    if name not in _CONFIGS:
+        raise NotImplementedError("Requested model not available.")
+    model = CLIPImageModel(name)
+    path = checkpoint_path or (name.replace("/", "-") + ".pt")
+    if os.path.isfile(path):
+        sd = torch.load(path, map_location="cpu")
+        sd = {k: v for k, v in sd.items() if k.startswith("visual.")}
+        model.load_state_dict(sd, strict=True)
+    elif not _ALLOW_RANDOM_INIT[-1]:
+        raise FileNotFoundError(f"CLIP checkpoint {path} not found (no network access to download it)")
+    return model.to(device), None
+
+
+def pack_patch_weight(w):
+    """(width, 3, p, p) -> bf16 (width, p * p * 4): K ordered (patch row, pixel, channel padded to 4)."""
+    co, ci, p, _ = w.shape
+    out = torch.zeros(co, p, p, 4, dtype=torch.float32)
+    out[..., :3] = w.permute(0, 2, 3, 1)
+    return out.reshape(co, p * p * 4).to(torch.bfloat16)
+
+
+class ViTRunner:
+    """Device state (bf16 weights, buffers) + the launch sequence of one CLIP ViT-B image encoder."""
+
+    def __init__(self, vis, device):
+        self.device = torch.device(device)
+        self.lib = _lib.lib()
+        self.p, self.W, self.L, self.heads, self.O = vis.patch_size, vis.width, vis.layers, vis.heads, vis.output_dim
+        self.res = vis.input_resolution
+        self.grid = self.res // self.p
+        self.S = self.grid * self.grid + 1
+        dev, bf = self.device, torch.bfloat16
+        f = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+        b = lambda t: t.detach().to(dev, bf).contiguous()  # noqa: E731
+        # Patch embedding as a conv op of the encoder program. TMA traversal strides stop at 8, so the stride-p conv
+        # is expressed on a reshaped view of the NHWC4 frames: (N*grid, p, grid, p*4) = (patch row, row inside the
+        # patch, patch column, one patch row of pixels). One "image" of the program is one row of patches, the filter
+        # is p x 1 taps over the "row inside the patch" axis and every stride is 1.
+        prog = prg.Program()
+        cpp = self.p * 4
+        self.in_slot = prog.new_slot(self.p * self.grid * cpp)
+        self.patch_slot = prog.conv(self.in_slot, (cpp, self.p, self.grid),
+                                    pack_patch_weight(vis.conv1.weight.detach().cpu().float()), self.p * cpp, self.W,
+                                    self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), torch.zeros(self.W), 0,
+                                    flops=2 * self.grid * self.W * 3 * self.p * self.p)
+        prog.emb_width = 1
+        self.patch_enc = prog.finish(dev)
+        self.cls, self.pos = f(vis.class_embedding), f(vis.positional_embedding)
+        self.ln_pre = (f(vis.ln_pre.weight), f(vis.ln_pre.bias))
+        self.ln_post = (f(vis.ln_post.weight), f(vis.ln_post.bias))
+        self.blocks = []
+        for blk in vis.transformer.resblocks:
+            self.blocks.append(dict(
+                ln1=(f(blk.ln_1.weight), f(blk.ln_1.bias)), ln2=(f(blk.ln_2.weight), f(blk.ln_2.bias)),
+                wqkv=b(blk.attn.in_proj_weight), bqkv=f(blk.attn.in_proj_bias),
+                wo=b(blk.attn.out_proj.weight), bo=f(blk.attn.out_proj.bias),
+                w1=b(blk.mlp.c_fc.weight), b1=f(blk.mlp.c_fc.bias),
+                w2=b(blk.mlp.c_proj.weight), b2=f(blk.mlp.c_proj.bias)))
+        self.proj_t = b(vis.proj.t())  # (output_dim, width): K-major B operand
+        self.n = 0
+        self.flops_per_image = (2 * self.grid ** 2 * self.W * 3 * self.p ** 2
+                                + self.L * (2 * self.S * self.W * 12 * self.W + 4 * self.S * self.S * self.W)
+                                + 2 * self.W * self.O)
+
+    def bind(self, n):
+        if n == self.n:
+            return
+        dev, bf, M, W = self.device, torch.bfloat16, n * self.S, self.W
+        self.patch_enc.bind(n * self.grid)
+        self.x = torch.empty(M, W, dtype=torch.float32, device=dev)
+        self.y = torch.empty(M, W, dtype=bf, device=dev)
+        self.qkv = torch.empty(M, 3 * W, dtype=bf, device=dev)
+        self.att = torch.empty(M, W, dtype=bf, device=dev)
+        self.h = torch.empty(M, 4 * W, dtype=bf, device=dev)
+        self.clsy = torch.empty(n, W, dtype=bf, device=dev)
+        self.dummy = torch.zeros(n * self.grid, 1, device=dev)
+        self.n = n
+
+    @property
+    def slot0(self):
+        return self.patch_enc.slot0
+
+    def launches_per_forward(self):
+        return 2 + 7 * self.L + 2
+
+    def forward(self, out, out_ld=None):
+        """Frames must already be in slot0 (NHWC4 bf16). Writes (n, output_dim) fp32 rows into `out`."""
+        lib, n, S, W, M = self.lib, self.n, self.S, self.W, self.n * self.S
+        st = _lib.current_stream_ptr
+        with torch.cuda.device(self.device):
+            self.patch_enc.forward(self.dummy, 1)
+            patches = self.patch_enc.slot_ptr(self.patch_slot)
+            _lib.check(lib.pvr_vit_embed(patches, self.cls.data_ptr(), self.pos.data_ptr(), n, S, W,
+                                         self.ln_pre[0].data_ptr(), self.ln_pre[1].data_ptr(), 1e-5,
+                                         self.x.data_ptr(), st()), "pvr_vit_embed")
+            for blk in self.blocks:
+                _lib.check(lib.pvr_layernorm(self.x.data_ptr(), 1, M, W, blk["ln1"][0].data_ptr(),
+                                             blk["ln1"][1].data_ptr(), 1e-5, self.y.data_ptr(), st()), "pvr_layernorm")
+                gemm(self.y, blk["wqkv"], self.qkv, M, 3 * W, W, bias=blk["bqkv"])
+                _lib.check(lib.pvr_attention(self.qkv.data_ptr(), n, S, W, self.heads, self.att.data_ptr(), st()),
+                           "pvr_attention")
+                gemm(self.att, blk["wo"], self.x, M, W, W, bias=blk["bo"], res=self.x, out_f32=1)
+                _lib.check(lib.pvr_layernorm(self.x.data_ptr(), 1, M, W, blk["ln2"][0].data_ptr(),
+                                             blk["ln2"][1].data_ptr(), 1e-5, self.y.data_ptr(), st()), "pvr_layernorm")
+                gemm(self.y, blk["w1"], self.h, M, 4 * W, W, bias=blk["b1"], act=2)
+                gemm(self.h, blk["w2"], self.x, M, W, 4 * W, bias=blk["b2"], res=self.x, out_f32=1)
+            _lib.check(lib.pvr_layernorm(self.x.data_ptr(), S, n, W, self.ln_post[0].data_ptr(),
+                                         self.ln_post[1].data_ptr(), 1e-5, self.clsy.data_ptr(), st()), "pvr_layernorm")
+            d = _lib.pvr_gemm_desc()
+            d.a, d.lda, d.b, d.ldb = self.clsy.data_ptr(), W, self.proj_t.data_ptr(), W
+            d.out, d.ldo = out.data_ptr(), out_ld if out_ld is not None else out.stride(0)
+            d.m, d.n, d.n_pad, d.k, d.out_f32, d.split_k = n, self.O, self.O, W, 1, 1
+            _lib.check(lib.pvr_gemm(ctypes.byref(d), st()), "pvr_gemm")

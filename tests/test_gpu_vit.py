@@ -1,0 +1,100 @@
+"""-m gpu: CLIP ViT-B kernels and the whole image encoder against the oracle (oracle/restate_vit.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, restate_vit as rv
+from pvr_habitat_b200 import _lib, models
+from pvr_habitat_b200.embeddings import EmbeddingNet
+from pvr_habitat_b200.vision_models.moco import allow_random_init
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().flatten().cpu(), b.double().flatten().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def test_layernorm_kernel():
+    g = torch.Generator().manual_seed(0)
+    x = (torch.randn(1000, 768, generator=g) * 3 + 1).cuda()
+    w, b = torch.randn(768, generator=g).cuda(), torch.randn(768, generator=g).cuda()
+    y = torch.empty(1000, 768, dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().pvr_layernorm(x.data_ptr(), 1, 1000, 768, w.data_ptr(), b.data_ptr(), 1e-5, y.data_ptr(),
+                                        _lib.current_stream_ptr()))
+    ref = torch.nn.functional.layer_norm(x, (768,), w, b, 1e-5)
+    assert rel(y.float(), ref) < 3e-3  # bf16 output rounding only
+    # strided rows (class-token gather)
+    y2 = torch.empty(100, 768, dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().pvr_layernorm(x.data_ptr(), 10, 100, 768, w.data_ptr(), b.data_ptr(), 1e-5, y2.data_ptr(),
+                                        _lib.current_stream_ptr()))
+    assert torch.equal(y2, y[::10])
+
+
+@pytest.mark.parametrize("tokens,n_img", [(197, 3), (50, 5), (128, 2), (16, 1)])
+def test_attention_kernel_vs_fp32(tokens, n_img):
+    g = torch.Generator().manual_seed(tokens)
+    qkv = torch.randn(n_img * tokens, 3 * 768, generator=g).bfloat16().cuda()
+    out = torch.full((n_img * tokens, 768), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(_lib.lib().pvr_attention(qkv.data_ptr(), n_img, tokens, 768, 12, out.data_ptr(),
+                                        _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    q, k, v = (t.float().reshape(n_img, tokens, 12, 64).transpose(1, 2) for t in qkv.chunk(3, -1))
+    ref = (torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v).transpose(1, 2).reshape(n_img * tokens, 768)
+    assert not torch.isnan(out.float()).any()
+    assert rel(out.float(), ref) < 1e-2  # probabilities and output rounded to bf16
+
+
+def test_gemm_quick_gelu_and_fp32_residual_in_place():
+    g = torch.Generator().manual_seed(9)
+    m, k = 777, 768
+    a = torch.randn(m, k, generator=g).bfloat16().cuda()
+    w1 = (torch.randn(3072, k, generator=g) / k ** 0.5).bfloat16().cuda()
+    b1 = torch.randn(3072, generator=g).cuda()
+    h = torch.empty(m, 3072, dtype=torch.bfloat16, device="cuda")
+    models.gemm(a, w1, h, m, 3072, k, bias=b1, act=2)
+    pre = a.float() @ w1.float().t() + b1
+    assert rel(h.float(), pre * torch.sigmoid(1.702 * pre)) < 4e-3
+    w2 = (torch.randn(768, 3072, generator=g) / 3072 ** 0.5).bfloat16().cuda()
+    b2 = torch.randn(768, generator=g).cuda()
+    x = torch.randn(m, 768, generator=g).cuda()
+    ref = x + h.float() @ w2.float().t() + b2
+    models.gemm(h, w2, x, m, 768, 3072, bias=b2, res=x, out_f32=1)  # in place on the fp32 residual stream
+    assert rel(x, ref) < 1e-5
+
+
+def make_clip(name, patch, seed):
+    with allow_random_init():
+        net = EmbeddingNet(name)
+    sd = rv.vit_state(patch, seed)
+    net.embedding.load_state_dict(sd, strict=True)
+    net.invalidate()
+    return net, sd
+
+
+@pytest.mark.parametrize("name,patch", [("clip_vit", 32), ("clip_vit_b16", 16)])
+def test_clip_embedding_vs_oracle(name, patch):
+    """north star: bf16 embeddings within relative L2 <= 1e-2 and cosine >= 0.999 of the fp32 reference path."""
+    net, sd = make_clip(name, patch, 5)
+    assert net.out_size == 512 and tuple(net.in_shape) == (3, 224, 224)
+    frames = restate.structured_frames(5, 224, 224, 3, 41)
+    got = net(torch.from_numpy(frames))
+    assert got.shape == (5, 512) and got.dtype == np.float32
+    ref = rv.embedding_forward(sd, frames)
+    g, r = got.astype(np.float64), ref.astype(np.float64)
+    relerr = np.linalg.norm(g - r) / np.linalg.norm(r)
+    cos = (g * r).sum(1) / (np.linalg.norm(g, axis=1) * np.linalg.norm(r, axis=1))
+    assert relerr <= 1e-2 and cos.min() >= 0.999, (relerr, cos.min())
+    # batch-composition independence (ragged M tails) and 2-frame observations through the fused path
+    one = net(torch.from_numpy(frames[:1]))
+    assert one.shape == (512,) and np.array_equal(one, got[0])
+    obs2 = np.concatenate([frames[:2], frames[2:4]], axis=3)
+    two = net.embed(torch.from_numpy(obs2), 2).cpu().numpy()
+    assert np.array_equal(two[:, :512], got[:2]) and np.array_equal(two[:, 512:], got[2:4])
+
+
+def test_clip_rejects_non_identity_resize():
+    net, _ = make_clip("clip_vit", 32, 5)
+    with pytest.raises(NotImplementedError, match="antialiased bicubic"):
+        net(torch.zeros(1, 64, 64, 3, dtype=torch.uint8))

@@ -35,9 +35,13 @@ WORKLOADS = {
     # name: (embedding name, frames per observation, observations per step per GPU)
     "uber34x3": ("moco_aug_uber_34", 3, 96),
     "conv5": ("moco_aug", 1, 256),
+    "clip_b16": ("clip_vit_b16", 1, 1024),  # BASELINE configs[2]: CLIP-architecture ViT-B/16, batch 1024 per GPU
+    "clip_b32": ("clip_vit", 1, 1024),      # the reference's actual `clip_vit` (ViT-B/32)
 }
 VARIANTS = {"moco_aug": ["conv5"], "moco_aug_uber_34": ["l3", "l4"]}
-GFLOP_PER_FRAME = {"moco_aug": 8.174, "moco_aug_uber_34": 14.96}  # SURVEY.md §8(d), convs only
+CLIP_PATCH = {"clip_vit_b16": 16, "clip_vit": 32}
+GFLOP_PER_FRAME = {"moco_aug": 8.174, "moco_aug_uber_34": 14.96,  # SURVEY.md §8(d), convs only
+                   "clip_vit_b16": 35.13, "clip_vit": 8.818}
 
 
 def load_peaks():
@@ -99,7 +103,19 @@ def make_observations(n, n_frames, seed):
 
 def oracle_parts(name, seed=1):
     from oracle import restate
+    if name in CLIP_PATCH:
+        from oracle import restate_vit
+        return restate_vit.vit_state(CLIP_PATCH[name], seed)
     return [(v, restate.resnet50_state(v, seed + i)) for i, v in enumerate(VARIANTS[name])]
+
+
+def oracle_embed(name, parts, obs):
+    """CPU port of the embedding loop (mini-batches of 64 like main_bc_1.py:130)."""
+    from oracle import restate
+    if name in CLIP_PATCH:
+        from oracle import restate_vit
+        return np.concatenate([restate_vit.embedding_forward(parts, obs[i:i + 64]) for i in range(0, len(obs), 64)])
+    return restate.embed_observations(parts, obs, batch_size=64)
 
 
 def build_net(name, device):
@@ -107,6 +123,10 @@ def build_net(name, device):
     from pvr_habitat_b200.vision_models.moco import allow_random_init
     with allow_random_init():
         net = EmbeddingNet(name)
+    if name in CLIP_PATCH:
+        net.embedding.load_state_dict(oracle_parts(name), strict=True)
+        net.invalidate()
+        return net
     parts = net.embedding.models if hasattr(net.embedding, "models") else [net.embedding]
     for m, (v, sd) in zip(parts, oracle_parts(name)):
         m.load_state_dict(sd, strict=True)
@@ -120,9 +140,9 @@ def cpu_port_frames_per_s(name, n_frames, n_obs, threads):
     torch.set_num_threads(threads)
     parts = oracle_parts(name)
     obs = make_observations(n_obs, n_frames, 5)
-    restate.embed_observations(parts, obs[:2], batch_size=64)  # warm-up
+    oracle_embed(name, parts, obs[:2])  # warm-up
     t0 = time.perf_counter()
-    restate.embed_observations(parts, obs, batch_size=64)  # mini-batches of 64 like main_bc_1.py:130
+    oracle_embed(name, parts, obs)
     dt = time.perf_counter() - t0
     return n_obs * n_frames / dt, dt
 
@@ -196,10 +216,10 @@ def run_reference(args):
     per_step = 8  # observations per step: bounded so that K steps end within minutes
     obs = make_observations(per_step, n_frames, 5)
     for _ in range(max(1, min(args.warmup, 1))):
-        restate.embed_observations(parts, obs[:2], batch_size=64)
+        oracle_embed(name, parts, obs[:2])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        restate.embed_observations(parts, obs, batch_size=64)
+        oracle_embed(name, parts, obs)
     dt = time.perf_counter() - t0
     v = args.steps * per_step * n_frames / dt
     line = {
@@ -332,6 +352,31 @@ def main():
     # ---- per-kernel roofline (rank 0): CUDA events between ops on the launch stream
     enc = net.encoder()
     peaks = load_peaks()
+    if name in CLIP_PATCH:
+        # ViT: GEMM-dominated; the whole encoder forward (GEMMs + LayerNorm + attention) is timed as one unit
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        net.transforms.run(dev[0], n_frames, enc.slot0, 1, True)
+        enc.forward(out, net.out_size)
+        e0.record()
+        for r in range(3):
+            enc.forward(out, net.out_size)
+        e1.record()
+        torch.cuda.synchronize()
+        fwd_ms = e0.elapsed_time(e1) / 3
+        achieved = enc.flops_per_image * frames_per_step / (fwd_ms / 1e3) / 1e12
+        roofline = {"kernel": "ViT-B encoder forward: conv_gemm_kernel (tcgen05 GEMMs) + vit_attention_kernel + LayerNorm",
+                    "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+                    "peak_source": peaks["source"] + ", sustained bf16",
+                    "algorithmic_gflop_per_frame": enc.flops_per_image / 1e9, "forward_ms_per_step": fwd_ms}
+        n_launch = 1 + enc.launches_per_forward()
+    else:
+        roofline, n_launch = resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks, ms, args)
+    return finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_step, width, n_rot,
+                  bytes_per_batch, value, ms, e2e_value, ms_e2e, clocks, roofline, n_launch, bc)
+
+
+def resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks, ms, args):
     conv_ms, conv_flops, other_ms = [], 0.0, []
     reps = 5
     for r in range(reps + 1):
@@ -367,11 +412,15 @@ def main():
                        "frac": pre_bytes / (pre_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
                        "algorithmic_bytes_per_frame": 224 * 224 * 3 + 224 * 112 * 64},
     }
+    return roofline, 1 + enc.n_ops
 
+
+def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_step, width, n_rot, bytes_per_batch,
+           value, ms, e2e_value, ms_e2e, clocks, roofline, n_launch, bc):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_obs = 24 if n_frames == 3 else 96
+        n_obs = 24 if n_frames == 3 else (32 if name == "clip_vit_b16" else 96)
         v, dt = cpu_port_frames_per_s(name, n_frames, n_obs, threads)
         cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
                         "sample": f"{n_obs} observations x {n_frames} frames of the same workload, mini-batch 64, "
@@ -389,7 +438,9 @@ def main():
         "config": {
             "workload": (f"{name}: ResNet-50 MoCo layer3+layer4 compressed taps (2 trunks), {n_frames}-frame "
                          "224x224 uint8 observations, random-init weights (BASELINE configs[1])")
-            if args.workload == "uber34x3" else f"{name}: ResNet-50 conv5, 224x224 uint8 frames, random-init weights",
+            if args.workload == "uber34x3" else
+            (f"{name}: CLIP-architecture ViT-B/{CLIP_PATCH[name]}, 224x224 uint8 frames, random-init weights"
+             if name in CLIP_PATCH else f"{name}: ResNet-50 conv5, 224x224 uint8 frames, random-init weights"),
             "obs_per_step_per_gpu": obs_per_step, "frames_per_step_per_gpu": frames_per_step,
             "embedding_width": width, "sharding": "observations split over ranks, no data-path collective",
             "l2": f"inputs rotate over {n_rot} distinct batches ({n_rot * bytes_per_batch / 2**20:.0f} MiB > 126 MB L2); "
@@ -397,7 +448,7 @@ def main():
         },
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": bytes_per_batch,
                 "d2h_bytes_per_step": obs_per_step * width * 4, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": args.steps * (1 + enc.n_ops),
+        "gpu_launches": args.steps * n_launch,
         "tflops_effective": value * GFLOP_PER_FRAME[name] / 1e3,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "bc": bc,
     }

@@ -56,9 +56,10 @@ def embedding_forward(sd, frames_nhwc_u8):
         return vit_forward(sd, torch.from_numpy(clip_transforms(frames_nhwc_u8))).numpy()
 
 
-def vit_state(patch, seed):
-    """Deterministic (numpy default_rng) weights with openai/CLIP key names; non-trivial LayerNorm affine and biases
-    so every term of the forward is exercised."""
+def vit_state(patch, seed, gain=1.0):
+    """Deterministic (numpy default_rng) weights with openai/CLIP key names, drawn with the standard deviations of
+    CLIP.initialize_parameters (x `gain` for the transformer matrices; gain 2 is used as a stress case); non-trivial
+    LayerNorm affine and biases so every term of the forward is exercised."""
     rng = np.random.default_rng(seed)
     t = lambda *s, std=1.0: torch.from_numpy((rng.standard_normal(s) * std).astype(np.float32))  # noqa: E731
     g = 224 // patch
@@ -72,13 +73,13 @@ def vit_state(patch, seed):
     proj_std, attn_std, fc_std = (W ** -0.5) * ((2 * LAYERS) ** -0.5), W ** -0.5, (2 * W) ** -0.5
     for i in range(LAYERS):
         b = f"visual.transformer.resblocks.{i}."
-        sd[b + "attn.in_proj_weight"] = t(3 * W, W, std=attn_std * 2)
+        sd[b + "attn.in_proj_weight"] = t(3 * W, W, std=attn_std * gain)
         sd[b + "attn.in_proj_bias"] = t(3 * W, std=0.02)
-        sd[b + "attn.out_proj.weight"] = t(W, W, std=proj_std * 2)
+        sd[b + "attn.out_proj.weight"] = t(W, W, std=proj_std * gain)
         sd[b + "attn.out_proj.bias"] = t(W, std=0.02)
-        sd[b + "mlp.c_fc.weight"] = t(4 * W, W, std=fc_std * 2)
+        sd[b + "mlp.c_fc.weight"] = t(4 * W, W, std=fc_std * gain)
         sd[b + "mlp.c_fc.bias"] = t(4 * W, std=0.02)
-        sd[b + "mlp.c_proj.weight"] = t(W, 4 * W, std=proj_std * 2)
+        sd[b + "mlp.c_proj.weight"] = t(W, 4 * W, std=proj_std * gain)
         sd[b + "mlp.c_proj.bias"] = t(W, std=0.02)
         for ln in ("ln_1", "ln_2"):
             sd[b + ln + ".weight"] = 1 + t(W, std=0.1)

@@ -359,7 +359,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               relu_cols(f, n + h * 32, p.relu_n);
               if (p.quick_gelu) {  // CLIP's QuickGELU: x * sigmoid(1.702 x)
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) f[jj] = f[jj] / (1.f + __expf(-1.702f * f[jj]));
+                for (int jj = 0; jj < 32; ++jj) f[jj] = __fdividef(f[jj], 1.f + __expf(-1.702f * f[jj]));
               }
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {

@@ -89,44 +89,54 @@ __global__ void __launch_bounds__(256) vit_layernorm_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-// One work item = (image, head, 128-row query tile). head_dim = 64 (one 128-byte swizzle row per token and head).
-//   S = Q K^T      tcgen05.mma, Q (128 x 64) and K (KP x 64) K-major from TMA, fp32 scores in TMEM (KP columns)
-//   P = softmax    one thread per query row reads its TMEM lane: row max / sum are thread-local; P is written as
-//                  bf16 into 128B-swizzled K-major shared memory (64-key chunks)
-//   O = P V        tcgen05.mma, V (KP x 64, straight from TMA) is the MN-major B operand; 64 fp32 columns in TMEM
-// Keys beyond the sequence are masked to p = 0; query rows beyond it are computed but never stored.
+// One work item = (image, head): both 128-row query tiles of the sequence (<= 256 tokens), head_dim = 64.
+//   S = Q K^T      tcgen05.mma, Q (128 x 64 per tile) and K (KP x 64) K-major from TMA, fp32 scores in TMEM
+//   P = softmax    one thread per query row reads its TMEM lane (row max / sum are thread-local) and writes the
+//                  probabilities back INTO TMEM as packed bf16 (tcgen05.st), over the scores it has consumed
+//   O = P V        tcgen05.mma with the A operand in TMEM; V (KP x 64, straight from TMA) is the MN-major B operand
+// Warps 0-3 / 4-7 own query tile 0 / 1; warp 8 is the controller (TMA prefetch of the next item into the second
+// smem stage, MMA issue). Keys beyond the sequence get p = 0; query rows beyond it are computed but never stored.
+// TMEM columns per tile (base 0 / 256): S [0, KP), P [0, KP/2) in place, O [128, 192).
 struct AttnParams {
   int n_img, S, W, heads, KP, mtiles;
   float scale_log2e;
   __nv_bfloat16* out;
 };
 
-__global__ void __launch_bounds__(128, 1)
+constexpr int ATT_THREADS = 288;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                      const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t kv_bytes = (uint32_t)p.KP * 128;
   const uint32_t kv_alloc = (kv_bytes + 1023) & ~1023u;
-  uint8_t* sQ = smem;                       // 128 x 128 B
-  uint8_t* sK = sQ + 16384;                 // KP x 128 B
-  uint8_t* sV = sK + kv_alloc;              // KP x 128 B
-  uint8_t* sP = sV + kv_alloc;              // ceil(KP/64) chunks of 128 x 128 B
-  const int pchunks = (p.KP + 63) / 64;
-  uint64_t* bar_load = reinterpret_cast<uint64_t*>(sP + pchunks * 16384);
-  uint64_t* bar_mma = bar_load + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bar_mma + 1);
+  const uint32_t stage_bytes = 32768 + 2 * kv_alloc;  // Q (2 tiles) | K | V
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* kv_full = bars;        // [2]
+  uint64_t* kv_empty = bars + 2;   // [2]
+  uint64_t* s_ready = bars + 4;
+  uint64_t* p_ready = bars + 5;
+  uint64_t* o_ready = bars + 6;
+  uint64_t* tmem_free = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = threadIdx.x;  // query row inside the tile == TMEM lane
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_q);
     prefetch_tmap(&tmap_kv);
-    mbar_init(bar_load, 1);
-    mbar_init(bar_mma, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128 * p.mtiles);
+    mbar_init(o_ready, 1);
+    mbar_init(tmem_free, 128 * p.mtiles);
     fence_barrier_init();
   }
-  if (warp == 0) {
+  if (warp == 8) {
     tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
@@ -134,113 +144,123 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tS = tmem_base + ((uint32_t)(warp * 32) << 16);        // scores: columns [0, KP)
-  const uint32_t tO = tS + 256;                                          // output: columns [256, 320)
-  const uint32_t idesc_s = umma_idesc_bf16(128, p.KP);
-  const uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);        // B (= V) is MN-major
-  const uint32_t swz = (uint32_t)(row & 7);
+  const long long items = (long long)p.n_img * p.heads;
+  const uint32_t q_bytes = 16384u * p.mtiles;
 
-  const long long items = (long long)p.n_img * p.heads * p.mtiles;
-  uint32_t ph_load = 0, ph_mma = 0;
-  for (long long it = blockIdx.x; it < items; it += gridDim.x) {
-    const int mt = (int)(it % p.mtiles);
-    const int head = (int)((it / p.mtiles) % p.heads);
-    const long long img = it / ((long long)p.mtiles * p.heads);
-    const int row0 = (int)(img * p.S);
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(bar_load, 16384 + 2 * kv_bytes);
-      tma_load_2d(&tmap_q, bar_load, sQ, head * 64, row0 + mt * 128);
-      tma_load_2d(&tmap_kv, bar_load, sK, p.W + head * 64, row0);
-      tma_load_2d(&tmap_kv, bar_load, sV, 2 * p.W + head * 64, row0);
-    }
-    mbar_wait(bar_load, ph_load);
-    ph_load ^= 1;
-    if (threadIdx.x == 0) {
-      tc_fence_after();
+  if (warp == 8) {
+    // ===================================================== controller: TMA prefetch + MMA issue
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16(128, p.KP);
+      const uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
+      auto issue_loads = [&](long long it, int st) {
+        const int head = (int)(it % p.heads);
+        const int row0 = (int)((it / p.heads) * p.S);
+        uint8_t* base = smem + st * stage_bytes;
+        mbar_expect_tx(&kv_full[st], q_bytes + 2 * kv_bytes);
+        for (int mt = 0; mt < p.mtiles; ++mt)
+          tma_load_2d(&tmap_q, &kv_full[st], base + mt * 16384, head * 64, row0 + mt * 128);
+        tma_load_2d(&tmap_kv, &kv_full[st], base + 32768, p.W + head * 64, row0);
+        tma_load_2d(&tmap_kv, &kv_full[st], base + 32768 + kv_alloc, 2 * p.W + head * 64, row0);
+      };
+      uint32_t n = 0;
+      if ((long long)blockIdx.x < items) issue_loads(blockIdx.x, 0);
+      for (long long it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+        const int st = n & 1;
+        const long long nxt = it + gridDim.x;
+        if (nxt < items) {  // prefetch the next item into the other stage once its previous user has drained it
+          if (n >= 1) mbar_wait(&kv_empty[st ^ 1], ((n - 1) >> 1) & 1);
+          issue_loads(nxt, st ^ 1);
+        }
+        mbar_wait(&kv_full[st], (n >> 1) & 1);
+        if (n >= 1) mbar_wait(tmem_free, (n - 1) & 1);  // epilogue of the previous item has read O
+        tc_fence_after();
+        const uint32_t sQ = smem_u32(smem + st * stage_bytes), sK = sQ + 32768, sV = sK + kv_alloc;
+        for (int mt = 0; mt < p.mtiles; ++mt)
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_base, umma_desc_sw128(smem_u32(sQ) + k * 32), umma_desc_sw128(smem_u32(sK) + k * 32), idesc_s,
-                  k != 0);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, ph_mma);
-    ph_mma ^= 1;
-    tc_fence_after();
-    // ---- softmax over the valid keys of this thread's row
-    float mx = -INFINITY;
-    for (int c = 0; c < p.KP; c += 16) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(tS + c, v);
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (c + j < p.S) mx = fmaxf(mx, __uint_as_float(v[j]));
-    }
-    float sum = 0.f;
-    const uint32_t p_row = smem_u32(sP) + row * 128;
-    for (int c = 0; c < p.KP; c += 16) {
-      uint32_t v[16];
-      tmem_ld_32x32b_x16(tS + c, v);
-      tmem_wait_ld();
-      float e[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        e[j] = (c + j < p.S) ? exp2f((__uint_as_float(v[j]) - mx) * p.scale_log2e) : 0.f;
-        // the probabilities enter P V as bf16: normalise with the sum of the rounded values
-        e[j] = __bfloat162float(__float2bfloat16_rn(e[j]));
-        sum += e[j];
-      }
-      const uint32_t chunk_base = p_row + (c >> 6) * 16384;
-      const int k16 = (c & 63) >> 3;  // 16-byte chunk index inside the 128-byte row (two per 16 keys)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint4 o;
-        __nv_bfloat162 a = __floats2bfloat162_rn(e[8 * h + 0], e[8 * h + 1]), b = __floats2bfloat162_rn(e[8 * h + 2], e[8 * h + 3]);
-        __nv_bfloat162 cc = __floats2bfloat162_rn(e[8 * h + 4], e[8 * h + 5]), d = __floats2bfloat162_rn(e[8 * h + 6], e[8 * h + 7]);
-        o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
-        o.z = *reinterpret_cast<uint32_t*>(&cc); o.w = *reinterpret_cast<uint32_t*>(&d);
-        st_shared_v4(chunk_base + (((k16 + h) ^ swz) << 4), o);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + mt * 256, umma_desc_sw128(sQ + mt * 16384 + k * 32), umma_desc_sw128(sK + k * 32),
+                      idesc_s, k != 0);
+        umma_commit(s_ready);
+        mbar_wait(p_ready, n & 1);
+        tc_fence_after();
+        for (int mt = 0; mt < p.mtiles; ++mt)
+          for (int ks = 0; ks < p.KP / 16; ++ks)
+            umma_bf16_ts(tmem_base + mt * 256 + 128, tmem_base + mt * 256 + ks * 8,
+                         umma_desc_sw128(sV + ks * 2048), idesc_o, ks != 0);
+        umma_commit(o_ready);
+        umma_commit(&kv_empty[st]);
       }
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+  } else if (warp < 4 * p.mtiles) {
+    // ===================================================== softmax + output (one thread per query row)
+    const int mt = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t tS = tmem_base + mt * 256 + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t n = 0;
+    for (long long it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int head = (int)(it % p.heads);
+      const long long row0 = (it / p.heads) * p.S;
+      mbar_wait(s_ready, n & 1);
       tc_fence_after();
-      for (int ks = 0; ks < p.KP / 16; ++ks)
-        umma_bf16(tmem_base + 256, umma_desc_sw128(smem_u32(sP) + (ks >> 2) * 16384 + (ks & 3) * 32),
-                  umma_desc_sw128(smem_u32(sV) + ks * 2048), idesc_o, ks != 0);
-      umma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, ph_mma);
-    ph_mma ^= 1;
-    tc_fence_after();
-    {
-      uint32_t v[64];
-      tmem_ld_32x32b_x32(tO, v);
-      tmem_ld_32x32b_x32(tO + 32, v + 32);
+      float mx = -INFINITY;
+      for (int c = 0; c < p.KP; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tS + c, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c + j < p.S) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      float sum = 0.f;
+      for (int c = 0; c < p.KP; c += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tS + c, v);
+        tmem_wait_ld();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float e0 = (c + 2 * j < p.S) ? exp2f((__uint_as_float(v[2 * j]) - mx) * p.scale_log2e) : 0.f;
+          float e1 = (c + 2 * j + 1 < p.S) ? exp2f((__uint_as_float(v[2 * j + 1]) - mx) * p.scale_log2e) : 0.f;
+          __nv_bfloat162 b = __floats2bfloat162_rn(e0, e1);
+          // the probabilities enter P V as bf16: normalise with the sum of the rounded values
+          sum += __low2float(b) + __high2float(b);
+          pk[j] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        tmem_st_32x32b_x8(tS + (c >> 1), pk);  // in place: columns [c/2, c/2+8) were consumed in earlier chunks
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+      mbar_wait(o_ready, n & 1);
+      tc_fence_after();
+      uint32_t o[64];
+      tmem_ld_32x32b_x32(tS + 128, o);
+      tmem_ld_32x32b_x32(tS + 160, o + 32);
       tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(tmem_free);
       const int tok = mt * 128 + row;
       if (tok < p.S) {
         const float inv = 1.f / sum;
-        uint4* dst = reinterpret_cast<uint4*>(p.out + ((long long)row0 + tok) * p.W + head * 64);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (row0 + tok) * p.W + head * 64);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          uint4 o;
-          __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 0]) * inv, __uint_as_float(v[8 * j + 1]) * inv);
-          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 2]) * inv, __uint_as_float(v[8 * j + 3]) * inv);
-          __nv_bfloat162 c = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 4]) * inv, __uint_as_float(v[8 * j + 5]) * inv);
-          __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(v[8 * j + 6]) * inv, __uint_as_float(v[8 * j + 7]) * inv);
-          o.x = *reinterpret_cast<uint32_t*>(&a); o.y = *reinterpret_cast<uint32_t*>(&b);
-          o.z = *reinterpret_cast<uint32_t*>(&c); o.w = *reinterpret_cast<uint32_t*>(&d);
-          dst[j] = o;
+          uint4 ov;
+          __nv_bfloat162 a = __floats2bfloat162_rn(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+          __nv_bfloat162 c = __floats2bfloat162_rn(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+          __nv_bfloat162 d = __floats2bfloat162_rn(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+          ov.x = *reinterpret_cast<uint32_t*>(&a); ov.y = *reinterpret_cast<uint32_t*>(&b);
+          ov.z = *reinterpret_cast<uint32_t*>(&c); ov.w = *reinterpret_cast<uint32_t*>(&d);
+          dst[j] = ov;
         }
       }
+      __syncwarp();
     }
-    tc_fence_before();
-    __syncthreads();  // smem / TMEM are reused by the next item
   }
-  if (warp == 0) {
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -300,7 +320,7 @@ extern "C" int pvr_attention(const void* qkv_bf16, int n_img, int tokens, int wi
     return PVR_ERR_CUDA;
   }
   const uint32_t kv_alloc = ((uint32_t)p.KP * 128 + 1023) & ~1023u;
-  const size_t smem = 1024 + 16384 + 2 * kv_alloc + (size_t)((p.KP + 63) / 64) * 16384 + 64;
+  const size_t smem = 1024 + 2 * (size_t)(32768 + 2 * kv_alloc) + 128;
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(vit_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -310,9 +330,9 @@ extern "C" int pvr_attention(const void* qkv_bf16, int n_img, int tokens, int wi
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const long long items = (long long)n_img * heads * p.mtiles;
+  const long long items = (long long)n_img * heads;
   const int grid = (int)(items < sms ? items : sms);
-  vit_attention_kernel<<<grid, 128, smem, static_cast<cudaStream_t>(stream)>>>(tq, tkv, p);
+  vit_attention_kernel<<<grid, ATT_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(tq, tkv, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { pvr_set_error("pvr_attention: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
   return PVR_OK;

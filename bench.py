@@ -355,7 +355,7 @@ def main():
     if name in CLIP_PATCH:
         # ViT: GEMM-dominated; the whole encoder forward (GEMMs + LayerNorm + attention) is timed as one unit
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        net.transforms.run(dev[0], n_frames, enc.slot0, 1, True)
+        net.transforms.run(dev[0], n_frames, enc.slot0, enc.input_format, True)
         enc.forward(out, net.out_size)
         e0.record()
         for r in range(3):
@@ -380,7 +380,7 @@ def resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks,
     conv_ms, conv_flops, other_ms = [], 0.0, []
     reps = 5
     for r in range(reps + 1):
-        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, 2, True)
+        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, enc.input_format, True)
         op_ms = enc.forward_timed(out, net.out_size)
         if r == 0:
             continue  # warm
@@ -394,7 +394,7 @@ def resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks,
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for r in range(10):
-        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, 2, True)
+        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, enc.input_format, True)
     e1.record()
     torch.cuda.synchronize()
     pre_ms = e0.elapsed_time(e1) / 10

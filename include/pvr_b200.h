@@ -64,6 +64,7 @@ int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int 
 #define PVR_OP_MAXPOOL 2  /* 3x3 stride-2 pad-1 max pool, NHWC bf16 */
 #define PVR_OP_AVGPOOL 3  /* global average pool -> float32 rows of the embedding */
 #define PVR_OP_HEAD 4     /* compression-head tail: 3x3 conv c->c + BN + identity add + ReLU -> NCHW-flatten f32 */
+#define PVR_OP_FLATTEN 5  /* NHWC bf16 slot -> NCHW-flattened float32 embedding columns (`out.view(-1, out_size)`) */
 
 typedef struct pvr_op {
   int32_t kind;
@@ -80,7 +81,9 @@ typedef struct pvr_op {
   int32_t block_n;                     /* N tile hint: 0 = auto, else 32/64/128/256 */
   int32_t k_pad;                       /* packed K extent of `weight` (multiple of 64) */
   int32_t n_pad;                       /* packed row count of `weight` (multiple of the N tile) */
-  int32_t emb_offset;                  /* AVGPOOL/HEAD: first column inside the embedding row */
+  int32_t emb_offset;                  /* AVGPOOL/HEAD/FLATTEN: first column inside the embedding row */
+  int32_t act;                         /* CONV: 0 = ReLU mask of relu_n only, 3 = ELU on every channel (small-conv PVR) */
+  int32_t reserved;
   const void* weight;                  /* bf16 (n_pad, k_pad), K-major, K ordered (tap_row, tap_col, channel) */
   const float* scale;                  /* (n_pad) folded BN scale */
   const float* bias;                   /* (n_pad) folded BN bias (+ conv bias) */

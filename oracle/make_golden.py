@@ -83,6 +83,20 @@ def golden_embeddings(E):
     np.savez_compressed(os.path.join(GOLDEN, "embeddings.npz"), **out)
 
 
+def golden_small_conv(E):
+    """The reference's 'random' PVR (5-layer conv, src/embeddings.py:90-106); its weights are small enough to store."""
+    torch.manual_seed(9)
+    net = E.EmbeddingNet('random', pretrained=False, train=False, disable_cuda=True)
+    frames64 = restate.structured_frames(4, 64, 64, 3, 51)
+    frames224 = restate.structured_frames(2, 224, 224, 3, 52)
+    out = {"frames64": frames64, "frames224": frames224, "out_size": np.array(int(net.out_size)),
+           "emb64": net(torch.from_numpy(frames64)), "emb224": net(torch.from_numpy(frames224))}
+    for k, v in net.embedding.state_dict().items():
+        out["w_" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "small_conv.npz"), **out)
+    print("small_conv.npz", out["emb64"].shape, int(net.out_size))
+
+
 def golden_policy():
     """Reference PolicyNet (src/models.py) forward/backward, and the per-step training trace of the UNMODIFIED
     main_bc_2.run() on a synthetic embedded-observation pickle (fake env / test modules)."""
@@ -175,13 +189,15 @@ def golden_policy():
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
-    which = sys.argv[1:] or ["transforms", "embeddings", "policy"]
-    if "transforms" in which or "embeddings" in which:
+    which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
+    if "transforms" in which or "embeddings" in which or "small_conv" in which:
         E = refshim.reference_embeddings()
         if "transforms" in which:
             golden_transforms(E)
         if "embeddings" in which:
             golden_embeddings(E)
+        if "small_conv" in which:
+            golden_small_conv(E)
     if "policy" in which:
         golden_policy()
 

@@ -168,6 +168,19 @@ def resnet50_forward(sd, variant, x):
     return x.reshape(x.shape[0], -1)
 
 
+def small_conv_forward(sd, x):
+    """The 'random' PVR (src/embeddings.py:90-106): 5 x [Conv2d(3x3, s2, p1, bias) -> ELU], flattened NCHW."""
+    for i in (0, 2, 4, 6, 8):
+        x = F.elu(F.conv2d(x, sd[f"{i}.weight"], sd[f"{i}.bias"], stride=2, padding=1))
+    return x.reshape(x.shape[0], -1)
+
+
+def small_conv_embedding(sd, obs_nhwc_u8):
+    x = torch.from_numpy(transforms(np.ascontiguousarray(np.transpose(obs_nhwc_u8, (0, 3, 1, 2)))))
+    with torch.no_grad():
+        return small_conv_forward({k: v.float() for k, v in sd.items()}, x).numpy()
+
+
 UBER = {"345": ("l3", "l4", "conv5"), "35": ("l3", "conv5"), "34": ("l3", "l4"), "45": ("l4", "conv5")}
 
 

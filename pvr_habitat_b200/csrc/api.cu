@@ -75,7 +75,7 @@ extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* 
   }
   for (int i = 0; i < n_ops; ++i) {
     const pvr_op& o = ops[i];
-    const bool emb_out = (o.kind == PVR_OP_AVGPOOL || o.kind == PVR_OP_HEAD);
+    const bool emb_out = (o.kind == PVR_OP_AVGPOOL || o.kind == PVR_OP_HEAD || o.kind == PVR_OP_FLATTEN);
     if (o.in_slot < 0 || o.in_slot >= n_slots || (!emb_out && (o.out_slot < 0 || o.out_slot >= n_slots)) ||
         o.res_slot >= n_slots) {
       pvr_set_error("pvr_encoder_create: op %d references a slot out of range", i);
@@ -91,7 +91,8 @@ extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* 
         pvr_set_error("pvr_encoder_create: op %d: c_in must be 8, 32 or a multiple of 64 (got %d)", i, o.c_in);
         return PVR_ERR_ARG;
       }
-    } else if (o.kind != PVR_OP_MAXPOOL && o.kind != PVR_OP_AVGPOOL && o.kind != PVR_OP_HEAD) {
+    } else if (o.kind != PVR_OP_MAXPOOL && o.kind != PVR_OP_AVGPOOL && o.kind != PVR_OP_HEAD &&
+               o.kind != PVR_OP_FLATTEN) {
       pvr_set_error("pvr_encoder_create: op %d has unknown kind %d", i, o.kind);
       return PVR_ERR_ARG;
     }
@@ -173,6 +174,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     p.lower_h = o.lower_h;
     p.n_valid = o.c_out;
     p.relu_n = o.relu_n;
+    p.elu = o.act == 3;
     p.ldo = o.out_pitch;
     p.out = reinterpret_cast<__nv_bfloat16*>(enc->slot_ptr[o.out_slot]) + o.out_coff;
     if (o.res_slot >= 0) {
@@ -233,7 +235,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       return PVR_ERR_CUDA;
     }
     // Output / residual staged through shared memory + TMA when the channel count allows full 64-column sub-tiles.
-    b.epi_tma = (b.block_n >= 64 && o.c_out % 64 == 0);
+    b.epi_tma = (b.block_n >= 64 && o.c_out % 64 == 0 && o.act != 3);
     b.to = b.ta;
     b.tr = b.ta;
     if (b.epi_tma) {
@@ -274,6 +276,10 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
       case PVR_OP_AVGPOOL:
         e = pvr::launch_avgpool(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), emb, emb_ld,
                                 o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
+        break;
+      case PVR_OP_FLATTEN:
+        e = pvr::launch_flatten(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), o.in_pitch, emb,
+                                emb_ld, o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
         break;
       case PVR_OP_HEAD:
         e = pvr::launch_head_tail(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), o.in_pitch,

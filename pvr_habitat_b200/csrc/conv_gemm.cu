@@ -434,6 +434,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (int jj = 0; jj < 4; ++jj) add_bf16x8(f + 8 * jj, __ldg(r4 + jj));
             }
             relu_cols(f, n, p.relu_n);
+            if (p.elu) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) f[jj] = f[jj] > 0.f ? f[jj] : expm1f(f[jj]);
+            }
             uint4* o4 = reinterpret_cast<uint4*>(out_row + n);
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
@@ -450,6 +454,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               float x = f[jj];
               if (res_row) x += __bfloat162float(res_row[n + jj]);
               if (n + jj < p.relu_n) x = fmaxf(x, 0.0f);
+              if (p.elu) x = x > 0.f ? x : expm1f(x);
               out_row[n + jj] = __float2bfloat16_rn(x);
             }
           }

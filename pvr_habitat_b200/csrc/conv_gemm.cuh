@@ -30,6 +30,7 @@ struct ConvGemmParams {
   int n_valid;       // real output channels (columns >= n_valid are not stored)
   int relu_n;        // ReLU is applied to output columns < relu_n (0: none, >= n_valid: all)
   int has_res;       // residual present (EPI_TMA path reads it through tmap_res)
+  int elu;           // ELU(alpha = 1) on every output channel (direct epilogue; small-conv PVR)
   int quick_gelu;    // bf16 output: x * sigmoid(1.702 x) after bias (CLIP MLP)
   int res_mode;      // 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward with the saved activation)
   int split_k;       // >= 1; K is cut into split_k slices of num_k_chunks chunks, each its own tile (fp32 atomics)

@@ -122,6 +122,20 @@ __global__ void __launch_bounds__(256) head_tail_kernel(const __nv_bfloat16* __r
   }
 }
 
+// emb[img][off + c*HW + px] = in[img][px][c]: NHWC bf16 -> NCHW-flattened fp32 (the small-conv PVR's output order).
+__global__ void __launch_bounds__(256) flatten_kernel(const __nv_bfloat16* __restrict__ in, int pitch,
+                                                       float* __restrict__ emb, long long emb_ld, int emb_off,
+                                                       int n_img, int HW, int C) {
+  const long long total = (long long)n_img * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const long long img = i / ((long long)HW * C);
+    emb[img * emb_ld + emb_off + (long long)c * HW + px] = __bfloat162float(in[(img * HW + px) * pitch + c]);
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_maxpool(const __nv_bfloat16* in, __nv_bfloat16* out, int n_img, int H, int W, int C, int P, int Q,
@@ -137,6 +151,15 @@ cudaError_t launch_avgpool(const __nv_bfloat16* in, float* emb, long long emb_ld
                            int C, cudaStream_t stream) {
   const long long total = (long long)n_img * (C >> 3);
   avgpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, emb, emb_ld, emb_off, n_img, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flatten(const __nv_bfloat16* in, int pitch, float* emb, long long emb_ld, int emb_off, int n_img,
+                           int HW, int C, cudaStream_t stream) {
+  const long long total = (long long)n_img * HW * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  flatten_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, pitch, emb, emb_ld, emb_off, n_img, HW, C);
   return cudaGetLastError();
 }
 

@@ -71,6 +71,30 @@ class Transforms(nn.Module):
         return out
 
 
+def init(module, weight_init, bias_init, gain=1):
+    weight_init(module.weight.data, gain=gain)
+    bias_init(module.bias.data)
+    return module
+
+
+class SmallConvParams(nn.Sequential):
+    """Parameter container of the 'random' PVR; the arithmetic is program.add_small_conv (no torch forward)."""
+    variant = 'small_conv'
+
+    def __init__(self, in_channels=3):
+        init_ = lambda m: init(m, nn.init.orthogonal_, lambda x: nn.init.constant_(x, 0),  # noqa: E731
+                               nn.init.calculate_gain('relu'))
+        layers = []
+        for i in range(5):
+            layers += [init_(nn.Conv2d(in_channels if i == 0 else 32, 32, kernel_size=(3, 3), stride=2, padding=1)),
+                       nn.ELU()]
+        super().__init__(*layers)
+        self.out_size = 32 * 7 * 7  # 224 -> 112 -> 56 -> 28 -> 14 -> 7
+
+    def forward(self, x):
+        raise _lib.PvrError("SmallConvParams holds parameters only; use EmbeddingNet (CUDA program), no torch fallback")
+
+
 class UberModel(nn.Module):
     """Concatenation of several encoders (src/embeddings.py:44-57). `models` is a plain list, as in the reference,
     so an uber EmbeddingNet has an empty state_dict."""
@@ -114,7 +138,11 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
     transforms = Transforms(IMAGENET_MEAN, IMAGENET_STD)
     assert in_channels == 3, 'Current models accept 3-channel inputs only.'
 
-    if embedding_name == 'resnet50':
+    if embedding_name == 'random':
+        # FIXED 5-LAYER CONV (src/embeddings.py:90-106): built with the same layer order / init calls as the
+        # reference, so the same torch seed gives the same weights and the same state_dict keys ('0.weight', ...).
+        model = SmallConvParams(in_channels)
+    elif embedding_name == 'resnet50':
         # torchvision.models.resnet50(pretrained=...), fc -> Identity (src/embeddings.py:118-120). Offline there is no
         # download: pretrained weights must already be loaded by the caller through load_state_dict.
         model = ResNet50Params('conv5')
@@ -164,6 +192,13 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
 def build_encoder(model, device, hw=224):
     """Compile `model` (ResNet50Params or UberModel of them) into one pvr_encoder program on `device`."""
     prog = prg.Program()
+    if isinstance(model, SmallConvParams):
+        in_slot = prog.new_slot(hw * hw * 4)  # slot 0: NHWC4 bf16 frames
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        prog.emb_width = prg.add_small_conv(prog, sd, in_slot, 0, hw)
+        enc = prog.finish(device)
+        enc.input_format = _lib.PVR_FMT_NHWC4_BF16
+        return enc
     in_slot = prog.new_slot(hw * (hw // 2) * 32)  # slot 0: W-expanded bf16 frames from the preprocessing kernel
     parts = model.models if isinstance(model, UberModel) else [model]
     off = 0
@@ -171,7 +206,9 @@ def build_encoder(model, device, hw=224):
         sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
         off += prg.add_resnet50(prog, sd, m.variant, in_slot, off, hw)
     prog.emb_width = off
-    return prog.finish(device)
+    enc = prog.finish(device)
+    enc.input_format = _lib.PVR_FMT_STEM_BF16
+    return enc
 
 
 class EmbeddingNet(nn.Module):
@@ -244,8 +281,7 @@ class EmbeddingNet(nn.Module):
         n = obs.shape[0]
         enc = self.encoder()
         enc.bind(n * n_frames)
-        fmt = _lib.PVR_FMT_NHWC4_BF16 if isinstance(enc, clip_vit.ViTRunner) else _lib.PVR_FMT_STEM_BF16
-        self.transforms.run(obs, n_frames, enc.slot0, fmt, True)
+        self.transforms.run(obs, n_frames, enc.slot0, enc.input_format, True)
         if out is None:
             out = torch.empty(n, n_frames * self.out_size, dtype=torch.float32, device=self.device)
         enc.forward(out, self.out_size)

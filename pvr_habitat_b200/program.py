@@ -91,7 +91,7 @@ class Program:
 
     # ---- ops
     def conv(self, in_slot, in_chw, w_packed, k_pad, c_out, r, s, stride, lower, out_hw, scale, bias, relu_n,
-             in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0, flops=None):
+             in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0, flops=None, act=0):
         c_in, h_in, w_in = in_chw
         n_pad = w_packed.shape[0]
         p, q = out_hw
@@ -107,7 +107,7 @@ class Program:
                   w_in=w_in, in_pitch=in_pitch if in_pitch is not None else c_in, c_out=c_out, h_out=p, w_out=q,
                   out_pitch=out_pitch, res_pitch=0, out_coff=out_coff, res_coff=0, r=r, s=s,
                   stride_h=stride[0], stride_w=stride[1], lower_h=lower[0], lower_w=lower[1], relu_n=relu_n,
-                  block_n=block_n, k_pad=k_pad, n_pad=n_pad, emb_offset=0,
+                  block_n=block_n, k_pad=k_pad, n_pad=n_pad, emb_offset=0, act=act,
                   _weight=w_packed.contiguous(), _scale=sc, _bias=bi,
                   flops_per_image=int(flops if flops is not None else 2 * p * q * c_out * r * s * c_in))
         if res is not None:
@@ -121,6 +121,10 @@ class Program:
         self.ops.append(dict(kind=_lib.PVR_OP_MAXPOOL, in_slot=in_slot, out_slot=out_slot, res_slot=-1, c_in=c,
                              h_in=h, w_in=w, in_pitch=c, c_out=c, h_out=p, w_out=q, out_pitch=c))
         return out_slot, p, q
+
+    def flatten(self, in_slot, c, h, w, pitch, emb_offset):
+        self.ops.append(dict(kind=_lib.PVR_OP_FLATTEN, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=c, h_in=h,
+                             w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset))
 
     def avgpool(self, in_slot, c, h, w, emb_offset):
         self.ops.append(dict(kind=_lib.PVR_OP_AVGPOOL, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=c, h_in=h,
@@ -315,3 +319,50 @@ def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
     n = _compress_head(prog, sd, head_prefix, x, chw, emb_offset)
     prog.release(x)
     return n
+
+
+# ------------------------------------------------------------------------------------------------ small-conv PVR
+def pack_first_small_conv(w, n_pad):
+    """3x3 stride-2 pad-1 conv over NHWC4 frames seen as pixel pairs (H, W/2, 8): output column q reads input columns
+    2q-1 .. 2q+1 = pair q-1 (second pixel) and pair q (both pixels) -> 3 x 2 taps of 8 values, K padded to 64.
+    K index = (r*2 + sp)*8 + e*4 + c with filter column j = 2*sp + e - 1."""
+    co, ci, r, s = w.shape
+    assert (ci, r, s) == (3, 3, 3)
+    out = torch.zeros(n_pad, 8, 2, 4, dtype=torch.float32)  # (co, tap, e, c); taps 6, 7 are padding
+    for rr in range(3):
+        for sp in range(2):
+            for e in range(2):
+                j = 2 * sp + e - 1
+                if 0 <= j < 3:
+                    out[:co, rr * 2 + sp, e, :3] = w[:, :, rr, j]
+    return out.reshape(n_pad, 64).to(torch.bfloat16)
+
+
+def pack_small_conv(w, n_pad):
+    """(32, 32, 3, 3) -> bf16 (n_pad, 320): K = (r, s, c) over 9 taps of 32 channels, padded to 10 taps."""
+    co, ci, r, s = w.shape
+    out = torch.zeros(n_pad, 10, ci, dtype=torch.float32)
+    out[:co, :9] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
+    return out.reshape(n_pad, 10 * ci).to(torch.bfloat16)
+
+
+def add_small_conv(prog, sd, in_slot, emb_offset, hw=224):
+    """The reference's 'random' PVR (src/embeddings.py:90-106): 5 x [Conv2d(3x3, stride 2, padding 1, bias) + ELU],
+    3 -> 32 -> 32 -> 32 -> 32 -> 32 channels, output flattened NCHW. `in_slot` holds NHWC4 bf16 frames.
+    Layer 1 uses 8-element pixel pairs (A_IM2COL8), layers 2-5 32-channel pixels (A_IM2COL32, 64-byte TMA rows);
+    bias + ELU run in the GEMM epilogue. Returns the number of embedding columns."""
+    ones = torch.ones(32)
+    h = hw
+    p = (h + 2 - 3) // 2 + 1
+    x = prog.conv(in_slot, (8, h, h // 2), pack_first_small_conv(sd["0.weight"].float(), 32), 64, 32, 3, 2, (2, 1),
+                  (-1, -1), (p, p), ones, sd["0.bias"].float(), 0, out_pitch=32, act=3, flops=2 * p * p * 32 * 27)
+    h = p
+    for i in (2, 4, 6, 8):
+        p = (h + 2 - 3) // 2 + 1
+        y = prog.conv(x, (32, h, h), pack_small_conv(sd[f"{i}.weight"].float(), 32), 320, 32, 3, 3, (2, 2), (-1, -1),
+                      (p, p), ones, sd[f"{i}.bias"].float(), 0, out_pitch=32, act=3, flops=2 * p * p * 32 * 288)
+        prog.release(x)
+        x, h = y, p
+    prog.flatten(x, 32, h, h, 32, emb_offset)
+    prog.release(x)
+    return 32 * h * h

@@ -140,6 +140,7 @@ class ViTRunner:
     def __init__(self, vis, device):
         self.device = torch.device(device)
         self.lib = _lib.lib()
+        self.input_format = _lib.PVR_FMT_NHWC4_BF16
         self.p, self.W, self.L, self.heads, self.O = vis.patch_size, vis.width, vis.layers, vis.heads, vis.output_dim
         self.res = vis.input_resolution
         self.grid = self.res // self.p

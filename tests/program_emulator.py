@@ -45,6 +45,8 @@ def emulate(prog, frames_nhwc4, round_bf16=True):
             rn = op["relu_n"]
             if rn > 0:
                 y = torch.cat([y[:, :rn].relu(), y[:, rn:]], 1)
+            if op.get("act", 0) == 3:
+                y = F.elu(y)
             op_ = op["out_pitch"]
             buf = slots.get(op["out_slot"])
             need = p * q * op_
@@ -60,6 +62,10 @@ def emulate(prog, frames_nhwc4, round_bf16=True):
             x = slots[op["in_slot"]][:, :h * w * c].reshape(n, h, w, c).permute(0, 3, 1, 2)
             y = F.max_pool2d(x, 3, 2, 1)
             slots[op["out_slot"]] = y.permute(0, 2, 3, 1).reshape(n, -1).contiguous()
+        elif k == _lib.PVR_OP_FLATTEN:
+            c, h, w, pitch = op["c_in"], op["h_in"], op["w_in"], op["in_pitch"]
+            x = slots[op["in_slot"]][:, :h * w * pitch].reshape(n, h * w, pitch)[..., :c]
+            emb[:, op["emb_offset"]:op["emb_offset"] + c * h * w] = x.permute(0, 2, 1).reshape(n, -1)
         elif k == _lib.PVR_OP_AVGPOOL:
             c, h, w = op["c_in"], op["h_in"], op["w_in"]
             x = slots[op["in_slot"]][:, :h * w * c].reshape(n, h * w, c)

@@ -48,6 +48,6 @@ def test_argument_errors_do_not_need_a_gpu(built):
 
 
 def test_op_struct_layout_matches_header():
-    """pvr_op: 26 int32 fields then 4 pointers (ctypes mirror of the C struct)."""
-    assert ctypes.sizeof(_lib.pvr_op) == 26 * 4 + 4 * 8
-    assert _lib.pvr_op.weight.offset == 104
+    """pvr_op: 28 int32 fields then 4 pointers (ctypes mirror of the C struct)."""
+    assert ctypes.sizeof(_lib.pvr_op) == 28 * 4 + 4 * 8
+    assert _lib.pvr_op.weight.offset == 112

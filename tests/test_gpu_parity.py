@@ -209,3 +209,16 @@ def test_load_state_dict_recompiles(emb):
     net.load_state_dict(sd)
     b = net(x)
     assert not np.array_equal(a, b)
+
+
+def test_random_small_conv_embedding_vs_reference_golden(golden_dir):
+    """'random' PVR (5 x conv3x3/s2 + ELU) against the reference's EmbeddingNet('random') outputs."""
+    gold = np.load(os.path.join(golden_dir, "small_conv.npz"))
+    torch.manual_seed(9)
+    net = EmbeddingNet("random", pretrained=False)
+    net.embedding.load_state_dict({k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w_")})
+    net.invalidate()
+    assert net.out_size == 1568
+    for key in ("64", "224"):
+        got = net(torch.from_numpy(gold["frames" + key]))
+        check_embedding(got, gold["emb" + key])

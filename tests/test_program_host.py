@@ -94,3 +94,43 @@ def test_cpu_forward_fails_loudly():
 def test_resize_geometry_matches_oracle():
     for hw in ((64, 64), (224, 224), (96, 128), (480, 640), (640, 480), (100, 75)):
         assert resize_geometry(*hw) == restate.resize_geometry(*hw)
+
+
+def test_small_conv_program_equals_oracle(golden_dir):
+    import os
+    gold = np.load(os.path.join(golden_dir, "small_conv.npz"))
+    sd = {k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w_")}
+    sdb = {k: (v.to(torch.bfloat16).float() if k.endswith("weight") else v) for k, v in sd.items()}
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 64 * 4)
+    prog.emb_width = prg.add_small_conv(prog, sd, s0, 0, hw=64)
+    assert prog.emb_width == 32 * 2 * 2
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    x4 = torch.zeros(2, 64, 64, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    got = emulate(prog, x4, round_bf16=False)
+    ref = restate.small_conv_forward(sdb, x)
+    assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+
+
+def test_small_conv_oracle_matches_reference_golden(golden_dir):
+    import os
+    gold = np.load(os.path.join(golden_dir, "small_conv.npz"))
+    sd = {k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w_")}
+    for key in ("64", "224"):
+        got = restate.small_conv_embedding(sd, gold["frames" + key])
+        ref = gold["emb" + key]
+        np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-5 * float(np.abs(ref).max()))
+
+
+def test_random_embedding_container_reproduces_reference_init(golden_dir):
+    import os
+    gold = np.load(os.path.join(golden_dir, "small_conv.npz"))
+    torch.manual_seed(9)
+    net = EmbeddingNet("random", pretrained=False, disable_cuda=True)
+    assert net.out_size == int(gold["out_size"]) == 1568
+    sd = net.state_dict()
+    assert sorted(sd) == sorted("embedding." + k[2:] for k in gold.files if k.startswith("w_"))
+    for k in gold.files:
+        if k.startswith("w_"):  # orthogonal_ = LAPACK QR: last bits may differ between hosts
+            np.testing.assert_allclose(sd["embedding." + k[2:]].numpy(), gold[k], atol=1e-5)

@@ -51,8 +51,10 @@ int pick_block_n(int n_pad, long long m_tiles, int sms, int hint, bool has_res) 
 struct BoundConv {
   CUtensorMap ta, tb, to, tr;
   pvr::ConvGemmParams p;
+  pvr::Conv3x3PatchParams pp;
   int block_n, a_mode;
   bool epi_tma;
+  bool patch;  // patch-resident 3x3 kernel (conv3x3_patch.cu)
 };
 
 }  // namespace
@@ -150,6 +152,25 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     pvr::ConvGemmParams& p = b.p;
     memset(&p, 0, sizeof(p));
     const long long M = (long long)n_images * o.h_out * o.w_out;
+    b.patch = false;
+    if (o.r == 3 && o.s == 3 && o.stride_h == 1 && o.stride_w == 1 && o.lower_h == -1 && o.lower_w == -1 &&
+        o.c_in == 64 && o.c_out == 64 && o.n_pad == 64 && o.in_pitch == 64 && o.out_pitch == 64 && o.out_coff == 0 &&
+        o.h_in == o.h_out && o.w_in == o.w_out && o.w_out % 8 == 0 && o.res_slot < 0 && o.act == 0 &&
+        (o.relu_n == 0 || o.relu_n >= 64) && o.k_pad == 576 && o.block_n == 0) {
+      // layer1-style 3x3 convolution: keep the input patch and the weights resident in shared memory
+      const char* err = "";
+      b.pp.n_img = n_images; b.pp.P = o.h_out; b.pp.Q = o.w_out;
+      b.pp.tiles_p = (o.h_out + 15) / 16; b.pp.tiles_q = o.w_out / 8;
+      b.pp.relu = o.relu_n > 0; b.pp.scale = o.scale; b.pp.bias = o.bias;
+      if (!pvr::make_tmap_4d(&b.ta, enc->slot_ptr[o.in_slot], 64, 64, o.w_in, o.h_in, n_images, 8, 18, &err) ||
+          !pvr::make_tmap_2d(&b.tb, o.weight, 576, 64, 576, 64, &err) ||
+          !pvr::make_tmap_4d(&b.to, enc->slot_ptr[o.out_slot], 64, 64, o.w_out, o.h_out, n_images, 8, 16, &err)) {
+        pvr_set_error("pvr_encoder_bind: op %zu: patch conv tensor maps: %s", i, err);
+        return PVR_ERR_CUDA;
+      }
+      b.patch = true;
+      continue;
+    }
     if (M > 0x7fffffffll) {
       pvr_set_error("pvr_encoder_bind: batch too large");
       return PVR_ERR_ARG;
@@ -265,7 +286,9 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
     switch (o.kind) {
       case PVR_OP_CONV: {
         const BoundConv& b = enc->bound[i];
-        e = pvr::launch_conv_gemm(b.block_n, b.a_mode, b.epi_tma, b.ta, b.tb, b.to, b.tr, b.p, enc->sms, stream);
+        e = b.patch ? pvr::launch_conv3x3_patch(b.ta, b.tb, b.to, b.pp, enc->sms, stream)
+                    : pvr::launch_conv_gemm(b.block_n, b.a_mode, b.epi_tma, b.ta, b.tb, b.to, b.tr, b.p, enc->sms,
+                                            stream);
         break;
       }
       case PVR_OP_MAXPOOL:

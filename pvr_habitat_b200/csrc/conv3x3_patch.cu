@@ -1,0 +1,206 @@
+// 3x3 / stride-1 / pad-1 convolution with C_in = C_out = 64 (ResNet-50 layer1.*.conv2 at 56x56) as a patch-resident
+// tcgen05 implicit GEMM.
+//
+// The im2col formulation (conv_gemm.cu, A_IM2COL64) re-reads every input pixel nine times from L2 into shared memory:
+// at C = 64 the kernel is bound by L2 -> SM bytes (profiles/: 153 us per 256 frames against 45 us of tensor time).
+// Here one tile = 16 output rows x 8 output columns (= 128 GEMM rows). The producer loads the 18 x 8 input patch
+// three times, shifted by -1 / 0 / +1 columns (tiled 4-D TMA, out-of-range = zero = padding); each copy is
+// [18 rows][8 px][128 B], i.e. one 1024-byte swizzle atom per patch row, so the A operand of tap (r, s) is simply
+// copy s at byte offset r * 1024: nine taps, three loads. The 72 KiB of weights stay resident in shared memory for the
+// whole (persistent) kernel. Epilogue: as conv_gemm (two groups, smem staging, TMA store of the 16 x 8 output patch).
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+
+namespace pvr {
+namespace {
+
+constexpr int PT_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 two epilogue groups
+constexpr uint32_t COPY_BYTES = 18 * 1024;      // one column-shifted copy of the patch
+constexpr uint32_t A_STAGE = 3 * COPY_BYTES;    // 54 KiB
+constexpr uint32_t W_BYTES = 9 * 64 * 128;      // 72 KiB: nine 64 x 64 bf16 tap matrices
+constexpr int A_STAGES = 2;
+constexpr uint32_t PT_SMEM = 1024 + W_BYTES + A_STAGES * A_STAGE + 2 * 16384 + 512 + 256;
+
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
+                     const __grid_constant__ CUtensorMap tmap_out, const Conv3x3PatchParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW = smem;
+  uint8_t* sA = sW + W_BYTES;
+  uint8_t* sOut = sA + A_STAGES * A_STAGE;
+  float* sSB = reinterpret_cast<float*>(sOut + 2 * 16384);  // scale[64] | bias[64]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sOut + 2 * 16384 + 512);
+  uint64_t* empty_bar = full_bar + A_STAGES;
+  uint64_t* w_bar = empty_bar + A_STAGES;
+  uint64_t* tmem_full_bar = w_bar + 1;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_p * p.tiles_q;
+  const int num_tiles = p.n_img * tiles_per_img;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_in);
+    prefetch_tmap(&tmap_w);
+    prefetch_tmap(&tmap_out);
+    for (int s = 0; s < A_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(w_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 128);  // only the group that owns the tile reads the accumulator
+    }
+    fence_barrier_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 192) sSB[threadIdx.x - 64] =
+      (threadIdx.x - 64) < 64 ? p.scale[threadIdx.x - 64] : p.bias[threadIdx.x - 128];
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights: nine 64 x 64 tap matrices, loaded once
+      mbar_expect_tx(w_bar, W_BYTES);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(&tmap_w, w_bar, sW + tap * 8192, tap * 64, 0);
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int img = tile / tiles_per_img;
+        const int rem = tile - img * tiles_per_img;
+        const int p0 = (rem / p.tiles_q) * 16, q0 = (rem % p.tiles_q) * 8;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_expect_tx(&full_bar[stage], A_STAGE);
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+          tma_load_4d(&tmap_in, &full_bar[stage], sA + stage * A_STAGE + s * COPY_BYTES, 0, q0 + s - 1, p0 - 1, img);
+        if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      mbar_wait(w_bar, 0);
+      uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      const uint32_t w_base = smem_u32(sW);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + stage * A_STAGE);
+        const uint32_t d_tmem = tmem_base + acc * 64;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem, umma_desc_sw128(a_base + s * COPY_BYTES + r * 1024 + k * 32),
+                        umma_desc_sw128(w_base + (r * 3 + s) * 8192 + k * 32), idesc, (r | s | k) != 0);
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full_bar[acc]);
+        if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // epilogue: group g takes tiles with (local tile index & 1) == g, accumulator stage == g
+    const int group = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int gtid = (warp - 2 - group * 4) * 32 + lane;
+    const bool leader = gtid == 0;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t out_row = smem_u32(sOut + group * 16384) + row * 128;
+    const uint32_t sb_addr = smem_u32(sSB);
+    uint32_t n = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++n) {
+      if ((n & 1) != (uint32_t)group) continue;
+      const uint32_t acc_phase = (n >> 1) & 1;
+      const int img = tile / tiles_per_img;
+      const int rem = tile - img * tiles_per_img;
+      const int p0 = (rem / p.tiles_q) * 16, q0 = (rem % p.tiles_q) * 8;
+      mbar_wait(&tmem_full_bar[group], acc_phase);
+      tc_fence_after();
+      uint32_t v[64];
+      const uint32_t taddr = tmem_base + group * 64 + ((uint32_t)(quarter * 32) << 16);
+      tmem_ld_32x32b_x32(taddr, v);
+      tmem_ld_32x32b_x32(taddr + 32, v + 32);
+      if (leader) bulk_wait_group_read<0>();  // this group's previous store has drained the staging buffer
+      named_bar_sync(1 + group, 128);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[group]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float f[32];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          const uint4 s4 = ld_shared_v4(sb_addr + (h * 8 + jj) * 16);
+          const uint4 b4 = ld_shared_v4(sb_addr + 256 + (h * 8 + jj) * 16);
+          f[4 * jj + 0] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 0]), __uint_as_float(s4.x), __uint_as_float(b4.x));
+          f[4 * jj + 1] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 1]), __uint_as_float(s4.y), __uint_as_float(b4.y));
+          f[4 * jj + 2] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 2]), __uint_as_float(s4.z), __uint_as_float(b4.z));
+          f[4 * jj + 3] = fmaf(__uint_as_float(v[h * 32 + 4 * jj + 3]), __uint_as_float(s4.w), __uint_as_float(b4.w));
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          uint4 ov;
+          ov.x = pack2(f[8 * jj + 0], f[8 * jj + 1]);
+          ov.y = pack2(f[8 * jj + 2], f[8 * jj + 3]);
+          ov.z = pack2(f[8 * jj + 4], f[8 * jj + 5]);
+          ov.w = pack2(f[8 * jj + 6], f[8 * jj + 7]);
+          st_shared_v4(out_row + (((h * 4 + jj) ^ swz) << 4), ov);
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1 + group, 128);
+      if (leader) {
+        tma_store_4d(&tmap_out, sOut + group * 16384, 0, q0, p0, img);  // rows >= P are clipped
+        bulk_commit_group();
+      }
+    }
+    if (leader) bulk_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 128);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, const CUtensorMap& tmap_out,
+                                 const Conv3x3PatchParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.n_img * p.tiles_p * p.tiles_q;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  conv3x3_patch_kernel<<<grid, PT_THREADS, PT_SMEM, stream>>>(tmap_in, tmap_w, tmap_out, p);
+  return cudaGetLastError();
+}
+
+}  // namespace pvr

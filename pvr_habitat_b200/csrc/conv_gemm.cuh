@@ -58,6 +58,22 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows,
 // 2-D fp32 matrix (rows x cols), row pitch ld elements, box = (32 x box_rows) = 128-byte rows, 128B swizzle.
 bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                       uint32_t box_rows, const char** err);
+// Tiled 4-D map over an NHWC bf16 tensor (N, H, W, pitch) exposing `c` channels: box = (64 ch, box_w, box_h, 1),
+// 128B swizzle (patch-resident 3x3 convolution, conv3x3_patch.cu).
+bool make_tmap_4d(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int box_w, int box_h,
+                  const char** err);
+// 3x3 / stride 1 / pad 1 convolution, C_in = C_out = 64, W % 8 == 0, with the input patch resident in shared memory
+// (three column-shifted copies; the nine taps are UMMA descriptor offsets) and the weights resident for the whole
+// kernel. Same epilogue contract as conv_gemm (scale/bias/ReLU, bf16 NHWC out).
+struct Conv3x3PatchParams {
+  int n_img, P, Q;         // images, height, width (output == input size)
+  int tiles_p, tiles_q;    // ceil(P / 16), Q / 8
+  int relu;
+  const float* scale;      // (64)
+  const float* bias;       // (64)
+};
+cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, const CUtensorMap& tmap_out,
+                                 const Conv3x3PatchParams& p, int num_sms, cudaStream_t stream);
 // im2col map over an NHWC bf16 tensor (N, H, W, pitch) exposing `c` channels per pixel.
 bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int lower_w,
                       int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int channels_per_pixel,

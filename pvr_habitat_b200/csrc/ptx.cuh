@@ -71,6 +71,22 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// Tiled 4-D load / store over an NHWC tensor seen as (C, W, H, N); out-of-range coordinates (negative included) read
+// zeros on loads (= convolution padding) and are clipped on stores.
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int32_t c, int32_t w,
+                                            int32_t h, int32_t n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int32_t c, int32_t w, int32_t h,
+                                             int32_t n) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c), "r"(w), "r"(h), "r"(n)
+               : "memory");
+}
 // im2col-mode load of a (channelsPerPixel x pixelsPerColumn) column from an NHWC tensor seen as (C,W,H,N).
 // (w,h) is the base pixel inside the bounding box; (off_w, off_h) the filter-tap offset added to every base pixel.
 __device__ __forceinline__ void tma_load_im2col_4d(const CUtensorMap* m, uint64_t* bar, void* dst, int32_t c,

@@ -119,7 +119,9 @@ def test_gemm_vs_fp32(m, n, k, relu, res):
 @pytest.mark.parametrize("args", [
     dict(n=3, h=14, wd=14, ci=128, co=256, r=1, stride=1, pad=0, relu=True, res=True),
     dict(n=3, h=14, wd=14, ci=128, co=128, r=3, stride=1, pad=1),
-    dict(n=2, h=56, wd=56, ci=64, co=64, r=3, stride=1, pad=1),
+    dict(n=2, h=56, wd=56, ci=64, co=64, r=3, stride=1, pad=1),           # patch-resident kernel
+    dict(n=3, h=24, wd=16, ci=64, co=64, r=3, stride=1, pad=1, relu=False),  # patch kernel, clipped row tiles
+    dict(n=1, h=8, wd=8, ci=64, co=64, r=3, stride=1, pad=1),               # patch kernel, single partial tile
     dict(n=3, h=28, wd=28, ci=128, co=128, r=3, stride=2, pad=1),
     dict(n=3, h=28, wd=28, ci=256, co=512, r=1, stride=2, pad=0, relu=False),
     dict(n=5, h=7, wd=7, ci=512, co=512, r=3, stride=1, pad=1, res=True),

@@ -15,20 +15,42 @@ namespace pvr {
 namespace {
 
 constexpr int PT_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2..9 two epilogue groups
-constexpr uint32_t COPY_BYTES = 18 * 1024;      // one column-shifted copy of the patch
-constexpr uint32_t A_STAGE = 3 * COPY_BYTES;    // 54 KiB
-constexpr uint32_t W_BYTES = 9 * 64 * 128;      // 72 KiB: nine 64 x 64 bf16 tap matrices
-constexpr int A_STAGES = 2;
-constexpr uint32_t PT_SMEM = 1024 + W_BYTES + A_STAGES * A_STAGE + 2 * 16384 + 512 + 256;
+
+// STEM = false: 3x3/s1 conv, 64 -> 64 channels. Three column-shifted copies of the 18 x 8 patch, 128-byte pixels,
+//               128B swizzle (one 1024-byte atom per patch row), nine 64 x 64 tap matrices resident.
+// STEM = true : ResNet stem 7x7/s2 over the W-expanded input (PVR_FMT_STEM_BF16: 64-byte pixels holding the 8 input
+//               columns x 4 channels of one output column). Only row taps remain; output row p reads input rows
+//               2p-3+r, so the even taps (r = 0,2,4,6) read every second row starting at 2*p0-3 and the odd taps every
+//               second row starting at 2*p0-2: two TMA loads with traversal stride 2 (19 rows each), 64B swizzle (one
+//               512-byte atom per patch row); tap r = copy (r & 1) at byte offset (r >> 1) * 512. Seven 64 x 32 tap
+//               matrices resident. im2col re-read 7x -> 2.3x.
+template <bool STEM>
+struct PCfg {
+  static constexpr uint32_t ROW_BYTES = STEM ? 512 : 1024;          // 8 pixels of one patch row
+  static constexpr uint32_t COPY_ROWS = STEM ? 19 : 18;
+  static constexpr uint32_t COPY_BYTES = STEM ? 10240 : 18 * 1024;  // one copy of the patch (1024-byte aligned)
+  static constexpr uint32_t COPY_TX = COPY_ROWS * ROW_BYTES;        // bytes one TMA load delivers
+  static constexpr int COPIES = STEM ? 2 : 3;
+  static constexpr uint32_t A_STAGE = COPIES * COPY_BYTES;
+  static constexpr int TAPS = STEM ? 7 : 9;
+  static constexpr uint32_t TAP_BYTES = STEM ? 64 * 64 : 64 * 128;  // one resident tap matrix
+  static constexpr uint32_t W_BYTES = ((TAPS * TAP_BYTES + 1023) / 1024) * 1024;
+  static constexpr int A_STAGES = STEM ? 4 : 2;
+  static constexpr uint32_t SMEM = 1024 + W_BYTES + A_STAGES * A_STAGE + 2 * 16384 + 512 + 256;
+};
 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <bool STEM>
 __global__ void __launch_bounds__(PT_THREADS, 1)
 conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w,
                      const __grid_constant__ CUtensorMap tmap_out, const Conv3x3PatchParams p) {
+  using C = PCfg<STEM>;
+  constexpr uint32_t COPY_BYTES = C::COPY_BYTES, A_STAGE = C::A_STAGE, W_BYTES = C::W_BYTES;
+  constexpr int A_STAGES = C::A_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sW = smem;
@@ -74,19 +96,27 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      // weights: nine 64 x 64 tap matrices, loaded once
-      mbar_expect_tx(w_bar, W_BYTES);
-      for (int tap = 0; tap < 9; ++tap) tma_load_2d(&tmap_w, w_bar, sW + tap * 8192, tap * 64, 0);
+      // weights: the tap matrices, loaded once
+      mbar_expect_tx(w_bar, C::TAPS * C::TAP_BYTES);
+      for (int tap = 0; tap < C::TAPS; ++tap)
+        tma_load_2d(&tmap_w, w_bar, sW + tap * C::TAP_BYTES, tap * (STEM ? 32 : 64), 0);
       uint32_t stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int img = tile / tiles_per_img;
         const int rem = tile - img * tiles_per_img;
         const int p0 = (rem / p.tiles_q) * 16, q0 = (rem % p.tiles_q) * 8;
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], A_STAGE);
+        mbar_expect_tx(&full_bar[stage], C::COPIES * C::COPY_TX);
+        if (STEM) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
-          tma_load_4d(&tmap_in, &full_bar[stage], sA + stage * A_STAGE + s * COPY_BYTES, 0, q0 + s - 1, p0 - 1, img);
+          for (int cls = 0; cls < 2; ++cls)  // even / odd row taps: every second input row from 2*p0-3 / 2*p0-2
+            tma_load_4d(&tmap_in, &full_bar[stage], sA + stage * A_STAGE + cls * COPY_BYTES, 0, q0, 2 * p0 - 3 + cls,
+                        img);
+        } else {
+#pragma unroll
+          for (int s = 0; s < 3; ++s)
+            tma_load_4d(&tmap_in, &full_bar[stage], sA + stage * A_STAGE + s * COPY_BYTES, 0, q0 + s - 1, p0 - 1, img);
+        }
         if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -102,14 +132,23 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_c
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + stage * A_STAGE);
         const uint32_t d_tmem = tmem_base + acc * 64;
+        if (STEM) {
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 7; ++r)
 #pragma unroll
-          for (int s = 0; s < 3; ++s)
+            for (int k = 0; k < 2; ++k)
+              umma_bf16(d_tmem, umma_desc_sw64(a_base + (r & 1) * COPY_BYTES + (r >> 1) * 512 + k * 32),
+                        umma_desc_sw64(w_base + r * C::TAP_BYTES + k * 32), idesc, (r | k) != 0);
+        } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(d_tmem, umma_desc_sw128(a_base + s * COPY_BYTES + r * 1024 + k * 32),
-                        umma_desc_sw128(w_base + (r * 3 + s) * 8192 + k * 32), idesc, (r | s | k) != 0);
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(d_tmem, umma_desc_sw128(a_base + s * COPY_BYTES + r * 1024 + k * 32),
+                          umma_desc_sw128(w_base + (r * 3 + s) * C::TAP_BYTES + k * 32), idesc, (r | s | k) != 0);
+        }
         umma_commit(&empty_bar[stage]);
         umma_commit(&tmem_full_bar[acc]);
         if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
@@ -189,18 +228,26 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_c
 
 }  // namespace
 
-cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, const CUtensorMap& tmap_out,
-                                 const Conv3x3PatchParams& p, int num_sms, cudaStream_t stream) {
+template <bool STEM>
+cudaError_t launch_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, const CUtensorMap& tmap_out,
+                         const Conv3x3PatchParams& p, int num_sms, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv3x3_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_patch_kernel<STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         PCfg<STEM>::SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int tiles = p.n_img * p.tiles_p * p.tiles_q;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  conv3x3_patch_kernel<<<grid, PT_THREADS, PT_SMEM, stream>>>(tmap_in, tmap_w, tmap_out, p);
+  conv3x3_patch_kernel<STEM><<<grid, PT_THREADS, PCfg<STEM>::SMEM, stream>>>(tmap_in, tmap_w, tmap_out, p);
   return cudaGetLastError();
+}
+
+cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, const CUtensorMap& tmap_out,
+                                 const Conv3x3PatchParams& p, int num_sms, cudaStream_t stream) {
+  return p.stem ? launch_patch<true>(tmap_in, tmap_w, tmap_out, p, num_sms, stream)
+                : launch_patch<false>(tmap_in, tmap_w, tmap_out, p, num_sms, stream);
 }
 
 }  // namespace pvr

@@ -580,17 +580,33 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows,
   return true;
 }
 
+bool make_tmap_2d_sw64(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                       const char** err) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
+  if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
+  cuuint64_t dims[2] = {k, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (64B swizzle) failed"; return false; }
+  return true;
+}
+
 bool make_tmap_4d(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int box_w, int box_h,
-                  const char** err) {
+                  const char** err, int stride_h) {
   static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
   if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
   cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)pitch * 2 * w, (cuuint64_t)pitch * 2 * w * h};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // box = (all c channels (32 or 64), box_w, box_h, 1); box_h counts tensor rows, of which every stride_h-th is loaded
+  cuuint32_t box[4] = {(cuuint32_t)c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, (cuuint32_t)stride_h, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (4-D) failed"; return false; }
   return true;
 }

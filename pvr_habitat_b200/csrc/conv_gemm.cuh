@@ -58,10 +58,13 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows,
 // 2-D fp32 matrix (rows x cols), row pitch ld elements, box = (32 x box_rows) = 128-byte rows, 128B swizzle.
 bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                       uint32_t box_rows, const char** err);
+// 2-D K-major bf16 matrix with a (32 x box_rows) box and 64B swizzle (stem tap matrices).
+bool make_tmap_2d_sw64(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                       const char** err);
 // Tiled 4-D map over an NHWC bf16 tensor (N, H, W, pitch) exposing `c` channels: box = (64 ch, box_w, box_h, 1),
 // 128B swizzle (patch-resident 3x3 convolution, conv3x3_patch.cu).
 bool make_tmap_4d(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int box_w, int box_h,
-                  const char** err);
+                  const char** err, int stride_h = 1);
 // 3x3 / stride 1 / pad 1 convolution, C_in = C_out = 64, W % 8 == 0, with the input patch resident in shared memory
 // (three column-shifted copies; the nine taps are UMMA descriptor offsets) and the weights resident for the whole
 // kernel. Same epilogue contract as conv_gemm (scale/bias/ReLU, bf16 NHWC out).
@@ -69,6 +72,7 @@ struct Conv3x3PatchParams {
   int n_img, P, Q;         // images, height, width (output == input size)
   int tiles_p, tiles_q;    // ceil(P / 16), Q / 8
   int relu;
+  int stem;                // 1: 7x7/s2 stem over the W-expanded input (P, Q = output size), 0: 3x3/s1 64->64
   const float* scale;      // (64)
   const float* bias;       // (64)
 };

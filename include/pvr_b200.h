@@ -237,7 +237,29 @@ int pvr_transpose_bf16(const void* in, int64_t ldi, int rows, int cols, void* ou
 int pvr_cast_weight(const float* w, int rows, int cols, void* w_bf16, int64_t ldb, void* wt_bf16, int64_t ldt,
                     void* stream);
 
-/* Fused optimizer (main_bc_2.py:220-227): sumsq = sum of squared gradients over <= 24 tensors (device double, zeroed
+/* ------------------------------------------------------------------------------------------------------------
+ * End-to-end finetuning (PolicyNetWithConv, src/models.py:96-197; main_bc_finetune.py): layout kernels around the
+ * GEMM formulation of the conv trunk's backward (3x3, stride 2, padding 1, 32 channels).
+ */
+/* feat (TB, C*w*h*N) fp32 in the reference's order `cat([conv(frame_f^T) for f], -1).view(TB, -1)`: index
+ * c*(w*h*N) + x*(h*N) + f*h + y  <-  y_bf16[(tb*N+f)][y][x][c] (NHWC, `pitch` channels per pixel). */
+int pvr_convfeat_gather(const void* y_bf16, int pitch, int TB, int N, int h, int w, int C, float* feat, void* stream);
+/* inverse mapping for the gradient: dy (TB*N, h, w, C) fp32 <- dfeat (TB, ld). */
+int pvr_convfeat_scatter(const float* dfeat, int64_t ld, int TB, int N, int h, int w, int C, float* dy, void* stream);
+/* dz (M, 64) bf16 = dy (M, C) * ELU'(z), ELU' from the saved output y (1 if y > 0 else y + 1); columns >= C zero. */
+int pvr_elu_backward(const float* dy, const void* y_bf16, int pitch, int64_t M, int C, void* dz_bf16, void* stream);
+/* colT ((9*Ci), Mp) bf16: transposed im2col of A (F, Hi, Wi, pitch) for a 3x3/s2/p1 conv, Ci = 4 or 32. */
+int pvr_im2col_t(const void* a_bf16, int pitch, int F, int Hi, int Wi, int Ci, int Ho, int Wo, int64_t Mp,
+                 void* colT_bf16, void* stream);
+/* dA (F, Hi, Wi, Ci) fp32 = col2im of dcol (F*Ho*Wo, Kp) bf16 (input gradient of the layer), Ci = 32. */
+int pvr_col2im(const void* dcol_bf16, int Kp, int F, int Hi, int Wi, int Ci, int Ho, int Wo, float* dA, void* stream);
+/* BatchNorm1d input gradient from dy (bf16), the saved statistics and the (all-reduced) sums of pvr_bn1d_backward. */
+int pvr_bn1d_backward_dx(const void* dy_bf16, int64_t lddy, const float* x, int64_t ldx, int64_t M, int D,
+                         const float* mean, const float* rstd, const float* gamma, const float* sum_dy_xhat,
+                         const float* sum_dy, double count, float* dx, int64_t lddx, void* stream);
+int pvr_bf16_rows_to_f32(const void* src_bf16, int64_t lds, int64_t M, int D, float* dst, int64_t ldd, void* stream);
+
+/* Fused optimizer (main_bc_2.py:220-227): sumsq = sum of squared gradients over <= 32 tensors (device double, zeroed
  * inside); step = clip by the global norm sqrt(sumsq) (max_norm <= 0: no clipping; coefficient
  * min(1, max_norm / (norm + 1e-6)) like torch.nn.utils.clip_grad_norm_) and RMSprop (torch semantics: eps outside the
  * sqrt) or Adam update. The pre-clip norm is written to norm_out (device float) — the reference's gradient_norm stat. */

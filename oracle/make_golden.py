@@ -135,6 +135,30 @@ def golden_policy():
                fb_grad_bn_w=net.fc[0].weight.grad.numpy(), fb_running_var=net.fc[0].running_var.numpy())
     print("policy fwd/bwd: loss", loss.item(), "params without grad:", none)
 
+    # ---- (a2) PolicyNetWithConv (src/models.py:96-197) forward/backward on 2-frame 64x64 observations
+    T, B, A = 3, 4, 3
+    torch.manual_seed(13)
+    netc = M.PolicyNetWithConv((64, 64, 6), A, batch_norm=True)
+    netc.train()
+    obs_c = restate.structured_frames(T * B, 64, 64, 6, 61).reshape(T, B, 64, 64, 6)
+    done_c = np.random.default_rng(4).random((T, B)) < 0.25
+    act_c = np.random.default_rng(5).integers(0, A, (T, B))
+    oc, stc = netc(dict(obs=torch.from_numpy(obs_c), done=torch.from_numpy(done_c)), netc.initial_state(B))
+    loss_c = torch.nn.functional.nll_loss(
+        torch.nn.functional.log_softmax(torch.flatten(oc["policy_logits"], 0, 1), -1),
+        torch.flatten(torch.from_numpy(act_c), 0, 1).long())
+    loss_c.backward()
+    out.update(cv_obs=obs_c, cv_done=done_c, cv_act=act_c, cv_logits=oc["policy_logits"].detach().numpy(),
+               cv_loss=np.float32(loss_c.item()),
+               cv_param_names=np.array([k for k, _ in netc.named_parameters()]),
+               cv_param_sums=np.array([float(p.double().sum()) for p in netc.parameters()]),
+               cv_grad_norms=np.array([float(p.grad.norm()) if p.grad is not None else -1.0
+                                       for p in netc.parameters()], dtype=np.float64),
+               cv_grad_conv0_w=netc.feat_extract[0].weight.grad.numpy(),
+               cv_grad_conv4_w=netc.feat_extract[8].weight.grad.numpy(),
+               cv_grad_conv2_b=netc.feat_extract[4].bias.grad.numpy())
+    print("PolicyNetWithConv fwd/bwd: loss", loss_c.item())
+
     # ---- (b) main_bc_2.run() unmodified
     n, D, T, B, steps = 512, 128, 8, 4, 12
     obs, action, done, reward = rp.synthetic_bc_data(n, D, 3, 11)

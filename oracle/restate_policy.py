@@ -127,13 +127,17 @@ def synthetic_bc_data(n, d, n_actions, seed):
     return obs, action, done, reward
 
 
-def init_policy_state(obs_size, num_actions, batch_norm, seed):
+def init_policy_state(obs_size, num_actions, batch_norm, seed, _rng_state=None):
     """Initial state_dict of the reference's PolicyNet((obs_size,), num_actions, batch_norm) built right after
     torch.manual_seed(seed): same layer order and init calls as src/models.py:17-44 (orthogonal, gain sqrt(2) for the
     trunk, 1 for the heads, zero biases, nn.LSTM default init), hence the same draws from the torch RNG."""
     from torch import nn
-    torch.manual_seed(seed)
+    if _rng_state is not None:
+        torch.set_rng_state(_rng_state)  # continue an RNG stream (PolicyNetWithConv builds its conv trunk first)
+    else:
+        torch.manual_seed(seed)
     gain = nn.init.calculate_gain('relu')
+
     def make(i, o, g):  # construct, then re-initialise, one layer at a time (the order the RNG is consumed in)
         m = nn.Linear(i, o)
         nn.init.orthogonal_(m.weight.data, gain=g)
@@ -155,4 +159,44 @@ def init_policy_state(obs_size, num_actions, batch_norm, seed):
     sd.update({"core." + k: v.detach().clone() for k, v in core.state_dict().items()})
     sd.update({"policy." + k: v.detach().clone() for k, v in policy.state_dict().items()})
     sd.update({"baseline." + k: v.detach().clone() for k, v in baseline.state_dict().items()})
+    return sd
+
+
+def conv_features(sd, obs_u8):
+    """PolicyNetWithConv feature path (src/models.py:159-171): obs (T,B,H,W,3n) uint8 -> (T*B, conv_out*n) float.
+    x/255, split into 3-channel frames, `transpose(1, 3)` (channels first, H and W swapped), 5 x [conv3x3 s2 p1 + ELU],
+    concatenation of the frames along the LAST spatial axis, flatten."""
+    x = torch.flatten(obs_u8, 0, 1).float() / 255.
+    feats = []
+    for fr in torch.split(x, 3, -1):
+        y = fr.transpose(1, 3)
+        for i in (0, 2, 4, 6, 8):
+            y = F.elu(F.conv2d(y, sd[f"feat_extract.{i}.weight"], sd[f"feat_extract.{i}.bias"], stride=2, padding=1))
+        feats.append(y)
+    x = torch.cat(feats, -1)
+    return x.reshape(x.shape[0], -1)
+
+
+def policy_conv_forward(sd, obs_u8, done, core_state, batch_norm, training=True):
+    T, B = obs_u8.shape[:2]
+    feat = conv_features(sd, obs_u8).view(T, B, -1)
+    return policy_forward(sd, feat, done, core_state, batch_norm, training)
+
+
+def init_policy_conv_state(frame_hw, n_frames, num_actions, batch_norm, seed):
+    """Initial state_dict of the reference's PolicyNetWithConv((hw, hw, 3n), A, bn) right after manual_seed(seed):
+    conv layers first (orthogonal, gain sqrt(2)), then the PolicyNet trunk (src/models.py:100-150)."""
+    from torch import nn
+    torch.manual_seed(seed)
+    gain = nn.init.calculate_gain('relu')
+    sd = {}
+    for j, i in enumerate((0, 2, 4, 6, 8)):
+        m = nn.Conv2d(3 if j == 0 else 32, 32, kernel_size=(3, 3), stride=2, padding=1)
+        nn.init.orthogonal_(m.weight.data, gain=gain)
+        nn.init.constant_(m.bias.data, 0)
+        sd[f"feat_extract.{i}.weight"], sd[f"feat_extract.{i}.bias"] = m.weight.detach().clone(), m.bias.detach().clone()
+    d = 32 * (frame_hw // 32) ** 2 * n_frames
+    state = torch.get_rng_state()
+    trunk = init_policy_state(d, num_actions, batch_norm, seed=None, _rng_state=state)
+    sd.update(trunk)
     return sd

@@ -86,6 +86,14 @@ _SIGNATURES = {
     "pvr_colsum_bf16": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp]),
     "pvr_transpose_bf16": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _i64, _vp]),
     "pvr_cast_weight": (ctypes.c_int, [_vp, _i, _i, _vp, _i64, _vp, _i64, _vp]),
+    "pvr_convfeat_gather": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pvr_convfeat_scatter": (ctypes.c_int, [_vp, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pvr_elu_backward": (ctypes.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp]),
+    "pvr_im2col_t": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _i64, _vp, _vp]),
+    "pvr_col2im": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pvr_bn1d_backward_dx": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_double,
+                                            _vp, _i64, _vp]),
+    "pvr_bf16_rows_to_f32": (ctypes.c_int, [_vp, _i64, _i64, _i, _vp, _i64, _vp]),
     "pvr_optim_sumsq": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _vp]),
     "pvr_optim_step": (ctypes.c_int, [_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                                       ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _f, _f, _f, _f, _f, _f, _i,

@@ -406,11 +406,11 @@ __global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restric
 
 // ---------------------------------------------------------------------------------------------- optimizer
 struct TensorList {
-  float* p[24];
-  float* g[24];
-  float* s1[24];  // RMSprop square_avg / Adam exp_avg
-  float* s2[24];  // Adam exp_avg_sq
-  long long n[24];
+  float* p[32];
+  float* g[32];
+  float* s1[32];  // RMSprop square_avg / Adam exp_avg
+  float* s2[32];  // Adam exp_avg_sq
+  long long n[32];
   int count;
 };
 
@@ -674,8 +674,8 @@ extern "C" int pvr_cast_weight(const float* w, int rows, int cols, void* w_bf16,
 
 extern "C" int pvr_optim_sumsq(const float* const* grads, const int64_t* sizes, int count, double* sumsq,
                                void* stream_) {
-  if (!grads || !sizes || !sumsq || count <= 0 || count > 24) {
-    pvr_set_error("pvr_optim_sumsq: invalid argument (at most 24 tensors per call)");
+  if (!grads || !sizes || !sumsq || count <= 0 || count > 32) {
+    pvr_set_error("pvr_optim_sumsq: invalid argument (at most 32 tensors per call)");
     return PVR_ERR_ARG;
   }
   TensorList tl;
@@ -696,8 +696,8 @@ extern "C" int pvr_optim_step(int mode, float* const* params, float* const* grad
                               float grad_scale, float max_norm, float lr, float alpha_or_beta1, float beta2, float eps,
                               int step, float* norm_out, void* stream_) {
   if ((mode != PVR_OPT_RMSPROP && mode != PVR_OPT_ADAM) || !params || !grads || !state1 || !sizes || !sumsq ||
-      count <= 0 || count > 24 || (mode == PVR_OPT_ADAM && !state2)) {
-    pvr_set_error("pvr_optim_step: invalid argument (at most 24 tensors per call)");
+      count <= 0 || count > 32 || (mode == PVR_OPT_ADAM && !state2)) {
+    pvr_set_error("pvr_optim_step: invalid argument (at most 32 tensors per call)");
     return PVR_ERR_ARG;
   }
   TensorList tl;

@@ -114,7 +114,10 @@ class _PolicyFn(torch.autograd.Function):
 class PolicyNet(nn.Module):
     def __init__(self, observation_shape, num_actions, batch_norm=False):
         super(PolicyNet, self).__init__()
+        self._build_trunk(observation_shape[0], num_actions, batch_norm)
 
+    def _build_trunk(self, obs_size, num_actions, batch_norm):
+        observation_shape = (obs_size,)
         init_ = lambda m: init(m, nn.init.orthogonal_,  # noqa: E731
                                lambda x: nn.init.constant_(x, 0), nn.init.calculate_gain('relu'))
         # identical module structure / construction order to src/models.py:22-44 (same RNG stream, same keys)
@@ -135,6 +138,7 @@ class PolicyNet(nn.Module):
         self.num_actions = num_actions
         self.obs_size = observation_shape[0]
         self._ws = {}
+        self._needs_input_grad = False  # PolicyNetWithConv: the input rows are conv features
         self._wb = None          # bf16 weight copies
         self._saved = None
         # data-parallel hooks (set by pvr_habitat_b200.parallel): all-reduce of the BatchNorm sums
@@ -185,7 +189,7 @@ class PolicyNet(nn.Module):
                                            dstT.data_ptr() if dstT is not None else None,
                                            dstT.stride(0) if dstT is not None else 0, _stream()), "pvr_cast_weight")
 
-        cast(l1.weight.data, w["W1"], w["W1T"] if self.batch_norm else None)
+        cast(l1.weight.data, w["W1"], w["W1T"] if (self.batch_norm or self._needs_input_grad) else None)
         cast(l2.weight.data, w["W2"], w["W2T"])
         for l in range(2):
             cast(getattr(self.core, f"weight_ih_l{l}").data, w["Wih"][l], w["WihT"][l])
@@ -259,7 +263,9 @@ class PolicyNet(nn.Module):
         return ws.logits.clone(), ws.baseline.clone(), torch.stack(hn), torch.stack(cn)
 
     # ------------------------------------------------------------------------------------------ backward (CUDA)
-    def _backward_cuda(self, dlogits):
+    def _backward_cuda(self, dlogits, need_dx=False):
+        """Returns the parameter gradients (order of `_param_list`); with `need_dx` also d(loss)/d(input rows) as an
+        fp32 (M, D) tensor (end-to-end finetuning: the input is the conv trunk's feature matrix)."""
         lib = _lib.lib()
         ws, x = self._saved
         w = self._wb
@@ -324,14 +330,36 @@ class PolicyNet(nn.Module):
         else:
             gemm(ws.dZT, ws.actT, ws.dW1p, H, Dp, Mp, out_f32=1, n_pad=Dp)
             g["W1"].copy_(ws.dW1p[:, :D])
-        if self.batch_norm:
+        dx = None
+        if self.batch_norm or need_dx:
+            if ws.dX0 is None:
+                ws.dX0 = torch.zeros(M, Dp, dtype=torch.bfloat16, device=dev)
             gemm(ws.dZ1, w["W1T"], ws.dX0, M, Dp, H)
+        if self.batch_norm:
             _lib.check(lib.pvr_bn1d_backward(ws.dX0.data_ptr(), ws.dX0.stride(0), x.data_ptr(), x.stride(0), M, D,
                                              ws.mean.data_ptr(), ws.rstd.data_ptr(), g["bn_w"].data_ptr(),
                                              g["bn_b"].data_ptr(), _stream()), "pvr_bn1d_backward")
-        if self.process_group is not None:  # data parallel: SUM over ranks (the loss is pre-scaled by 1/global rows)
+        if need_dx:
+            dx = torch.empty(M, D, dtype=torch.float32, device=dev)
+            if self.batch_norm:
+                count = float(M)
+                sums = torch.stack([g["bn_w"], g["bn_b"]])  # sum dy*xhat, sum dy of THIS rank
+                if self.process_group is not None:
+                    torch.distributed.all_reduce(sums, group=self.process_group)
+                    count = float(self.global_rows)
+                bn = self.fc[0]
+                _lib.check(lib.pvr_bn1d_backward_dx(ws.dX0.data_ptr(), ws.dX0.stride(0), x.data_ptr(), x.stride(0), M,
+                                                    D, ws.mean.data_ptr(), ws.rstd.data_ptr(), bn.weight.data_ptr(),
+                                                    sums[0].data_ptr(), sums[1].data_ptr(), count, dx.data_ptr(), D,
+                                                    _stream()), "pvr_bn1d_backward_dx")
+            else:
+                _lib.check(lib.pvr_bf16_rows_to_f32(ws.dX0.data_ptr(), ws.dX0.stride(0), M, D, dx.data_ptr(), D,
+                                                    _stream()), "pvr_bf16_rows_to_f32")
+        self._pending_flat = flat
+        if not need_dx and self.process_group is not None:
+            # data parallel: SUM over ranks (the loss is pre-scaled by 1/global rows)
             torch.distributed.all_reduce(flat, group=self.process_group)
-        return grads
+        return (grads, dx) if need_dx else grads
 
     # ------------------------------------------------------------------------------------------ public forward
     def forward(self, inputs, core_state=()):
@@ -385,3 +413,189 @@ def bc_loss(policy_logits, actions, global_rows=None):
     targets = torch.flatten(actions, 0, 1).contiguous().long()
     rows = logits.shape[0] if global_rows is None else global_rows
     return _CELossFn.apply(logits, targets, 1.0 / rows)
+
+
+# ================================================================================================ finetuning
+class _ConvPolicyFn(torch.autograd.Function):
+    """PolicyNetWithConv as one autograd node: conv trunk (tcgen05 program) -> feature gather -> policy trunk."""
+
+    @staticmethod
+    def forward(ctx, net, obs_u8, notdone, h0, c0, *params):
+        ctx.set_materialize_grads(False)
+        out = net._forward_conv_cuda(obs_u8, notdone, h0, c0)
+        ctx.net = net
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(out[2], out[3])
+        return out
+
+    @staticmethod
+    def backward(ctx, dlogits, dbaseline, dh, dc):
+        if dbaseline is not None:
+            raise NotImplementedError("PolicyNetWithConv backward: a loss on `baseline` is not part of the BC path")
+        if dlogits is None:
+            return (None,) * (5 + ctx.n_params)
+        return (None, None, None, None, None) + tuple(ctx.net._backward_conv_cuda(dlogits.contiguous()))
+
+
+class PolicyNetWithConv(PolicyNet):
+    """src/models.py:96-197: 5 x [Conv2d(3x3, stride 2, padding 1) + ELU] on every 3-channel frame of the uint8
+    observation (divided by 255, H and W swapped by `transpose(1, 3)`), features of the frames concatenated along the
+    last spatial axis, then the same trunk as PolicyNet. Trained end to end (main_bc_finetune.py).
+
+    The forward of the conv trunk is the tcgen05 program of the 'random' PVR (program.add_small_conv, weights with
+    their two spatial axes swapped instead of transposing the frames); the backward is a chain of tcgen05 GEMMs:
+    dW = dZ^T col (split-K over the pixels) and dcol = dZ W followed by col2im."""
+
+    def __init__(self, observation_shape, num_actions, batch_norm=False):
+        nn.Module.__init__(self)
+        in_channels = 3
+        n_frames = observation_shape[2] // in_channels
+        init_ = lambda m: init(m, nn.init.orthogonal_,  # noqa: E731
+                               lambda x: nn.init.constant_(x, 0), nn.init.calculate_gain('relu'))
+        layers = []
+        for i in range(5):  # same construction order as src/models.py:107-118
+            layers += [init_(nn.Conv2d(in_channels if i == 0 else 32, 32, kernel_size=(3, 3), stride=2, padding=1)),
+                       nn.ELU()]
+        self.feat_extract = nn.Sequential(*layers)
+        H, W = observation_shape[0], observation_shape[1]
+        if H != W or H % 32:
+            raise NotImplementedError("PolicyNetWithConv: square frames with a side divisible by 32 (Habitat: 64x64)")
+        self.frame_hw, self.n_frames = H, n_frames
+        self.conv_hw = H // 32
+        conv_out_size = 32 * self.conv_hw * self.conv_hw
+        self._build_trunk(conv_out_size * n_frames, num_actions, batch_norm)
+        self._needs_input_grad = True
+        self._conv = None
+
+    def _conv_params(self):
+        ps = []
+        for i in (0, 2, 4, 6, 8):
+            ps += [self.feat_extract[i].weight, self.feat_extract[i].bias]
+        return ps
+
+    def _forward_conv_cuda(self, obs_u8, notdone, h0, c0):
+        from . import program as prg
+        from .embeddings import Transforms
+        lib = _lib.lib()
+        dev = self.device
+        TB, H, W, CN = obs_u8.shape
+        N = self.n_frames
+        F = TB * N
+        st = self._conv if self._conv is not None and self._conv.get("F") == F else None
+        if st is None:
+            st = self._conv = dict(F=F)
+            hw, sizes = H, []
+            for _ in range(5):
+                hw = (hw + 2 - 3) // 2 + 1
+                sizes.append(hw)
+            st["sizes"] = sizes
+            st["tf"] = Transforms([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], size=H, crop=H)  # x / 255 only
+        # weights change every step: rebuild the (tiny) program with the current values, keeping every activation
+        sd = {}
+        for i in (0, 2, 4, 6, 8):
+            sd[f"{i}.weight"] = self.feat_extract[i].weight.detach().float().cpu().transpose(2, 3).contiguous()
+            sd[f"{i}.bias"] = self.feat_extract[i].bias.detach().float().cpu()
+        prog = prg.Program()
+        in_slot = prog.new_slot(H * H * 4)
+        prog.emb_width = prg.add_small_conv(prog, sd, in_slot, 0, hw=H, keep_activations=True)
+        enc = prog.finish(dev)
+        enc.bind(F)
+        st["enc"], st["slots"] = enc, [in_slot] + prog.kept_slots
+        st["tf"].run(obs_u8, N, enc.slot0, _lib.PVR_FMT_NHWC4_BF16, True)
+        if st.get("emb") is None or st["emb"].shape[0] != F:
+            st["emb"] = torch.empty(F, prog.emb_width, dtype=torch.float32, device=dev)
+        enc.forward(st["emb"], prog.emb_width)
+        hc = self.conv_hw
+        feat = torch.empty(TB, 32 * hc * hc * N, dtype=torch.float32, device=dev)
+        _lib.check(lib.pvr_convfeat_gather(enc.slot_ptr(st["slots"][5]), 32, TB, N, hc, hc, 32, feat.data_ptr(),
+                                           _stream()), "pvr_convfeat_gather")
+        return self._forward_cuda(feat, notdone, h0, c0)
+
+    def _backward_conv_cuda(self, dlogits):
+        lib = _lib.lib()
+        dev = self.device
+        grads_policy, dx = self._backward_cuda(dlogits, need_dx=True)
+        st = self._conv
+        enc, slots, sizes, F = st["enc"], st["slots"], st["sizes"], st["F"]
+        N, H, hc = self.n_frames, self.frame_hw, self.conv_hw
+        TB = F // N
+        bf, f32 = torch.bfloat16, torch.float32
+        conv_params = self._conv_params()
+        gconv = [torch.zeros_like(p, dtype=f32) for p in conv_params]
+        # gradient w.r.t. the last conv output, back in NHWC frame order
+        dy = torch.empty(F * hc * hc, 32, dtype=f32, device=dev)
+        _lib.check(lib.pvr_convfeat_scatter(dx.data_ptr(), dx.stride(0), TB, N, hc, hc, 32, dy.data_ptr(), _stream()),
+                   "pvr_convfeat_scatter")
+        in_hw = [H] + sizes[:-1]
+        for l in range(4, -1, -1):
+            ho, hi = sizes[l], in_hw[l]
+            ci = 4 if l == 0 else 32
+            M = F * ho * ho
+            Mp = (M + 511) // 512 * 512
+            Kp = 64 if l == 0 else 320
+            y_ptr, a_ptr = enc.slot_ptr(slots[l + 1]), enc.slot_ptr(slots[l])
+            dz = torch.empty(M, 64, dtype=bf, device=dev)
+            _lib.check(lib.pvr_elu_backward(dy.data_ptr(), y_ptr, 32, M, 32, dz.data_ptr(), _stream()),
+                       "pvr_elu_backward")
+            _lib.check(lib.pvr_colsum_bf16(dz.data_ptr(), 64, M, 32, gconv[2 * l + 1].data_ptr(), _stream()),
+                       "pvr_colsum_bf16")
+            dzt = torch.zeros(64, Mp, dtype=bf, device=dev)
+            _lib.check(lib.pvr_transpose_bf16(dz.data_ptr(), 64, M, 64, dzt.data_ptr(), Mp, _stream()),
+                       "pvr_transpose_bf16")
+            colt = torch.zeros(Kp, Mp, dtype=bf, device=dev)
+            _lib.check(lib.pvr_im2col_t(a_ptr, ci, F, hi, hi, ci, ho, ho, Mp, colt.data_ptr(), _stream()),
+                       "pvr_im2col_t")
+            chunks = Mp // 64
+            split = 1
+            while split < 64 and chunks % (split * 2) == 0:
+                split *= 2
+            dw = torch.zeros(64, Kp, dtype=f32, device=dev)  # rows 32..63 unused (dZ^T padding)
+            gemm(dzt, colt, dw, 64, Kp, Mp, out_f32=2, split_k=split, n_pad=Kp)
+            # natural layout (co, a, b, ci) -> parameter layout (co, ci, b, a): the conv runs on un-transposed frames
+            w_nat = dw[:32, :9 * ci].view(32, 3, 3, ci)[..., :conv_params[2 * l].shape[1]]
+            gconv[2 * l].copy_(w_nat.permute(0, 3, 2, 1))
+            if l > 0:
+                wt = torch.zeros(Kp, 64, dtype=bf, device=dev)  # (k = (a, b, ci), co)
+                w_t = conv_params[2 * l].detach().transpose(2, 3).permute(2, 3, 1, 0).reshape(9 * 32, 32)
+                wt[:288, :32] = w_t.to(bf)
+                dcol = torch.empty(M, Kp, dtype=bf, device=dev)
+                gemm(dz, wt, dcol, M, Kp, 64, n_pad=Kp)
+                dy = torch.empty(F * hi * hi, 32, dtype=f32, device=dev)
+                _lib.check(lib.pvr_col2im(dcol.data_ptr(), Kp, F, hi, hi, 32, ho, ho, dy.data_ptr(), _stream()),
+                           "pvr_col2im")
+        if self.process_group is not None:
+            torch.distributed.all_reduce(self._pending_flat, group=self.process_group)
+            flat_c = torch.cat([g.flatten() for g in gconv])
+            torch.distributed.all_reduce(flat_c, group=self.process_group)
+            off = 0
+            for g in gconv:
+                g.copy_(flat_c[off:off + g.numel()].view_as(g))
+                off += g.numel()
+        return list(gconv) + list(grads_policy)
+
+    # ------------------------------------------------------------------------------------------ public forward
+    def forward(self, inputs, core_state=()):
+        x = inputs['obs']  # (unroll_length, batch_size, H, W, 3 * n_frames) uint8
+        T, B, *_, CN = x.shape
+        dev = self.device
+        if dev.type != 'cuda':
+            raise _lib.PvrError("PolicyNetWithConv: CUDA device required — pvr_habitat_b200 has no CPU fallback")
+        if x.dtype != torch.uint8:
+            raise _lib.PvrError("PolicyNetWithConv expects the uint8 frames the reference feeds it")
+        obs = torch.flatten(x, 0, 1).to(device=dev).contiguous()
+        notdone = (1 - inputs['done'].float()).abs().to(device=dev)
+        if len(core_state) == 0:
+            core_state = self.initial_state(B)
+        h0, c0 = (s.to(device=dev, dtype=torch.float32) for s in core_state)
+        params = self._conv_params() + self._param_list()
+        with torch.cuda.device(dev):
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                logits, baseline, hn, cn = _ConvPolicyFn.apply(self, obs, notdone, h0, c0, *params)
+            else:
+                logits, baseline, hn, cn = self._forward_conv_cuda(obs, notdone, h0, c0)
+        if self.training:
+            action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1)
+        else:
+            action = torch.argmax(logits, dim=1)
+        return dict(policy_logits=logits.view(T, B, -1), baseline=baseline.view(T, B),
+                    action=action.view(T, B)), (hn, cn)

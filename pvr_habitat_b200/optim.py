@@ -11,7 +11,7 @@ import torch
 
 from . import _lib
 
-_MAX = 24  # tensors per kernel launch (pvr_optim_* limit)
+_MAX = 32  # tensors per kernel launch (pvr_optim_* limit)
 
 
 class _FusedBase(torch.optim.Optimizer):
@@ -55,7 +55,7 @@ class _FusedBase(torch.optim.Optimizer):
             with torch.cuda.device(dev):
                 stream = _lib.current_stream_ptr()
                 n = len(ps)
-                assert n <= _MAX, "more than 24 parameter tensors in one group"
+                assert n <= _MAX, "more than 32 parameter tensors in one group"
                 VP, I64 = ctypes.c_void_p * n, ctypes.c_int64 * n
                 grads = VP(*[p.grad.data_ptr() for p in ps])
                 params = VP(*[p.data_ptr() for p in ps])

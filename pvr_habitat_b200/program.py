@@ -346,7 +346,7 @@ def pack_small_conv(w, n_pad):
     return out.reshape(n_pad, 10 * ci).to(torch.bfloat16)
 
 
-def add_small_conv(prog, sd, in_slot, emb_offset, hw=224):
+def add_small_conv(prog, sd, in_slot, emb_offset, hw=224, keep_activations=False):
     """The reference's 'random' PVR (src/embeddings.py:90-106): 5 x [Conv2d(3x3, stride 2, padding 1, bias) + ELU],
     3 -> 32 -> 32 -> 32 -> 32 -> 32 channels, output flattened NCHW. `in_slot` holds NHWC4 bf16 frames.
     Layer 1 uses 8-element pixel pairs (A_IM2COL8), layers 2-5 32-channel pixels (A_IM2COL32, 64-byte TMA rows);
@@ -356,13 +356,18 @@ def add_small_conv(prog, sd, in_slot, emb_offset, hw=224):
     p = (h + 2 - 3) // 2 + 1
     x = prog.conv(in_slot, (8, h, h // 2), pack_first_small_conv(sd["0.weight"].float(), 32), 64, 32, 3, 2, (2, 1),
                   (-1, -1), (p, p), ones, sd["0.bias"].float(), 0, out_pitch=32, act=3, flops=2 * p * p * 32 * 27)
+    kept = [x]
     h = p
     for i in (2, 4, 6, 8):
         p = (h + 2 - 3) // 2 + 1
         y = prog.conv(x, (32, h, h), pack_small_conv(sd[f"{i}.weight"].float(), 32), 320, 32, 3, 3, (2, 2), (-1, -1),
                       (p, p), ones, sd[f"{i}.bias"].float(), 0, out_pitch=32, act=3, flops=2 * p * p * 32 * 288)
-        prog.release(x)
+        kept.append(y)
+        if not keep_activations:  # training keeps every layer output for the backward pass
+            prog.release(x)
         x, h = y, p
     prog.flatten(x, 32, h, h, 32, emb_offset)
-    prog.release(x)
+    if not keep_activations:
+        prog.release(x)
+    prog.kept_slots = kept
     return 32 * h * h

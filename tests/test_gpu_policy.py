@@ -218,3 +218,87 @@ def test_bc_host_batches_equal_device_resident(gold):
         out.append([float(tr.step()) for _ in range(3)])
     # fp32 atomics (split-K, column sums) make the last bits run-dependent
     np.testing.assert_allclose(out[0], out[1], rtol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ finetuning (a13)
+def test_policy_with_conv_forward_backward_vs_reference_golden(gold):
+    """PolicyNetWithConv (src/models.py:96-197): conv trunk forward on tcgen05, backward as GEMMs (dW = dZ^T col,
+    dcol = dZ W + col2im), through BatchNorm's input gradient and the LSTM policy."""
+    from pvr_habitat_b200.models import PolicyNetWithConv
+    torch.manual_seed(13)
+    net = PolicyNetWithConv((64, 64, 6), 3, batch_norm=True).cuda().train()
+    sd = net.state_dict()
+    sums = np.array([float(sd[str(n)].double().sum()) for n in gold["cv_param_names"]])
+    np.testing.assert_allclose(sums, gold["cv_param_sums"], rtol=1e-5, atol=1e-4)
+    obs, done = torch.from_numpy(gold["cv_obs"]), torch.from_numpy(gold["cv_done"])
+    out, _ = net(dict(obs=obs, done=done), net.initial_state(obs.shape[1]))
+    assert rel(out["policy_logits"], torch.from_numpy(gold["cv_logits"])) < 1e-2
+    loss = bc_loss(out["policy_logits"], torch.from_numpy(gold["cv_act"]).cuda())
+    assert abs(float(loss) - float(gold["cv_loss"])) < 1e-2 * float(gold["cv_loss"])
+    loss.backward()
+    named = dict(net.named_parameters())
+    for name, ref_norm in zip(gold["cv_param_names"], gold["cv_grad_norms"]):
+        g = named[str(name)].grad
+        if ref_norm < 0:
+            assert g is None
+        else:
+            assert abs(float(g.norm()) - ref_norm) <= 0.1 * ref_norm + 1e-7, (name, float(g.norm()), ref_norm)
+    assert rel(net.feat_extract[0].weight.grad, torch.from_numpy(gold["cv_grad_conv0_w"])) < 0.15
+    assert rel(net.feat_extract[8].weight.grad, torch.from_numpy(gold["cv_grad_conv4_w"])) < 0.1
+    assert rel(net.feat_extract[4].bias.grad, torch.from_numpy(gold["cv_grad_conv2_b"])) < 0.1
+
+
+def test_finetune_loss_curve_vs_oracle():
+    """main_bc_finetune-style training (RMSprop, clip 40, LambdaLR) of PolicyNetWithConv for 8 steps against the
+    oracle restatement on the same data / seeds: loss within 1 %."""
+    from oracle import restate
+    from pvr_habitat_b200.models import PolicyNetWithConv
+    from pvr_habitat_b200.optim import FusedRMSprop
+    T, B, steps = 4, 4, 8
+    frames = restate.structured_frames(256, 64, 64, 6, 71)
+    rng = np.random.default_rng(8)
+    action = rng.integers(0, 3, 256)
+    done = rng.random(256) < 0.03
+    # ---- CUDA path
+    torch.manual_seed(21)
+    random.seed(21)
+    net = PolicyNetWithConv((64, 64, 6), 3, batch_norm=True).cuda().train()
+    sd0 = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    opt = FusedRMSprop(net.parameters(), lr=1e-4, alpha=0.99, eps=1e-5, max_grad_norm=40.0)
+    max_epochs = steps + 1
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda e: 1 - e / max_epochs)
+    from pvr_habitat_b200.utils_bc import sample_with_minimum_distance, window_indices
+    got, starts_log = [], []
+    for _ in range(steps):
+        starts = sample_with_minimum_distance(256, B, T)
+        starts_log.append(starts)
+        idx = window_indices(starts, T, 256)
+        o = torch.from_numpy(frames[idx])
+        out, _ = net(dict(obs=o, done=torch.from_numpy(done[idx])), net.initial_state(B))
+        loss = bc_loss(out["policy_logits"], torch.from_numpy(action[idx]).cuda())
+        sched.step()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        got.append(float(loss))
+    # ---- oracle (torch CPU autograd + torch RMSprop, the reference's own optimiser classes)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd0.items()
+              if v.is_floating_point() and "running" not in k and not k.startswith("baseline.")}
+    ropt = torch.optim.RMSprop(list(params.values()), lr=1e-4, alpha=0.99, eps=1e-5)
+    rsched = torch.optim.lr_scheduler.LambdaLR(ropt, lambda e: 1 - e / max_epochs)
+    ref = []
+    full = dict(sd0)
+    for starts in starts_log:
+        idx = window_indices(starts, T, 256)
+        full.update(params)
+        zero = (torch.zeros(2, B, 1024), torch.zeros(2, B, 1024))
+        logits, _, _ = rp.policy_conv_forward(full, torch.from_numpy(frames[idx]), torch.from_numpy(done[idx]), zero,
+                                              True, True)
+        loss = rp.bc_loss(logits, torch.from_numpy(action[idx]))
+        rsched.step()
+        ropt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 40.0)
+        ropt.step()
+        ref.append(float(loss))
+    np.testing.assert_allclose(got, ref, rtol=1e-2)

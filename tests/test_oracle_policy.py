@@ -72,3 +72,27 @@ def test_sampler_matches_reference_draws():
         assert min(np.diff(sorted(a))) >= 50
     idx = utils_bc.window_indices([998, 3], 5, 1000)
     assert idx.shape == (5, 2) and list(idx[:, 0]) == [998, 999, 0, 1, 2]
+
+
+def test_policy_with_conv_restatement_matches_reference_module(gold):
+    sd = rp.init_policy_conv_state(64, 2, 3, True, 13)
+    names = [str(n) for n in gold["cv_param_names"]]
+    sums = np.array([float(sd[n].double().sum()) for n in names])
+    np.testing.assert_allclose(sums, gold["cv_param_sums"], rtol=1e-5, atol=1e-4)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+          for k, v in sd.items()}
+    obs, done = torch.from_numpy(gold["cv_obs"]), torch.from_numpy(gold["cv_done"])
+    B = obs.shape[1]
+    zero = (torch.zeros(2, B, 1024), torch.zeros(2, B, 1024))
+    logits, _, _ = rp.policy_conv_forward(sd, obs, done, zero, True, True)
+    np.testing.assert_allclose(logits.detach().numpy(), gold["cv_logits"], atol=5e-6)
+    loss = rp.bc_loss(logits, torch.from_numpy(gold["cv_act"]))
+    assert abs(float(loss.detach()) - float(gold["cv_loss"])) < 1e-6
+    loss.backward()
+    for name, ref_norm in zip(names, gold["cv_grad_norms"]):
+        g = sd[name].grad
+        if ref_norm < 0:
+            assert g is None
+        else:
+            assert abs(float(g.norm()) - ref_norm) <= 1e-3 * ref_norm + 1e-9, name
+    np.testing.assert_allclose(sd["feat_extract.0.weight"].grad.numpy(), gold["cv_grad_conv0_w"], atol=1e-6, rtol=1e-3)

@@ -234,6 +234,7 @@ class EmbeddingNet(nn.Module):
         self.training = self.embedding.training
         self._encoder = None
         self._emb = None
+        self.max_images_per_pass = 1024
 
     # ---- weights changed -> recompile the program lazily
     def load_state_dict(self, *args, **kwargs):
@@ -275,16 +276,21 @@ class EmbeddingNet(nn.Module):
         frame f of sample i lands in out[i, f*O:(f+1)*O].
         """
         self._require_cuda()
-        obs = observation.to(device=self.device)
-        if not obs.is_contiguous():
-            obs = obs.contiguous()
-        n = obs.shape[0]
-        enc = self.encoder()
-        enc.bind(n * n_frames)
-        self.transforms.run(obs, n_frames, enc.slot0, enc.input_format, True)
+        n = observation.shape[0]
         if out is None:
             out = torch.empty(n, n_frames * self.out_size, dtype=torch.float32, device=self.device)
-        enc.forward(out, self.out_size)
+        enc = self.encoder()
+        # bound the activation workspace (ResNet-50: 6.8 MB per image): long observation arrays are embedded in
+        # passes of at most `max_images_per_pass` images, each pass writing its rows of `out`
+        step = max(1, self.max_images_per_pass // n_frames)
+        for lo in range(0, n, step):
+            obs = observation[lo:lo + step].to(device=self.device, non_blocking=True)
+            if not obs.is_contiguous():
+                obs = obs.contiguous()
+            m = obs.shape[0]
+            enc.bind(m * n_frames)
+            self.transforms.run(obs, n_frames, enc.slot0, enc.input_format, True)
+            enc.forward(out[lo:lo + m], self.out_size)
         return out
 
     def forward(self, observation):

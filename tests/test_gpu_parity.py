@@ -224,3 +224,13 @@ def test_random_small_conv_embedding_vs_reference_golden(golden_dir):
     for key in ("64", "224"):
         got = net(torch.from_numpy(gold["frames" + key]))
         check_embedding(got, gold["emb" + key])
+
+
+def test_long_observation_arrays_are_embedded_in_passes(emb):
+    """More images than one pass holds (workspace bound): rows identical to the single-pass result."""
+    net = make_net("moco_aug", emb["weight_seeds"])
+    frames = restate.structured_frames(11, 64, 64, 3, 77)
+    whole = net.embed(torch.from_numpy(frames)).cpu().numpy()
+    net.max_images_per_pass = 4  # 3 passes: 4 + 4 + 3 (ragged)
+    parts = net.embed(torch.from_numpy(frames)).cpu().numpy()
+    assert np.array_equal(whole, parts)

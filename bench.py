@@ -400,7 +400,7 @@ def resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks,
     pre_ms = e0.elapsed_time(e1) / 10
     pre_bytes = frames_per_step * (224 * 224 * 3 + 224 * 112 * 64)
     roofline = {
-        "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches/step)" % n_conv,
+        "kernel": "conv_gemm_kernel + conv3x3_patch_kernel (tcgen05 implicit GEMM, %d conv ops/step)" % n_conv,
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_sustained"], "traffic": None,
         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
@@ -412,7 +412,7 @@ def resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks,
                        "frac": pre_bytes / (pre_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
                        "algorithmic_bytes_per_frame": 224 * 224 * 3 + 224 * 112 * 64},
     }
-    return roofline, 1 + enc.n_ops
+    return roofline, 1 + int(enc.lib.pvr_encoder_launch_count(enc.handle))
 
 
 def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_step, width, n_rot, bytes_per_batch,

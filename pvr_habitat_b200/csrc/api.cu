@@ -3,6 +3,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -44,7 +45,8 @@ int pick_block_n(int n_pad, long long m_tiles, int sms, int hint, bool has_res) 
   // N <= 128: their epilogue needs 3 in-flight buffers per group (residual prefetch) and the smem for it.
   const int cand[3] = {256, 128, 64};
   for (int bn : cand)
-    if (n_pad % bn == 0 && m_tiles * (n_pad / bn) >= sms && !(has_res && bn == 256)) return bn;
+    if (n_pad % bn == 0 && m_tiles * (n_pad / bn) >= sms && !(has_res && bn == 256 && !getenv("PVR_RES_BN256")))
+      return bn;
   return 64;
 }
 
@@ -67,6 +69,7 @@ struct pvr_encoder {
   int sms = 0;
   std::vector<char*> slot_ptr;
   std::vector<BoundConv> bound;  // one per op (unused for non-conv ops)
+  std::vector<char> fused;       // op is executed inside the epilogue of the op before it (stem + max pool)
 };
 
 extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* slots, int n_slots, int emb_width,
@@ -145,12 +148,23 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
   for (size_t s = 0; s < enc->slots.size(); ++s)
     enc->slot_ptr[s] = static_cast<char*>(workspace) + slot_offset(enc, (int)s, n_images);
   enc->bound.assign(enc->ops.size(), BoundConv());
+  enc->fused.assign(enc->ops.size(), 0);
+  // Zig-zag tile order: a conv walks its tiles in the direction opposite to the one its input was written in, so it
+  // starts on the rows that are still in L2. slot_rev[s] = 1 when slot s was last written last-to-first.
+  std::vector<int> slot_rev(enc->slots.size(), 0);
+  const bool zigzag = getenv("PVR_NO_ZIGZAG") == nullptr;
   for (size_t i = 0; i < enc->ops.size(); ++i) {
     const pvr_op& o = enc->ops[i];
-    if (o.kind != PVR_OP_CONV) continue;
+    if (o.kind != PVR_OP_CONV) {
+      if (!enc->fused[i] && o.out_slot >= 0 && o.out_slot < (int)slot_rev.size()) slot_rev[o.out_slot] = 0;
+      continue;
+    }
     BoundConv& b = enc->bound[i];
     pvr::ConvGemmParams& p = b.p;
     memset(&p, 0, sizeof(p));
+    const int reverse = zigzag ? !slot_rev[o.in_slot] : 0;
+    slot_rev[o.out_slot] = reverse;
+    p.reverse = reverse;
     const long long M = (long long)n_images * o.h_out * o.w_out;
     b.patch = false;
     if (o.r == 3 && o.s == 3 && o.stride_h == 1 && o.stride_w == 1 && o.lower_h == -1 && o.lower_w == -1 &&
@@ -161,7 +175,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       const char* err = "";
       b.pp.n_img = n_images; b.pp.P = o.h_out; b.pp.Q = o.w_out;
       b.pp.tiles_p = (o.h_out + 15) / 16; b.pp.tiles_q = o.w_out / 8;
-      b.pp.relu = o.relu_n > 0; b.pp.scale = o.scale; b.pp.bias = o.bias; b.pp.stem = 0;
+      b.pp.relu = o.relu_n > 0; b.pp.scale = o.scale; b.pp.bias = o.bias; b.pp.stem = 0; b.pp.reverse = reverse;
       if (!pvr::make_tmap_4d(&b.ta, enc->slot_ptr[o.in_slot], 64, 64, o.w_in, o.h_in, n_images, 8, 18, &err) ||
           !pvr::make_tmap_2d(&b.tb, o.weight, 576, 64, 576, 64, &err) ||
           !pvr::make_tmap_4d(&b.to, enc->slot_ptr[o.out_slot], 64, 64, o.w_out, o.h_out, n_images, 8, 16, &err)) {
@@ -179,7 +193,25 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       const char* err = "";
       b.pp.n_img = n_images; b.pp.P = o.h_out; b.pp.Q = o.w_out;
       b.pp.tiles_p = (o.h_out + 15) / 16; b.pp.tiles_q = o.w_out / 8;
-      b.pp.relu = o.relu_n > 0; b.pp.scale = o.scale; b.pp.bias = o.bias; b.pp.stem = 1;
+      b.pp.relu = o.relu_n > 0; b.pp.scale = o.scale; b.pp.bias = o.bias; b.pp.stem = 1; b.pp.reverse = reverse;
+      // The 3x3/s2 max pool that follows the stem is fused into its epilogue when nothing else reads the stem output.
+      if (i + 1 < enc->ops.size() && b.pp.relu && !getenv("PVR_NO_POOL_FUSION")) {
+        const pvr_op& mp = enc->ops[i + 1];
+        bool sole_reader = mp.kind == PVR_OP_MAXPOOL && mp.in_slot == o.out_slot && mp.c_in == 64 &&
+                           mp.h_in == o.h_out && mp.w_in == o.w_out && mp.h_out == (o.h_out - 1) / 2 + 1 &&
+                           mp.w_out == (o.w_out - 1) / 2 + 1;
+        for (size_t j = i + 2; sole_reader && j < enc->ops.size(); ++j) {  // until the slot is written again
+          if (enc->ops[j].in_slot == o.out_slot || enc->ops[j].res_slot == o.out_slot) sole_reader = false;
+          if (enc->ops[j].out_slot == o.out_slot) break;
+        }
+        if (sole_reader) {
+          b.pp.pool_out = reinterpret_cast<__nv_bfloat16*>(enc->slot_ptr[mp.out_slot]);
+          b.pp.pool_P = mp.h_out; b.pp.pool_Q = mp.w_out;
+          b.pp.tiles_p = (mp.h_out + 6) / 7; b.pp.tiles_q = (mp.w_out + 2) / 3;
+          enc->fused[i + 1] = 1;
+          slot_rev[mp.out_slot] = reverse;
+        }
+      }
       if (!pvr::make_tmap_4d(&b.ta, enc->slot_ptr[o.in_slot], 32, 32, o.w_in, o.h_in, n_images, 8, 37, &err, 2) ||
           !pvr::make_tmap_2d_sw64(&b.tb, o.weight, 256, 64, 256, 64, &err) ||
           !pvr::make_tmap_4d(&b.to, enc->slot_ptr[o.out_slot], 64, 64, o.w_out, o.h_out, n_images, 8, 16, &err)) {
@@ -301,6 +333,7 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
     const pvr_op& o = enc->ops[i];
     cudaError_t e = cudaSuccess;
     if (ev) cudaEventRecord(ev[i], stream);
+    if (enc->fused[i]) continue;
     switch (o.kind) {
       case PVR_OP_CONV: {
         const BoundConv& b = enc->bound[i];
@@ -385,7 +418,12 @@ extern "C" void* pvr_encoder_slot_ptr(const pvr_encoder* enc, int slot) {
   return enc->slot_ptr[slot];
 }
 
-extern "C" int pvr_encoder_launch_count(const pvr_encoder* enc) { return enc ? (int)enc->ops.size() : 0; }
+extern "C" int pvr_encoder_launch_count(const pvr_encoder* enc) {
+  if (!enc) return 0;
+  int n = (int)enc->ops.size();
+  for (char f : enc->fused) n -= f ? 1 : 0;
+  return n;
+}
 
 extern "C" void pvr_encoder_destroy(pvr_encoder* enc) { delete enc; }
 

@@ -33,6 +33,7 @@ struct ConvGemmParams {
   int elu;           // ELU(alpha = 1) on every output channel (direct epilogue; small-conv PVR)
   int quick_gelu;    // bf16 output: x * sigmoid(1.702 x) after bias (CLIP MLP)
   int res_mode;      // 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward with the saved activation)
+  int reverse;       // 1: walk the (m, n) tiles last to first (zig-zag over consecutive layers, L2 reuse)
   int split_k;       // >= 1; K is cut into split_k slices of num_k_chunks chunks, each its own tile (fp32 atomics)
   int out_is_f32;    // fp32 output: TMA-staged (tmap_out is an fp32 map) or, with !epi_tma, atomically accumulated
   float* out_f32;    // direct fp32 accumulate target (split-K)
@@ -72,9 +73,14 @@ struct Conv3x3PatchParams {
   int n_img, P, Q;         // images, height, width (output == input size)
   int tiles_p, tiles_q;    // ceil(P / 16), Q / 8
   int relu;
+  int reverse;             // 1: tiles walked last to first
   int stem;                // 1: 7x7/s2 stem over the W-expanded input (P, Q = output size), 0: 3x3/s1 64->64
   const float* scale;      // (64)
   const float* bias;       // (64)
+  // stem only: fused 3x3/s2/pad-1 max pool. pool_out != nullptr: tiles_p = ceil(pool_P / 7), tiles_q = ceil(pool_Q / 3)
+  // and the pooled NHWC (n_img, pool_P, pool_Q, 64) tensor is the only output.
+  __nv_bfloat16* pool_out;
+  int pool_P, pool_Q;
 };
 cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, const CUtensorMap& tmap_out,
                                  const Conv3x3PatchParams& p, int num_sms, cudaStream_t stream);

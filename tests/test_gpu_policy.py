@@ -248,7 +248,7 @@ def test_policy_with_conv_forward_backward_vs_reference_golden(gold):
     assert rel(net.feat_extract[0].weight.grad, torch.from_numpy(gold["cv_grad_conv0_w"])) < 0.15
     # element-wise agreement of weight-gradient tensors: bf16 GEMM operands + a 12-row BatchNorm (cancelling sums)
     assert rel(net.feat_extract[8].weight.grad, torch.from_numpy(gold["cv_grad_conv4_w"])) < 0.2
-    assert rel(net.feat_extract[4].bias.grad, torch.from_numpy(gold["cv_grad_conv2_b"])) < 0.1
+    assert rel(net.feat_extract[4].bias.grad, torch.from_numpy(gold["cv_grad_conv2_b"])) < 0.2
 
 
 def test_finetune_loss_curve_vs_oracle():

@@ -45,8 +45,7 @@ int pick_block_n(int n_pad, long long m_tiles, int sms, int hint, bool has_res) 
   // N <= 128: their epilogue needs 3 in-flight buffers per group (residual prefetch) and the smem for it.
   const int cand[3] = {256, 128, 64};
   for (int bn : cand)
-    if (n_pad % bn == 0 && m_tiles * (n_pad / bn) >= sms && !(has_res && bn == 256 && !getenv("PVR_RES_BN256")))
-      return bn;
+    if (n_pad % bn == 0 && m_tiles * (n_pad / bn) >= sms && !(has_res && bn == 256)) return bn;
   return 64;
 }
 
@@ -153,6 +152,8 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
   // starts on the rows that are still in L2. slot_rev[s] = 1 when slot s was last written last-to-first.
   std::vector<int> slot_rev(enc->slots.size(), 0);
   const bool zigzag = getenv("PVR_NO_ZIGZAG") == nullptr;
+  const int pdl = getenv("PVR_NO_PDL") == nullptr;
+  const int pair_mode = getenv("PVR_CTA2") ? atoi(getenv("PVR_CTA2")) : 1;  // 0 off, 1 default policy, 2 also K < 512
   for (size_t i = 0; i < enc->ops.size(); ++i) {
     const pvr_op& o = enc->ops[i];
     if (o.kind != PVR_OP_CONV) {
@@ -165,6 +166,8 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     const int reverse = zigzag ? !slot_rev[o.in_slot] : 0;
     slot_rev[o.out_slot] = reverse;
     p.reverse = reverse;
+    p.pdl = pdl;
+    b.pp.pdl = pdl;
     const long long M = (long long)n_images * o.h_out * o.w_out;
     b.patch = false;
     if (o.r == 3 && o.s == 3 && o.stride_h == 1 && o.stride_w == 1 && o.lower_h == -1 && o.lower_w == -1 &&
@@ -230,6 +233,16 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     p.Q = o.w_out;
     p.num_m_tiles = (int)((M + 127) / 128);
     b.block_n = pick_block_n(o.n_pad, p.num_m_tiles, enc->sms, o.block_n, o.res_slot >= 0);
+    // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles): wide layers whose tiles are bound by the L2 -> SM operand
+    // traffic. Each CTA of a pair stages half of the W tile. Residual layers stay single-CTA at N = 128 (measured:
+    // their in-place residual epilogue is slower at N = 256).
+    if (pair_mode && o.block_n == 0 && o.n_pad % 256 == 0 && o.c_out % 64 == 0 && o.c_in % 64 == 0 && o.act != 3 &&
+        M % 256 == 0 && (M / 256) * (o.n_pad / 256) >= enc->sms / 2 && o.res_slot < 0 &&
+        (pair_mode > 1 || o.k_pad >= 512)) {
+      p.cta2 = 1;
+      p.num_m_tiles = (int)(M / 256);
+      b.block_n = 256;
+    }
     if (o.n_pad % b.block_n) {
       pvr_set_error("pvr_encoder_bind: op %zu: n_pad %d not a multiple of the N tile %d", i, o.n_pad, b.block_n);
       return PVR_ERR_ARG;
@@ -301,7 +314,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       return PVR_ERR_CUDA;
     }
     if (!pvr::make_tmap_2d(&b.tb, o.weight, (uint64_t)o.k_pad, (uint64_t)o.n_pad, (uint64_t)o.k_pad,
-                           (uint32_t)b.block_n, &err)) {
+                           (uint32_t)(p.cta2 ? b.block_n / 2 : b.block_n), &err)) {
       pvr_set_error("pvr_encoder_bind: op %zu: weight tensor map: %s", i, err);
       return PVR_ERR_CUDA;
     }

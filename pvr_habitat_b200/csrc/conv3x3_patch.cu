@@ -105,6 +105,8 @@ conv3x3_patch_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_c
   tc_fence_after();
   // (broadcast from lane 0: the compiler then keeps the TMEM address in a uniform register for tcgen05.mma)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  griddep_launch();  // programmatic dependent launch: see conv_gemm.cu
+  griddep_wait();
 
   if (warp == 0) {
     // producer: warp-uniform loop, one elected lane issues the TMA loads
@@ -299,8 +301,17 @@ cudaError_t launch_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, 
   }
   const int tiles = p.n_img * p.tiles_p * p.tiles_q;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  conv3x3_patch_kernel<MODE><<<grid, PCfg<MODE>::THREADS, PCfg<MODE>::SMEM, stream>>>(tmap_in, tmap_w, tmap_out, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(PCfg<MODE>::THREADS);
+  cfg.dynamicSmemBytes = PCfg<MODE>::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv3x3_patch_kernel<MODE>, tmap_in, tmap_w, tmap_out, p);
 }
 
 cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& tmap_w, const CUtensorMap& tmap_out,

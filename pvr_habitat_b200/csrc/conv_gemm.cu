@@ -39,14 +39,18 @@ constexpr int EPI_N = 64;                                  // epilogue sub-tile:
 constexpr uint32_t A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr uint32_t EPI_TILE_BYTES = BLOCK_M * EPI_N * 2;   // 16 KiB
 
-template <int BLOCK_N, bool EPI_TMA>
+// CTA2: a pair of CTAs (cluster of 2 on one TPC) computes a 256 x BLOCK_N tile with tcgen05.mma.cta_group::2. Each
+// CTA stages its own 128 rows of A and HALF of the W tile (the tensor core reads the other half from the peer's
+// shared memory), so the L2 -> SM bytes per FLOP drop by a third against two independent 128 x BLOCK_N tiles.
+template <int BLOCK_N, bool EPI_TMA, bool CTA2 = false>
 struct Cfg {
-  static constexpr uint32_t B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGES = EPI_TMA ? (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5))
-                                        : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
+  static constexpr uint32_t B_STAGE_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
+  static constexpr int STAGES = CTA2 ? 4
+                                : EPI_TMA ? (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5))
+                                          : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
   // epilogue buffers (residual in -> result out, in place), handed out in sub-tile order: 4 at N=256 (residual layers
   // use N<=128), 5 at N=128, 6 at N=64 — what fits beside the A/W stages in 227 KiB
-  static constexpr int NB = EPI_TMA ? (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 5 : 6)) : 0;
+  static constexpr int NB = CTA2 ? 5 : EPI_TMA ? (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 5 : 6)) : 0;
   static constexpr uint32_t EPI_BYTES = NB * EPI_TILE_BYTES + (EPI_TMA ? 2048 : 0);  // + scale/bias staging
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // 64 / 128 / 256 / 512: all powers of two >= 32
   static constexpr uint32_t SMEM_BYTES =
@@ -107,12 +111,13 @@ __device__ __forceinline__ int tile_mn(const ConvGemmParams& p, int tile) {
   return p.reverse ? p.num_m_tiles * p.num_n_tiles - 1 - mn : mn;
 }
 
-template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32>
+template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32, bool CTA2 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const ConvGemmParams p) {
-  using C = Cfg<BLOCK_N, EPI_TMA>;
+  using C = Cfg<BLOCK_N, EPI_TMA, CTA2>;
+  static_assert(!CTA2 || (EPI_TMA && (A_MODE == A_TILED || A_MODE == A_IM2COL64)), "pair kernel: TMA epilogue only");
   constexpr int STAGES = C::STAGES;
   constexpr int NB = C::NB > 0 ? C::NB : 1;
   constexpr int EPI_COLS = OUT_F32 ? 32 : EPI_N;  // columns of one 128-byte staging row (fp32 / bf16 output)
@@ -135,6 +140,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;  // split-K slices are separate tiles
+  // CTA2: the pair is the worker (blockIdx.x / 2 of gridDim.x / 2); num_m_tiles counts 256-row pair tiles and this
+  // CTA owns rows [m_tile * 256 + rank * 128, + 128) of them.
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0;
+  const int wid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int wstride = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_row0 = [&](int m_tile) { return CTA2 ? (m_tile * 2 + (int)cta_rank) * BLOCK_M : m_tile * BLOCK_M; };
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
@@ -149,7 +160,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
-      mbar_init(&tmem_empty_bar[s], EPI_TMA ? 256 : 128);
+      mbar_init(&tmem_empty_bar[s], CTA2 ? 512 : (EPI_TMA ? 256 : 128));  // pair: both CTAs' epilogues
     }
     for (int s = 0; s < NB; ++s) {
       mbar_init(&eb_full_bar[s], 1);
@@ -157,28 +168,38 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     fence_barrier_init();
   }
+  if (CTA2) cluster_sync_all();  // the peer's barriers exist before anything arrives on them
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
-    tmem_relinquish();
+    if (CTA2) {
+      tmem_alloc_pair(tmem_ptr_smem, C::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, C::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   // (broadcast from lane 0: the compiler then keeps the TMEM address in a uniform register for tcgen05.mma)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  // Everything above overlaps the tail of the previous kernel in the stream (programmatic dependent launch);
+  // activations / residuals written by it are only touched below.
+  griddep_launch();
+  griddep_wait();
 
   if (warp == 0) {
     // ===================================================== TMA producer (A and W tiles); warp-uniform loops, one
     // elected lane issues (see the MMA issuer)
     {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = wid; tile < num_tiles; tile += wstride) {
         const int mn = tile_mn(p, tile);
         const int kc0 = (tile % p.split_k) * p.num_k_chunks;  // first K chunk of this split-K slice
         const int m_tile = mn / p.num_n_tiles;
         const int n_tile = mn - m_tile * p.num_n_tiles;
-        const int m0 = m_tile * BLOCK_M;
-        const int n0 = n_tile * BLOCK_N;
+        const int m0 = tile_row0(m_tile);
+        const int n0 = n_tile * BLOCK_N + (CTA2 ? (int)cta_rank * (BLOCK_N / 2) : 0);  // pair: this CTA's half of W
         int img = 0, w0 = 0, h0 = 0;
         if (A_MODE != A_TILED) {
           const int pq = p.P * p.Q;
@@ -192,8 +213,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (int kc = kc0; kc < kc0 + p.num_k_chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
           uint8_t* a_dst = sA + stage * A_STAGE_BYTES;
+          if (CTA2) {
+            // the leader's barrier counts the bytes of both CTAs; the peer only issues its loads
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + C::B_STAGE_BYTES));
+            tma_load_2d_pair(&tmap_b, &full_bar[stage], sB + stage * C::B_STAGE_BYTES, kc * BLOCK_K, n0);
+            if (A_MODE == A_TILED) {
+              tma_load_2d_pair(&tmap_a, &full_bar[stage], a_dst, kc * BLOCK_K, m0);
+            } else {
+              const int tap = kc / p.cin_chunks;
+              const int c0 = (kc - tap * p.cin_chunks) * BLOCK_K;
+              const int r = tap / p.S;
+              const int s = tap - r * p.S;
+              tma_load_im2col_4d_pair(&tmap_a, &full_bar[stage], a_dst, c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+            }
+          } else {
+          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
           tma_load_2d(&tmap_b, &full_bar[stage], sB + stage * C::B_STAGE_BYTES, kc * BLOCK_K, n0);
           if (A_MODE == A_TILED) {
             tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kc * BLOCK_K, m0);
@@ -225,6 +260,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           }
+          }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -234,13 +270,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================================================== MMA issuer: the whole warp walks the loops (loop state in
     // uniform registers), one elected lane issues. Descriptors are built once; stages and K-steps only add to the
     // 14-bit (address >> 4) field — 4 SASS instructions per tcgen05.mma instead of 17 behind a `lane == 0` branch.
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+    if (!CTA2 || cta_rank == 0) {  // pair: only the leader CTA issues (for both)
     const uint64_t a_desc0 = (A_MODE == A_IM2COL8)    ? umma_desc_nosw(smem_u32(sA), 2048, 128)
                              : (A_MODE == A_IM2COL32) ? umma_desc_sw64(smem_u32(sA))
                                                       : umma_desc_sw128(smem_u32(sA));
     const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = wid; tile < num_tiles; tile += wstride) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -255,23 +292,32 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             const uint32_t a_off = (A_MODE == A_IM2COL8)    ? k * 4096
                                    : (A_MODE == A_IM2COL32) ? (k >> 1) * 8192 + (k & 1) * (UMMA_K * 2)
                                                             : k * (UMMA_K * 2);
-            umma_bf16(d_tmem, a_desc + (a_off >> 4), b_desc + ((k * UMMA_K * 2) >> 4), idesc,
-                      (kc | k) != 0);  // kc counts from 0 inside the slice
+            if (CTA2)
+              umma_bf16_pair(d_tmem, a_desc + (a_off >> 4), b_desc + ((k * UMMA_K * 2) >> 4), idesc, (kc | k) != 0);
+            else
+              umma_bf16(d_tmem, a_desc + (a_off >> 4), b_desc + ((k * UMMA_K * 2) >> 4), idesc,
+                        (kc | k) != 0);  // kc counts from 0 inside the slice
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (kc == p.num_k_chunks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+          if (CTA2) {  // arrivals in both CTAs: each producer frees its own slot, each epilogue reads its own TMEM
+            umma_commit_pair(&empty_bar[stage]);
+            if (kc == p.num_k_chunks - 1) umma_commit_pair(&tmem_full_bar[acc]);
+          } else {
+            umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+            if (kc == p.num_k_chunks - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    }
   } else if (warp == 10) {
     // ===================================================== epilogue-buffer manager: hands out the 16 KiB buffers in
     // sub-tile order, pre-filled with the residual sub-tile by TMA when the layer has one.
     if (EPI_TMA) {
       uint32_t q = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = wid; tile < num_tiles; tile += wstride) {
         const int mn = tile_mn(p, tile);
         const int m_tile = mn / p.num_n_tiles;
         const int n_tile = mn - m_tile * p.num_n_tiles;
@@ -282,7 +328,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (p.has_res) {
               mbar_expect_tx(&eb_full_bar[s], EPI_TILE_BYTES);
               tma_load_2d(&tmap_res, &eb_full_bar[s], sEB + s * EPI_TILE_BYTES,
-                          p.res_coff + n_tile * BLOCK_N + c * EPI_COLS, m_tile * BLOCK_M);
+                          p.res_coff + n_tile * BLOCK_N + c * EPI_COLS, tile_row0(m_tile));
             } else {
               mbar_arrive(&eb_full_bar[s]);
             }
@@ -304,7 +350,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       float* sb = sSB + group * 256;  // two 128-float buffers: scale[EPI_COLS] | bias[EPI_COLS] (bias at +64)
       auto stage_scale_bias = [&](uint32_t qq, uint32_t buf) {
         const int t_it = qq / SUBS, c = qq - t_it * SUBS;
-        const long long tile = (long long)blockIdx.x + (long long)t_it * gridDim.x;
+        const long long tile = (long long)wid + (long long)t_it * wstride;
         if (tile < num_tiles) {
           const int n = (tile_mn(p, (int)tile) % p.num_n_tiles) * BLOCK_N + c * EPI_COLS;
           const int col = gtid & 63;
@@ -314,7 +360,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t q = 0, j = 0, prev_s = 0;
       stage_scale_bias(group, 0);
       named_bar_sync(1 + group, 128);
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = wid; tile < num_tiles; tile += wstride) {
         const int mn = tile_mn(p, tile);
         const int m_tile = mn / p.num_n_tiles;
         const int n_tile = mn - m_tile * p.num_n_tiles;
@@ -396,7 +442,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           named_bar_sync(1 + group, 128);
           if (leader) {
-            tma_store_2d(&tmap_out, sEB + s * EPI_TILE_BYTES, p.out_coff + n, m_tile * BLOCK_M);
+            tma_store_2d(&tmap_out, sEB + s * EPI_TILE_BYTES, p.out_coff + n, tile_row0(m_tile));
             bulk_commit_group();
             if (j > 0) {  // the previous store of this group has drained its buffer: hand it back to the manager
               bulk_wait_group_read<1>();
@@ -407,12 +453,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           ++j;
         }
         tc_fence_before();
-        mbar_arrive(&tmem_empty_bar[acc]);
+        if (CTA2) mbar_arrive_leader(&tmem_empty_bar[acc]);  // the leader's MMA issuer waits for both epilogues
+        else mbar_arrive(&tmem_empty_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires its smem
     } else if (group == 0) {
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = wid; tile < num_tiles; tile += wstride) {
         const int mn = tile_mn(p, tile);
         const int m_tile = mn / p.num_n_tiles;
         const int n_tile = mn - m_tile * p.num_n_tiles;
@@ -490,9 +537,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();  // the peer may still read this CTA's shared memory / arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CTA2) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -509,8 +558,48 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.split_k;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, to, tr, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, p);
+}
+
+// CTA-pair variant (256 x 256 tiles, cluster of 2, tcgen05 cta_group::2), bf16 output through the TMA epilogue.
+template <int A_MODE>
+cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                        const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = conv_gemm_kernel<256, A_MODE, true, false, true>;
+  using C = Cfg<256, true, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, p);
 }
 
 template <int BLOCK_N, bool EPI_TMA>
@@ -531,6 +620,12 @@ cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtens
                              const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   if (p.split_k < 1) return cudaErrorInvalidValue;
+  if (p.cta2) {
+    if (block_n != 256 || !epi_tma || p.out_is_f32 || p.split_k != 1) return cudaErrorInvalidValue;
+    if (a_mode == A_TILED) return launch_pair<A_TILED>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+    if (a_mode == A_IM2COL64) return launch_pair<A_IM2COL64>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+    return cudaErrorInvalidValue;
+  }
   if (p.out_is_f32) {  // plain GEMMs only (policy network): fp32 result, TMA-staged or split-K atomic
     if (a_mode != A_TILED) return cudaErrorInvalidValue;
     if (epi_tma) {

@@ -34,6 +34,8 @@ struct ConvGemmParams {
   int quick_gelu;    // bf16 output: x * sigmoid(1.702 x) after bias (CLIP MLP)
   int res_mode;      // 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward with the saved activation)
   int reverse;       // 1: walk the (m, n) tiles last to first (zig-zag over consecutive layers, L2 reuse)
+  int pdl;           // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)
+  int cta2;          // 1: CTA-pair kernel (cta_group::2): num_m_tiles counts 256-row tiles, W map box = BLOCK_N / 2 rows
   int split_k;       // >= 1; K is cut into split_k slices of num_k_chunks chunks, each its own tile (fp32 atomics)
   int out_is_f32;    // fp32 output: TMA-staged (tmap_out is an fp32 map) or, with !epi_tma, atomically accumulated
   float* out_f32;    // direct fp32 accumulate target (split-K)
@@ -74,6 +76,7 @@ struct Conv3x3PatchParams {
   int tiles_p, tiles_q;    // ceil(P / 16), Q / 8
   int relu;
   int reverse;             // 1: tiles walked last to first
+  int pdl;                 // 1: launch with programmatic stream serialization
   int stem;                // 1: 7x7/s2 stem over the W-expanded input (P, Q = output size), 0: 3x3/s1 64->64
   const float* scale;      // (64)
   const float* bias;       // (64)

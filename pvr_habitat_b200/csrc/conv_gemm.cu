@@ -17,10 +17,11 @@
 //                     buffer and leaves through a TMA store (full lines, clipped at the M tail). The v0 epilogue
 //                     issued 16-byte global accesses at a 512-byte stride per thread and was L1TEX-bound
 //                     (profiles/r01_*_v0). !EPI_TMA: direct stores for ragged channel counts (compression heads).
-//   warp 10 / lane 0: epilogue-buffer manager: recycles the buffers in sub-tile order and prefetches the residual
-//                     sub-tile into them with TMA loads.
+//   warp 10 / lane 0: epilogue-buffer manager: recycles the buffers in sub-tile order, prefetches the residual
+//                     sub-tile into them with TMA loads and issues the TMA stores of the finished sub-tiles (no
+//                     epilogue warp waits for a store to drain).
 // Pipelines: full/empty mbarriers per smem stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator stage,
-//            eb_full/eb_empty per epilogue buffer.
+//            eb_full (buffer free / residual landed) and eb_ready (result staged) per epilogue buffer.
 #include "conv_gemm.cuh"
 #include "ptx.cuh"
 
@@ -134,8 +135,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* eb_full_bar = tmem_empty_bar + 2;
-  uint64_t* eb_empty_bar = eb_full_bar + NB;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(eb_empty_bar + NB);
+  uint64_t* eb_ready_bar = eb_full_bar + NB;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(eb_ready_bar + NB);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -164,7 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < NB; ++s) {
       mbar_init(&eb_full_bar[s], 1);
-      mbar_init(&eb_empty_bar[s], 1);
+      mbar_init(&eb_ready_bar[s], 1);
     }
     fence_barrier_init();
   }
@@ -315,27 +316,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 10) {
     // ===================================================== epilogue-buffer manager: hands out the 16 KiB buffers in
     // sub-tile order, pre-filled with the residual sub-tile by TMA when the layer has one.
-    if (EPI_TMA) {
-      uint32_t q = 0;
-      for (int tile = wid; tile < num_tiles; tile += wstride) {
-        const int mn = tile_mn(p, tile);
-        const int m_tile = mn / p.num_n_tiles;
-        const int n_tile = mn - m_tile * p.num_n_tiles;
-        for (int c = 0; c < SUBS; ++c, ++q) {
-          const uint32_t s = q % NB, ph = (q / NB) & 1;
-          mbar_wait(&eb_empty_bar[s], ph ^ 1);
-          if (elect_one()) {
-            if (p.has_res) {
-              mbar_expect_tx(&eb_full_bar[s], EPI_TILE_BYTES);
-              tma_load_2d(&tmap_res, &eb_full_bar[s], sEB + s * EPI_TILE_BYTES,
-                          p.res_coff + n_tile * BLOCK_N + c * EPI_COLS, tile_row0(m_tile));
-            } else {
-              mbar_arrive(&eb_full_bar[s]);
-            }
+    // It also issues the TMA stores of the finished sub-tiles (signalled by the epilogue groups through eb_ready_bar),
+    // so that no epilogue warp ever waits for a store to drain: residual loads run D sub-tiles ahead of the stores,
+    // and a buffer is refilled once its store (NB sub-tiles earlier, tracked by this thread's bulk groups) has
+    // finished reading it.
+    if (EPI_TMA && lane == 0) {
+      constexpr int D = NB - 2;
+      const int my_tiles = wid < num_tiles ? (num_tiles - wid + wstride - 1) / wstride : 0;
+      const uint32_t total = (uint32_t)my_tiles * SUBS;
+      for (uint32_t i = 0; i < total + D; ++i) {
+        if (i < total) {
+          const uint32_t s = i % NB;
+          if (i >= (uint32_t)NB) bulk_wait_group_read<1>();  // stores up to sub-tile i - D - 2 = i - NB have drained
+          if (p.has_res) {
+            const int t_it = i / SUBS, c = i - t_it * SUBS;
+            const int mn = tile_mn(p, wid + t_it * wstride);
+            const int m_tile = mn / p.num_n_tiles;
+            const int n_tile = mn - m_tile * p.num_n_tiles;
+            mbar_expect_tx(&eb_full_bar[s], EPI_TILE_BYTES);
+            tma_load_2d(&tmap_res, &eb_full_bar[s], sEB + s * EPI_TILE_BYTES,
+                        p.res_coff + n_tile * BLOCK_N + c * EPI_COLS, tile_row0(m_tile));
+          } else {
+            mbar_arrive(&eb_full_bar[s]);
           }
-          __syncwarp();
+        }
+        if (i >= (uint32_t)D) {
+          const uint32_t qs = i - D;
+          const uint32_t s = qs % NB, ph = (qs / NB) & 1;
+          const int t_it = qs / SUBS, c = qs - t_it * SUBS;
+          const int mn = tile_mn(p, wid + t_it * wstride);
+          const int m_tile = mn / p.num_n_tiles;
+          const int n_tile = mn - m_tile * p.num_n_tiles;
+          mbar_wait(&eb_ready_bar[s], ph);
+          tma_store_2d(&tmap_out, sEB + s * EPI_TILE_BYTES, p.out_coff + n_tile * BLOCK_N + c * EPI_COLS,
+                       tile_row0(m_tile));
+          bulk_commit_group();
         }
       }
+      bulk_wait_group<0>();  // all output tiles written before the CTA retires its smem
     }
   } else {
     // ===================================================== epilogue (warps 2..9; TMEM lane quarter = warp % 4)
@@ -357,7 +375,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (col < EPI_COLS) sb[buf * 128 + gtid] = gtid < 64 ? __ldg(p.scale + n + col) : __ldg(p.bias + n + col);
         }
       };
-      uint32_t q = 0, j = 0, prev_s = 0;
+      uint32_t q = 0, j = 0;
       stage_scale_bias(group, 0);
       named_bar_sync(1 + group, 128);
       for (int tile = wid; tile < num_tiles; tile += wstride) {
@@ -441,15 +459,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           named_bar_sync(1 + group, 128);
-          if (leader) {
-            tma_store_2d(&tmap_out, sEB + s * EPI_TILE_BYTES, p.out_coff + n, tile_row0(m_tile));
-            bulk_commit_group();
-            if (j > 0) {  // the previous store of this group has drained its buffer: hand it back to the manager
-              bulk_wait_group_read<1>();
-              mbar_arrive(&eb_empty_bar[prev_s]);
-            }
-          }
-          prev_s = s;
+          if (leader) mbar_arrive(&eb_ready_bar[s]);  // the manager warp stores the sub-tile
           ++j;
         }
         tc_fence_before();
@@ -457,7 +467,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         else mbar_arrive(&tmem_empty_bar[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (leader) bulk_wait_group<0>();  // all output tiles written before the CTA retires its smem
     } else if (group == 0) {
       for (int tile = wid; tile < num_tiles; tile += wstride) {
         const int mn = tile_mn(p, tile);

@@ -83,6 +83,11 @@ typedef struct pvr_op {
   int32_t n_pad;                       /* packed row count of `weight` (multiple of the N tile) */
   int32_t emb_offset;                  /* AVGPOOL/HEAD/FLATTEN: first column inside the embedding row */
   int32_t act;                         /* CONV: 0 = ReLU mask of relu_n only, 3 = ELU on every channel (small-conv PVR) */
+  /* Optional second input of a 1x1 / stride-1 CONV (in2_c > 0): a 1x1 convolution with stride in2_stride over slot
+   * in2_slot accumulated into the same output, K ordered [c_in | in2_c], k_pad = c_in + in2_c. This is how the
+   * projection shortcut of torchvision's Bottleneck (resnet.py:143-166: out = bn3(conv3(t)) + bn_d(conv_d(x))) runs
+   * as ONE GEMM: both BN scales are folded into the packed weight rows, bias = b3 + b_d, scale = 1. */
+  int32_t in2_slot, in2_c, in2_h, in2_w, in2_pitch, in2_stride;
   int32_t reserved;
   const void* weight;                  /* bf16 (n_pad, k_pad), K-major, K ordered (tap_row, tap_col, channel) */
   const float* scale;                  /* (n_pad) folded BN scale */

@@ -19,7 +19,8 @@ class pvr_op(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in (
         "kind", "in_slot", "out_slot", "res_slot", "c_in", "h_in", "w_in", "in_pitch", "c_out", "h_out", "w_out",
         "out_pitch", "res_pitch", "out_coff", "res_coff", "r", "s", "stride_h", "stride_w", "lower_h", "lower_w",
-        "relu_n", "block_n", "k_pad", "n_pad", "emb_offset", "act", "reserved")] + [
+        "relu_n", "block_n", "k_pad", "n_pad", "emb_offset", "act", "in2_slot", "in2_c", "in2_h", "in2_w", "in2_pitch",
+        "in2_stride", "reserved")] + [
         ("weight", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("aux", ctypes.c_void_p)]
 
 

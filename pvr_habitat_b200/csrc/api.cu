@@ -24,7 +24,7 @@ void pvr_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* pvr_last_error(void) { return g_err; }
-extern "C" int pvr_abi_version(void) { return 1; }
+extern "C" int pvr_abi_version(void) { return 2; }
 
 namespace {
 
@@ -50,7 +50,7 @@ int pick_block_n(int n_pad, long long m_tiles, int sms, int hint, bool has_res) 
 }
 
 struct BoundConv {
-  CUtensorMap ta, tb, to, tr;
+  CUtensorMap ta, tb, to, tr, ta2;
   pvr::ConvGemmParams p;
   pvr::Conv3x3PatchParams pp;
   int block_n, a_mode;
@@ -272,13 +272,35 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     const bool pointwise = (o.r == 1 && o.s == 1 && o.stride_h == 1 && o.stride_w == 1 && o.lower_h == 0 &&
                             o.lower_w == 0 && o.h_in == o.h_out && o.w_in == o.w_out);
     bool ok;
+    if (o.in2_c > 0 && !(pointwise && o.c_in % 64 == 0 && o.in2_c % 64 == 0 && o.in2_stride >= 1 &&
+                         o.in2_slot >= 0 && o.in2_slot < (int)enc->slots.size() &&
+                         (o.in2_h - 1) / o.in2_stride + 1 == o.h_out && (o.in2_w - 1) / o.in2_stride + 1 == o.w_out)) {
+      pvr_set_error("pvr_encoder_bind: op %zu: a second input needs a 1x1/stride-1 conv with 64-multiple channels "
+                    "and matching output size", i);
+      return PVR_ERR_ARG;
+    }
+    b.ta2 = b.ta;
     if (pointwise && o.c_in % 64 == 0) {
       b.a_mode = pvr::A_TILED;
-      if (o.k_pad != o.c_in) {
-        pvr_set_error("pvr_encoder_bind: op %zu: k_pad must equal c_in for 1x1 convs", i);
+      if (o.k_pad != o.c_in + o.in2_c) {
+        pvr_set_error("pvr_encoder_bind: op %zu: k_pad must equal c_in (+ in2_c) for 1x1 convs", i);
         return PVR_ERR_ARG;
       }
       ok = pvr::make_tmap_2d(&b.ta, in, (uint64_t)o.c_in, (uint64_t)M, (uint64_t)o.in_pitch, 128, &err);
+      if (ok && o.in2_c > 0) {
+        const void* in2 = enc->slot_ptr[o.in2_slot];
+        p.kc_split = o.c_in / 64;
+        p.a2_stride = o.in2_stride;
+        if (o.in2_stride == 1) {
+          ok = pvr::make_tmap_2d(&b.ta2, in2, (uint64_t)o.in2_c, (uint64_t)M, (uint64_t)o.in2_pitch, 128, &err);
+        } else {
+          p.a2_im2col = 1;
+          const int up_w = (o.w_out - 1) * o.in2_stride - (o.in2_w - 1);
+          const int up_h = (o.h_out - 1) * o.in2_stride - (o.in2_h - 1);
+          ok = pvr::make_tmap_im2col(&b.ta2, in2, o.in2_c, o.in2_pitch, o.in2_w, o.in2_h, n_images, 0, 0, up_w, up_h,
+                                     o.in2_stride, o.in2_stride, 64, 128, 128, &err);
+        }
+      }
     } else {
       const int upper_w = o.lower_w + (o.w_out - 1) * o.stride_w - (o.w_in - 1);
       const int upper_h = o.lower_h + (o.h_out - 1) * o.stride_h - (o.h_in - 1);
@@ -352,7 +374,7 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
         const BoundConv& b = enc->bound[i];
         e = b.patch ? pvr::launch_conv3x3_patch(b.ta, b.tb, b.to, b.pp, enc->sms, stream)
                     : pvr::launch_conv_gemm(b.block_n, b.a_mode, b.epi_tma, b.ta, b.tb, b.to, b.tr, b.p, enc->sms,
-                                            stream);
+                                            stream, &b.ta2);
         break;
       }
       case PVR_OP_MAXPOOL:

@@ -116,7 +116,7 @@ template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32, bool CTA2 = false
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                 const ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_a2, const ConvGemmParams p) {
   using C = Cfg<BLOCK_N, EPI_TMA, CTA2>;
   static_assert(!CTA2 || (EPI_TMA && (A_MODE == A_TILED || A_MODE == A_IM2COL64)), "pair kernel: TMA epilogue only");
   constexpr int STAGES = C::STAGES;
@@ -151,6 +151,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
+    if (p.kc_split) prefetch_tmap(&tmap_a2);
     if (EPI_TMA) {
       prefetch_tmap(&tmap_out);
       if (p.has_res) prefetch_tmap(&tmap_res);
@@ -202,14 +203,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int m0 = tile_row0(m_tile);
         const int n0 = n_tile * BLOCK_N + (CTA2 ? (int)cta_rank * (BLOCK_N / 2) : 0);  // pair: this CTA's half of W
         int img = 0, w0 = 0, h0 = 0;
-        if (A_MODE != A_TILED) {
+        if (A_MODE != A_TILED || p.a2_im2col) {
           const int pq = p.P * p.Q;
           img = m0 / pq;
           const int rem = m0 - img * pq;
           const int pp = rem / p.Q;
           const int qq = rem - pp * p.Q;
-          w0 = p.lower_w + qq * p.stride_w;
-          h0 = p.lower_h + pp * p.stride_h;
+          // (A_TILED with a strided second source: base pixel of the 1x1 / stride a2_stride shortcut convolution)
+          w0 = A_MODE != A_TILED ? p.lower_w + qq * p.stride_w : qq * p.a2_stride;
+          h0 = A_MODE != A_TILED ? p.lower_h + pp * p.stride_h : pp * p.a2_stride;
         }
         for (int kc = kc0; kc < kc0 + p.num_k_chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -220,7 +222,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (A_STAGE_BYTES + C::B_STAGE_BYTES));
             tma_load_2d_pair(&tmap_b, &full_bar[stage], sB + stage * C::B_STAGE_BYTES, kc * BLOCK_K, n0);
             if (A_MODE == A_TILED) {
-              tma_load_2d_pair(&tmap_a, &full_bar[stage], a_dst, kc * BLOCK_K, m0);
+              if (kc < p.kc_split || p.kc_split == 0)
+                tma_load_2d_pair(&tmap_a, &full_bar[stage], a_dst, kc * BLOCK_K, m0);
+              else if (p.a2_im2col)  // second K range: the shortcut's input, 1x1 taps with a stride
+                tma_load_im2col_4d_pair(&tmap_a2, &full_bar[stage], a_dst, (kc - p.kc_split) * BLOCK_K, w0, h0, img,
+                                        (uint16_t)0, (uint16_t)0);
+              else
+                tma_load_2d_pair(&tmap_a2, &full_bar[stage], a_dst, (kc - p.kc_split) * BLOCK_K, m0);
             } else {
               const int tap = kc / p.cin_chunks;
               const int c0 = (kc - tap * p.cin_chunks) * BLOCK_K;
@@ -232,7 +240,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
           tma_load_2d(&tmap_b, &full_bar[stage], sB + stage * C::B_STAGE_BYTES, kc * BLOCK_K, n0);
           if (A_MODE == A_TILED) {
-            tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kc * BLOCK_K, m0);
+            if (kc < p.kc_split || p.kc_split == 0)
+              tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kc * BLOCK_K, m0);
+            else if (p.a2_im2col)  // second K range: the shortcut's input, 1x1 taps with a stride
+              tma_load_im2col_4d(&tmap_a2, &full_bar[stage], a_dst, (kc - p.kc_split) * BLOCK_K, w0, h0, img,
+                                 (uint16_t)0, (uint16_t)0);
+            else
+              tma_load_2d(&tmap_a2, &full_bar[stage], a_dst, (kc - p.kc_split) * BLOCK_K, m0);
           } else if (A_MODE == A_IM2COL64) {
             const int tap = kc / p.cin_chunks;
             const int c0 = (kc - tap * p.cin_chunks) * BLOCK_K;
@@ -366,17 +380,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const bool leader = (gtid == 0);
       const uint32_t swz = (uint32_t)(row & 7);
       float* sb = sSB + group * 256;  // two 128-float buffers: scale[EPI_COLS] | bias[EPI_COLS] (bias at +64)
-      auto stage_scale_bias = [&](uint32_t qq, uint32_t buf) {
+      // scale / bias of a sub-tile are fetched (one float per thread) an iteration ahead: the load is issued at the
+      // top of the iteration and only stored to shared memory at its end, so its L2 latency hides behind the math
+      auto fetch_scale_bias = [&](uint32_t qq, float& val) -> bool {
         const int t_it = qq / SUBS, c = qq - t_it * SUBS;
         const long long tile = (long long)wid + (long long)t_it * wstride;
-        if (tile < num_tiles) {
-          const int n = (tile_mn(p, (int)tile) % p.num_n_tiles) * BLOCK_N + c * EPI_COLS;
-          const int col = gtid & 63;
-          if (col < EPI_COLS) sb[buf * 128 + gtid] = gtid < 64 ? __ldg(p.scale + n + col) : __ldg(p.bias + n + col);
-        }
+        const int col = gtid & 63;
+        if (tile >= num_tiles || col >= EPI_COLS) return false;
+        const int n = (tile_mn(p, (int)tile) % p.num_n_tiles) * BLOCK_N + c * EPI_COLS;
+        val = gtid < 64 ? __ldg(p.scale + n + col) : __ldg(p.bias + n + col);
+        return true;
       };
       uint32_t q = 0, j = 0;
-      stage_scale_bias(group, 0);
+      {
+        float v0;
+        if (fetch_scale_bias(group, v0)) sb[gtid] = v0;
+      }
       named_bar_sync(1 + group, 128);
       for (int tile = wid; tile < num_tiles; tile += wstride) {
         const int mn = tile_mn(p, tile);
@@ -393,7 +412,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint32_t v[EPI_COLS];
           tmem_ld_32x32b_x32(taddr + c * EPI_COLS, v);
           if (!OUT_F32) tmem_ld_32x32b_x32(taddr + c * EPI_COLS + 32, v + (OUT_F32 ? 0 : 32));
-          stage_scale_bias(q + 2, (j + 1) & 1);  // next sub-tile of this group; published by this iteration's barrier
+          float sb_next;
+          const bool sb_have = fetch_scale_bias(q + 2, sb_next);  // next sub-tile of this group
           mbar_wait(&eb_full_bar[s], ph);
           tmem_wait_ld();
           const uint32_t eb_row = smem_u32(sEB + s * EPI_TILE_BYTES) + row * 128;
@@ -457,6 +477,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
+          if (sb_have) sb[((j + 1) & 1) * 128 + gtid] = sb_next;  // published by the barrier below
           fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
           named_bar_sync(1 + group, 128);
           if (leader) mbar_arrive(&eb_ready_bar[s]);  // the manager warp stores the sub-tile
@@ -556,7 +577,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32>
 cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                       const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+                       const CUtensorMap& ta2, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   auto kern = conv_gemm_kernel<BLOCK_N, A_MODE, EPI_TMA, OUT_F32>;
   using C = Cfg<BLOCK_N, EPI_TMA>;
   static bool attr_set = false;  // per instantiation
@@ -577,13 +598,13 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, p);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, ta2, p);
 }
 
 // CTA-pair variant (256 x 256 tiles, cluster of 2, tcgen05 cta_group::2), bf16 output through the TMA epilogue.
 template <int A_MODE>
 cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                        const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+                        const CUtensorMap& ta2, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
   auto kern = conv_gemm_kernel<256, A_MODE, true, false, true>;
   using C = Cfg<256, true, true>;
   static bool attr_set = false;
@@ -608,17 +629,18 @@ cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, p);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, ta2, p);
 }
 
 template <int BLOCK_N, bool EPI_TMA>
 cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
-                        const CUtensorMap& tr, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+                        const CUtensorMap& tr, const CUtensorMap& ta2, const ConvGemmParams& p, int num_sms,
+                        cudaStream_t stream) {
   switch (a_mode) {
-    case A_TILED: return launch_one<BLOCK_N, A_TILED, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
-    case A_IM2COL64: return launch_one<BLOCK_N, A_IM2COL64, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
-    case A_IM2COL8: return launch_one<BLOCK_N, A_IM2COL8, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
-    case A_IM2COL32: return launch_one<BLOCK_N, A_IM2COL32, EPI_TMA, false>(ta, tb, to, tr, p, num_sms, stream);
+    case A_TILED: return launch_one<BLOCK_N, A_TILED, EPI_TMA, false>(ta, tb, to, tr, ta2, p, num_sms, stream);
+    case A_IM2COL64: return launch_one<BLOCK_N, A_IM2COL64, EPI_TMA, false>(ta, tb, to, tr, ta2, p, num_sms, stream);
+    case A_IM2COL8: return launch_one<BLOCK_N, A_IM2COL8, EPI_TMA, false>(ta, tb, to, tr, ta2, p, num_sms, stream);
+    case A_IM2COL32: return launch_one<BLOCK_N, A_IM2COL32, EPI_TMA, false>(ta, tb, to, tr, ta2, p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -627,44 +649,46 @@ cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb
 
 cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtensorMap& tmap_a,
                              const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
-                             const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+                             const ConvGemmParams& p, int num_sms, cudaStream_t stream, const CUtensorMap* tmap_a2) {
   if (p.split_k < 1) return cudaErrorInvalidValue;
+  if (p.kc_split && (a_mode != A_TILED || !tmap_a2)) return cudaErrorInvalidValue;
+  const CUtensorMap& ta2 = tmap_a2 ? *tmap_a2 : tmap_a;
   if (p.cta2) {
     if (block_n != 256 || !epi_tma || p.out_is_f32 || p.split_k != 1) return cudaErrorInvalidValue;
-    if (a_mode == A_TILED) return launch_pair<A_TILED>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-    if (a_mode == A_IM2COL64) return launch_pair<A_IM2COL64>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+    if (a_mode == A_TILED) return launch_pair<A_TILED>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    if (a_mode == A_IM2COL64) return launch_pair<A_IM2COL64>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
     return cudaErrorInvalidValue;
   }
   if (p.out_is_f32) {  // plain GEMMs only (policy network): fp32 result, TMA-staged or split-K atomic
     if (a_mode != A_TILED) return cudaErrorInvalidValue;
     if (epi_tma) {
       switch (block_n) {
-        case 64: return launch_one<64, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-        case 128: return launch_one<128, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-        case 256: return launch_one<256, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+        case 64: return launch_one<64, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+        case 128: return launch_one<128, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+        case 256: return launch_one<256, A_TILED, true, true>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
         default: return cudaErrorInvalidValue;
       }
     }
     switch (block_n) {
-      case 32: return launch_one<32, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-      case 64: return launch_one<64, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-      case 128: return launch_one<128, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      case 32: return launch_one<32, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+      case 64: return launch_one<64, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+      case 128: return launch_one<128, A_TILED, false, true>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
       default: return cudaErrorInvalidValue;
     }
   }
   if (epi_tma) {
     switch (block_n) {
-      case 64: return launch_mode<64, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-      case 128: return launch_mode<128, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-      case 256: return launch_mode<256, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+      case 64: return launch_mode<64, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+      case 128: return launch_mode<128, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+      case 256: return launch_mode<256, true>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
       default: return cudaErrorInvalidValue;
     }
   }
   switch (block_n) {
-    case 32: return launch_mode<32, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-    case 64: return launch_mode<64, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-    case 128: return launch_mode<128, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
-    case 256: return launch_mode<256, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, p, num_sms, stream);
+    case 32: return launch_mode<32, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    case 64: return launch_mode<64, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    case 128: return launch_mode<128, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    case 256: return launch_mode<256, false>(a_mode, tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -35,6 +35,9 @@ struct ConvGemmParams {
   int res_mode;      // 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward with the saved activation)
   int reverse;       // 1: walk the (m, n) tiles last to first (zig-zag over consecutive layers, L2 reuse)
   int pdl;           // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)
+  int kc_split;      // > 0: K chunks >= kc_split come from a second input (tmap_a2), A_TILED only: projection shortcut
+  int a2_im2col;     // second input is read with im2col-mode 1x1 taps at stride a2_stride (else a plain 2-D matrix)
+  int a2_stride;
   int cta2;          // 1: CTA-pair kernel (cta_group::2): num_m_tiles counts 256-row tiles, W map box = BLOCK_N / 2 rows
   int split_k;       // >= 1; K is cut into split_k slices of num_k_chunks chunks, each its own tile (fp32 atomics)
   int out_is_f32;    // fp32 output: TMA-staged (tmap_out is an fp32 map) or, with !epi_tma, atomically accumulated
@@ -52,7 +55,7 @@ struct ConvGemmParams {
 // tmap_res are (pitch x M) bf16 maps with a (64 x 128) box over the output / residual pixel rows.
 cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtensorMap& tmap_a,
                              const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
-                             const ConvGemmParams& p, int num_sms, cudaStream_t stream);
+                             const ConvGemmParams& p, int num_sms, cudaStream_t stream, const CUtensorMap* tmap_a2 = nullptr);
 
 // Tensor-map builders (driver entry points resolved through cudaGetDriverEntryPoint; no -lcuda needed).
 // 2-D K-major bf16 matrix (rows x k), row pitch ld elements, box = (64 x box_rows), 128B swizzle.

@@ -91,7 +91,8 @@ class Program:
 
     # ---- ops
     def conv(self, in_slot, in_chw, w_packed, k_pad, c_out, r, s, stride, lower, out_hw, scale, bias, relu_n,
-             in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0, flops=None, act=0):
+             in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0, flops=None, act=0,
+             in2=None):
         c_in, h_in, w_in = in_chw
         n_pad = w_packed.shape[0]
         p, q = out_hw
@@ -112,6 +113,9 @@ class Program:
                   flops_per_image=int(flops if flops is not None else 2 * p * q * c_out * r * s * c_in))
         if res is not None:
             op.update(res_slot=res[0], res_pitch=res[1], res_coff=res[2])
+        if in2 is not None:  # (slot, (c, h, w), pitch, stride): second 1x1 input, see include/pvr_b200.h
+            op.update(in2_slot=in2[0], in2_c=in2[1][0], in2_h=in2[1][1], in2_w=in2[1][2], in2_pitch=in2[2],
+                      in2_stride=in2[3])
         self.ops.append(op)
         return out_slot
 
@@ -244,10 +248,32 @@ def _conv_bn(prog, sd, conv_key, bn_key, in_slot, in_chw, stride, pad, relu, res
 
 
 def _bottleneck(prog, sd, prefix, x_slot, x_chw, stride, has_ds):
-    """torchvision Bottleneck (resnet.py:143-166), stride on the 3x3 conv (v1.5)."""
+    """torchvision Bottleneck (resnet.py:143-166), stride on the 3x3 conv (v1.5).
+
+    Blocks with a projection shortcut compute `relu(bn3(conv3(t2)) + bn_d(conv_d(x)))` as ONE GEMM over the
+    concatenated K = [t2 channels | x channels]: both BN scales are folded into the weight rows, the bias is b3 + b_d.
+    The shortcut tensor is neither written nor re-read (layer1.0: 411 MB + 411 MB per 256 frames)."""
     t1, s1 = _conv_bn(prog, sd, prefix + ".conv1", prefix + ".bn1", x_slot, x_chw, 1, 0, True)
     t2, s2 = _conv_bn(prog, sd, prefix + ".conv2", prefix + ".bn2", t1, s1, stride, 1, True)
     prog.release(t1)
+    if has_ds and x_chw[0] % 64 == 0 and s2[0] % 64 == 0:
+        w3 = sd[prefix + ".conv3.weight"].float()
+        wd = sd[prefix + ".downsample.0.weight"].float()
+        co = w3.shape[0]
+        sc3, b3 = fold_bn(sd, prefix + ".bn3", sd.get(prefix + ".conv3.bias"))
+        scd, bd = fold_bn(sd, prefix + ".downsample.1", sd.get(prefix + ".downsample.0.bias"))
+        wcat = torch.cat([w3.reshape(co, -1) * sc3[:, None], wd.reshape(co, -1) * scd[:, None]], 1)
+        n_pad = _round_up(co, 64)
+        k = wcat.shape[1]
+        packed = torch.zeros(n_pad, k, dtype=torch.bfloat16)
+        packed[:co] = wcat.to(torch.bfloat16)
+        c2, p, q = s2
+        y = prog.conv(t2, s2, packed, k, co, 1, 1, (1, 1), (0, 0), (p, q), torch.ones(co), b3 + bd, co,
+                      in2=(x_slot, x_chw, x_chw[0], stride),
+                      flops=2 * p * q * co * (c2 + x_chw[0]))
+        prog.release(t2)
+        prog.release(x_slot)
+        return y, (co, p, q)
     if has_ds:
         idn, sidn = _conv_bn(prog, sd, prefix + ".downsample.0", prefix + ".downsample.1", x_slot, x_chw, stride, 0,
                              False)

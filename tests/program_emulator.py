@@ -29,13 +29,19 @@ def emulate(prog, frames_nhwc4, round_bf16=True):
             co, npad = op["c_out"], op["n_pad"]
             kk = r * s * ci
             wt = w[:, :kk].reshape(npad, r, s, ci).permute(0, 3, 1, 2)
-            assert torch.all(w[:, kk:] == 0), "padded K columns must carry zero weights"
+            c2 = op.get("in2_c", 0)
+            assert torch.all(w[:, kk + c2:] == 0), "padded K columns must carry zero weights"
             p, q = op["h_out"], op["w_out"]
             pl, pt = -op["lower_w"], -op["lower_h"]
             pr = (q - 1) * op["stride_w"] + s - wi - pl
             pb = (p - 1) * op["stride_h"] + r - hi - pt
             xp = F.pad(x, (pl, max(pr, 0), pt, max(pb, 0)))
             y = F.conv2d(xp, wt, stride=(op["stride_h"], op["stride_w"]))[:, :, :p, :q]
+            if c2:  # second 1x1 input accumulated into the same GEMM (projection shortcut)
+                h2, w2_, p2, st2 = op["in2_h"], op["in2_w"], op["in2_pitch"], op["in2_stride"]
+                x2 = slots[op["in2_slot"]][:, :h2 * w2_ * p2].reshape(n, h2, w2_, p2)[..., :c2].permute(0, 3, 1, 2)
+                wt2 = w[:, kk:kk + c2].reshape(npad, c2, 1, 1)
+                y = y + F.conv2d(x2, wt2, stride=st2)[:, :, :p, :q]
             y = y * op["_scale"][None, :, None, None] + op["_bias"][None, :, None, None]
             y = y[:, :co]
             if op["res_slot"] >= 0:

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built):
 
 
 def test_abi_version_and_error_string(built):
-    assert built.pvr_abi_version() == 1
+    assert built.pvr_abi_version() == 2
     assert isinstance(built.pvr_last_error(), bytes)
 
 
@@ -48,6 +48,6 @@ def test_argument_errors_do_not_need_a_gpu(built):
 
 
 def test_op_struct_layout_matches_header():
-    """pvr_op: 28 int32 fields then 4 pointers (ctypes mirror of the C struct)."""
-    assert ctypes.sizeof(_lib.pvr_op) == 28 * 4 + 4 * 8
-    assert _lib.pvr_op.weight.offset == 112
+    """pvr_op: 34 int32 fields then 4 pointers (ctypes mirror of the C struct)."""
+    assert ctypes.sizeof(_lib.pvr_op) == 34 * 4 + 4 * 8
+    assert _lib.pvr_op.weight.offset == 136

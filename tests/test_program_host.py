@@ -26,7 +26,9 @@ def test_program_equals_oracle_network(variant, width):
     x4[..., :3] = x.permute(0, 2, 3, 1)
     got = emulate(prog, prg.expand_stem_input(x4), round_bf16=False)
     ref = restate.resnet50_forward(sd, variant, x)
-    assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+    # 3e-3: the four projection-shortcut blocks fold their BN scales into the packed weight rows, which are then
+    # rounded to bf16 again (a packing mistake shows up at O(1))
+    assert float((got - ref).abs().max()) <= 3e-3 * float(ref.abs().max())
 
 
 def test_stem_packing_is_the_7x7_stride2_conv():
@@ -54,7 +56,11 @@ def test_slot_planning_never_aliases_live_tensors():
             assert op["out_slot"] != op["in_slot"] and op["out_slot"] != 0
             if op["res_slot"] >= 0:
                 assert op["res_slot"] != op["in_slot"]
-    assert len(prog.ops) == 53 + 2  # 53 convs + maxpool + avgpool
+            if op.get("in2_c", 0):
+                assert op["in2_slot"] not in (op["out_slot"], op["in_slot"])
+    # 53 convs - 4 projection shortcuts (fused into conv3 as a second K range) + maxpool + avgpool
+    assert len(prog.ops) == 49 + 2
+    assert sum(1 for op in prog.ops if op.get("in2_c", 0)) == 4
     assert len(prog.slot_elems) <= 6
 
 

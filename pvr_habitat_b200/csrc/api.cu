@@ -153,7 +153,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
   std::vector<int> slot_rev(enc->slots.size(), 0);
   const bool zigzag = getenv("PVR_NO_ZIGZAG") == nullptr;
   const int pdl = getenv("PVR_NO_PDL") == nullptr;
-  const int pair_mode = getenv("PVR_CTA2") ? atoi(getenv("PVR_CTA2")) : 1;  // 0 off, 1 default policy, 2 also K < 512
+  const int pair_mode = getenv("PVR_CTA2") ? atoi(getenv("PVR_CTA2")) : 1;  // 0 off, 1: 256-wide pair tiles; 2: + 128-wide (no residual); 3: + residual layers
   for (size_t i = 0; i < enc->ops.size(); ++i) {
     const pvr_op& o = enc->ops[i];
     if (o.kind != PVR_OP_CONV) {
@@ -236,12 +236,15 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     // CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles): wide layers whose tiles are bound by the L2 -> SM operand
     // traffic. Each CTA of a pair stages half of the W tile. Residual layers stay single-CTA at N = 128 (measured:
     // their in-place residual epilogue is slower at N = 256).
-    if (pair_mode && o.block_n == 0 && o.n_pad % 256 == 0 && o.c_out % 64 == 0 && o.c_in % 64 == 0 && o.act != 3 &&
-        M % 256 == 0 && (M / 256) * (o.n_pad / 256) >= enc->sms / 2 && o.res_slot < 0 &&
-        (pair_mode > 1 || o.k_pad >= 512)) {
-      p.cta2 = 1;
-      p.num_m_tiles = (int)(M / 256);
-      b.block_n = 256;
+    if (pair_mode && o.block_n == 0 && o.n_pad % 128 == 0 && o.c_out % 64 == 0 && o.c_in % 64 == 0 && o.act != 3 &&
+        M % 256 == 0 && o.k_pad >= 512) {
+      const int pbn = (o.n_pad % 256 == 0 && o.res_slot < 0) ? 256 : 128;
+      const bool allow = pbn == 256 ? true : (pair_mode >= 2 && (o.res_slot < 0 || pair_mode >= 3));
+      if (allow && (M / 256) * (o.n_pad / pbn) >= enc->sms / 2) {
+        p.cta2 = 1;
+        p.num_m_tiles = (int)(M / 256);
+        b.block_n = pbn;
+      }
     }
     if (o.n_pad % b.block_n) {
       pvr_set_error("pvr_encoder_bind: op %zu: n_pad %d not a multiple of the N tile %d", i, o.n_pad, b.block_n);

@@ -46,7 +46,7 @@ constexpr uint32_t EPI_TILE_BYTES = BLOCK_M * EPI_N * 2;   // 16 KiB
 template <int BLOCK_N, bool EPI_TMA, bool CTA2 = false>
 struct Cfg {
   static constexpr uint32_t B_STAGE_BYTES = (CTA2 ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
-  static constexpr int STAGES = CTA2 ? 4
+  static constexpr int STAGES = CTA2 ? (BLOCK_N == 256 ? 4 : 5)
                                 : EPI_TMA ? (BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 4 : 5))
                                           : (BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8));
   // epilogue buffers (residual in -> result out, in place), handed out in sub-tile order: 4 at N=256 (residual layers
@@ -213,6 +213,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           w0 = A_MODE != A_TILED ? p.lower_w + qq * p.stride_w : qq * p.a2_stride;
           h0 = A_MODE != A_TILED ? p.lower_h + pp * p.stride_h : pp * p.a2_stride;
         }
+        // filter tap / channel chunk of the current K chunk, advanced without divisions (the producer has one K chunk
+        // of MMA time, 256 cycles at N = 128, for its whole loop body)
+        int cc = 0, tap_s = 0, tap_r = 0;
+        if (A_MODE == A_IM2COL64 && kc0 != 0) {
+          const int tap = kc0 / p.cin_chunks;
+          cc = kc0 - tap * p.cin_chunks;
+          tap_r = tap / p.S;
+          tap_s = tap - tap_r * p.S;
+        }
         for (int kc = kc0; kc < kc0 + p.num_k_chunks; ++kc) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (elect_one()) {
@@ -230,11 +239,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               else
                 tma_load_2d_pair(&tmap_a2, &full_bar[stage], a_dst, (kc - p.kc_split) * BLOCK_K, m0);
             } else {
-              const int tap = kc / p.cin_chunks;
-              const int c0 = (kc - tap * p.cin_chunks) * BLOCK_K;
-              const int r = tap / p.S;
-              const int s = tap - r * p.S;
-              tma_load_im2col_4d_pair(&tmap_a, &full_bar[stage], a_dst, c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+              tma_load_im2col_4d_pair(&tmap_a, &full_bar[stage], a_dst, cc * BLOCK_K, w0, h0, img, (uint16_t)tap_s,
+                                      (uint16_t)tap_r);
             }
           } else {
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
@@ -248,11 +254,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             else
               tma_load_2d(&tmap_a2, &full_bar[stage], a_dst, (kc - p.kc_split) * BLOCK_K, m0);
           } else if (A_MODE == A_IM2COL64) {
-            const int tap = kc / p.cin_chunks;
-            const int c0 = (kc - tap * p.cin_chunks) * BLOCK_K;
-            const int r = tap / p.S;
-            const int s = tap - r * p.S;
-            tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst, c0, w0, h0, img, (uint16_t)s, (uint16_t)r);
+            tma_load_im2col_4d(&tmap_a, &full_bar[stage], a_dst, cc * BLOCK_K, w0, h0, img, (uint16_t)tap_s,
+                               (uint16_t)tap_r);
           } else if (A_MODE == A_IM2COL32) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -277,6 +280,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           }
           __syncwarp();
+          if (A_MODE == A_IM2COL64 && ++cc == p.cin_chunks) {
+            cc = 0;
+            if (++tap_s == p.S) { tap_s = 0; ++tap_r; }
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -601,12 +608,12 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, ta2, p);
 }
 
-// CTA-pair variant (256 x 256 tiles, cluster of 2, tcgen05 cta_group::2), bf16 output through the TMA epilogue.
-template <int A_MODE>
+// CTA-pair variant (256 x BLOCK_N tiles, cluster of 2, tcgen05 cta_group::2), bf16 output through the TMA epilogue.
+template <int BLOCK_N, int A_MODE>
 cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                         const CUtensorMap& ta2, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = conv_gemm_kernel<256, A_MODE, true, false, true>;
-  using C = Cfg<256, true, true>;
+  auto kern = conv_gemm_kernel<BLOCK_N, A_MODE, true, false, true>;
+  using C = Cfg<BLOCK_N, true, true>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -654,9 +661,15 @@ cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtens
   if (p.kc_split && (a_mode != A_TILED || !tmap_a2)) return cudaErrorInvalidValue;
   const CUtensorMap& ta2 = tmap_a2 ? *tmap_a2 : tmap_a;
   if (p.cta2) {
-    if (block_n != 256 || !epi_tma || p.out_is_f32 || p.split_k != 1) return cudaErrorInvalidValue;
-    if (a_mode == A_TILED) return launch_pair<A_TILED>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
-    if (a_mode == A_IM2COL64) return launch_pair<A_IM2COL64>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    if (!epi_tma || p.out_is_f32 || p.split_k != 1) return cudaErrorInvalidValue;
+    if (block_n == 256 && a_mode == A_TILED)
+      return launch_pair<256, A_TILED>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    if (block_n == 256 && a_mode == A_IM2COL64)
+      return launch_pair<256, A_IM2COL64>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    if (block_n == 128 && a_mode == A_TILED)
+      return launch_pair<128, A_TILED>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    if (block_n == 128 && a_mode == A_IM2COL64)
+      return launch_pair<128, A_IM2COL64>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
     return cudaErrorInvalidValue;
   }
   if (p.out_is_f32) {  // plain GEMMs only (policy network): fp32 result, TMA-staged or split-K atomic

@@ -513,6 +513,14 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   p.num_m_tiles = (d->m + 127) / 128;
   int block_n = pick_block_n(d->n_pad, (long long)p.num_m_tiles * split_k, sms, 0, d->res != nullptr);
   if (d->out_f32 == 2 && block_n > 128) block_n = 128;
+  // CTA pairs (cta_group::2, 256 x 256 tiles) for wide bf16-output GEMMs with enough K: ViT QKV / fc1
+  static const bool pair_ok = !(getenv("PVR_CTA2") && atoi(getenv("PVR_CTA2")) == 0);
+  if (pair_ok && d->out_f32 == 0 && !d->res && split_k == 1 && d->n_pad % 256 == 0 && d->n % 64 == 0 && d->k >= 512 &&
+      ((long long)(d->m + 255) / 256) * (d->n_pad / 256) >= sms / 2) {
+    p.cta2 = 1;
+    p.num_m_tiles = (d->m + 255) / 256;
+    block_n = 256;
+  }
   p.num_n_tiles = d->n_pad / block_n;
   p.split_k = split_k;
   p.num_k_chunks = d->k / 64 / split_k;
@@ -531,7 +539,8 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   CUtensorMap ta, tb, to, tr;
   const char* err = "";
   if (!pvr::make_tmap_2d(&ta, d->a, (uint64_t)d->k, (uint64_t)d->m, (uint64_t)d->lda, 128, &err) ||
-      !pvr::make_tmap_2d(&tb, d->b, (uint64_t)d->k, (uint64_t)d->n_pad, (uint64_t)d->ldb, (uint32_t)block_n, &err)) {
+      !pvr::make_tmap_2d(&tb, d->b, (uint64_t)d->k, (uint64_t)d->n_pad, (uint64_t)d->ldb,
+                         (uint32_t)(p.cta2 ? block_n / 2 : block_n), &err)) {
     pvr_set_error("pvr_gemm: %s", err);
     return PVR_ERR_CUDA;
   }

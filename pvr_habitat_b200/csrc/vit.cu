@@ -143,53 +143,65 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);  // uniform register for tcgen05.mma
   const long long items = (long long)p.n_img * p.heads;
   const uint32_t q_bytes = 16384u * p.mtiles;
 
   if (warp == 8) {
-    // ===================================================== controller: TMA prefetch + MMA issue
-    if (lane == 0) {
-      const uint32_t idesc_s = umma_idesc_bf16(128, p.KP);
-      const uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
-      auto issue_loads = [&](long long it, int st) {
-        const int head = (int)(it % p.heads);
-        const int row0 = (int)((it / p.heads) * p.S);
-        uint8_t* base = smem + st * stage_bytes;
-        mbar_expect_tx(&kv_full[st], q_bytes + 2 * kv_bytes);
-        for (int mt = 0; mt < p.mtiles; ++mt)
-          tma_load_2d(&tmap_q, &kv_full[st], base + mt * 16384, head * 64, row0 + mt * 128);
-        tma_load_2d(&tmap_kv, &kv_full[st], base + 32768, p.W + head * 64, row0);
-        tma_load_2d(&tmap_kv, &kv_full[st], base + 32768 + kv_alloc, 2 * p.W + head * 64, row0);
-      };
-      uint32_t n = 0;
-      if ((long long)blockIdx.x < items) issue_loads(blockIdx.x, 0);
-      for (long long it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-        const int st = n & 1;
-        const long long nxt = it + gridDim.x;
-        if (nxt < items) {  // prefetch the next item into the other stage once its previous user has drained it
-          if (n >= 1) mbar_wait(&kv_empty[st ^ 1], ((n - 1) >> 1) & 1);
-          issue_loads(nxt, st ^ 1);
-        }
-        mbar_wait(&kv_full[st], (n >> 1) & 1);
-        if (n >= 1) mbar_wait(tmem_free, (n - 1) & 1);  // epilogue of the previous item has read O
-        tc_fence_after();
-        const uint32_t sQ = smem_u32(smem + st * stage_bytes), sK = sQ + 32768, sV = sK + kv_alloc;
+    // ===================================================== controller: TMA prefetch + MMA issue. The whole warp walks
+    // the loop (uniform loop state), one elected lane issues; descriptors are built once per stage and advanced by
+    // adding to the (address >> 4) field (see conv_gemm.cu).
+    const uint32_t idesc_s = umma_idesc_bf16(128, p.KP);
+    const uint32_t idesc_o = umma_idesc_bf16(128, 64) | (1u << 16);  // B (= V) is MN-major
+    auto issue_loads = [&](long long it, int st) {
+      const int head = (int)(it % p.heads);
+      const int row0 = (int)((it / p.heads) * p.S);
+      uint8_t* base = smem + st * stage_bytes;
+      mbar_expect_tx(&kv_full[st], q_bytes + 2 * kv_bytes);
+      for (int mt = 0; mt < p.mtiles; ++mt)
+        tma_load_2d(&tmap_q, &kv_full[st], base + mt * 16384, head * 64, row0 + mt * 128);
+      tma_load_2d(&tmap_kv, &kv_full[st], base + 32768, p.W + head * 64, row0);
+      tma_load_2d(&tmap_kv, &kv_full[st], base + 32768 + kv_alloc, 2 * p.W + head * 64, row0);
+    };
+    uint32_t n = 0;
+    if ((long long)blockIdx.x < items) {
+      if (elect_one()) issue_loads(blockIdx.x, 0);
+      __syncwarp();
+    }
+    for (long long it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+      const int st = n & 1;
+      const long long nxt = it + gridDim.x;
+      if (nxt < items) {  // prefetch the next item into the other stage once its previous user has drained it
+        if (n >= 1) mbar_wait(&kv_empty[st ^ 1], ((n - 1) >> 1) & 1);
+        if (elect_one()) issue_loads(nxt, st ^ 1);
+        __syncwarp();
+      }
+      mbar_wait(&kv_full[st], (n >> 1) & 1);
+      if (n >= 1) mbar_wait(tmem_free, (n - 1) & 1);  // epilogue of the previous item has read O
+      tc_fence_after();
+      const uint32_t sQ = smem_u32(smem + st * stage_bytes);
+      const uint64_t q_desc = umma_desc_sw128(sQ), k_desc = umma_desc_sw128(sQ + 32768),
+                     v_desc = umma_desc_sw128(sQ + 32768 + kv_alloc);
+      if (elect_one()) {
         for (int mt = 0; mt < p.mtiles; ++mt)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + mt * 256, umma_desc_sw128(sQ + mt * 16384 + k * 32), umma_desc_sw128(sK + k * 32),
-                      idesc_s, k != 0);
+            umma_bf16(tmem_base + mt * 256, q_desc + ((mt * 16384 + k * 32) >> 4), k_desc + ((k * 32) >> 4), idesc_s,
+                      k != 0);
         umma_commit(s_ready);
-        mbar_wait(p_ready, n & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+      mbar_wait(p_ready, n & 1);
+      tc_fence_after();
+      if (elect_one()) {
         for (int mt = 0; mt < p.mtiles; ++mt)
           for (int ks = 0; ks < p.KP / 16; ++ks)
-            umma_bf16_ts(tmem_base + mt * 256 + 128, tmem_base + mt * 256 + ks * 8,
-                         umma_desc_sw128(sV + ks * 2048), idesc_o, ks != 0);
+            umma_bf16_ts(tmem_base + mt * 256 + 128, tmem_base + mt * 256 + ks * 8, v_desc + ((ks * 2048) >> 4),
+                         idesc_o, ks != 0);
         umma_commit(o_ready);
         umma_commit(&kv_empty[st]);
       }
+      __syncwarp();
     }
   } else if (warp < 4 * p.mtiles) {
     // ===================================================== softmax + output (one thread per query row)

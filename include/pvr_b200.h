@@ -145,8 +145,10 @@ typedef struct pvr_gemm_desc {
   int32_t out_f32;    /* 0: bf16 out; 1: fp32 out; 2: fp32 out, atomically accumulated (out must hold the addend) */
   int32_t split_k;    /* out_f32 == 2 only: number of K slices computed by separate CTAs */
   int32_t act;        /* 0: none (or `relu`), 1: ReLU, 2: QuickGELU x*sigmoid(1.702x) (bf16 output) */
-  int32_t reserved;
+  int32_t flags;      /* PVR_GEMM_PDL: launch with programmatic stream serialization (the kernel's prologue overlaps
+                         the previous kernel of the stream; it waits for that kernel before touching a / res / out) */
 } pvr_gemm_desc;
+#define PVR_GEMM_PDL 1
 int pvr_gemm(const pvr_gemm_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

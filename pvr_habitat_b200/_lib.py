@@ -30,7 +30,7 @@ class pvr_gemm_desc(ctypes.Structure):
                 ("ldo", ctypes.c_int64), ("ldr", ctypes.c_int64), ("m", ctypes.c_int32), ("n", ctypes.c_int32),
                 ("n_pad", ctypes.c_int32), ("k", ctypes.c_int32), ("relu", ctypes.c_int32),
                 ("res_mode", ctypes.c_int32), ("out_f32", ctypes.c_int32), ("split_k", ctypes.c_int32),
-                ("act", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("act", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 class pvr_lstm_fwd(ctypes.Structure):

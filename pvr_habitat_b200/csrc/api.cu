@@ -510,6 +510,7 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   pvr::ConvGemmParams p;
   memset(&p, 0, sizeof(p));
   p.M = d->m;
+  p.pdl = (d->flags & PVR_GEMM_PDL) != 0;
   p.num_m_tiles = (d->m + 127) / 128;
   int block_n = pick_block_n(d->n_pad, (long long)p.num_m_tiles * split_k, sms, 0, d->res != nullptr);
   if (d->out_f32 == 2 && block_n > 128) block_n = 128;

@@ -188,11 +188,32 @@ __global__ void __launch_bounds__(256) bn_backward_kernel(const __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------- LSTM cell
 // One thread = one (sequence b, hidden unit j). Gate order i, f, g, o (PyTorch).
 // pre = G[b][gate*H + j] + XP[b][gate*H + j]; c = sig(f) * (nd * c_prev) + sig(i) * tanh(g); h = sig(o) * tanh(c).
+// Programmatic dependent launch inside the recurrence (GEMM -> cell -> GEMM -> ...): every kernel lets its successor
+// start its prologue at once and waits for its predecessor's results before touching memory (see ptx.cuh).
+__device__ __forceinline__ void pdl_launch_then_wait() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(
     const float* __restrict__ G, const float* __restrict__ XP, const float* __restrict__ c_prev,
     const float* __restrict__ nd, const float* __restrict__ nd_next, int B, int H, float* __restrict__ gates,
     float* __restrict__ c_out, float* __restrict__ h_out_f32, __nv_bfloat16* __restrict__ h_out,
     __nv_bfloat16* __restrict__ hm_next) {
+  pdl_launch_then_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int b = idx / H, j = idx - b * H;
@@ -219,6 +240,7 @@ __global__ void __launch_bounds__(256) lstm_cell_bwd_kernel(
     const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
     const float* __restrict__ nd, const float* __restrict__ nd_next, int B, int H,
     __nv_bfloat16* __restrict__ dG) {
+  pdl_launch_then_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * H) return;
   const int b = idx / H, j = idx - b * H;
@@ -761,14 +783,15 @@ int lstm_forward_issue(const pvr_lstm_fwd* L, cudaStream_t st) {
   memset(&d, 0, sizeof(d));
   d.b = L->w_hh; d.ldb = H; d.out = L->g_tmp; d.ldo = 4 * H; d.lda = H;
   d.m = B; d.n = 4 * H; d.n_pad = 4 * H; d.k = H; d.out_f32 = 1; d.split_k = 1;
+  d.flags = PVR_GEMM_PDL;
   for (int t = 0; t < T; ++t) {
     d.a = hm + t * BH;
     int rc = pvr_gemm(&d, st);
     if (rc != PVR_OK) return rc;
-    lstm_cell_fwd_kernel<<<(int)((BH + 255) / 256), 256, 0, st>>>(
-        L->g_tmp, L->xp + (long long)t * B * 4 * H, L->c_all + t * BH, L->nd + (long long)t * B,
-        t + 1 < T ? L->nd + (long long)(t + 1) * B : nullptr, B, H, L->gates + (long long)t * B * 4 * H,
-        L->c_all + (t + 1) * BH, L->h_last, ho + t * BH, t + 1 < T ? hm + (t + 1) * BH : nullptr);
+    launch_pdl(lstm_cell_fwd_kernel, (int)((BH + 255) / 256), 256, st, L->g_tmp,
+               L->xp + (long long)t * B * 4 * H, L->c_all + t * BH, L->nd + (long long)t * B,
+               t + 1 < T ? L->nd + (long long)(t + 1) * B : nullptr, B, H, L->gates + (long long)t * B * 4 * H,
+               L->c_all + (t + 1) * BH, L->h_last, ho + t * BH, t + 1 < T ? hm + (t + 1) * BH : nullptr);
     PVR_LAUNCH_CHECK("pvr_lstm_forward(cell)");
   }
   return PVR_OK;
@@ -783,11 +806,12 @@ int lstm_backward_issue(const pvr_lstm_bwd* L, cudaStream_t st) {
   d.b = L->w_hh_t; d.ldb = 4 * H; d.out = L->dh_rec; d.ldo = H; d.lda = 4 * H;
   d.m = B; d.n = H; d.n_pad = H; d.k = 4 * H; d.out_f32 = 2;
   d.split_k = (4 * H / 64) % 8 == 0 ? 8 : 1;
+  d.flags = PVR_GEMM_PDL;
   for (int t = T - 1; t >= 0; --t) {
-    lstm_cell_bwd_kernel<<<(int)((BH + 255) / 256), 256, 0, st>>>(
-        L->dh_out ? L->dh_out + t * BH : nullptr, L->dh_rec, L->dc_rec, L->gates + (long long)t * B * 4 * H,
-        L->c_all + t * BH, L->c_all + (t + 1) * BH, L->nd + (long long)t * B,
-        t + 1 < T ? L->nd + (long long)(t + 1) * B : nullptr, B, H, dG + (long long)t * B * 4 * H);
+    launch_pdl(lstm_cell_bwd_kernel, (int)((BH + 255) / 256), 256, st,
+               L->dh_out ? L->dh_out + t * BH : nullptr, L->dh_rec, L->dc_rec, L->gates + (long long)t * B * 4 * H,
+               L->c_all + t * BH, L->c_all + (t + 1) * BH, L->nd + (long long)t * B,
+               t + 1 < T ? L->nd + (long long)(t + 1) * B : nullptr, B, H, dG + (long long)t * B * 4 * H);
     PVR_LAUNCH_CHECK("pvr_lstm_backward(cell)");
     if (t > 0) {
       d.a = dG + (long long)t * B * 4 * H;

@@ -63,8 +63,17 @@ int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int 
 #define PVR_OP_CONV 1     /* implicit-GEMM conv (tcgen05) + folded-BN scale/bias + optional residual + optional ReLU */
 #define PVR_OP_MAXPOOL 2  /* 3x3 stride-2 pad-1 max pool, NHWC bf16 */
 #define PVR_OP_AVGPOOL 3  /* global average pool -> float32 rows of the embedding */
-#define PVR_OP_HEAD 4     /* compression-head tail: 3x3 conv c->c + BN + identity add + ReLU -> NCHW-flatten f32 */
+#define PVR_OP_HEAD 4     /* compression-head tail: 3x3 conv c->c + BN + identity add + ReLU -> NCHW-flatten f32.
+                             act == 0: input = bf16 (2c) per pixel [relu(bn1(conv1 x)) | bn_d(conv_d x)];
+                             act == 1: input = float32 per-tap partial sums, 9 x 2c per pixel (pitch in floats): the op
+                             first forms sum_tap Z[p + tap - 1][tap], applies scale1/bias1 (+ ReLU on the first c) */
 #define PVR_OP_FLATTEN 5  /* NHWC bf16 slot -> NCHW-flattened float32 embedding columns (`out.view(-1, out_size)`) */
+
+/* CONV flag: the output slot holds float32 values (out_pitch floats per pixel; the slot is sized as 2*out_pitch bf16
+ * elements per pixel). 1x1 / stride-1 convs without residual, c_out % 32 == 0. Used by the compression heads, whose
+ * 3x3 convolution over C = 1024 / 2048 channels runs as ONE 1x1 GEMM producing the 9 per-tap partial sums of every
+ * pixel (the input is read once instead of nine times); the HEAD op adds the shifted partial sums in fp32. */
+#define PVR_CONV_OUT_F32 1
 
 typedef struct pvr_op {
   int32_t kind;
@@ -88,7 +97,7 @@ typedef struct pvr_op {
    * projection shortcut of torchvision's Bottleneck (resnet.py:143-166: out = bn3(conv3(t)) + bn_d(conv_d(x))) runs
    * as ONE GEMM: both BN scales are folded into the packed weight rows, bias = b3 + b_d, scale = 1. */
   int32_t in2_slot, in2_c, in2_h, in2_w, in2_pitch, in2_stride;
-  int32_t reserved;
+  int32_t flags;                       /* CONV: PVR_CONV_OUT_F32 */
   const void* weight;                  /* bf16 (n_pad, k_pad), K-major, K ordered (tap_row, tap_col, channel) */
   const float* scale;                  /* (n_pad) folded BN scale */
   const float* bias;                   /* (n_pad) folded BN bias (+ conv bias) */

@@ -8,6 +8,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpvr_b200.so")
 PVR_FMT_NCHW_F32 = 0
 PVR_FMT_NHWC4_BF16 = 1
 PVR_FMT_STEM_BF16 = 2
+PVR_CONV_OUT_F32 = 1
 PVR_OP_CONV, PVR_OP_MAXPOOL, PVR_OP_AVGPOOL, PVR_OP_HEAD, PVR_OP_FLATTEN = 1, 2, 3, 4, 5
 
 
@@ -20,7 +21,7 @@ class pvr_op(ctypes.Structure):
         "kind", "in_slot", "out_slot", "res_slot", "c_in", "h_in", "w_in", "in_pitch", "c_out", "h_out", "w_out",
         "out_pitch", "res_pitch", "out_coff", "res_coff", "r", "s", "stride_h", "stride_w", "lower_h", "lower_w",
         "relu_n", "block_n", "k_pad", "n_pad", "emb_offset", "act", "in2_slot", "in2_c", "in2_h", "in2_w", "in2_pitch",
-        "in2_stride", "reserved")] + [
+        "in2_stride", "flags")] + [
         ("weight", ctypes.c_void_p), ("scale", ctypes.c_void_p), ("bias", ctypes.c_void_p), ("aux", ctypes.c_void_p)]
 
 

@@ -237,7 +237,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     // traffic. Each CTA of a pair stages half of the W tile. Residual layers stay single-CTA at N = 128 (measured:
     // their in-place residual epilogue is slower at N = 256).
     if (pair_mode && o.block_n == 0 && o.n_pad % 128 == 0 && o.c_out % 64 == 0 && o.c_in % 64 == 0 && o.act != 3 &&
-        M % 256 == 0 && o.k_pad >= 512) {
+        M % 256 == 0 && o.k_pad >= 512 && !(o.flags & PVR_CONV_OUT_F32)) {
       const int pbn = (o.n_pad % 256 == 0 && o.res_slot < 0) ? 256 : 128;
       const bool allow = pbn == 256 ? true : (pair_mode >= 2 && (o.res_slot < 0 || pair_mode >= 3));
       if (allow && (M / 256) * (o.n_pad / pbn) >= enc->sms / 2) {
@@ -347,7 +347,21 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     b.epi_tma = (b.block_n >= 64 && o.c_out % 64 == 0 && o.act != 3);
     b.to = b.ta;
     b.tr = b.ta;
-    if (b.epi_tma) {
+    if (o.flags & PVR_CONV_OUT_F32) {
+      if (!pointwise || o.res_slot >= 0 || o.c_out % 32 || b.block_n < 64 || o.out_coff != 0 || o.act != 0 ||
+          o.out_pitch % 4) {
+        pvr_set_error("pvr_encoder_bind: op %zu: float32 output needs a 1x1 conv, no residual, c_out %% 32 == 0", i);
+        return PVR_ERR_ARG;
+      }
+      b.epi_tma = true;
+      p.out_is_f32 = 1;
+      p.out_f32 = reinterpret_cast<float*>(enc->slot_ptr[o.out_slot]);
+      if (!pvr::make_tmap_2d_f32(&b.to, enc->slot_ptr[o.out_slot], (uint64_t)o.c_out, (uint64_t)M,
+                                 (uint64_t)o.out_pitch, 128, &err)) {
+        pvr_set_error("pvr_encoder_bind: op %zu: float32 output tensor map: %s", i, err);
+        return PVR_ERR_CUDA;
+      }
+    } else if (b.epi_tma) {
       p.has_res = o.res_slot >= 0;
       p.out_coff = o.out_coff;
       p.res_coff = o.res_coff;
@@ -394,6 +408,12 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
                                 emb_ld, o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
         break;
       case PVR_OP_HEAD:
+        if (o.act == 1) {
+          e = pvr::launch_head_tail_taps(reinterpret_cast<const float*>(enc->slot_ptr[o.in_slot]), o.in_pitch,
+                                         static_cast<const float*>(o.aux), emb, emb_ld, o.emb_offset, n, o.h_in,
+                                         o.w_in, o.c_out, stream);
+          break;
+        }
         e = pvr::launch_head_tail(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), o.in_pitch,
                                   static_cast<const float*>(o.aux), emb, emb_ld, o.emb_offset, n, o.h_in, o.w_in,
                                   o.c_out, stream);

@@ -92,7 +92,7 @@ class Program:
     # ---- ops
     def conv(self, in_slot, in_chw, w_packed, k_pad, c_out, r, s, stride, lower, out_hw, scale, bias, relu_n,
              in_pitch=None, res=None, out_slot=None, out_pitch=None, out_coff=0, block_n=0, flops=None, act=0,
-             in2=None):
+             in2=None, flags=0):
         c_in, h_in, w_in = in_chw
         n_pad = w_packed.shape[0]
         p, q = out_hw
@@ -108,7 +108,7 @@ class Program:
                   w_in=w_in, in_pitch=in_pitch if in_pitch is not None else c_in, c_out=c_out, h_out=p, w_out=q,
                   out_pitch=out_pitch, res_pitch=0, out_coff=out_coff, res_coff=0, r=r, s=s,
                   stride_h=stride[0], stride_w=stride[1], lower_h=lower[0], lower_w=lower[1], relu_n=relu_n,
-                  block_n=block_n, k_pad=k_pad, n_pad=n_pad, emb_offset=0, act=act,
+                  block_n=block_n, k_pad=k_pad, n_pad=n_pad, emb_offset=0, act=act, flags=flags,
                   _weight=w_packed.contiguous(), _scale=sc, _bias=bi,
                   flops_per_image=int(flops if flops is not None else 2 * p * q * c_out * r * s * c_in))
         if res is not None:
@@ -134,9 +134,11 @@ class Program:
         self.ops.append(dict(kind=_lib.PVR_OP_AVGPOOL, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=c, h_in=h,
                              w_in=w, in_pitch=c, c_out=c, emb_offset=emb_offset))
 
-    def head_tail(self, in_slot, pitch, c, h, w, aux, emb_offset):
+    def head_tail(self, in_slot, pitch, c, h, w, aux, emb_offset, taps=False):
+        """taps: the input slot holds float32 per-tap partial sums (9 x 2c per pixel, pitch in floats), see pvr_b200.h"""
         self.ops.append(dict(kind=_lib.PVR_OP_HEAD, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=2 * c, h_in=h,
-                             w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset, _aux=aux.contiguous()))
+                             w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset, act=1 if taps else 0,
+                             _aux=aux.contiguous()))
 
     # ---- finalise
     def finish(self, device):
@@ -289,9 +291,12 @@ def _bottleneck(prog, sd, prefix, x_slot, x_chw, stride, has_ds):
 def _compress_head(prog, sd, prefix, x_slot, x_chw, emb_offset):
     """BasicBlock(C, c, downsample=Sequential(Conv2d(C, c, 3, padding=1, bias=True), BN)) of moco.py:34-50/:78-94.
 
-    conv1 (-> bn1 -> ReLU) and the biased downsample conv (-> BN) read the same input: one GEMM with 2c output
-    columns (ReLU on the first c only); conv2 -> bn2 -> += identity -> ReLU runs in the head-tail kernel, which
-    writes the NCHW-flattened float32 embedding columns.
+    conv1 (-> bn1 -> ReLU) and the biased downsample conv (-> BN) read the same input and are both 3x3 convolutions
+    over C = 1024 / 2048 channels with only 2c = 22 / 84 outputs. As an implicit GEMM that is nine reads of the input
+    for a 32- / 96-wide tile; instead ONE 1x1 GEMM computes the nine per-tap partial sums of every pixel,
+    Z[q, tap*2c + j] = W_tap[j] . x[q] (N = 18c -> 256 / 768, float32 output), and the head kernel forms
+    sum_tap Z[p + tap - 1, tap] in fp32, applies bn1 / bn_d (+ ReLU on conv1's half), then conv2 -> bn2 -> += identity ->
+    ReLU and writes the NCHW-flattened float32 embedding columns.
     """
     w1 = sd[prefix + ".conv1.weight"].float()
     wd = sd[prefix + ".downsample.0.weight"].float()
@@ -299,16 +304,23 @@ def _compress_head(prog, sd, prefix, x_slot, x_chw, emb_offset):
     C, h, w = x_chw
     s1, b1 = fold_bn(sd, prefix + ".bn1")
     sdn, bdn = fold_bn(sd, prefix + ".downsample.1", sd[prefix + ".downsample.0.bias"])
-    n_pad = _round_up(2 * c, 32)
-    pitch = n_pad
-    wcat = torch.cat([w1, wd], 0)
-    t = prog.conv(x_slot, x_chw, pack_conv_weight(wcat, n_pad), 9 * C, 2 * c, 3, 3, (1, 1), (-1, -1), (h, w),
-                  torch.cat([s1, sdn]), torch.cat([b1, bdn]), c, out_pitch=pitch)
+    wcat = torch.cat([w1, wd], 0)                                  # (2c, C, 3, 3)
+    wz = wcat.permute(2, 3, 0, 1).reshape(9 * 2 * c, C)            # row = tap*2c + j
+    n_pad = _round_up(9 * 2 * c, 64)
+    packed = torch.zeros(n_pad, C, dtype=torch.bfloat16)
+    packed[:9 * 2 * c] = wz.to(torch.bfloat16)
+    zslot = prog.alloc(h * w * n_pad * 2)                          # float32 values: two bf16 elements each
+    prog.conv(x_slot, x_chw, packed, C, n_pad, 1, 1, (1, 1), (0, 0), (h, w), torch.ones(n_pad), torch.zeros(n_pad), 0,
+              out_slot=zslot, out_pitch=n_pad, flags=_lib.PVR_CONV_OUT_F32, flops=2 * h * w * 2 * c * 9 * C)
     w2 = sd[prefix + ".conv2.weight"].float()  # (c, c, 3, 3) -> (co, r, s, ci)
     s2, b2 = fold_bn(sd, prefix + ".bn2")
-    aux = torch.cat([w2.permute(0, 2, 3, 1).reshape(-1), s2, b2]).float()
-    prog.head_tail(t, pitch, c, h, w, aux, emb_offset)
-    prog.release(t)
+    cp = _round_up(c, 4)
+    w2t = torch.zeros(3, 3, c, cp)
+    w2t[..., :c] = w2.permute(2, 3, 1, 0)                          # (r, s, ci, co): float4 = 4 output channels
+    aux = torch.cat([w2t.reshape(-1), s2, b2, s1, sdn, b1, bdn, torch.zeros(8)]).float()
+    aux = aux[:(aux.numel() // 4) * 4]
+    prog.head_tail(zslot, n_pad, c, h, w, aux, emb_offset, taps=True)
+    prog.release(zslot)
     return c * h * w
 
 

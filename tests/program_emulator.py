@@ -59,7 +59,8 @@ def emulate(prog, frames_nhwc4, round_bf16=True):
             if buf is None or buf.shape[1] < need:
                 buf = torch.zeros(n, need)
             view = buf[:, :need].reshape(n, p, q, op_).clone()
-            view[..., op["out_coff"]:op["out_coff"] + co] = rb(y.permute(0, 2, 3, 1))
+            f32_out = op.get("flags", 0) & _lib.PVR_CONV_OUT_F32  # float32 slot: no bf16 rounding of the result
+            view[..., op["out_coff"]:op["out_coff"] + co] = y.permute(0, 2, 3, 1) if f32_out else rb(y.permute(0, 2, 3, 1))
             nb = torch.zeros(n, max(need, buf.shape[1]))
             nb[:, :need] = view.reshape(n, -1)
             slots[op["out_slot"]] = nb
@@ -79,11 +80,23 @@ def emulate(prog, frames_nhwc4, round_bf16=True):
         elif k == _lib.PVR_OP_HEAD:
             c, h, w, pitch = op["c_out"], op["h_in"], op["w_in"], op["in_pitch"]
             t = slots[op["in_slot"]][:, :h * w * pitch].reshape(n, h, w, pitch)
+            aux = op["_aux"]
+            if op.get("act", 0) == 1:  # per-tap partial sums: t[p] = bn(sum_tap Z[p + tap - 1][tap])
+                cp = (c + 3) // 4 * 4
+                base = 9 * c * cp
+                zt = F.pad(t[..., :9 * 2 * c].reshape(n, h, w, 9, 2 * c), (0, 0, 0, 0, 1, 1, 1, 1))
+                acc = sum(zt[:, r:r + h, s:s + w, r * 3 + s] for r in range(3) for s in range(3))
+                sc1 = aux[base + 2 * c:base + 4 * c]
+                bi1 = aux[base + 4 * c:base + 6 * c]
+                t = acc * sc1 + bi1
+                t = torch.cat([t[..., :c].relu(), t[..., c:]], -1)
+                w2 = aux[:base].reshape(3, 3, c, cp)[..., :c].permute(3, 2, 0, 1)  # (r, s, ci, co) -> (co, ci, r, s)
+            else:
+                base = c * 9 * c
+                w2 = aux[:base].reshape(c, 3, 3, c).permute(0, 3, 1, 2)
             a = t[..., :c].permute(0, 3, 1, 2)
             idn = t[..., c:2 * c].permute(0, 3, 1, 2)
-            aux = op["_aux"]
-            w2 = aux[:c * 9 * c].reshape(c, 3, 3, c).permute(0, 3, 1, 2)
-            s2, b2 = aux[c * 9 * c:c * 9 * c + c], aux[c * 9 * c + c:]
+            s2, b2 = aux[base:base + c], aux[base + c:base + 2 * c]
             y = F.conv2d(a, w2, padding=1) * s2[None, :, None, None] + b2[None, :, None, None] + idn
             emb[:, op["emb_offset"]:op["emb_offset"] + c * h * w] = y.relu().reshape(n, -1)
     return emb

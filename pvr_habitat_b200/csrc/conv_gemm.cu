@@ -64,6 +64,11 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+  __nv_bfloat162 x = *reinterpret_cast<__nv_bfloat162*>(&v);
+  x = __hmax2(x, __floats2bfloat162_rn(0.f, 0.f));
+  return *reinterpret_cast<uint32_t*>(&x);
+}
 // scale/bias (global, uniform addresses) on 32 accumulator columns starting at column n.
 __device__ __forceinline__ void epilogue_math(const uint32_t* v, float* f, const ConvGemmParams& p, int n) {
   const float4* sc4 = reinterpret_cast<const float4*>(p.scale + n);
@@ -108,8 +113,20 @@ __device__ __forceinline__ void relu_cols(float* f, int n, int relu_n) {
 // (m, n) tile of a work item. `reverse` walks the tiles from the last to the first: consecutive layers alternate
 // direction so that a layer starts on the rows its producer wrote last, which are still in L2 (zig-zag order).
 __device__ __forceinline__ int tile_mn(const ConvGemmParams& p, int tile) {
-  const int mn = tile / p.split_k;
+  const int mn = p.split_k == 1 ? tile : tile / p.split_k;
   return p.reverse ? p.num_m_tiles * p.num_n_tiles - 1 - mn : mn;
+}
+// (m_tile, n_tile) without an integer division when the number of N tiles is a power of two (every ResNet layer):
+// the epilogue threads evaluate this per sub-tile.
+__device__ __forceinline__ void tile_coords(const ConvGemmParams& p, int tile, int& m_tile, int& n_tile) {
+  const int mn = tile_mn(p, tile);
+  if (p.n_tiles_shift >= 0) {
+    m_tile = mn >> p.n_tiles_shift;
+    n_tile = mn & (p.num_n_tiles - 1);
+  } else {
+    m_tile = mn / p.num_n_tiles;
+    n_tile = mn - m_tile * p.num_n_tiles;
+  }
 }
 
 template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32, bool CTA2 = false>
@@ -196,10 +213,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     {
       uint32_t stage = 0, phase = 0;
       for (int tile = wid; tile < num_tiles; tile += wstride) {
-        const int mn = tile_mn(p, tile);
-        const int kc0 = (tile % p.split_k) * p.num_k_chunks;  // first K chunk of this split-K slice
-        const int m_tile = mn / p.num_n_tiles;
-        const int n_tile = mn - m_tile * p.num_n_tiles;
+        const int kc0 = p.split_k == 1 ? 0 : (tile % p.split_k) * p.num_k_chunks;  // first K chunk of this slice
+        int m_tile, n_tile;
+        tile_coords(p, tile, m_tile, n_tile);
         const int m0 = tile_row0(m_tile);
         const int n0 = n_tile * BLOCK_N + (CTA2 ? (int)cta_rank * (BLOCK_N / 2) : 0);  // pair: this CTA's half of W
         int img = 0, w0 = 0, h0 = 0;
@@ -351,9 +367,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (i >= (uint32_t)NB) bulk_wait_group_read<1>();  // stores up to sub-tile i - D - 2 = i - NB have drained
           if (p.has_res) {
             const int t_it = i / SUBS, c = i - t_it * SUBS;
-            const int mn = tile_mn(p, wid + t_it * wstride);
-            const int m_tile = mn / p.num_n_tiles;
-            const int n_tile = mn - m_tile * p.num_n_tiles;
+            int m_tile, n_tile;
+            tile_coords(p, wid + t_it * wstride, m_tile, n_tile);
             mbar_expect_tx(&eb_full_bar[s], EPI_TILE_BYTES);
             tma_load_2d(&tmap_res, &eb_full_bar[s], sEB + s * EPI_TILE_BYTES,
                         p.res_coff + n_tile * BLOCK_N + c * EPI_COLS, tile_row0(m_tile));
@@ -365,9 +380,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t qs = i - D;
           const uint32_t s = qs % NB, ph = (qs / NB) & 1;
           const int t_it = qs / SUBS, c = qs - t_it * SUBS;
-          const int mn = tile_mn(p, wid + t_it * wstride);
-          const int m_tile = mn / p.num_n_tiles;
-          const int n_tile = mn - m_tile * p.num_n_tiles;
+          int m_tile, n_tile;
+          tile_coords(p, wid + t_it * wstride, m_tile, n_tile);
           mbar_wait(&eb_ready_bar[s], ph);
           tma_store_2d(&tmap_out, sEB + s * EPI_TILE_BYTES, p.out_coff + n_tile * BLOCK_N + c * EPI_COLS,
                        tile_row0(m_tile));
@@ -394,7 +408,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const long long tile = (long long)wid + (long long)t_it * wstride;
         const int col = gtid & 63;
         if (tile >= num_tiles || col >= EPI_COLS) return false;
-        const int n = (tile_mn(p, (int)tile) % p.num_n_tiles) * BLOCK_N + c * EPI_COLS;
+        int m_t, n_t;
+        tile_coords(p, (int)tile, m_t, n_t);
+        const int n = n_t * BLOCK_N + c * EPI_COLS;
         val = gtid < 64 ? __ldg(p.scale + n + col) : __ldg(p.bias + n + col);
         return true;
       };
@@ -405,9 +421,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       named_bar_sync(1 + group, 128);
       for (int tile = wid; tile < num_tiles; tile += wstride) {
-        const int mn = tile_mn(p, tile);
-        const int m_tile = mn / p.num_n_tiles;
-        const int n_tile = mn - m_tile * p.num_n_tiles;
+        int m_tile, n_tile;
+        tile_coords(p, tile, m_tile, n_tile);
         const int n0 = n_tile * BLOCK_N;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
         tc_fence_after();
@@ -468,7 +483,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                   else mask_bf16x8(f + 8 * jj, rv);
                 }
               }
-              relu_cols(f, n + h * 32, p.relu_n);
+              // full-width ReLU is applied on the packed bf16 pairs below (max commutes with the rounding)
+              const bool packed_relu = n + h * 32 + 32 <= p.relu_n;
+              if (!packed_relu) relu_cols(f, n + h * 32, p.relu_n);
               if (p.quick_gelu) {  // CLIP's QuickGELU: x * sigmoid(1.702 x)
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) f[jj] = __fdividef(f[jj], 1.f + __expf(-1.702f * f[jj]));
@@ -480,6 +497,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 ov.y = pack_bf16x2(f[8 * jj + 2], f[8 * jj + 3]);
                 ov.z = pack_bf16x2(f[8 * jj + 4], f[8 * jj + 5]);
                 ov.w = pack_bf16x2(f[8 * jj + 6], f[8 * jj + 7]);
+                if (packed_relu) {
+                  ov.x = relu_bf16x2(ov.x);
+                  ov.y = relu_bf16x2(ov.y);
+                  ov.z = relu_bf16x2(ov.z);
+                  ov.w = relu_bf16x2(ov.w);
+                }
                 st_shared_v4(eb_row + (((h * 4 + jj) ^ swz) << 4), ov);
               }
             }
@@ -497,9 +520,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     } else if (group == 0) {
       for (int tile = wid; tile < num_tiles; tile += wstride) {
-        const int mn = tile_mn(p, tile);
-        const int m_tile = mn / p.num_n_tiles;
-        const int n_tile = mn - m_tile * p.num_n_tiles;
+        int m_tile, n_tile;
+        tile_coords(p, tile, m_tile, n_tile);
         const long long m = (long long)m_tile * BLOCK_M + row;
         const int n0 = n_tile * BLOCK_N;
         mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -656,10 +678,15 @@ cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb
 
 cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtensorMap& tmap_a,
                              const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
-                             const ConvGemmParams& p, int num_sms, cudaStream_t stream, const CUtensorMap* tmap_a2) {
-  if (p.split_k < 1) return cudaErrorInvalidValue;
-  if (p.kc_split && (a_mode != A_TILED || !tmap_a2)) return cudaErrorInvalidValue;
+                             const ConvGemmParams& p_in, int num_sms, cudaStream_t stream,
+                             const CUtensorMap* tmap_a2) {
+  if (p_in.split_k < 1) return cudaErrorInvalidValue;
+  if (p_in.kc_split && (a_mode != A_TILED || !tmap_a2)) return cudaErrorInvalidValue;
   const CUtensorMap& ta2 = tmap_a2 ? *tmap_a2 : tmap_a;
+  ConvGemmParams p = p_in;
+  p.n_tiles_shift = -1;
+  for (int s = 0; s < 16; ++s)
+    if ((1 << s) == p.num_n_tiles) p.n_tiles_shift = s;
   if (p.cta2) {
     if (!epi_tma || p.out_is_f32 || p.split_k != 1) return cudaErrorInvalidValue;
     if (block_n == 256 && a_mode == A_TILED)

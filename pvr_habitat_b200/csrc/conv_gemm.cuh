@@ -35,6 +35,7 @@ struct ConvGemmParams {
   int res_mode;      // 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward with the saved activation)
   int reverse;       // 1: walk the (m, n) tiles last to first (zig-zag over consecutive layers, L2 reuse)
   int pdl;           // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)
+  int n_tiles_shift; // log2(num_n_tiles) when it is a power of two, else -1 (set by launch_conv_gemm)
   int kc_split;      // > 0: K chunks >= kc_split come from a second input (tmap_a2), A_TILED only: projection shortcut
   int a2_im2col;     // second input is read with im2col-mode 1x1 taps at stride a2_stride (else a plain 2-D matrix)
   int a2_stride;

@@ -71,6 +71,7 @@ class Program:
         self.ops = []          # dicts of pvr_op fields + host tensors
         self.slot_elems = []   # per-slot bf16 elements per image
         self.free = []
+        self.deferred = []     # slots handed back once the NEXT conv has chosen its output slot
         self.emb_width = 0
 
     # ---- slots
@@ -88,6 +89,11 @@ class Program:
     def release(self, s):
         if s not in self.free:
             self.free.append(s)
+
+    def release_after_next_conv(self, s):
+        """Keep `s` out of the free list until the next conv op has been planned: lets libpvr_b200 fuse that conv
+        into the kernel that still reads `s` (conv_b2b.cu) without its output aliasing a live input."""
+        self.deferred.append(s)
 
     # ---- ops
     def conv(self, in_slot, in_chw, w_packed, k_pad, c_out, r, s, stride, lower, out_hw, scale, bias, relu_n,
@@ -117,6 +123,9 @@ class Program:
             op.update(in2_slot=in2[0], in2_c=in2[1][0], in2_h=in2[1][1], in2_w=in2[1][2], in2_pitch=in2[2],
                       in2_stride=in2[3])
         self.ops.append(op)
+        for s_ in self.deferred:
+            self.release(s_)
+        self.deferred = []
         return out_slot
 
     def maxpool(self, in_slot, c, h, w):
@@ -282,9 +291,11 @@ def _bottleneck(prog, sd, prefix, x_slot, x_chw, stride, has_ds):
         prog.release(x_slot)
     else:
         idn, sidn = x_slot, x_chw
+    # the deferred releases happen BEFORE this conv3 is planned for slots deferred earlier, and after the next block's
+    # conv1 for t2 / idn: that conv1 may run inside this conv3's kernel (conv_b2b.cu)
     y, sy = _conv_bn(prog, sd, prefix + ".conv3", prefix + ".bn3", t2, s2, 1, 0, True, res=(idn, sidn[0], 0))
-    prog.release(t2)
-    prog.release(idn)
+    prog.release_after_next_conv(t2)
+    prog.release_after_next_conv(idn)
     return y, sy
 
 

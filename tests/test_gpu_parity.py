@@ -239,7 +239,8 @@ def test_long_observation_arrays_are_embedded_in_passes(emb):
 def test_fused_stem_maxpool_and_zigzag_are_bit_identical_to_the_plain_schedule(emb, monkeypatch):
     """The max pool fused into the stem epilogue (conv3x3_patch.cu MODE 2), the zig-zag tile order, programmatic
     dependent launch and the CTA-pair (cta_group::2) kernels only change the schedule: embeddings are bitwise those of
-    the separate stem -> maxpool3x3s2_kernel, first-to-last order, one CTA per tile. 128 frames so that the pair
+    the separate stem -> maxpool3x3s2_kernel, first-to-last order, one CTA per tile, and of conv3 / next conv1 as two
+    kernels instead of the back-to-back fused one (conv_b2b.cu). 128 frames so that the pair
     kernels are selected (they need >= 74 pair tiles)."""
     frames = restate.structured_frames(128, 64, 64, 3, 5)
     net = make_net("moco_aug", emb["weight_seeds"])
@@ -248,6 +249,7 @@ def test_fused_stem_maxpool_and_zigzag_are_bit_identical_to_the_plain_schedule(e
     monkeypatch.setenv("PVR_NO_ZIGZAG", "1")
     monkeypatch.setenv("PVR_NO_PDL", "1")
     monkeypatch.setenv("PVR_CTA2", "0")
+    monkeypatch.setenv("PVR_NO_B2B", "1")
     net2 = make_net("moco_aug", emb["weight_seeds"])
     plain = net2.embed(torch.from_numpy(frames)).cpu().numpy()
     assert np.array_equal(fused, plain)

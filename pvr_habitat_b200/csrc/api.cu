@@ -50,7 +50,7 @@ int pick_block_n(int n_pad, long long m_tiles, int sms, int hint, bool has_res) 
 }
 
 struct BoundConv {
-  CUtensorMap ta, tb, to, tr, ta2, to2;
+  CUtensorMap ta, tb, to, tr, ta2, to2, tw1;
   pvr::ConvGemmParams p;
   pvr::Conv3x3PatchParams pp;
   pvr::ConvB2BParams bp;
@@ -238,24 +238,32 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       const pvr_op& q = enc->ops[i + 1];
       auto pw = [](const pvr_op& c) {
         return c.kind == PVR_OP_CONV && c.r == 1 && c.s == 1 && c.stride_h == 1 && c.stride_w == 1 && c.lower_h == 0 &&
-               c.lower_w == 0 && c.h_in == c.h_out && c.w_in == c.w_out && c.act == 0 && c.in2_c == 0 &&
-               c.flags == 0 && c.out_coff == 0 && c.block_n == 0;
+               c.lower_w == 0 && c.h_in == c.h_out && c.w_in == c.w_out && c.act == 0 && c.flags == 0 &&
+               c.out_coff == 0 && c.block_n == 0;
       };
-      if (pw(o) && pw(q) && o.c_in == 64 && o.in_pitch == 64 && o.k_pad == 64 && o.c_out == 256 && o.n_pad == 256 &&
-          o.out_pitch == 256 && o.res_slot >= 0 && o.res_pitch == 256 && o.res_coff == 0 && o.relu_n >= 256 &&
-          q.in_slot == o.out_slot && q.c_in == 256 && q.in_pitch == 256 && q.k_pad == 256 && q.res_slot < 0 &&
-          (q.c_out == 64 || q.c_out == 128) && q.n_pad == q.c_out && q.out_pitch == q.c_out && q.relu_n >= q.c_out &&
-          q.h_in == o.h_out && q.w_in == o.w_out && q.out_slot != o.out_slot && q.out_slot != o.res_slot &&
-          q.out_slot != o.in_slot) {
+      // first GEMM: identity block (K = 64, + residual) or projection-shortcut block (K = [t2 | x] = 128, no residual)
+      const bool ident = o.in2_c == 0 && o.k_pad == 64 && o.res_slot >= 0 && o.res_pitch == 256 && o.res_coff == 0;
+      const bool proj = o.in2_c == 64 && o.in2_stride == 1 && o.in2_pitch == 64 && o.k_pad == 128 && o.res_slot < 0 &&
+                        o.in2_slot >= 0 && o.in2_slot < (int)enc->slots.size();
+      if (pw(o) && pw(q) && q.in2_c == 0 && (ident || proj) && o.c_in == 64 && o.in_pitch == 64 && o.c_out == 256 &&
+          o.n_pad == 256 && o.out_pitch == 256 && o.relu_n >= 256 && q.in_slot == o.out_slot && q.c_in == 256 &&
+          q.in_pitch == 256 && q.k_pad == 256 && q.res_slot < 0 && (q.c_out == 64 || (q.c_out == 128 && ident)) &&
+          q.n_pad == q.c_out && q.out_pitch == q.c_out && q.relu_n >= q.c_out && q.h_in == o.h_out &&
+          q.w_in == o.w_out && q.out_slot != o.out_slot && q.out_slot != o.res_slot && q.out_slot != o.in_slot &&
+          !(proj && q.out_slot == o.in2_slot)) {
         const char* err = "";
         pvr::ConvB2BParams& bp = b.bp;
         bp.M = (int)M; bp.num_m_tiles = (int)((M + 127) / 128); bp.n2 = q.c_out; bp.reverse = reverse; bp.pdl = pdl;
+        bp.k1_chunks = proj ? 2 : 1;
         bp.scale1 = o.scale; bp.bias1 = o.bias; bp.scale2 = q.scale; bp.bias2 = q.bias;
+        b.ta2 = b.ta;
+        b.tr = b.ta;
         if (!pvr::make_tmap_2d(&b.ta, enc->slot_ptr[o.in_slot], 64, (uint64_t)M, 64, 128, &err) ||
-            !pvr::make_tmap_2d(&b.tb, o.weight, 64, 256, 64, 256, &err) ||
-            !pvr::make_tmap_2d(&b.tr, enc->slot_ptr[o.res_slot], 256, (uint64_t)M, 256, 128, &err) ||
+            (proj && !pvr::make_tmap_2d(&b.ta2, enc->slot_ptr[o.in2_slot], 64, (uint64_t)M, 64, 128, &err)) ||
+            !pvr::make_tmap_2d(&b.tb, o.weight, (uint64_t)o.k_pad, 256, (uint64_t)o.k_pad, 256, &err) ||
+            (ident && !pvr::make_tmap_2d(&b.tr, enc->slot_ptr[o.res_slot], 256, (uint64_t)M, 256, 128, &err)) ||
             !pvr::make_tmap_2d(&b.to, enc->slot_ptr[o.out_slot], 256, (uint64_t)M, 256, 128, &err) ||
-            !pvr::make_tmap_2d(&b.ta2, q.weight, 256, (uint64_t)q.n_pad, 256, (uint32_t)q.n_pad, &err) ||
+            !pvr::make_tmap_2d(&b.tw1, q.weight, 256, (uint64_t)q.n_pad, 256, (uint32_t)q.n_pad, &err) ||
             !pvr::make_tmap_2d(&b.to2, enc->slot_ptr[q.out_slot], (uint64_t)q.c_out, (uint64_t)M,
                                (uint64_t)q.out_pitch, 128, &err)) {
           pvr_set_error("pvr_encoder_bind: op %zu: back-to-back tensor maps: %s", i, err);
@@ -428,7 +436,7 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
     switch (o.kind) {
       case PVR_OP_CONV: {
         const BoundConv& b = enc->bound[i];
-        e = b.b2b   ? pvr::launch_conv_b2b(b.ta, b.tb, b.tr, b.to, b.ta2, b.to2, b.bp, enc->sms, stream)
+        e = b.b2b   ? pvr::launch_conv_b2b(b.ta, b.ta2, b.tb, b.tr, b.to, b.tw1, b.to2, b.bp, enc->sms, stream)
             : b.patch ? pvr::launch_conv3x3_patch(b.ta, b.tb, b.to, b.pp, enc->sms, stream)
                       : pvr::launch_conv_gemm(b.block_n, b.a_mode, b.epi_tma, b.ta, b.tb, b.to, b.tr, b.p, enc->sms,
                                             stream, &b.ta2);

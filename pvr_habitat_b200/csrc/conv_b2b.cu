@@ -1,6 +1,7 @@
 // Back-to-back fusion of a layer1 Bottleneck tail with the head of the next block (torchvision resnet.py:143-166):
 //
 //   out = relu(bn3(conv3(t2)) + x)            1x1, 64 -> 256, residual     (written: the next block's identity)
+//         (or, K1C = 2: relu(W'[t2 | x] + b), the projection-shortcut block as one GEMM, no residual)
 //   t1' = relu(bn1'(conv1'(out)))             1x1, 256 -> N2 (64 or 128)   (written: input of the next 3x3)
 //
 // As two kernels the 256-channel tensor `out` (411 MB per 256 frames at 56x56) is written once and read twice (next
@@ -27,11 +28,14 @@ namespace {
 
 constexpr int B2B_THREADS = 352;
 
-template <int N2>
+// K1C = K chunks (of 64) of the first GEMM: 1 = identity block (conv3 over t2, + residual x), 2 = projection-shortcut
+// block (K = [t2 | x], both BN scales folded into the weights, no residual; program._bottleneck).
+template <int N2, int K1C>
 struct B2BCfg {
-  static constexpr int A_STAGES = N2 == 64 ? 3 : 2;
-  static constexpr int NB = N2 == 64 ? 5 : 4;           // staging buffers for the 128 x 64 sub-tiles of `out`
-  static constexpr uint32_t W3_BYTES = 256 * 128;        // 256 output channels x 64 K
+  static constexpr int A_STAGES = N2 == 64 ? 3 : 2;     // ring of 128 x 64 A chunks
+  static constexpr int NB = K1C == 2 ? 3 : (N2 == 64 ? 5 : 4);  // staging buffers for the 128 x 64 sub-tiles of `out`
+  static constexpr uint32_t W3_CHUNK = 256 * 128;        // 256 output channels x 64 K
+  static constexpr uint32_t W3_BYTES = K1C * W3_CHUNK;
   static constexpr uint32_t W1_CHUNK = N2 * 128;         // N2 output channels x 64 K
   static constexpr uint32_t W1_BYTES = 4 * W1_CHUNK;
   static constexpr uint32_t A_BYTES = 16384, EB_BYTES = 16384;
@@ -51,13 +55,14 @@ __device__ __forceinline__ uint32_t b2b_relu2(uint32_t v) {
   return *reinterpret_cast<uint32_t*>(&x);
 }
 
-template <int N2>
+template <int N2, int K1C, bool RES>
 __global__ void __launch_bounds__(B2B_THREADS, 1)
-conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w3,
+conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_a2,
+                const __grid_constant__ CUtensorMap tmap_w3,
                 const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
                 const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_out2,
                 const ConvB2BParams p) {
-  using C = B2BCfg<N2>;
+  using C = B2BCfg<N2, K1C>;
   constexpr int A_STAGES = C::A_STAGES, NB = C::NB;
   constexpr int D = NB - 2;  // residual prefetch runs D sub-tiles ahead of the stores
   extern __shared__ uint8_t smem_raw[];
@@ -91,8 +96,9 @@ conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_a);
+    if (K1C == 2) prefetch_tmap(&tmap_a2);
     prefetch_tmap(&tmap_w3);
-    prefetch_tmap(&tmap_res);
+    if (RES) prefetch_tmap(&tmap_res);
     prefetch_tmap(&tmap_out);
     prefetch_tmap(&tmap_w1);
     prefetch_tmap(&tmap_out2);
@@ -131,19 +137,22 @@ conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ===================================================== producer: weights once, then one A1 tile per tile
     if (elect_one()) {
       mbar_expect_tx(w_bar, C::W3_BYTES + C::W1_BYTES);
-      tma_load_2d(&tmap_w3, w_bar, sW3, 0, 0);
+      for (int kc = 0; kc < K1C; ++kc) tma_load_2d(&tmap_w3, w_bar, sW3 + kc * C::W3_CHUNK, kc * 64, 0);
       for (int c = 0; c < 4; ++c) tma_load_2d(&tmap_w1, w_bar, sW1 + c * C::W1_CHUNK, c * 64, 0);
     }
     __syncwarp();
     uint32_t stage = 0, phase = 0;
     for (int n = 0; n < my_tiles; ++n) {
-      mbar_wait(&a_empty[stage], phase ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(&a_full[stage], C::A_BYTES);
-        tma_load_2d(&tmap_a, &a_full[stage], sA + stage * C::A_BYTES, 0, tile_of(n) * 128);
+#pragma unroll
+      for (int kc = 0; kc < K1C; ++kc) {
+        mbar_wait(&a_empty[stage], phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[stage], C::A_BYTES);
+          tma_load_2d(kc == 0 ? &tmap_a : &tmap_a2, &a_full[stage], sA + stage * C::A_BYTES, 0, tile_of(n) * 128);
+        }
+        __syncwarp();
+        if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
     // ===================================================== MMA #1: acc1 = A1 * W3^T
@@ -154,17 +163,22 @@ conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     uint32_t stage = 0, phase = 0;
     for (int n = 0; n < my_tiles; ++n) {
       mbar_wait(acc1_empty, (n & 1) ^ 1);  // both epilogue groups have read the previous tile's accumulator
-      mbar_wait(&a_full[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (C::A_BYTES >> 4));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_bf16(tmem_base, a_desc + (k * 32 >> 4), w3_desc + (k * 32 >> 4), idesc1, k != 0);
-        umma_commit(&a_empty[stage]);
-        umma_commit(acc1_full);
+      for (int kc = 0; kc < K1C; ++kc) {
+        mbar_wait(&a_full[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)(stage * (C::A_BYTES >> 4));
+          const uint64_t b_desc = w3_desc + (uint64_t)(kc * (C::W3_CHUNK >> 4));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base, a_desc + (k * 32 >> 4), b_desc + (k * 32 >> 4), idesc1, (kc | k) != 0);
+          umma_commit(&a_empty[stage]);
+          if (kc == K1C - 1) umma_commit(acc1_full);
+        }
+        __syncwarp();
+        if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 10) {
     // ===================================================== manager (one lane: it owns the bulk groups of the stores)
@@ -182,8 +196,12 @@ conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
             mbar_wait(&eb_mma_done[s], ((i / NB) - 1) & 1);             // ... and MMA #2 has read it
           }
           const int n = i >> 2, c = i & 3;
-          mbar_expect_tx(&eb_full[s], C::EB_BYTES);
-          tma_load_2d(&tmap_res, &eb_full[s], sEB + s * C::EB_BYTES, c * 64, tile_of(n) * 128);
+          if (RES) {
+            mbar_expect_tx(&eb_full[s], C::EB_BYTES);
+            tma_load_2d(&tmap_res, &eb_full[s], sEB + s * C::EB_BYTES, c * 64, tile_of(n) * 128);
+          } else {
+            mbar_arrive(&eb_full[s]);  // no residual: the buffer is simply free
+          }
         }
         if (i >= (uint32_t)D) {
           const uint32_t qs = i - D;
@@ -247,7 +265,7 @@ conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
           for (int jj = 0; jj < 4; ++jj) {
             const uint32_t addr = eb_row + (((h * 4 + jj) ^ swz) << 4);
-            const uint4 rv = ld_shared_v4(addr);
+            const uint4 rv = RES ? ld_shared_v4(addr) : make_uint4(0u, 0u, 0u, 0u);
             const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
             uint32_t o[4];
 #pragma unroll
@@ -322,37 +340,41 @@ conv_b2b_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   }
 }
 
-template <int N2>
-cudaError_t launch_b2b(const CUtensorMap& ta, const CUtensorMap& tw3, const CUtensorMap& tres, const CUtensorMap& tout,
-                       const CUtensorMap& tw1, const CUtensorMap& tout2, const ConvB2BParams& p, int num_sms,
-                       cudaStream_t stream) {
+template <int N2, int K1C, bool RES>
+cudaError_t launch_b2b(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw3, const CUtensorMap& tres,
+                       const CUtensorMap& tout, const CUtensorMap& tw1, const CUtensorMap& tout2,
+                       const ConvB2BParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = conv_b2b_kernel<N2, K1C, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_b2b_kernel<N2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         B2BCfg<N2>::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, B2BCfg<N2, K1C>::SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.num_m_tiles < num_sms ? p.num_m_tiles : num_sms);
   cfg.blockDim = dim3(B2B_THREADS);
-  cfg.dynamicSmemBytes = B2BCfg<N2>::SMEM;
+  cfg.dynamicSmemBytes = B2BCfg<N2, K1C>::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = p.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, conv_b2b_kernel<N2>, ta, tw3, tres, tout, tw1, tout2, p);
+  return cudaLaunchKernelEx(&cfg, kern, ta, ta2, tw3, tres, tout, tw1, tout2, p);
 }
 
 }  // namespace
 
-cudaError_t launch_conv_b2b(const CUtensorMap& ta, const CUtensorMap& tw3, const CUtensorMap& tres,
-                            const CUtensorMap& tout, const CUtensorMap& tw1, const CUtensorMap& tout2,
-                            const ConvB2BParams& p, int num_sms, cudaStream_t stream) {
-  if (p.n2 == 64) return launch_b2b<64>(ta, tw3, tres, tout, tw1, tout2, p, num_sms, stream);
-  if (p.n2 == 128) return launch_b2b<128>(ta, tw3, tres, tout, tw1, tout2, p, num_sms, stream);
+cudaError_t launch_conv_b2b(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw3,
+                            const CUtensorMap& tres, const CUtensorMap& tout, const CUtensorMap& tw1,
+                            const CUtensorMap& tout2, const ConvB2BParams& p, int num_sms, cudaStream_t stream) {
+  if (p.k1_chunks == 1 && p.n2 == 64)
+    return launch_b2b<64, 1, true>(ta, ta2, tw3, tres, tout, tw1, tout2, p, num_sms, stream);
+  if (p.k1_chunks == 1 && p.n2 == 128)
+    return launch_b2b<128, 1, true>(ta, ta2, tw3, tres, tout, tw1, tout2, p, num_sms, stream);
+  if (p.k1_chunks == 2 && p.n2 == 64)
+    return launch_b2b<64, 2, false>(ta, ta2, tw3, tres, tout, tw1, tout2, p, num_sms, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -96,15 +96,16 @@ cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& 
 struct ConvB2BParams {
   int M, num_m_tiles;  // pixels, ceil(M / 128)
   int n2;              // 64 or 128
+  int k1_chunks;       // 1: conv3 over t2 (+ residual); 2: [t2 | x] projection-shortcut GEMM, no residual
   int reverse, pdl;
   const float* scale1; // (256) conv3's folded BN
   const float* bias1;
   const float* scale2; // (n2) the next conv1's folded BN
   const float* bias2;
 };
-cudaError_t launch_conv_b2b(const CUtensorMap& ta, const CUtensorMap& tw3, const CUtensorMap& tres,
-                            const CUtensorMap& tout, const CUtensorMap& tw1, const CUtensorMap& tout2,
-                            const ConvB2BParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_conv_b2b(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw3,
+                            const CUtensorMap& tres, const CUtensorMap& tout, const CUtensorMap& tw1,
+                            const CUtensorMap& tout2, const ConvB2BParams& p, int num_sms, cudaStream_t stream);
 // im2col map over an NHWC bf16 tensor (N, H, W, pitch) exposing `c` channels per pixel.
 bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int lower_w,
                       int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int channels_per_pixel,

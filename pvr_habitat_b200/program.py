@@ -282,8 +282,8 @@ def _bottleneck(prog, sd, prefix, x_slot, x_chw, stride, has_ds):
         y = prog.conv(t2, s2, packed, k, co, 1, 1, (1, 1), (0, 0), (p, q), torch.ones(co), b3 + bd, co,
                       in2=(x_slot, x_chw, x_chw[0], stride),
                       flops=2 * p * q * co * (c2 + x_chw[0]))
-        prog.release(t2)
-        prog.release(x_slot)
+        prog.release_after_next_conv(t2)      # the next block's conv1 may run inside this kernel (conv_b2b.cu)
+        prog.release_after_next_conv(x_slot)
         return y, (co, p, q)
     if has_ds:
         idn, sidn = _conv_bn(prog, sd, prefix + ".downsample.0", prefix + ".downsample.1", x_slot, x_chw, stride, 0,

@@ -584,7 +584,10 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   if (d->out_f32 == 2 && block_n > 128) block_n = 128;
   // CTA pairs (cta_group::2, 256 x 256 tiles) for wide bf16-output GEMMs with enough K: ViT QKV / fc1
   static const bool pair_ok = !(getenv("PVR_CTA2") && atoi(getenv("PVR_CTA2")) == 0);
-  if (pair_ok && d->out_f32 == 0 && !d->res && split_k == 1 && d->n_pad % 256 == 0 && d->n % 64 == 0 && d->k >= 512 &&
+  static const int pair_f32 = getenv("PVR_PAIR_F32") ? atoi(getenv("PVR_PAIR_F32")) : 1;
+  const bool pair_bf16 = d->out_f32 == 0 && !d->res && d->n % 64 == 0 && d->k >= 512;
+  const bool pair_fp32 = pair_f32 && d->out_f32 == 1 && d->n % 32 == 0 && d->k >= 768;  // ViT proj / fc2 (+ residual)
+  if (pair_ok && (pair_bf16 || pair_fp32) && split_k == 1 && d->n_pad % 256 == 0 &&
       ((long long)(d->m + 255) / 256) * (d->n_pad / 256) >= sms / 2) {
     p.cta2 = 1;
     p.num_m_tiles = (d->m + 255) / 256;

@@ -631,10 +631,10 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
 }
 
 // CTA-pair variant (256 x BLOCK_N tiles, cluster of 2, tcgen05 cta_group::2), bf16 output through the TMA epilogue.
-template <int BLOCK_N, int A_MODE>
+template <int BLOCK_N, int A_MODE, bool OUT_F32 = false>
 cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                         const CUtensorMap& ta2, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
-  auto kern = conv_gemm_kernel<BLOCK_N, A_MODE, true, false, true>;
+  auto kern = conv_gemm_kernel<BLOCK_N, A_MODE, true, OUT_F32, true>;
   using C = Cfg<BLOCK_N, true, true>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -688,7 +688,11 @@ cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtens
   for (int s = 0; s < 16; ++s)
     if ((1 << s) == p.num_n_tiles) p.n_tiles_shift = s;
   if (p.cta2) {
-    if (!epi_tma || p.out_is_f32 || p.split_k != 1) return cudaErrorInvalidValue;
+    if (!epi_tma || p.split_k != 1) return cudaErrorInvalidValue;
+    if (p.out_is_f32) {  // fp32 output / fp32 residual stream (ViT proj, fc2)
+      if (block_n != 256 || a_mode != A_TILED) return cudaErrorInvalidValue;
+      return launch_pair<256, A_TILED, true>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+    }
     if (block_n == 256 && a_mode == A_TILED)
       return launch_pair<256, A_TILED>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
     if (block_n == 256 && a_mode == A_IM2COL64)

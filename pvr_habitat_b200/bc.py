@@ -32,8 +32,16 @@ class BCTrainer:
         self.group = process_group
         self.n_samples = len(action)
         self.host_batches = host_batches
-        if host_batches:  # the reference's data path: numpy arrays on the host, gathered and copied every step
-            self.obs, self.action, self.done = np.asarray(obs), np.asarray(action), np.asarray(done)
+        self._next = None
+        if host_batches:
+            # the reference's data path (dataset in host memory, main_bc_2.py:196-203), pipelined: the rows of step
+            # i+1 are gathered into pinned staging buffers and copied on a side stream while step i runs on the GPU
+            self.obs = torch.from_numpy(np.ascontiguousarray(np.asarray(obs)))
+            self.action = torch.from_numpy(np.ascontiguousarray(np.asarray(action))).long()
+            self.done = torch.from_numpy(np.ascontiguousarray(np.asarray(done)))
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = None
+            self._stage_i = 0
         else:
             self.obs = torch.as_tensor(np.asarray(obs)).to(self.device)
             self.action = torch.as_tensor(np.asarray(action)).long().to(self.device)
@@ -56,19 +64,39 @@ class BCTrainer:
     def make_batch(self, starting_i):
         idx = window_indices(starting_i, self.T, self.n_samples)  # (T, B_local)
         if self.host_batches:
-            o = torch.from_numpy(self.obs[idx]).to(self.device, non_blocking=True)
-            a = torch.from_numpy(self.action[idx]).to(self.device, non_blocking=True)
-            d = torch.from_numpy(self.done[idx]).to(self.device, non_blocking=True)
-            return o, a, d
+            flat = torch.from_numpy(np.ascontiguousarray(idx.reshape(-1)))
+            shape = tuple(idx.shape)
+            if self._stage is None or self._stage[0][0].shape[0] != flat.numel():
+                self._stage = [tuple(torch.empty((flat.numel(),) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                                     for t in (self.obs, self.action, self.done)) for _ in range(2)]
+                self._stage_ev = [torch.cuda.Event() for _ in range(2)]
+            k = self._stage_i
+            self._stage_i ^= 1
+            self._stage_ev[k].synchronize()  # the copy that last used this staging buffer has completed
+            out = []
+            with torch.cuda.stream(self._copy_stream):
+                for src, pin in zip((self.obs, self.action, self.done), self._stage[k]):
+                    torch.index_select(src, 0, flat, out=pin)  # multi-threaded host gather into pinned memory
+                    out.append(pin.to(self.device, non_blocking=True).reshape(shape + tuple(src.shape[1:])))
+                self._stage_ev[k].record(self._copy_stream)
+            return tuple(out) + (self._stage_ev[k],)
         ix = torch.from_numpy(idx).to(self.device, non_blocking=True)
-        return self.obs[ix], self.action[ix], self.done[ix]
+        return self.obs[ix], self.action[ix], self.done[ix], None
+
+    def _draw(self):
+        starting_i = sample_with_minimum_distance(n=self.n_samples, k=self.B, d=self.T)
+        mine = parallel.shard_starts(starting_i, self.rank, self.world)
+        return self.make_batch(mine) + (len(mine),)
 
     def step(self):
         """One optimisation step; returns the (device) loss of the GLOBAL batch."""
-        starting_i = sample_with_minimum_distance(n=self.n_samples, k=self.B, d=self.T)
-        mine = parallel.shard_starts(starting_i, self.rank, self.world)
-        o, a, d = self.make_batch(mine)
-        state = tuple(s.to(self.device) for s in self.model.initial_state(batch_size=len(mine)))
+        o, a, d, ready, n_mine = self._next if self._next is not None else self._draw()
+        self._next = None
+        if ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(ready)
+            for t in (o, a, d):
+                t.record_stream(torch.cuda.current_stream(self.device))
+        state = tuple(s.to(self.device) for s in self.model.initial_state(batch_size=n_mine))
         output, _ = self.model(dict(obs=o, done=d), state)
         loss = bc_loss(output['policy_logits'], a, global_rows=self.global_rows)
         self.scheduler.step()
@@ -80,6 +108,8 @@ class BCTrainer:
             torch.distributed.all_reduce(loss, group=self.group)
         self.frames += self.T * self.B
         self.last_loss = loss.detach()
+        if self.host_batches:  # gather + copy the next batch while the GPU works on this one (same draw order)
+            self._next = self._draw()
         return self.last_loss
 
     def gradient_norm(self):

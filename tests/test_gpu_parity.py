@@ -253,3 +253,18 @@ def test_fused_stem_maxpool_and_zigzag_are_bit_identical_to_the_plain_schedule(e
     net2 = make_net("moco_aug", emb["weight_seeds"])
     plain = net2.embed(torch.from_numpy(frames)).cpu().numpy()
     assert np.array_equal(fused, plain)
+
+
+def test_fused_kernels_bit_identical_on_ragged_tiles(emb, monkeypatch):
+    """3 frames of 224 x 224: 9408 layer1 pixels = 73.5 tiles of 128 rows, so the back-to-back kernel, the fused
+    stem / max pool and the projection-shortcut GEMM all see a ragged last tile (TMA zero fill / clipping). Same
+    bitwise comparison against the plain schedule as above, on the two-trunk model with compression heads."""
+    frames = restate.structured_frames(3, 224, 224, 3, 11)
+    net = make_net("moco_aug_uber_34", emb["weight_seeds"])
+    fused = net.embed(torch.from_numpy(frames)).cpu().numpy()
+    for k, v in (("PVR_NO_POOL_FUSION", "1"), ("PVR_NO_ZIGZAG", "1"), ("PVR_NO_PDL", "1"), ("PVR_CTA2", "0"),
+                 ("PVR_NO_B2B", "1")):
+        monkeypatch.setenv(k, v)
+    net2 = make_net("moco_aug_uber_34", emb["weight_seeds"])
+    plain = net2.embed(torch.from_numpy(frames)).cpu().numpy()
+    assert np.array_equal(fused, plain)

@@ -474,6 +474,31 @@ __global__ void __launch_bounds__(256) optim_step_kernel(const TensorList tl, co
   float* s1 = tl.s1[t];
   float* s2 = tl.s2[t];
   const long long n = tl.n[t];
+  // float4 path for the large, 16-byte aligned tensors (weights): 4x fewer instructions, more bytes in flight
+  if (mode == 0 && (n & 3) == 0 &&
+      ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(s1)) & 15) == 0) {
+    float4* p4 = reinterpret_cast<float4*>(p);
+    float4* g4 = reinterpret_cast<float4*>(g);
+    float4* v4 = reinterpret_cast<float4*>(s1);
+    const float oma = 1.f - alpha_or_beta1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2);
+         i += (long long)gridDim.x * blockDim.x) {
+      float4 gr = g4[i], v = v4[i], w = p4[i];
+      gr.x *= coef; gr.y *= coef; gr.z *= coef; gr.w *= coef;
+      v.x = alpha_or_beta1 * v.x + oma * gr.x * gr.x;
+      v.y = alpha_or_beta1 * v.y + oma * gr.y * gr.y;
+      v.z = alpha_or_beta1 * v.z + oma * gr.z * gr.z;
+      v.w = alpha_or_beta1 * v.w + oma * gr.w * gr.w;
+      w.x -= lr * gr.x / (sqrtf(v.x) + eps);
+      w.y -= lr * gr.y / (sqrtf(v.y) + eps);
+      w.z -= lr * gr.z / (sqrtf(v.z) + eps);
+      w.w -= lr * gr.w / (sqrtf(v.w) + eps);
+      g4[i] = gr;
+      v4[i] = v;
+      p4[i] = w;
+    }
+    return;
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gr = g[i] * coef;
     g[i] = gr;  // the clipped gradient stays visible in .grad, like clip_grad_norm_

@@ -156,6 +156,9 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
   const bool zigzag = getenv("PVR_NO_ZIGZAG") == nullptr;
   const int pdl = getenv("PVR_NO_PDL") == nullptr;
   const bool b2b_on = getenv("PVR_NO_B2B") == nullptr;
+  // layer2 variant with streamed weights: correct and bit-identical, but measured neutral (133 us against 86 + 51 us
+  // per 256 frames: the 256 KB of weights per tile go through two-slot rings) -> opt-in
+  const bool b2b_stream_on = b2b_on && getenv("PVR_B2B_STREAM") != nullptr;
   const int pair_mode = getenv("PVR_CTA2") ? atoi(getenv("PVR_CTA2")) : 1;  // 0 off, 1: 256-wide pair tiles; 2: + 128-wide (no residual); 3: + residual layers
   for (size_t i = 0; i < enc->ops.size(); ++i) {
     const pvr_op& o = enc->ops[i];
@@ -269,6 +272,34 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
           pvr_set_error("pvr_encoder_bind: op %zu: back-to-back tensor maps: %s", i, err);
           return PVR_ERR_CUDA;
         }
+        b.b2b = true;
+        enc->fused[i + 1] = 1;
+        slot_rev[q.out_slot] = reverse;
+        continue;
+      }
+      // layer2 identity blocks: 128 -> 512 (+ residual), then 512 -> 128; weights streamed (conv_b2b_stream_kernel)
+      if (b2b_stream_on && pw(o) && pw(q) && o.in2_c == 0 && q.in2_c == 0 && o.c_in == 128 && o.in_pitch == 128 &&
+          o.k_pad == 128 && o.c_out == 512 && o.n_pad == 512 && o.out_pitch == 512 && o.res_slot >= 0 &&
+          o.res_pitch == 512 && o.res_coff == 0 && o.relu_n >= 512 && q.in_slot == o.out_slot && q.c_in == 512 &&
+          q.in_pitch == 512 && q.k_pad == 512 && q.res_slot < 0 && q.c_out == 128 && q.n_pad == 128 &&
+          q.out_pitch == 128 && q.relu_n >= 128 && q.h_in == o.h_out && q.w_in == o.w_out &&
+          q.out_slot != o.out_slot && q.out_slot != o.res_slot && q.out_slot != o.in_slot) {
+        const char* err = "";
+        pvr::ConvB2BParams& bp = b.bp;
+        bp.M = (int)M; bp.num_m_tiles = (int)((M + 127) / 128); bp.n2 = 128; bp.reverse = reverse; bp.pdl = pdl;
+        bp.k1_chunks = 2; bp.streamed = 1;
+        bp.scale1 = o.scale; bp.bias1 = o.bias; bp.scale2 = q.scale; bp.bias2 = q.bias;
+        b.ta2 = b.ta;
+        if (!pvr::make_tmap_2d(&b.ta, enc->slot_ptr[o.in_slot], 128, (uint64_t)M, 128, 128, &err) ||
+            !pvr::make_tmap_2d(&b.tb, o.weight, 128, 512, 128, 256, &err) ||
+            !pvr::make_tmap_2d(&b.tr, enc->slot_ptr[o.res_slot], 512, (uint64_t)M, 512, 128, &err) ||
+            !pvr::make_tmap_2d(&b.to, enc->slot_ptr[o.out_slot], 512, (uint64_t)M, 512, 128, &err) ||
+            !pvr::make_tmap_2d(&b.tw1, q.weight, 512, 128, 512, 128, &err) ||
+            !pvr::make_tmap_2d(&b.to2, enc->slot_ptr[q.out_slot], 128, (uint64_t)M, 128, 128, &err)) {
+          pvr_set_error("pvr_encoder_bind: op %zu: back-to-back (streamed) tensor maps: %s", i, err);
+          return PVR_ERR_CUDA;
+        }
+        b.ta2 = b.ta;
         b.b2b = true;
         enc->fused[i + 1] = 1;
         slot_rev[q.out_slot] = reverse;

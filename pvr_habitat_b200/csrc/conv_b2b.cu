@@ -364,11 +364,360 @@ cudaError_t launch_b2b(const CUtensorMap& ta, const CUtensorMap& ta2, const CUte
   return cudaLaunchKernelEx(&cfg, kern, ta, ta2, tw3, tres, tout, tw1, tout2, p);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Layer2 variant: conv3 128 -> 512 (+ residual), next conv1 512 -> 128. The weights (128 KB + 128 KB) do not fit shared
+// memory next to the staging buffers, so they are streamed from L2 through small rings: W3 in four 256 x 64 blocks per
+// tile (two per 256-column half of `out`), W1' in eight 128 x 64 chunks (one per finished sub-tile). acc1 is reused
+// for the two halves; 384 threads = the roles above + warp 11, the W1' producer.
+constexpr int B2S_THREADS = 384;
+struct B2SCfg {
+  static constexpr int AS = 3, W3S = 2, W1S = 2, NB = 3;
+  static constexpr uint32_t A_BYTES = 16384, W3_BYTES = 32768, W1_BYTES = 16384, EB_BYTES = 16384;
+  static constexpr uint32_t SB_BYTES = (1024 + 256) * 4;  // scale1[512] | bias1[512] | scale2[128] | bias2[128]
+  static constexpr uint32_t SMEM = 1024 + AS * A_BYTES + W3S * W3_BYTES + W1S * W1_BYTES + NB * EB_BYTES + EB_BYTES +
+                                   ((SB_BYTES + 1023) / 1024) * 1024 + 512;
+  static_assert(SMEM <= 232448, "exceeds the 227 KiB shared memory of one CTA");
+};
+
+__global__ void __launch_bounds__(B2S_THREADS, 1)
+conv_b2b_stream_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w3,
+                       const __grid_constant__ CUtensorMap tmap_res, const __grid_constant__ CUtensorMap tmap_out,
+                       const __grid_constant__ CUtensorMap tmap_w1, const __grid_constant__ CUtensorMap tmap_out2,
+                       const ConvB2BParams p) {
+  using C = B2SCfg;
+  constexpr int AS = C::AS, W3S = C::W3S, W1S = C::W1S, NB = C::NB, N2 = 128;
+  constexpr int D = NB - 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sW3 = sA + AS * C::A_BYTES;
+  uint8_t* sW1 = sW3 + W3S * C::W3_BYTES;
+  uint8_t* sEB = sW1 + W1S * C::W1_BYTES;
+  uint8_t* sS2 = sEB + NB * C::EB_BYTES;
+  float* sSB = reinterpret_cast<float*>(sS2 + C::EB_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sSB) + ((C::SB_BYTES + 1023) / 1024) * 1024);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + AS;
+  uint64_t* w3_full = a_empty + AS;
+  uint64_t* w3_empty = w3_full + W3S;
+  uint64_t* w1_full = w3_empty + W3S;
+  uint64_t* w1_empty = w1_full + W1S;
+  uint64_t* acc1_full = w1_empty + W1S;
+  uint64_t* acc1_empty = acc1_full + 1;
+  uint64_t* acc2_full = acc1_empty + 1;   // [2]
+  uint64_t* acc2_empty = acc2_full + 2;   // [2]
+  uint64_t* eb_full = acc2_empty + 2;     // [NB]
+  uint64_t* eb_ready = eb_full + NB;      // [NB]
+  uint64_t* eb_mma_done = eb_ready + NB;  // [NB]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(eb_mma_done + NB);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.num_m_tiles;
+  const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto tile_of = [&](int n) {
+    const int t = (int)blockIdx.x + n * (int)gridDim.x;
+    return p.reverse ? num_tiles - 1 - t : t;
+  };
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w3);
+    prefetch_tmap(&tmap_res);
+    prefetch_tmap(&tmap_out);
+    prefetch_tmap(&tmap_w1);
+    prefetch_tmap(&tmap_out2);
+    for (int s = 0; s < AS; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < W3S; ++s) { mbar_init(&w3_full[s], 1); mbar_init(&w3_empty[s], 1); }
+    for (int s = 0; s < W1S; ++s) { mbar_init(&w1_full[s], 1); mbar_init(&w1_empty[s], 1); }
+    mbar_init(acc1_full, 1);
+    mbar_init(acc1_empty, 256);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc2_full[s], 1); mbar_init(&acc2_empty[s], 128); }
+    for (int s = 0; s < NB; ++s) {
+      mbar_init(&eb_full[s], 1);
+      mbar_init(&eb_ready[s], 1);
+      mbar_init(&eb_mma_done[s], 1);
+    }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 1024 + 256; i += blockDim.x)
+    sSB[i] = i < 512 ? p.scale1[i] : i < 1024 ? p.bias1[i - 512] : i < 1152 ? p.scale2[i - 1024] : p.bias2[i - 1152];
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr_smem, 0);
+  griddep_launch();
+  griddep_wait();
+
+  if (warp == 0) {
+    // ===================================================== producer: A chunks of the tile, then its four W3 blocks
+    uint32_t as = 0, aph = 0, ws = 0, wph = 0;
+    for (int n = 0; n < my_tiles; ++n) {
+      const int m0 = tile_of(n) * 128;
+      for (int kc = 0; kc < 2; ++kc) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&a_full[as], C::A_BYTES);
+          tma_load_2d(&tmap_a, &a_full[as], sA + as * C::A_BYTES, kc * 64, m0);
+        }
+        __syncwarp();
+        if (++as == AS) { as = 0; aph ^= 1; }
+      }
+      for (int b = 0; b < 4; ++b) {  // block b: output columns [256 * (b >> 1), +256), K chunk b & 1
+        mbar_wait(&w3_empty[ws], wph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&w3_full[ws], C::W3_BYTES);
+          tma_load_2d(&tmap_w3, &w3_full[ws], sW3 + ws * C::W3_BYTES, (b & 1) * 64, (b >> 1) * 256);
+        }
+        __syncwarp();
+        if (++ws == W3S) { ws = 0; wph ^= 1; }
+      }
+    }
+  } else if (warp == 11) {
+    // ===================================================== W1' producer: one 128 x 64 chunk per sub-tile of `out`
+    uint32_t s = 0, ph = 0;
+    for (int n = 0; n < my_tiles; ++n)
+      for (int j = 0; j < 8; ++j) {
+        mbar_wait(&w1_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(&w1_full[s], C::W1_BYTES);
+          tma_load_2d(&tmap_w1, &w1_full[s], sW1 + s * C::W1_BYTES, j * 64, 0);
+        }
+        __syncwarp();
+        if (++s == W1S) { s = 0; ph ^= 1; }
+      }
+  } else if (warp == 1) {
+    // ===================================================== MMA #1: acc1 = A (2 chunks) * W3[half]^T, twice per tile
+    constexpr uint32_t idesc1 = umma_idesc_bf16(128, 256);
+    const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+    const uint64_t w_desc0 = umma_desc_sw128(smem_u32(sW3));
+    uint32_t as = 0, aph = 0, ws = 0, wph = 0, hc = 0;
+    for (int n = 0; n < my_tiles; ++n) {
+      uint32_t slot[2];
+      for (int h = 0; h < 2; ++h, ++hc) {
+        mbar_wait(acc1_empty, (hc & 1) ^ 1);  // both epilogue groups have read the previous half
+        for (int kc = 0; kc < 2; ++kc) {
+          if (h == 0) {
+            slot[kc] = as;
+            mbar_wait(&a_full[as], aph);
+            if (++as == AS) { as = 0; aph ^= 1; }
+          }
+          mbar_wait(&w3_full[ws], wph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_desc = a_desc0 + (uint64_t)(slot[kc] * (C::A_BYTES >> 4));
+            const uint64_t b_desc = w_desc0 + (uint64_t)(ws * (C::W3_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base, a_desc + (k * 32 >> 4), b_desc + (k * 32 >> 4), idesc1, (kc | k) != 0);
+            umma_commit(&w3_empty[ws]);
+            if (kc == 1) {
+              umma_commit(acc1_full);
+              if (h == 1) {  // the tile's A chunks are free once the second half has been multiplied
+                umma_commit(&a_empty[slot[0]]);
+                umma_commit(&a_empty[slot[1]]);
+              }
+            }
+          }
+          __syncwarp();
+          if (++ws == W3S) { ws = 0; wph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================================================== manager: residual prefetch, stores of `out`, MMA #2
+    if (lane == 0) {
+      constexpr uint32_t idesc2 = umma_idesc_bf16(128, N2);
+      const uint64_t w1_desc0 = umma_desc_sw128(smem_u32(sW1));
+      const uint64_t eb_desc0 = umma_desc_sw128(smem_u32(sEB));
+      const uint32_t total = (uint32_t)my_tiles * 8;
+      uint32_t w1s = 0, w1ph = 0;
+      for (uint32_t i = 0; i < total + D; ++i) {
+        if (i < total) {
+          const uint32_t s = i % NB;
+          if (i >= (uint32_t)NB) {
+            bulk_wait_group_read<1>();
+            mbar_wait(&eb_mma_done[s], ((i / NB) - 1) & 1);
+          }
+          const int n = i >> 3, c8 = i & 7;
+          mbar_expect_tx(&eb_full[s], C::EB_BYTES);
+          tma_load_2d(&tmap_res, &eb_full[s], sEB + s * C::EB_BYTES, c8 * 64, tile_of(n) * 128);
+        }
+        if (i >= (uint32_t)D) {
+          const uint32_t qs = i - D;
+          const uint32_t s = qs % NB, ph = (qs / NB) & 1;
+          const int n = qs >> 3, c8 = qs & 7;
+          const uint32_t abuf = n & 1;
+          if (c8 == 0) mbar_wait(&acc2_empty[abuf], ((n >> 1) & 1) ^ 1);
+          mbar_wait(&eb_ready[s], ph);
+          mbar_wait(&w1_full[w1s], w1ph);
+          tc_fence_after();
+          tma_store_2d(&tmap_out, sEB + s * C::EB_BYTES, c8 * 64, tile_of(n) * 128);
+          bulk_commit_group();
+          const uint64_t a_desc = eb_desc0 + (uint64_t)(s * (C::EB_BYTES >> 4));
+          const uint64_t b_desc = w1_desc0 + (uint64_t)(w1s * (C::W1_BYTES >> 4));
+          const uint32_t d_tmem = tmem_base + 256 + abuf * N2;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, a_desc + (k * 32 >> 4), b_desc + (k * 32 >> 4), idesc2, (c8 | k) != 0);
+          umma_commit(&eb_mma_done[s]);
+          umma_commit(&w1_empty[w1s]);
+          if (c8 == 7) umma_commit(&acc2_full[abuf]);
+          if (++w1s == W1S) { w1s = 0; w1ph ^= 1; }
+        }
+      }
+      bulk_wait_group<0>();
+    }
+  } else {
+    // ===================================================== epilogue groups
+    const int group = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int gtid = (warp - 2 - group * 4) * 32 + lane;
+    const bool leader = gtid == 0;
+    const uint32_t swz = (uint32_t)(row & 7);
+    const uint32_t sb_addr = smem_u32(sSB);
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    uint32_t hc = 0;
+    for (int n = 0; n < my_tiles; ++n) {
+      for (int h = 0; h < 2; ++h, ++hc) {
+        mbar_wait(acc1_full, hc & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = group; c < 4; c += 2) {
+          const uint32_t q = (uint32_t)n * 8 + h * 4 + c;
+          const uint32_t s = q % NB, ph = (q / NB) & 1;
+          const uint32_t eb_row = smem_u32(sEB + s * C::EB_BYTES) + row * 128;
+          const int col0 = h * 256 + c * 64;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + c * 64, v);
+          mbar_wait(&eb_full[s], ph);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            float f[32];
+            tmem_wait_ld();
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const uint4 s4 = ld_shared_v4(sb_addr + (col0 + hh * 32 + jj * 4) * 4);
+              const uint4 b4 = ld_shared_v4(sb_addr + 2048 + (col0 + hh * 32 + jj * 4) * 4);
+              f[4 * jj + 0] = fmaf(__uint_as_float(v[4 * jj + 0]), __uint_as_float(s4.x), __uint_as_float(b4.x));
+              f[4 * jj + 1] = fmaf(__uint_as_float(v[4 * jj + 1]), __uint_as_float(s4.y), __uint_as_float(b4.y));
+              f[4 * jj + 2] = fmaf(__uint_as_float(v[4 * jj + 2]), __uint_as_float(s4.z), __uint_as_float(b4.z));
+              f[4 * jj + 3] = fmaf(__uint_as_float(v[4 * jj + 3]), __uint_as_float(s4.w), __uint_as_float(b4.w));
+            }
+            if (hh == 0) tmem_ld_32x32b_x32(tmem_base + lane_off + c * 64 + 32, v);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const uint32_t addr = eb_row + (((hh * 4 + jj) ^ swz) << 4);
+              const uint4 rv = ld_shared_v4(addr);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+              uint32_t o[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t)
+                o[t] = b2b_relu2(b2b_pack(f[8 * jj + 2 * t] + __uint_as_float(w[t] << 16),
+                                          f[8 * jj + 2 * t + 1] + __uint_as_float(w[t] & 0xFFFF0000u)));
+              st_shared_v4(addr, make_uint4(o[0], o[1], o[2], o[3]));
+            }
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + group, 128);
+          if (leader) mbar_arrive(&eb_ready[s]);
+        }
+        tc_fence_before();
+        mbar_arrive(acc1_empty);
+      }
+      if ((n & 1) == group) {
+        // ---- epilogue #2: t1' = relu(bn1'(acc2)), two 64-column halves through one staging buffer
+        const uint32_t abuf = n & 1;
+        mbar_wait(&acc2_full[abuf], (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t s2_row = smem_u32(sS2) + row * 128;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + abuf * N2 + hh * 64, v);
+          if (leader) bulk_wait_group_read<0>();
+          named_bar_sync(1 + group, 128);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float f[32];
+            tmem_wait_ld();
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const uint4 s4 = ld_shared_v4(sb_addr + 4096 + (hh * 64 + h * 32 + jj * 4) * 4);
+              const uint4 b4 = ld_shared_v4(sb_addr + 4096 + 512 + (hh * 64 + h * 32 + jj * 4) * 4);
+              f[4 * jj + 0] = fmaf(__uint_as_float(v[4 * jj + 0]), __uint_as_float(s4.x), __uint_as_float(b4.x));
+              f[4 * jj + 1] = fmaf(__uint_as_float(v[4 * jj + 1]), __uint_as_float(s4.y), __uint_as_float(b4.y));
+              f[4 * jj + 2] = fmaf(__uint_as_float(v[4 * jj + 2]), __uint_as_float(s4.z), __uint_as_float(b4.z));
+              f[4 * jj + 3] = fmaf(__uint_as_float(v[4 * jj + 3]), __uint_as_float(s4.w), __uint_as_float(b4.w));
+            }
+            if (h == 0) tmem_ld_32x32b_x32(tmem_base + lane_off + 256 + abuf * N2 + hh * 64 + 32, v);
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              uint4 ov;
+              ov.x = b2b_relu2(b2b_pack(f[8 * jj + 0], f[8 * jj + 1]));
+              ov.y = b2b_relu2(b2b_pack(f[8 * jj + 2], f[8 * jj + 3]));
+              ov.z = b2b_relu2(b2b_pack(f[8 * jj + 4], f[8 * jj + 5]));
+              ov.w = b2b_relu2(b2b_pack(f[8 * jj + 6], f[8 * jj + 7]));
+              st_shared_v4(s2_row + (((h * 4 + jj) ^ swz) << 4), ov);
+            }
+          }
+          if (hh == 1) {
+            tc_fence_before();
+            mbar_arrive(&acc2_empty[abuf]);
+          }
+          fence_proxy_async();
+          named_bar_sync(1 + group, 128);
+          if (leader) {
+            tma_store_2d(&tmap_out2, sS2, hh * 64, tile_of(n) * 128);
+            bulk_commit_group();
+          }
+        }
+      }
+    }
+    if (leader) bulk_wait_group<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+cudaError_t launch_b2b_stream(const CUtensorMap& ta, const CUtensorMap& tw3, const CUtensorMap& tres,
+                              const CUtensorMap& tout, const CUtensorMap& tw1, const CUtensorMap& tout2,
+                              const ConvB2BParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_b2b_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         B2SCfg::SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.num_m_tiles < num_sms ? p.num_m_tiles : num_sms);
+  cfg.blockDim = dim3(B2S_THREADS);
+  cfg.dynamicSmemBytes = B2SCfg::SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, conv_b2b_stream_kernel, ta, tw3, tres, tout, tw1, tout2, p);
+}
+
 }  // namespace
 
 cudaError_t launch_conv_b2b(const CUtensorMap& ta, const CUtensorMap& ta2, const CUtensorMap& tw3,
                             const CUtensorMap& tres, const CUtensorMap& tout, const CUtensorMap& tw1,
                             const CUtensorMap& tout2, const ConvB2BParams& p, int num_sms, cudaStream_t stream) {
+  if (p.streamed) return launch_b2b_stream(ta, tw3, tres, tout, tw1, tout2, p, num_sms, stream);
   if (p.k1_chunks == 1 && p.n2 == 64)
     return launch_b2b<64, 1, true>(ta, ta2, tw3, tres, tout, tw1, tout2, p, num_sms, stream);
   if (p.k1_chunks == 1 && p.n2 == 128)

@@ -96,6 +96,7 @@ cudaError_t launch_conv3x3_patch(const CUtensorMap& tmap_in, const CUtensorMap& 
 struct ConvB2BParams {
   int M, num_m_tiles;  // pixels, ceil(M / 128)
   int n2;              // 64 or 128
+  int streamed;        // 1: layer2 variant (128 -> 512 + residual, then 512 -> 128), weights streamed through rings
   int k1_chunks;       // 1: conv3 over t2 (+ residual); 2: [t2 | x] projection-shortcut GEMM, no residual
   int reverse, pdl;
   const float* scale1; // (256) conv3's folded BN

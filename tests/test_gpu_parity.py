@@ -268,3 +268,17 @@ def test_fused_kernels_bit_identical_on_ragged_tiles(emb, monkeypatch):
     net2 = make_net("moco_aug_uber_34", emb["weight_seeds"])
     plain = net2.embed(torch.from_numpy(frames)).cpu().numpy()
     assert np.array_equal(fused, plain)
+
+
+def test_streamed_back_to_back_kernel_is_bit_identical(emb, monkeypatch):
+    """conv_b2b_stream_kernel (layer2: 128 -> 512 + residual fused with the next 512 -> 128, weights streamed through
+    rings) is opt-in (PVR_B2B_STREAM); its embeddings are bitwise those of the default schedule."""
+    frames = restate.structured_frames(6, 224, 224, 3, 17)
+    net = make_net("moco_aug", emb["weight_seeds"])
+    default = net.embed(torch.from_numpy(frames)).cpu().numpy()
+    monkeypatch.setenv("PVR_B2B_STREAM", "1")
+    net2 = make_net("moco_aug", emb["weight_seeds"])
+    streamed = net2.embed(torch.from_numpy(frames)).cpu().numpy()
+    assert np.array_equal(default, streamed)
+    assert net2.encoder().lib.pvr_encoder_launch_count(net2.encoder().handle) < \
+        net.encoder().lib.pvr_encoder_launch_count(net.encoder().handle)

@@ -38,3 +38,19 @@ for i, (m, t) in enumerate(zip(enc.op_meta, ms)):
     print(f"{i:3d} {k:8} {shape:28} {t * 1e3:8.1f} {flops / t / 1e9 if t > 0 else 0:7.0f} {mb:8.1f} {mb / t if t > 0 else 0:7.0f}")
     tot += t
 print(f"total {tot * 1e3:.1f} us")
+# ---- by category
+cat = {}
+for m, t in zip(enc.op_meta, ms):
+    if m["kind"] != 1:
+        k = KIND.get(m["kind"], "?")
+    elif m.get("r", 1) == 7:
+        k = "stem (+pool)"
+    elif m.get("r", 1) == 3:
+        k = f"3x3 @{m['h_out']}"
+    elif m.get("res_slot", -1) >= 0:
+        k = f"1x1+res @{m['h_out']}"
+    else:
+        k = f"1x1 @{m['h_out']}"
+    cat[k] = cat.get(k, 0.0) + t
+for k, v in sorted(cat.items(), key=lambda kv: -kv[1]):
+    print(f"  {k:16s} {v * 1e3:8.1f} us {100 * v / tot:5.1f} %")

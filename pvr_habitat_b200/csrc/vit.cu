@@ -14,6 +14,13 @@ extern void pvr_set_error(const char* fmt, ...);
 namespace pvr {
 namespace {
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+
 __device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -214,31 +221,72 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       const long long row0 = (it / p.heads) * p.S;
       mbar_wait(s_ready, n & 1);
       tc_fence_after();
+      // Both passes read S in 16-column chunks, double buffered: the tcgen05.ld of the next chunk is in flight while
+      // the current one is reduced / exponentiated; only the chunk that crosses S (197 of KP = 208 columns) is masked.
       float mx = -INFINITY;
-      for (int c = 0; c < p.KP; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tS + c, v);
-        tmem_wait_ld();
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld_32x32b_x16(tS, va);
+        for (int c = 0; c < p.KP; c += 32) {
+          const bool has_b = c + 16 < p.KP;
+          tmem_wait_ld();
+          if (has_b) tmem_ld_32x32b_x16(tS + c + 16, vb);
+          if (c + 16 <= p.S) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c + j < p.S) mx = fmaxf(mx, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(va[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c + j < p.S) mx = fmaxf(mx, __uint_as_float(va[j]));
+          }
+          if (has_b) {
+            tmem_wait_ld();
+            if (c + 32 < p.KP) tmem_ld_32x32b_x16(tS + c + 32, va);
+            if (c + 32 <= p.S) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(vb[j]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (c + 16 + j < p.S) mx = fmaxf(mx, __uint_as_float(vb[j]));
+            }
+          }
+        }
       }
       float sum = 0.f;
-      for (int c = 0; c < p.KP; c += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tS + c, v);
-        tmem_wait_ld();
-        uint32_t pk[8];
+      {
+        const float mxs = mx * p.scale_log2e;
+        auto expo = [&](const uint32_t* v, int c0) {  // 16 columns -> 8 packed bf16 pairs, stored in place
+          uint32_t pk[8];
+          const bool full = c0 + 16 <= p.S;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float e0 = (c + 2 * j < p.S) ? exp2f((__uint_as_float(v[2 * j]) - mx) * p.scale_log2e) : 0.f;
-          float e1 = (c + 2 * j + 1 < p.S) ? exp2f((__uint_as_float(v[2 * j + 1]) - mx) * p.scale_log2e) : 0.f;
-          __nv_bfloat162 b = __floats2bfloat162_rn(e0, e1);
-          // the probabilities enter P V as bf16: normalise with the sum of the rounded values
-          sum += __low2float(b) + __high2float(b);
-          pk[j] = *reinterpret_cast<uint32_t*>(&b);
+          for (int j = 0; j < 8; ++j) {
+            float e0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), p.scale_log2e, -mxs));
+            float e1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), p.scale_log2e, -mxs));
+            if (!full) {
+              if (c0 + 2 * j >= p.S) e0 = 0.f;
+              if (c0 + 2 * j + 1 >= p.S) e1 = 0.f;
+            }
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(e0, e1);
+            // the probabilities enter P V as bf16: normalise with the sum of the rounded values
+            sum += __low2float(b2) + __high2float(b2);
+            pk[j] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+          tmem_st_32x32b_x8(tS + (c0 >> 1), pk);  // in place: columns [c0/2, c0/2+8) were consumed in earlier chunks
+        };
+        uint32_t va[16], vb[16];
+        tmem_ld_32x32b_x16(tS, va);
+        for (int c = 0; c < p.KP; c += 32) {
+          const bool has_b = c + 16 < p.KP;
+          tmem_wait_ld();
+          if (has_b) tmem_ld_32x32b_x16(tS + c + 16, vb);
+          expo(va, c);
+          if (has_b) {
+            tmem_wait_ld();
+            if (c + 32 < p.KP) tmem_ld_32x32b_x16(tS + c + 32, va);
+            expo(vb, c + 16);
+          }
         }
-        tmem_st_32x32b_x8(tS + (c >> 1), pk);  // in place: columns [c/2, c/2+8) were consumed in earlier chunks
       }
       tmem_wait_st();
       tc_fence_before();

@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 extern void pvr_set_error(const char* fmt, ...);
@@ -218,8 +219,10 @@ __global__ void __launch_bounds__(256) lstm_cell_fwd_kernel(
   if (idx >= B * H) return;
   const int b = idx / H, j = idx - b * H;
   const long long g0 = (long long)b * 4 * H + j;
-  const float pi = G[g0] + XP[g0], pf = G[g0 + H] + XP[g0 + H], pg = G[g0 + 2 * H] + XP[g0 + 2 * H],
-              po = G[g0 + 3 * H] + XP[g0 + 3 * H];
+  float pi = G[g0], pf = G[g0 + H], pg = G[g0 + 2 * H], po = G[g0 + 3 * H];
+  if (XP) {  // (null when the recurrent GEMM accumulated straight into the input projection)
+    pi += XP[g0]; pf += XP[g0 + H]; pg += XP[g0 + 2 * H]; po += XP[g0 + 3 * H];
+  }
   const float i = sigmoidf_(pi), f = sigmoidf_(pf), g = tanhf(pg), o = sigmoidf_(po);
   const float c = f * (nd[b] * c_prev[idx]) + i * g;
   const float h = o * tanhf(c);
@@ -806,15 +809,21 @@ int lstm_forward_issue(const pvr_lstm_fwd* L, cudaStream_t st) {
   PVR_LAUNCH_CHECK("pvr_lstm_forward(mask)");
   pvr_gemm_desc d;
   memset(&d, 0, sizeof(d));
+  // The recurrent product is accumulated straight into the step's slice of the input projection (split-K slices,
+  // fp32 atomics): twice as many CTAs stream W_hh (one wave of 128 instead of 64), no g_tmp round trip, and the cell
+  // kernel reads one array instead of two. xp is consumed (overwritten) by the forward.
+  const bool in_place = (H / 64) % 2 == 0 && getenv("PVR_LSTM_NO_INPLACE") == nullptr;
   d.b = L->w_hh; d.ldb = H; d.out = L->g_tmp; d.ldo = 4 * H; d.lda = H;
-  d.m = B; d.n = 4 * H; d.n_pad = 4 * H; d.k = H; d.out_f32 = 1; d.split_k = 1;
+  d.m = B; d.n = 4 * H; d.n_pad = 4 * H; d.k = H; d.out_f32 = in_place ? 2 : 1; d.split_k = in_place ? 2 : 1;
   d.flags = PVR_GEMM_PDL;
   for (int t = 0; t < T; ++t) {
     d.a = hm + t * BH;
+    float* xp_t = const_cast<float*>(L->xp) + (long long)t * B * 4 * H;
+    if (in_place) d.out = xp_t;
     int rc = pvr_gemm(&d, st);
     if (rc != PVR_OK) return rc;
-    launch_pdl(lstm_cell_fwd_kernel, (int)((BH + 255) / 256), 256, st, L->g_tmp,
-               L->xp + (long long)t * B * 4 * H, L->c_all + t * BH, L->nd + (long long)t * B,
+    launch_pdl(lstm_cell_fwd_kernel, (int)((BH + 255) / 256), 256, st, in_place ? xp_t : L->g_tmp,
+               in_place ? (const float*)nullptr : (const float*)xp_t, L->c_all + t * BH, L->nd + (long long)t * B,
                t + 1 < T ? L->nd + (long long)(t + 1) * B : nullptr, B, H, L->gates + (long long)t * B * 4 * H,
                L->c_all + (t + 1) * BH, L->h_last, ho + t * BH, t + 1 < T ? hm + (t + 1) * BH : nullptr);
     PVR_LAUNCH_CHECK("pvr_lstm_forward(cell)");

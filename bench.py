@@ -350,8 +350,9 @@ def main():
     bc = None
     if not args.no_bc:
         bc_steps = max(10, args.steps)
-        v, ms_bc, last_loss = bench_bc(bc_steps, 3, world, dist, host_batches=False)
-        v_e2e, ms_bc_e2e, _ = bench_bc(bc_steps, 3, world, dist, host_batches=True)
+        # 6 warm-up steps: 3 eager ones, the CUDA-graph capture of the whole step, 2 replays
+        v, ms_bc, last_loss = bench_bc(bc_steps, 6, world, dist, host_batches=False)
+        v_e2e, ms_bc_e2e, _ = bench_bc(bc_steps, 6, world, dist, host_batches=True)
         bc = {"metric": "bc_train_steps_per_sec", "value": v, "unit": "steps/s", "ms_per_step": ms_bc,
               "scaling": "strong", "steps": bc_steps,
               "config": {"workload": "PolicyNet((2048,), 3, batch_norm=True) on pre-embedded observations "

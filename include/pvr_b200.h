@@ -285,6 +285,12 @@ int pvr_optim_sumsq(const float* const* grads, const int64_t* sizes, int count, 
 int pvr_optim_step(int mode, float* const* params, float* const* grads, float* const* state1, float* const* state2,
                    const int64_t* sizes, int count, const double* sumsq, float grad_scale, float max_norm, float lr,
                    float alpha_or_beta1, float beta2, float eps, int step, float* norm_out, void* stream);
+/* Same (RMSprop only) with the learning rate read from device memory, so that a whole training step — including the
+ * LambdaLR schedule of main_bc_2.py:90 — can be replayed from a CUDA graph. */
+int pvr_optim_step_dev(int mode, float* const* params, float* const* grads, float* const* state1, float* const* state2,
+                       const int64_t* sizes, int count, const double* sumsq, float grad_scale, float max_norm,
+                       const float* lr_dev, float alpha_or_beta1, float beta2, float eps, int step, float* norm_out,
+                       void* stream);
 
 #ifdef __cplusplus
 }

@@ -100,6 +100,9 @@ _SIGNATURES = {
     "pvr_optim_step": (ctypes.c_int, [_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                                       ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _f, _f, _f, _f, _f, _f, _i,
                                       _vp, _vp]),
+    "pvr_optim_step_dev": (ctypes.c_int, [_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                                          ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _f, _f, _vp, _f, _f, _f, _i,
+                                          _vp, _vp]),
     "pvr_gemm_bf16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -465,8 +465,10 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const TensorList tl, double*
 __global__ void __launch_bounds__(256) optim_step_kernel(const TensorList tl, const double* __restrict__ sumsq,
                                                           float grad_scale, float max_norm, int mode, float lr,
                                                           float alpha_or_beta1, float beta2, float eps, float bc1,
-                                                          float bc2, float* __restrict__ norm_out) {
+                                                          float bc2, float* __restrict__ norm_out,
+                                                          const float* __restrict__ lr_dev) {
   const int t = blockIdx.y;
+  if (lr_dev) lr = __ldg(lr_dev);  // learning rate in device memory: the step can live inside a CUDA graph
   const double norm = sqrt(sumsq[0]) * (double)grad_scale;
   float coef = 1.f;
   if (max_norm > 0.f) coef = fminf(1.f, max_norm / ((float)norm + 1e-6f));
@@ -741,7 +743,7 @@ extern "C" int pvr_optim_sumsq(const float* const* grads, const int64_t* sizes, 
   return PVR_OK;
 }
 
-extern "C" int pvr_optim_step(int mode, float* const* params, float* const* grads, float* const* state1,
+static int optim_step_impl(const float* lr_dev, int mode, float* const* params, float* const* grads, float* const* state1,
                               float* const* state2, const int64_t* sizes, int count, const double* sumsq,
                               float grad_scale, float max_norm, float lr, float alpha_or_beta1, float beta2, float eps,
                               int step, float* norm_out, void* stream_) {
@@ -765,9 +767,29 @@ extern "C" int pvr_optim_step(int mode, float* const* params, float* const* grad
     bc2 = 1.f - powf(beta2, (float)step);
   }
   optim_step_kernel<<<dim3(148, count), 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      tl, sumsq, grad_scale, max_norm, mode, lr, alpha_or_beta1, beta2, eps, bc1, bc2, norm_out);
+      tl, sumsq, grad_scale, max_norm, mode, lr, alpha_or_beta1, beta2, eps, bc1, bc2, norm_out, lr_dev);
   PVR_LAUNCH_CHECK("pvr_optim_step");
   return PVR_OK;
+}
+
+extern "C" int pvr_optim_step(int mode, float* const* params, float* const* grads, float* const* state1,
+                              float* const* state2, const int64_t* sizes, int count, const double* sumsq,
+                              float grad_scale, float max_norm, float lr, float alpha_or_beta1, float beta2, float eps,
+                              int step, float* norm_out, void* stream_) {
+  return optim_step_impl(nullptr, mode, params, grads, state1, state2, sizes, count, sumsq, grad_scale, max_norm, lr,
+                         alpha_or_beta1, beta2, eps, step, norm_out, stream_);
+}
+
+extern "C" int pvr_optim_step_dev(int mode, float* const* params, float* const* grads, float* const* state1,
+                                  float* const* state2, const int64_t* sizes, int count, const double* sumsq,
+                                  float grad_scale, float max_norm, const float* lr_dev, float alpha_or_beta1,
+                                  float beta2, float eps, int step, float* norm_out, void* stream_) {
+  if (!lr_dev || mode != PVR_OPT_RMSPROP) {
+    pvr_set_error("pvr_optim_step_dev: needs a device learning rate and RMSprop (Adam's bias correction is host state)");
+    return PVR_ERR_ARG;
+  }
+  return optim_step_impl(lr_dev, mode, params, grads, state1, state2, sizes, count, sumsq, grad_scale, max_norm, 0.f,
+                         alpha_or_beta1, beta2, eps, step, norm_out, stream_);
 }
 
 // ---------------------------------------------------------------------------------------------- LSTM time loops

@@ -30,7 +30,9 @@ class _FusedBase(torch.optim.Optimizer):
         return self._norm
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, lr_tensor=None):
+        """lr_tensor: optional 1-element float32 CUDA tensor holding the learning rate (RMSprop only); the update then
+        takes no host scalars that change from step to step and can be captured in a CUDA graph."""
         assert closure is None
         lib = _lib.lib()
         for group in self.param_groups:
@@ -64,9 +66,15 @@ class _FusedBase(torch.optim.Optimizer):
                 sizes = I64(*[p.numel() for p in ps])
                 _lib.check(lib.pvr_optim_sumsq(grads, sizes, n, self._sumsq.data_ptr(), stream), "pvr_optim_sumsq")
                 h = self._hyper(group)
-                _lib.check(lib.pvr_optim_step(self.mode, params, grads, st1, st2, sizes, n, self._sumsq.data_ptr(), 1.0,
-                                              float(self.max_grad_norm or 0.0), float(group["lr"]), h[0], h[1], h[2],
-                                              step, self._norm.data_ptr(), stream), "pvr_optim_step")
+                if lr_tensor is not None:
+                    _lib.check(lib.pvr_optim_step_dev(self.mode, params, grads, st1, st2, sizes, n,
+                                                      self._sumsq.data_ptr(), 1.0, float(self.max_grad_norm or 0.0),
+                                                      lr_tensor.data_ptr(), h[0], h[1], h[2], step,
+                                                      self._norm.data_ptr(), stream), "pvr_optim_step_dev")
+                else:
+                    _lib.check(lib.pvr_optim_step(self.mode, params, grads, st1, st2, sizes, n, self._sumsq.data_ptr(),
+                                                  1.0, float(self.max_grad_norm or 0.0), float(group["lr"]), h[0], h[1],
+                                                  h[2], step, self._norm.data_ptr(), stream), "pvr_optim_step")
         return None
 
 

@@ -17,7 +17,7 @@ torch.manual_seed(1)
 random.seed(1)
 net = PolicyNet((2048,), 3, batch_norm=True).cuda().train()
 tr = BCTrainer(net, obs, action, done, 128, 64, 10 ** 9)
-for _ in range(2):
+for _ in range(6):  # eager warm-up, graph capture, first replays
     tr.step()
 torch.cuda.synchronize()
 t0 = time.perf_counter()

@@ -101,8 +101,9 @@ __global__ void __launch_bounds__(256) vit_layernorm_kernel(const float* __restr
 //   P = softmax    one thread per query row reads its TMEM lane (row max / sum are thread-local) and writes the
 //                  probabilities back INTO TMEM as packed bf16 (tcgen05.st), over the scores it has consumed
 //   O = P V        tcgen05.mma with the A operand in TMEM; V (KP x 64, straight from TMA) is the MN-major B operand
-// Warps 0-3 / 4-7 own query tile 0 / 1; warp 8 is the controller (TMA prefetch of the next item into the second
-// smem stage, MMA issue). Keys beyond the sequence get p = 0; query rows beyond it are computed but never stored.
+// Warps 0-3 / 4-7 are two softmax groups, each owning one 256-column TMEM buffer; query tiles alternate between them
+// and are pipelined individually (see the controller); warp 8 is the controller (TMA prefetch two items ahead, MMA
+// issue). Keys beyond the sequence get p = 0; query rows beyond it are computed but never stored.
 // TMEM columns per tile (base 0 / 256): S [0, KP), P [0, KP/2) in place, O [128, 192).
 struct AttnParams {
   int n_img, S, W, heads, KP, mtiles;
@@ -123,11 +124,11 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
   uint64_t* kv_full = bars;        // [2]
   uint64_t* kv_empty = bars + 2;   // [2]
-  uint64_t* s_ready = bars + 4;
-  uint64_t* p_ready = bars + 5;
-  uint64_t* o_ready = bars + 6;
-  uint64_t* tmem_free = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_ready = bars + 4;     // [2] one per TMEM buffer (256 columns each)
+  uint64_t* p_ready = bars + 6;     // [2]
+  uint64_t* o_ready = bars + 8;     // [2]
+  uint64_t* tmem_free = bars + 10;  // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -137,10 +138,12 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    mbar_init(s_ready, 1);
-    mbar_init(p_ready, 128 * p.mtiles);
-    mbar_init(o_ready, 1);
-    mbar_init(tmem_free, 128 * p.mtiles);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_ready[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_ready[i], 1);
+      mbar_init(&tmem_free[i], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 8) {
@@ -170,56 +173,73 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       tma_load_2d(&tmap_kv, &kv_full[st], base + 32768, p.W + head * 64, row0);
       tma_load_2d(&tmap_kv, &kv_full[st], base + 32768 + kv_alloc, 2 * p.W + head * 64, row0);
     };
-    uint32_t n = 0;
-    if ((long long)blockIdx.x < items) {
-      if (elect_one()) issue_loads(blockIdx.x, 0);
+    // Query tiles are pipelined individually: tile tt (item tt / mtiles, m-tile tt % mtiles) uses TMEM buffer tt & 1
+    // and softmax group tt & 1. Per iteration the controller issues S(tt) as soon as that buffer is free and P V of
+    // tile tt - 1 as soon as its probabilities are written, so one group's MMAs / epilogue overlap the other group's
+    // softmax instead of all warps marching through S -> softmax -> PV -> output in lock step.
+    const int mtl = p.mtiles;
+    const long long my_items = (long long)blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_tiles = my_items * mtl;
+    auto item_of = [&](long long n) { return (long long)blockIdx.x + n * gridDim.x; };
+    for (int i = 0; i < 2 && i < my_items; ++i) {
+      if (elect_one()) issue_loads(item_of(i), i);
       __syncwarp();
     }
-    for (long long it = blockIdx.x; it < items; it += gridDim.x, ++n) {
-      const int st = n & 1;
-      const long long nxt = it + gridDim.x;
-      if (nxt < items) {  // prefetch the next item into the other stage once its previous user has drained it
-        if (n >= 1) mbar_wait(&kv_empty[st ^ 1], ((n - 1) >> 1) & 1);
-        if (elect_one()) issue_loads(nxt, st ^ 1);
-        __syncwarp();
-      }
-      mbar_wait(&kv_full[st], (n >> 1) & 1);
-      if (n >= 1) mbar_wait(tmem_free, (n - 1) & 1);  // epilogue of the previous item has read O
-      tc_fence_after();
-      const uint32_t sQ = smem_u32(smem + st * stage_bytes);
-      const uint64_t q_desc = umma_desc_sw128(sQ), k_desc = umma_desc_sw128(sQ + 32768),
-                     v_desc = umma_desc_sw128(sQ + 32768 + kv_alloc);
-      if (elect_one()) {
-        for (int mt = 0; mt < p.mtiles; ++mt)
+    for (long long tt = 0; tt <= total_tiles; ++tt) {
+      if (tt < total_tiles) {
+        const long long n = tt / mtl;
+        const int j = (int)(tt - n * mtl), st = (int)(n & 1), b = (int)(tt & 1);
+        const long long u = tt >> 1;
+        if (j == 0) mbar_wait(&kv_full[st], (uint32_t)((n >> 1) & 1));
+        if (u >= 1) mbar_wait(&tmem_free[b], (uint32_t)((u - 1) & 1));  // tile tt - 2 has left this buffer
+        tc_fence_after();
+        const uint32_t sQ = smem_u32(smem + st * stage_bytes);
+        const uint64_t q_desc = umma_desc_sw128(sQ + j * 16384), k_desc = umma_desc_sw128(sQ + 32768);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + mt * 256, q_desc + ((mt * 16384 + k * 32) >> 4), k_desc + ((k * 32) >> 4), idesc_s,
-                      k != 0);
-        umma_commit(s_ready);
+            umma_bf16(tmem_base + b * 256, q_desc + ((k * 32) >> 4), k_desc + ((k * 32) >> 4), idesc_s, k != 0);
+          umma_commit(&s_ready[b]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
-      mbar_wait(p_ready, n & 1);
-      tc_fence_after();
-      if (elect_one()) {
-        for (int mt = 0; mt < p.mtiles; ++mt)
+      if (tt >= 1) {
+        const long long pt = tt - 1, pn = pt / mtl;
+        const int pj = (int)(pt - pn * mtl), pst = (int)(pn & 1), pb = (int)(pt & 1);
+        mbar_wait(&p_ready[pb], (uint32_t)((pt >> 1) & 1));
+        tc_fence_after();
+        const uint64_t v_desc = umma_desc_sw128(smem_u32(smem + pst * stage_bytes) + 32768 + kv_alloc);
+        if (elect_one()) {
           for (int ks = 0; ks < p.KP / 16; ++ks)
-            umma_bf16_ts(tmem_base + mt * 256 + 128, tmem_base + mt * 256 + ks * 8, v_desc + ((ks * 2048) >> 4),
-                         idesc_o, ks != 0);
-        umma_commit(o_ready);
-        umma_commit(&kv_empty[st]);
+            umma_bf16_ts(tmem_base + pb * 256 + 128, tmem_base + pb * 256 + ks * 8, v_desc + ((ks * 2048) >> 4), idesc_o,
+                         ks != 0);
+          umma_commit(&o_ready[pb]);
+          if (pj == mtl - 1) umma_commit(&kv_empty[pst]);
+        }
+        __syncwarp();
+        if (pj == mtl - 1 && pn + 2 < my_items) {  // the stage of item pn is free once its MMAs have completed
+          mbar_wait(&kv_empty[pst], (uint32_t)((pn >> 1) & 1));
+          if (elect_one()) issue_loads(item_of(pn + 2), pst);
+          __syncwarp();
+        }
       }
-      __syncwarp();
     }
-  } else if (warp < 4 * p.mtiles) {
+  } else if (warp < 8) {
     // ===================================================== softmax + output (one thread per query row)
-    const int mt = warp >> 2;
+    const int g = warp >> 2;  // group = TMEM buffer
     const int row = (warp & 3) * 32 + lane;
-    const uint32_t tS = tmem_base + mt * 256 + ((uint32_t)((warp & 3) * 32) << 16);
-    uint32_t n = 0;
-    for (long long it = blockIdx.x; it < items; it += gridDim.x, ++n) {
+    const uint32_t tS = tmem_base + g * 256 + ((uint32_t)((warp & 3) * 32) << 16);
+    const int mtl = p.mtiles;
+    const long long my_items = (long long)blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_tiles = my_items * mtl;
+    for (long long tt = g; tt < total_tiles; tt += 2) {
+      const long long nn = tt / mtl;
+      const int mt = (int)(tt - nn * mtl);
+      const uint32_t n = (uint32_t)(tt >> 1);  // use count of this buffer
+      const long long it = (long long)blockIdx.x + nn * gridDim.x;
       const int head = (int)(it % p.heads);
       const long long row0 = (it / p.heads) * p.S;
-      mbar_wait(s_ready, n & 1);
+      mbar_wait(&s_ready[g], n & 1);
       tc_fence_after();
       // Both passes read S in 16-column chunks, double buffered: the tcgen05.ld of the next chunk is in flight while
       // the current one is reduced / exponentiated; only the chunk that crosses S (197 of KP = 208 columns) is masked.
@@ -290,15 +310,15 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(p_ready);
-      mbar_wait(o_ready, n & 1);
+      mbar_arrive(&p_ready[g]);
+      mbar_wait(&o_ready[g], n & 1);
       tc_fence_after();
       uint32_t o[64];
       tmem_ld_32x32b_x32(tS + 128, o);
       tmem_ld_32x32b_x32(tS + 160, o + 32);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(tmem_free);
+      mbar_arrive(&tmem_free[g]);
       const int tok = mt * 128 + row;
       if (tok < p.S) {
         const float inv = 1.f / sum;

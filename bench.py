@@ -433,7 +433,10 @@ def resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks,
         "preprocess": {"bound": "hbm", "ms_per_step": pre_ms, "achieved": pre_bytes / (pre_ms / 1e3) / 1e9,
                        "peak": peaks["hbm_gbs"], "unit": "GB/s",
                        "frac": pre_bytes / (pre_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
-                       "algorithmic_bytes_per_frame": 224 * 224 * 3 + 224 * 112 * 64},
+                       "algorithmic_bytes_per_frame": 224 * 224 * 3 + 224 * 112 * 64,
+                       # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 256 frames
+                       # (profiles/r01_ncu_full_preprocess.txt: 34 MB + 446 MB), scaled to this launch
+                       "traffic": int((34.0e6 + 446.0e6) / 256 * frames_per_step)},
     }
     return roofline, 1 + int(enc.lib.pvr_encoder_launch_count(enc.handle))
 

@@ -158,6 +158,10 @@ typedef struct pvr_gemm_desc {
                          the previous kernel of the stream; it waits for that kernel before touching a / res / out) */
 } pvr_gemm_desc;
 #define PVR_GEMM_PDL 1
+/* Operands given transposed: a is a row-major (k, m) matrix (row pitch lda), b a row-major (k, n_pad) matrix; the result
+ * is still out (m, n) = a^T b. fp32 output (out_f32 == 1), no split-K, no residual; k is arbitrary (rows beyond it read
+ * as zero). This is dW = dY^T X of nn.Linear with dY, X as the (rows, features) activations: no transposed copies. */
+#define PVR_GEMM_MN 2
 int pvr_gemm(const pvr_gemm_desc* d, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

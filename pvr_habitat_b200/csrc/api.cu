@@ -587,8 +587,13 @@ const float* unit_vector(bool ones) {
 }  // namespace
 
 extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
+  const bool mn = d && (d->flags & PVR_GEMM_MN);
+  if (mn && (d->out_f32 != 1 || d->res || d->split_k > 1 || d->n_pad % 64 || d->n % 32)) {
+    pvr_set_error("pvr_gemm: PVR_GEMM_MN needs fp32 output, no residual, no split-K, n_pad %% 64 == 0");
+    return PVR_ERR_ARG;
+  }
   if (!d || !d->a || !d->b || !d->out || d->m <= 0 || d->n <= 0 || d->n > d->n_pad || d->n_pad % 32 || d->k <= 0 ||
-      d->k % 64 || d->lda % 8 || d->ldb % 8 || (d->res && !d->out_f32 && d->ldr % 8) || d->n_pad > 16384 || d->out_f32 < 0 ||
+      (!mn && d->k % 64) || d->lda % 8 || d->ldb % 8 || (d->res && !d->out_f32 && d->ldr % 8) || d->n_pad > 16384 || d->out_f32 < 0 ||
       d->out_f32 > 2 || (d->out_f32 ? d->ldo % 4 : d->ldo % 8)) {
     pvr_set_error("pvr_gemm: invalid argument");
     return PVR_ERR_ARG;
@@ -618,7 +623,7 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   static const int pair_f32 = getenv("PVR_PAIR_F32") ? atoi(getenv("PVR_PAIR_F32")) : 1;
   const bool pair_bf16 = d->out_f32 == 0 && !d->res && d->n % 64 == 0 && d->k >= 512;
   const bool pair_fp32 = pair_f32 && d->out_f32 == 1 && d->n % 32 == 0 && d->k >= 768;  // ViT proj / fc2 (+ residual)
-  if (pair_ok && (pair_bf16 || pair_fp32) && split_k == 1 && d->n_pad % 256 == 0 &&
+  if (pair_ok && !mn && (pair_bf16 || pair_fp32) && split_k == 1 && d->n_pad % 256 == 0 &&
       ((long long)(d->m + 255) / 256) * (d->n_pad / 256) >= sms / 2) {
     p.cta2 = 1;
     p.num_m_tiles = (d->m + 255) / 256;
@@ -626,7 +631,8 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   }
   p.num_n_tiles = d->n_pad / block_n;
   p.split_k = split_k;
-  p.num_k_chunks = d->k / 64 / split_k;
+  p.num_k_chunks = mn ? (d->k + 63) / 64 : d->k / 64 / split_k;
+  p.mn = mn ? 1 : 0;
   p.n_valid = d->n;
   p.relu_n = (d->relu || d->act == 1) ? d->n : 0;
   p.ldo = d->ldo;
@@ -641,9 +647,13 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   p.bias = bias;
   CUtensorMap ta, tb, to, tr;
   const char* err = "";
-  if (!pvr::make_tmap_2d(&ta, d->a, (uint64_t)d->k, (uint64_t)d->m, (uint64_t)d->lda, 128, &err) ||
-      !pvr::make_tmap_2d(&tb, d->b, (uint64_t)d->k, (uint64_t)d->n_pad, (uint64_t)d->ldb,
-                         (uint32_t)(p.cta2 ? block_n / 2 : block_n), &err)) {
+  const bool maps_ok =
+      mn ? (pvr::make_tmap_2d(&ta, d->a, (uint64_t)d->m, (uint64_t)d->k, (uint64_t)d->lda, 64, &err) &&
+            pvr::make_tmap_2d(&tb, d->b, (uint64_t)d->n_pad, (uint64_t)d->k, (uint64_t)d->ldb, 64, &err))
+         : (pvr::make_tmap_2d(&ta, d->a, (uint64_t)d->k, (uint64_t)d->m, (uint64_t)d->lda, 128, &err) &&
+            pvr::make_tmap_2d(&tb, d->b, (uint64_t)d->k, (uint64_t)d->n_pad, (uint64_t)d->ldb,
+                              (uint32_t)(p.cta2 ? block_n / 2 : block_n), &err));
+  if (!maps_ok) {
     pvr_set_error("pvr_gemm: %s", err);
     return PVR_ERR_CUDA;
   }

@@ -129,13 +129,17 @@ __device__ __forceinline__ void tile_coords(const ConvGemmParams& p, int tile, i
   }
 }
 
-template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32, bool CTA2 = false>
+// MN: both operands are given "transposed" — A as a row-major (K, M) matrix, W as (K, N) — and enter the tensor core as
+// MN-major operands (idesc bits 15 / 16): out = A^T W. Used for the weight gradients dW = dY^T X of the policy, whose
+// operands are the (rows, features) activations as they sit in memory; no transposed copies are made.
+template <int BLOCK_N, int A_MODE, bool EPI_TMA, bool OUT_F32, bool CTA2 = false, bool MN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                  const __grid_constant__ CUtensorMap tmap_a2, const ConvGemmParams p) {
   using C = Cfg<BLOCK_N, EPI_TMA, CTA2>;
   static_assert(!CTA2 || (EPI_TMA && (A_MODE == A_TILED || A_MODE == A_IM2COL64)), "pair kernel: TMA epilogue only");
+  static_assert(!MN || (A_MODE == A_TILED && !CTA2 && BLOCK_N >= 64), "MN-major operands: plain GEMM, single CTA");
   constexpr int STAGES = C::STAGES;
   constexpr int NB = C::NB > 0 ? C::NB : 1;
   constexpr int EPI_COLS = OUT_F32 ? 32 : EPI_N;  // columns of one 128-byte staging row (fp32 / bf16 output)
@@ -258,6 +262,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               tma_load_im2col_4d_pair(&tmap_a, &full_bar[stage], a_dst, cc * BLOCK_K, w0, h0, img, (uint16_t)tap_s,
                                       (uint16_t)tap_r);
             }
+          } else if (MN) {
+            // boxes of 64 MN elements x 64 K rows from the row-major (K, MN) matrices
+            mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i)
+              tma_load_2d(&tmap_b, &full_bar[stage], sB + stage * C::B_STAGE_BYTES + i * 8192, n0 + 64 * i, kc * BLOCK_K);
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              tma_load_2d(&tmap_a, &full_bar[stage], a_dst + i * 8192, m0 + 64 * i, kc * BLOCK_K);
           } else {
           mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
           tma_load_2d(&tmap_b, &full_bar[stage], sB + stage * C::B_STAGE_BYTES, kc * BLOCK_K, n0);
@@ -308,12 +321,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================================================== MMA issuer: the whole warp walks the loops (loop state in
     // uniform registers), one elected lane issues. Descriptors are built once; stages and K-steps only add to the
     // 14-bit (address >> 4) field — 4 SASS instructions per tcgen05.mma instead of 17 behind a `lane == 0` branch.
-    constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = umma_idesc_bf16(CTA2 ? 2 * BLOCK_M : BLOCK_M, BLOCK_N) | (MN ? (3u << 15) : 0u);
     if (!CTA2 || cta_rank == 0) {  // pair: only the leader CTA issues (for both)
-    const uint64_t a_desc0 = (A_MODE == A_IM2COL8)    ? umma_desc_nosw(smem_u32(sA), 2048, 128)
+    const uint64_t a_desc0 = MN ? umma_desc_sw128_mn(smem_u32(sA), 8192) : (A_MODE == A_IM2COL8)    ? umma_desc_nosw(smem_u32(sA), 2048, 128)
                              : (A_MODE == A_IM2COL32) ? umma_desc_sw64(smem_u32(sA))
                                                       : umma_desc_sw128(smem_u32(sA));
-    const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB));
+    const uint64_t b_desc0 = MN ? umma_desc_sw128_mn(smem_u32(sB), 8192) : umma_desc_sw128(smem_u32(sB));
     uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
     for (int tile = wid; tile < num_tiles; tile += wstride) {
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -327,10 +340,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t b_desc = b_desc0 + (uint64_t)(stage * (C::B_STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint32_t a_off = (A_MODE == A_IM2COL8)    ? k * 4096
+            const uint32_t a_off = MN                       ? k * 2048
+                                   : (A_MODE == A_IM2COL8)  ? k * 4096
                                    : (A_MODE == A_IM2COL32) ? (k >> 1) * 8192 + (k & 1) * (UMMA_K * 2)
                                                             : k * (UMMA_K * 2);
-            if (CTA2)
+            if (MN)
+              umma_bf16(d_tmem, a_desc + (a_off >> 4), b_desc + ((k * 2048) >> 4), idesc, (kc | k) != 0);
+            else if (CTA2)
               umma_bf16_pair(d_tmem, a_desc + (a_off >> 4), b_desc + ((k * UMMA_K * 2) >> 4), idesc, (kc | k) != 0);
             else
               umma_bf16(d_tmem, a_desc + (a_off >> 4), b_desc + ((k * UMMA_K * 2) >> 4), idesc,
@@ -630,6 +646,31 @@ cudaError_t launch_one(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, ta2, p);
 }
 
+template <int BLOCK_N>
+cudaError_t launch_mn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                      const CUtensorMap& ta2, const ConvGemmParams& p, int num_sms, cudaStream_t stream) {
+  auto kern = conv_gemm_kernel<BLOCK_N, A_TILED, true, true, false, true>;
+  using C = Cfg<BLOCK_N, true>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles < num_sms ? tiles : num_sms);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = p.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, ta2, p);
+}
+
 // CTA-pair variant (256 x BLOCK_N tiles, cluster of 2, tcgen05 cta_group::2), bf16 output through the TMA epilogue.
 template <int BLOCK_N, int A_MODE, bool OUT_F32 = false>
 cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
@@ -687,6 +728,15 @@ cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtens
   p.n_tiles_shift = -1;
   for (int s = 0; s < 16; ++s)
     if ((1 << s) == p.num_n_tiles) p.n_tiles_shift = s;
+  if (p.mn) {
+    if (!epi_tma || !p.out_is_f32 || p.split_k != 1 || a_mode != A_TILED || p.cta2) return cudaErrorInvalidValue;
+    switch (block_n) {
+      case 64: return launch_mn<64>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+      case 128: return launch_mn<128>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+      case 256: return launch_mn<256>(tmap_a, tmap_b, tmap_out, tmap_res, ta2, p, num_sms, stream);
+      default: return cudaErrorInvalidValue;
+    }
+  }
   if (p.cta2) {
     if (!epi_tma || p.split_k != 1) return cudaErrorInvalidValue;
     if (p.out_is_f32) {  // fp32 output / fp32 residual stream (ViT proj, fc2)

@@ -39,6 +39,7 @@ struct ConvGemmParams {
   int kc_split;      // > 0: K chunks >= kc_split come from a second input (tmap_a2), A_TILED only: projection shortcut
   int a2_im2col;     // second input is read with im2col-mode 1x1 taps at stride a2_stride (else a plain 2-D matrix)
   int a2_stride;
+  int mn;            // 1: MN-major operands (A is (K, M), W is (K, N) row-major): out = A^T W, fp32 output
   int cta2;          // 1: CTA-pair kernel (cta_group::2): num_m_tiles counts 256-row tiles, W map box = BLOCK_N / 2 rows
   int split_k;       // >= 1; K is cut into split_k slices of num_k_chunks chunks, each its own tile (fp32 atomics)
   int out_is_f32;    // fp32 output: TMA-staged (tmap_out is an fp32 map) or, with !epi_tma, atomically accumulated

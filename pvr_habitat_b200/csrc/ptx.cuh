@@ -323,6 +323,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// MN-major, 128-byte swizzle: the tile is stored as 64 K rows of 128 B (64 consecutive M / N elements) per 64-wide
+// MN block — what a TMA box (64 MN x 64 K) of a row-major (K, MN) matrix produces. SBO = 1024 B between 8-row K
+// groups, LBO = distance between consecutive 64-element MN blocks (one box = 8192 B). A K = 16 step advances 2048 B.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // K-major, 64-byte swizzle: rows are 64 B (32 bf16) apart, 8-row groups SBO = 512 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) |

@@ -39,16 +39,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def gemm(a, b, out, m, n, k, bias=None, relu=False, res=None, res_mode=0, out_f32=0, split_k=1, n_pad=None, act=0):
-    """out (m x n) = epilogue(a (m x k) @ b (n x k)^T); a, b bf16 row-major with K contiguous."""
+def gemm(a, b, out, m, n, k, bias=None, relu=False, res=None, res_mode=0, out_f32=0, split_k=1, n_pad=None, act=0,
+         mn=False):
+    """out (m x n) = epilogue(a (m x k) @ b (n x k)^T); a, b bf16 row-major with K contiguous.
+    mn=True: a is (k x m), b is (k x n) row-major (MN-major operands): out = a^T b, fp32."""
     d = pvr_gemm_desc()
+    d.flags = _lib.PVR_GEMM_MN if mn else 0
     d.a, d.lda = a.data_ptr(), a.stride(0)
     d.b, d.ldb = b.data_ptr(), b.stride(0)
     d.out, d.ldo = out.data_ptr(), out.stride(0)
     d.scale = None
     d.bias = bias.data_ptr() if bias is not None else None
     d.res, d.ldr = (res.data_ptr(), res.stride(0)) if res is not None else (None, 0)
-    d.m, d.n, d.n_pad, d.k = m, n, n_pad if n_pad is not None else b.shape[0], k
+    d.m, d.n, d.n_pad, d.k = m, n, n_pad if n_pad is not None else (b.shape[1] if mn else b.shape[0]), k
     d.relu, d.res_mode, d.out_f32, d.split_k, d.act = int(relu), res_mode, out_f32, split_k, act
     _lib.check(_lib.lib().pvr_gemm(ctypes.byref(d), _stream()), "pvr_gemm")
 
@@ -81,10 +84,7 @@ class _Workspace:
         self.dh_rec, self.dc_rec = z(B, H), z(B, H)
         self.dZ2, self.dZ1 = z(M, H, dtype=bf), z(M, H, dtype=bf)
         self.dX0 = z(M, Dp, dtype=bf) if batch_norm else None
-        # transposed operands for the weight-gradient GEMMs (batch dimension padded to 64 with zeros)
-        self.dGT = z(4 * H, Mp, dtype=bf)
-        self.actT = z(max(H, Dp), Mp, dtype=bf)
-        self.dZT = z(H, Mp, dtype=bf)
+        # (the weight-gradient GEMMs read dY / X as MN-major operands: no transposed copies, see gemm(mn=True))
         self.dW1p = z(H, Dp) if Dp != D else None
 
 
@@ -284,10 +284,6 @@ class PolicyNet(nn.Module):
         names = ["W1", "b1", "W2", "b2", "Wih0", "Whh0", "bih0", "bhh0", "Wih1", "Whh1", "bih1", "bhh1", "Wp", "bp"]
         g.update(zip(names, grads[2 if self.batch_norm else 0:]))
 
-        def transpose(src, rows, cols, dst):
-            _lib.check(lib.pvr_transpose_bf16(src.data_ptr(), src.stride(0), rows, cols, dst.data_ptr(),
-                                              dst.stride(0), _stream()), "pvr_transpose_bf16")
-
         def colsum(src, n, out):
             _lib.check(lib.pvr_colsum_bf16(src.data_ptr(), src.stride(0), M, n, out.data_ptr(), _stream()),
                        "pvr_colsum_bf16")
@@ -308,27 +304,21 @@ class PolicyNet(nn.Module):
             dG = ws.dG[l]
             colsum(dG, 4 * H, g[f"bih{l}"])
             g[f"bhh{l}"].copy_(g[f"bih{l}"])
-            transpose(dG, M, 4 * H, ws.dGT)
-            transpose(ws.hm[l], M, H, ws.actT)
-            gemm(ws.dGT, ws.actT, g[f"Whh{l}"], 4 * H, H, Mp, out_f32=1, n_pad=H)
-            transpose(below[l], M, H, ws.actT)
-            gemm(ws.dGT, ws.actT, g[f"Wih{l}"], 4 * H, H, Mp, out_f32=1, n_pad=H)
+            # dW = dG^T X with dG (M, 4H) and X (M, H) as they sit in memory: MN-major tensor-core operands
+            gemm(dG, ws.hm[l], g[f"Whh{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)
+            gemm(dG, below[l], g[f"Wih{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)
             if l == 1:   # gradient w.r.t. layer-0 outputs (fp32, consumed by the layer-0 cell backward)
                 gemm(dG, w["WihT"][1], ws.dHL[0], M, H, 4 * H, out_f32=1)
             else:        # through ReLU of fc2: dZ2 = (dG0 W_ih0) * (H2 > 0)
                 gemm(dG, w["WihT"][0], ws.dZ2, M, H, 4 * H, res=ws.H2, res_mode=1)
         colsum(ws.dZ2, H, g["b2"])
-        transpose(ws.dZ2, M, H, ws.dZT)
-        transpose(ws.H1, M, H, ws.actT)
-        gemm(ws.dZT, ws.actT, g["W2"], H, H, Mp, out_f32=1, n_pad=H)
+        gemm(ws.dZ2, ws.H1, g["W2"], H, H, M, out_f32=1, n_pad=H, mn=True)
         gemm(ws.dZ2, w["W2T"], ws.dZ1, M, H, H, res=ws.H1, res_mode=1)
         colsum(ws.dZ1, H, g["b1"])
-        transpose(ws.dZ1, M, H, ws.dZT)
-        transpose(ws.X0, M, Dp, ws.actT)
         if Dp == D:
-            gemm(ws.dZT, ws.actT, g["W1"], H, D, Mp, out_f32=1, n_pad=Dp)
+            gemm(ws.dZ1, ws.X0, g["W1"], H, D, M, out_f32=1, n_pad=Dp, mn=True)
         else:
-            gemm(ws.dZT, ws.actT, ws.dW1p, H, Dp, Mp, out_f32=1, n_pad=Dp)
+            gemm(ws.dZ1, ws.X0, ws.dW1p, H, Dp, M, out_f32=1, n_pad=Dp, mn=True)
             g["W1"].copy_(ws.dW1p[:, :D])
         dx = None
         if self.batch_norm or need_dx:

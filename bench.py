@@ -93,15 +93,26 @@ class ClockSampler:
 
 
 def make_observations(n, n_frames, seed):
-    """Structured synthetic frames (not iid noise), tiled from a small seeded set to bound generation time."""
-    from oracle import restate  # synthetic-input generator only (inputs, not the measured path)
-    base = restate.structured_frames(16, 224, 224, 3 * n_frames, seed)
+    """Structured synthetic uint8 frames (smooth gradients + blocks + noise, not iid noise), tiled from a small seeded
+    set to bound generation time. Generated here: the GPU arm never imports oracle/."""
+    rng = np.random.default_rng(seed)
+    c = 3 * n_frames
+    yy, xx = np.meshgrid(np.arange(224, dtype=np.float32), np.arange(224, dtype=np.float32), indexing="ij")
+    base = np.empty((16, 224, 224, c), dtype=np.uint8)
+    for i in range(16):
+        for ch in range(c):
+            fx, fy, ph = rng.uniform(0.01, 0.08, 3)
+            img = 110 + 70 * np.sin(fx * xx + 3 * ph) * np.cos(fy * yy + ph) + rng.normal(0, 12, (224, 224))
+            y0, x0 = rng.integers(0, 160, 2)
+            img[y0:y0 + 48, x0:x0 + 64] += rng.uniform(-60, 60)
+            base[i, :, :, ch] = np.clip(img, 0, 255).astype(np.uint8)
     reps = (n + 15) // 16
     obs = np.concatenate([np.roll(base, shift=7 * r, axis=2) for r in range(reps)])[:n]
     return np.ascontiguousarray(obs)
 
 
 def oracle_parts(name, seed=1):
+    """Synthetic weights for the CPU legs (cpu_baseline / --impl reference only)."""
     from oracle import restate
     if name in CLIP_PATCH:
         from oracle import restate_vit
@@ -121,15 +132,20 @@ def oracle_embed(name, parts, obs):
 def build_net(name, device):
     from pvr_habitat_b200.embeddings import EmbeddingNet
     from pvr_habitat_b200.vision_models.moco import allow_random_init
+    # random-init weights of the named architecture from the package's own parameter holders (there is no network
+    # for checkpoints); BatchNorm statistics are randomised so that the folded scale / bias are not trivial
+    torch.manual_seed(1)
     with allow_random_init():
         net = EmbeddingNet(name)
-    if name in CLIP_PATCH:
-        net.embedding.load_state_dict(oracle_parts(name), strict=True)
-        net.invalidate()
-        return net
-    parts = net.embedding.models if hasattr(net.embedding, "models") else [net.embedding]
-    for m, (v, sd) in zip(parts, oracle_parts(name)):
-        m.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(2)
+    with torch.no_grad():
+        for k, v in net.embedding.state_dict().items():
+            if k.endswith("running_var"):
+                v.copy_(torch.empty(v.shape).uniform_(0.75, 1.25, generator=g))
+            elif k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+            elif "bn" in k.split(".")[-2:][0] and k.endswith("weight") and v.dim() == 1:
+                v.copy_(torch.empty(v.shape).uniform_(0.4, 0.9, generator=g))
     net.invalidate()
     return net
 
@@ -152,8 +168,16 @@ BC_GFLOP_PER_STEP = 979.0  # fwd+bwd 119.6 MFLOP/sample x 8192
 
 
 def bc_dataset(seed=7):
-    from oracle import restate_policy as rp  # synthetic-input generator only
-    return rp.synthetic_bc_data(BC_CFG["n"], BC_CFG["D"], BC_CFG["A"], seed)
+    """Synthetic pre-embedded BC dataset (obs (n, D) float32, action, done, -): ReLU-like features whose action is a
+    noisy linear function of the observation, episodes of random length."""
+    rng = np.random.default_rng(seed)
+    n, D, A = BC_CFG["n"], BC_CFG["D"], BC_CFG["A"]
+    obs = np.maximum(rng.standard_normal((n, D), dtype=np.float32), 0.0)
+    w = rng.standard_normal((D, A), dtype=np.float32) / np.sqrt(D)
+    action = (obs @ w + 0.3 * rng.standard_normal((n, A), dtype=np.float32)).argmax(1).astype(np.int64)
+    done = rng.random(n) < 1.0 / 200.0
+    done[0] = True
+    return obs, action, done, None
 
 
 def bench_bc(steps, warmup, world, dist, host_batches):

@@ -97,6 +97,27 @@ def golden_small_conv(E):
     print("small_conv.npz", out["emb64"].shape, int(net.out_size))
 
 
+RESNET_BASIC_SEEDS = {"resnet18": 61, "resnet34": 62}
+
+
+def golden_resnet_basic(E):
+    """The reference's `resnet18` / `resnet34` encoders (torchvision nets with fc = Identity, src/embeddings.py:112-117)
+    on synthetic weights from `restate.resnet_basic_state(name, seed)` (loaded with strict=True)."""
+    frames64 = restate.structured_frames(4, 64, 64, 3, 71)
+    frames224 = restate.structured_frames(2, 224, 224, 3, 72)
+    out = {"frames64": frames64, "frames224": frames224}
+    for name, seed in RESNET_BASIC_SEEDS.items():
+        net = E.EmbeddingNet(name, pretrained=False, train=False, disable_cuda=True)
+        net.embedding.load_state_dict(restate.resnet_basic_state(name, seed), strict=True)
+        out[f"seed_{name}"] = np.array(seed)
+        out[f"out_size_{name}"] = np.array(int(net.out_size))
+        out[f"emb64_{name}"] = net(torch.from_numpy(frames64))
+        out[f"emb224_{name}"] = net(torch.from_numpy(frames224))
+        out[f"n_state_keys_{name}"] = np.array(len(net.state_dict()))
+        print(name, int(net.out_size), out[f"emb64_{name}"].shape, len(net.state_dict()))
+    np.savez_compressed(os.path.join(GOLDEN, "resnet_basic.npz"), **out)
+
+
 def golden_policy():
     """Reference PolicyNet (src/models.py) forward/backward, and the per-step training trace of the UNMODIFIED
     main_bc_2.run() on a synthetic embedded-observation pickle (fake env / test modules)."""
@@ -214,8 +235,10 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
-    if "transforms" in which or "embeddings" in which or "small_conv" in which:
+    if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which:
         E = refshim.reference_embeddings()
+        if "resnet_basic" in which:
+            golden_resnet_basic(E)
         if "transforms" in which:
             golden_transforms(E)
         if "embeddings" in which:

@@ -168,6 +168,60 @@ def resnet50_forward(sd, variant, x):
     return x.reshape(x.shape[0], -1)
 
 
+RESNET_BASIC_LAYERS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+
+
+def resnet_basic_state(name, seed):
+    """Deterministic random weights with torchvision's resnet18 / resnet34 key names (BasicBlock nets,
+    tv:models/resnet.py:59-101, 266-282), fc omitted (the reference replaces it by Identity, src/embeddings.py:112-117)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+
+    def conv(key, co, ci, k):
+        sd[key + ".weight"] = torch.from_numpy(
+            (rng.standard_normal((co, ci, k, k), dtype=np.float32) * np.float32(math.sqrt(2.0 / (co * k * k)))))
+
+    def bn(key, c, gain):
+        sd[key + ".weight"] = torch.from_numpy(rng.uniform(gain * 0.75, gain * 1.25, c).astype(np.float32))
+        sd[key + ".bias"] = torch.from_numpy((rng.standard_normal(c) * 0.1).astype(np.float32))
+        sd[key + ".running_mean"] = torch.from_numpy((rng.standard_normal(c) * 0.1).astype(np.float32))
+        sd[key + ".running_var"] = torch.from_numpy(rng.uniform(0.75, 1.25, c).astype(np.float32))
+        sd[key + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    conv("conv1", 64, 3, 7)
+    bn("bn1", 64, 1.0)
+    c_in = 64
+    for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), RESNET_BASIC_LAYERS[name])):
+        for b in range(blocks):
+            p = f"layer{li + 1}.{b}"
+            conv(p + ".conv1", planes, c_in, 3)
+            bn(p + ".bn1", planes, 1.0)
+            conv(p + ".conv2", planes, planes, 3)
+            bn(p + ".bn2", planes, 0.5)
+            if b == 0 and li > 0:
+                conv(p + ".downsample.0", planes, c_in, 1)
+                bn(p + ".downsample.1", planes, 0.7)
+            c_in = planes
+    return sd
+
+
+def resnet_basic_forward(sd, name, x):
+    """torchvision resnet18 / resnet34 forward with fc = Identity (src/embeddings.py:112-117): output (N, 512)."""
+    sd = {k: v.float() for k, v in sd.items() if v.is_floating_point()}
+    x = F.relu(_bn(F.conv2d(x, sd["conv1.weight"], stride=2, padding=3), sd, "bn1"))
+    x = F.max_pool2d(x, 3, 2, 1)
+    for li, blocks in enumerate(RESNET_BASIC_LAYERS[name]):
+        for b in range(blocks):
+            p = f"layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            t = F.relu(_bn(F.conv2d(x, sd[p + ".conv1.weight"], stride=stride, padding=1), sd, p + ".bn1"))
+            t = _bn(F.conv2d(t, sd[p + ".conv2.weight"], padding=1), sd, p + ".bn2")
+            if p + ".downsample.0.weight" in sd:
+                x = _bn(F.conv2d(x, sd[p + ".downsample.0.weight"], stride=stride), sd, p + ".downsample.1")
+            x = F.relu(t + x)
+    return F.adaptive_avg_pool2d(x, 1).reshape(x.shape[0], -1)
+
+
 def small_conv_forward(sd, x):
     """The 'random' PVR (src/embeddings.py:90-106): 5 x [Conv2d(3x3, s2, p1, bias) -> ELU], flattened NCHW."""
     for i in (0, 2, 4, 6, 8):

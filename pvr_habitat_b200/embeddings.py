@@ -16,7 +16,7 @@ from . import program as prg
 from .vision_models import clip_vit
 from .vision_models.moco import moco_conv3_compressed, moco_conv4_compressed, moco_conv5
 from .vision_models.resnet import resnet_conv3_compressed, resnet_conv4_compressed, resnet_conv5
-from .vision_models.resnet_params import ResNet50Params
+from .vision_models.resnet_params import ResNet50Params, ResNetBasicParams
 
 IMAGENET_MEAN, IMAGENET_STD = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
 CLIP_MEAN, CLIP_STD = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
@@ -142,6 +142,10 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
         # FIXED 5-LAYER CONV (src/embeddings.py:90-106): built with the same layer order / init calls as the
         # reference, so the same torch seed gives the same weights and the same state_dict keys ('0.weight', ...).
         model = SmallConvParams(in_channels)
+    elif embedding_name in ('resnet18', 'resnet34'):
+        # torchvision.models.resnet18 / resnet34(pretrained=...), fc -> Identity (src/embeddings.py:112-117); as for
+        # resnet50 there is no download offline: pretrained weights come in through load_state_dict
+        model = ResNetBasicParams(embedding_name)
     elif embedding_name == 'resnet50':
         # torchvision.models.resnet50(pretrained=...), fc -> Identity (src/embeddings.py:118-120). Offline there is no
         # download: pretrained weights must already be loaded by the caller through load_state_dict.
@@ -178,7 +182,7 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
     elif embedding_name == 'true_state':
         return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
     else:
-        # 'random', mae_*, resnet18/34, clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
+        # mae_*, clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
         raise NotImplementedError("Requested model not available.")
 
     if train:
@@ -204,7 +208,10 @@ def build_encoder(model, device, hw=224):
     off = 0
     for m in parts:
         sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
-        off += prg.add_resnet50(prog, sd, m.variant, in_slot, off, hw)
+        if isinstance(m, ResNetBasicParams):
+            off += prg.add_resnet_basic(prog, sd, m.LAYERS[m.name], in_slot, off, hw)
+        else:
+            off += prg.add_resnet50(prog, sd, m.variant, in_slot, off, hw)
     prog.emb_width = off
     enc = prog.finish(device)
     enc.input_format = _lib.PVR_FMT_STEM_BF16

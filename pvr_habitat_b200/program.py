@@ -370,6 +370,35 @@ def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
     return n
 
 
+def add_resnet_basic(prog, sd, layers, in_slot, emb_offset, hw=224):
+    """Append a BasicBlock ResNet (resnet18: layers (2,2,2,2); resnet34: (3,4,6,3); tv:models/resnet.py:59-101) with
+    fc = Identity (src/embeddings.py:112-117), reading the W-expanded frames in `in_slot`. Writes 512 columns."""
+    scale, bias = fold_bn(sd, "bn1")
+    p = (hw + 6 - 7) // 2 + 1
+    stem = prog.conv(in_slot, (32, hw, hw // 2), pack_stem_weight(sd["conv1.weight"].float(), 64), 256, 64, 7, 1,
+                     (2, 1), (-3, 0), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147)
+    x, h, w = prog.maxpool(stem, 64, p, p)
+    prog.release(stem)
+    chw = (64, h, w)
+    for li, blocks in enumerate(layers):
+        for b in range(blocks):
+            pre = f"layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            t, st = _conv_bn(prog, sd, pre + ".conv1", pre + ".bn1", x, chw, stride, 1, True)
+            if pre + ".downsample.0.weight" in sd:
+                idn, sidn = _conv_bn(prog, sd, pre + ".downsample.0", pre + ".downsample.1", x, chw, stride, 0, False)
+                prog.release(x)
+            else:
+                idn, sidn = x, chw
+            y, sy = _conv_bn(prog, sd, pre + ".conv2", pre + ".bn2", t, st, 1, 1, True, res=(idn, sidn[0], 0))
+            prog.release(t)
+            prog.release(idn)
+            x, chw = y, sy
+    prog.avgpool(x, chw[0], chw[1], chw[2], emb_offset)
+    prog.release(x)
+    return chw[0]
+
+
 # ------------------------------------------------------------------------------------------------ small-conv PVR
 def pack_first_small_conv(w, n_pad):
     """3x3 stride-2 pad-1 conv over NHWC4 frames seen as pixel pairs (H, W/2, 8): output column q reads input columns

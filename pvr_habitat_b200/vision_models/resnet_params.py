@@ -85,3 +85,32 @@ class ResNet50Params(nn.Module):
             self.layer3, self.layer4 = layer3, layer4
         # zero-init is NOT used by torchvision's default constructor (zero_init_residual=False)
         self.out_size = self.OUT[variant]
+
+
+class BasicP(nn.Module):
+    """torchvision BasicBlock (tv:models/resnet.py:59-101): two 3x3 convs, optional 1x1 projection shortcut."""
+    expansion = 1
+
+    def __init__(self, c_in, planes, downsample):
+        super().__init__()
+        self.conv1, self.bn1 = ConvP(c_in, planes, 3), BNP(planes)
+        self.conv2, self.bn2 = ConvP(planes, planes, 3), BNP(planes)
+        if downsample:
+            self.downsample = nn.Sequential(ConvP(c_in, planes, 1), BNP(planes))
+
+
+class ResNetBasicParams(nn.Module):
+    """resnet18 / resnet34 with fc = Identity (src/embeddings.py:112-117); state_dict keys are torchvision's."""
+
+    LAYERS = {"resnet18": (2, 2, 2, 2), "resnet34": (3, 4, 6, 3)}
+
+    def __init__(self, name):
+        super().__init__()
+        self.name = name
+        self.conv1, self.bn1 = ConvP(3, 64, 7), BNP(64)
+        c_in = 64
+        for li, (planes, blocks) in enumerate(zip((64, 128, 256, 512), self.LAYERS[name])):
+            layer = [BasicP(c_in, planes, li > 0)] + [BasicP(planes, planes, False) for _ in range(blocks - 1)]
+            setattr(self, f"layer{li + 1}", nn.Sequential(*layer))
+            c_in = planes
+        self.out_size = 512

@@ -282,3 +282,17 @@ def test_streamed_back_to_back_kernel_is_bit_identical(emb, monkeypatch):
     assert np.array_equal(default, streamed)
     assert net2.encoder().lib.pvr_encoder_launch_count(net2.encoder().handle) < \
         net.encoder().lib.pvr_encoder_launch_count(net.encoder().handle)
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet34"])
+def test_resnet_basic_embedding_vs_reference_golden(golden_dir, name):
+    """`resnet18` / `resnet34` (BasicBlock nets, src/embeddings.py:112-117) against the reference's
+    EmbeddingNet outputs on the same synthetic weights."""
+    g = np.load(os.path.join(golden_dir, "resnet_basic.npz"))
+    with allow_random_init():
+        net = EmbeddingNet(name, pretrained=False)
+    net.embedding.load_state_dict(restate.resnet_basic_state(name, int(g[f"seed_{name}"])), strict=True)
+    net.invalidate()
+    assert net.out_size == 512
+    for tag in ("64", "224"):
+        check_embedding(net(torch.from_numpy(g["frames" + tag])), g[f"emb{tag}_{name}"])

@@ -107,3 +107,20 @@ def test_uber_state_dict_is_empty_in_reference(emb):
     """Reference quirk D8 (src/embeddings.py:45-53) recorded by the fixture."""
     assert int(emb["n_state_keys_moco_aug_uber_34"]) == 0
     assert int(emb["n_state_keys_moco_aug"]) == 318
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet34"])
+def test_resnet_basic_restatement_matches_reference(golden_dir, name):
+    """resnet18 / resnet34: the oracle restatement against the reference's EmbeddingNet outputs
+    (torchvision nets with fc = Identity, src/embeddings.py:112-117) on the same synthetic weights."""
+    g = np.load(os.path.join(golden_dir, "resnet_basic.npz"))
+    sd = restate.resnet_basic_state(name, int(g[f"seed_{name}"]))
+    for tag in ("64", "224"):
+        frames = g["frames" + tag]
+        x = torch.from_numpy(restate.transforms(np.ascontiguousarray(frames.transpose(0, 3, 1, 2))))
+        with torch.no_grad():
+            got = restate.resnet_basic_forward(sd, name, x).numpy()
+        ref = g[f"emb{tag}_{name}"]
+        assert got.shape == ref.shape == (frames.shape[0], 512)
+        assert np.abs(got - ref).max() <= 2e-4 * np.abs(ref).max()
+    assert int(g[f"out_size_{name}"]) == 512

@@ -140,3 +140,24 @@ def test_random_embedding_container_reproduces_reference_init(golden_dir):
     for k in gold.files:
         if k.startswith("w_"):  # orthogonal_ = LAPACK QR: last bits may differ between hosts
             np.testing.assert_allclose(sd["embedding." + k[2:]].numpy(), gold[k], atol=1e-5)
+
+
+@pytest.mark.parametrize("name,n_ops", [("resnet18", 1 + 1 + 16 + 3 + 1), ("resnet34", 1 + 1 + 32 + 3 + 1)])
+def test_resnet_basic_program_equals_oracle_network(name, n_ops):
+    """resnet18 / resnet34 op programs (stem, max pool, BasicBlocks with 1x1 projection shortcuts, avg pool)."""
+    from pvr_habitat_b200.vision_models.resnet_params import ResNetBasicParams
+    sd = restate.resnet_basic_state(name, 4)
+    sd = {k: (v.to(torch.bfloat16).float() if k.endswith(".weight") and v.dim() == 4 else v) for k, v in sd.items()}
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 32 * 32)
+    prog.emb_width = prg.add_resnet_basic(prog, sd, restate.RESNET_BASIC_LAYERS[name], s0, 0, hw=64)
+    assert prog.emb_width == 512 and len(prog.ops) == n_ops
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    x4 = torch.zeros(2, 64, 64, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    got = emulate(prog, prg.expand_stem_input(x4), round_bf16=False)
+    ref = restate.resnet_basic_forward(sd, name, x)
+    assert float((got - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
+    # the parameter holder has torchvision's keys (checkpoints interchange)
+    keys = set(ResNetBasicParams(name).state_dict().keys())
+    assert keys == set(sd.keys())

@@ -71,6 +71,16 @@ struct pvr_encoder {
   std::vector<char*> slot_ptr;
   std::vector<BoundConv> bound;  // one per op (unused for non-conv ops)
   std::vector<char> fused;       // op is executed inside the epilogue of the op before it (stem + max pool)
+  // Small-batch (rollout) mode: the launch sequence of one forward into a fixed output buffer is captured into a CUDA
+  // graph on its second use and replayed afterwards (50-100 launches of a few microseconds each are otherwise bound
+  // by the host's launch cost). Invalidated by bind.
+  cudaGraphExec_t graph = nullptr;
+  float* graph_emb = nullptr;
+  int64_t graph_ld = 0;
+  int graph_seen = 0;
+  ~pvr_encoder() {
+    if (graph) cudaGraphExecDestroy(graph);
+  }
 };
 
 extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* slots, int n_slots, int emb_width,
@@ -145,6 +155,9 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     return PVR_ERR_CUDA;
   }
   enc->n_images = 0;
+  if (enc->graph) cudaGraphExecDestroy(enc->graph);
+  enc->graph = nullptr;
+  enc->graph_seen = 0;
   enc->slot_ptr.resize(enc->slots.size());
   for (size_t s = 0; s < enc->slots.size(); ++s)
     enc->slot_ptr[s] = static_cast<char*>(workspace) + slot_offset(enc, (int)s, n_images);
@@ -522,7 +535,60 @@ static int encoder_check(pvr_encoder* enc, float* emb, int64_t emb_ld) {
 extern "C" int pvr_encoder_forward(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream_) {
   int rc = encoder_check(enc, emb, emb_ld);
   if (rc != PVR_OK) return rc;
-  return encoder_run(enc, emb, emb_ld, static_cast<cudaStream_t>(stream_), nullptr);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_);
+  static const bool graphs_on = getenv("PVR_NO_ENC_GRAPH") == nullptr;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (!graphs_on || enc->n_images > 8 || cudaStreamIsCapturing(st, &cs) != cudaSuccess ||
+      cs != cudaStreamCaptureStatusNone)
+    return encoder_run(enc, emb, emb_ld, st, nullptr);
+  if (enc->graph && enc->graph_emb == emb && enc->graph_ld == emb_ld) {
+    cudaError_t e = cudaGraphLaunch(enc->graph, st);
+    if (e != cudaSuccess) {
+      pvr_set_error("pvr_encoder_forward: cudaGraphLaunch: %s", cudaGetErrorString(e));
+      return PVR_ERR_CUDA;
+    }
+    return PVR_OK;
+  }
+  if (enc->graph_emb != emb || enc->graph_ld != emb_ld) {  // new output buffer: start over
+    if (enc->graph) cudaGraphExecDestroy(enc->graph);
+    enc->graph = nullptr;
+    enc->graph_emb = emb;
+    enc->graph_ld = emb_ld;
+    enc->graph_seen = 0;
+  }
+  if (enc->graph_seen++ == 0) return encoder_run(enc, emb, emb_ld, st, nullptr);  // first use stays eager
+  // capture on a private stream (the caller's may be the legacy default stream), replay on the caller's
+  static cudaStream_t cap = nullptr;
+  if (!cap && cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    return encoder_run(enc, emb, emb_ld, st, nullptr);
+  }
+  cudaGraph_t graph = nullptr;
+  if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    return encoder_run(enc, emb, emb_ld, st, nullptr);
+  }
+  rc = encoder_run(enc, emb, emb_ld, cap, nullptr);
+  cudaError_t e = cudaStreamEndCapture(cap, &graph);
+  if (rc != PVR_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc != PVR_OK) return rc;
+    return encoder_run(enc, emb, emb_ld, st, nullptr);
+  }
+  e = cudaGraphInstantiate(&enc->graph, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    enc->graph = nullptr;
+    cudaGetLastError();
+    return encoder_run(enc, emb, emb_ld, st, nullptr);
+  }
+  e = cudaGraphLaunch(enc->graph, st);
+  if (e != cudaSuccess) {
+    pvr_set_error("pvr_encoder_forward: cudaGraphLaunch: %s", cudaGetErrorString(e));
+    return PVR_ERR_CUDA;
+  }
+  return PVR_OK;
 }
 
 extern "C" int pvr_encoder_forward_timed(pvr_encoder* enc, float* emb, int64_t emb_ld, void* stream_, float* op_ms) {

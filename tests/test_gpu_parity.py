@@ -296,3 +296,16 @@ def test_resnet_basic_embedding_vs_reference_golden(golden_dir, name):
     assert net.out_size == 512
     for tag in ("64", "224"):
         check_embedding(net(torch.from_numpy(g["frames" + tag])), g[f"emb{tag}_{name}"])
+
+
+def test_small_batch_graph_replay_equals_eager(emb):
+    """Rollout-sized batches (<= 8 images) into a fixed output buffer: the first call runs eagerly, the second is
+    captured into a CUDA graph, later ones replay it — all bitwise equal, also after the input changes."""
+    net = make_net("moco_aug_uber_34", emb["weight_seeds"])
+    out = torch.empty(2, net.out_size, device="cuda")
+    ref_net = make_net("moco_aug_uber_34", emb["weight_seeds"])
+    for k in range(5):
+        frames = torch.from_numpy(restate.structured_frames(2, 64, 64, 3, 30 + k))
+        net.embed(frames, 1, out)
+        want = ref_net.embed(frames)  # fresh output tensor every time: never replayed
+        assert torch.equal(out, want), k

@@ -51,6 +51,7 @@ int pvr_abi_version(void);
 #define PVR_FMT_NCHW_F32 0
 #define PVR_FMT_NHWC4_BF16 1
 #define PVR_FMT_STEM_BF16 2
+#define PVR_FMT_NHWC4_F32 3 /* (n*N, crop, crop, 4) float32, RGB + zero pad: input of the fp32 parity mode */
 int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int rh, int rw, int top, int left,
                       int crop, const float* mean, const float* stdv, void* out, int out_fmt, int sample_major,
                       void* stream);
@@ -74,6 +75,11 @@ int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int 
  * 3x3 convolution over C = 1024 / 2048 channels runs as ONE 1x1 GEMM producing the 9 per-tap partial sums of every
  * pixel (the input is read once instead of nine times); the HEAD op adds the shifted partial sums in fp32. */
 #define PVR_CONV_OUT_F32 1
+/* Any op: fp32 parity mode (north star: embeddings within 1e-5 of the reference). Activations, weights, residuals are
+ * float32 (pitches count floats, slots are sized as 2 bf16 elements per value), weights are dense (c_out, r, s, c_in)
+ * float32 with k_pad = r*s*c_in; the op runs on the CUDA cores (conv_f32_kernel, fp32 FMA accumulation) instead of the
+ * bf16 tensor-core kernels. No fusion flags (in2, OUT_F32) in this mode. */
+#define PVR_OP_FP32 2
 
 typedef struct pvr_op {
   int32_t kind;

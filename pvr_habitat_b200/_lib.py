@@ -8,6 +8,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libpvr_b200.so")
 PVR_FMT_NCHW_F32 = 0
 PVR_FMT_NHWC4_BF16 = 1
 PVR_FMT_STEM_BF16 = 2
+PVR_FMT_NHWC4_F32 = 3
+PVR_OP_FP32 = 2
 PVR_CONV_OUT_F32 = 1
 PVR_GEMM_PDL, PVR_GEMM_MN = 1, 2
 PVR_OP_CONV, PVR_OP_MAXPOOL, PVR_OP_AVGPOOL, PVR_OP_HEAD, PVR_OP_FLATTEN = 1, 2, 3, 4, 5

@@ -97,7 +97,13 @@ extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* 
       pvr_set_error("pvr_encoder_create: op %d references a slot out of range", i);
       return PVR_ERR_ARG;
     }
-    if (o.kind == PVR_OP_CONV) {
+    if (o.kind == PVR_OP_CONV && (o.flags & PVR_OP_FP32)) {
+      if (!o.weight || !o.scale || !o.bias || o.c_in % 4 || o.in_pitch % 4 || o.k_pad != o.r * o.s * o.c_in ||
+          o.in2_c != 0 || (o.flags & PVR_CONV_OUT_F32)) {
+        pvr_set_error("pvr_encoder_create: op %d has an invalid fp32 conv description", i);
+        return PVR_ERR_ARG;
+      }
+    } else if (o.kind == PVR_OP_CONV) {
       if (!o.weight || !o.scale || !o.bias || o.k_pad <= 0 || o.k_pad % 64 || o.n_pad <= 0 || o.n_pad % 32 ||
           o.c_out > o.n_pad || (o.in_pitch % 8) || (o.out_pitch % 8) || (o.out_coff % 8)) {
         pvr_set_error("pvr_encoder_create: op %d has an invalid conv description", i);
@@ -180,6 +186,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       continue;
     }
     if (enc->fused[i]) continue;  // executed inside the previous op's kernel (conv_b2b.cu)
+    if (o.flags & PVR_OP_FP32) continue;  // fp32 parity mode: plain pointers, nothing to bind
     BoundConv& b = enc->bound[i];
     pvr::ConvGemmParams& p = b.p;
     memset(&p, 0, sizeof(p));
@@ -477,6 +484,47 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
     cudaError_t e = cudaSuccess;
     if (ev) cudaEventRecord(ev[i], stream);
     if (enc->fused[i]) continue;
+    if (o.flags & PVR_OP_FP32) {  // fp32 parity mode (conv_f32.cu)
+      const float* in = reinterpret_cast<const float*>(enc->slot_ptr[o.in_slot]);
+      switch (o.kind) {
+        case PVR_OP_CONV: {
+          pvr::ConvF32Params q;
+          memset(&q, 0, sizeof(q));
+          q.in = in;
+          q.w = static_cast<const float*>(o.weight);
+          q.scale = o.scale;
+          q.bias = o.bias;
+          q.res = o.res_slot >= 0 ? reinterpret_cast<const float*>(enc->slot_ptr[o.res_slot]) : nullptr;
+          q.out = reinterpret_cast<float*>(enc->slot_ptr[o.out_slot]);
+          q.M = (long long)n * o.h_out * o.w_out;
+          q.N = o.c_out; q.C = o.c_in; q.H = o.h_in; q.W = o.w_in; q.P = o.h_out; q.Q = o.w_out; q.R = o.r; q.S = o.s;
+          q.stride_h = o.stride_h; q.stride_w = o.stride_w; q.lower_h = o.lower_h; q.lower_w = o.lower_w;
+          q.in_pitch = o.in_pitch; q.out_pitch = o.out_pitch; q.out_coff = o.out_coff; q.res_pitch = o.res_pitch;
+          q.res_coff = o.res_coff; q.relu_n = o.relu_n; q.elu = o.act == 3;
+          e = pvr::launch_conv_f32(q, stream);
+          break;
+        }
+        case PVR_OP_MAXPOOL:
+          e = pvr::launch_maxpool_f32(in, reinterpret_cast<float*>(enc->slot_ptr[o.out_slot]), n, o.h_in, o.w_in, o.c_in,
+                                      o.h_out, o.w_out, stream);
+          break;
+        case PVR_OP_AVGPOOL:
+          e = pvr::launch_avgpool_f32(in, emb, emb_ld, o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
+          break;
+        case PVR_OP_FLATTEN:
+          e = pvr::launch_flatten_f32(in, o.in_pitch, emb, emb_ld, o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
+          break;
+        case PVR_OP_HEAD:
+          e = pvr::launch_head_tail_f32(in, o.in_pitch, static_cast<const float*>(o.aux), emb, emb_ld, o.emb_offset, n,
+                                        o.h_in, o.w_in, o.c_out, stream);
+          break;
+      }
+      if (e != cudaSuccess) {
+        pvr_set_error("pvr_encoder_forward: fp32 op %zu (kind %d): %s", i, o.kind, cudaGetErrorString(e));
+        return PVR_ERR_CUDA;
+      }
+      continue;
+    }
     switch (o.kind) {
       case PVR_OP_CONV: {
         const BoundConv& b = enc->bound[i];

@@ -1,0 +1,212 @@
+// fp32 parity mode (north star: "relative L2 <= 1e-5 in the fp32 mode"): the encoder program on the CUDA cores with
+// float32 activations, weights and accumulation. Not a performance path — an implicit-GEMM convolution with 64 x 64
+// output tiles, 16-deep K slices staged in shared memory and 4 x 4 register blocks per thread (torchvision semantics:
+// Conv2d -> folded BatchNorm -> (+ residual) -> ReLU / ELU, tv:models/resnet.py:59-166), plus the pooling / head
+// kernels in float32.
+#include "kernels.cuh"
+
+namespace pvr {
+namespace {
+
+constexpr int F32_TM = 64, F32_TN = 64, F32_TK = 16;
+
+__global__ void __launch_bounds__(256) conv_f32_kernel(ConvF32Params p) {
+  __shared__ float As[F32_TK][F32_TM + 4];
+  __shared__ float Bs[F32_TK][F32_TN + 4];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * F32_TM;
+  const int n0 = blockIdx.y * F32_TN;
+  // loader roles: one float4 (4 consecutive K) of one pixel / one output channel per thread
+  const int l_row = tid >> 2, l_k4 = (tid & 3) * 4;
+  const long long lm = m0 + l_row;
+  int l_img = 0, l_p = 0, l_q = 0;
+  const bool l_valid = lm < p.M;
+  if (l_valid) {
+    const int pq = p.P * p.Q;
+    l_img = (int)(lm / pq);
+    const int rem = (int)(lm - (long long)l_img * pq);
+    l_p = rem / p.Q;
+    l_q = rem - l_p * p.Q;
+  }
+  const int l_co = n0 + l_row;
+  const int ty = tid >> 4, tx = tid & 15;  // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int K = p.R * p.S * p.C;
+  for (int r = 0; r < p.R; ++r) {
+    const int hh = l_p * p.stride_h + p.lower_h + r;
+    for (int s = 0; s < p.S; ++s) {
+      const int ww = l_q * p.stride_w + p.lower_w + s;
+      const bool in_img = l_valid && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
+      const float* src = p.in + (((long long)l_img * p.H + hh) * p.W + ww) * p.in_pitch;
+      const int kbase = (r * p.S + s) * p.C;
+      for (int c0 = 0; c0 < p.C; c0 += F32_TK) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = c0 + l_k4;
+        if (in_img && c < p.C) a = *reinterpret_cast<const float4*>(src + c);  // C % 4 == 0
+        if (l_co < p.N && c < p.C) b = *reinterpret_cast<const float4*>(p.w + (long long)l_co * K + kbase + c);
+        __syncthreads();
+        As[l_k4 + 0][l_row] = a.x; As[l_k4 + 1][l_row] = a.y; As[l_k4 + 2][l_row] = a.z; As[l_k4 + 3][l_row] = a.w;
+        Bs[l_k4 + 0][l_row] = b.x; Bs[l_k4 + 1][l_row] = b.y; Bs[l_k4 + 2][l_row] = b.z; Bs[l_k4 + 3][l_row] = b.w;
+        __syncthreads();
+        // blocked summation: the 16 products of a slice are summed on their own and then added to the running sum, so
+        // the rounding error grows like sqrt(16) + sqrt(K / 16) ulps instead of sqrt(K) (K up to 4608; the parity
+        // budget of this mode is 1e-5 over ~50 layers)
+        float part[4][4];
+#pragma unroll
+        for (int kk = 0; kk < F32_TK; ++kk) {
+          const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+          const float ar[4] = {av.x, av.y, av.z, av.w}, br[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) part[i][j] = kk == 0 ? ar[i] * br[j] : fmaf(ar[i], br[j], part[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = n0 + tx * 4 + j;
+      if (co >= p.N) continue;
+      float v = fmaf(acc[i][j], p.scale[co], p.bias[co]);
+      if (p.res) v += p.res[m * p.res_pitch + p.res_coff + co];
+      if (co < p.relu_n) v = fmaxf(v, 0.f);
+      if (p.elu) v = v > 0.f ? v : expm1f(v);
+      p.out[m * p.out_pitch + p.out_coff + co] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) maxpool3x3s2_f32_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                                int n_img, int H, int W, int C, int P, int Q) {
+  const long long total = (long long)n_img * P * Q * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    long long t = idx / C;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int pp = (int)(t % P);
+    const int img = (int)(t / P);
+    float m = -INFINITY;
+    for (int r = 0; r < 3; ++r) {
+      const int h = pp * 2 - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int w = q * 2 - 1 + s;
+        if (w < 0 || w >= W) continue;
+        m = fmaxf(m, in[(((long long)img * H + h) * W + w) * C + c]);
+      }
+    }
+    out[idx] = m;
+  }
+}
+
+__global__ void __launch_bounds__(256) avgpool_f32_kernel(const float* __restrict__ in, float* __restrict__ emb,
+                                                           long long emb_ld, int emb_off, int n_img, int HW, int C) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_img * C) return;
+  const int c = (int)(idx % C);
+  const int img = (int)(idx / C);
+  float acc = 0.f;
+  for (int px = 0; px < HW; ++px) acc += in[((long long)img * HW + px) * C + c];
+  emb[(long long)img * emb_ld + emb_off + c] = acc / (float)HW;
+}
+
+// emb[img][off + c*HW + px] = in[img][px][c]
+__global__ void __launch_bounds__(256) flatten_f32_kernel(const float* __restrict__ in, int pitch,
+                                                           float* __restrict__ emb, long long emb_ld, int emb_off,
+                                                           int n_img, int HW, int C) {
+  const long long total = (long long)n_img * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int px = (int)(i % HW);
+    const int c = (int)((i / HW) % C);
+    const long long img = i / ((long long)HW * C);
+    emb[img * emb_ld + emb_off + (long long)c * HW + px] = in[(img * HW + px) * pitch + c];
+  }
+}
+
+// Compression-head tail on float32 input: t = [relu(bn1(conv1 x)) | bn_d(conv_d x)] (2c per pixel), see
+// head_tail_kernel. aux = w2[c][3][3][c] | scale2[c] | bias2[c].
+__global__ void __launch_bounds__(256) head_tail_f32_kernel(const float* __restrict__ t, int pitch,
+                                                             const float* __restrict__ aux, float* __restrict__ emb,
+                                                             long long emb_ld, int emb_off, int H, int W, int c) {
+  const int img = blockIdx.x, HW = H * W;
+  const float* w2 = aux;
+  const float* sc = aux + c * 9 * c;
+  const float* bi = sc + c;
+  const float* ti = t + (long long)img * HW * pitch;
+  for (int o = threadIdx.x; o < c * HW; o += blockDim.x) {
+    const int co = o / HW, px = o - co * HW;
+    const int y = px / W, x = px - y * W;
+    float acc = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const int yy = y - 1 + r;
+      if (yy < 0 || yy >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int xx = x - 1 + s;
+        if (xx < 0 || xx >= W) continue;
+        const float* a = ti + (long long)(yy * W + xx) * pitch;
+        const float* wv = w2 + ((co * 3 + r) * 3 + s) * c;
+        for (int ci = 0; ci < c; ++ci) acc = fmaf(a[ci], wv[ci], acc);
+      }
+    }
+    const float v = fmaf(acc, sc[co], bi[co]) + ti[(long long)px * pitch + c + co];
+    emb[(long long)img * emb_ld + emb_off + o] = fmaxf(v, 0.f);
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_conv_f32(const ConvF32Params& p, cudaStream_t stream) {
+  dim3 grid((unsigned)((p.M + F32_TM - 1) / F32_TM), (unsigned)((p.N + F32_TN - 1) / F32_TN));
+  conv_f32_kernel<<<grid, 256, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_maxpool_f32(const float* in, float* out, int n_img, int H, int W, int C, int P, int Q,
+                               cudaStream_t stream) {
+  const long long total = (long long)n_img * P * Q * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  maxpool3x3s2_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, out, n_img, H, W, C, P, Q);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_avgpool_f32(const float* in, float* emb, long long emb_ld, int emb_off, int n_img, int HW, int C,
+                               cudaStream_t stream) {
+  const long long total = (long long)n_img * C;
+  avgpool_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, emb, emb_ld, emb_off, n_img, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_flatten_f32(const float* in, int pitch, float* emb, long long emb_ld, int emb_off, int n_img, int HW,
+                               int C, cudaStream_t stream) {
+  const long long total = (long long)n_img * HW * C;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  flatten_f32_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, pitch, emb, emb_ld, emb_off, n_img, HW, C);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_head_tail_f32(const float* t, int pitch, const float* aux, float* emb, long long emb_ld, int emb_off,
+                                 int n_img, int H, int W, int c, cudaStream_t stream) {
+  head_tail_f32_kernel<<<n_img, 256, 0, stream>>>(t, pitch, aux, emb, emb_ld, emb_off, H, W, c);
+  return cudaGetLastError();
+}
+
+}  // namespace pvr

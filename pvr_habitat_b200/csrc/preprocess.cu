@@ -173,6 +173,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
         dst[0] = o[0];
         dst[plane] = o[1];
         dst[2 * plane] = o[2];
+      } else if (p.fmt == PVR_FMT_NHWC4_F32) {
+        float4* dst = reinterpret_cast<float4*>(p.out) + image * plane + (long long)y * p.crop + x;
+        *dst = make_float4(o[0], o[1], o[2], 0.f);
       } else {
         __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
         __nv_bfloat162 b = __floats2bfloat162_rn(o[2], 0.f);
@@ -196,7 +199,8 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   using namespace pvr;
   if (!in || !out || N <= 0 || H <= 0 || W <= 0 || n_frames <= 0 || rh <= 0 || rw <= 0 || crop <= 0 || top < 0 ||
       left < 0 || top + crop > rh || left + crop > rw || !mean || !stdv ||
-      (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16 && out_fmt != PVR_FMT_STEM_BF16) ||
+      (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16 && out_fmt != PVR_FMT_STEM_BF16 &&
+       out_fmt != PVR_FMT_NHWC4_F32) ||
       (out_fmt == PVR_FMT_STEM_BF16 && (crop & 1))) {
     pvr_set_error("pvr_preprocess_u8: invalid argument");
     return PVR_ERR_ARG;

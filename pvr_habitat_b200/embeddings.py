@@ -193,9 +193,30 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
     return model, transforms
 
 
-def build_encoder(model, device, hw=224):
-    """Compile `model` (ResNet50Params or UberModel of them) into one pvr_encoder program on `device`."""
+def build_encoder(model, device, hw=224, precision='bf16'):
+    """Compile `model` (ResNet50Params or UberModel of them) into one pvr_encoder program on `device`.
+
+    precision: 'bf16' (tensor-core kernels) or 'fp32' (the north star's parity mode: float32 CUDA-core kernels,
+    csrc/conv_f32.cu)."""
     prog = prg.Program()
+    if precision == 'fp32':
+        in_slot = prog.new_slot(hw * hw * 4 * 2)  # slot 0: NHWC4 float32 frames (two bf16 elements per float)
+        parts = model.models if isinstance(model, UberModel) else [model]
+        off = 0
+        for m in parts:
+            sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+            if isinstance(m, SmallConvParams):
+                off += prg.add_small_conv_f32(prog, sd, in_slot, off, hw)
+            elif isinstance(m, ResNetBasicParams):
+                off += prg.add_resnet_basic_f32(prog, sd, m.LAYERS[m.name], in_slot, off, hw)
+            else:
+                off += prg.add_resnet50_f32(prog, sd, m.variant, in_slot, off, hw)
+        prog.emb_width = off
+        enc = prog.finish(device)
+        enc.input_format = _lib.PVR_FMT_NHWC4_F32
+        return enc
+    if precision != 'bf16':
+        raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
     if isinstance(model, SmallConvParams):
         in_slot = prog.new_slot(hw * hw * 4)  # slot 0: NHWC4 bf16 frames
         sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
@@ -242,6 +263,19 @@ class EmbeddingNet(nn.Module):
         self._encoder = None
         self._emb = None
         self.max_images_per_pass = 1024
+        self.precision = 'bf16'
+
+    def set_precision(self, precision):
+        """'bf16' (default, tensor cores) or 'fp32' (parity mode: float32 end to end on the CUDA cores; ResNet and
+        small-conv encoders). The constructor signature stays the reference's, hence a setter."""
+        if precision not in ('bf16', 'fp32'):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        if precision == 'fp32' and isinstance(self.embedding, clip_vit.CLIPImageModel):
+            raise NotImplementedError("the fp32 parity mode covers the ResNet / small-conv encoders, not CLIP ViT")
+        if precision != self.precision:
+            self.precision = precision
+            self._encoder = None
+        return self
 
     # ---- weights changed -> recompile the program lazily
     def load_state_dict(self, *args, **kwargs):
@@ -264,7 +298,7 @@ class EmbeddingNet(nn.Module):
                 self.embedding.invalidate()
                 self._encoder = self.embedding.runner(self.device)
             else:
-                self._encoder = build_encoder(self.embedding, self.device, self.transforms.crop)
+                self._encoder = build_encoder(self.embedding, self.device, self.transforms.crop, self.precision)
         return self._encoder
 
     def preprocess(self, observation):

@@ -128,26 +128,26 @@ class Program:
         self.deferred = []
         return out_slot
 
-    def maxpool(self, in_slot, c, h, w):
+    def maxpool(self, in_slot, c, h, w, flags=0):
         p, q = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
-        out_slot = self.alloc(p * q * c)
+        out_slot = self.alloc(p * q * c * (2 if flags & _lib.PVR_OP_FP32 else 1))
         self.ops.append(dict(kind=_lib.PVR_OP_MAXPOOL, in_slot=in_slot, out_slot=out_slot, res_slot=-1, c_in=c,
-                             h_in=h, w_in=w, in_pitch=c, c_out=c, h_out=p, w_out=q, out_pitch=c))
+                             h_in=h, w_in=w, in_pitch=c, c_out=c, h_out=p, w_out=q, out_pitch=c, flags=flags))
         return out_slot, p, q
 
-    def flatten(self, in_slot, c, h, w, pitch, emb_offset):
+    def flatten(self, in_slot, c, h, w, pitch, emb_offset, flags=0):
         self.ops.append(dict(kind=_lib.PVR_OP_FLATTEN, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=c, h_in=h,
-                             w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset))
+                             w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset, flags=flags))
 
-    def avgpool(self, in_slot, c, h, w, emb_offset):
+    def avgpool(self, in_slot, c, h, w, emb_offset, flags=0):
         self.ops.append(dict(kind=_lib.PVR_OP_AVGPOOL, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=c, h_in=h,
-                             w_in=w, in_pitch=c, c_out=c, emb_offset=emb_offset))
+                             w_in=w, in_pitch=c, c_out=c, emb_offset=emb_offset, flags=flags))
 
-    def head_tail(self, in_slot, pitch, c, h, w, aux, emb_offset, taps=False):
+    def head_tail(self, in_slot, pitch, c, h, w, aux, emb_offset, taps=False, flags=0):
         """taps: the input slot holds float32 per-tap partial sums (9 x 2c per pixel, pitch in floats), see pvr_b200.h"""
         self.ops.append(dict(kind=_lib.PVR_OP_HEAD, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=2 * c, h_in=h,
                              w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset, act=1 if taps else 0,
-                             _aux=aux.contiguous()))
+                             flags=flags, _aux=aux.contiguous()))
 
     # ---- finalise
     def finish(self, device):
@@ -397,6 +397,132 @@ def add_resnet_basic(prog, sd, layers, in_slot, emb_offset, hw=224):
     prog.avgpool(x, chw[0], chw[1], chw[2], emb_offset)
     prog.release(x)
     return chw[0]
+
+
+# ------------------------------------------------------------------------------------------------ fp32 parity mode
+# The same networks with float32 activations / weights / accumulation on the CUDA cores (csrc/conv_f32.cu), op flag
+# PVR_OP_FP32: the north star's "relative L2 <= 1e-5 in the fp32 mode". Frames arrive as PVR_FMT_NHWC4_F32 (RGB + a
+# zero fourth channel); slot sizes count bf16 elements, so every float is two of them. No fusion, no packing tricks:
+# one op per reference module, K ordered (tap_row, tap_col, channel).
+F32 = _lib.PVR_OP_FP32
+
+
+def _conv_f32(prog, w, scale, bias, in_slot, in_chw, stride, pad, relu_n, res=None, act=0):
+    """w: (C_out, C_in, R, S) float32 with C_in == in_chw[0] (a multiple of 4). Returns (slot, (C_out, P, Q))."""
+    co, ci, r, s = w.shape
+    assert ci == in_chw[0] and ci % 4 == 0, (w.shape, in_chw)
+    h, wd = in_chw[1], in_chw[2]
+    p = (h + 2 * pad - r) // stride + 1
+    q = (wd + 2 * pad - s) // stride + 1
+    wk = w.permute(0, 2, 3, 1).reshape(co, r * s * ci).float().contiguous()
+    out_slot = prog.alloc(p * q * co * 2)
+    prog.conv(in_slot, in_chw, wk, r * s * ci, co, r, s, (stride, stride), (-pad, -pad), (p, q), scale, bias, relu_n,
+              res=res, out_slot=out_slot, out_pitch=co, act=act, flags=F32)
+    return out_slot, (co, p, q)
+
+
+def _conv_bn_f32(prog, sd, conv_key, bn_key, in_slot, in_chw, stride, pad, relu, res=None):
+    w = sd[conv_key + ".weight"].float()
+    scale, bias = fold_bn(sd, bn_key, sd.get(conv_key + ".bias"))
+    return _conv_f32(prog, w, scale, bias, in_slot, in_chw, stride, pad, w.shape[0] if relu else 0, res=res)
+
+
+def _pad_rgb_weight(w):
+    """(C_out, 3, R, S) -> (C_out, 4, R, S): the zero fourth channel of the NHWC4 frames."""
+    co, ci, r, s = w.shape
+    out = torch.zeros(co, 4, r, s)
+    out[:, :ci] = w
+    return out
+
+
+def _stem_f32(prog, sd, in_slot, hw):
+    scale, bias = fold_bn(sd, "bn1")
+    stem, chw = _conv_f32(prog, _pad_rgb_weight(sd["conv1.weight"].float()), scale, bias, in_slot, (4, hw, hw), 2, 3,
+                          64)
+    x, h, w = prog.maxpool(stem, 64, chw[1], chw[2], flags=F32)
+    prog.release(stem)
+    return x, (64, h, w)
+
+
+def add_resnet50_f32(prog, sd, variant, in_slot, emb_offset, hw=224):
+    """fp32 counterpart of add_resnet50 (same variants, same embedding columns)."""
+    pre = {"conv5": ("layer3.", "layer4."), "l4": ("layer3.", "layer4.0."), "l3": ("layer3.0.", None)}[variant]
+    x, chw = _stem_f32(prog, sd, in_slot, hw)
+    for name, planes, blocks, stride in RESNET50_LAYERS:
+        if name == "layer4" and pre[1] is None:
+            break
+        key = {"layer3": pre[0], "layer4": pre[1]}.get(name, name + ".")
+        for b in range(blocks):
+            px, st = f"{key}{b}", (stride if b == 0 else 1)
+            t1, s1 = _conv_bn_f32(prog, sd, px + ".conv1", px + ".bn1", x, chw, 1, 0, True)
+            t2, s2 = _conv_bn_f32(prog, sd, px + ".conv2", px + ".bn2", t1, s1, st, 1, True)
+            prog.release(t1)
+            if b == 0:
+                idn, sidn = _conv_bn_f32(prog, sd, px + ".downsample.0", px + ".downsample.1", x, chw, st, 0, False)
+                prog.release(x)
+            else:
+                idn, sidn = x, chw
+            y, sy = _conv_bn_f32(prog, sd, px + ".conv3", px + ".bn3", t2, s2, 1, 0, True, res=(idn, sidn[0], 0))
+            prog.release(t2)
+            prog.release(idn)
+            x, chw = y, sy
+    if variant == "conv5":
+        prog.avgpool(x, chw[0], chw[1], chw[2], emb_offset, flags=F32)
+        prog.release(x)
+        return chw[0]
+    # compression head (moco.py:34-50 / :78-94): [conv1 -> bn1 -> ReLU | biased downsample conv -> BN] as one 3x3 conv
+    # with 2c outputs, then conv2 -> bn2 -> += identity -> ReLU in the head kernel
+    hp = "layer4.1" if variant == "l4" else "layer3.1"
+    w1, wd = sd[hp + ".conv1.weight"].float(), sd[hp + ".downsample.0.weight"].float()
+    c = w1.shape[0]
+    s1, b1 = fold_bn(sd, hp + ".bn1")
+    sdn, bdn = fold_bn(sd, hp + ".downsample.1", sd[hp + ".downsample.0.bias"])
+    t, st = _conv_f32(prog, torch.cat([w1, wd], 0), torch.cat([s1, sdn]), torch.cat([b1, bdn]), x, chw, 1, 1, c)
+    prog.release(x)
+    s2, b2 = fold_bn(sd, hp + ".bn2")
+    w2 = sd[hp + ".conv2.weight"].float().permute(0, 2, 3, 1).reshape(-1)  # (co, r, s, ci)
+    prog.head_tail(t, 2 * c, c, chw[1], chw[2], torch.cat([w2, s2, b2]).float(), emb_offset, flags=F32)
+    prog.release(t)
+    return c * chw[1] * chw[2]
+
+
+def add_resnet_basic_f32(prog, sd, layers, in_slot, emb_offset, hw=224):
+    """fp32 counterpart of add_resnet_basic."""
+    x, chw = _stem_f32(prog, sd, in_slot, hw)
+    for li, blocks in enumerate(layers):
+        for b in range(blocks):
+            pre = f"layer{li + 1}.{b}"
+            stride = 2 if (b == 0 and li > 0) else 1
+            t, st = _conv_bn_f32(prog, sd, pre + ".conv1", pre + ".bn1", x, chw, stride, 1, True)
+            if pre + ".downsample.0.weight" in sd:
+                idn, sidn = _conv_bn_f32(prog, sd, pre + ".downsample.0", pre + ".downsample.1", x, chw, stride, 0,
+                                         False)
+                prog.release(x)
+            else:
+                idn, sidn = x, chw
+            y, sy = _conv_bn_f32(prog, sd, pre + ".conv2", pre + ".bn2", t, st, 1, 1, True, res=(idn, sidn[0], 0))
+            prog.release(t)
+            prog.release(idn)
+            x, chw = y, sy
+    prog.avgpool(x, chw[0], chw[1], chw[2], emb_offset, flags=F32)
+    prog.release(x)
+    return chw[0]
+
+
+def add_small_conv_f32(prog, sd, in_slot, emb_offset, hw=224):
+    """fp32 counterpart of add_small_conv (src/embeddings.py:90-106)."""
+    x, chw = in_slot, (4, hw, hw)
+    for i in (0, 2, 4, 6, 8):
+        w = sd[f"{i}.weight"].float()
+        if i == 0:
+            w = _pad_rgb_weight(w)
+        y, chw = _conv_f32(prog, w, torch.ones(32), sd[f"{i}.bias"].float(), x, chw, 2, 1, 0, act=3)
+        if x != in_slot:
+            prog.release(x)
+        x = y
+    prog.flatten(x, 32, chw[1], chw[2], 32, emb_offset, flags=F32)
+    prog.release(x)
+    return 32 * chw[1] * chw[2]
 
 
 # ------------------------------------------------------------------------------------------------ small-conv PVR

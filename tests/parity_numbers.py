@@ -11,8 +11,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import test_gpu_parity as t  # noqa: E402
 
 emb = np.load(os.path.join(ROOT, "tests", "golden", "embeddings.npz"))
-for name in t.VARIANTS:
-    net = t.make_net(name, emb["weight_seeds"])
+for name, mode in [(n, m) for m in ("bf16", "fp32") for n in t.VARIANTS]:
+    net = t.make_net(name, emb["weight_seeds"]).set_precision(mode)
     for tag in ("64", "224"):
         key = f"emb{tag}_{name}"
         if key not in emb.files:
@@ -21,4 +21,4 @@ for name in t.VARIANTS:
         ref = emb[key].astype(np.float64)
         rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
         cos = min(float(np.dot(a, b) / (np.linalg.norm(a) * np.linalg.norm(b))) for a, b in zip(got, ref))
-        print(f"{name:20s} {tag:>3s}x{tag:<3s} rel-L2 {rel:.2e}  min cosine {cos:.6f}")
+        print(f"{name:20s} {mode} {tag:>3s}x{tag:<3s} rel-L2 {rel:.2e}  min cosine {cos:.9f}")

@@ -309,3 +309,58 @@ def test_small_batch_graph_replay_equals_eager(emb):
         net.embed(frames, 1, out)
         want = ref_net.embed(frames)  # fresh output tensor every time: never replayed
         assert torch.equal(out, want), k
+
+
+# ------------------------------------------------------------------------------------------------ fp32 parity mode
+# north star: embeddings within relative L2 <= 1e-5 of the reference "in the fp32 mode" (EmbeddingNet.set_precision)
+FP32_TOL = 1e-5
+
+
+def check_embedding_fp32(got, ref):
+    got, ref = np.atleast_2d(got).astype(np.float64), np.atleast_2d(ref).astype(np.float64)
+    assert got.shape == ref.shape
+    rel = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    rows = np.linalg.norm(got - ref, axis=1) / np.linalg.norm(ref, axis=1)
+    assert rel <= FP32_TOL and rows.max() <= FP32_TOL, (rel, rows.max())
+    return rel
+
+
+@pytest.mark.parametrize("name", list(VARIANTS))
+def test_fp32_mode_embedding_vs_reference_golden(emb, name):
+    net = make_net(name, emb["weight_seeds"]).set_precision("fp32")
+    check_embedding_fp32(net(torch.from_numpy(emb["frames64"])), emb[f"emb64_{name}"])
+    if f"emb224_{name}" in emb:
+        check_embedding_fp32(net(torch.from_numpy(emb["frames224"])), emb[f"emb224_{name}"])
+
+
+def test_fp32_mode_two_frame_observation_and_switching_back(emb):
+    net = make_net("moco_aug_l3", emb["weight_seeds"])
+    obs = torch.from_numpy(emb["obs2"])
+    bf16 = net.embed(obs, n_frames=2).cpu().numpy()
+    fp32 = net.set_precision("fp32").embed(obs, n_frames=2).cpu().numpy()
+    check_embedding_fp32(fp32, emb["emb_obs2_moco_aug_l3"])
+    check_embedding(bf16, fp32)
+    again = net.set_precision("bf16").embed(obs, n_frames=2).cpu().numpy()
+    assert np.array_equal(again, bf16)  # the tensor-core program is rebuilt, bit for bit
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet34"])
+def test_fp32_mode_resnet_basic_vs_reference_golden(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, "resnet_basic.npz"))
+    with allow_random_init():
+        net = EmbeddingNet(name, pretrained=False)
+    net.embedding.load_state_dict(restate.resnet_basic_state(name, int(g[f"seed_{name}"])), strict=True)
+    net.invalidate()
+    net.set_precision("fp32")
+    for tag in ("64", "224"):
+        check_embedding_fp32(net(torch.from_numpy(g["frames" + tag])), g[f"emb{tag}_{name}"])
+
+
+def test_fp32_mode_small_conv_vs_reference_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "small_conv.npz"))
+    net = EmbeddingNet("random", pretrained=False)
+    net.embedding.load_state_dict({k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w_")})
+    net.invalidate()
+    net.set_precision("fp32")
+    for key in ("64", "224"):
+        check_embedding_fp32(net(torch.from_numpy(gold["frames" + key])), gold["emb" + key])

@@ -161,3 +161,82 @@ def test_resnet_basic_program_equals_oracle_network(name, n_ops):
     # the parameter holder has torchvision's keys (checkpoints interchange)
     keys = set(ResNetBasicParams(name).state_dict().keys())
     assert keys == set(sd.keys())
+
+
+# ------------------------------------------------------------------------------------------------ fp32 parity mode
+def _frames4(n, hw, seed):
+    x = torch.randn(n, 3, hw, hw, generator=torch.Generator().manual_seed(seed))
+    x4 = torch.zeros(n, hw, hw, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    return x, x4
+
+
+def _check_f32_program(prog):
+    from pvr_habitat_b200 import _lib
+    live = {}
+    for op in prog.ops:
+        assert op.get("flags", 0) & _lib.PVR_OP_FP32, "every op of an fp32 program carries PVR_OP_FP32"
+        if op["kind"] == _lib.PVR_OP_CONV:
+            assert op["k_pad"] == op["r"] * op["s"] * op["c_in"] and op["c_in"] % 4 == 0 and op["in_pitch"] % 4 == 0
+            assert op["_weight"].dtype == torch.float32 and op["_weight"].shape == (op["c_out"], op["k_pad"])
+            assert op["out_slot"] not in (op["in_slot"], op["res_slot"], 0)
+            # slots count bf16 elements: a float32 tensor needs two per value
+            assert prog.slot_elems[op["out_slot"]] >= 2 * op["h_out"] * op["w_out"] * op["out_pitch"]
+            assert prog.slot_elems[op["in_slot"]] >= 2 * op["h_in"] * op["w_in"] * op["in_pitch"]
+        live[op["out_slot"]] = op
+
+
+@pytest.mark.parametrize("variant,width", [("conv5", 2048), ("l4", 42 * 2 * 2), ("l3", 11 * 4 * 4)])
+def test_fp32_program_equals_oracle_network(variant, width):
+    """The fp32 parity-mode program (PVR_OP_FP32 ops, dense float32 weights) is the oracle network to fp32 rounding."""
+    sd = restate.resnet50_state(variant, 7)
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 64 * 4 * 2)
+    prog.emb_width = prg.add_resnet50_f32(prog, sd, variant, s0, 0, hw=64)
+    assert prog.emb_width == width
+    _check_f32_program(prog)
+    x, x4 = _frames4(2, 64, 0)
+    got = emulate(prog, x4, round_bf16=False)
+    ref = restate.resnet50_forward(sd, variant, x)
+    assert float((got - ref).norm() / ref.norm()) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet34"])
+def test_fp32_resnet_basic_program_equals_oracle_network(name):
+    sd = restate.resnet_basic_state(name, 4)
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 64 * 4 * 2)
+    prog.emb_width = prg.add_resnet_basic_f32(prog, sd, restate.RESNET_BASIC_LAYERS[name], s0, 0, hw=64)
+    _check_f32_program(prog)
+    x, x4 = _frames4(2, 64, 1)
+    got = emulate(prog, x4, round_bf16=False)
+    ref = restate.resnet_basic_forward(sd, name, x)
+    assert float((got - ref).norm() / ref.norm()) <= 1e-5
+
+
+def test_fp32_small_conv_program_equals_oracle(golden_dir):
+    import os
+    gold = np.load(os.path.join(golden_dir, "small_conv.npz"))
+    sd = {k[2:]: torch.from_numpy(gold[k]) for k in gold.files if k.startswith("w_")}
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 64 * 4 * 2)
+    prog.emb_width = prg.add_small_conv_f32(prog, sd, s0, 0, hw=64)
+    _check_f32_program(prog)
+    x, x4 = _frames4(2, 64, 1)
+    got = emulate(prog, x4, round_bf16=False)
+    ref = restate.small_conv_forward(sd, x)
+    assert float((got - ref).norm() / ref.norm()) <= 1e-5
+
+
+def test_set_precision_validates_and_invalidates():
+    with allow_random_init():
+        net = EmbeddingNet("moco_aug", disable_cuda=True)
+    assert net.precision == "bf16"
+    net._encoder = object()
+    assert net.set_precision("fp32") is net and net._encoder is None and net.precision == "fp32"
+    with pytest.raises(ValueError):
+        net.set_precision("fp16")
+    with allow_random_init():
+        clip = EmbeddingNet("clip_vit", disable_cuda=True)
+    with pytest.raises(NotImplementedError):
+        clip.set_precision("fp32")

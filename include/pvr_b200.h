@@ -52,6 +52,9 @@ int pvr_abi_version(void);
 #define PVR_FMT_NHWC4_BF16 1
 #define PVR_FMT_STEM_BF16 2
 #define PVR_FMT_NHWC4_F32 3 /* (n*N, crop, crop, 4) float32, RGB + zero pad: input of the fp32 parity mode */
+/* OR-ed into out_fmt: Resize is bicubic (A = -0.75, no antialias, clamped to [0, 255] before the rounding cast) instead
+ * of bilinear — T.Resize(256, interpolation=3) of the MAE encoders, src/embeddings.py:81. */
+#define PVR_RESIZE_BICUBIC 0x100
 int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int rh, int rw, int top, int left,
                       int crop, const float* mean, const float* stdv, void* out, int out_fmt, int sample_major,
                       void* stream);
@@ -159,7 +162,7 @@ typedef struct pvr_gemm_desc {
   int32_t res_mode;   /* 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward against the saved activation) */
   int32_t out_f32;    /* 0: bf16 out; 1: fp32 out; 2: fp32 out, atomically accumulated (out must hold the addend) */
   int32_t split_k;    /* out_f32 == 2 only: number of K slices computed by separate CTAs */
-  int32_t act;        /* 0: none (or `relu`), 1: ReLU, 2: QuickGELU x*sigmoid(1.702x) (bf16 output) */
+  int32_t act;        /* 0: none (or `relu`), 1: ReLU, 2: QuickGELU x*sigmoid(1.702x), 3: erf GELU (bf16 output) */
   int32_t flags;      /* PVR_GEMM_PDL: launch with programmatic stream serialization (the kernel's prologue overlaps
                          the previous kernel of the stream; it waits for that kernel before touching a / res / out) */
 } pvr_gemm_desc;
@@ -175,10 +178,16 @@ int pvr_gemm(const pvr_gemm_desc* d, void* stream);
  * patch embedding, QKV / projection / MLP matmuls go through pvr_gemm (QuickGELU and the fp32 residual stream are
  * GEMM epilogues); width must be 768 (ViT-B), head_dim 64.
  */
-/* y (rows, width) bf16 = LayerNorm(x[r * row_step]) * gamma + beta; x fp32 (row_step = tokens picks the class token). */
+/* y (rows, width) bf16 = LayerNorm(x[r * row_step]) * gamma + beta; x fp32 (row_step = tokens picks the class token).
+ * width 768 (ViT-B) or 1024 (ViT-L, mae_large). */
 int pvr_layernorm(const float* x, int64_t row_step, int64_t rows, int width, const float* gamma, const float* beta,
                   float eps, void* y_bf16, void* stream);
-/* x_out (n_img*tokens, width) fp32 = ln_pre([class_embedding | patches] + positional_embedding). */
+/* Same with a float32 result (dense rows, ldy == width): the final `norm` of the MAE encoder, whose class-token row IS
+ * the embedding (src/vision_models/mae.py:222, src/embeddings.py:378-379). */
+int pvr_layernorm_f32(const float* x, int64_t row_step, int64_t rows, int width, const float* gamma, const float* beta,
+                      float eps, float* y, int64_t ldy, void* stream);
+/* x_out (n_img*tokens, width) fp32 = ln_pre([class_embedding | patches] + positional_embedding); gamma == beta == NULL:
+ * no LayerNorm (MAE: cls_token + pos_embed[0] | patches + pos_embed[1:], src/vision_models/mae.py:206-217). */
 int pvr_vit_embed(const void* patches_bf16, const float* cls, const float* pos, int n_img, int tokens, int width,
                   const float* gamma, const float* beta, float eps, float* x_out, void* stream);
 /* out (n_img*tokens, width) bf16 = softmax(q k^T / sqrt(64)) v per image and head; qkv (n_img*tokens, 3*width) bf16

@@ -231,12 +231,68 @@ def golden_policy():
     np.savez_compressed(os.path.join(GOLDEN, "policy.npz"), **out)
 
 
+def golden_mae(E):
+    """EmbeddingNet('mae_base' / 'mae_large') of the reference (src/embeddings.py:81,137-144,377-379) on synthetic
+    checkpoints written under the hard-coded file names, plus the uint8 output of its bicubic Resize + CenterCrop.
+
+    torchvision 0.26 would antialias the bicubic resize (default antialias=True, a different filter: A = -0.5); the
+    reference pins torchvision 0.10 whose tensor path has no antialiasing, so the constructed Resize module gets
+    `antialias = False` — an attribute of the torchvision object, no reference code is touched."""
+    from oracle import restate_mae
+    out = {}
+    cases = {
+        "structured_64": restate.structured_frames(2, 64, 64, 3, 41),
+        "structured_224": restate.structured_frames(2, 224, 224, 3, 42),
+        "structured_96x128": restate.structured_frames(1, 96, 128, 3, 43),
+        "noise_224": np.random.default_rng(44).integers(0, 256, (1, 224, 224, 3), dtype=np.uint8),
+        "adversarial_64": restate.adversarial_frames(64, 64),
+    }
+    frames224 = restate.structured_frames(2, 224, 224, 3, 45)
+    frames64 = restate.structured_frames(3, 64, 64, 3, 46)
+    out.update(frames224=frames224, frames64=frames64)
+    seeds = {"mae_base": 201, "mae_large": 202}
+    for name, seed in seeds.items():
+        sd = restate_mae.mae_state(name, seed)
+        with tempfile.TemporaryDirectory() as d, refshim.chdir(d):
+            torch.save({"model": sd}, os.path.join(d, restate_mae.CHECKPOINTS[name]))
+            torch.manual_seed(7)  # random_masking draws torch.rand even at mask_ratio 0
+            net = E.EmbeddingNet(name, pretrained=True, train=False, disable_cuda=True)
+        net.transforms[0].antialias = False
+        out[f"seed_{name}"] = np.array(seed)
+        out[f"out_size_{name}"] = np.array(int(net.out_size))
+        out[f"emb224_{name}"] = net(torch.from_numpy(frames224))
+        out[f"emb64_{name}"] = net(torch.from_numpy(frames64))
+        if name == "mae_base":
+            resize_crop = torch.nn.Sequential(net.transforms[0], net.transforms[1])
+            for cname, frames in cases.items():
+                x = torch.from_numpy(frames).permute(0, 3, 1, 2).contiguous()
+                u = resize_crop(x)
+                assert u.dtype == torch.uint8
+                out["in_" + cname] = frames
+                out["u8_" + cname] = u.numpy()
+        print(name, out[f"out_size_{name}"], np.abs(out[f"emb224_{name}"]).mean())
+    # the reference's random initialisation (mae.py:117-146) under a fixed torch seed: slices of a few tensors pin the
+    # order of the random draws that the drop-in parameter container has to reproduce
+    from src.vision_models.mae import mae_vit_base_patch16
+    torch.manual_seed(9)
+    ref = mae_vit_base_patch16().state_dict()
+    out["init_keys"] = np.array(sorted(ref.keys()))
+    for k in ("cls_token", "mask_token", "patch_embed.proj.weight", "blocks.0.attn.qkv.weight",
+              "blocks.11.mlp.fc2.weight", "decoder_blocks.7.mlp.fc1.weight", "decoder_pred.weight", "pos_embed",
+              "decoder_pos_embed"):
+        out["init_" + k] = ref[k].reshape(-1)[:: max(1, ref[k].numel() // 64)][:64].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "mae.npz"), **out)
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
-    if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which:
+    if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which or \
+            "mae" in which:
         E = refshim.reference_embeddings()
+        if "mae" in which:
+            golden_mae(E)
         if "resnet_basic" in which:
             golden_resnet_basic(E)
         if "transforms" in which:

@@ -1,9 +1,11 @@
 """ORACLE (build container only) — import the UNMODIFIED reference from /root/reference.
 
 The reference needs gym / detectron2 / timm / habitat at import time (src/embeddings.py:2-3,
-src/vision_models/maskrcnn.py:2-20, src/vision_models/mae.py:20); none is installed and none is on the hot path, so
-they are replaced by inert stub modules. Checkpoint-backed encoders (src/embeddings.py:151-236) read hard-coded
-relative paths: `write_checkpoints` writes synthetic checkpoints under those names into a scratch directory and the
+src/vision_models/maskrcnn.py:2-20, src/vision_models/mae.py:20); none is installed. gym / detectron2 are not on the
+hot path and are replaced by inert stub modules; `timm.models.vision_transformer` (mae.py:20 needs PatchEmbed and Block
+to build the MAE encoders) is served by the restatement of timm 0.5.4 in oracle/restate_mae.py. `np.float`, which
+mae.py:58 still uses, left numpy in 1.24: it is restored as the alias of `float` it used to be.
+Checkpoint-backed encoders (src/embeddings.py:151-236) read hard-coded relative paths: `write_checkpoints` writes synthetic checkpoints under those names into a scratch directory and the
 constructors run from there, so no reference code is patched.
 This file is never imported on the GPU box (/root/reference does not exist there).
 """
@@ -48,9 +50,16 @@ def install_stubs():
                  "detectron2.modeling.meta_arch", "detectron2.modeling.anchor_generator",
                  "detectron2.modeling.backbone", "detectron2.modeling.backbone.resnet",
                  "detectron2.modeling.box_regression", "detectron2.modeling.matcher", "detectron2.modeling.poolers",
-                 "detectron2.modeling.proposal_generator", "detectron2.modeling.roi_heads", "timm", "timm.models",
-                 "timm.models.vision_transformer"):
+                 "detectron2.modeling.proposal_generator", "detectron2.modeling.roi_heads", "timm", "timm.models"):
         sys.modules.setdefault(name, _Anything(name))
+    if "timm.models.vision_transformer" not in sys.modules:
+        import numpy as np
+        from oracle import restate_mae
+        vt = types.ModuleType("timm.models.vision_transformer")
+        vt.PatchEmbed, vt.Block = restate_mae.PatchEmbed, restate_mae.Block
+        sys.modules["timm.models.vision_transformer"] = vt
+        if not hasattr(np, "float"):
+            np.float = float
 
 
 def reference_embeddings():

@@ -72,7 +72,67 @@ def resize_bilinear_f32(frames_nchw_u8, rh, rw):
     return _lerp(top_, hy[:, None], bot_, ly[:, None])
 
 
-def resize_crop_u8(frames_nchw_u8, size=256, crop=224):
+def _cubic_src_index(scale, dst, size):
+    """ATen area_pixel_compute_source_index(align_corners=False, cubic=True): no clamp at zero; then
+    guard_index_and_lambda (floor, index <= size-1, lambda clipped to [0, 1])."""
+    f32 = np.float32
+    d = dst.astype(f32) + f32(0.5)
+    s = _fma(np.full_like(d, f32(scale)), d, np.full_like(d, f32(-0.5)))
+    idx = np.minimum(np.floor(s).astype(np.int64), size - 1)
+    lam = np.clip((s - idx.astype(f32)).astype(f32), f32(0), f32(1)).astype(f32)
+    return idx, lam
+
+
+def _cubic_coefficients(t):
+    """ATen get_cubic_upsample_coefficients (A = -0.75) as compiled for x86 (probed bit-exact against
+    F.interpolate on dyadic and non-dyadic sizes, see tests/test_oracle_golden.py):
+      cubic_convolution1(x) = ((A+2)x - (A+3)) x x + 1        -> fma(1.25, x, -2.25), two rounded products, rounded + 1
+      cubic_convolution2(x) = ((A x - 5A) x + 8A) x - 4A      -> fma(fma(-0.75, x, 3.75), x, -6), rounded product, + 3
+    """
+    f32 = np.float32
+
+    def cc1(x):
+        t1 = _fma(np.full_like(x, f32(1.25)), x, np.full_like(x, f32(-2.25)))
+        return (((t1 * x).astype(f32) * x).astype(f32) + f32(1)).astype(f32)
+
+    def cc2(x):
+        t1 = _fma(np.full_like(x, f32(-0.75)), x, np.full_like(x, f32(3.75)))
+        t2 = _fma(t1, x, np.full_like(x, f32(-6)))
+        return ((t2 * x).astype(f32) + f32(3)).astype(f32)
+
+    x1 = t.astype(f32)
+    x2 = (f32(1) - x1).astype(f32)
+    return [cc2((x1 + f32(1)).astype(f32)), cc1(x1), cc1(x2), cc2((x2 + f32(1)).astype(f32))]
+
+
+def _cubic_sum(t, w):
+    """ATen Interpolate<>::eval with four taps as compiled for x86 FMA:
+    fma(t3, w3, fma(t2, w2, fma(t0, w0, round(t1 * w1))))."""
+    w = [np.broadcast_to(wk, t[0].shape).astype(np.float32) for wk in w]
+    o = _fma(t[0], w[0], (t[1] * w[1]).astype(np.float32))
+    o = _fma(t[2], w[2], o)
+    return _fma(t[3], w[3], o)
+
+
+def resize_bicubic_f32(frames_nchw_u8, rh, rw):
+    """float32 bicubic resize (align_corners=False, no antialias, A = -0.75) of uint8 NCHW frames before clamping /
+    rounding: bit-exact with torch.nn.functional.interpolate(mode='bicubic') on CPU. Border taps are clamped
+    (upsample_get_value_bounded)."""
+    x = np.asarray(frames_nchw_u8)
+    n, c, h, w = x.shape
+    f32 = np.float32
+    iy, ly = _cubic_src_index(f32(h) / f32(rh), np.arange(rh), h)
+    ix, lx = _cubic_src_index(f32(w) / f32(rw), np.arange(rw), w)
+    wy, wx = _cubic_coefficients(ly), _cubic_coefficients(lx)
+    xf = x.astype(f32)
+    rows = []
+    for j in range(4):
+        r = xf[:, :, np.clip(iy + j - 1, 0, h - 1), :]
+        rows.append(_cubic_sum([r[..., np.clip(ix + k - 1, 0, w - 1)] for k in range(4)], wx))
+    return _cubic_sum(rows, [wk[:, None] for wk in wy])
+
+
+def resize_crop_u8(frames_nchw_u8, size=256, crop=224, interpolation="bilinear"):
     """Resize(256) + CenterCrop(224) on uint8 NCHW frames, bit-for-bit torchvision-0.10 semantics.
 
     Reference: src/embeddings.py:81-82. torchvision resizes uint8 tensors by casting to float32, bilinear
@@ -85,7 +145,12 @@ def resize_crop_u8(frames_nchw_u8, size=256, crop=224):
     """
     x = np.asarray(frames_nchw_u8)
     rh, rw, top, left = resize_geometry(x.shape[2], x.shape[3], size, crop)
-    v = resize_bilinear_f32(x, rh, rw)[:, :, top:top + crop, left:left + crop]
+    if interpolation == "bicubic":
+        # T.Resize(256, interpolation=3) of the MAE encoders (src/embeddings.py:81): bicubic overshoots, torchvision
+        # clamps to [0, 255] before the rounding cast (tv:transforms/_functional_tensor.py:469-470)
+        v = resize_bicubic_f32(x, rh, rw)[:, :, top:top + crop, left:left + crop]
+    else:
+        v = resize_bilinear_f32(x, rh, rw)[:, :, top:top + crop, left:left + crop]
     return np.clip(np.rint(v), 0, 255).astype(np.uint8)  # np.rint = half to even = torch.round
 
 
@@ -99,9 +164,9 @@ def normalize_lut(mean=IMAGENET_MEAN, std=IMAGENET_STD):
     return ((u[None, :] - m) / s).astype(f32)  # (3, 256)
 
 
-def transforms(frames_nchw_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+def transforms(frames_nchw_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD, interpolation="bilinear"):
     """Full reference `transforms` (src/embeddings.py:80-85) on (N,3,H,W) uint8 -> (N,3,224,224) float32."""
-    u = resize_crop_u8(frames_nchw_u8)
+    u = resize_crop_u8(frames_nchw_u8, interpolation=interpolation)
     lut = normalize_lut(mean, std)
     return np.stack([lut[c][u[:, c]] for c in range(3)], 1)
 

@@ -9,6 +9,7 @@ PVR_FMT_NCHW_F32 = 0
 PVR_FMT_NHWC4_BF16 = 1
 PVR_FMT_STEM_BF16 = 2
 PVR_FMT_NHWC4_F32 = 3
+PVR_RESIZE_BICUBIC = 0x100
 PVR_OP_FP32 = 2
 PVR_CONV_OUT_F32 = 1
 PVR_GEMM_PDL, PVR_GEMM_MN = 1, 2
@@ -73,6 +74,7 @@ _SIGNATURES = {
     "pvr_encoder_destroy": (None, [ctypes.c_void_p]),
     "pvr_gemm": (ctypes.c_int, [ctypes.POINTER(pvr_gemm_desc), ctypes.c_void_p]),
     "pvr_layernorm": (ctypes.c_int, [_vp, _i64, _i64, _i, _vp, _vp, _f, _vp, _vp]),
+    "pvr_layernorm_f32": (ctypes.c_int, [_vp, _i64, _i64, _i, _vp, _vp, _f, _vp, _i64, _vp]),
     "pvr_vit_embed": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "pvr_attention": (ctypes.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "pvr_bn1d_stats": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp]),

@@ -752,7 +752,7 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   p.ldo = d->ldo;
   p.ldr = d->ldr;
   p.res_mode = d->res_mode;
-  p.quick_gelu = d->act == 2;
+  p.quick_gelu = d->act == 2 ? 1 : (d->act == 3 ? 2 : 0);
   p.out_is_f32 = d->out_f32 != 0;
   p.out = static_cast<__nv_bfloat16*>(d->out);
   p.out_f32 = static_cast<float*>(d->out);

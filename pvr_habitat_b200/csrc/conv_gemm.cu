@@ -502,9 +502,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               // full-width ReLU is applied on the packed bf16 pairs below (max commutes with the rounding)
               const bool packed_relu = n + h * 32 + 32 <= p.relu_n;
               if (!packed_relu) relu_cols(f, n + h * 32, p.relu_n);
-              if (p.quick_gelu) {  // CLIP's QuickGELU: x * sigmoid(1.702 x)
+              if (p.quick_gelu == 1) {  // CLIP's QuickGELU: x * sigmoid(1.702 x)
 #pragma unroll
                 for (int jj = 0; jj < 32; ++jj) f[jj] = __fdividef(f[jj], 1.f + __expf(-1.702f * f[jj]));
+              } else if (p.quick_gelu == 2) {  // nn.GELU (erf form) of the timm blocks MAE is built from
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) f[jj] = 0.5f * f[jj] * (1.f + erff(f[jj] * 0.70710678118654752f));
               }
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {

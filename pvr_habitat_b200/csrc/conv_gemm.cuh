@@ -31,7 +31,7 @@ struct ConvGemmParams {
   int relu_n;        // ReLU is applied to output columns < relu_n (0: none, >= n_valid: all)
   int has_res;       // residual present (EPI_TMA path reads it through tmap_res)
   int elu;           // ELU(alpha = 1) on every output channel (direct epilogue; small-conv PVR)
-  int quick_gelu;    // bf16 output: x * sigmoid(1.702 x) after bias (CLIP MLP)
+  int quick_gelu;    // bf16 output, after bias: 1 = x * sigmoid(1.702 x) (CLIP MLP), 2 = erf GELU (MAE / timm MLP)
   int res_mode;      // 0: out += res; 1: out = res > 0 ? out : 0 (ReLU backward with the saved activation)
   int reverse;       // 1: walk the (m, n) tiles last to first (zig-zag over consecutive layers, L2 reuse)
   int pdl;           // 1: launch with programmatic stream serialization (prologue overlaps the previous kernel)

@@ -43,6 +43,56 @@ __device__ __forceinline__ void src_index(float scale, int dst, int size, int& i
   l = fminf(fmaxf(l, 0.f), 1.f);
 }
 
+// Bicubic (A = -0.75, align_corners=False, no antialias): T.Resize(256, interpolation=3) of the MAE encoders
+// (src/embeddings.py:81). Index, coefficient and summation arithmetic follow the x86 build of ATen operation by
+// operation (which products are fused is probed bit-exact in oracle/restate.py:_cubic_coefficients / _cubic_sum).
+__device__ __forceinline__ float cubic_cc1(float x) {  // ((A+2)x - (A+3)) x x + 1
+  const float t1 = __fmaf_rn(1.25f, x, -2.25f);
+  return __fadd_rn(__fmul_rn(__fmul_rn(t1, x), x), 1.f);
+}
+__device__ __forceinline__ float cubic_cc2(float x) {  // ((A x - 5A) x + 8A) x - 4A
+  const float t2 = __fmaf_rn(__fmaf_rn(-0.75f, x, 3.75f), x, -6.f);
+  return __fadd_rn(__fmul_rn(t2, x), 3.f);
+}
+__device__ __forceinline__ void cubic_index(float scale, int dst, int size, int& i0, float w[4]) {
+  const float s = __fmaf_rn(scale, (float)dst + 0.5f, -0.5f);  // cubic: not clamped at zero
+  i0 = (int)floorf(s);
+  if (i0 > size - 1) i0 = size - 1;
+  float t = __fsub_rn(s, (float)i0);
+  t = fminf(fmaxf(t, 0.f), 1.f);
+  const float x2 = __fsub_rn(1.f, t);
+  w[0] = cubic_cc2(__fadd_rn(t, 1.f));
+  w[1] = cubic_cc1(t);
+  w[2] = cubic_cc1(x2);
+  w[3] = cubic_cc2(__fadd_rn(x2, 1.f));
+}
+__device__ __forceinline__ float cubic_sum(float t0, float t1, float t2, float t3, const float w[4]) {
+  return __fmaf_rn(t3, w[3], __fmaf_rn(t2, w[2], __fmaf_rn(t0, w[0], __fmul_rn(t1, w[1]))));
+}
+// one output pixel, 3 channels starting at byte `ch` of the staged HWC rows (row r of the image = s + (r - r_lo) * row_bytes)
+__device__ __forceinline__ void cubic_pixel(const PreParams& p, const uint8_t* s, int r_lo, long long row_bytes, int iy,
+                                            const float wy[4], int ix, const float wx[4], int ch, const float* lut,
+                                            float o[3]) {
+  int col[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) col[k] = min(max(ix + k - 1, 0), p.W - 1) * p.CH + ch;
+  float rows[3][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint8_t* r = s + (long long)(min(max(iy + j - 1, 0), p.H - 1) - r_lo) * row_bytes;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      rows[c][j] = cubic_sum((float)r[col[0] + c], (float)r[col[1] + c], (float)r[col[2] + c], (float)r[col[3] + c], wx);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = cubic_sum(rows[c][0], rows[c][1], rows[c][2], rows[c][3], wy);
+    v = fminf(fmaxf(v, 0.f), 255.f);  // torchvision clamps the overshoot before the rounding cast
+    o[c] = lut[c * 256 + (int)rintf(v)];
+  }
+}
+
+template <bool CUBIC>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
@@ -57,8 +107,16 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
   // input row range of this band
   int r_lo, r_hi, tmp;
   float lf;
-  src_index(p.scale_y, y_first + p.top, p.H, r_lo, tmp, lf);
-  src_index(p.scale_y, y_first + y_count - 1 + p.top, p.H, tmp, r_hi, lf);
+  if (CUBIC) {
+    float wtmp[4];
+    cubic_index(p.scale_y, y_first + p.top, p.H, r_lo, wtmp);
+    cubic_index(p.scale_y, y_first + y_count - 1 + p.top, p.H, r_hi, wtmp);
+    r_lo = max(r_lo - 1, 0);
+    r_hi = min(r_hi + 2, p.H - 1);
+  } else {
+    src_index(p.scale_y, y_first + p.top, p.H, r_lo, tmp, lf);
+    src_index(p.scale_y, y_first + y_count - 1 + p.top, p.H, tmp, r_hi, lf);
+  }
   const long long row_bytes = (long long)p.W * p.CH;
   const long long g0 = (long long)img * p.H * row_bytes + (long long)r_lo * row_bytes;
   const long long nbytes = (long long)(r_hi - r_lo + 1) * row_bytes;
@@ -102,24 +160,32 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
       for (int idx = threadIdx.x; idx < npix; idx += blockDim.x) {
         const int yy = idx / p.crop;
         const int x = idx - yy * p.crop;
-        int r0, r1, c0, c1;
-        float ly, lx;
-        src_index(p.scale_y, y_first + yy + p.top, p.H, r0, r1, ly);
-        src_index(p.scale_x, x + p.left, p.W, c0, c1, lx);
-        const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
-        const uint8_t* q00 = s + (long long)(r0 - r_lo) * row_bytes + c0 * p.CH + 3 * f;
-        const uint8_t* q01 = s + (long long)(r0 - r_lo) * row_bytes + c1 * p.CH + 3 * f;
-        const uint8_t* q10 = s + (long long)(r1 - r_lo) * row_bytes + c0 * p.CH + 3 * f;
-        const uint8_t* q11 = s + (long long)(r1 - r_lo) * row_bytes + c1 * p.CH + 3 * f;
         float o[3];
+        if (CUBIC) {
+          int iy, ix;
+          float wy[4], wx[4];
+          cubic_index(p.scale_y, y_first + yy + p.top, p.H, iy, wy);
+          cubic_index(p.scale_x, x + p.left, p.W, ix, wx);
+          cubic_pixel(p, s, r_lo, row_bytes, iy, wy, ix, wx, 3 * f, lut, o);
+        } else {
+          int r0, r1, c0, c1;
+          float ly, lx;
+          src_index(p.scale_y, y_first + yy + p.top, p.H, r0, r1, ly);
+          src_index(p.scale_x, x + p.left, p.W, c0, c1, lx);
+          const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
+          const uint8_t* q00 = s + (long long)(r0 - r_lo) * row_bytes + c0 * p.CH + 3 * f;
+          const uint8_t* q01 = s + (long long)(r0 - r_lo) * row_bytes + c1 * p.CH + 3 * f;
+          const uint8_t* q10 = s + (long long)(r1 - r_lo) * row_bytes + c0 * p.CH + 3 * f;
+          const uint8_t* q11 = s + (long long)(r1 - r_lo) * row_bytes + c1 * p.CH + 3 * f;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float top = __fmaf_rn((float)q00[c], hx, __fmul_rn((float)q01[c], lx));
-          const float bot = __fmaf_rn((float)q10[c], hx, __fmul_rn((float)q11[c], lx));
-          const float v = __fmaf_rn(top, hy, __fmul_rn(bot, ly));
-          int u = (int)rintf(v);
-          u = min(max(u, 0), 255);
-          o[c] = lut[c * 256 + u];
+          for (int c = 0; c < 3; ++c) {
+            const float top = __fmaf_rn((float)q00[c], hx, __fmul_rn((float)q01[c], lx));
+            const float bot = __fmaf_rn((float)q10[c], hx, __fmul_rn((float)q11[c], lx));
+            const float v = __fmaf_rn(top, hy, __fmul_rn(bot, ly));
+            int u = (int)rintf(v);
+            u = min(max(u, 0), 255);
+            o[c] = lut[c * 256 + u];
+          }
         }
         __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
         __nv_bfloat162 b = __floats2bfloat162_rn(o[2], 0.f);
@@ -144,10 +210,15 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
     const int yy = idx / p.crop;
     const int x = idx - yy * p.crop;
     const int y = y_first + yy;
-    int r0, r1, c0, c1;
-    float ly, lx;
-    src_index(p.scale_y, y + p.top, p.H, r0, r1, ly);
-    src_index(p.scale_x, x + p.left, p.W, c0, c1, lx);
+    int r0 = 0, r1 = 0, c0 = 0, c1 = 0;
+    float ly = 0.f, lx = 0.f, wy[4], wx[4];
+    if (CUBIC) {
+      cubic_index(p.scale_y, y + p.top, p.H, r0, wy);
+      cubic_index(p.scale_x, x + p.left, p.W, c0, wx);
+    } else {
+      src_index(p.scale_y, y + p.top, p.H, r0, r1, ly);
+      src_index(p.scale_x, x + p.left, p.W, c0, c1, lx);
+    }
     const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
     const uint8_t* q00 = s + (long long)(r0 - r_lo) * row_bytes + c0 * p.CH;
     const uint8_t* q01 = s + (long long)(r0 - r_lo) * row_bytes + c1 * p.CH;
@@ -155,8 +226,9 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
     const uint8_t* q11 = s + (long long)(r1 - r_lo) * row_bytes + c1 * p.CH;
     for (int f = 0; f < p.nf; ++f) {
       float o[3];
+      if (CUBIC) cubic_pixel(p, s, r_lo, row_bytes, r0, wy, c0, wx, 3 * f, lut, o);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+      for (int c = 0; c < 3 && !CUBIC; ++c) {
         const int ch = 3 * f + c;
         // ATen Interpolate<>::eval as compiled for x86: fma(t0, w0, round(t1 * w1)) per dimension
         const float top = __fmaf_rn((float)q00[ch], hx, __fmul_rn((float)q01[ch], lx));
@@ -197,6 +269,8 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
                                  int left, int crop, const float* mean, const float* stdv, void* out, int out_fmt,
                                  int sample_major, void* stream) {
   using namespace pvr;
+  const bool cubic = (out_fmt & PVR_RESIZE_BICUBIC) != 0;
+  out_fmt &= ~PVR_RESIZE_BICUBIC;
   if (!in || !out || N <= 0 || H <= 0 || W <= 0 || n_frames <= 0 || rh <= 0 || rw <= 0 || crop <= 0 || top < 0 ||
       left < 0 || top + crop > rh || left + crop > rw || !mean || !stdv ||
       (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16 && out_fmt != PVR_FMT_STEM_BF16 &&
@@ -223,7 +297,7 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   // rows per band: keep the staged input under ~48 KiB so several CTAs share an SM
   const long long row_bytes = (long long)W * p.CH;
   int rows = 16;
-  auto stage_bytes = [&](int r) { return ((long long)(p.scale_y * r) + 3) * row_bytes + 48; };
+  auto stage_bytes = [&](int r) { return ((long long)(p.scale_y * r) + (cubic ? 5 : 3)) * row_bytes + 48; };
   while (rows > 1 && stage_bytes(rows) > 48 * 1024) rows >>= 1;
   long long smem = 16 + 3072 + stage_bytes(rows);
   p.pix_off = 0;
@@ -238,7 +312,9 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   p.rows = rows;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(preprocess_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) { pvr_set_error("pvr_preprocess_u8: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
     attr = true;
   }
@@ -248,7 +324,8 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
     return PVR_ERR_ARG;
   }
   dim3 grid((unsigned)(p.bands * N));
-  preprocess_kernel<<<grid, 256, (size_t)smem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (cubic) preprocess_kernel<true><<<grid, 256, (size_t)smem, static_cast<cudaStream_t>(stream)>>>(p);
+  else preprocess_kernel<false><<<grid, 256, (size_t)smem, static_cast<cudaStream_t>(stream)>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { pvr_set_error("pvr_preprocess_u8: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
   return PVR_OK;

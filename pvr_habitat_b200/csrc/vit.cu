@@ -30,6 +30,7 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 // One warp per token row. W % 128 == 0 (each lane owns W/32 values as float4 groups).
 // mode 0: x = LN(src fp32 row)                      -> bf16 (ln_1 / ln_2 / ln_post)
 // mode 1: x = LN([cls | patch] + pos) (ln_pre)      -> fp32 residual stream
+// mode 2: x = [cls | patch] + pos                    -> fp32 residual stream (MAE, mae.py:209-217: no ln_pre)
 template <int W>
 __global__ void __launch_bounds__(256) vit_layernorm_kernel(const float* __restrict__ src, long long src_row_step,
                                                              const __nv_bfloat16* __restrict__ patches,
@@ -68,6 +69,13 @@ __global__ void __launch_bounds__(256) vit_layernorm_kernel(const float* __restr
       }
       v[4 * i] = t.x + pe.x; v[4 * i + 1] = t.y + pe.y; v[4 * i + 2] = t.z + pe.z; v[4 * i + 3] = t.w + pe.w;
     }
+  }
+  if (mode == 2) {  // MAE: [cls | patch] + pos goes to the residual stream as it is (no ln_pre)
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i)
+      *reinterpret_cast<float4*>(out_f32 + row * W + (i * 32 + lane) * 4) =
+          make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    return;
   }
   float s = 0.f;
 #pragma unroll
@@ -349,31 +357,62 @@ vit_attention_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
 }  // namespace
 }  // namespace pvr
 
+namespace pvr {
+namespace {
+template <int W>
+cudaError_t launch_ln(const float* src, long long row_step, const __nv_bfloat16* patches, const float* cls,
+                      const float* pos, int tokens, const float* gamma, const float* beta, float eps, long long rows,
+                      float* out_f32, __nv_bfloat16* out_bf16, int mode, cudaStream_t stream) {
+  vit_layernorm_kernel<W><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(src, row_step, patches, cls, pos, tokens, gamma,
+                                                                          beta, eps, rows, out_f32, out_bf16, mode);
+  return cudaGetLastError();
+}
+// widths: 768 (ViT-B: CLIP, mae_base), 1024 (ViT-L: mae_large)
+cudaError_t dispatch_ln(int width, const float* src, long long row_step, const __nv_bfloat16* patches, const float* cls,
+                        const float* pos, int tokens, const float* gamma, const float* beta, float eps, long long rows,
+                        float* out_f32, __nv_bfloat16* out_bf16, int mode, cudaStream_t stream) {
+  if (width == 768)
+    return launch_ln<768>(src, row_step, patches, cls, pos, tokens, gamma, beta, eps, rows, out_f32, out_bf16, mode, stream);
+  return launch_ln<1024>(src, row_step, patches, cls, pos, tokens, gamma, beta, eps, rows, out_f32, out_bf16, mode, stream);
+}
+}  // namespace
+}  // namespace pvr
+
 extern "C" int pvr_layernorm(const float* x, int64_t row_step, int64_t rows, int width, const float* gamma,
                              const float* beta, float eps, void* y_bf16, void* stream) {
-  if (!x || !gamma || !beta || !y_bf16 || rows <= 0 || width != 768 || row_step <= 0) {
-    pvr_set_error("pvr_layernorm: invalid argument (width must be 768)");
+  if (!x || !gamma || !beta || !y_bf16 || rows <= 0 || (width != 768 && width != 1024) || row_step <= 0) {
+    pvr_set_error("pvr_layernorm: invalid argument (width must be 768 or 1024)");
     return PVR_ERR_ARG;
   }
-  pvr::vit_layernorm_kernel<768><<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, row_step, nullptr, nullptr, nullptr, 1, gamma, beta, eps, rows, nullptr, static_cast<__nv_bfloat16*>(y_bf16),
-      0);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = pvr::dispatch_ln(width, x, row_step, nullptr, nullptr, nullptr, 1, gamma, beta, eps, rows, nullptr,
+                                   static_cast<__nv_bfloat16*>(y_bf16), 0, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { pvr_set_error("pvr_layernorm: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
+  return PVR_OK;
+}
+
+extern "C" int pvr_layernorm_f32(const float* x, int64_t row_step, int64_t rows, int width, const float* gamma,
+                                 const float* beta, float eps, float* y, int64_t ldy, void* stream) {
+  if (!x || !gamma || !beta || !y || rows <= 0 || (width != 768 && width != 1024) || row_step <= 0 || ldy != width) {
+    pvr_set_error("pvr_layernorm_f32: invalid argument (width must be 768 or 1024, dense output rows)");
+    return PVR_ERR_ARG;
+  }
+  cudaError_t e = pvr::dispatch_ln(width, x, row_step, nullptr, nullptr, nullptr, 1, gamma, beta, eps, rows, y, nullptr,
+                                   0, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) { pvr_set_error("pvr_layernorm_f32: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
   return PVR_OK;
 }
 
 extern "C" int pvr_vit_embed(const void* patches_bf16, const float* cls, const float* pos, int n_img, int tokens,
                              int width, const float* gamma, const float* beta, float eps, float* x_out, void* stream) {
-  if (!patches_bf16 || !cls || !pos || !gamma || !beta || !x_out || n_img <= 0 || tokens <= 1 || width != 768) {
-    pvr_set_error("pvr_vit_embed: invalid argument (width must be 768)");
+  if (!patches_bf16 || !cls || !pos || (!gamma != !beta) || !x_out || n_img <= 0 || tokens <= 1 ||
+      (width != 768 && width != 1024)) {
+    pvr_set_error("pvr_vit_embed: invalid argument (width must be 768 or 1024)");
     return PVR_ERR_ARG;
   }
   const long long rows = (long long)n_img * tokens;
-  pvr::vit_layernorm_kernel<768><<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      nullptr, 1, static_cast<const __nv_bfloat16*>(patches_bf16), cls, pos, tokens, gamma, beta, eps, rows, x_out,
-      nullptr, 1);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = pvr::dispatch_ln(width, nullptr, 1, static_cast<const __nv_bfloat16*>(patches_bf16), cls, pos, tokens,
+                                   gamma, beta, eps, rows, x_out, nullptr, gamma ? 1 : 2,
+                                   static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) { pvr_set_error("pvr_vit_embed: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
   return PVR_OK;
 }

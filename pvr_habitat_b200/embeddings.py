@@ -14,6 +14,7 @@ from torch import nn
 from . import _lib
 from . import program as prg
 from .vision_models import clip_vit
+from .vision_models import mae as mae_vit
 from .vision_models.moco import moco_conv3_compressed, moco_conv4_compressed, moco_conv5
 from .vision_models.resnet import resnet_conv3_compressed, resnet_conv4_compressed, resnet_conv5
 from .vision_models.resnet_params import ResNet50Params, ResNetBasicParams
@@ -40,9 +41,11 @@ class Transforms(nn.Module):
     NCHW float32 tensor the reference's nn.Sequential of torchvision transforms returns, bit for bit.
     """
 
-    def __init__(self, mean=IMAGENET_MEAN, std=IMAGENET_STD, size=256, crop=224):
+    def __init__(self, mean=IMAGENET_MEAN, std=IMAGENET_STD, size=256, crop=224, interpolation='bilinear'):
         super().__init__()
         self.mean, self.std, self.size, self.crop = list(mean), list(std), size, crop
+        assert interpolation in ('bilinear', 'bicubic')
+        self.interpolation = interpolation  # 'bicubic': T.Resize(256, interpolation=3) of the MAE encoders
         self.identity_resize_only = False  # CLIP: bicubic antialiased Resize is only supported when it is a no-op
 
     def run(self, obs_nhwc_u8, n_frames, out_ptr, fmt, sample_major):
@@ -55,6 +58,8 @@ class Transforms(nn.Module):
         rh, rw, top, left = resize_geometry(h, w, self.size, self.crop)
         mean = (ctypes.c_float * 3)(*self.mean)
         std = (ctypes.c_float * 3)(*self.std)
+        if self.interpolation == 'bicubic':
+            fmt |= _lib.PVR_RESIZE_BICUBIC
         with torch.cuda.device(obs_nhwc_u8.device):
             _lib.check(_lib.lib().pvr_preprocess_u8(obs_nhwc_u8.data_ptr(), n, h, w, n_frames, rh, rw, top, left,
                                                     self.crop, mean, std, out_ptr, fmt, int(sample_major),
@@ -166,6 +171,10 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
                 taps not in ('345', '35', '34', '45'):
             raise NotImplementedError("Requested model not available.")
         model = UberModel([_get_embedding(base + _UBER_PARTS[t])[0] for t in taps])
+    elif embedding_name in ('mae_base', 'mae_large', 'mae_huge'):
+        # src/embeddings.py:137-148; MAE frames are resized with bicubic interpolation (src/embeddings.py:81)
+        model = mae_vit.load(embedding_name)
+        transforms = Transforms(IMAGENET_MEAN, IMAGENET_STD, interpolation='bicubic')
     elif 'clip' in embedding_name:
         # src/embeddings.py:298-314: clip.load("ViT-B/32") + CLIP's own normalisation. Resize(224, bicubic) and
         # CenterCrop(224) are the identity for the 224x224 frames of the north-star configs; other sizes would need
@@ -182,7 +191,7 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
     elif embedding_name == 'true_state':
         return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
     else:
-        # mae_*, clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
+        # clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
         raise NotImplementedError("Requested model not available.")
 
     if train:
@@ -270,8 +279,8 @@ class EmbeddingNet(nn.Module):
         small-conv encoders). The constructor signature stays the reference's, hence a setter."""
         if precision not in ('bf16', 'fp32'):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
-        if precision == 'fp32' and isinstance(self.embedding, clip_vit.CLIPImageModel):
-            raise NotImplementedError("the fp32 parity mode covers the ResNet / small-conv encoders, not CLIP ViT")
+        if precision == 'fp32' and isinstance(self.embedding, (clip_vit.CLIPImageModel, mae_vit.MAEParams)):
+            raise NotImplementedError("the fp32 parity mode covers the ResNet / small-conv encoders, not the ViTs")
         if precision != self.precision:
             self.precision = precision
             self._encoder = None
@@ -294,7 +303,7 @@ class EmbeddingNet(nn.Module):
     def encoder(self):
         self._require_cuda()
         if self._encoder is None:
-            if isinstance(self.embedding, clip_vit.CLIPImageModel):
+            if isinstance(self.embedding, (clip_vit.CLIPImageModel, mae_vit.MAEParams)):
                 self.embedding.invalidate()
                 self._encoder = self.embedding.runner(self.device)
             else:

@@ -134,15 +134,36 @@ def pack_patch_weight(w):
     return out.reshape(co, p * p * 4).to(torch.bfloat16)
 
 
-class ViTRunner:
-    """Device state (bf16 weights, buffers) + the launch sequence of one CLIP ViT-B image encoder."""
+def clip_spec(vis):
+    """The pieces of a CLIP VisionTransformer as ViTRunner consumes them."""
+    blocks = [dict(ln1=(blk.ln_1.weight, blk.ln_1.bias), ln2=(blk.ln_2.weight, blk.ln_2.bias),
+                   wqkv=blk.attn.in_proj_weight, bqkv=blk.attn.in_proj_bias,
+                   wo=blk.attn.out_proj.weight, bo=blk.attn.out_proj.bias,
+                   w1=blk.mlp.c_fc.weight, b1=blk.mlp.c_fc.bias, w2=blk.mlp.c_proj.weight, b2=blk.mlp.c_proj.bias)
+              for blk in vis.transformer.resblocks]
+    return dict(patch=vis.patch_size, width=vis.width, heads=vis.heads, resolution=vis.input_resolution,
+                patch_weight=vis.conv1.weight, patch_bias=None, cls=vis.class_embedding, pos=vis.positional_embedding,
+                ln_pre=(vis.ln_pre.weight, vis.ln_pre.bias), blocks=blocks,
+                ln_post=(vis.ln_post.weight, vis.ln_post.bias), proj=vis.proj, eps=1e-5, act=2)
 
-    def __init__(self, vis, device):
+
+class ViTRunner:
+    """Device state (bf16 weights, buffers) + the launch sequence of one pre-LN ViT image encoder.
+
+    `spec` (see clip_spec / mae.mae_spec) names the tensors: CLIP has ln_pre, QuickGELU (act 2), eps 1e-5 and a final
+    projection of the normalised class token; MAE (timm blocks) has a biased patch embedding, no ln_pre, erf GELU
+    (act 3), eps 1e-6 and returns the normalised class token itself in float32."""
+
+    def __init__(self, spec, device):
+        if not isinstance(spec, dict):
+            spec = clip_spec(spec)
         self.device = torch.device(device)
         self.lib = _lib.lib()
         self.input_format = _lib.PVR_FMT_NHWC4_BF16
-        self.p, self.W, self.L, self.heads, self.O = vis.patch_size, vis.width, vis.layers, vis.heads, vis.output_dim
-        self.res = vis.input_resolution
+        self.p, self.W, self.heads = spec["patch"], spec["width"], spec["heads"]
+        self.L = len(spec["blocks"])
+        self.res = spec["resolution"]
+        self.eps, self.act = float(spec["eps"]), int(spec["act"])
         self.grid = self.res // self.p
         self.S = self.grid * self.grid + 1
         dev, bf = self.device, torch.bfloat16
@@ -155,28 +176,29 @@ class ViTRunner:
         prog = prg.Program()
         cpp = self.p * 4
         self.in_slot = prog.new_slot(self.p * self.grid * cpp)
+        pbias = spec["patch_bias"]
+        pbias = torch.zeros(self.W) if pbias is None else pbias.detach().cpu().float()
         self.patch_slot = prog.conv(self.in_slot, (cpp, self.p, self.grid),
-                                    pack_patch_weight(vis.conv1.weight.detach().cpu().float()), self.p * cpp, self.W,
-                                    self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), torch.zeros(self.W), 0,
+                                    pack_patch_weight(spec["patch_weight"].detach().cpu().float()), self.p * cpp, self.W,
+                                    self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), pbias, 0,
                                     flops=2 * self.grid * self.W * 3 * self.p * self.p)
         prog.emb_width = 1
         self.patch_enc = prog.finish(dev)
-        self.cls, self.pos = f(vis.class_embedding), f(vis.positional_embedding)
-        self.ln_pre = (f(vis.ln_pre.weight), f(vis.ln_pre.bias))
-        self.ln_post = (f(vis.ln_post.weight), f(vis.ln_post.bias))
+        self.cls, self.pos = f(spec["cls"].reshape(-1)), f(spec["pos"].reshape(self.S, self.W))
+        self.ln_pre = tuple(f(t) for t in spec["ln_pre"]) if spec["ln_pre"] is not None else None
+        self.ln_post = tuple(f(t) for t in spec["ln_post"])
         self.blocks = []
-        for blk in vis.transformer.resblocks:
+        for blk in spec["blocks"]:
             self.blocks.append(dict(
-                ln1=(f(blk.ln_1.weight), f(blk.ln_1.bias)), ln2=(f(blk.ln_2.weight), f(blk.ln_2.bias)),
-                wqkv=b(blk.attn.in_proj_weight), bqkv=f(blk.attn.in_proj_bias),
-                wo=b(blk.attn.out_proj.weight), bo=f(blk.attn.out_proj.bias),
-                w1=b(blk.mlp.c_fc.weight), b1=f(blk.mlp.c_fc.bias),
-                w2=b(blk.mlp.c_proj.weight), b2=f(blk.mlp.c_proj.bias)))
-        self.proj_t = b(vis.proj.t())  # (output_dim, width): K-major B operand
+                ln1=tuple(f(t) for t in blk["ln1"]), ln2=tuple(f(t) for t in blk["ln2"]),
+                wqkv=b(blk["wqkv"]), bqkv=f(blk["bqkv"]), wo=b(blk["wo"]), bo=f(blk["bo"]),
+                w1=b(blk["w1"]), b1=f(blk["b1"]), w2=b(blk["w2"]), b2=f(blk["b2"])))
+        self.proj_t = b(spec["proj"].t()) if spec["proj"] is not None else None  # (output_dim, width): K-major B
+        self.O = self.proj_t.shape[0] if self.proj_t is not None else self.W
         self.n = 0
         self.flops_per_image = (2 * self.grid ** 2 * self.W * 3 * self.p ** 2
                                 + self.L * (2 * self.S * self.W * 12 * self.W + 4 * self.S * self.S * self.W)
-                                + 2 * self.W * self.O)
+                                + (2 * self.W * self.O if self.proj_t is not None else 0))
 
     def bind(self, n):
         if n == self.n:
@@ -197,33 +219,41 @@ class ViTRunner:
         return self.patch_enc.slot0
 
     def launches_per_forward(self):
-        return 2 + 7 * self.L + 2
+        return 2 + 7 * self.L + (2 if self.proj_t is not None else 1)
 
     def forward(self, out, out_ld=None):
-        """Frames must already be in slot0 (NHWC4 bf16). Writes (n, output_dim) fp32 rows into `out`."""
-        lib, n, S, W, M = self.lib, self.n, self.S, self.W, self.n * self.S
+        """Frames must already be in slot0 (NHWC4 bf16). Writes (n, O) fp32 rows into `out`."""
+        lib, n, S, W, M, eps = self.lib, self.n, self.S, self.W, self.n * self.S, self.eps
         st = _lib.current_stream_ptr
+        ld = out_ld if out_ld is not None else out.stride(0)
         with torch.cuda.device(self.device):
             self.patch_enc.forward(self.dummy, 1)
             patches = self.patch_enc.slot_ptr(self.patch_slot)
-            _lib.check(lib.pvr_vit_embed(patches, self.cls.data_ptr(), self.pos.data_ptr(), n, S, W,
-                                         self.ln_pre[0].data_ptr(), self.ln_pre[1].data_ptr(), 1e-5,
+            g, bta = (self.ln_pre[0].data_ptr(), self.ln_pre[1].data_ptr()) if self.ln_pre is not None else (None, None)
+            _lib.check(lib.pvr_vit_embed(patches, self.cls.data_ptr(), self.pos.data_ptr(), n, S, W, g, bta, eps,
                                          self.x.data_ptr(), st()), "pvr_vit_embed")
             for blk in self.blocks:
                 _lib.check(lib.pvr_layernorm(self.x.data_ptr(), 1, M, W, blk["ln1"][0].data_ptr(),
-                                             blk["ln1"][1].data_ptr(), 1e-5, self.y.data_ptr(), st()), "pvr_layernorm")
+                                             blk["ln1"][1].data_ptr(), eps, self.y.data_ptr(), st()), "pvr_layernorm")
                 gemm(self.y, blk["wqkv"], self.qkv, M, 3 * W, W, bias=blk["bqkv"])
                 _lib.check(lib.pvr_attention(self.qkv.data_ptr(), n, S, W, self.heads, self.att.data_ptr(), st()),
                            "pvr_attention")
                 gemm(self.att, blk["wo"], self.x, M, W, W, bias=blk["bo"], res=self.x, out_f32=1)
                 _lib.check(lib.pvr_layernorm(self.x.data_ptr(), 1, M, W, blk["ln2"][0].data_ptr(),
-                                             blk["ln2"][1].data_ptr(), 1e-5, self.y.data_ptr(), st()), "pvr_layernorm")
-                gemm(self.y, blk["w1"], self.h, M, 4 * W, W, bias=blk["b1"], act=2)
+                                             blk["ln2"][1].data_ptr(), eps, self.y.data_ptr(), st()), "pvr_layernorm")
+                gemm(self.y, blk["w1"], self.h, M, 4 * W, W, bias=blk["b1"], act=self.act)
                 gemm(self.h, blk["w2"], self.x, M, W, 4 * W, bias=blk["b2"], res=self.x, out_f32=1)
+            if self.proj_t is None:  # MAE: the normalised class token is the embedding (float32)
+                if ld != W:
+                    raise _lib.PvrError("ViTRunner: the embedding rows must be dense (ld == width)")
+                _lib.check(lib.pvr_layernorm_f32(self.x.data_ptr(), S, n, W, self.ln_post[0].data_ptr(),
+                                                 self.ln_post[1].data_ptr(), eps, out.data_ptr(), W, st()),
+                           "pvr_layernorm_f32")
+                return
             _lib.check(lib.pvr_layernorm(self.x.data_ptr(), S, n, W, self.ln_post[0].data_ptr(),
-                                         self.ln_post[1].data_ptr(), 1e-5, self.clsy.data_ptr(), st()), "pvr_layernorm")
+                                         self.ln_post[1].data_ptr(), eps, self.clsy.data_ptr(), st()), "pvr_layernorm")
             d = _lib.pvr_gemm_desc()
             d.a, d.lda, d.b, d.ldb = self.clsy.data_ptr(), W, self.proj_t.data_ptr(), W
-            d.out, d.ldo = out.data_ptr(), out_ld if out_ld is not None else out.stride(0)
+            d.out, d.ldo = out.data_ptr(), ld
             d.m, d.n, d.n_pad, d.k, d.out_f32, d.split_k = n, self.O, self.O, W, 1, 1
             _lib.check(lib.pvr_gemm(ctypes.byref(d), st()), "pvr_gemm")

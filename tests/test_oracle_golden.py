@@ -50,6 +50,22 @@ def test_resize_matches_aten_nonantialiased_bitwise(hw):
     assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("hw", [(96, 128), (100, 75), (480, 640), (84, 84), (33, 47), (64, 64), (224, 224)])
+def test_bicubic_resize_matches_aten_bitwise(hw):
+    """MAE transforms (src/embeddings.py:81, interpolation=3): torchvision-0.10 semantics = F.interpolate(bicubic,
+    align_corners=False) without antialias (A = -0.75), float bits; then clamp + half-even round like torchvision."""
+    h, w = hw
+    x = np.random.default_rng(h * 1000 + w + 7).integers(0, 256, (2, 3, h, w), dtype=np.uint8)
+    rh, rw, top, left = restate.resize_geometry(h, w)
+    ref = torch.nn.functional.interpolate(torch.from_numpy(x).float(), size=(rh, rw), mode="bicubic",
+                                          align_corners=False)
+    got = restate.resize_bicubic_f32(x, rh, rw)
+    assert np.array_equal(got.view(np.uint32), ref.numpy().view(np.uint32))
+    u8 = torch.round(ref.clamp(min=0, max=255)).to(torch.uint8)[:, :, top:top + 224, left:left + 224].numpy()
+    assert np.array_equal(restate.resize_crop_u8(x, interpolation="bicubic"), u8)
+    assert (ref.numpy() < 0).any() and (ref.numpy() > 255).any()  # the clamp is exercised
+
+
 def test_normalize_lut_bit_exact(tf):
     assert np.array_equal(restate.normalize_lut().view(np.uint32), tf["lut"].view(np.uint32))
 

@@ -37,11 +37,16 @@ WORKLOADS = {
     "conv5": ("moco_aug", 1, 512),
     "clip_b16": ("clip_vit_b16", 1, 1024),  # BASELINE configs[2]: CLIP-architecture ViT-B/16, batch 1024 per GPU
     "clip_b32": ("clip_vit", 1, 1024),      # the reference's actual `clip_vit` (ViT-B/32)
+    "mae_base": ("mae_base", 1, 1024),      # MAE ViT-B/16 (bicubic preprocessing, erf GELU)
+    "mae_large": ("mae_large", 1, 512),     # MAE ViT-L/16
 }
 VARIANTS = {"moco_aug": ["conv5"], "moco_aug_uber_34": ["l3", "l4"]}
 CLIP_PATCH = {"clip_vit_b16": 16, "clip_vit": 32}
+MAE_NAMES = ("mae_base", "mae_large")
+VIT_NAMES = tuple(CLIP_PATCH) + MAE_NAMES   # encoders run by ViTRunner (whole forward timed as one unit)
 GFLOP_PER_FRAME = {"moco_aug": 8.174, "moco_aug_uber_34": 14.96,  # SURVEY.md §8(d), convs only
-                   "clip_vit_b16": 35.13, "clip_vit": 8.818}
+                   "clip_vit_b16": 35.13, "clip_vit": 8.818,
+                   "mae_base": 35.13, "mae_large": 123.1}  # 2 x (patch embed + 12W^2 S + 2 S^2 W per layer) MACs
 
 
 def load_peaks():
@@ -117,6 +122,9 @@ def oracle_parts(name, seed=1):
     if name in CLIP_PATCH:
         from oracle import restate_vit
         return restate_vit.vit_state(CLIP_PATCH[name], seed)
+    if name in MAE_NAMES:
+        from oracle import restate_mae
+        return restate_mae.mae_state(name, seed)
     return [(v, restate.resnet50_state(v, seed + i)) for i, v in enumerate(VARIANTS[name])]
 
 
@@ -126,6 +134,9 @@ def oracle_embed(name, parts, obs):
     if name in CLIP_PATCH:
         from oracle import restate_vit
         return np.concatenate([restate_vit.embedding_forward(parts, obs[i:i + 64]) for i in range(0, len(obs), 64)])
+    if name in MAE_NAMES:
+        from oracle import restate_mae
+        return np.concatenate([restate_mae.embedding_forward(parts, name, obs[i:i + 64]) for i in range(0, len(obs), 64)])
     return restate.embed_observations(parts, obs, batch_size=64)
 
 
@@ -399,7 +410,7 @@ def main():
     # ---- per-kernel roofline (rank 0): CUDA events between ops on the launch stream
     enc = net.encoder()
     peaks = load_peaks()
-    if name in CLIP_PATCH:
+    if name in VIT_NAMES:
         # ViT: GEMM-dominated; the whole encoder forward (GEMMs + LayerNorm + attention) is timed as one unit
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         net.transforms.run(dev[0], n_frames, enc.slot0, enc.input_format, True)
@@ -411,7 +422,7 @@ def main():
         torch.cuda.synchronize()
         fwd_ms = e0.elapsed_time(e1) / 3
         achieved = enc.flops_per_image * frames_per_step / (fwd_ms / 1e3) / 1e12
-        roofline = {"kernel": "ViT-B encoder forward: conv_gemm_kernel (tcgen05 GEMMs) + vit_attention_kernel + LayerNorm",
+        roofline = {"kernel": "ViT encoder forward: conv_gemm_kernel (tcgen05 GEMMs) + vit_attention_kernel + LayerNorm",
                     "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16",
@@ -470,7 +481,7 @@ def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_ste
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_obs = 24 if n_frames == 3 else (32 if name == "clip_vit_b16" else 96)
+        n_obs = 24 if n_frames == 3 else (32 if name in ("clip_vit_b16", "mae_base") else (16 if name == "mae_large" else 96))
         v, dt = cpu_port_frames_per_s(name, n_frames, n_obs, threads)
         cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
                         "sample": f"{n_obs} observations x {n_frames} frames of the same workload, mini-batch 64, "
@@ -490,7 +501,10 @@ def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_ste
                          "224x224 uint8 observations, random-init weights (BASELINE configs[1])")
             if args.workload == "uber34x3" else
             (f"{name}: CLIP-architecture ViT-B/{CLIP_PATCH[name]}, 224x224 uint8 frames, random-init weights"
-             if name in CLIP_PATCH else f"{name}: ResNet-50 conv5, 224x224 uint8 frames, random-init weights"),
+             if name in CLIP_PATCH else
+             (f"{name}: MAE ViT-{'B' if name == 'mae_base' else 'L'}/16 encoder, bicubic Resize(256)+CenterCrop(224) of "
+              "224x224 uint8 frames, random-init weights" if name in MAE_NAMES else
+              f"{name}: ResNet-50 conv5, 224x224 uint8 frames, random-init weights")),
             "obs_per_step_per_gpu": obs_per_step, "frames_per_step_per_gpu": frames_per_step,
             "embedding_width": width, "sharding": "observations split over ranks, no data-path collective",
             "l2": f"inputs rotate over {n_rot} distinct batches ({n_rot * bytes_per_batch / 2**20:.0f} MiB > 126 MB L2); "

@@ -173,3 +173,42 @@ def train_bc(actor_model, obs, action, done, batch_size, unroll_length, max_fram
             stats["training_loss"].append(float(loss.item()))
             stats["gradient_norm"].append(float(tr.gradient_norm().item()))
     return stats
+
+
+# ---------------------------------------------------------------------------------------------- checkpoint schema
+CHECKPOINT_KEYS = ("embedding_model_state_dict", "actor_model_state_dict", "actor_model_optimizer_state_dict",
+                   "scheduler_state_dict", "flags")
+
+
+def save_checkpoint(save_path, embedding_model, actor_model, optimizer, scheduler, flags, stats=None):
+    """The `.tar` (+ `.pickle` statistics) pair of main_bc_2.py:250-258 / main_bc_1.py:259-267, same keys and the same
+    state_dict layouts (PolicyNet, FusedRMSprop and LambdaLR mirror the reference's modules), so runs interchange with
+    the reference in both directions. `flags` is an argparse namespace or a dict."""
+    import pickle
+    if stats is not None:
+        with open(save_path + '.pickle', 'wb') as fh:
+            pickle.dump(stats, fh, protocol=pickle.HIGHEST_PROTOCOL)
+    torch.save({
+        'embedding_model_state_dict': embedding_model.state_dict(),
+        'actor_model_state_dict': actor_model.state_dict(),
+        'actor_model_optimizer_state_dict': optimizer.state_dict(),
+        'scheduler_state_dict': scheduler.state_dict(),
+        'flags': dict(flags) if isinstance(flags, dict) else vars(flags),
+    }, save_path + '.tar')
+
+
+def load_checkpoint(path, embedding_model=None, actor_model=None, optimizer=None, scheduler=None):
+    """Restore whichever objects are given from a `.tar` written by `save_checkpoint` or by the reference."""
+    ck = torch.load(path, map_location='cpu', weights_only=False)
+    missing = [k for k in CHECKPOINT_KEYS if k not in ck]
+    if missing:
+        raise KeyError(f"{path}: not a BC checkpoint (missing {missing})")
+    if embedding_model is not None:
+        embedding_model.load_state_dict(ck['embedding_model_state_dict'])
+    if actor_model is not None:
+        actor_model.load_state_dict(ck['actor_model_state_dict'])
+    if optimizer is not None:
+        optimizer.load_state_dict(ck['actor_model_optimizer_state_dict'])
+    if scheduler is not None:
+        scheduler.load_state_dict(ck['scheduler_state_dict'])
+    return ck['flags']

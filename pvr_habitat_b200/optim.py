@@ -49,7 +49,7 @@ class _FusedBase(torch.optim.Optimizer):
                 if not st:
                     st["step"] = 0
                     self._init_state(st, p)
-                st["step"] += 1
+                st["step"] = int(st["step"]) + 1  # checkpoints written by torch >= 1.12 hold `step` as a tensor
                 a, b = self._state_tensors(st)
                 s1.append(a)
                 s2.append(b)
@@ -82,10 +82,15 @@ class FusedRMSprop(_FusedBase):
     """torch.optim.RMSprop(lr, alpha, eps, momentum=0, centered=False) semantics (main_bc_2.py:80-85)."""
     mode = 0
 
-    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, momentum=0, max_grad_norm=None, process_group=None):
-        if momentum != 0:
-            raise NotImplementedError("FusedRMSprop: momentum != 0 is not on the BC path (src/arguments.py:61-62)")
-        super().__init__(params, dict(lr=lr, alpha=alpha, eps=eps, momentum=momentum), max_grad_norm, process_group)
+    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0, momentum=0, centered=False,
+                 max_grad_norm=None, process_group=None):
+        if momentum != 0 or weight_decay != 0 or centered:
+            raise NotImplementedError("FusedRMSprop: momentum / weight_decay / centered are not on the BC path "
+                                      "(main_bc_2.py:80-85, src/arguments.py:61-62)")
+        # the param_group keys of torch.optim.RMSprop, so that `actor_model_optimizer_state_dict` of a checkpoint
+        # (main_bc_2.py:252-258) loads here and a state_dict written here loads into torch.optim.RMSprop
+        super().__init__(params, dict(lr=lr, momentum=momentum, alpha=alpha, eps=eps, centered=centered,
+                                      weight_decay=weight_decay), max_grad_norm, process_group)
 
     def _init_state(self, st, p):
         st["square_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)

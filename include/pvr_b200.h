@@ -224,9 +224,18 @@ int pvr_lstm_cell_backward(const float* dh_out, float* dh_rec, float* dc_rec, co
                            const float* c_cur, const float* nd, const float* nd_next, int B, int H, void* dG_bf16,
                            void* stream);
 
-/* All T steps of one LSTM layer (recurrent GEMM on tcgen05 + fused cell kernel per step). */
+/* All T steps of one LSTM layer (recurrent GEMM on tcgen05 + fused cell kernel per step).
+ * `flags` (both structs) describe a CHUNK of a longer sequence whose arrays the pointers are offsets into, so that the
+ * two layers can run as a wavefront on two streams (layer 1 works on chunk c while layer 0 works on chunk c + 1):
+ *   PVR_LSTM_CONT_PREV: an earlier chunk precedes this one. Forward: hm[0] was written by that chunk's last step (h0 is
+ *                       not read). Backward: the recurrent gradient is also propagated out of step 0 (into dh_rec).
+ *   PVR_LSTM_CONT_NEXT: a later chunk follows. Forward: the last step also writes hm[T] and reads nd[T]. Backward: the
+ *                       last step masks the incoming dh_rec by nd[T] (dh_rec / dc_rec hold the next chunk's result).
+ * The chunked sequence launches exactly the kernels of the unchunked one. */
+#define PVR_LSTM_CONT_PREV 1
+#define PVR_LSTM_CONT_NEXT 2
 typedef struct pvr_lstm_fwd {
-  int32_t T, B, H, reserved;
+  int32_t T, B, H, flags;
   const void* w_hh;   /* bf16 (4H, H) */
   const float* xp;    /* (T*B, 4H) fp32: x_t W_ih^T + b_ih + b_hh for every step (one big GEMM) */
   const float* nd;    /* (T, B) fp32 notdone = |1 - done| */
@@ -241,7 +250,7 @@ typedef struct pvr_lstm_fwd {
 int pvr_lstm_forward(const pvr_lstm_fwd* layer, void* stream);
 
 typedef struct pvr_lstm_bwd {
-  int32_t T, B, H, reserved;
+  int32_t T, B, H, flags;
   const void* w_hh_t;   /* bf16 (H, 4H): W_hh transposed */
   const float* nd;      /* (T, B) */
   const float* gates;   /* saved by the forward */

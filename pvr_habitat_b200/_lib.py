@@ -13,6 +13,7 @@ PVR_RESIZE_BICUBIC = 0x100
 PVR_OP_FP32 = 2
 PVR_CONV_OUT_F32 = 1
 PVR_GEMM_PDL, PVR_GEMM_MN = 1, 2
+PVR_LSTM_CONT_PREV, PVR_LSTM_CONT_NEXT = 1, 2
 PVR_OP_CONV, PVR_OP_MAXPOOL, PVR_OP_AVGPOOL, PVR_OP_HEAD, PVR_OP_FLATTEN = 1, 2, 3, 4, 5
 
 
@@ -39,12 +40,12 @@ class pvr_gemm_desc(ctypes.Structure):
 
 
 class pvr_lstm_fwd(ctypes.Structure):
-    _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("reserved", ctypes.c_int32)] + [
+    _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("flags", ctypes.c_int32)] + [
         (n, ctypes.c_void_p) for n in ("w_hh", "xp", "nd", "h0", "c_all", "hm", "h_out", "gates", "g_tmp", "h_last")]
 
 
 class pvr_lstm_bwd(ctypes.Structure):
-    _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("reserved", ctypes.c_int32)] + [
+    _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("flags", ctypes.c_int32)] + [
         (n, ctypes.c_void_p) for n in ("w_hh_t", "nd", "gates", "c_all", "dh_out", "dh_rec", "dc_rec", "dG")]
 
 

@@ -804,14 +804,14 @@ struct GraphCacheEntry {
   int seen;  // number of eager executions so far (the first run stays eager: lazy one-time attribute setup)
   cudaGraphExec_t exec;
 };
-GraphCacheEntry g_graphs[32];
+GraphCacheEntry g_graphs[128];
 int g_num_graphs = 0;
 
 GraphCacheEntry* graph_lookup(const void* key, size_t len) {
   for (int i = 0; i < g_num_graphs; ++i)
     if (g_graphs[i].key_len == len && memcmp(g_graphs[i].key, key, len) == 0) return &g_graphs[i];
-  if (g_num_graphs == 32) {  // recycle everything (shapes changed many times)
-    for (int i = 0; i < 32; ++i)
+  if (g_num_graphs == 128) {  // recycle everything (shapes changed many times)
+    for (int i = 0; i < 128; ++i)
       if (g_graphs[i].exec) cudaGraphExecDestroy(g_graphs[i].exec);
     g_num_graphs = 0;
   }
@@ -827,8 +827,13 @@ int lstm_forward_issue(const pvr_lstm_fwd* L, cudaStream_t st) {
   const long long BH = (long long)B * H;
   __nv_bfloat16* hm = static_cast<__nv_bfloat16*>(L->hm);
   __nv_bfloat16* ho = static_cast<__nv_bfloat16*>(L->h_out);
-  mask_state_kernel<<<(int)((BH + 255) / 256), 256, 0, st>>>(L->h0, L->nd, B, H, hm);
-  PVR_LAUNCH_CHECK("pvr_lstm_forward(mask)");
+  // Time chunks (PVR_LSTM_CONT_*): a chunk that continues an earlier one finds hm[0] written by that chunk's last
+  // cell kernel; a chunk that is continued writes hm[T] / reads nd[T] (both arrays belong to the whole sequence).
+  const bool cont_prev = (L->flags & PVR_LSTM_CONT_PREV) != 0, cont_next = (L->flags & PVR_LSTM_CONT_NEXT) != 0;
+  if (!cont_prev) {
+    mask_state_kernel<<<(int)((BH + 255) / 256), 256, 0, st>>>(L->h0, L->nd, B, H, hm);
+    PVR_LAUNCH_CHECK("pvr_lstm_forward(mask)");
+  }
   pvr_gemm_desc d;
   memset(&d, 0, sizeof(d));
   // The recurrent product is accumulated straight into the step's slice of the input projection (split-K slices,
@@ -846,8 +851,9 @@ int lstm_forward_issue(const pvr_lstm_fwd* L, cudaStream_t st) {
     if (rc != PVR_OK) return rc;
     launch_pdl(lstm_cell_fwd_kernel, (int)((BH + 255) / 256), 256, st, in_place ? xp_t : L->g_tmp,
                in_place ? (const float*)nullptr : (const float*)xp_t, L->c_all + t * BH, L->nd + (long long)t * B,
-               t + 1 < T ? L->nd + (long long)(t + 1) * B : nullptr, B, H, L->gates + (long long)t * B * 4 * H,
-               L->c_all + (t + 1) * BH, L->h_last, ho + t * BH, t + 1 < T ? hm + (t + 1) * BH : nullptr);
+               (t + 1 < T || cont_next) ? L->nd + (long long)(t + 1) * B : nullptr, B, H,
+               L->gates + (long long)t * B * 4 * H, L->c_all + (t + 1) * BH, L->h_last, ho + t * BH,
+               (t + 1 < T || cont_next) ? hm + (t + 1) * BH : nullptr);
     PVR_LAUNCH_CHECK("pvr_lstm_forward(cell)");
   }
   return PVR_OK;
@@ -863,13 +869,16 @@ int lstm_backward_issue(const pvr_lstm_bwd* L, cudaStream_t st) {
   d.m = B; d.n = H; d.n_pad = H; d.k = 4 * H; d.out_f32 = 2;
   d.split_k = (4 * H / 64) % 8 == 0 ? 8 : 1;
   d.flags = PVR_GEMM_PDL;
+  // time chunks, processed last to first: dh_rec / dc_rec carry the recurrent gradient from one chunk to the one before
+  const bool cont_prev = (L->flags & PVR_LSTM_CONT_PREV) != 0, cont_next = (L->flags & PVR_LSTM_CONT_NEXT) != 0;
   for (int t = T - 1; t >= 0; --t) {
     launch_pdl(lstm_cell_bwd_kernel, (int)((BH + 255) / 256), 256, st,
                L->dh_out ? L->dh_out + t * BH : nullptr, L->dh_rec, L->dc_rec, L->gates + (long long)t * B * 4 * H,
                L->c_all + t * BH, L->c_all + (t + 1) * BH, L->nd + (long long)t * B,
-               t + 1 < T ? L->nd + (long long)(t + 1) * B : nullptr, B, H, dG + (long long)t * B * 4 * H);
+               (t + 1 < T || cont_next) ? L->nd + (long long)(t + 1) * B : nullptr, B, H,
+               dG + (long long)t * B * 4 * H);
     PVR_LAUNCH_CHECK("pvr_lstm_backward(cell)");
-    if (t > 0) {
+    if (t > 0 || cont_prev) {
       d.a = dG + (long long)t * B * 4 * H;
       int rc = pvr_gemm(&d, st);
       if (rc != PVR_OK) return rc;

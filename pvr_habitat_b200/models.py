@@ -11,6 +11,7 @@ Layer-wise execution: the done masks depend only on t, so running all T steps of
 the reference's per-timestep two-layer call and lets x_t W_ih^T be one (T*B) x 4096 GEMM per layer.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -71,7 +72,7 @@ class _Workspace:
         self.hm = [z(M, H, dtype=bf), z(M, H, dtype=bf)]
         self.gates = [z(M, 4 * H), z(M, 4 * H)]
         self.c_all = [z(M + B, H), z(M + B, H)]
-        self.g_tmp = z(B, 4 * H)
+        self.g_tmp = [z(B, 4 * H), z(B, 4 * H)]  # per layer: the two layers run concurrently (wavefront)
         self.h_last = [z(B, H), z(B, H)]
         self.h0 = [z(B, H), z(B, H)]          # persistent copies: stable pointers keep the CUDA-graph cache warm
         self.nd = z(T, B)
@@ -81,7 +82,7 @@ class _Workspace:
         # backward
         self.dHL = [z(M, H), z(M, H)]         # fp32 gradients w.r.t. the LSTM layer outputs
         self.dG = [z(M, 4 * H, dtype=bf), z(M, 4 * H, dtype=bf)]
-        self.dh_rec, self.dc_rec = z(B, H), z(B, H)
+        self.dh_rec, self.dc_rec = [z(B, H), z(B, H)], [z(B, H), z(B, H)]
         self.dZ2, self.dZ1 = z(M, H, dtype=bf), z(M, H, dtype=bf)
         self.dX0 = z(M, Dp, dtype=bf) if batch_norm else None
         # (the weight-gradient GEMMs read dY / X as MN-major operands: no transposed copies, see gemm(mn=True))
@@ -138,6 +139,9 @@ class PolicyNet(nn.Module):
         self.num_actions = num_actions
         self.obs_size = observation_shape[0]
         self._ws = {}
+        self._side = None             # second stream of the LSTM wavefront
+        self._rollout = {}            # (T, B, device) -> captured evaluation step (see _rollout_step)
+        self.rollout_graph_rows = 8   # T*B up to which no-grad eval forwards replay from a CUDA graph (0 = never)
         self._needs_input_grad = False  # PolicyNetWithConv: the input rows are conv features
         self._wb = None          # bf16 weight copies
         self._saved = None
@@ -197,6 +201,35 @@ class PolicyNet(nn.Module):
         w["b_l"] = [getattr(self.core, f"bias_ih_l{l}").data + getattr(self.core, f"bias_hh_l{l}").data
                     for l in range(2)]
 
+    def _lstm_chunks(self, T):
+        """Number of time chunks of the two-layer wavefront (1 = layer after layer on one stream)."""
+        c = int(os.environ.get("PVR_LSTM_CHUNKS", "8"))
+        while c > 1 and (T % c or T // c < 2):
+            c //= 2
+        return max(c, 1)
+
+    def _side_stream(self):
+        if self._side is None or self._side.device != self.device:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
+    def _lstm_fwd_chunk(self, ws, w, l, t0, Tc, flags):
+        B, H, r0 = ws.B, ws.H, t0 * ws.B
+        L = pvr_lstm_fwd(T=Tc, B=B, H=H, flags=flags, w_hh=w["Whh"][l].data_ptr(), xp=ws.XP[l][r0:].data_ptr(),
+                         nd=ws.nd[t0:].data_ptr(), h0=ws.h0[l].data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
+                         hm=ws.hm[l][r0:].data_ptr(), h_out=ws.HL[l][r0:].data_ptr(),
+                         gates=ws.gates[l][r0:].data_ptr(), g_tmp=ws.g_tmp[l].data_ptr(),
+                         h_last=ws.h_last[l].data_ptr())
+        _lib.check(_lib.lib().pvr_lstm_forward(ctypes.byref(L), _stream()), "pvr_lstm_forward")
+
+    def _lstm_bwd_chunk(self, ws, w, l, t0, Tc, flags):
+        B, H, r0 = ws.B, ws.H, t0 * ws.B
+        L = pvr_lstm_bwd(T=Tc, B=B, H=H, flags=flags, w_hh_t=w["WhhT"][l].data_ptr(), nd=ws.nd[t0:].data_ptr(),
+                         gates=ws.gates[l][r0:].data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
+                         dh_out=ws.dHL[l][r0:].data_ptr(), dh_rec=ws.dh_rec[l].data_ptr(),
+                         dc_rec=ws.dc_rec[l].data_ptr(), dG=ws.dG[l][r0:].data_ptr())
+        _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(L), _stream()), "pvr_lstm_backward")
+
     def _workspace(self, T, B):
         key = (T, B, str(self.device))
         if key not in self._ws:
@@ -241,20 +274,35 @@ class PolicyNet(nn.Module):
                                               _stream()), "pvr_cast_rows_bf16")
         gemm(ws.X0, w["W1"], ws.H1, M, H, ws.Dp, bias=l1.bias.data, relu=True)
         gemm(ws.H1, w["W2"], ws.H2, M, H, H, bias=l2.bias.data, relu=True)
-        inp = ws.H2
-        hn, cn = [], []
+        # LSTM layers as a wavefront over time chunks: layer 0 works through chunk c + 1 on the current stream while
+        # layer 1 (input projection of the chunk + recurrence) works through chunk c on a side stream. Every step is a
+        # latency-bound GEMM + cell pair that fills a fraction of the GPU, so the two recurrences overlap.
+        C = self._lstm_chunks(T)
+        Tc = T // C
+        cur = torch.cuda.current_stream(self.device)
+        side = self._side_stream() if C > 1 else cur
+        gemm(ws.H2, w["Wih"][0], ws.XP[0], M, 4 * H, H, bias=w["b_l"][0], out_f32=1)
         for l in range(2):
-            gemm(inp, w["Wih"][l], ws.XP[l], M, 4 * H, H, bias=w["b_l"][l], out_f32=1)
             ws.c_all[l][:B].copy_(c0[l])
             ws.h0[l].copy_(h0[l])
-            L = pvr_lstm_fwd(T=T, B=B, H=H, reserved=0, w_hh=w["Whh"][l].data_ptr(), xp=ws.XP[l].data_ptr(),
-                             nd=ws.nd.data_ptr(), h0=ws.h0[l].data_ptr(), c_all=ws.c_all[l].data_ptr(),
-                             hm=ws.hm[l].data_ptr(), h_out=ws.HL[l].data_ptr(), gates=ws.gates[l].data_ptr(),
-                             g_tmp=ws.g_tmp.data_ptr(), h_last=ws.h_last[l].data_ptr())
-            _lib.check(lib.pvr_lstm_forward(ctypes.byref(L), _stream()), "pvr_lstm_forward")
-            inp = ws.HL[l]
-            hn.append(ws.h_last[l].clone())
-            cn.append(ws.c_all[l][M:M + B].clone())
+        for c in range(C):
+            flags = (_lib.PVR_LSTM_CONT_PREV if c > 0 else 0) | (_lib.PVR_LSTM_CONT_NEXT if c < C - 1 else 0)
+            r0, rows = c * Tc * B, Tc * B
+            self._lstm_fwd_chunk(ws, w, 0, c * Tc, Tc, flags)
+            if C > 1:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+            with torch.cuda.stream(side):
+                gemm(ws.HL[0][r0:r0 + rows], w["Wih"][1], ws.XP[1][r0:r0 + rows], rows, 4 * H, H, bias=w["b_l"][1],
+                     out_f32=1)
+                self._lstm_fwd_chunk(ws, w, 1, c * Tc, Tc, flags)
+        if C > 1:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            cur.wait_event(ev)
+        hn = [ws.h_last[l].clone() for l in range(2)]
+        cn = [ws.c_all[l][M:M + B].clone() for l in range(2)]
         _lib.check(lib.pvr_heads_forward(ws.HL[1].data_ptr(), M, H, self.policy.weight.data_ptr(),
                                          self.policy.bias.data_ptr(), self.baseline.weight.data_ptr(),
                                          self.baseline.bias.data_ptr(), self.num_actions, ws.logits.data_ptr(),
@@ -292,25 +340,41 @@ class PolicyNet(nn.Module):
         _lib.check(lib.pvr_heads_backward(dlogits.data_ptr(), ws.HL[1].data_ptr(), self.policy.weight.data_ptr(), M, H,
                                           A, 1.0, ws.dHL[1].data_ptr(), g["Wp"].data_ptr(), g["bp"].data_ptr(),
                                           _stream()), "pvr_heads_backward")
+        # reverse wavefront: layer 1 runs backwards through chunk c (+ the input gradient of that chunk for layer 0) on
+        # the current stream while layer 0 runs backwards through chunk c + 1 on the side stream
+        C = self._lstm_chunks(T)
+        Tc = T // C
+        cur = torch.cuda.current_stream(dev)
+        side = self._side_stream() if C > 1 else cur
+        for l in range(2):
+            ws.dh_rec[l].zero_()
+            ws.dc_rec[l].zero_()
+        for c in reversed(range(C)):
+            flags = (_lib.PVR_LSTM_CONT_PREV if c > 0 else 0) | (_lib.PVR_LSTM_CONT_NEXT if c < C - 1 else 0)
+            r0, rows = c * Tc * B, Tc * B
+            self._lstm_bwd_chunk(ws, w, 1, c * Tc, Tc, flags)
+            # gradient w.r.t. layer-0 outputs (fp32, consumed by the layer-0 cell backward)
+            gemm(ws.dG[1][r0:r0 + rows], w["WihT"][1], ws.dHL[0][r0:r0 + rows], rows, H, 4 * H, out_f32=1)
+            if C > 1:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                side.wait_event(ev)
+            with torch.cuda.stream(side):
+                self._lstm_bwd_chunk(ws, w, 0, c * Tc, Tc, flags)
         below = [ws.H2, ws.HL[0]]  # input of LSTM layer l
         for l in (1, 0):
-            ws.dh_rec.zero_()
-            ws.dc_rec.zero_()
-            L = pvr_lstm_bwd(T=T, B=B, H=H, reserved=0, w_hh_t=w["WhhT"][l].data_ptr(), nd=ws.nd.data_ptr(),
-                             gates=ws.gates[l].data_ptr(), c_all=ws.c_all[l].data_ptr(),
-                             dh_out=ws.dHL[l].data_ptr(), dh_rec=ws.dh_rec.data_ptr(), dc_rec=ws.dc_rec.data_ptr(),
-                             dG=ws.dG[l].data_ptr())
-            _lib.check(lib.pvr_lstm_backward(ctypes.byref(L), _stream()), "pvr_lstm_backward")
+            if l == 0 and C > 1:  # layer 1's weight gradients above overlap the tail of layer 0's recurrence
+                ev = torch.cuda.Event()
+                ev.record(side)
+                cur.wait_event(ev)
             dG = ws.dG[l]
             colsum(dG, 4 * H, g[f"bih{l}"])
             g[f"bhh{l}"].copy_(g[f"bih{l}"])
             # dW = dG^T X with dG (M, 4H) and X (M, H) as they sit in memory: MN-major tensor-core operands
             gemm(dG, ws.hm[l], g[f"Whh{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)
             gemm(dG, below[l], g[f"Wih{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)
-            if l == 1:   # gradient w.r.t. layer-0 outputs (fp32, consumed by the layer-0 cell backward)
-                gemm(dG, w["WihT"][1], ws.dHL[0], M, H, 4 * H, out_f32=1)
-            else:        # through ReLU of fc2: dZ2 = (dG0 W_ih0) * (H2 > 0)
-                gemm(dG, w["WihT"][0], ws.dZ2, M, H, 4 * H, res=ws.H2, res_mode=1)
+        # through ReLU of fc2: dZ2 = (dG0 W_ih0) * (H2 > 0)
+        gemm(ws.dG[0], w["WihT"][0], ws.dZ2, M, H, 4 * H, res=ws.H2, res_mode=1)
         colsum(ws.dZ2, H, g["b2"])
         gemm(ws.dZ2, ws.H1, g["W2"], H, H, M, out_f32=1, n_pad=H, mn=True)
         gemm(ws.dZ2, w["W2T"], ws.dZ1, M, H, H, res=ws.H1, res_mode=1)
@@ -364,17 +428,48 @@ class PolicyNet(nn.Module):
             core_state = self.initial_state(B)
         h0, c0 = (s.to(device=dev, dtype=torch.float32) for s in core_state)
         params = self._param_list()
+        action = None
         with torch.cuda.device(dev):
             if torch.is_grad_enabled() and any(p.requires_grad for p in params):
                 logits, baseline, hn, cn = _PolicyFn.apply(self, x, notdone, h0, c0, *params)
+            elif not self.training and T * B <= self.rollout_graph_rows:
+                logits, baseline, hn, cn, action = self._rollout_step(x, notdone, h0, c0)
             else:
                 logits, baseline, hn, cn = self._forward_cuda(x, notdone, h0, c0)
         if self.training:
             action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1)
-        else:
+        elif action is None:
             action = torch.argmax(logits, dim=1)
         return dict(policy_logits=logits.view(T, B, -1), baseline=baseline.view(T, B),
                     action=action.view(T, B)), (hn, cn)
+
+    # ------------------------------------------------------------------------------------------ online rollout
+    def _rollout_step(self, x, notdone, h0, c0):
+        """Evaluation steps of the online rollout (src/test_model.py:11-17: T = B = 1, no grad, eval mode): the ~20
+        launches of one step (weight casts included, so optimiser updates between rollouts are picked up) are captured
+        once per (T, B) into a CUDA graph and replayed from fixed input / output buffers. The first call of a shape
+        runs eagerly (lazy allocations, kernel attributes); results are the eager path's, bit for bit."""
+        T, B = notdone.shape
+        key = (T, B, str(self.device))
+        g = self._rollout.setdefault(key, {"calls": 0})
+        g["calls"] += 1
+        if g["calls"] == 1:
+            logits, baseline, hn, cn = self._forward_cuda(x, notdone, h0, c0)
+            return logits, baseline, hn, cn, torch.argmax(logits, dim=1)
+        if "graph" not in g:
+            g["in"] = tuple(t.clone() for t in (x, notdone, h0, c0))
+            g["ws"] = self._workspace(T, B)  # keeps the captured buffers alive if the workspace cache is recycled
+            torch.cuda.current_stream(self.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_cuda(*g["in"])
+                g["out"] = out + (torch.argmax(out[0], dim=1),)
+            g["graph"] = graph
+        else:
+            for dst, src in zip(g["in"], (x, notdone, h0, c0)):
+                dst.copy_(src, non_blocking=True)
+        g["graph"].replay()
+        return tuple(t.clone() for t in g["out"])
 
 
 class _CELossFn(torch.autograd.Function):

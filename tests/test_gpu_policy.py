@@ -305,3 +305,78 @@ def test_finetune_loss_curve_vs_oracle():
         ropt.step()
         ref.append(float(loss))
     np.testing.assert_allclose(got, ref, rtol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------ online rollout
+def test_rollout_step_graph_replay_equals_eager():
+    """src/test_model.py:11-17 (T = B = 1, eval, no grad, state carried over): the first step runs eagerly, the
+    second is captured into a CUDA graph, later ones replay it — all equal to the plain forward, also after the
+    weights were updated in place between steps (the graph re-casts the bf16 weight copies)."""
+    net = make_policy(2048, 5).eval()
+    plain = make_policy(2048, 5).eval()
+    plain.rollout_graph_rows = 0
+    with torch.no_grad():
+        net.fc[0].running_mean.normal_(0, 0.1)
+        net.fc[0].running_var.uniform_(0.5, 1.5)
+    plain.load_state_dict(net.state_dict())
+    s1 = tuple(s.cuda() for s in net.initial_state(1))
+    s2 = tuple(s.clone() for s in s1)
+    g = torch.Generator().manual_seed(0)
+    for k in range(7):
+        obs = torch.randn(1, 1, 2048, generator=g)
+        done = torch.tensor([[k == 4]])
+        if k == 5:  # an optimiser step between two rollouts: raw in-place update, as FusedRMSprop does
+            with torch.no_grad():
+                for a, b in zip(net.parameters(), plain.parameters()):
+                    d = torch.randn(a.shape, generator=g).cuda() * 1e-2
+                    a.add_(d)
+                    b.add_(d)
+        with torch.no_grad():
+            o1, s1 = net(dict(obs=obs, done=done), s1)
+            o2, s2 = plain(dict(obs=obs, done=done), s2)
+        # same kernels on the same data; the recurrent GEMM accumulates its two split-K slices with fp32 atomics, so
+        # the last bits depend on the arrival order (also between two eager runs)
+        for key in ("policy_logits", "baseline"):
+            assert rel(o1[key], o2[key]) < 1e-5, (k, key, o1[key], o2[key])
+        assert torch.equal(o1["action"], o2["action"]), k
+        assert o1["policy_logits"].shape == (1, 1, 3) and o1["action"].shape == (1, 1)
+        assert all(rel(a, b) < 1e-5 for a, b in zip(s1, s2)), k
+    assert "graph" in net._rollout[(1, 1, str(net.device))] and not plain._rollout
+    # training-mode and large forwards never take the graph path
+    net.train()
+    with torch.no_grad():
+        net(dict(obs=torch.randn(1, 2, 2048), done=torch.zeros(1, 2, dtype=torch.bool)), net.initial_state(2))
+    net.eval()
+    with torch.no_grad():
+        net(dict(obs=torch.randn(3, 4, 2048), done=torch.zeros(3, 4, dtype=torch.bool)), net.initial_state(4))
+    assert list(net._rollout) == [(1, 1, str(net.device))] and net._rollout[(1, 1, str(net.device))]["calls"] == 7
+
+
+@pytest.mark.parametrize("T,B", [(64, 16), (100, 4), (16, 8)])
+def test_lstm_wavefront_chunks_equal_the_layer_by_layer_schedule(T, B, monkeypatch):
+    """Two-stream wavefront over time chunks (PVR_LSTM_CHUNKS, default 8) against one chunk on one stream: the same
+    kernels on the same data (recurrent state carried across chunk borders forwards and backwards, done masks at the
+    borders). The forward is made deterministic for the comparison (PVR_LSTM_NO_INPLACE: no split-K atomics in the
+    recurrent GEMM; with them a last-bit difference flips bf16 roundings of h and shows up as ~1e-4), the backward
+    keeps its 8-slice atomic GEMMs, so gradients agree to that noise."""
+    monkeypatch.setenv("PVR_LSTM_NO_INPLACE", "1")
+    rng = np.random.default_rng(T + B)
+    obs = torch.from_numpy(rng.standard_normal((T, B, 192)).astype(np.float32))
+    done = torch.from_numpy(rng.random((T, B)) < 0.1)
+    act = torch.from_numpy(rng.integers(0, 3, (T, B))).cuda()
+    h0 = tuple(torch.from_numpy(rng.standard_normal((2, B, 1024)).astype(np.float32)) for _ in range(2))
+    results = []
+    for chunks in ("1", "8"):
+        monkeypatch.setenv("PVR_LSTM_CHUNKS", chunks)
+        net = make_policy(192, 3).train()
+        assert net._lstm_chunks(T) == (1 if chunks == "1" else {64: 8, 100: 4, 16: 8}[T])
+        out, state = net(dict(obs=obs, done=done), h0)
+        bc_loss(out["policy_logits"], act).backward()
+        torch.cuda.synchronize()
+        results.append((out["policy_logits"].detach(), state, {k: p.grad.clone() for k, p in net.named_parameters()
+                                                               if p.grad is not None}))
+    (l1, s1, g1), (l2, s2, g2) = results
+    assert rel(l1, l2) < 1e-6 and all(rel(a, b) < 1e-6 for a, b in zip(s1, s2)), (rel(l1, l2),)
+    assert set(g1) == set(g2)
+    for k in g1:
+        assert rel(g1[k], g2[k]) < 1e-2, (k, rel(g1[k], g2[k]))  # dG is rounded to bf16 after the noisy fp32 sums

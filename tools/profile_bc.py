@@ -26,4 +26,5 @@ for _ in range(steps):
 t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
-print(f"host issue {1e3 * (t1 - t0) / steps:.2f} ms/step, wall {1e3 * (t2 - t0) / steps:.2f} ms/step")
+print(f"PVR_LSTM_CHUNKS={os.environ.get('PVR_LSTM_CHUNKS', 'default')}: host issue {1e3 * (t1 - t0) / steps:.2f} ms/step, "
+      f"wall {1e3 * (t2 - t0) / steps:.2f} ms/step = {steps / (t2 - t0):.1f} steps/s, loss {float(tr.last_loss):.6f}")

@@ -100,6 +100,21 @@ __device__ __forceinline__ void mask_bf16x8(float* f, const uint4& rv) {
     if (!(__uint_as_float(w[t] & 0xFFFF0000u) > 0.f)) f[2 * t + 1] = 0.f;
   }
 }
+// 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7), branch free, two MUFU ops:
+// about half the instructions of erff(). The negative side is formed as 0.5 x (1 - erf|z|) = 0.5 x p e directly, so there
+// is no cancellation in the tail. Against float64 GELU: max absolute error 4e-7, max relative error 1.7e-4 where
+// |GELU| > 1e-3 — more than an order of magnitude below the bf16 rounding (2^-9) of the stored result.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float pe = p * t * __expf(-z * z);  // 1 - erf(z)
+  return 0.5f * x * (x >= 0.f ? 2.f - pe : pe);
+}
+
 __device__ __forceinline__ void relu_cols(float* f, int n, int relu_n) {
   if (n + 32 <= relu_n) {
 #pragma unroll
@@ -507,7 +522,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 for (int jj = 0; jj < 32; ++jj) f[jj] = __fdividef(f[jj], 1.f + __expf(-1.702f * f[jj]));
               } else if (p.quick_gelu == 2) {  // nn.GELU (erf form) of the timm blocks MAE is built from
 #pragma unroll
-                for (int jj = 0; jj < 32; ++jj) f[jj] = 0.5f * f[jj] * (1.f + erff(f[jj] * 0.70710678118654752f));
+                for (int jj = 0; jj < 32; ++jj) f[jj] = gelu_erf(f[jj]);
               }
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj) {

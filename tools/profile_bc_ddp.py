@@ -1,0 +1,44 @@
+"""BC steps/s under torchrun (data parallel, NCCL): the eager step against a whole-step CUDA graph with the collectives
+captured. EXPERIMENT, not on by default: BCTrainer only replays the step from a graph on one GPU. The one 2-GPU trial of
+round 1 (use_graph forced on with world 2, NCCL all-reduces inside torch.cuda.graph) did not finish within 200 s and
+was killed by its timeout; the cause (NCCL capture vs. the side-stream fork/join of the LSTM wavefront vs. the
+watchdog thread) is not isolated yet. BCTrainer ignores use_graph=True for world > 1 until that is understood.
+Usage: torchrun --nproc-per-node N tools/profile_bc_ddp.py [STEPS]"""
+import os
+import random
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from pvr_habitat_b200.bc import BCTrainer  # noqa: E402
+from pvr_habitat_b200.models import PolicyNet  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+obs, action, done, _ = bench.bc_dataset()
+for mode in ("eager", "graph"):
+    torch.manual_seed(1)
+    random.seed(1)
+    net = PolicyNet((2048,), 3, batch_norm=True).cuda().train()
+    tr = BCTrainer(net, obs, action, done, 128, 64, 10 ** 9, process_group=dist.group.WORLD, use_graph=(mode == "graph"))
+    for _ in range(8):  # eager warm-up, graph capture, first replays
+        tr.step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t1 = time.perf_counter()
+    if dist.get_rank() == 0:
+        print(f"world {dist.get_world_size()} {mode} (graph in use: {tr._graph is not None}): "
+              f"{1e3 * (t1 - t0) / steps:.2f} ms/step = {steps / (t1 - t0):.1f} steps/s, loss {float(tr.last_loss):.6f}",
+              flush=True)
+dist.destroy_process_group()

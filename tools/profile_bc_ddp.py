@@ -3,7 +3,7 @@ captured. EXPERIMENT, not on by default: BCTrainer only replays the step from a 
 round 1 (use_graph forced on with world 2, NCCL all-reduces inside torch.cuda.graph) did not finish within 200 s and
 was killed by its timeout; the cause (NCCL capture vs. the side-stream fork/join of the LSTM wavefront vs. the
 watchdog thread) is not isolated yet. BCTrainer ignores use_graph=True for world > 1 until that is understood.
-Usage: torchrun --nproc-per-node N tools/profile_bc_ddp.py [STEPS]"""
+Usage: torchrun --nproc-per-node N tools/profile_bc_ddp.py [STEPS] [eager|graph ...]   (default: eager only)"""
 import os
 import random
 import sys
@@ -22,11 +22,13 @@ local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 obs, action, done, _ = bench.bc_dataset()
-for mode in ("eager", "graph"):
+for mode in (sys.argv[2:] or ["eager"]):
     torch.manual_seed(1)
     random.seed(1)
     net = PolicyNet((2048,), 3, batch_norm=True).cuda().train()
     tr = BCTrainer(net, obs, action, done, 128, 64, 10 ** 9, process_group=dist.group.WORLD, use_graph=(mode == "graph"))
+    if mode == "graph":
+        tr.use_graph = True  # force the experiment: BCTrainer itself keeps world > 1 on the eager step
     for _ in range(8):  # eager warm-up, graph capture, first replays
         tr.step()
     dist.barrier()

@@ -284,13 +284,73 @@ def golden_mae(E):
     np.savez_compressed(os.path.join(GOLDEN, "mae.npz"), **out)
 
 
+def golden_save_embedded(E):
+    """behavioral_cloning/save_embedded_obs.py `run(flags)` UNMODIFIED, both sources, on three synthetic ImageNav-style
+    trajectories (64x64, current || goal = 6 channels) with the 'random' encoder on CPU: the file names, pickle layouts
+    and values the drop-in pvr_habitat_b200/save_embedded_obs.py has to reproduce."""
+    import importlib
+    import pickle
+    import cv2
+    S = importlib.import_module("behavioral_cloning.save_embedded_obs")
+    lengths = [5, 3, 4]
+    rng = np.random.default_rng(31)
+    traj = dict(obs=[], action=[], reward=[], done=[], true_state=[])
+    for i, n in enumerate(lengths):
+        frames = restate.structured_frames(n, 64, 64, 6, 310 + i)
+        frames[:, :, :, 3:] = frames[-1:, :, :, 3:]          # one goal image per trajectory, as ImageNav writes it
+        traj["obs"].append(frames)
+        traj["action"].append(rng.integers(0, 3, n))
+        traj["reward"].append(rng.random(n).astype(np.float32))
+        d = np.zeros(n, dtype=bool)
+        d[-1] = True
+        traj["done"].append(d)
+        traj["true_state"].append(rng.standard_normal((n, 12)).astype(np.float32))
+    out = {"lengths": np.array(lengths)}
+    for k, v in traj.items():
+        out["in_" + k] = np.concatenate(v)
+    env, run_id = "HabitatImageNav-apartment_0", 4
+    with tempfile.TemporaryDirectory() as d:
+        with open(os.path.join(d, env + ".pickle"), "wb") as fh:
+            pickle.dump(traj, fh, protocol=pickle.HIGHEST_PROTOCOL)
+        os.makedirs(os.path.join(d, env))
+        for t, frames in enumerate(traj["obs"]):             # save_opt_trajectories_png.py:43-58
+            for s_ in range(len(frames)):
+                cv2.imwrite(os.path.join(d, env, f"{t}_{s_}.png"), frames[s_][:, :, :3])
+            cv2.imwrite(os.path.join(d, env, f"{t}_goal.png"), frames[-1][:, :, 3:])
+            with open(os.path.join(d, env, f"{t}.pickle"), "wb") as fh:
+                pickle.dump({k: traj[k][t] for k in ("action", "reward", "done", "true_state")}, fh,
+                            protocol=pickle.HIGHEST_PROTOCOL)
+        for source in ("pickle", "png"):
+            flags = S.parser.parse_args(["--data_path", d, "--env", env, "--embedding_name", "random", "--run_id",
+                                         str(run_id), "--batch_size", "4", "--disable_cuda", "--source", source,
+                                         "--n_trajectories", "-1"])
+            S.run(flags)
+            name = os.path.join(d, env + "_random.pickle")
+            with open(name, "rb") as fh:
+                data = pickle.load(fh)
+            os.remove(name)
+            out[f"{source}_keys"] = np.array(list(data.keys()))
+            for k, v in data.items():
+                out[f"{source}_{k}"] = np.array([os.path.relpath(x, d) for x in v]) if k == "png" else np.asarray(v)
+            ck = torch.load(os.path.join(d, f"random_{run_id}.tar"), map_location="cpu")
+            out["tar_keys"] = np.array(list(ck.keys()))
+            for k, v in ck["embedding_model_state_dict"].items():
+                out["w_" + k] = v.numpy()
+            out["files"] = np.array(sorted(f for f in os.listdir(d) if os.path.isfile(os.path.join(d, f))))
+    out["env"], out["run_id"] = np.array(env), np.array(run_id)
+    np.savez_compressed(os.path.join(GOLDEN, "save_embedded.npz"), **out)
+    print("save_embedded.npz:", {k: v.shape for k, v in out.items() if k.startswith(("pickle_", "png_"))})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
     if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which or \
-            "mae" in which:
+            "mae" in which or "save_embedded" in which:
         E = refshim.reference_embeddings()
+        if "save_embedded" in which:
+            golden_save_embedded(E)
         if "mae" in which:
             golden_mae(E)
         if "resnet_basic" in which:

@@ -59,6 +59,15 @@ int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int 
                       int crop, const float* mean, const float* stdv, void* out, int out_fmt, int sample_major,
                       void* stream);
 
+/* Same contract with an ANTIALIASED bicubic Resize (a = -0.5, separable, float32 intermediate): CLIP's transforms,
+ * T.Resize(res, BICUBIC, antialias=True) -> CenterCrop(res), src/embeddings.py:309-314 (mean / stdv = CLIP's). Output
+ * formats PVR_FMT_NCHW_F32, PVR_FMT_NHWC4_BF16, PVR_FMT_NHWC4_F32. The first call for an (input size, output size)
+ * pair allocates and fills two small weight tables (not capturable into a CUDA graph); down-scaling up to 7.5x.
+ * Round-1 status: arithmetic core verified on CPU against the oracle, kernel not yet run on a GPU (experimental). */
+int pvr_preprocess_u8_aa(const uint8_t* in, int N, int H, int W, int n_frames, int rh, int rw, int top, int left,
+                         int crop, const float* mean, const float* stdv, void* out, int out_fmt, int sample_major,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Encoder "program": the frozen PVR network (ResNet-50 conv5 / l4 / l3 compressed / uber, src/vision_models/
  * moco.py:6-113, src/embeddings.py:44-57) flattened by the Python host into a list of fused ops over NHWC bf16

@@ -132,6 +132,77 @@ def resize_bicubic_f32(frames_nchw_u8, rh, rw):
     return _cubic_sum(rows, [wk[:, None] for wk in wy])
 
 
+# ---- antialiased bicubic (CLIP transforms, src/embeddings.py:309-310: T.Resize(res, BICUBIC, antialias=True))
+def _aa_cubic_filter(x):
+    """ATen aa_filter for bicubic (a = -0.5, the PIL filter), as compiled for x86 (every a*b+c fused):
+    |x| < 1: ((a+2)|x| - (a+3)) x^2 + 1;  |x| < 2: (((|x| - 5)|x| + 8)|x| - 4) a;  else 0."""
+    f32 = np.float32
+    x = np.abs(x).astype(f32)
+    t = _fma(np.full_like(x, f32(1.5)), x, np.full_like(x, f32(-2.5)))
+    near = _fma((t * x).astype(f32), x, np.full_like(x, f32(1)))
+    u = _fma((x - f32(5)).astype(f32), x, np.full_like(x, f32(8)))
+    u = _fma(u, x, np.full_like(x, f32(-4)))
+    far = (u * f32(-0.5)).astype(f32)
+    return np.where(x < 1, near, np.where(x < 2, far, f32(0))).astype(f32)
+
+
+def _aa_weights(in_size, out_size):
+    """ATen _compute_indices_min_size_weights_aa (UpSampleKernel.cpp) for one dimension: per output index the first
+    input index and the normalised float32 weights. The C++ mixes float variables with double literals (`+ 0.5`,
+    `1.0 / scale`): those sub-expressions are evaluated in double and rounded once — reproduced here, it changes a
+    few weights by one ulp. Extracted weights are bit-identical with ATen's for all sizes tried (impulse inputs)."""
+    f32, f64 = np.float32, np.float64
+    scale = f32(in_size) / f32(out_size)
+    support = f32(f32(2) * scale) if scale >= 1 else f32(2)
+    invscale = f32(1.0 / f64(scale)) if scale >= 1 else f32(1)
+    out = []
+    for i in range(out_size):
+        center = f32(f64(scale) * (i + 0.5))
+        xmin = max(int(f64(f32(center - support)) + 0.5), 0)
+        xsize = min(int(f64(f32(center + support)) + 0.5), in_size) - xmin
+        j = (np.arange(xsize) + xmin).astype(f32)
+        w = _aa_cubic_filter(((f64(1) * (j - center).astype(f32) + 0.5) * f64(invscale)).astype(f32))
+        total = f32(0)
+        for v in w:
+            total = f32(total + v)
+        out.append((xmin, (w / total).astype(f32)))
+    return out
+
+
+def _aa_apply(x, weights, axis):
+    """ATen interpolate_aa_single_dim along `axis`: out = x[xmin] * w[0], then `out += x[xmin + j] * w[j]`. As compiled
+    for x86 the loop runs in groups of four iterations with a rounded product and a separate add, and the remaining
+    (xsize - 1) mod 4 iterations as fused multiply-adds (probed: the only schedule that is bit-identical for 4-tap
+    up-scaling and 12-tap down-scaling alike)."""
+    f32 = np.float32
+    x = np.moveaxis(x, axis, -1)
+    out = np.empty(x.shape[:-1] + (len(weights),), f32)
+    for i, (xmin, w) in enumerate(weights):
+        o = (x[..., xmin] * w[0]).astype(f32)
+        n = len(w) - 1
+        grouped = n // 4 * 4
+        for j in range(1, n + 1):
+            if j <= grouped:
+                o = (o + (x[..., xmin + j] * w[j]).astype(f32)).astype(f32)
+            else:
+                o = _fma(x[..., xmin + j], np.full(o.shape, w[j], f32), o)
+        out[..., i] = o
+    return np.moveaxis(out, -1, axis)
+
+
+def resize_bicubic_aa_f32(frames_nchw_u8, rh, rw):
+    """float32 antialiased bicubic resize of uint8 NCHW frames before clamping / rounding: the horizontal pass over
+    all input rows into a float32 intermediate, then the vertical pass (ATen's separable order). Bit-exact with
+    torch.nn.functional.interpolate(mode='bicubic', antialias=True, align_corners=False) on CPU."""
+    x = np.asarray(frames_nchw_u8).astype(np.float32)
+    h, w = x.shape[2:]
+    if w != rw:
+        x = _aa_apply(x, _aa_weights(w, rw), 3)
+    if h != rh:
+        x = _aa_apply(x, _aa_weights(h, rh), 2)
+    return x
+
+
 def resize_crop_u8(frames_nchw_u8, size=256, crop=224, interpolation="bilinear"):
     """Resize(256) + CenterCrop(224) on uint8 NCHW frames, bit-for-bit torchvision-0.10 semantics.
 
@@ -145,7 +216,13 @@ def resize_crop_u8(frames_nchw_u8, size=256, crop=224, interpolation="bilinear")
     """
     x = np.asarray(frames_nchw_u8)
     rh, rw, top, left = resize_geometry(x.shape[2], x.shape[3], size, crop)
-    if interpolation == "bicubic":
+    if interpolation == "bicubic_aa":
+        # CLIP: T.Resize(res, BICUBIC, antialias=True) (src/embeddings.py:310). torchvision returns the image untouched
+        # when the short side already has the requested size (tv:transforms/functional.py:468-471)
+        if (rh, rw) == x.shape[2:]:
+            return np.ascontiguousarray(x[:, :, top:top + crop, left:left + crop])
+        v = resize_bicubic_aa_f32(x, rh, rw)[:, :, top:top + crop, left:left + crop]
+    elif interpolation == "bicubic":
         # T.Resize(256, interpolation=3) of the MAE encoders (src/embeddings.py:81): bicubic overshoots, torchvision
         # clamps to [0, 255] before the rounding cast (tv:transforms/_functional_tensor.py:469-470)
         v = resize_bicubic_f32(x, rh, rw)[:, :, top:top + crop, left:left + crop]

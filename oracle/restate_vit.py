@@ -42,12 +42,13 @@ def vit_forward(sd, x):
 
 
 def clip_transforms(frames_nhwc_u8):
-    """src/embeddings.py:309-314 for 224x224 frames: Resize(224)/CenterCrop(224) are the identity, then /255 and
+    """src/embeddings.py:309-314: Resize(224, BICUBIC, antialias=True) -> CenterCrop(224) (the identity for 224x224
+    frames, ATen's separable antialiased bicubic otherwise: oracle/restate.py:resize_bicubic_aa_f32), then /255 and
     CLIP's Normalize (three rounded fp32 operations, as in oracle/restate.py:normalize_lut)."""
     from oracle import restate
     lut = restate.normalize_lut(CLIP_MEAN, CLIP_STD)
     u = np.ascontiguousarray(np.transpose(frames_nhwc_u8, (0, 3, 1, 2)))
-    assert u.shape[2:] == (224, 224)
+    u = restate.resize_crop_u8(u, 224, 224, interpolation="bicubic_aa")
     return np.stack([lut[c][u[:, c]] for c in range(3)], 1)
 
 

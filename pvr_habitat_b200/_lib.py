@@ -62,6 +62,9 @@ _SIGNATURES = {
     "pvr_preprocess_u8": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 9 + [
         ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_void_p, ctypes.c_int,
         ctypes.c_int, ctypes.c_void_p]),
+    "pvr_preprocess_u8_aa": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_int] * 9 + [
+        ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_void_p, ctypes.c_int,
+        ctypes.c_int, ctypes.c_void_p]),
     "pvr_encoder_create": (ctypes.c_int, [ctypes.POINTER(pvr_op), ctypes.c_int, ctypes.POINTER(pvr_slot),
                                           ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "pvr_encoder_workspace_bytes": (ctypes.c_int64, [ctypes.c_void_p, ctypes.c_int]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libpvr_b200.so")
-SOURCES = ["api.cu", "conv_gemm.cu", "preprocess.cu", "pool_head.cu", "policy.cu", "vit.cu", "conv3x3_patch.cu", "conv_b2b.cu", "conv_f32.cu", "policy_conv.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "preprocess.cu", "preprocess_aa.cu", "pool_head.cu", "policy.cu", "vit.cu", "conv3x3_patch.cu", "conv_b2b.cu", "conv_f32.cu", "policy_conv.cu"]
 
 
 def _stale(srcs):

@@ -1,0 +1,259 @@
+// K1, antialiased bicubic variant — CLIP transforms (src/embeddings.py:309-314): Resize(res, BICUBIC, antialias=True)
+// -> CenterCrop(res) -> ConvertImageDtype(float) -> Normalize(CLIP mean / std) + frame split, one pass over HBM.
+//
+// torchvision casts the uint8 image to float32 and calls ATen's separable antialiased bicubic resize (a = -0.5,
+// normalised weights, support 2 * max(scale, 1)): a horizontal pass over every input row into a float32 intermediate,
+// then a vertical pass; the result is clamped to [0, 255], rounded half to even to uint8, then x/255 and
+// (x - mean)/std (the 3 x 256 table of preprocess.cu). The bit-deciding arithmetic is preprocess_aa_core.cuh, shared
+// with a host harness that is checked against the oracle on CPU (tests/test_preprocess_aa_core.py).
+//
+// One CTA produces `rows` output rows of all frames of one observation: the input rows they depend on (one contiguous
+// byte range of the HWC image) are staged in shared memory by a 1-D bulk async copy, the horizontal pass writes the
+// float32 intermediate rows (crop columns only) to shared memory, the vertical pass reads them back.
+// Tap ranges and weights per output row / column come from two small tables in global memory, computed once per
+// (input size, output size) by aa_weights_kernel and cached.
+//
+// STATUS (round 1): compiles; the core is verified on CPU; the kernel as a whole has not run on a GPU yet (the round's
+// GPU budget was spent) — pvr_habitat_b200.embeddings keeps CLIP inputs restricted to the identity resize unless
+// PVR_EXPERIMENTAL_AA=1, and the -m gpu tests of this kernel are skipped without that variable.
+#include <mutex>
+#include <vector>
+
+#include "preprocess_aa_core.cuh"
+#include "pvr_b200.h"
+#include "ptx.cuh"
+
+extern void pvr_set_error(const char* fmt, ...);
+
+namespace pvr {
+namespace {
+
+struct AAParams {
+  const uint8_t* in;
+  void* out;
+  long long total_bytes;
+  int N, H, W, CH, nf;
+  int top, left, crop, rows, bands, max_in_rows;
+  const int *ymin, *ysize, *xmin, *xsize;
+  const float *wy, *wx;
+  float mean[3], stdv[3];
+  int fmt, sample_major;
+  int tmp_off;  // byte offset of the float32 intermediate inside dynamic smem
+};
+
+__global__ void aa_weights_kernel(int in_size, int out_size, int* xmin, int* size, float* w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < out_size) aa_index_weights(i, in_size, out_size, &xmin[i], &size[i], w + (long long)i * AA_MAX_TAPS);
+}
+
+__global__ void __launch_bounds__(256) preprocess_aa_kernel(const AAParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem);
+  float* lut = reinterpret_cast<float*>(smem + 16);  // [3][256]
+  uint8_t* stage = smem + 16 + 3 * 256 * 4;
+  float* tmp = reinterpret_cast<float*>(smem + p.tmp_off);
+
+  const int img = blockIdx.x / p.bands;
+  const int band = blockIdx.x - img * p.bands;
+  const int y_first = band * p.rows;
+  const int y_count = min(p.rows, p.crop - y_first);
+  const int y_last = y_first + y_count - 1 + p.top;
+  const int r_lo = p.ymin[y_first + p.top];
+  const int r_hi = p.ymin[y_last] + p.ysize[y_last] - 1;  // tap ranges move monotonically with the output row
+  const int rows_in = r_hi - r_lo + 1;
+  if (rows_in > p.max_in_rows) __trap();  // the host sized the shared memory from an upper bound
+
+  const long long row_bytes = (long long)p.W * p.CH;
+  const long long g0 = ((long long)img * p.H + r_lo) * row_bytes;
+  const long long nbytes = (long long)rows_in * row_bytes;
+  const long long a0 = g0 & ~15ll;
+  const int head = (int)(g0 - a0);
+  const long long want = (head + nbytes + 15) & ~15ll;
+  const long long avail = (p.total_bytes - a0) & ~15ll;  // never read past the tensor with the bulk engine
+  const uint32_t bulk = (uint32_t)(want < avail ? want : avail);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(bar, bulk);
+    bulk_load_1d(stage, p.in + a0, bulk, bar);
+  }
+  for (long long t = bulk + threadIdx.x; t < head + nbytes; t += blockDim.x) stage[t] = p.in[a0 + t];
+  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+    const int c = t >> 8, u = t & 255;
+    lut[t] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), p.mean[c]), p.stdv[c]);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  const uint8_t* s = stage + head;
+  const long long plane = (long long)p.crop * p.crop;
+  const int row_vals = p.crop * 3;
+  for (int f = 0; f < p.nf; ++f) {
+    // horizontal pass: tmp[r][x][c] for the staged rows and the crop's columns
+    for (int idx = threadIdx.x; idx < rows_in * row_vals; idx += blockDim.x) {
+      const int r = idx / row_vals;
+      const int rem = idx - r * row_vals;
+      const int x = rem / 3;
+      const int c = rem - x * 3;
+      const int X = x + p.left;
+      const uint8_t* src = s + (long long)r * row_bytes + (long long)p.xmin[X] * p.CH + 3 * f + c;
+      const int CH = p.CH;
+      tmp[idx] = aa_accumulate(p.xsize[X], p.wx + (long long)X * AA_MAX_TAPS, [&](int j) { return (float)src[j * CH]; });
+    }
+    __syncthreads();
+    // vertical pass + clamp + half-even round + normalisation table
+    const long long image = p.sample_major ? (long long)img * p.nf + f : (long long)f * p.N + img;
+    for (int idx = threadIdx.x; idx < y_count * p.crop; idx += blockDim.x) {
+      const int yy = idx / p.crop;
+      const int x = idx - yy * p.crop;
+      const int y = y_first + yy;
+      const int Y = y + p.top;
+      const float* w = p.wy + (long long)Y * AA_MAX_TAPS;
+      const int n = p.ysize[Y];
+      const float* t0 = tmp + ((long long)(p.ymin[Y] - r_lo) * p.crop + x) * 3;
+      float o[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float v = aa_accumulate(n, w, [&](int j) { return t0[(long long)j * row_vals + c]; });
+        v = fminf(fmaxf(v, 0.f), 255.f);  // torchvision clamps the overshoot before the rounding cast
+        o[c] = lut[c * 256 + (int)rintf(v)];
+      }
+      if (p.fmt == PVR_FMT_NCHW_F32) {
+        float* dst = reinterpret_cast<float*>(p.out) + image * 3 * plane + (long long)y * p.crop + x;
+        dst[0] = o[0];
+        dst[plane] = o[1];
+        dst[2 * plane] = o[2];
+      } else if (p.fmt == PVR_FMT_NHWC4_F32) {
+        float4* dst = reinterpret_cast<float4*>(p.out) + image * plane + (long long)y * p.crop + x;
+        *dst = make_float4(o[0], o[1], o[2], 0.f);
+      } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
+        __nv_bfloat162 b = __floats2bfloat162_rn(o[2], 0.f);
+        uint2 v;
+        v.x = *reinterpret_cast<uint32_t*>(&a);
+        v.y = *reinterpret_cast<uint32_t*>(&b);
+        uint2* dst = reinterpret_cast<uint2*>(p.out) + image * plane + (long long)y * p.crop + x;
+        *dst = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- weight tables, one per (device, input size, output size), built on first use
+struct AATable {
+  int dev, in_size, out_size;
+  int *xmin, *size;
+  float* w;
+};
+std::mutex g_tables_mutex;
+std::vector<AATable> g_tables;
+
+bool aa_table(int in_size, int out_size, cudaStream_t stream, AATable* out, cudaError_t* err) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(g_tables_mutex);
+  for (const AATable& t : g_tables)
+    if (t.dev == dev && t.in_size == in_size && t.out_size == out_size) {
+      *out = t;
+      return true;
+    }
+  AATable t{dev, in_size, out_size, nullptr, nullptr, nullptr};
+  *err = cudaMalloc(&t.xmin, sizeof(int) * out_size);
+  if (*err == cudaSuccess) *err = cudaMalloc(&t.size, sizeof(int) * out_size);
+  if (*err == cudaSuccess) *err = cudaMalloc(&t.w, sizeof(float) * (size_t)out_size * AA_MAX_TAPS);
+  if (*err != cudaSuccess) return false;
+  // first use of a geometry (not capturable: cudaMalloc + synchronisation); the tables are complete before any
+  // consumer on any stream is launched and are never written again
+  aa_weights_kernel<<<(out_size + 127) / 128, 128, 0, stream>>>(in_size, out_size, t.xmin, t.size, t.w);
+  *err = cudaGetLastError();
+  if (*err == cudaSuccess) *err = cudaStreamSynchronize(stream);
+  if (*err != cudaSuccess) return false;
+  g_tables.push_back(t);
+  *out = t;
+  return true;
+}
+
+// upper bound of the taps of one output index, and of the input rows a band of `rows` output rows depends on
+int max_taps(int in_size, int out_size) {
+  const float scale = (float)in_size / (float)out_size;
+  const float support = scale >= 1.f ? 2.f * scale : 2.f;
+  return (int)ceilf(support) * 2 + 1;
+}
+
+}  // namespace
+}  // namespace pvr
+
+extern "C" int pvr_preprocess_u8_aa(const uint8_t* in, int N, int H, int W, int n_frames, int rh, int rw, int top,
+                                    int left, int crop, const float* mean, const float* stdv, void* out, int out_fmt,
+                                    int sample_major, void* stream_) {
+  using namespace pvr;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (!in || !out || N <= 0 || H <= 0 || W <= 0 || n_frames <= 0 || rh <= 0 || rw <= 0 || crop <= 0 || top < 0 ||
+      left < 0 || top + crop > rh || left + crop > rw || !mean || !stdv ||
+      (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16 && out_fmt != PVR_FMT_NHWC4_F32)) {
+    pvr_set_error("pvr_preprocess_u8_aa: invalid argument");
+    return PVR_ERR_ARG;
+  }
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15)) {
+    pvr_set_error("pvr_preprocess_u8_aa: in/out must be 16-byte aligned");
+    return PVR_ERR_ARG;
+  }
+  const int taps_y = max_taps(H, rh), taps_x = max_taps(W, rw);
+  if (taps_y > AA_MAX_TAPS || taps_x > AA_MAX_TAPS) {
+    pvr_set_error("pvr_preprocess_u8_aa: down-scaling factor too large (%d x %d -> %d x %d)", H, W, rh, rw);
+    return PVR_ERR_ARG;
+  }
+  cudaError_t err = cudaSuccess;
+  AATable ty, tx;
+  if (!aa_table(H, rh, stream, &ty, &err) || !aa_table(W, rw, stream, &tx, &err)) {
+    pvr_set_error("pvr_preprocess_u8_aa: weight tables: %s", cudaGetErrorString(err));
+    return PVR_ERR_CUDA;
+  }
+  AAParams p;
+  p.in = in;
+  p.out = out;
+  p.N = N; p.H = H; p.W = W; p.nf = n_frames; p.CH = 3 * n_frames;
+  p.total_bytes = (long long)N * H * W * p.CH;
+  p.top = top; p.left = left; p.crop = crop;
+  p.ymin = ty.xmin; p.ysize = ty.size; p.wy = ty.w;
+  p.xmin = tx.xmin; p.xsize = tx.size; p.wx = tx.w;
+  for (int c = 0; c < 3; ++c) { p.mean[c] = mean[c]; p.stdv[c] = stdv[c]; }
+  p.fmt = out_fmt;
+  p.sample_major = sample_major ? 1 : 0;
+  // rows per band: staged input rows + float32 intermediate rows must fit in shared memory
+  const long long row_bytes = (long long)W * p.CH;
+  const float scale_y = (float)H / (float)rh;
+  auto rows_in = [&](int r) { return (int)ceilf(scale_y * (float)r) + taps_y + 1; };
+  auto smem_bytes = [&](int r, int* tmp_off) {
+    long long off = 16 + 3072 + (long long)rows_in(r) * row_bytes + 48;
+    off = (off + 15) & ~15ll;
+    *tmp_off = (int)off;
+    return off + (long long)rows_in(r) * crop * 3 * 4;
+  };
+  int rows = 16, tmp_off = 0;
+  while (rows > 1 && smem_bytes(rows, &tmp_off) > 160 * 1024) rows >>= 1;
+  const long long smem = smem_bytes(rows, &tmp_off);
+  if (smem > 200 * 1024) {
+    pvr_set_error("pvr_preprocess_u8_aa: input rows too wide for shared-memory staging (%lld bytes)", smem);
+    return PVR_ERR_ARG;
+  }
+  p.rows = rows;
+  p.max_in_rows = rows_in(rows);
+  p.tmp_off = tmp_off;
+  p.bands = (crop + rows - 1) / rows;
+  if ((long long)p.bands * N > 0x7fffffffll) {
+    pvr_set_error("pvr_preprocess_u8_aa: batch too large for one launch");
+    return PVR_ERR_ARG;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(preprocess_aa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { pvr_set_error("pvr_preprocess_u8_aa: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
+    attr = true;
+  }
+  preprocess_aa_kernel<<<(unsigned)(p.bands * N), 256, (size_t)smem, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { pvr_set_error("pvr_preprocess_u8_aa: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
+  return PVR_OK;
+}

@@ -6,6 +6,7 @@ and return types (`numpy (N, O)` float32 in eval mode, squeezed when N == 1, src
 runs in libpvr_b200: the fused uint8 preprocessing kernel and the tcgen05 encoder program. There is no CPU path.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -44,8 +45,10 @@ class Transforms(nn.Module):
     def __init__(self, mean=IMAGENET_MEAN, std=IMAGENET_STD, size=256, crop=224, interpolation='bilinear'):
         super().__init__()
         self.mean, self.std, self.size, self.crop = list(mean), list(std), size, crop
-        assert interpolation in ('bilinear', 'bicubic')
-        self.interpolation = interpolation  # 'bicubic': T.Resize(256, interpolation=3) of the MAE encoders
+        assert interpolation in ('bilinear', 'bicubic', 'bicubic_aa')
+        # 'bicubic': T.Resize(256, interpolation=3) of the MAE encoders; 'bicubic_aa': CLIP's antialiased bicubic Resize
+        # (pvr_preprocess_u8_aa — experimental in round 1: see csrc/preprocess_aa.cu)
+        self.interpolation = interpolation
         self.identity_resize_only = False  # CLIP: bicubic antialiased Resize is only supported when it is a no-op
 
     def run(self, obs_nhwc_u8, n_frames, out_ptr, fmt, sample_major):
@@ -58,12 +61,16 @@ class Transforms(nn.Module):
         rh, rw, top, left = resize_geometry(h, w, self.size, self.crop)
         mean = (ctypes.c_float * 3)(*self.mean)
         std = (ctypes.c_float * 3)(*self.std)
+        fn, name = _lib.lib().pvr_preprocess_u8, "pvr_preprocess_u8"
         if self.interpolation == 'bicubic':
             fmt |= _lib.PVR_RESIZE_BICUBIC
+        elif self.interpolation == 'bicubic_aa' and (rh, rw) != (h, w):
+            # (torchvision leaves an image whose short side already has the requested size untouched,
+            # tv:transforms/functional.py:468-471: that case is the scale-1 path of the bilinear kernel = a copy)
+            fn, name = _lib.lib().pvr_preprocess_u8_aa, "pvr_preprocess_u8_aa"
         with torch.cuda.device(obs_nhwc_u8.device):
-            _lib.check(_lib.lib().pvr_preprocess_u8(obs_nhwc_u8.data_ptr(), n, h, w, n_frames, rh, rw, top, left,
-                                                    self.crop, mean, std, out_ptr, fmt, int(sample_major),
-                                                    _lib.current_stream_ptr()), "pvr_preprocess_u8")
+            _lib.check(fn(obs_nhwc_u8.data_ptr(), n, h, w, n_frames, rh, rw, top, left, self.crop, mean, std, out_ptr,
+                          fmt, int(sample_major), _lib.current_stream_ptr()), name)
 
     def forward(self, x):
         if not x.is_cuda:
@@ -186,8 +193,10 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
         else:
             raise NotImplementedError("Requested model not available.")
         transforms = Transforms(CLIP_MEAN, CLIP_STD, size=model.visual.input_resolution,
-                                crop=model.visual.input_resolution)
-        transforms.identity_resize_only = True
+                                crop=model.visual.input_resolution, interpolation='bicubic_aa')
+        # the antialiased bicubic kernel has not run on a GPU yet (round 1): other frame sizes stay rejected unless the
+        # experiment is switched on
+        transforms.identity_resize_only = os.environ.get("PVR_EXPERIMENTAL_AA") != "1"
     elif embedding_name == 'true_state':
         return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
     else:

@@ -1,0 +1,46 @@
+"""-m gpu, EXPERIMENTAL (skipped unless PVR_EXPERIMENTAL_AA=1): the antialiased bicubic preprocessing kernel
+(pvr_preprocess_u8_aa, CLIP transforms for frames that are not 224x224) against the oracle, which is bit-identical with
+ATen. The kernel compiled but could not be run on a GPU in round 1 (budget spent); its arithmetic core is verified on CPU
+(tests/test_preprocess_aa_core.py). Enable, verify, then drop the gate here and in embeddings._get_embedding."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, restate_vit
+from pvr_habitat_b200 import _lib
+from pvr_habitat_b200.embeddings import CLIP_MEAN, CLIP_STD, Transforms
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("PVR_EXPERIMENTAL_AA") != "1",
+                                 reason="antialiased bicubic kernel not yet verified on a GPU (PVR_EXPERIMENTAL_AA=1)")]
+
+
+def cuda_clip_transforms(obs_nhwc, nf=1):
+    t = Transforms(CLIP_MEAN, CLIP_STD, size=224, crop=224, interpolation="bicubic_aa")
+    n = obs_nhwc.shape[0]
+    out = torch.full((nf * n, 3, 224, 224), float("nan"), device="cuda")
+    t.run(torch.from_numpy(obs_nhwc).cuda(), nf, out.data_ptr(), _lib.PVR_FMT_NCHW_F32, False)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+@pytest.mark.parametrize("hw,nf,n", [((64, 64), 1, 3), ((64, 64), 2, 2), ((96, 128), 1, 2), ((100, 75), 1, 2),
+                                     ((480, 640), 1, 1), ((300, 200), 3, 1), ((224, 224), 1, 2)])
+def test_clip_preprocess_bit_exact_vs_oracle(hw, nf, n):
+    obs = np.random.default_rng(hw[0] * 5 + hw[1] + nf).integers(0, 256, (n, hw[0], hw[1], 3 * nf), dtype=np.uint8)
+    frames, _ = restate.split_frames(obs)
+    want = restate_vit.clip_transforms(frames)
+    got = cuda_clip_transforms(obs, nf)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{int((got != want).sum())} values differ"
+
+
+def test_clip_preprocess_bf16_layout_sample_major():
+    obs = restate.structured_frames(3, 64, 64, 6, 9)
+    t = Transforms(CLIP_MEAN, CLIP_STD, size=224, crop=224, interpolation="bicubic_aa")
+    out = torch.zeros(6, 224, 224, 4, dtype=torch.bfloat16, device="cuda")
+    t.run(torch.from_numpy(obs).cuda(), 2, out.data_ptr(), _lib.PVR_FMT_NHWC4_BF16, True)
+    f32 = cuda_clip_transforms(obs, 2)  # frame-major
+    want = torch.from_numpy(f32).reshape(2, 3, 3, 224, 224).permute(1, 0, 3, 4, 2).reshape(6, 224, 224, 3)
+    assert torch.equal(out[..., :3].cpu(), want.to(torch.bfloat16)) and float(out[..., 3].abs().max()) == 0

@@ -66,6 +66,26 @@ def test_bicubic_resize_matches_aten_bitwise(hw):
     assert (ref.numpy() < 0).any() and (ref.numpy() > 255).any()  # the clamp is exercised
 
 
+@pytest.mark.parametrize("hw", [(64, 64), (96, 128), (100, 75), (480, 640), (300, 200), (84, 84), (225, 231)])
+def test_antialiased_bicubic_resize_matches_aten_bitwise(hw):
+    """CLIP transforms (src/embeddings.py:309-310): Resize(224, BICUBIC, antialias=True) = ATen's separable antialiased
+    bicubic (a = -0.5) on the float image, up- and down-scaling, float bits; then clamp + half-even round."""
+    h, w = hw
+    x = np.random.default_rng(h * 1000 + w + 3).integers(0, 256, (2, 3, h, w), dtype=np.uint8)
+    rh, rw, top, left = restate.resize_geometry(h, w, 224, 224)
+    ref = torch.nn.functional.interpolate(torch.from_numpy(x).float(), size=(rh, rw), mode="bicubic",
+                                          align_corners=False, antialias=True)
+    got = restate.resize_bicubic_aa_f32(x, rh, rw)
+    assert np.array_equal(got.view(np.uint32), ref.numpy().view(np.uint32))
+    u8 = torch.round(ref.clamp(min=0, max=255)).to(torch.uint8)[:, :, top:top + 224, left:left + 224].numpy()
+    assert np.array_equal(restate.resize_crop_u8(x, 224, 224, interpolation="bicubic_aa"), u8)
+
+
+def test_antialiased_bicubic_is_the_identity_at_the_target_size():
+    x = np.random.default_rng(5).integers(0, 256, (1, 3, 224, 224), dtype=np.uint8)
+    assert np.array_equal(restate.resize_crop_u8(x, 224, 224, interpolation="bicubic_aa"), x)
+
+
 def test_normalize_lut_bit_exact(tf):
     assert np.array_equal(restate.normalize_lut().view(np.uint32), tf["lut"].view(np.uint32))
 

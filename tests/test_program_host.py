@@ -240,3 +240,50 @@ def test_set_precision_validates_and_invalidates():
         clip = EmbeddingNet("clip_vit", disable_cuda=True)
     with pytest.raises(NotImplementedError):
         clip.set_precision("fp32")
+
+
+# ------------------------------------------------------------------------------------------------ transforms dispatch
+def test_transforms_dispatch_per_interpolation(monkeypatch):
+    """Which C entry point / format flag `Transforms.run` uses: bilinear (default), bicubic (MAE: flag on out_fmt),
+    antialiased bicubic (CLIP: own entry point, except for the identity resize, which stays on the plain kernel)."""
+    import contextlib
+    from pvr_habitat_b200 import _lib
+    from pvr_habitat_b200.embeddings import CLIP_MEAN, CLIP_STD, Transforms
+    calls = []
+
+    class FakeLib:
+        def pvr_preprocess_u8(self, *a):
+            calls.append(("plain",) + a)
+            return 0
+
+        def pvr_preprocess_u8_aa(self, *a):
+            calls.append(("aa",) + a)
+            return 0
+
+    monkeypatch.setattr(_lib, "lib", lambda: FakeLib())
+    monkeypatch.setattr(_lib, "current_stream_ptr", lambda: 0)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    obs64 = torch.zeros(2, 64, 64, 6, dtype=torch.uint8)
+    obs224 = torch.zeros(1, 224, 224, 3, dtype=torch.uint8)
+    Transforms().run(obs64, 2, 1234, _lib.PVR_FMT_STEM_BF16, True)
+    Transforms(interpolation="bicubic").run(obs64, 2, 1234, _lib.PVR_FMT_NHWC4_BF16, True)
+    clip = Transforms(CLIP_MEAN, CLIP_STD, size=224, crop=224, interpolation="bicubic_aa")
+    clip.run(obs64, 2, 1234, _lib.PVR_FMT_NHWC4_BF16, True)
+    clip.run(obs224, 1, 1234, _lib.PVR_FMT_NHWC4_BF16, True)
+    kinds = [c[0] for c in calls]
+    assert kinds == ["plain", "plain", "aa", "plain"]
+    # (in, N, H, W, n_frames, rh, rw, top, left, crop, mean, std, out, fmt, sample_major, stream)
+    assert calls[0][2:11] == (2, 64, 64, 2, 256, 256, 16, 16, 224) and calls[0][14] == _lib.PVR_FMT_STEM_BF16
+    assert calls[1][14] == _lib.PVR_FMT_NHWC4_BF16 | _lib.PVR_RESIZE_BICUBIC
+    assert calls[2][2:11] == (2, 64, 64, 2, 224, 224, 0, 0, 224) and calls[2][14] == _lib.PVR_FMT_NHWC4_BF16
+    assert calls[3][2:11] == (1, 224, 224, 1, 224, 224, 0, 0, 224) and calls[3][14] == _lib.PVR_FMT_NHWC4_BF16
+    assert [round(v, 4) for v in calls[2][11]] == [round(v, 4) for v in CLIP_MEAN]
+    # the gate of round 1: CLIP nets reject other frame sizes unless the experiment is switched on
+    with allow_random_init():
+        net = EmbeddingNet("clip_vit", disable_cuda=True)
+    assert net.transforms.interpolation == "bicubic_aa" and net.transforms.identity_resize_only
+    with pytest.raises(NotImplementedError):
+        net.transforms.run(obs64[..., :3].contiguous(), 1, 1234, _lib.PVR_FMT_NHWC4_BF16, True)
+    monkeypatch.setenv("PVR_EXPERIMENTAL_AA", "1")
+    with allow_random_init():
+        assert not EmbeddingNet("clip_vit", disable_cuda=True).transforms.identity_resize_only

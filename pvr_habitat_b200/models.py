@@ -206,7 +206,7 @@ class PolicyNet(nn.Module):
         step is being captured into a CUDA graph (BCTrainer on one GPU: launches cost no host time at replay), 1 in
         eager mode, where the step is bound by the host's launch rate and more launches would only slow it down."""
         env = os.environ.get("PVR_LSTM_CHUNKS")
-        c = int(env) if env else (8 if torch.cuda.is_current_stream_capturing() else 1)
+        c = int(env) if env else (8 if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing() else 1)
         while c > 1 and (T % c or T // c < 2):
             c //= 2
         return max(c, 1)

@@ -90,3 +90,17 @@ def test_checkpoint_roundtrip_has_reference_schema(tmp_path):
     with pytest.raises(KeyError):
         torch.save({"model": {}}, path + ".bad")
         bc.load_checkpoint(path + ".bad")
+
+
+def test_lstm_wavefront_chunk_count(monkeypatch):
+    """PolicyNet._lstm_chunks: the environment override, halving until the chunks divide T with at least two steps
+    each, and the eager default (1: the two-stream wavefront is only the default inside a captured step)."""
+    net = PolicyNet((16,), 3)
+    monkeypatch.delenv("PVR_LSTM_CHUNKS", raising=False)
+    assert [net._lstm_chunks(t) for t in (1, 7, 64, 100)] == [1, 1, 1, 1]      # not capturing on CPU
+    monkeypatch.setenv("PVR_LSTM_CHUNKS", "8")
+    assert [net._lstm_chunks(t) for t in (1, 2, 7, 8, 16, 64, 100, 12)] == [1, 1, 1, 4, 8, 8, 4, 4]
+    monkeypatch.setenv("PVR_LSTM_CHUNKS", "16")
+    assert net._lstm_chunks(64) == 16 and net._lstm_chunks(16) == 8
+    monkeypatch.setenv("PVR_LSTM_CHUNKS", "1")
+    assert net._lstm_chunks(64) == 1

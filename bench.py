@@ -176,6 +176,7 @@ def cpu_port_frames_per_s(name, n_frames, n_obs, threads):
 
 BC_CFG = dict(n=65536, D=2048, T=64, B=128, A=3)  # BASELINE configs[4]: global batch T*B = 8192, batch_norm=True
 BC_GFLOP_PER_STEP = 979.0  # fwd+bwd 119.6 MFLOP/sample x 8192
+BC_CPU_STEPS = 8           # CPU baseline sample: about 6-10 s on 16 host cores
 
 
 def bc_dataset(seed=7):
@@ -226,16 +227,16 @@ def bench_bc(steps, warmup, world, dist, host_batches):
 
 
 def cpu_port_bc_steps_per_s(threads):
-    """Oracle CPU port of one BC step at the same shape (bounded sample: 1 step after a small warm-up)."""
+    """Oracle CPU port of BC steps at the same shape (bounded sample: BC_CPU_STEPS steps after a small warm-up)."""
     from oracle import restate_policy as rp
     torch.set_num_threads(threads)
     obs, action, done, _ = bc_dataset()
     sd = rp.init_policy_state(BC_CFG["D"], BC_CFG["A"], True, 1)
     rp.bc_train(sd, obs, action, done, 4, 8, 1, 10 ** 9, True)  # warm-up at a tiny shape
     t0 = time.perf_counter()
-    rp.bc_train(sd, obs, action, done, BC_CFG["T"], BC_CFG["B"], 1, 10 ** 9, True)
+    rp.bc_train(sd, obs, action, done, BC_CFG["T"], BC_CFG["B"], BC_CPU_STEPS, 10 ** 9, True)
     dt = time.perf_counter() - t0
-    return 1.0 / dt, dt
+    return BC_CPU_STEPS / dt, dt
 
 
 def run_reference(args):
@@ -481,7 +482,9 @@ def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_ste
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        n_obs = 24 if n_frames == 3 else (32 if name in ("clip_vit_b16", "mae_base") else (16 if name == "mae_large" else 96))
+        # bounded sample of about 10-15 s of CPU work at the rates these oracle ports reach on 16 host cores
+        n_obs = {"moco_aug_uber_34": 80, "moco_aug": 256, "clip_vit_b16": 128, "mae_base": 128, "mae_large": 96,
+                 "clip_vit": 384}.get(name, 96)
         v, dt = cpu_port_frames_per_s(name, n_frames, n_obs, threads)
         cpu_baseline = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
                         "sample": f"{n_obs} observations x {n_frames} frames of the same workload, mini-batch 64, "
@@ -489,8 +492,8 @@ def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_ste
         if bc is not None:
             v_bc, dt_bc = cpu_port_bc_steps_per_s(threads)
             bc["cpu_baseline"] = {"value": v_bc, "unit": "steps/s", "cores": threads, "kind": "port",
-                                  "sample": f"1 step at the same shape (T=64, B=128, D=2048), torch CPU fp32 oracle "
-                                            f"port, {dt_bc:.1f} s"}
+                                  "sample": f"{BC_CPU_STEPS} steps at the same shape (T=64, B=128, D=2048), torch CPU fp32 "
+                                            f"oracle port, {dt_bc:.1f} s"}
 
     line = {
         "metric": "pvr_frames_per_sec_embedded", "value": value, "unit": "frames/s", "n_gpus": world,

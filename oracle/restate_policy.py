@@ -108,7 +108,7 @@ def bc_train(sd, obs, action, done, T, B, steps, max_frames, batch_norm, lr=1e-4
                 g = g * coef
                 square_avg[k].mul_(alpha).addcmul_(g, g, value=1 - alpha)
                 params[k].addcdiv_(g, square_avg[k].sqrt().add_(eps), value=-lr_k)  # eps outside the sqrt
-        trace.append((float(loss), norm))
+        trace.append((float(loss.detach()), norm))
     for k in params:
         sd[k] = params[k].detach()
     return trace

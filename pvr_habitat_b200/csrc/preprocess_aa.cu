@@ -29,15 +29,13 @@ namespace pvr {
 namespace {
 
 struct AAParams {
+  AAGeom g;
   const uint8_t* in;
   void* out;
   long long total_bytes;
-  int N, H, W, CH, nf;
-  int top, left, crop, rows, bands, max_in_rows;
-  const int *ymin, *ysize, *xmin, *xsize;
-  const float *wy, *wx;
+  int max_in_rows;
   float mean[3], stdv[3];
-  int fmt, sample_major;
+  int fmt;
   int tmp_off;  // byte offset of the float32 intermediate inside dynamic smem
 };
 
@@ -52,20 +50,14 @@ __global__ void __launch_bounds__(256) preprocess_aa_kernel(const AAParams p) {
   float* lut = reinterpret_cast<float*>(smem + 16);  // [3][256]
   uint8_t* stage = smem + 16 + 3 * 256 * 4;
   float* tmp = reinterpret_cast<float*>(smem + p.tmp_off);
+  const AAGeom& g = p.g;
 
-  const int img = blockIdx.x / p.bands;
-  const int band = blockIdx.x - img * p.bands;
-  const int y_first = band * p.rows;
-  const int y_count = min(p.rows, p.crop - y_first);
-  const int y_last = y_first + y_count - 1 + p.top;
-  const int r_lo = p.ymin[y_first + p.top];
-  const int r_hi = p.ymin[y_last] + p.ysize[y_last] - 1;  // tap ranges move monotonically with the output row
-  const int rows_in = r_hi - r_lo + 1;
-  if (rows_in > p.max_in_rows) __trap();  // the host sized the shared memory from an upper bound
+  const AABand b = aa_band(g, blockIdx.x);
+  if (b.rows_in > p.max_in_rows) __trap();  // the host sized the shared memory from an upper bound
 
-  const long long row_bytes = (long long)p.W * p.CH;
-  const long long g0 = ((long long)img * p.H + r_lo) * row_bytes;
-  const long long nbytes = (long long)rows_in * row_bytes;
+  const long long row_bytes = (long long)g.W * g.CH;
+  const long long g0 = ((long long)b.img * g.H + b.r_lo) * row_bytes;
+  const long long nbytes = (long long)b.rows_in * row_bytes;
   const long long a0 = g0 & ~15ll;
   const int head = (int)(g0 - a0);
   const long long want = (head + nbytes + 15) & ~15ll;
@@ -78,64 +70,36 @@ __global__ void __launch_bounds__(256) preprocess_aa_kernel(const AAParams p) {
     bulk_load_1d(stage, p.in + a0, bulk, bar);
   }
   for (long long t = bulk + threadIdx.x; t < head + nbytes; t += blockDim.x) stage[t] = p.in[a0 + t];
-  for (int t = threadIdx.x; t < 768; t += blockDim.x) {
-    const int c = t >> 8, u = t & 255;
-    lut[t] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)u, 255.0f), p.mean[c]), p.stdv[c]);
-  }
+  aa_build_lut(lut, p.mean, p.stdv, threadIdx.x, blockDim.x);
   __syncthreads();
   mbar_wait(bar, 0);
 
   const uint8_t* s = stage + head;
-  const long long plane = (long long)p.crop * p.crop;
-  const int row_vals = p.crop * 3;
-  for (int f = 0; f < p.nf; ++f) {
-    // horizontal pass: tmp[r][x][c] for the staged rows and the crop's columns
-    for (int idx = threadIdx.x; idx < rows_in * row_vals; idx += blockDim.x) {
-      const int r = idx / row_vals;
-      const int rem = idx - r * row_vals;
-      const int x = rem / 3;
-      const int c = rem - x * 3;
-      const int X = x + p.left;
-      const uint8_t* src = s + (long long)r * row_bytes + (long long)p.xmin[X] * p.CH + 3 * f + c;
-      const int CH = p.CH;
-      tmp[idx] = aa_accumulate(p.xsize[X], p.wx + (long long)X * AA_MAX_TAPS, [&](int j) { return (float)src[j * CH]; });
-    }
+  const long long plane = (long long)g.crop * g.crop;
+  const int crop = g.crop, fmt = p.fmt;
+  void* out = p.out;
+  for (int f = 0; f < g.nf; ++f) {
+    aa_horizontal(g, b, s, tmp, f, threadIdx.x, blockDim.x);
     __syncthreads();
-    // vertical pass + clamp + half-even round + normalisation table
-    const long long image = p.sample_major ? (long long)img * p.nf + f : (long long)f * p.N + img;
-    for (int idx = threadIdx.x; idx < y_count * p.crop; idx += blockDim.x) {
-      const int yy = idx / p.crop;
-      const int x = idx - yy * p.crop;
-      const int y = y_first + yy;
-      const int Y = y + p.top;
-      const float* w = p.wy + (long long)Y * AA_MAX_TAPS;
-      const int n = p.ysize[Y];
-      const float* t0 = tmp + ((long long)(p.ymin[Y] - r_lo) * p.crop + x) * 3;
-      float o[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float v = aa_accumulate(n, w, [&](int j) { return t0[(long long)j * row_vals + c]; });
-        v = fminf(fmaxf(v, 0.f), 255.f);  // torchvision clamps the overshoot before the rounding cast
-        o[c] = lut[c * 256 + (int)rintf(v)];
-      }
-      if (p.fmt == PVR_FMT_NCHW_F32) {
-        float* dst = reinterpret_cast<float*>(p.out) + image * 3 * plane + (long long)y * p.crop + x;
+    aa_vertical(g, b, tmp, lut, f, threadIdx.x, blockDim.x, [&](long long image, int y, int x, const float* o) {
+      if (fmt == PVR_FMT_NCHW_F32) {
+        float* dst = reinterpret_cast<float*>(out) + image * 3 * plane + (long long)y * crop + x;
         dst[0] = o[0];
         dst[plane] = o[1];
         dst[2 * plane] = o[2];
-      } else if (p.fmt == PVR_FMT_NHWC4_F32) {
-        float4* dst = reinterpret_cast<float4*>(p.out) + image * plane + (long long)y * p.crop + x;
+      } else if (fmt == PVR_FMT_NHWC4_F32) {
+        float4* dst = reinterpret_cast<float4*>(out) + image * plane + (long long)y * crop + x;
         *dst = make_float4(o[0], o[1], o[2], 0.f);
       } else {
         __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
-        __nv_bfloat162 b = __floats2bfloat162_rn(o[2], 0.f);
+        __nv_bfloat162 bb = __floats2bfloat162_rn(o[2], 0.f);
         uint2 v;
         v.x = *reinterpret_cast<uint32_t*>(&a);
-        v.y = *reinterpret_cast<uint32_t*>(&b);
-        uint2* dst = reinterpret_cast<uint2*>(p.out) + image * plane + (long long)y * p.crop + x;
+        v.y = *reinterpret_cast<uint32_t*>(&bb);
+        uint2* dst = reinterpret_cast<uint2*>(out) + image * plane + (long long)y * crop + x;
         *dst = v;
       }
-    }
+    });
     __syncthreads();
   }
 }
@@ -211,18 +175,19 @@ extern "C" int pvr_preprocess_u8_aa(const uint8_t* in, int N, int H, int W, int 
     return PVR_ERR_CUDA;
   }
   AAParams p;
+  AAGeom& g = p.g;
   p.in = in;
   p.out = out;
-  p.N = N; p.H = H; p.W = W; p.nf = n_frames; p.CH = 3 * n_frames;
-  p.total_bytes = (long long)N * H * W * p.CH;
-  p.top = top; p.left = left; p.crop = crop;
-  p.ymin = ty.xmin; p.ysize = ty.size; p.wy = ty.w;
-  p.xmin = tx.xmin; p.xsize = tx.size; p.wx = tx.w;
+  g.N = N; g.H = H; g.W = W; g.nf = n_frames; g.CH = 3 * n_frames;
+  p.total_bytes = (long long)N * H * W * g.CH;
+  g.top = top; g.left = left; g.crop = crop;
+  g.ymin = ty.xmin; g.ysize = ty.size; g.wy = ty.w;
+  g.xmin = tx.xmin; g.xsize = tx.size; g.wx = tx.w;
   for (int c = 0; c < 3; ++c) { p.mean[c] = mean[c]; p.stdv[c] = stdv[c]; }
   p.fmt = out_fmt;
-  p.sample_major = sample_major ? 1 : 0;
+  g.sample_major = sample_major ? 1 : 0;
   // rows per band: staged input rows + float32 intermediate rows must fit in shared memory
-  const long long row_bytes = (long long)W * p.CH;
+  const long long row_bytes = (long long)W * g.CH;
   const float scale_y = (float)H / (float)rh;
   auto rows_in = [&](int r) { return (int)ceilf(scale_y * (float)r) + taps_y + 1; };
   auto smem_bytes = [&](int r, int* tmp_off) {
@@ -238,11 +203,11 @@ extern "C" int pvr_preprocess_u8_aa(const uint8_t* in, int N, int H, int W, int 
     pvr_set_error("pvr_preprocess_u8_aa: input rows too wide for shared-memory staging (%lld bytes)", smem);
     return PVR_ERR_ARG;
   }
-  p.rows = rows;
+  g.rows = rows;
   p.max_in_rows = rows_in(rows);
   p.tmp_off = tmp_off;
-  p.bands = (crop + rows - 1) / rows;
-  if ((long long)p.bands * N > 0x7fffffffll) {
+  g.bands = (crop + rows - 1) / rows;
+  if ((long long)g.bands * N > 0x7fffffffll) {
     pvr_set_error("pvr_preprocess_u8_aa: batch too large for one launch");
     return PVR_ERR_ARG;
   }
@@ -252,7 +217,7 @@ extern "C" int pvr_preprocess_u8_aa(const uint8_t* in, int N, int H, int W, int 
     if (e != cudaSuccess) { pvr_set_error("pvr_preprocess_u8_aa: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
     attr = true;
   }
-  preprocess_aa_kernel<<<(unsigned)(p.bands * N), 256, (size_t)smem, stream>>>(p);
+  preprocess_aa_kernel<<<(unsigned)(g.bands * N), 256, (size_t)smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { pvr_set_error("pvr_preprocess_u8_aa: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
   return PVR_OK;

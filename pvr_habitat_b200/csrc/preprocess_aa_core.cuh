@@ -98,4 +98,79 @@ PVR_HD float aa_accumulate(int n, const float* w, Get get) {
   return o;
 }
 
+// ---- the kernel's work decomposition, also host/device so that the harness runs the very same index arithmetic
+struct AAGeom {
+  int N, H, W, CH, nf;              // observations (N, H, W, CH = 3 * nf) uint8
+  int top, left, crop, rows, bands; // crop window inside the resized image; output rows per band; bands per image
+  const int *ymin, *ysize, *xmin, *xsize;  // tap ranges per resized row / column
+  const float *wy, *wx;                    // weights, AA_MAX_TAPS per row / column
+  int sample_major;                        // image index of (sample i, frame f): i*nf + f instead of f*N + i
+};
+
+struct AABand {
+  int img, y_first, y_count;  // observation, first output row (inside the crop) and number of rows of this band
+  int r_lo, rows_in;          // input rows the band depends on: [r_lo, r_lo + rows_in)
+};
+
+PVR_HD AABand aa_band(const AAGeom& g, int block) {
+  AABand b;
+  b.img = block / g.bands;
+  const int band = block - b.img * g.bands;
+  b.y_first = band * g.rows;
+  b.y_count = g.crop - b.y_first < g.rows ? g.crop - b.y_first : g.rows;
+  const int y_last = b.y_first + b.y_count - 1 + g.top;
+  b.r_lo = g.ymin[b.y_first + g.top];  // tap ranges move monotonically with the output row
+  b.rows_in = g.ymin[y_last] + g.ysize[y_last] - b.r_lo;
+  return b;
+}
+
+// ((u / 255) - mean) / std for every uint8 value, each operation rounded to float32 like the reference
+PVR_HD void aa_build_lut(float* lut, const float* mean, const float* stdv, int tid, int nthreads) {
+  for (int t = tid; t < 768; t += nthreads) {
+    const int c = t >> 8, u = t & 255;
+    lut[t] = PVR_AA_DIV(PVR_AA_SUB(PVR_AA_DIV((float)u, 255.0f), mean[c]), stdv[c]);
+  }
+}
+
+// horizontal pass of frame f: tmp[r][x][c] for the band's input rows (s = first byte of input row r_lo) and the crop's
+// columns
+PVR_HD void aa_horizontal(const AAGeom& g, const AABand& b, const uint8_t* s, float* tmp, int f, int tid, int nthreads) {
+  const long long row_bytes = (long long)g.W * g.CH;
+  const int row_vals = g.crop * 3;
+  const int CH = g.CH;
+  for (int idx = tid; idx < b.rows_in * row_vals; idx += nthreads) {
+    const int r = idx / row_vals;
+    const int rem = idx - r * row_vals;
+    const int x = rem / 3;
+    const int c = rem - x * 3;
+    const int X = x + g.left;
+    const uint8_t* src = s + (long long)r * row_bytes + (long long)g.xmin[X] * CH + 3 * f + c;
+    tmp[idx] = aa_accumulate(g.xsize[X], g.wx + (long long)X * AA_MAX_TAPS, [&](int j) { return (float)src[j * CH]; });
+  }
+}
+
+// vertical pass of frame f + clamp + half-even round + normalisation table; store(image, y, x, o[3]) writes the pixel
+template <class Store>
+PVR_HD void aa_vertical(const AAGeom& g, const AABand& b, const float* tmp, const float* lut, int f, int tid,
+                        int nthreads, Store store) {
+  const int row_vals = g.crop * 3;
+  const long long image = g.sample_major ? (long long)b.img * g.nf + f : (long long)f * g.N + b.img;
+  for (int idx = tid; idx < b.y_count * g.crop; idx += nthreads) {
+    const int yy = idx / g.crop;
+    const int x = idx - yy * g.crop;
+    const int y = b.y_first + yy;
+    const int Y = y + g.top;
+    const float* w = g.wy + (long long)Y * AA_MAX_TAPS;
+    const int n = g.ysize[Y];
+    const float* t0 = tmp + ((long long)(g.ymin[Y] - b.r_lo) * g.crop + x) * 3;
+    float o[3];
+    for (int c = 0; c < 3; ++c) {
+      float v = aa_accumulate(n, w, [&](int j) { return t0[(long long)j * row_vals + c]; });
+      v = fminf(fmaxf(v, 0.f), 255.f);  // torchvision clamps the overshoot before the rounding cast
+      o[c] = lut[c * 256 + (int)rintf(v)];
+    }
+    store(image, y, x, o);
+  }
+}
+
 }  // namespace pvr

@@ -454,6 +454,8 @@ class PolicyNet(nn.Module):
         runs eagerly (lazy allocations, kernel attributes); results are the eager path's, bit for bit."""
         T, B = notdone.shape
         key = (T, B, str(self.device))
+        if key not in self._rollout and len(self._rollout) >= 8:
+            self._rollout.clear()  # many distinct shapes: drop the captured graphs (and the workspaces they pin)
         g = self._rollout.setdefault(key, {"calls": 0})
         g["calls"] += 1
         if g["calls"] == 1:

@@ -380,3 +380,34 @@ def test_lstm_wavefront_chunks_equal_the_layer_by_layer_schedule(T, B, monkeypat
     assert set(g1) == set(g2)
     for k in g1:
         assert rel(g1[k], g2[k]) < 1e-2, (k, rel(g1[k], g2[k]))  # dG is rounded to bf16 after the noisy fp32 sums
+
+
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: not yet run on a GPU; the CPU "
+                                        "emulation of the same rounding points (tests/test_policy_bf16_budget_cpu.py) "
+                                        "meets the bound")
+def test_trained_policy_argmax_agreement_vs_oracle():
+    """North star: policy action argmax identical on >= 99.9 % of frames. A policy trained for 40 BC steps on the CUDA
+    path (logit margins opened up), then the CUDA eval forward against the fp32 oracle on 4096 frames with the same
+    weights."""
+    D, n = 256, 8192
+    rng = np.random.default_rng(0)
+    obs = np.maximum(rng.standard_normal((n, D)).astype(np.float32), 0)
+    w = rng.standard_normal((D, 3)).astype(np.float32) / np.sqrt(D)
+    action = (obs @ w + 0.3 * rng.standard_normal((n, 3)).astype(np.float32)).argmax(1)
+    done = rng.random(n) < 1 / 200
+    torch.manual_seed(1)
+    random.seed(1)
+    net = PolicyNet((D,), 3, True).cuda().train()
+    tr = BCTrainer(net, obs, action, done, 32, 16, 10 ** 9)
+    losses = [float(tr.step()) for _ in range(40)]
+    assert losses[-1] < losses[0]
+    net.eval()
+    sd = {k: v.detach().cpu().clone() for k, v in net.state_dict().items()}
+    o = torch.from_numpy(obs[:4096]).view(64, 64, D)
+    d = torch.from_numpy(done[:4096]).view(64, 64)
+    with torch.no_grad():
+        out, _ = net(dict(obs=o, done=d), net.initial_state(64))
+        ref, _, _ = rp.policy_forward(sd, o, d, (torch.zeros(2, 64, 1024), torch.zeros(2, 64, 1024)), True, False)
+    agree = float((out["policy_logits"].argmax(-1).cpu() == ref.argmax(-1)).float().mean())
+    assert torch.equal(out["action"], out["policy_logits"].argmax(-1))
+    assert rel(out["policy_logits"], ref) < 1e-2 and agree >= 0.999, (agree, rel(out["policy_logits"], ref))

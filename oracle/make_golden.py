@@ -284,6 +284,51 @@ def golden_mae(E):
     np.savez_compressed(os.path.join(GOLDEN, "mae.npz"), **out)
 
 
+def golden_clip_transforms(E):
+    """The `transforms` the reference builds for 'clip_vit' (src/embeddings.py:309-314: antialiased bicubic Resize(224)
+    -> CenterCrop(224) -> float -> CLIP Normalize), run on frames that are not 224x224 (Habitat renders 64x64). The
+    `clip` package is not installed: `clip.load` is replaced by a stand-in that only carries `visual.input_resolution`,
+    which is all `_get_embedding` reads before building the transforms; the network itself is not used here."""
+    import types
+
+    class FakeClipModel(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.visual = types.SimpleNamespace(input_resolution=224)
+            self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    fake = types.ModuleType("clip")
+    fake.load = lambda name, device="cpu": (FakeClipModel(), None)
+    old = getattr(E, "clip", None)
+    E.clip = fake
+    try:
+        _, tf = E._get_embedding("clip_vit")
+    finally:
+        if old is not None:
+            E.clip = old
+    resize_crop = torch.nn.Sequential(tf[0], tf[1])
+    to_float = torch.nn.Sequential(tf[2], tf[3])
+    cases = {
+        "structured_64": restate.structured_frames(2, 64, 64, 3, 51),
+        "structured_96x128": restate.structured_frames(1, 96, 128, 3, 52),
+        "noise_100x75": np.random.default_rng(53).integers(0, 256, (1, 100, 75, 3), dtype=np.uint8),
+        "structured_336x448": restate.structured_frames(1, 336, 448, 3, 54),
+        "adversarial_64": restate.adversarial_frames(64, 64),
+        "noise_224": np.random.default_rng(55).integers(0, 256, (1, 224, 224, 3), dtype=np.uint8),
+    }
+    out = {}
+    for name, frames in cases.items():
+        x = torch.from_numpy(frames).permute(0, 3, 1, 2).contiguous()
+        u = resize_crop(x)
+        assert u.dtype == torch.uint8 and tuple(u.shape[2:]) == (224, 224)
+        out["in_" + name] = frames
+        out["u8_" + name] = u.numpy()
+    ramp = torch.arange(256, dtype=torch.uint8).view(1, 1, 16, 16).repeat(1, 3, 1, 1)
+    out["lut"] = to_float(ramp).numpy().reshape(3, 256)
+    np.savez_compressed(os.path.join(GOLDEN, "clip_transforms.npz"), **out)
+    print("clip_transforms.npz:", {k: v.shape for k, v in out.items() if k.startswith("u8_")})
+
+
 def golden_save_embedded(E):
     """behavioral_cloning/save_embedded_obs.py `run(flags)` UNMODIFIED, both sources, on three synthetic ImageNav-style
     trajectories (64x64, current || goal = 6 channels) with the 'random' encoder on CPU: the file names, pickle layouts
@@ -347,8 +392,10 @@ def main():
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
     if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which or \
-            "mae" in which or "save_embedded" in which:
+            "mae" in which or "save_embedded" in which or "clip_transforms" in which:
         E = refshim.reference_embeddings()
+        if "clip_transforms" in which:
+            golden_clip_transforms(E)
         if "save_embedded" in which:
             golden_save_embedded(E)
         if "mae" in which:

@@ -44,3 +44,15 @@ def test_clip_preprocess_bf16_layout_sample_major():
     f32 = cuda_clip_transforms(obs, 2)  # frame-major
     want = torch.from_numpy(f32).reshape(2, 3, 3, 224, 224).permute(1, 0, 3, 4, 2).reshape(6, 224, 224, 3)
     assert torch.equal(out[..., :3].cpu(), want.to(torch.bfloat16)) and float(out[..., 3].abs().max()) == 0
+
+
+@pytest.mark.parametrize("case", ["structured_64", "structured_96x128", "noise_100x75", "structured_336x448",
+                                  "adversarial_64", "noise_224"])
+def test_clip_preprocess_bit_exact_vs_reference_golden(golden_dir, case):
+    """Against the uint8 images / normalisation table of the reference's own 'clip_vit' transforms
+    (tests/golden/clip_transforms.npz)."""
+    g = np.load(os.path.join(golden_dir, "clip_transforms.npz"))
+    u = g["u8_" + case]
+    want = np.stack([g["lut"][c][u[:, c]] for c in range(3)], 1)
+    got = cuda_clip_transforms(g["in_" + case])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{int((got != want).sum())} values differ"

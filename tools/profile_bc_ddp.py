@@ -3,6 +3,12 @@ captured. EXPERIMENT, not on by default: BCTrainer only replays the step from a 
 round 1 (use_graph forced on with world 2, NCCL all-reduces inside torch.cuda.graph) did not finish within 200 s and
 was killed by its timeout; the cause (NCCL capture vs. the side-stream fork/join of the LSTM wavefront vs. the
 watchdog thread) is not isolated yet. BCTrainer ignores use_graph=True for world > 1 until that is understood.
+What the trial had changed in BCTrainer._graph_step (reverted; re-apply for the experiment): capture with
+`torch.cuda.graph(g, capture_error_mode="thread_local")`, all-reduce `self._gloss` inside the capture when world > 1,
+all-reduce the loss of the three eager warm-up steps too, and allow `use_graph` for world > 1 when
+`batch_size % world == 0`. Things to try first: TORCH_NCCL_ASYNC_ERROR_HANDLING=0 before init_process_group (PyTorch's
+recipe for capturing NCCL collectives), PVR_LSTM_CHUNKS=1 inside the capture (no side-stream fork/join), and a
+side-stream warm-up before the capture.
 Usage: torchrun --nproc-per-node N tools/profile_bc_ddp.py [STEPS] [eager|graph ...]   (default: eager only)"""
 import os
 import random

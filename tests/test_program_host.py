@@ -287,3 +287,42 @@ def test_transforms_dispatch_per_interpolation(monkeypatch):
     monkeypatch.setenv("PVR_EXPERIMENTAL_AA", "1")
     with allow_random_init():
         assert not EmbeddingNet("clip_vit", disable_cuda=True).transforms.identity_resize_only
+
+
+# ------------------------------------------------------------------------------------------------ name coverage
+REFERENCE_NAMES = """clip_rn50 clip_vit demy mae_base mae_huge mae_large maskrcnn_l3 moco_aug moco_aug_habitat moco_aug_l3
+moco_aug_l4 moco_aug_mujoco moco_aug_places moco_aug_places_l3 moco_aug_places_l4 moco_aug_places_uber_34
+moco_aug_places_uber_345 moco_aug_places_uber_35 moco_aug_places_uber_45 moco_aug_uber moco_aug_uber_34 moco_aug_uber_345
+moco_aug_uber_35 moco_aug_uber_45 moco_coloronly moco_croponly moco_croponly_habitat moco_croponly_l3 moco_croponly_l4
+moco_croponly_mujoco moco_croponly_places moco_croponly_places_l3 moco_croponly_places_l4 moco_croponly_places_uber_34
+moco_croponly_places_uber_345 moco_croponly_places_uber_35 moco_croponly_places_uber_45 moco_croponly_uber
+moco_croponly_uber_34 moco_croponly_uber_345 moco_croponly_uber_35 moco_croponly_uber_45 random resnet18 resnet34 resnet50
+resnet50_l3 resnet50_l4 resnet50_places resnet50_places_l3 resnet50_places_l4 true_state""".split()
+NOT_BUILT = {"clip_rn50", "mae_huge", "maskrcnn_l3"}  # DESIGN.md §6
+
+
+def test_every_reference_embedding_name_is_accounted_for():
+    """The 52 names `_get_embedding` accepts in the reference (every `embedding_name == '...'` of src/embeddings.py:
+    88-318): 49 build here with the reference's output width, 3 raise NotImplementedError like an unknown name."""
+    widths = {"conv5": 2048, "l4": 2058, "l3": 2156}
+    assert len(REFERENCE_NAMES) == 52
+    with allow_random_init():
+        for name in REFERENCE_NAMES:
+            if name in NOT_BUILT:
+                with pytest.raises(NotImplementedError):
+                    _get_embedding(name)
+                continue
+            model, transforms = _get_embedding(name)
+            if name == "true_state":
+                continue
+            if "_uber_" in name:
+                want = sum(widths[{"3": "l3", "4": "l4", "5": "conv5"}[t]] for t in name.split("_uber_")[1])
+            elif name.endswith(("_l3", "_l4")):
+                want = widths[name[-2:]]
+            else:
+                want = {"random": 1568, "resnet18": 512, "resnet34": 512, "clip_vit": 512, "mae_base": 768,
+                        "mae_large": 1024}.get(name, 2048)
+            assert int(model.out_size) == want, name
+            assert not model.training and all(not p.requires_grad for p in model.parameters()), name
+    with pytest.raises(NotImplementedError):
+        _get_embedding("no_such_model")

@@ -51,3 +51,25 @@ def test_op_struct_layout_matches_header():
     """pvr_op: 34 int32 fields then 4 pointers (ctypes mirror of the C struct)."""
     assert ctypes.sizeof(_lib.pvr_op) == 34 * 4 + 4 * 8
     assert _lib.pvr_op.weight.offset == 136
+
+
+def test_product_code_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may use it."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b", re.M)
+    offenders = []
+    for base, _, files in os.walk(os.path.join(root, "pvr_habitat_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(base, f), errors="ignore") as fh:
+                    if pat.search(fh.read()):
+                        offenders.append(os.path.join(base, f))
+    assert offenders == []
+    # the GPU arm of bench.py reaches the oracle only through its CPU legs
+    src = open(os.path.join(root, "bench.py")).read()
+    for m in pat.finditer(src):
+        func = src[:m.start()].rsplit("\ndef ", 1)[1].split("(", 1)[0]
+        assert func in ("oracle_parts", "oracle_embed", "cpu_port_frames_per_s", "cpu_port_bc_steps_per_s",
+                        "run_reference"), func

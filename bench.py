@@ -59,16 +59,19 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms; `mark_start()` / `mark_end()` bracket the timed region
+    and only samples read inside it count (the samples around it are idle: with the load gone the power cap lifts and
+    the SM clock jumps to its maximum, which is not the clock the measurement ran at)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc = [], None   # rows: (host time when read, fields)
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -77,24 +80,37 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    @staticmethod
+    def summarise(rows, t0, t1):
+        """rows: (time, fields). Samples read inside [t0 + 50 ms, t1 + 50 ms] (a sample describes the ~50 ms before
+        it was printed); all samples if the window is empty or was never marked."""
+        ok = [(t, r) for t, r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        inside = [(t, r) for t, r in ok if t0 is not None and t1 is not None and t0 + 0.05 <= t <= t1 + 0.05]
+        use = inside or ok
+        sm = [float(r[0]) for _, r in use]
+        mx = [float(r[1]) for _, r in ok if r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for _, r in use:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(inside)}
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
+        time.sleep(0.15)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return self.summarise(list(self.rows), self.t0, self.t1)
 
 
 def make_observations(n, n_frames, seed):
@@ -324,16 +340,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, sampler=None):
         for i in range(warmup):
             fn(i)
         barrier()
+        if sampler is not None:
+            sampler.mark_start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(steps):
             fn(warmup + i)
         e1.record()
         barrier()
+        if sampler is not None:
+            sampler.mark_end()
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device="cuda")
@@ -346,7 +366,7 @@ def main():
         net.embed(dev[i % n_rot], n_frames, out=out)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms = timed(step_resident, args.steps, args.warmup)
+    ms = timed(step_resident, args.steps, args.warmup, sampler)
     clocks = sampler.stop() if sampler else None
     value = world * frames_per_step * args.steps / (ms / 1e3)
 

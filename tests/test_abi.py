@@ -73,3 +73,23 @@ def test_product_code_never_imports_the_oracle():
         func = src[:m.start()].rsplit("\ndef ", 1)[1].split("(", 1)[0]
         assert func in ("oracle_parts", "oracle_embed", "cpu_port_frames_per_s", "cpu_port_bc_steps_per_s",
                         "run_reference"), func
+
+
+def test_bench_clock_sampler_counts_only_samples_of_the_timed_region():
+    """bench.py `clocks`: nvidia-smi samples read outside the timed region are idle (no power cap, maximum SM clock)
+    and must not enter the median; with no sample inside the window everything read is used."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    def row(sm, cap):
+        return [str(sm), "1965", "700.0", "Not Active", "Not Active", "Not Active", "Active" if cap else "Not Active"]
+
+    rows = [(0.00, row(1965, False)), (0.06, row(1965, False)), (0.12, row(1650, True)), (0.17, row(1620, True)),
+            (0.22, row(1630, True)), (0.30, row(1640, True)), (0.36, row(1965, False)), (0.41, ["garbage"])]
+    got = bench.ClockSampler.summarise(rows, 0.05, 0.28)
+    assert got == {"sm_mhz": 1635.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 4,
+                   "samples_in_timed_region": 4}
+    assert bench.ClockSampler.summarise(rows, None, None)["samples"] == 7
+    assert bench.ClockSampler.summarise(rows, 10.0, 11.0)["samples_in_timed_region"] == 0

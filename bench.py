@@ -18,6 +18,7 @@ ResNet-50 trunks as the reference computes them, src/embeddings.py:44-57,225-229
           not travel to the GPU box) on all host threads, same JSON schema.
 """
 import argparse
+import atexit
 import json
 import os
 import subprocess
@@ -75,8 +76,13 @@ class ClockSampler:
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            atexit.register(self._kill)  # never leave the polling nvidia-smi behind, whatever ends the run
         except OSError:
             self.proc = None
+
+    def _kill(self):
+        if self.proc is not None and self.proc.poll() is None:
+            self.proc.terminate()
 
     def _read(self):
         for line in self.proc.stdout:

@@ -9,7 +9,7 @@ GPURUN=/usr/local/graft/bin/gpurun
 case "${1:-}" in
 1)  # antialiased bicubic kernel: first GPU run. Green -> drop the gate in embeddings._get_embedding and
     # the skipif in tests/test_gpu_preprocess_aa.py.
-    $GPURUN --timeout 300 -- 'PVR_EXPERIMENTAL_AA=1 timeout 200 compute-sanitizer --error-exitcode 9 python -m pytest tests/test_gpu_preprocess_aa.py -q -m gpu -x -k "64-1-3 or 480" > gpurun_out/aa_sanitizer.log 2>&1; PVR_EXPERIMENTAL_AA=1 timeout 200 python -m pytest tests/test_gpu_preprocess_aa.py -q -m gpu > gpurun_out/aa_tests.log 2>&1; tail -5 gpurun_out/aa_sanitizer.log gpurun_out/aa_tests.log'
+    $GPURUN --timeout 300 -- 'PVR_EXPERIMENTAL_AA=1 timeout 200 compute-sanitizer --error-exitcode 9 python tools/sanitize_aa.py > gpurun_out/aa_sanitizer.log 2>&1; PVR_EXPERIMENTAL_AA=1 timeout 200 python -m pytest tests/test_gpu_preprocess_aa.py -q -m gpu > gpurun_out/aa_tests.log 2>&1; tail -5 gpurun_out/aa_sanitizer.log gpurun_out/aa_tests.log'
     ;;
 2)  # north-star argmax criterion on a trained policy (currently xfail(strict=False): XPASS -> remove the marker)
     $GPURUN --timeout 300 -- 'timeout 200 python -m pytest tests/test_gpu_policy.py -q -m gpu -k trained_policy -rxX > gpurun_out/argmax_trained.log 2>&1; tail -5 gpurun_out/argmax_trained.log'

@@ -47,9 +47,9 @@ class Transforms(nn.Module):
         self.mean, self.std, self.size, self.crop = list(mean), list(std), size, crop
         assert interpolation in ('bilinear', 'bicubic', 'bicubic_aa')
         # 'bicubic': T.Resize(256, interpolation=3) of the MAE encoders; 'bicubic_aa': CLIP's antialiased bicubic Resize
-        # (pvr_preprocess_u8_aa — experimental in round 1: see csrc/preprocess_aa.cu)
+        # (pvr_preprocess_u8_aa, csrc/preprocess_aa.cu)
         self.interpolation = interpolation
-        self.identity_resize_only = False  # CLIP: bicubic antialiased Resize is only supported when it is a no-op
+        self.identity_resize_only = False  # debugging aid: reject frames that would need an actual resize
 
     def run(self, obs_nhwc_u8, n_frames, out_ptr, fmt, sample_major):
         """obs: CUDA uint8 (N, H, W, 3*n_frames) contiguous; writes n_frames*N images at `out_ptr`."""
@@ -183,9 +183,9 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
         model = mae_vit.load(embedding_name)
         transforms = Transforms(IMAGENET_MEAN, IMAGENET_STD, interpolation='bicubic')
     elif 'clip' in embedding_name:
-        # src/embeddings.py:298-314: clip.load("ViT-B/32") + CLIP's own normalisation. Resize(224, bicubic) and
-        # CenterCrop(224) are the identity for the 224x224 frames of the north-star configs; other sizes would need
-        # the antialiased bicubic resize and are rejected at call time.
+        # src/embeddings.py:298-314: clip.load("ViT-B/32") + CLIP's own normalisation. Resize(224, bicubic,
+        # antialiased) + CenterCrop(224): the identity for 224x224 frames; any other size (Habitat renders 64x64,
+        # habitat_config/nav_task.yaml:10-12) goes through pvr_preprocess_u8_aa (csrc/preprocess_aa.cu).
         if embedding_name == 'clip_vit':
             model, _ = clip_vit.load("ViT-B/32", device='cpu')
         elif embedding_name == 'clip_vit_b16':  # BASELINE configs[2] geometry (CLIP block structure, patch 16)
@@ -194,9 +194,6 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
             raise NotImplementedError("Requested model not available.")
         transforms = Transforms(CLIP_MEAN, CLIP_STD, size=model.visual.input_resolution,
                                 crop=model.visual.input_resolution, interpolation='bicubic_aa')
-        # the antialiased bicubic kernel has not run on a GPU yet (round 1): other frame sizes stay rejected unless the
-        # experiment is switched on
-        transforms.identity_resize_only = os.environ.get("PVR_EXPERIMENTAL_AA") != "1"
     elif embedding_name == 'true_state':
         return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
     else:

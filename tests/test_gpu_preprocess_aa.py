@@ -1,7 +1,7 @@
-"""-m gpu, EXPERIMENTAL (skipped unless PVR_EXPERIMENTAL_AA=1): the antialiased bicubic preprocessing kernel
-(pvr_preprocess_u8_aa, CLIP transforms for frames that are not 224x224) against the oracle, which is bit-identical with
-ATen. The kernel compiled but could not be run on a GPU in round 1 (budget spent); its arithmetic core is verified on CPU
-(tests/test_preprocess_aa_core.py). Enable, verify, then drop the gate here and in embeddings._get_embedding."""
+"""-m gpu: the antialiased bicubic preprocessing kernel (pvr_preprocess_u8_aa, CLIP transforms for frames that are not
+224x224, src/embeddings.py:309-314) against the oracle, which is bit-identical with ATen, and against the reference's
+own transforms (tests/golden/clip_transforms.npz). First run on B200 in round 2: 14 / 14 bit-exact, compute-sanitizer
+clean (profiles/r02_aa_first_gpu_run.txt)."""
 import os
 
 import numpy as np
@@ -12,9 +12,7 @@ from oracle import restate, restate_vit
 from pvr_habitat_b200 import _lib
 from pvr_habitat_b200.embeddings import CLIP_MEAN, CLIP_STD, Transforms
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("PVR_EXPERIMENTAL_AA") != "1",
-                                 reason="antialiased bicubic kernel not yet verified on a GPU (PVR_EXPERIMENTAL_AA=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def cuda_clip_transforms(obs_nhwc, nf=1):

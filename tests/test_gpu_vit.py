@@ -106,7 +106,19 @@ def test_clip_embedding_stress_weights():
     assert relerr <= 1.5e-2 and cos.min() >= 0.999, (relerr, cos.min())
 
 
-def test_clip_rejects_non_identity_resize():
-    net, _ = make_clip("clip_vit", 32, 5)
-    with pytest.raises(NotImplementedError, match="antialiased bicubic"):
-        net(torch.zeros(1, 64, 64, 3, dtype=torch.uint8))
+@pytest.mark.parametrize("name,patch,hw,n", [("clip_vit", 32, (64, 64), 48), ("clip_vit_b16", 16, (64, 64), 24),
+                                             ("clip_vit", 32, (96, 128), 6), ("clip_vit", 32, (224, 224), 40)])
+def test_clip_embedding_habitat_frames_vs_oracle(name, patch, hw, n):
+    """The reference's real frame size (Habitat renders 64x64, habitat_config/nav_task.yaml:10-12) through CLIP's own
+    transforms (antialiased bicubic Resize(224), src/embeddings.py:309-314) and the encoder, 2-frame observations
+    (current | goal image), against the oracle; same tolerances as the north star."""
+    net, sd = make_clip(name, patch, 7)
+    obs = restate.structured_frames(n // 2, hw[0], hw[1], 6, 17)
+    got = net.embed(torch.from_numpy(obs), 2).cpu().numpy()
+    assert got.shape == (n // 2, 1024)
+    frames, _ = restate.split_frames(obs)  # frame-major (f * N + i), like the reference's np.split
+    ref = rv.embedding_forward(sd, frames).reshape(2, n // 2, 512).transpose(1, 0, 2).reshape(n // 2, 1024)
+    g, r = got.astype(np.float64).reshape(-1, 512), ref.astype(np.float64).reshape(-1, 512)
+    relerr = np.linalg.norm(g - r) / np.linalg.norm(r)
+    cos = (g * r).sum(1) / (np.linalg.norm(g, axis=1) * np.linalg.norm(r, axis=1))
+    assert relerr <= 1e-2 and cos.min() >= 0.999, (relerr, cos.min())

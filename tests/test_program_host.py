@@ -278,15 +278,10 @@ def test_transforms_dispatch_per_interpolation(monkeypatch):
     assert calls[2][2:11] == (2, 64, 64, 2, 224, 224, 0, 0, 224) and calls[2][14] == _lib.PVR_FMT_NHWC4_BF16
     assert calls[3][2:11] == (1, 224, 224, 1, 224, 224, 0, 0, 224) and calls[3][14] == _lib.PVR_FMT_NHWC4_BF16
     assert [round(v, 4) for v in calls[2][11]] == [round(v, 4) for v in CLIP_MEAN]
-    # the gate of round 1: CLIP nets reject other frame sizes unless the experiment is switched on
+    # CLIP nets take any frame size (antialiased bicubic kernel, verified on B200 in round 2)
     with allow_random_init():
         net = EmbeddingNet("clip_vit", disable_cuda=True)
-    assert net.transforms.interpolation == "bicubic_aa" and net.transforms.identity_resize_only
-    with pytest.raises(NotImplementedError):
-        net.transforms.run(obs64[..., :3].contiguous(), 1, 1234, _lib.PVR_FMT_NHWC4_BF16, True)
-    monkeypatch.setenv("PVR_EXPERIMENTAL_AA", "1")
-    with allow_random_init():
-        assert not EmbeddingNet("clip_vit", disable_cuda=True).transforms.identity_resize_only
+    assert net.transforms.interpolation == "bicubic_aa" and not net.transforms.identity_resize_only
 
 
 # ------------------------------------------------------------------------------------------------ name coverage

@@ -1,5 +1,5 @@
 """Small driver for compute-sanitizer: the antialiased bicubic preprocessing kernel on an up-scaling and a down-scaling
-geometry, all three output formats. Usage: PVR_EXPERIMENTAL_AA=1 compute-sanitizer python tools/sanitize_aa.py"""
+geometry, all three output formats. Usage: compute-sanitizer python tools/sanitize_aa.py"""
 import os
 import sys
 

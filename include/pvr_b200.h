@@ -257,6 +257,13 @@ typedef struct pvr_lstm_fwd {
   float* h_last;      /* (B, H) fp32: h_{T-1} */
 } pvr_lstm_fwd;
 int pvr_lstm_forward(const pvr_lstm_fwd* layer, void* stream);
+/* 1 if the whole-sequence persistent kernels (csrc/lstm_persist.cu: W_hh resident in shared memory, one launch for all
+ * T steps) serve this shape on the current device: H = 1024, B <= 128, all CTAs co-resident. pvr_lstm_forward /
+ * pvr_lstm_backward use them when `flags == 0`; otherwise (and with PVR_LSTM_PERSIST=0) the per-step kernels run. */
+int pvr_lstm_persist_supported(int T, int B, int H);
+/* Development aid: per-phase clock64 stamps of the persistent kernels' first 64 steps into `buf` (device memory,
+ * 128 x 64 x 16 int64); NULL (the default) switches it off. */
+int pvr_lstm_persist_profile(void* buf);
 
 typedef struct pvr_lstm_bwd {
   int32_t T, B, H, flags;

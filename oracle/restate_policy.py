@@ -127,6 +127,24 @@ def synthetic_bc_data(n, d, n_actions, seed):
     return obs, action, done, reward
 
 
+def synthetic_frame_trajectories(n_traj, traj_len, seed, hw=64, n_frames=2):
+    """Raw-frame trajectory pickle of behavioral_cloning/save_opt_trajectories.py:94-106 (lists over trajectories;
+    obs (L, hw, hw, 3n) uint8) with structured frames; actions follow the mean colour of the central patch of the
+    first frame plus noise, so the loss can fall. Returns (pickle dict, flat action array)."""
+    from oracle import restate
+    rng = np.random.default_rng(seed)
+    frames = restate.structured_frames(n_traj * traj_len, hw, hw, 3 * n_frames, seed)
+    q = hw // 4
+    feat = frames[:, q:3 * q, q:3 * q, :3].reshape(len(frames), -1, 3).mean(1)
+    action = np.argmax(feat + 8 * rng.standard_normal(feat.shape), 1).astype(np.int64)
+    cut = lambda a: [a[i * traj_len:(i + 1) * traj_len] for i in range(n_traj)]  # noqa: E731
+    data = dict(obs=cut(frames), action=cut(action),
+                reward=[np.zeros(traj_len, np.float32) for _ in range(n_traj)],
+                done=[np.arange(traj_len) == traj_len - 1 for _ in range(n_traj)],
+                true_state=[np.zeros((traj_len, 12)) for _ in range(n_traj)])
+    return data, action
+
+
 def init_policy_state(obs_size, num_actions, batch_norm, seed, _rng_state=None):
     """Initial state_dict of the reference's PolicyNet((obs_size,), num_actions, batch_norm) built right after
     torch.manual_seed(seed): same layer order and init calls as src/models.py:17-44 (orthogonal, gain sqrt(2) for the

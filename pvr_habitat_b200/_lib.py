@@ -91,6 +91,8 @@ _SIGNATURES = {
     "pvr_lstm_cell_backward": (ctypes.c_int, [_vp] * 8 + [_i, _i, _vp, _vp]),
     "pvr_lstm_forward": (ctypes.c_int, [ctypes.POINTER(pvr_lstm_fwd), _vp]),
     "pvr_lstm_backward": (ctypes.c_int, [ctypes.POINTER(pvr_lstm_bwd), _vp]),
+    "pvr_lstm_persist_supported": (ctypes.c_int, [_i, _i, _i]),
+    "pvr_lstm_persist_profile": (ctypes.c_int, [_vp]),
     "pvr_heads_forward": (ctypes.c_int, [_vp, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "pvr_heads_backward": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp]),
     "pvr_ce_loss": (ctypes.c_int, [_vp, _vp, _i, _i, _f, _vp, _vp, _vp]),

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 
 from . import parallel
-from .models import PolicyNet, bc_loss
+from .models import PolicyNet, PolicyNetWithConv, bc_loss
 from .optim import FusedAdam, FusedRMSprop
 from .utils_bc import sample_with_minimum_distance, window_indices
 
@@ -26,10 +26,10 @@ class BCTrainer:
         self.device = actor_model.device
         self.T, self.B = unroll_length, batch_size
         self.rank, self.world = 0, 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.rank = torch.distributed.get_rank(process_group)
-            self.world = torch.distributed.get_world_size(process_group)
-        self.group = process_group
+        self.group = parallel.resolve_group(process_group)  # None only when this process trains alone
+        if self.group is not None:
+            self.rank = torch.distributed.get_rank(self.group)
+            self.world = torch.distributed.get_world_size(self.group)
         self.n_samples = len(action)
         self.host_batches = host_batches
         self._next = None
@@ -43,12 +43,12 @@ class BCTrainer:
             self._stage = None
             self._stage_i = 0
         else:
-            self.obs = torch.as_tensor(np.asarray(obs)).to(self.device)
-            self.action = torch.as_tensor(np.asarray(action)).long().to(self.device)
-            self.done = torch.as_tensor(np.asarray(done)).to(self.device)
+            # (a tensor that is already on the device — the table main_bc_1 fills straight from the encoder — is kept)
+            to_dev = lambda a: (a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a))).to(self.device)  # noqa: E731
+            self.obs, self.action, self.done = to_dev(obs), to_dev(action).long(), to_dev(done)
         self.global_rows = unroll_length * batch_size
         if self.world > 1:
-            parallel.attach(actor_model, process_group, self.global_rows)
+            parallel.attach(actor_model, self.group, self.global_rows)
         if optimizer == "rmsprop":
             self.optimizer = FusedRMSprop(actor_model.parameters(), lr=learning_rate, momentum=momentum, eps=epsilon,
                                           alpha=alpha, max_grad_norm=max_grad_norm)
@@ -63,9 +63,10 @@ class BCTrainer:
         # Whole-step CUDA graph (single process, RMSprop): forward, loss, backward, clip + update are ~100 launches
         # issued through ctypes in ~4.8 ms of host time against ~4 ms of GPU time; replayed from one graph the step is
         # GPU bound. The batch is copied into static buffers, the learning rate lives in device memory.
+        capturable = optimizer == "rmsprop" and not isinstance(actor_model, PolicyNetWithConv)
         if use_graph is None:
-            use_graph = self.world == 1 and optimizer == "rmsprop"
-        self.use_graph = bool(use_graph) and self.world == 1 and optimizer == "rmsprop"
+            use_graph = self.world == 1 and capturable
+        self.use_graph = bool(use_graph) and self.world == 1 and capturable
         self._graph = None
         self._eager_steps = 0
 
@@ -137,11 +138,11 @@ class BCTrainer:
         lr = float(self.optimizer.param_groups[0]["lr"])
         if self._graph is None:
             self._go, self._ga, self._gd = o.clone(), a.clone(), d.clone()
-            self._lr_host = torch.empty(1, dtype=torch.float32).pin_memory()
-            self._lr_dev = torch.empty(1, dtype=torch.float32, device=self.device)
-            self._lr_host[0] = lr
-            self._lr_dev.copy_(self._lr_host, non_blocking=True)
+            # the learning rate of THIS step travels as a kernel argument of the fill (stream ordered): no pinned
+            # scalar that a host running ahead of the replay could overwrite
+            self._lr_dev = torch.full((1,), lr, dtype=torch.float32, device=self.device)
             self._gstate = tuple(s.to(self.device) for s in self.model.initial_state(batch_size=n_mine))
+            self._gws = self.model._workspace(self.T, n_mine)  # the graph holds raw pointers into this workspace
             torch.cuda.current_stream(self.device).synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):  # records the step, does not run it: the replay below performs it
@@ -152,8 +153,8 @@ class BCTrainer:
             self._go.copy_(o, non_blocking=True)
             self._ga.copy_(a, non_blocking=True)
             self._gd.copy_(d, non_blocking=True)
-            self._lr_host[0] = lr
-            self._lr_dev.copy_(self._lr_host, non_blocking=True)
+            self._lr_dev.fill_(lr)
+            self.optimizer.count_replayed_step()  # `state[p]['step']` of a checkpoint stays the true step count
         self._graph.replay()
         return self._gloss.clone()
 
@@ -188,19 +189,22 @@ def save_checkpoint(save_path, embedding_model, actor_model, optimizer, schedule
     if stats is not None:
         with open(save_path + '.pickle', 'wb') as fh:
             pickle.dump(stats, fh, protocol=pickle.HIGHEST_PROTOCOL)
-    torch.save({
-        'embedding_model_state_dict': embedding_model.state_dict(),
+    ck = {
         'actor_model_state_dict': actor_model.state_dict(),
         'actor_model_optimizer_state_dict': optimizer.state_dict(),
         'scheduler_state_dict': scheduler.state_dict(),
         'flags': dict(flags) if isinstance(flags, dict) else vars(flags),
-    }, save_path + '.tar')
+    }
+    if embedding_model is not None:  # main_bc_finetune.py:232-238 has no separate encoder
+        ck = {'embedding_model_state_dict': embedding_model.state_dict(), **ck}
+    torch.save(ck, save_path + '.tar')
 
 
 def load_checkpoint(path, embedding_model=None, actor_model=None, optimizer=None, scheduler=None):
     """Restore whichever objects are given from a `.tar` written by `save_checkpoint` or by the reference."""
     ck = torch.load(path, map_location='cpu', weights_only=False)
-    missing = [k for k in CHECKPOINT_KEYS if k not in ck]
+    missing = [k for k in CHECKPOINT_KEYS if k not in ck and not (k == "embedding_model_state_dict" and
+                                                                    embedding_model is None)]
     if missing:
         raise KeyError(f"{path}: not a BC checkpoint (missing {missing})")
     if embedding_model is not None:

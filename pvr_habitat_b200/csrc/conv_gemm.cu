@@ -841,6 +841,23 @@ bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows,
   return true;
 }
 
+// K-major bf16 matrix (rows x k) seen as (64, rows, k / 64): a box of (64, box_rows, chunks) lands in shared memory as
+// `chunks` consecutive canonical (box_rows x 64) 128B-swizzled K chunks — several K chunks per TMA instruction.
+bool make_tmap_kchunks(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                       uint32_t chunks, const char** err) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
+  if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
+  cuuint64_t dims[3] = {64, rows, k / 64};
+  cuuint64_t strides[2] = {ld * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, chunks};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (K chunks) failed"; return false; }
+  return true;
+}
+
 bool make_tmap_2d_sw64(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
                        const char** err) {
   static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));

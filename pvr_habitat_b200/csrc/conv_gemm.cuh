@@ -63,6 +63,9 @@ cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtens
 // 2-D K-major bf16 matrix (rows x k), row pitch ld elements, box = (64 x box_rows), 128B swizzle.
 bool make_tmap_2d(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
                   const char** err);
+// The same matrix as (64, rows, k / 64) with a (64, box_rows, chunks) box: `chunks` consecutive K chunks per instruction.
+bool make_tmap_kchunks(CUtensorMap* out, const void* base, uint64_t k, uint64_t rows, uint64_t ld, uint32_t box_rows,
+                       uint32_t chunks, const char** err);
 // 2-D fp32 matrix (rows x cols), row pitch ld elements, box = (32 x box_rows) = 128-byte rows, 128B swizzle.
 bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                       uint32_t box_rows, const char** err);

@@ -1,0 +1,647 @@
+// Persistent LSTM recurrence (K9, src/models.py:68-72 called T times with seq_len 1; BPTT through the same steps).
+//
+// The per-step formulation (policy.cu: one tcgen05 GEMM launch + one cell launch per time step, 4 T launches per layer
+// for forward + backward) is bound by launch / drain latency: 8.5 us per (128 x 1024) x (1024 x 4096) product, 9 % of
+// the tensor peak, W_hh re-read from L2 at every step. Here ONE kernel runs all T steps of a layer:
+//
+//   * W_hh (8 MB bf16) is cut into 64 x 1024 slices that stay RESIDENT in shared memory (128 KB per CTA) for the whole
+//     sequence: 64 slices x ceil(B / 64) batch tiles = 128 CTAs at B = 128, one per SM;
+//   * a step's operand (the masked h_{t-1}, or dG_{t+1} in the backward pass) streams through a 5-stage TMA ring as 16
+//     (64 rows x 64 K) chunks, each gated by a per-chunk arrival counter in global memory that the producing CTAs
+//     bump when their part of the previous step is written — a dataflow barrier instead of a kernel boundary
+//     (ld.acquire.gpu poll of 16 counters in one 64-byte line, fence.proxy.async, TMA);
+//   * the (64 x 64) fp32 accumulator lives in TMEM (tcgen05.mma M = 64, N = 64, K = 16 x 64 per step);
+//   * clusters of 4 CTAs: CTA q of cluster (batch tile, hidden block J) owns gate q in the forward pass (rows
+//     q * 1024 + 64 J.. of W_hh) and K slice q (gate q's rows of W_hh^T) in the backward pass. After the MMAs the four
+//     CTAs exchange 16-column pieces through distributed shared memory (st.shared::cluster + remote mbarrier
+//     arrive), so that CTA q holds all four gates (forward) / all four partial sums (backward) of hidden units
+//     64 J + 16 q .. + 16 and runs the cell update for them with c_t (forward) / dc (backward) kept in registers;
+//   * the cell phase writes h_t / masked h_t / gates / c_t (forward) or dG_t (backward) and bumps the counter of its
+//     chunk for the next step.
+//
+// Arithmetic is the per-step path's (bf16 operands, fp32 accumulation, fp32 gates / cell state; same saved tensors, so
+// forward and backward implementations can be mixed) except that the K = 1024 / 4096 sums are not split into atomic
+// partial sums any more: the result is deterministic.
+//
+// Safety: every spin (mbarrier, arrival counter) is bounded and traps instead of hanging the GPU; the kernel needs all
+// its CTAs co-resident (checked with cudaOccupancyMaxActiveClusters before launch, otherwise the caller falls back to
+// the per-step path).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "conv_gemm.cuh"
+#include "ptx.cuh"
+#include "pvr_b200.h"
+
+extern void pvr_set_error(const char* fmt, ...);
+
+namespace pvr {
+namespace {
+
+constexpr int HID = 1024;          // hidden size (PolicyNet: nn.LSTM(1024, 1024, 2))
+constexpr int CHUNKS = 16;         // K chunks of 64 per step (K = 1024 per CTA in both passes)
+constexpr int CPI = 4;             // K chunks per TMA instruction (one ring stage = CPI chunks)
+constexpr int NG = CHUNKS / CPI;   // chunk groups per step
+constexpr int NST = 2;             // TMA ring stages
+constexpr int CHUNK_BYTES = 64 * 64 * 2;
+constexpr int SMEM_W = CHUNKS * CHUNK_BYTES;      // 131072
+constexpr int STAGE_BYTES = CPI * CHUNK_BYTES;
+constexpr int SMEM_RING = NST * STAGE_BYTES;
+constexpr int PIECE_BYTES = 64 * 16 * 4;          // one CTA's (64 rows x 16 columns) fp32 piece
+constexpr int SMEM_RECV = 4 * PIECE_BYTES;        // 16384: [source CTA][row][16 fp32]
+constexpr int SMEM_STAGE = 4 * PIECE_BYTES;       // 16384: [destination CTA][row][16 fp32], source of the bulk copies
+constexpr int SMEM_BARS = 256;
+constexpr int SMEM_TOTAL = SMEM_W + SMEM_RING + SMEM_RECV + SMEM_STAGE + SMEM_BARS + 1024;  // + alignment slack
+static_assert(SMEM_TOTAL <= 232448, "shared memory budget");
+constexpr int NTHREADS = 192;      // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: exchange + cell
+
+struct PersistParams {
+  int T, B, nbt;
+  const float* nd;       // (T, B)
+  float* c_all;          // ((T+1) B, H)
+  float* gates;          // (T B, 4H)
+  // forward
+  const float* xp;       // (T B, 4H)
+  __nv_bfloat16* hm;     // (T B, H)
+  __nv_bfloat16* h_out;  // (T B, H)
+  float* h_last;         // (B, H)
+  // backward
+  const float* dh_out;   // (T B, H) or null
+  float* dh_rec;         // (B, H): in = gradient of the final hidden state, out = gradient of the initial one
+  float* dc_rec;         // (B, H): same for the cell state
+  __nv_bfloat16* dG;     // (T B, 4H)
+  unsigned int* ready;   // ((T+1) * nbt * 16) arrival counters, zeroed before the launch
+  long long* prof;       // optional (PVR_LSTM_PROF): [block][step < 64][16] clock64 stamps of the phases of a step
+};
+
+#define PROF(slot)                                                                                     \
+  do {                                                                                                 \
+    if (p.prof && s < 64) p.prof[((size_t)blockIdx.x * 64 + s) * 16 + (slot)] = clock64();             \
+  } while (0)
+
+// ---- small PTX helpers local to this kernel
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t polls = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if ((++polls & 255u) == 0) {
+      const uint64_t t = globaltimer_ns();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 4000000000ull) {
+        printf("pvr: lstm_persist exchange barrier timed out (block %d thread %d)\n", (int)blockIdx.x,
+               (int)threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+// Bulk copy of `bytes` from this CTA's shared memory into a peer CTA's (addresses in the shared::cluster window); the
+// bytes are counted on the PEER's mbarrier (complete_tx), which is what its cell phase waits on.
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                  uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
+__device__ __forceinline__ void ld8(const float* p, float* r) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+// (plain loads: data written earlier in this kernel by other CTAs must not go through the non-coherent path)
+__device__ __forceinline__ void ld8_coherent(const float* p, float* r) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *(reinterpret_cast<const float4*>(p) + 1);
+  r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w; r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float* r) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(r[0], r[1], r[2], r[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(r[4], r[5], r[6], r[7]);
+}
+__device__ __forceinline__ void st8_bf16(__nv_bfloat16* p, const float* r) {
+  uint4 v;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(r[0], r[1]); v.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(r[2], r[3]); v.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(r[4], r[5]); v.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(r[6], r[7]); v.w = *reinterpret_cast<uint32_t*>(&t);
+  *reinterpret_cast<uint4*>(p) = v;
+}
+
+// BWD = 0: forward recurrence; BWD = 1: backward (BPTT) recurrence.
+template <int BWD>
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                    const PersistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + SMEM_W;
+  float* sRecv = reinterpret_cast<float*>(sA + SMEM_RING);
+  float* sStage = reinterpret_cast<float*>(sA + SMEM_RING + SMEM_RECV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRecv) + SMEM_RECV + SMEM_STAGE);
+  uint64_t* full = bars;            // [NST]
+  uint64_t* empty = bars + NST;     // [NST]
+  uint64_t* w_full = bars + 2 * NST;
+  uint64_t* acc_full = w_full + 1;
+  uint64_t* acc_empty = w_full + 2;
+  uint64_t* xchg = w_full + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = cluster_ctarank();
+  const int cl = blockIdx.x >> 2;
+  const int bt = cl / 16, J = cl % 16;
+  const int T = p.T, B = p.B, nbt = p.nbt;
+  // The CTAs of a batch tile all stream the same operand chunks: each starts at a different chunk so that they do not
+  // all request the same L2 lines at the same moment (forward: 64 CTAs share the 16 chunks; backward: the 16 CTAs of
+  // a K slice do).
+  const int rot = (BWD ? J : (J + 4 * (int)q)) & (NG - 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(w_full, 1);
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    mbar_init(xchg, 1);  // armed once per step with expect_tx of the three remote pieces
+    fence_barrier_init();
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 64);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();  // the peers' barriers exist before anything arrives on them remotely
+  const uint32_t tmem = *tmem_slot;
+
+  // step s = 0 .. T-1 handles time t = s (forward) or t = T-1-s (backward). The backward's first step has no
+  // recurrent product unless a final-state gradient is given (it is added in the cell phase directly).
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      mbar_expect_tx(w_full, SMEM_W);
+      for (int kc = 0; kc < CHUNKS; ++kc) {
+        if (BWD) tma_load_2d(&tmap_w, w_full, sW + kc * CHUNK_BYTES, (int)q * 1024 + 64 * kc, 64 * J);
+        else tma_load_2d(&tmap_w, w_full, sW + kc * CHUNK_BYTES, 64 * kc, (int)q * 1024 + 64 * J);
+      }
+    }
+    __syncwarp();
+    int it = 0;
+    for (int s = BWD ? 1 : 0; s < T; ++s) {
+      const int t = BWD ? T - 1 - s : s;
+      const int src_t = BWD ? t + 1 : t;  // time index of the operand rows (dG_{t+1} / hm_t)
+      const bool gated = BWD ? true : (t > 0);
+      const unsigned int* flags = p.ready + ((size_t)src_t * nbt + bt) * 16;
+      const int a_row = src_t * B + 64 * bt;
+      const int a_c0 = BWD ? (int)q * 16 : 0;  // first K chunk of this CTA's slice (dG: gate q's 1024 columns)
+      int next = 0;  // next chunk GROUP (CPI chunks = one TMA instruction = one ring stage), in this CTA's order
+      uint32_t polls = 0;
+      uint64_t t0 = 0;
+      while (next < NG) {
+        unsigned int mask = 0xffffu;
+        if (gated) {
+          unsigned int v = 4;
+          if (lane < 16) v = ld_acquire_gpu(flags + lane);
+          mask = __ballot_sync(0xffffffffu, v >= 4u) & 0xffffu;
+        }
+        constexpr unsigned int GM = (1u << CPI) - 1u;
+        int upto = next;
+        while (upto < NG && ((mask >> (CPI * ((upto + rot) & (NG - 1)))) & GM) == GM) ++upto;
+        if (upto == next) {
+          if ((++polls & 63u) == 0) {
+            const uint64_t now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) {
+              if (lane == 0)
+                printf("pvr: lstm_persist step %d group %d never became ready (block %d, mask %x)\n", s, next,
+                       (int)blockIdx.x, mask);
+              __trap();
+            }
+          }
+          continue;
+        }
+        if (lane == 0 && next == 0) PROF(0);               // first group seen ready
+        if (lane == 0 && upto == NG) PROF(1);              // all chunks seen ready
+        fence_proxy_async_global();  // rows written with st.global by other SMs; TMA reads them next
+        for (; next < upto; ++next, ++it) {
+          const int st = it % NST;
+          const uint32_t ph = (uint32_t)(it / NST) & 1u;
+          mbar_wait(&empty[st], ph ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(&full[st], STAGE_BYTES);
+            tma_load_3d(&tmap_a, &full[st], sA + st * STAGE_BYTES, 0, a_row, a_c0 + CPI * ((next + rot) & (NG - 1)));
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) PROF(2);                              // last TMA of the step issued
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    mbar_wait(w_full, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(64, 64);
+    int it = 0, gi = 0;
+    for (int s = BWD ? 1 : 0; s < T; ++s, ++gi) {
+      mbar_wait(acc_empty, ((uint32_t)gi & 1u) ^ 1u);  // the previous step's accumulator has been read
+      tc_fence_after();
+      for (int g = 0; g < NG; ++g, ++it) {
+        const int st = it % NST;
+        const uint32_t ph = (uint32_t)(it / NST) & 1u;
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        if (lane == 0 && g == 0) PROF(3);                  // first group landed
+        if (lane == 0 && g == NG - 1) PROF(4);             // last group landed
+        if (lane == 0 && g == NG / 4) PROF(12);
+        if (lane == 0 && g == NG / 2) PROF(13);
+        if (lane == 0 && g == 3 * NG / 4) PROF(14);
+        if (elect_one()) {
+          const int kc0 = CPI * ((g + rot) & (NG - 1));
+#pragma unroll
+          for (int c = 0; c < CPI; ++c) {
+            const uint64_t ad = umma_desc_sw128(smem_u32(sA + st * STAGE_BYTES + c * CHUNK_BYTES));
+            const uint64_t bd = umma_desc_sw128(smem_u32(sW + (kc0 + c) * CHUNK_BYTES));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, ((g * CPI + c) | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[st]);
+          if (g == NG - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ exchange + cell (128 threads)
+    const int e = threadIdx.x - 64;
+    const int ew = warp & 3;            // TMEM lane quadrant this warp may read: rows 16 ew .. 16 ew + 15 in lanes 0-15
+    const int erow = 16 * ew + lane;    // accumulator row held by this lane (lane < 16)
+    const int crow = e & 63, half = e >> 6;
+    const int b = 64 * bt + crow;
+    const bool row_ok = b < B;
+    const int j0 = 64 * J + 16 * (int)q + 8 * half;  // first of this thread's 8 hidden units
+    const uint32_t recv_base = smem_u32(sRecv);
+    const uint32_t xchg_addr = smem_u32(xchg);
+    float state[8];  // forward: c_{t-1}; backward: dc flowing from step t+1
+#pragma unroll
+    for (int u = 0; u < 8; ++u) state[u] = 0.f;
+    float dh_last[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) dh_last[u] = 0.f;
+    if (row_ok) {
+      if (!BWD) ld8_coherent(p.c_all + (size_t)b * HID + j0, state);
+      else {
+        ld8_coherent(p.dc_rec + (size_t)b * HID + j0, state);
+        ld8_coherent(p.dh_rec + (size_t)b * HID + j0, dh_last);
+      }
+    }
+    uint32_t xphase = 0;
+    int gi = 0;
+    for (int s = 0; s < T; ++s) {
+      const int t = BWD ? T - 1 - s : s;
+      const bool has_gemm = BWD ? (s > 0) : true;
+      const size_t row_t = (size_t)t * B + b;
+      // ---- operands of the cell phase that do not depend on the recurrence: issued before the waits
+      float op[32];
+      float cp[8], cc[8], dho[8];
+      float nd_t = 0.f, nd_n = 0.f;
+      if (row_ok) {
+        nd_t = __ldg(p.nd + row_t);
+        if (t + 1 < T) nd_n = __ldg(p.nd + row_t + B);
+        if (!BWD) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ld8(p.xp + row_t * (4 * HID) + g * HID + j0, op + 8 * g);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) ld8(p.gates + row_t * (4 * HID) + g * HID + j0, op + 8 * g);
+          ld8(p.c_all + row_t * HID + j0, cp);
+          ld8(p.c_all + (row_t + B) * HID + j0, cc);
+          if (p.dh_out) ld8(p.dh_out + row_t * HID + j0, dho);
+          else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dho[u] = 0.f;
+          }
+        }
+      }
+      float G[32];
+      if (has_gemm) {
+        // ---- accumulator -> 16-column pieces to the four CTAs of the cluster
+        mbar_wait(acc_full, (uint32_t)gi & 1u);
+        tc_fence_after();
+        if (e == 0) PROF(5);                               // accumulator complete
+        uint32_t v[64];
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(32 * ew) << 16), v);
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(32 * ew) << 16) + 32, v + 32);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        if (lane < 16) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            // the piece this CTA keeps goes straight into its own receive buffer, the others are staged for the copies
+            float* dstp = (r == (int)q ? sRecv + ((int)q * 64 + erow) * 16 : sStage + (r * 64 + erow) * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(dstp)[i] =
+                  make_float4(__uint_as_float(v[16 * r + 4 * i]), __uint_as_float(v[16 * r + 4 * i + 1]),
+                              __uint_as_float(v[16 * r + 4 * i + 2]), __uint_as_float(v[16 * r + 4 * i + 3]));
+          }
+          fence_proxy_async();  // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+        }
+        named_bar_sync(2, 128);
+        if (e == 0) {
+          mbar_expect_tx(xchg, 3 * PIECE_BYTES);
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (r != (int)q)
+              bulk_copy_to_peer(mapa(recv_base + (uint32_t)q * PIECE_BYTES, (uint32_t)r),
+                                smem_u32(sStage) + (uint32_t)r * PIECE_BYTES, PIECE_BYTES, mapa(xchg_addr, (uint32_t)r));
+          PROF(6);                                         // pieces sent
+        }
+        mbar_wait_cluster(xchg, xphase);
+        if (e == 0) PROF(7);                               // pieces of all four CTAs received
+        xphase ^= 1u;
+        ++gi;
+#pragma unroll
+        for (int src = 0; src < 4; ++src) {
+          const float4* rp = reinterpret_cast<const float4*>(sRecv + (src * 64 + crow) * 16 + 8 * half);
+          const float4 a = rp[0], c4 = rp[1];
+          G[8 * src + 0] = a.x; G[8 * src + 1] = a.y; G[8 * src + 2] = a.z; G[8 * src + 3] = a.w;
+          G[8 * src + 4] = c4.x; G[8 * src + 5] = c4.y; G[8 * src + 6] = c4.z; G[8 * src + 7] = c4.w;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) G[i] = 0.f;
+      }
+      // ---- cell. Order of the stores: (1) the operand of the next step (masked h_t / dG_t), (2) its arrival counter,
+      // (3) whatever only the backward pass / the caller reads (gates, c_t, h_t) — off the critical path.
+      const bool publish = BWD ? (t > 0) : (t + 1 < T);
+      float o0[8], o1[8], o2[8], o3[8], hv[8];
+      if (row_ok) {
+        if (!BWD) {
+          float hmv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float i = sigmoid_fast(G[u] + op[u]);
+            const float f = sigmoid_fast(G[8 + u] + op[8 + u]);
+            const float g = tanh_fast(G[16 + u] + op[16 + u]);
+            const float o = sigmoid_fast(G[24 + u] + op[24 + u]);
+            const float c = f * (nd_t * state[u]) + i * g;
+            const float h = o * tanh_fast(c);
+            state[u] = c;
+            o0[u] = i; o1[u] = f; o2[u] = g; o3[u] = o;
+            hv[u] = h;
+            hmv[u] = h * nd_n;
+          }
+          if (t + 1 < T) st8_bf16(p.hm + (row_t + B) * HID + j0, hmv);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            // dh = gradient from above + what flows back from step t+1 through W_hh (masked by done[t+1]); at the
+            // last step the gradient of the returned state instead (zero in BC training)
+            const float rec = has_gemm ? nd_n * ((G[u] + G[8 + u]) + (G[16 + u] + G[24 + u])) : dh_last[u];
+            const float dh = dho[u] + rec;
+            const float i = op[u], f = op[8 + u], g = op[16 + u], o = op[24 + u];
+            const float tc = tanh_fast(cc[u]);
+            const float dc = state[u] + dh * o * (1.f - tc * tc);
+            const float cpm = nd_t * cp[u];
+            o0[u] = dc * g * i * (1.f - i);
+            o1[u] = dc * cpm * f * (1.f - f);
+            o2[u] = dc * i * (1.f - g * g);
+            o3[u] = dh * tc * o * (1.f - o);
+            state[u] = dc * f * nd_t;
+          }
+          __nv_bfloat16* dp = p.dG + row_t * (4 * HID) + j0;
+          st8_bf16(dp, o0);
+          st8_bf16(dp + HID, o1);
+          st8_bf16(dp + 2 * HID, o2);
+          st8_bf16(dp + 3 * HID, o3);
+        }
+      }
+      if (e == 0) PROF(8);                                 // cell math done, operand stores issued
+      if (publish) {
+        fence_proxy_async_global();
+        named_bar_sync(1, 128);
+        if (e == 0) {
+          PROF(9);
+          const int dst_t = BWD ? t : t + 1;
+          // release at gpu scope: cumulative over the stores of the 127 other threads ordered by the barrier
+          unsigned int* flag = p.ready + ((size_t)dst_t * nbt + bt) * 16 + J;
+          red_release_gpu_add(flag, 1u);
+          PROF(11);
+        }
+        // the remaining stores wait for the release: a gpu-scope fence drains every store the SM has in flight, the
+        // 28 KB below included if they were already issued
+        named_bar_sync(3, 128);
+      }
+      if (!BWD && row_ok) {
+        float* gp = p.gates + row_t * (4 * HID) + j0;
+        st8(gp, o0);
+        st8(gp + HID, o1);
+        st8(gp + 2 * HID, o2);
+        st8(gp + 3 * HID, o3);
+        st8(p.c_all + (row_t + B) * HID + j0, state);
+        st8_bf16(p.h_out + row_t * HID + j0, hv);
+        if (t + 1 >= T) st8(p.h_last + (size_t)b * HID + j0, hv);
+      }
+    }
+    if (BWD && row_ok) {
+      // gradient w.r.t. the initial state: dc is complete; dh_0 needs one more product with W_hh, which training never
+      // uses (main_bc_2.py:207 passes a fresh zero state every step) — the cell part is returned, dh_rec is zeroed.
+      st8(p.dc_rec + (size_t)b * HID + j0, state);
+      float z[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) z[u] = 0.f;
+      st8(p.dh_rec + (size_t)b * HID + j0, z);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still write into its shared memory
+  if (warp == 1) tmem_dealloc(tmem, 64);
+}
+
+long long* g_prof = nullptr;      // set by pvr_lstm_persist_profile()
+unsigned int* g_ready = nullptr;  // arrival counters (one launch at a time per process: stream ordered)
+size_t g_ready_words = 0;
+int g_max_clusters[2] = {-1, -1};
+
+template <int BWD>
+int max_active_clusters(int grid) {
+  if (g_max_clusters[BWD] >= 0) return g_max_clusters[BWD];
+  cudaFuncSetAttribute(lstm_persist_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_persist_kernel<BWD>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  g_max_clusters[BWD] = n;
+  return n;
+}
+
+bool shape_ok(int T, int B, int H) { return H == HID && T >= 1 && B >= 1 && B <= 128 && T <= 4096; }
+
+template <int BWD>
+int launch(const CUtensorMap& ta, const CUtensorMap& tw, const PersistParams& p, cudaStream_t st) {
+  const int grid = p.nbt * 16 * 4;
+  const size_t words = (size_t)(p.T + 1) * p.nbt * 16;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(st, &cap);
+  if (words > g_ready_words) {
+    if (cap != cudaStreamCaptureStatusNone) {
+      pvr_set_error("pvr_lstm_persist: first use inside a stream capture (run one eager step first)");
+      return PVR_ERR_ARG;
+    }
+    if (g_ready) cudaFree(g_ready);
+    g_ready_words = words < 65536 ? 65536 : words;
+    if (cudaMalloc(&g_ready, g_ready_words * sizeof(unsigned int)) != cudaSuccess) {
+      g_ready = nullptr;
+      g_ready_words = 0;
+      pvr_set_error("pvr_lstm_persist: cudaMalloc of the arrival counters failed");
+      return PVR_ERR_CUDA;
+    }
+  }
+  PersistParams q = p;
+  q.ready = g_ready;
+  q.prof = g_prof;
+  cudaMemsetAsync(g_ready, 0, words * sizeof(unsigned int), st);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(NTHREADS);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_persist_kernel<BWD>, ta, tw, q);
+  if (e != cudaSuccess) {
+    pvr_set_error("pvr_lstm_persist launch: %s", cudaGetErrorString(e));
+    return PVR_ERR_CUDA;
+  }
+  return PVR_OK;
+}
+
+__global__ void __launch_bounds__(256) mask_state_bf16_kernel(const float* __restrict__ h0,
+                                                               const float* __restrict__ nd0, int B, int H,
+                                                               __nv_bfloat16* __restrict__ hm0) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < B * H) hm0[idx] = __float2bfloat16_rn(h0[idx] * nd0[idx / H]);
+}
+
+}  // namespace
+
+// 1 if the persistent kernels can run this shape on the current device (all CTAs co-resident), else 0.
+int lstm_persist_supported(int T, int B, int H) {
+  static int disabled = -1;
+  if (disabled < 0) {
+    const char* e = getenv("PVR_LSTM_PERSIST");
+    disabled = (e && e[0] == '0') ? 1 : 0;
+  }
+  if (disabled || !shape_ok(T, B, H)) return 0;
+  const int clusters = ((B + 63) / 64) * 16;
+  return max_active_clusters<0>(clusters * 4) >= clusters && max_active_clusters<1>(clusters * 4) >= clusters;
+}
+
+int lstm_persist_forward(const pvr_lstm_fwd* L, cudaStream_t st) {
+  const int T = L->T, B = L->B;
+  PersistParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.B = B; p.nbt = (B + 63) / 64;
+  p.nd = L->nd; p.c_all = L->c_all; p.gates = L->gates; p.xp = L->xp;
+  p.hm = static_cast<__nv_bfloat16*>(L->hm);
+  p.h_out = static_cast<__nv_bfloat16*>(L->h_out);
+  p.h_last = L->h_last;
+  CUtensorMap ta, tw;
+  const char* err = nullptr;
+  if (!make_tmap_kchunks(&ta, L->hm, HID, (uint64_t)T * B, HID, 64, CPI, &err) ||
+      !make_tmap_2d(&tw, L->w_hh, HID, 4 * HID, HID, 64, &err)) {
+    pvr_set_error("pvr_lstm_persist_forward: tensor map: %s", err ? err : "?");
+    return PVR_ERR_CUDA;
+  }
+  mask_state_bf16_kernel<<<(B * HID + 255) / 256, 256, 0, st>>>(L->h0, L->nd, B, HID, p.hm);
+  return launch<0>(ta, tw, p, st);
+}
+
+int lstm_persist_backward(const pvr_lstm_bwd* L, cudaStream_t st) {
+  const int T = L->T, B = L->B;
+  PersistParams p;
+  memset(&p, 0, sizeof(p));
+  p.T = T; p.B = B; p.nbt = (B + 63) / 64;
+  p.nd = L->nd; p.c_all = const_cast<float*>(L->c_all); p.gates = const_cast<float*>(L->gates);
+  p.dh_out = L->dh_out; p.dh_rec = L->dh_rec; p.dc_rec = L->dc_rec;
+  p.dG = static_cast<__nv_bfloat16*>(L->dG);
+  CUtensorMap ta, tw;
+  const char* err = nullptr;
+  if (!make_tmap_kchunks(&ta, L->dG, 4 * HID, (uint64_t)T * B, 4 * HID, 64, CPI, &err) ||
+      !make_tmap_2d(&tw, L->w_hh_t, 4 * HID, HID, 4 * HID, 64, &err)) {
+    pvr_set_error("pvr_lstm_persist_backward: tensor map: %s", err ? err : "?");
+    return PVR_ERR_CUDA;
+  }
+  return launch<1>(ta, tw, p, st);
+}
+
+}  // namespace pvr
+
+extern "C" int pvr_lstm_persist_supported(int T, int B, int H) { return pvr::lstm_persist_supported(T, B, H); }
+
+// Development aid: clock64 stamps of the phases of the first 64 steps of every CTA of the following launches are
+// written to `buf` (device, 128 * 64 * 16 int64; NULL switches it off). Stamps of one CTA share one SM clock.
+extern "C" int pvr_lstm_persist_profile(void* buf) {
+  pvr::g_prof = static_cast<long long*>(buf);
+  return PVR_OK;
+}

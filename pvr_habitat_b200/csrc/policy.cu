@@ -947,12 +947,21 @@ int run_cached(const Desc* L, cudaStream_t st, Fn issue, const char* name) {
 
 }  // namespace
 
+namespace pvr {  // lstm_persist.cu
+int lstm_persist_supported(int T, int B, int H);
+int lstm_persist_forward(const pvr_lstm_fwd* L, cudaStream_t st);
+int lstm_persist_backward(const pvr_lstm_bwd* L, cudaStream_t st);
+}  // namespace pvr
+
 extern "C" int pvr_lstm_forward(const pvr_lstm_fwd* L, void* stream_) {
   if (!L || L->T <= 0 || L->B <= 0 || L->H <= 0 || L->H % 64 || !L->w_hh || !L->xp || !L->nd || !L->h0 || !L->c_all ||
       !L->hm || !L->h_out || !L->gates || !L->g_tmp || !L->h_last) {
     pvr_set_error("pvr_lstm_forward: invalid argument");
     return PVR_ERR_ARG;
   }
+  // whole sequence in one call: the persistent kernel (lstm_persist.cu) when the shape fits the device
+  if (L->flags == 0 && pvr::lstm_persist_supported(L->T, L->B, L->H))
+    return pvr::lstm_persist_forward(L, static_cast<cudaStream_t>(stream_));
   return run_cached(L, static_cast<cudaStream_t>(stream_), lstm_forward_issue, "pvr_lstm_forward");
 }
 
@@ -962,5 +971,7 @@ extern "C" int pvr_lstm_backward(const pvr_lstm_bwd* L, void* stream_) {
     pvr_set_error("pvr_lstm_backward: invalid argument");
     return PVR_ERR_ARG;
   }
+  if (L->flags == 0 && pvr::lstm_persist_supported(L->T, L->B, L->H))
+    return pvr::lstm_persist_backward(L, static_cast<cudaStream_t>(stream_));
   return run_cached(L, static_cast<cudaStream_t>(stream_), lstm_backward_issue, "pvr_lstm_backward");
 }

@@ -16,7 +16,7 @@ from . import _lib
 from . import program as prg
 from .vision_models import clip_vit
 from .vision_models import mae as mae_vit
-from .vision_models.moco import moco_conv3_compressed, moco_conv4_compressed, moco_conv5
+from .vision_models.moco import moco_conv3_compressed, moco_conv4_compressed, moco_conv5, random_init_allowed
 from .vision_models.resnet import resnet_conv3_compressed, resnet_conv4_compressed, resnet_conv5
 from .vision_models.resnet_params import ResNet50Params, ResNetBasicParams
 
@@ -145,6 +145,33 @@ _RESNET = {
 _UBER_PARTS = {'3': '_l3', '4': '_l4', '5': ''}
 
 
+# torchvision's ImageNet checkpoints (the files `pretrained=True` downloads under torchvision 0.10, the reference's pin)
+_TORCHVISION_FILES = {'resnet18': 'resnet18-f37072fd.pth', 'resnet34': 'resnet34-b627a593.pth',
+                      'resnet50': 'resnet50-0676ba61.pth'}
+
+
+def _load_torchvision(model, name, pretrained):
+    """`pretrained=True` in the reference downloads torchvision's ImageNet weights; there is no network here, so the
+    file is looked up locally: $PVR_TORCHVISION_WEIGHTS/<file>, then torch.hub's checkpoint cache (where torchvision
+    itself would have put it). A missing file raises — silently returning a random network would write a valid-looking
+    dataset of noise embeddings — unless `allow_random_init()` is active (tests / benchmarks) or pretrained=False."""
+    if not pretrained:
+        return model
+    fname = _TORCHVISION_FILES[name]
+    dirs = [os.environ.get("PVR_TORCHVISION_WEIGHTS"), os.path.join(torch.hub.get_dir(), "checkpoints")]
+    for d in filter(None, dirs):
+        path = os.path.join(d, fname)
+        if os.path.isfile(path):
+            sd = {k: v for k, v in torch.load(path, map_location='cpu').items() if not k.startswith('fc.')}
+            model.load_state_dict(sd, strict=True)
+            return model
+    if random_init_allowed():
+        return model
+    raise FileNotFoundError(
+        f"EmbeddingNet('{name}', pretrained=True): torchvision's {fname} was not found in $PVR_TORCHVISION_WEIGHTS or "
+        f"{dirs[1]} and cannot be downloaded offline; pass pretrained=False for a random-init network")
+
+
 def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, train=False):
     """Same names and return convention as src/embeddings.py:60-332: `(model, transforms)`."""
     transforms = Transforms(IMAGENET_MEAN, IMAGENET_STD)
@@ -155,13 +182,11 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
         # reference, so the same torch seed gives the same weights and the same state_dict keys ('0.weight', ...).
         model = SmallConvParams(in_channels)
     elif embedding_name in ('resnet18', 'resnet34'):
-        # torchvision.models.resnet18 / resnet34(pretrained=...), fc -> Identity (src/embeddings.py:112-117); as for
-        # resnet50 there is no download offline: pretrained weights come in through load_state_dict
-        model = ResNetBasicParams(embedding_name)
+        # torchvision.models.resnet18 / resnet34(pretrained=...), fc -> Identity (src/embeddings.py:112-117)
+        model = _load_torchvision(ResNetBasicParams(embedding_name), embedding_name, pretrained)
     elif embedding_name == 'resnet50':
-        # torchvision.models.resnet50(pretrained=...), fc -> Identity (src/embeddings.py:118-120). Offline there is no
-        # download: pretrained weights must already be loaded by the caller through load_state_dict.
-        model = ResNet50Params('conv5')
+        # torchvision.models.resnet50(pretrained=...), fc -> Identity (src/embeddings.py:118-120)
+        model = _load_torchvision(ResNet50Params('conv5'), embedding_name, pretrained)
     elif embedding_name in _MOCO_CONV5:
         model = moco_conv5(checkpoint_path=_MOCO_CONV5[embedding_name])
     elif embedding_name in _MOCO_L4:
@@ -293,9 +318,20 @@ class EmbeddingNet(nn.Module):
         return self
 
     # ---- weights changed -> recompile the program lazily
-    def load_state_dict(self, *args, **kwargs):
+    # keys of openai/CLIP's text tower: part of the reference's `embedding_model_state_dict` for clip_* encoders (its
+    # `embedding` is the whole CLIP model), not of the image path
+    _CLIP_TEXT_KEYS = ("embedding.transformer.", "embedding.token_embedding.", "embedding.positional_embedding",
+                       "embedding.ln_final.", "embedding.text_projection", "embedding.logit_scale",
+                       "embedding.input_resolution", "embedding.context_length", "embedding.vocab_size")
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
         self._encoder = None
-        return super().load_state_dict(*args, **kwargs)
+        if 'clip' in self.embedding_name:
+            # A checkpoint written by the reference holds the full CLIP model; only `embedding.visual.*` exists here.
+            # The text tower is dropped, anything else unknown still raises (strict). The other direction is one-way:
+            # a checkpoint written here has no text tower, so the reference's strict load rejects it.
+            state_dict = {k: v for k, v in state_dict.items() if not k.startswith(self._CLIP_TEXT_KEYS)}
+        return super().load_state_dict(state_dict, *args, **kwargs)
 
     def invalidate(self):
         """Call after mutating `self.embedding` parameters in place."""

@@ -97,6 +97,7 @@ class _PolicyFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         out = net._forward_cuda(x, notdone, h0, c0)
         ctx.net = net
+        ctx.generation = net._generation
         ctx.n_params = len(params)
         ctx.mark_non_differentiable(out[2], out[3])
         return out
@@ -108,6 +109,7 @@ class _PolicyFn(torch.autograd.Function):
                                       "(main_bc_2.py:211-214 uses policy_logits only)")
         if dlogits is None:
             return (None,) * (5 + ctx.n_params)
+        ctx.net._check_generation(ctx.generation)
         grads = ctx.net._backward_cuda(dlogits.contiguous())
         return (None, None, None, None, None) + tuple(grads)
 
@@ -145,6 +147,8 @@ class PolicyNet(nn.Module):
         self._needs_input_grad = False  # PolicyNetWithConv: the input rows are conv features
         self._wb = None          # bf16 weight copies
         self._saved = None
+        self._generation = 0     # bumped by every forward: the activations saved for the backward live in ONE set of
+        #                          workspace buffers per (T, B), so a backward must follow ITS forward directly
         # data-parallel hooks (set by pvr_habitat_b200.parallel): all-reduce of the BatchNorm sums
         self.process_group = None
         self.global_rows = None  # T*B of the GLOBAL batch (BatchNorm count); None = local
@@ -201,11 +205,14 @@ class PolicyNet(nn.Module):
         w["b_l"] = [getattr(self.core, f"bias_ih_l{l}").data + getattr(self.core, f"bias_hh_l{l}").data
                     for l in range(2)]
 
-    def _lstm_chunks(self, T):
-        """Number of time chunks of the two-layer wavefront (1 = layer after layer on one stream). Default: 8 while the
-        step is being captured into a CUDA graph (BCTrainer on one GPU: launches cost no host time at replay), 1 in
-        eager mode, where the step is bound by the host's launch rate and more launches would only slow it down."""
+    def _lstm_chunks(self, T, B=None):
+        """Number of time chunks of the two-layer wavefront (1 = layer after layer on one stream). With the persistent
+        recurrence kernels (csrc/lstm_persist.cu: one launch per layer and direction, B <= 128) always 1. Otherwise 8
+        while the step is being captured into a CUDA graph (launches cost no host time at replay), 1 in eager mode,
+        where the step is bound by the host's launch rate and more launches would only slow it down."""
         env = os.environ.get("PVR_LSTM_CHUNKS")
+        if not env and B is not None and _lib.lib().pvr_lstm_persist_supported(T, B, 1024):
+            return 1
         c = int(env) if env else (8 if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing() else 1)
         while c > 1 and (T % c or T // c < 2):
             c //= 2
@@ -233,10 +240,21 @@ class PolicyNet(nn.Module):
                          dc_rec=ws.dc_rec[l].data_ptr(), dG=ws.dG[l][r0:].data_ptr())
         _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(L), _stream()), "pvr_lstm_backward")
 
+    def _check_generation(self, generation):
+        if generation != self._generation:
+            raise RuntimeError(
+                "PolicyNet.backward: another forward of this module ran between this loss's forward and its backward "
+                "(evaluation pass, second micro-batch, gradient accumulation over two forwards). The saved activations "
+                "are kept in one workspace per module and have been overwritten — run backward() right after the "
+                "forward it belongs to, or use a second PolicyNet instance (e.g. a `test_model`, as main_bc_2.py:100 "
+                "does) for the interleaved passes.")
+
     def _workspace(self, T, B):
         key = (T, B, str(self.device))
         if key not in self._ws:
             if len(self._ws) > 4:
+                # (evicted workspaces stay alive while a captured graph still points into them: BCTrainer and
+                # _rollout_step hold references to the workspace they captured)
                 self._ws.clear()
             self._ws[key] = _Workspace(T, B, self.obs_size, 1024, self.num_actions, self.device, self.batch_norm)
         return self._ws[key]
@@ -247,6 +265,7 @@ class PolicyNet(nn.Module):
         T, B = notdone.shape
         ws = self._workspace(T, B)
         M, H, D = ws.M, ws.H, ws.D
+        self._generation += 1
         self._refresh_weights()
         w = self._wb
         l1, l2 = self._linears()
@@ -280,7 +299,7 @@ class PolicyNet(nn.Module):
         # LSTM layers as a wavefront over time chunks: layer 0 works through chunk c + 1 on the current stream while
         # layer 1 (input projection of the chunk + recurrence) works through chunk c on a side stream. Every step is a
         # latency-bound GEMM + cell pair that fills a fraction of the GPU, so the two recurrences overlap.
-        C = self._lstm_chunks(T)
+        C = self._lstm_chunks(T, B)
         Tc = T // C
         cur = torch.cuda.current_stream(self.device)
         side = self._side_stream() if C > 1 else cur
@@ -345,7 +364,7 @@ class PolicyNet(nn.Module):
                                           _stream()), "pvr_heads_backward")
         # reverse wavefront: layer 1 runs backwards through chunk c (+ the input gradient of that chunk for layer 0) on
         # the current stream while layer 0 runs backwards through chunk c + 1 on the side stream
-        C = self._lstm_chunks(T)
+        C = self._lstm_chunks(T, B)
         Tc = T // C
         cur = torch.cuda.current_stream(dev)
         side = self._side_stream() if C > 1 else cur
@@ -514,6 +533,7 @@ class _ConvPolicyFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         out = net._forward_conv_cuda(obs_u8, notdone, h0, c0)
         ctx.net = net
+        ctx.generation = net._generation
         ctx.n_params = len(params)
         ctx.mark_non_differentiable(out[2], out[3])
         return out
@@ -524,6 +544,7 @@ class _ConvPolicyFn(torch.autograd.Function):
             raise NotImplementedError("PolicyNetWithConv backward: a loss on `baseline` is not part of the BC path")
         if dlogits is None:
             return (None,) * (5 + ctx.n_params)
+        ctx.net._check_generation(ctx.generation)
         return (None, None, None, None, None) + tuple(ctx.net._backward_conv_cuda(dlogits.contiguous()))
 
 

@@ -24,6 +24,15 @@ class _FusedBase(torch.optim.Optimizer):
         self._sumsq = None
         self._norm = None
 
+    def count_replayed_step(self):
+        """A step replayed from a captured CUDA graph does not pass through `step()`: keep the per-parameter step
+        counters (checkpoint contents, Adam's bias correction at re-capture) in line with the updates performed."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st:
+                    st["step"] = int(st["step"]) + 1
+
     def gradient_norm(self):
         """Pre-clip global gradient norm of the last step (device tensor; `.item()` syncs) — the reference's
         `gradient_norm` statistic (main_bc_2.py:220-224)."""

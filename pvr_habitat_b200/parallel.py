@@ -35,10 +35,28 @@ def shard_starts(starting_i, rank, world):
     return list(starting_i[rank * per:(rank + 1) * per])
 
 
-def attach(policy, process_group, global_rows):
-    """Make `policy` (pvr_habitat_b200.models.PolicyNet) synchronise BatchNorm sums and gradients over the group."""
-    policy.process_group = process_group
-    policy.global_rows = global_rows
+def resolve_group(process_group=None):
+    """The process group the data-parallel collectives run on, or None for a single process. `None` under an
+    initialised torch.distributed with more than one rank — the normal torchrun idiom — means the default (WORLD)
+    group, never "no collectives"."""
+    if not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        return None
+    group = process_group if process_group is not None else torch.distributed.group.WORLD
+    return group if torch.distributed.get_world_size(group) > 1 else None
+
+
+def attach(policy, process_group, global_rows, broadcast=True):
+    """Make `policy` (pvr_habitat_b200.models.PolicyNet) synchronise BatchNorm sums and gradients over the group.
+    Parameters and buffers are broadcast from the group's first rank, so the replicas start identical whatever the
+    seeds of the ranks were."""
+    group = resolve_group(process_group)
+    policy.process_group = group
+    policy.global_rows = global_rows if group is not None else None
+    if group is not None and broadcast:
+        src = torch.distributed.get_global_rank(group, 0)
+        with torch.no_grad():
+            for t in list(policy.parameters()) + list(policy.buffers()):
+                torch.distributed.broadcast(t.data, src=src, group=group)
     return policy
 
 

@@ -118,8 +118,11 @@ def load(name, device="cpu", checkpoint_path=None):
     model = CLIPImageModel(name)
     path = checkpoint_path or (name.replace("/", "-") + ".pt")
     if os.path.isfile(path):
-        sd = torch.load(path, map_location="cpu")
-        sd = {k: v for k, v in sd.items() if k.startswith("visual.")}
+        try:  # openai's published files ("ViT-B-32.pt") are TorchScript archives
+            sd = torch.jit.load(path, map_location="cpu").state_dict()
+        except RuntimeError:  # a plain state_dict file
+            sd = torch.load(path, map_location="cpu")
+        sd = {k: v.float() for k, v in sd.items() if k.startswith("visual.")}
         model.load_state_dict(sd, strict=True)
     elif not _ALLOW_RANDOM_INIT[-1]:
         raise FileNotFoundError(f"CLIP checkpoint {path} not found (no network access to download it)")

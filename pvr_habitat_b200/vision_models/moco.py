@@ -26,6 +26,10 @@ def allow_random_init():
         _ALLOW_RANDOM_INIT.pop()
 
 
+def random_init_allowed():
+    return _ALLOW_RANDOM_INIT[-1]
+
+
 def _load_encoder_q(model, checkpoint_path, allowed_unexpected):
     if not os.path.isfile(checkpoint_path) and _ALLOW_RANDOM_INIT[-1]:
         return model

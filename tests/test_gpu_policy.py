@@ -354,11 +354,12 @@ def test_rollout_step_graph_replay_equals_eager():
 
 @pytest.mark.parametrize("T,B", [(64, 16), (100, 4), (16, 8)])
 def test_lstm_wavefront_chunks_equal_the_layer_by_layer_schedule(T, B, monkeypatch):
-    """Two-stream wavefront over time chunks (PVR_LSTM_CHUNKS, default 8) against one chunk on one stream: the same
-    kernels on the same data (recurrent state carried across chunk borders forwards and backwards, done masks at the
-    borders). The forward is made deterministic for the comparison (PVR_LSTM_NO_INPLACE: no split-K atomics in the
-    recurrent GEMM; with them a last-bit difference flips bf16 roundings of h and shows up as ~1e-4), the backward
-    keeps its 8-slice atomic GEMMs, so gradients agree to that noise."""
+    """The two implementations of the recurrence on the same data: one chunk per layer = the persistent whole-sequence
+    kernels (csrc/lstm_persist.cu; deterministic sums, exp-based sigmoid / tanh with the fast exponential) against the
+    per-step kernels run as a two-stream wavefront over time chunks (PVR_LSTM_CHUNKS = 8: recurrent state carried
+    across chunk borders forwards and backwards, done masks at the borders; expf / tanhf, 8-slice atomic GEMMs in the
+    backward). They share the rounding points (bf16 recurrent operand, bf16 dG), so the results agree to the noise of
+    a bf16 rounding of h landing on the other side (~1e-3 relative on the logits)."""
     monkeypatch.setenv("PVR_LSTM_NO_INPLACE", "1")
     rng = np.random.default_rng(T + B)
     obs = torch.from_numpy(rng.standard_normal((T, B, 192)).astype(np.float32))
@@ -376,10 +377,10 @@ def test_lstm_wavefront_chunks_equal_the_layer_by_layer_schedule(T, B, monkeypat
         results.append((out["policy_logits"].detach(), state, {k: p.grad.clone() for k, p in net.named_parameters()
                                                                if p.grad is not None}))
     (l1, s1, g1), (l2, s2, g2) = results
-    assert rel(l1, l2) < 1e-6 and all(rel(a, b) < 1e-6 for a, b in zip(s1, s2)), (rel(l1, l2),)
+    assert rel(l1, l2) < 3e-3 and all(rel(a, b) < 3e-3 for a, b in zip(s1, s2)), (rel(l1, l2),)
     assert set(g1) == set(g2)
     for k in g1:
-        assert rel(g1[k], g2[k]) < 1e-2, (k, rel(g1[k], g2[k]))  # dG is rounded to bf16 after the noisy fp32 sums
+        assert rel(g1[k], g2[k]) < 2e-2, (k, rel(g1[k], g2[k]))  # dG is rounded to bf16 after the noisy fp32 sums
 
 
 def test_trained_policy_argmax_agreement_vs_oracle():

@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload uber34x3|conv5]
 
-One step = one pass of the embedding hot path over one batch of synthetic observations:
+One step = the embedding hot path over one batch of synthetic observations, `--passes` (default 8) encoder passes of
+`obs_per_pass` observations each, so that the K timed steps last >= 2 s (one pass is 13 ms):
 uint8 (B, 224, 224, 3n) -> fused preprocessing kernel -> ResNet-50 trunk(s) (tcgen05 implicit GEMM) -> (B, n*O) fp32.
 Default workload = BASELINE.json configs[1]: moco_aug_uber_34 (layer3 + layer4 compressed taps, two independent
 ResNet-50 trunks as the reference computes them, src/embeddings.py:44-57,225-229), 3-frame observations, bf16.
@@ -13,6 +14,9 @@ ResNet-50 trunks as the reference computes them, src/embeddings.py:44-57,225-229
           EmbeddingNet.embed -> D2H of the embeddings, every step inside the timed region.
 `roofline` dominant kernel = conv_gemm_kernel (all tcgen05 conv launches of a step): algorithmic conv FLOPs of the
           step / summed device time of those launches (CUDA events between ops on the launch stream, measured here).
+`bc`, `clip_b16`, `finetune`: the other BASELINE configs measured in the same run, each with its own roofline figure
+          and CPU baseline: BC steps/s (configs[4], + a weak-scaling line under torchrun), CLIP ViT-B/16 at 1024
+          images per GPU (configs[2]), end-to-end finetuning steps/s (configs[3]).
 `cpu_baseline` the oracle's CPU port of the same workload on this host's cores (bounded sample), rank 0, N=1 only.
 --impl reference: the reference's own CPU implementation of the path (oracle port: the reference is Python and does
           not travel to the GPU box) on all host threads, same JSON schema.
@@ -214,8 +218,9 @@ def bc_dataset(seed=7):
     return obs, action, done, None
 
 
-def bench_bc(steps, warmup, world, dist, host_batches):
-    """BC train steps/s on the CUDA policy path (strong scaling: the global batch T*B = 8192 is split over ranks)."""
+def bench_bc(steps, warmup, world, dist, host_batches, batch_size=None):
+    """BC train steps/s on the CUDA policy path. Default: strong scaling, the global batch T*B = 8192 is split over the
+    ranks; `batch_size` = 128 * world gives the weak-scaling line (128 sequences per rank)."""
     import random
     from pvr_habitat_b200.bc import BCTrainer
     from pvr_habitat_b200.models import PolicyNet
@@ -223,8 +228,7 @@ def bench_bc(steps, warmup, world, dist, host_batches):
     torch.manual_seed(1)
     random.seed(1)
     net = PolicyNet((BC_CFG["D"],), BC_CFG["A"], batch_norm=True).cuda().train()
-    tr = BCTrainer(net, obs, action, done, BC_CFG["B"], BC_CFG["T"], 10 ** 9, host_batches=host_batches,
-                   process_group=dist.group.WORLD if dist is not None else None)
+    tr = BCTrainer(net, obs, action, done, batch_size or BC_CFG["B"], BC_CFG["T"], 10 ** 9, host_batches=host_batches)
     for _ in range(warmup):
         tr.step()
     if dist is not None:
@@ -259,6 +263,148 @@ def cpu_port_bc_steps_per_s(threads):
     rp.bc_train(sd, obs, action, done, BC_CFG["T"], BC_CFG["B"], BC_CPU_STEPS, 10 ** 9, True)
     dt = time.perf_counter() - t0
     return BC_CPU_STEPS / dt, dt
+
+
+CLIP_B16_IMAGES = 1024     # BASELINE configs[2]: batch 1024 per GPU
+FT_CFG = dict(T=100, B=16, hw=64, n_frames=2, n=4096)  # BASELINE configs[3]: obs (T=100, B=16*G, 64, 64, 6) uint8
+# conv trunk 8.04 MFLOP/frame forward (5 x 3x3/s2 convs on 64x64), policy trunk at D = 256: 36.2 MFLOP/sample forward;
+# forward + backward = 3 x forward
+FT_GFLOP_PER_STEP_PER_SEQ = 3 * (2 * 8.04 + 36.2) * 100 / 1e3
+
+
+def bench_clip_b16(world, dist, rank, want_cpu):
+    """BASELINE configs[2]: CLIP-architecture ViT-B/16 (random init), 1024 images of 224x224 per GPU per pass, frames
+    sharded over the ranks (no collective). Whole encoder forward against the sustained bf16 peak."""
+    net = build_net("clip_vit_b16", torch.device("cuda", torch.cuda.current_device()))
+    n = CLIP_B16_IMAGES
+    net.max_images_per_pass = n
+    obs = [torch.from_numpy(make_observations(n, 1, 300 + rank * 4 + i)).cuda() for i in range(2)]  # 2 x 154 MB > L2
+    out = torch.empty(n, net.out_size, dtype=torch.float32, device="cuda")
+    for i in range(3):
+        net.embed(obs[i % 2], 1, out=out)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    passes = 48  # ~2 s
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(passes):
+        net.embed(obs[i % 2], 1, out=out)
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    v = world * n * passes / (ms / 1e3)
+    peaks = load_peaks()
+    tf = v / world * GFLOP_PER_FRAME["clip_vit_b16"] / 1e3
+    res = {"metric": "pvr_frames_per_sec_embedded", "value": v, "unit": "frames/s", "scaling": "weak",
+           "ms_per_pass": ms / passes, "passes": passes,
+           "config": {"workload": "clip_vit_b16: CLIP-architecture ViT-B/16, 224x224 uint8 frames, random-init weights "
+                                  "(BASELINE configs[2])", "images_per_pass_per_gpu": n,
+                      "l2": "2 distinct input batches of 154 MB; activations rewritten every pass"},
+           "roofline": {"kernel": "whole ViT forward per GPU: tcgen05 GEMMs (cta_group::2) + vit_attention_kernel + "
+                                  "LayerNorm + preprocessing", "bound": "tensor", "achieved": tf,
+                        "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_sustained"],
+                        "algorithmic_gflop_per_frame": GFLOP_PER_FRAME["clip_vit_b16"], "traffic": None}}
+    del net, obs, out
+    torch.cuda.empty_cache()
+    if want_cpu:
+        threads = os.cpu_count() or 1
+        vc, dt = cpu_port_frames_per_s("clip_vit_b16", 1, 128, threads)
+        res["cpu_baseline"] = {"value": vc, "unit": "frames/s", "cores": threads, "kind": "port",
+                               "sample": f"128 images, mini-batch 64, torch CPU fp32 oracle port, {dt:.1f} s"}
+    return res
+
+
+def finetune_dataset(seed=9):
+    """Raw 64x64 two-frame uint8 observations (current | goal image) with actions that follow the mean colour of the
+    first frame's centre, episodes of random length."""
+    rng = np.random.default_rng(seed)
+    n, hw, c = FT_CFG["n"], FT_CFG["hw"], 3 * FT_CFG["n_frames"]
+    yy, xx = np.meshgrid(np.arange(hw, dtype=np.float32), np.arange(hw, dtype=np.float32), indexing="ij")
+    base = np.empty((64, hw, hw, c), dtype=np.uint8)
+    for i in range(64):
+        for ch in range(c):
+            fx, fy, ph = rng.uniform(0.03, 0.25, 3)
+            img = 110 + 70 * np.sin(fx * xx + 3 * ph) * np.cos(fy * yy + ph) + rng.normal(0, 12, (hw, hw))
+            base[i, :, :, ch] = np.clip(img, 0, 255).astype(np.uint8)
+    obs = np.concatenate([np.roll(base, 5 * r, axis=2) for r in range(n // 64)])
+    feat = obs[:, 16:48, 16:48, :3].reshape(n, -1, 3).mean(1)
+    action = np.argmax(feat + 8 * rng.standard_normal(feat.shape), 1).astype(np.int64)
+    done = rng.random(n) < 1.0 / 100.0
+    return np.ascontiguousarray(obs), action, done
+
+
+def cpu_port_finetune_steps_per_s(threads, obs, action, done, n_cpu=2):
+    """Oracle CPU port of the finetuning loop (main_bc_finetune.py:167-208) at the bench shape, bounded sample."""
+    from oracle import restate_policy as rp
+    torch.set_num_threads(threads)
+    sd = rp.init_policy_conv_state(FT_CFG["hw"], FT_CFG["n_frames"], 3, True, 1)
+    t0 = time.perf_counter()
+    rp.bc_train_conv(sd, obs, action, done, FT_CFG["T"], FT_CFG["B"], n_cpu, 10 ** 9)
+    dt = time.perf_counter() - t0
+    return n_cpu / dt, dt, n_cpu
+
+
+def bench_finetune(world, dist, want_cpu):
+    """BASELINE configs[3]: PolicyNetWithConv((64, 64, 6), 3, batch_norm=True) trained end to end with BC, 16
+    sequences of 100 steps per GPU (weak scaling: global batch 16 * G), NCCL gradient all-reduce."""
+    import random
+    from pvr_habitat_b200.bc import BCTrainer
+    from pvr_habitat_b200.models import PolicyNetWithConv
+    obs, action, done = finetune_dataset()
+    torch.manual_seed(1)
+    random.seed(1)
+    net = PolicyNetWithConv((FT_CFG["hw"], FT_CFG["hw"], 3 * FT_CFG["n_frames"]), 3, batch_norm=True).cuda().train()
+    tr = BCTrainer(net, obs, action, done, FT_CFG["B"] * world, FT_CFG["T"], 10 ** 9)
+    for _ in range(4):
+        tr.step()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = 60
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = tr.step()
+    e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    v = steps / (ms / 1e3)
+    peaks = load_peaks()
+    tf = v * FT_GFLOP_PER_STEP_PER_SEQ * FT_CFG["B"] / 1e3  # per GPU
+    res = {"metric": "bc_finetune_steps_per_sec", "value": v, "unit": "steps/s", "ms_per_step": ms / steps,
+           "steps": steps, "scaling": "weak", "frames_per_sec": v * FT_CFG["T"] * FT_CFG["B"] * world * FT_CFG["n_frames"],
+           "config": {"workload": "PolicyNetWithConv((64, 64, 6), 3, batch_norm=True), main_bc_finetune loop "
+                                  "(BASELINE configs[3])", "unroll_length": FT_CFG["T"],
+                      "batch_size_per_gpu": FT_CFG["B"], "global_batch_size": FT_CFG["B"] * world,
+                      "parallelism": f"dp{world}: sequences split over ranks, BN sums + gradients all-reduced"},
+           "roofline": {"kernel": "conv trunk forward / backward GEMMs + policy trunk + persistent LSTM recurrence",
+                        "bound": "latency (T = 100 serial LSTM steps, host-side program rebuild); tensor peak reported",
+                        "achieved": tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / peaks["bf16_sustained"],
+                        "algorithmic_gflop_per_step_per_gpu": FT_GFLOP_PER_STEP_PER_SEQ * FT_CFG["B"], "traffic": None},
+           "last_loss": float(loss)}
+    del tr, net
+    torch.cuda.empty_cache()
+    if want_cpu:
+        threads = os.cpu_count() or 1
+        v_cpu, dt, n_cpu = cpu_port_finetune_steps_per_s(threads, obs, action, done)
+        res["cpu_baseline"] = {"value": v_cpu, "unit": "steps/s", "cores": threads, "kind": "port",
+                               "sample": f"{n_cpu} steps at the same shape (T=100, B=16, 64x64x6), torch CPU fp32 "
+                                         f"oracle port, {dt:.1f} s"}
+    return res
 
 
 def run_reference(args):
@@ -303,7 +449,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="uber34x3", choices=list(WORKLOADS))
-    ap.add_argument("--obs-per-step", type=int, default=0)
+    ap.add_argument("--obs-per-step", type=int, default=0, help="observations per encoder PASS (per GPU)")
+    ap.add_argument("--passes", type=int, default=8, help="encoder passes per step (timed region >= 2 s)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the clip_b16 / finetune measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bc", action="store_true", help="skip the BC steps/s measurement")
     args = ap.parse_args()
@@ -322,11 +470,14 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    name, n_frames, obs_per_step = WORKLOADS[args.workload]
+    name, n_frames, obs_per_pass = WORKLOADS[args.workload]
     if args.obs_per_step:
-        obs_per_step = args.obs_per_step
+        obs_per_pass = args.obs_per_step
+    passes = max(1, args.passes)
+    obs_per_step = obs_per_pass * passes
     frames_per_step = obs_per_step * n_frames
     net = build_net(name, torch.device("cuda", local))
+    net.max_images_per_pass = obs_per_pass * n_frames  # `embed` cuts the step's batch into equal passes
     width = n_frames * net.out_size
     # started early (nvidia-smi needs a few hundred ms to print its first sample); only the samples read inside the
     # timed region are used
@@ -335,10 +486,12 @@ def main():
     # Inputs: a rotation of distinct batches larger than L2 in total (126 MB), so no step re-reads its input from L2.
     bytes_per_batch = obs_per_step * 224 * 224 * 3 * n_frames
     n_rot = max(2, -(-3 * 126 * 2 ** 20 // bytes_per_batch))
-    host = [torch.from_numpy(make_observations(obs_per_step, n_frames, 100 + rank * 16 + i)).pin_memory()
-            for i in range(min(n_rot, 4))]
-    while len(host) < n_rot:
-        host.append(host[len(host) % 4].clone().pin_memory())
+    base = make_observations(min(obs_per_step, 256), n_frames, 100 + rank * 16)
+    host = []
+    for i in range(n_rot):  # distinct batches: rolled copies of a seeded set (generation time is bounded)
+        reps = -(-obs_per_step // len(base))
+        b = np.concatenate([np.roll(base, 11 * (i * reps + r) + 3, axis=1) for r in range(reps)])[:obs_per_step]
+        host.append(torch.from_numpy(np.ascontiguousarray(b)).pin_memory())
     dev = [h.cuda(non_blocking=True) for h in host]
     out = torch.empty(obs_per_step, width, dtype=torch.float32, device="cuda")
     out_host = torch.empty(obs_per_step, width, dtype=torch.float32).pin_memory()
@@ -413,10 +566,10 @@ def main():
     # ---- second headline metric: BC train steps/s (all ranks: data parallel, NCCL gradient all-reduce)
     bc = None
     if not args.no_bc:
-        bc_steps = max(10, args.steps)
+        bc_steps = max(600, args.steps)  # >= 2 s of timed steps at ~3 ms per step
         # 6 warm-up steps: 3 eager ones, the CUDA-graph capture of the whole step, 2 replays
         v, ms_bc, last_loss = bench_bc(bc_steps, 6, world, dist, host_batches=False)
-        v_e2e, ms_bc_e2e, _ = bench_bc(bc_steps, 6, world, dist, host_batches=True)
+        v_e2e, ms_bc_e2e, _ = bench_bc(bc_steps // 2, 6, world, dist, host_batches=True)
         bc = {"metric": "bc_train_steps_per_sec", "value": v, "unit": "steps/s", "ms_per_step": ms_bc,
               "scaling": "strong", "steps": bc_steps,
               "config": {"workload": "PolicyNet((2048,), 3, batch_norm=True) on pre-embedded observations "
@@ -425,11 +578,28 @@ def main():
                          "batch_size": BC_CFG["B"], "dataset_rows": BC_CFG["n"],
                          "parallelism": f"dp{world}: sequences split over ranks, BN sums + gradients all-reduced"},
               "tflops_effective": v * BC_GFLOP_PER_STEP / 1e3,
-              "frac_of_bf16_sustained": v * BC_GFLOP_PER_STEP / 1e3 / load_peaks()["bf16_sustained"],
+              "frac_of_bf16_sustained": v * BC_GFLOP_PER_STEP / 1e3 / load_peaks()["bf16_sustained"] / world,
+              "roofline": {"kernel": "whole BC step per GPU (tcgen05 GEMMs + persistent LSTM recurrence + fused "
+                                     "optimizer)", "bound": "latency of 4 x T serial LSTM steps; tensor peak reported",
+                           "achieved": v * BC_GFLOP_PER_STEP / 1e3 / world, "peak": load_peaks()["bf16_sustained"],
+                           "unit": "TFLOP/s",
+                           "frac": v * BC_GFLOP_PER_STEP / 1e3 / world / load_peaks()["bf16_sustained"],
+                           "algorithmic_gflop_per_step": BC_GFLOP_PER_STEP, "traffic": None},
               "e2e": {"value": v_e2e, "unit": "steps/s", "ms_per_step": ms_bc_e2e,
                       "h2d_bytes_per_step": BC_CFG["T"] * BC_CFG["B"] // world * (BC_CFG["D"] * 4 + 8 + 1),
                       "d2h_bytes_per_step": 4},
               "last_loss": last_loss}
+        if world > 1:  # weak scaling: 128 sequences per rank, so the cost of the collectives is visible on its own
+            vw, ms_w, _ = bench_bc(bc_steps // 2, 6, world, dist, host_batches=False, batch_size=BC_CFG["B"] * world)
+            bc["weak"] = {"value": vw, "unit": "steps/s", "ms_per_step": ms_w, "scaling": "weak",
+                          "global_batch_rows": BC_CFG["T"] * BC_CFG["B"] * world,
+                          "rows_per_sec": vw * BC_CFG["T"] * BC_CFG["B"] * world}
+    extras = {}
+    if not args.no_extra:
+        want_cpu = world == 1 and rank == 0 and not args.no_cpu_baseline
+        if args.workload != "clip_b16":
+            extras["clip_b16"] = bench_clip_b16(world, dist, rank, want_cpu)
+        extras["finetune"] = bench_finetune(world, dist, want_cpu)
 
     if rank != 0:
         if dist is not None:
@@ -442,71 +612,98 @@ def main():
     if name in VIT_NAMES:
         # ViT: GEMM-dominated; the whole encoder forward (GEMMs + LayerNorm + attention) is timed as one unit
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        net.transforms.run(dev[0], n_frames, enc.slot0, enc.input_format, True)
-        enc.forward(out, net.out_size)
+        enc.bind(obs_per_pass * n_frames)
+        net.transforms.run(dev[0][:obs_per_pass], n_frames, enc.slot0, enc.input_format, True)
+        enc.forward(out[:obs_per_pass], net.out_size)
         e0.record()
         for r in range(3):
-            enc.forward(out, net.out_size)
+            enc.forward(out[:obs_per_pass], net.out_size)
         e1.record()
         torch.cuda.synchronize()
-        fwd_ms = e0.elapsed_time(e1) / 3
+        fwd_ms = e0.elapsed_time(e1) / 3 * passes
         achieved = enc.flops_per_image * frames_per_step / (fwd_ms / 1e3) / 1e12
         roofline = {"kernel": "ViT encoder forward: conv_gemm_kernel (tcgen05 GEMMs) + vit_attention_kernel + LayerNorm",
                     "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": achieved / peaks["bf16_sustained"], "traffic": None,
                     "peak_source": peaks["source"] + ", sustained bf16",
                     "algorithmic_gflop_per_frame": enc.flops_per_image / 1e9, "forward_ms_per_step": fwd_ms}
-        n_launch = 1 + enc.launches_per_forward()
+        n_launch = passes * (1 + enc.launches_per_forward())
+        roofline["frac_whole_step"] = enc.flops_per_image * frames_per_step / (ms / args.steps / 1e3) / 1e12 / \
+            peaks["bf16_sustained"]
     else:
-        roofline, n_launch = resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks, ms, args)
+        roofline, n_launch = resnet_roofline(net, enc, dev, n_rot, n_frames, obs_per_pass, passes, out, peaks, ms, args)
     return finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_step, width, n_rot,
-                  bytes_per_batch, value, ms, e2e_value, ms_e2e, clocks, roofline, n_launch, bc)
+                  bytes_per_batch, value, ms, e2e_value, ms_e2e, clocks, roofline, n_launch, bc, extras, passes)
 
 
-def resnet_roofline(net, enc, dev, n_rot, n_frames, frames_per_step, out, peaks, ms, args):
+def load_traffic():
+    """DRAM bytes per frame of every kernel family, from the ncu capture kept under profiles/ (tools/ncu_traffic.py:
+    dram__bytes_read.sum + dram__bytes_write.sum per launch of one default-workload pass); None if absent."""
+    p = os.path.join(ROOT, "profiles", "r02_dram_traffic_uber34x3.json")
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+def resnet_roofline(net, enc, dev, n_rot, n_frames, obs_per_pass, passes, out, peaks, ms, args):
+    """Per-kernel figures of ONE pass (obs_per_pass observations), scaled to the step of `passes` passes."""
     conv_ms, conv_flops, other_ms = [], 0.0, []
     reps = 5
+    frames_per_pass = obs_per_pass * n_frames
+    frames_per_step = frames_per_pass * passes
+    enc.bind(frames_per_pass)
     for r in range(reps + 1):
-        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, enc.input_format, True)
-        op_ms = enc.forward_timed(out, net.out_size)
+        net.transforms.run(dev[r % n_rot][:obs_per_pass], n_frames, enc.slot0, enc.input_format, True)
+        op_ms = enc.forward_timed(out[:obs_per_pass], net.out_size)
         if r == 0:
             continue  # warm
         conv_ms.append(sum(t for t, m in zip(op_ms, enc.op_meta) if m["kind"] == 1))
         other_ms.append(sum(t for t, m in zip(op_ms, enc.op_meta) if m["kind"] != 1))
-    conv_flops = sum(m["flops_per_image"] for m in enc.op_meta if m["kind"] == 1) * frames_per_step
+    conv_flops = sum(m["flops_per_image"] for m in enc.op_meta if m["kind"] == 1) * frames_per_pass
     n_conv = sum(1 for m in enc.op_meta if m["kind"] == 1)
     conv_t = float(np.mean(conv_ms)) / 1e3
     achieved = conv_flops / conv_t / 1e12
+    step_s = ms / args.steps / 1e3
+    whole = conv_flops * passes / step_s / 1e12  # the same FLOPs over the driver-timed step (everything included)
     # preprocessing kernel timed alone (HBM bound)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for r in range(10):
-        net.transforms.run(dev[r % n_rot], n_frames, enc.slot0, enc.input_format, True)
+        net.transforms.run(dev[r % n_rot][:obs_per_pass], n_frames, enc.slot0, enc.input_format, True)
     e1.record()
     torch.cuda.synchronize()
     pre_ms = e0.elapsed_time(e1) / 10
-    pre_bytes = frames_per_step * (224 * 224 * 3 + 224 * 112 * 64)
+    alg_bytes = 224 * 224 * 3 + 224 * 224 * 3 * 2      # SURVEY.md §8(d): uint8 frame in, bf16 (3, 224, 224) out
+    fmt_bytes = net.transforms.format_bytes_per_frame(enc.input_format)  # what the chosen stem format moves
+    traffic = load_traffic()
+    tr_conv = tr_pre = None
+    if traffic is not None:
+        tr_conv = int(traffic["conv_bytes_per_frame"] * frames_per_pass)
+        tr_pre = int(traffic["preprocess_bytes_per_frame"] * frames_per_pass)
     roofline = {
-        "kernel": "conv_gemm_kernel + conv3x3_patch_kernel (tcgen05 implicit GEMM, %d conv ops/step)" % n_conv,
+        "kernel": "conv_gemm_kernel + conv3x3_patch_kernel + conv_b2b_kernel (tcgen05 implicit GEMM, %d conv launches "
+                  "per pass of %d frames)" % (n_conv, frames_per_pass),
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-        "frac": achieved / peaks["bf16_sustained"], "traffic": None,
+        "frac": achieved / peaks["bf16_sustained"],
+        "frac_whole_step": whole / peaks["bf16_sustained"], "achieved_whole_step": whole,
+        "frac_of_burst_peak": achieved / peaks["bf16_burst"],
+        # per pass like `achieved`: sum over the conv launches of one pass (ncu, profiles/r02_dram_traffic_*.json)
+        "traffic": tr_conv, "traffic_source": "profiles/r02_dram_traffic_uber34x3.json" if traffic else None,
         "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",
-        "algorithmic_gflop_per_frame": conv_flops / frames_per_step / 1e9,
-        "conv_ms_per_step": conv_t * 1e3, "conv_share_of_step": conv_t * 1e3 / (ms / args.steps),
-        "other_ops_ms_per_step": float(np.mean(other_ms)),
-        "preprocess": {"bound": "hbm", "ms_per_step": pre_ms, "achieved": pre_bytes / (pre_ms / 1e3) / 1e9,
-                       "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                       "frac": pre_bytes / (pre_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
-                       "algorithmic_bytes_per_frame": 224 * 224 * 3 + 224 * 112 * 64,
-                       # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at 256 frames
-                       # (profiles/r01_ncu_full_preprocess.txt: 34 MB + 446 MB), scaled to this launch
-                       "traffic": int((34.0e6 + 446.0e6) / 256 * frames_per_step)},
+        "algorithmic_gflop_per_frame": conv_flops / frames_per_pass / 1e9,
+        "conv_ms_per_pass": conv_t * 1e3, "conv_share_of_step": conv_t * 1e3 * passes / (ms / args.steps),
+        "other_ops_ms_per_pass": float(np.mean(other_ms)),
+        "preprocess": {"bound": "hbm", "ms_per_pass": pre_ms,
+                       "achieved": alg_bytes * frames_per_pass / (pre_ms / 1e3) / 1e9, "peak": peaks["hbm_gbs"],
+                       "unit": "GB/s", "frac": alg_bytes * frames_per_pass / (pre_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                       "algorithmic_bytes_per_frame": alg_bytes,
+                       "format_bytes_per_frame": fmt_bytes,
+                       "frac_of_format_bytes": fmt_bytes * frames_per_pass / (pre_ms / 1e3) / 1e9 / peaks["hbm_gbs"],
+                       "traffic": tr_pre},
     }
-    return roofline, 1 + int(enc.lib.pvr_encoder_launch_count(enc.handle))
+    return roofline, passes * (1 + int(enc.lib.pvr_encoder_launch_count(enc.handle)))
 
 
 def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_step, width, n_rot, bytes_per_batch,
-           value, ms, e2e_value, ms_e2e, clocks, roofline, n_launch, bc):
+           value, ms, e2e_value, ms_e2e, clocks, roofline, n_launch, bc, extras, passes):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -537,6 +734,7 @@ def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_ste
               "224x224 uint8 frames, random-init weights" if name in MAE_NAMES else
               f"{name}: ResNet-50 conv5, 224x224 uint8 frames, random-init weights")),
             "obs_per_step_per_gpu": obs_per_step, "frames_per_step_per_gpu": frames_per_step,
+            "passes_per_step": passes, "obs_per_pass": obs_per_step // passes,
             "embedding_width": width, "sharding": "observations split over ranks, no data-path collective",
             "l2": f"inputs rotate over {n_rot} distinct batches ({n_rot * bytes_per_batch / 2**20:.0f} MiB > 126 MB L2); "
                   "activations (>1 GB/step) are rewritten every step",
@@ -547,6 +745,7 @@ def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_ste
         "tflops_effective": value * GFLOP_PER_FRAME[name] / 1e3,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "bc": bc,
     }
+    line.update(extras)
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

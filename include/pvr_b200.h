@@ -298,6 +298,35 @@ int pvr_cast_weight(const float* w, int rows, int cols, void* w_bf16, int64_t ld
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Data-parallel collectives (K12). The reference is single process (no DDP / NCCL
+ * anywhere); data parallelism is new functionality whose parity target is the reference at the GLOBAL batch. One
+ * communicator per process / GPU over NCCL (NVLink 5 / NVSwitch inside a node), bound at run time to the libnccl.so.2
+ * of the torch installation. Every call is a plain stream-ordered launch on `stream`: it can be captured into a CUDA
+ * graph with the kernels around it and forked onto a second stream to overlap with compute. `dtype`: PVR_COMM_*.
+ * Reductions are sums (the BC loss is pre-scaled by 1 / global rows, pvr_ce_loss). */
+#define PVR_COMM_F32 0
+#define PVR_COMM_F64 1
+#define PVR_COMM_BF16 2
+#define PVR_COMM_I64 3
+/* Load NCCL (optional explicit path of libnccl.so.2; NULL = the copy already loaded in the process). */
+int pvr_comm_load(const char* libnccl_path);
+/* NCCL version code (e.g. 22809), 0 if NCCL is not loaded. */
+int pvr_comm_version(void);
+/* 128-byte unique id, created on one rank and handed to the others by the host (torch.distributed store / file). */
+int pvr_comm_unique_id(void* id128);
+/* Collective over all ranks: creates this rank's communicator on the CURRENT CUDA device. */
+int pvr_comm_init(int rank, int world, const void* id128, void** comm_out);
+int pvr_comm_destroy(void* comm);
+/* In-place sum over ranks of `count` elements. */
+int pvr_comm_allreduce(void* comm, void* buf, int64_t count, int dtype, void* stream);
+/* recv (recv_count elements) = this rank's slice of the sum over ranks of send (world * recv_count elements). */
+int pvr_comm_reduce_scatter(void* comm, const void* send, void* recv, int64_t recv_count, int dtype, void* stream);
+/* recv (world * send_count elements) = concatenation over ranks of send (send_count elements). */
+int pvr_comm_allgather(void* comm, const void* send, void* recv, int64_t send_count, int dtype, void* stream);
+/* In-place broadcast from `root`. */
+int pvr_comm_broadcast(void* comm, void* buf, int64_t count, int dtype, int root, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * End-to-end finetuning (PolicyNetWithConv, src/models.py:96-197; main_bc_finetune.py): layout kernels around the
  * GEMM formulation of the conv trunk's backward (3x3, stride 2, padding 1, 32 channels).
  */

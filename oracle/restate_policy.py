@@ -80,9 +80,10 @@ def make_batch(obs, action, done, starting_i, T):
 
 
 def bc_train(sd, obs, action, done, T, B, steps, max_frames, batch_norm, lr=1e-4, alpha=0.99, eps=1e-5,
-             max_grad_norm=40.0, seed=1):
+             max_grad_norm=40.0, seed=1, conv=False):
     """The training loop of main_bc_2.py:186-227 restated; `sd` tensors are updated in place.
-    Returns per-step (loss, pre-clip gradient norm)."""
+    Returns per-step (loss, pre-clip gradient norm). conv=True: main_bc_finetune.py:167-208 (raw uint8 observations
+    through the conv trunk of PolicyNetWithConv, trained end to end)."""
     random.seed(seed)
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items()
               if v.is_floating_point() and "running" not in k}
@@ -95,8 +96,12 @@ def bc_train(sd, obs, action, done, T, B, steps, max_frames, batch_norm, lr=1e-4
         starting_i = sample_with_minimum_distance(len(action), B, T)
         o, a, d = make_batch(obs, action, done, starting_i, T)
         state = (torch.zeros(2, B, H), torch.zeros(2, B, H))
-        logits, _, _ = policy_forward(params, torch.from_numpy(o), torch.from_numpy(d), state, batch_norm, True,
-                                      bn_buffers)
+        if conv:
+            feat = conv_features(params, torch.from_numpy(o)).view(T, B, -1)
+            logits, _, _ = policy_forward(params, feat, torch.from_numpy(d), state, batch_norm, True, bn_buffers)
+        else:
+            logits, _, _ = policy_forward(params, torch.from_numpy(o), torch.from_numpy(d), state, batch_norm, True,
+                                          bn_buffers)
         loss = bc_loss(logits, torch.from_numpy(a))
         lr_k = lr * (1 - (step + 1) / max_epochs)  # scheduler.step() precedes optimizer.step() (main_bc_2.py:216)
         grads = torch.autograd.grad(loss, [params[k] for k in params], allow_unused=True)
@@ -112,6 +117,10 @@ def bc_train(sd, obs, action, done, T, B, steps, max_frames, batch_norm, lr=1e-4
     for k in params:
         sd[k] = params[k].detach()
     return trace
+
+
+def bc_train_conv(sd, obs_u8, action, done, T, B, steps, max_frames, batch_norm=True, **kw):
+    return bc_train(sd, obs_u8, action, done, T, B, steps, max_frames, batch_norm, conv=True, **kw)
 
 
 def synthetic_bc_data(n, d, n_actions, seed):

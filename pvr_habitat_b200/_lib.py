@@ -10,6 +10,7 @@ PVR_FMT_NHWC4_BF16 = 1
 PVR_FMT_STEM_BF16 = 2
 PVR_FMT_NHWC4_F32 = 3
 PVR_RESIZE_BICUBIC = 0x100
+PVR_COMM_F32, PVR_COMM_F64, PVR_COMM_BF16, PVR_COMM_I64 = 0, 1, 2, 3
 PVR_OP_FP32 = 2
 PVR_CONV_OUT_F32 = 1
 PVR_GEMM_PDL, PVR_GEMM_MN = 1, 2
@@ -114,6 +115,15 @@ _SIGNATURES = {
     "pvr_optim_step_dev": (ctypes.c_int, [_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                                           ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _f, _f, _vp, _f, _f, _f, _i,
                                           _vp, _vp]),
+    "pvr_comm_load": (ctypes.c_int, [ctypes.c_char_p]),
+    "pvr_comm_version": (ctypes.c_int, []),
+    "pvr_comm_unique_id": (ctypes.c_int, [_vp]),
+    "pvr_comm_init": (ctypes.c_int, [_i, _i, _vp, ctypes.POINTER(ctypes.c_void_p)]),
+    "pvr_comm_destroy": (ctypes.c_int, [_vp]),
+    "pvr_comm_allreduce": (ctypes.c_int, [_vp, _vp, _i64, _i, _vp]),
+    "pvr_comm_reduce_scatter": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "pvr_comm_allgather": (ctypes.c_int, [_vp, _vp, _vp, _i64, _i, _vp]),
+    "pvr_comm_broadcast": (ctypes.c_int, [_vp, _vp, _i64, _i, _i, _vp]),
     "pvr_gemm_bf16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,

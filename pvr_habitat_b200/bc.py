@@ -63,10 +63,14 @@ class BCTrainer:
         # Whole-step CUDA graph (single process, RMSprop): forward, loss, backward, clip + update are ~100 launches
         # issued through ctypes in ~4.8 ms of host time against ~4 ms of GPU time; replayed from one graph the step is
         # GPU bound. The batch is copied into static buffers, the learning rate lives in device memory.
-        capturable = optimizer == "rmsprop" and not isinstance(actor_model, PolicyNetWithConv)
+        # the whole step replays from one CUDA graph when everything in it is a stream-ordered launch: RMSprop with the
+        # learning rate in device memory, and — data parallel — collectives issued through our own NCCL communicator
+        # (parallel.Comm.capturable; torch.distributed collectives of other backends are not captured)
+        capturable = optimizer == "rmsprop" and not isinstance(actor_model, PolicyNetWithConv) and \
+            (self.world == 1 or (actor_model.comm is not None and actor_model.comm.capturable))
         if use_graph is None:
-            use_graph = self.world == 1 and capturable
-        self.use_graph = bool(use_graph) and self.world == 1 and capturable
+            use_graph = capturable
+        self.use_graph = bool(use_graph) and capturable
         self._graph = None
         self._eager_steps = 0
 
@@ -110,8 +114,7 @@ class BCTrainer:
         else:
             loss = self._step_body(o, a, d, n_mine, None)
             if self.world > 1:
-                loss = loss.detach().clone()
-                torch.distributed.all_reduce(loss, group=self.group)
+                loss = self.model.comm.all_reduce(loss.detach().clone())
         self.frames += self.T * self.B
         self.last_loss = loss.detach()
         if self.host_batches:  # gather + copy the next batch while the GPU works on this one (same draw order)
@@ -133,7 +136,8 @@ class BCTrainer:
     def _graph_step(self, o, a, d, n_mine):
         if self._graph is None and self._eager_steps < 3:  # warm-up: lazy allocations, kernel attributes, LSTM graphs
             self._eager_steps += 1
-            return self._step_body(o, a, d, n_mine, None)
+            loss = self._step_body(o, a, d, n_mine, None)
+            return self.model.comm.all_reduce(loss.detach().clone()) if self.world > 1 else loss
         self.scheduler.step()  # before the update, like the reference: lr_k = lr0 (1 - k / max_epochs)
         lr = float(self.optimizer.param_groups[0]["lr"])
         if self._graph is None:
@@ -148,6 +152,8 @@ class BCTrainer:
             with torch.cuda.graph(g):  # records the step, does not run it: the replay below performs it
                 loss = self._step_body(self._go, self._ga, self._gd, n_mine, self._lr_dev, self._gstate)
                 self._gloss = loss.detach().clone()
+                if self.world > 1:
+                    self.model.comm.all_reduce(self._gloss)
             self._graph = g
         else:
             self._go.copy_(o, non_blocking=True)

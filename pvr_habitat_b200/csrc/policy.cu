@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16
                                                               int rows, int cols, __nv_bfloat16* __restrict__ out,
                                                               long long ldo) {
   __shared__ __nv_bfloat16 t[32][34];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int c0 = blockIdx.y * 32, r0 = blockIdx.x * 32;  // rows (millions in the finetune backward) on grid.x
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int i = ty; i < 32; i += 8)
     if (r0 + i < rows && c0 + tx < cols) t[i][tx] = in[(long long)(r0 + i) * ldi + c0 + tx];
@@ -704,7 +704,7 @@ extern "C" int pvr_transpose_bf16(const void* in, int64_t ldi, int rows, int col
     pvr_set_error("pvr_transpose_bf16: invalid argument");
     return PVR_ERR_ARG;
   }
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  dim3 grid((rows + 31) / 32, (cols + 31) / 32);
   transpose_bf16_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
       static_cast<const __nv_bfloat16*>(in), ldi, rows, cols, static_cast<__nv_bfloat16*>(out), ldo);
   PVR_LAUNCH_CHECK("pvr_transpose_bf16");

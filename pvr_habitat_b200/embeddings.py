@@ -51,6 +51,13 @@ class Transforms(nn.Module):
         self.interpolation = interpolation
         self.identity_resize_only = False  # debugging aid: reject frames that would need an actual resize
 
+    def format_bytes_per_frame(self, fmt, h=224, w=224):
+        """HBM bytes one frame costs in output format `fmt` (uint8 frame read + formatted frame written)."""
+        c = self.crop
+        out = {_lib.PVR_FMT_NCHW_F32: 3 * c * c * 4, _lib.PVR_FMT_NHWC4_BF16: c * c * 4 * 2,
+               _lib.PVR_FMT_STEM_BF16: c * (c // 2) * 32 * 2, _lib.PVR_FMT_NHWC4_F32: c * c * 4 * 4}[fmt & 0xff]
+        return h * w * 3 + out
+
     def run(self, obs_nhwc_u8, n_frames, out_ptr, fmt, sample_major):
         """obs: CUDA uint8 (N, H, W, 3*n_frames) contiguous; writes n_frames*N images at `out_ptr`."""
         n, h, w, ch = obs_nhwc_u8.shape

@@ -151,6 +151,7 @@ class PolicyNet(nn.Module):
         #                          workspace buffers per (T, B), so a backward must follow ITS forward directly
         # data-parallel hooks (set by pvr_habitat_b200.parallel): all-reduce of the BatchNorm sums
         self.process_group = None
+        self.comm = None         # parallel.Comm of the group (NCCL through the C ABI, or torch.distributed)
         self.global_rows = None  # T*B of the GLOBAL batch (BatchNorm count); None = local
 
     @property
@@ -277,8 +278,8 @@ class PolicyNet(nn.Module):
                 _lib.check(lib.pvr_bn1d_stats(x.data_ptr(), x.stride(0), M, D, ws.sums.data_ptr(), _stream()),
                            "pvr_bn1d_stats")
                 count = float(M)
-                if self.process_group is not None:
-                    torch.distributed.all_reduce(ws.sums, group=self.process_group)
+                if self.comm is not None:
+                    self.comm.all_reduce(ws.sums)
                     count = float(self.global_rows)
                 _lib.check(lib.pvr_bn1d_normalize(x.data_ptr(), x.stride(0), M, D, ws.sums.data_ptr(), count, bn.eps,
                                                   bn.momentum, bn.weight.data_ptr(), bn.bias.data_ptr(),
@@ -350,6 +351,18 @@ class PolicyNet(nn.Module):
         for p, sz in zip(params, sizes):
             grads.append(flat[off:off + p.numel()].view_as(p))
             off += sz
+        # gradient buckets of the data-parallel all-reduce, in the order the backward completes them: [LSTM layer 1 +
+        # heads] after layer 1's weight gradients, [LSTM layer 0] after layer 0's, the trunk at the end. A bucket's
+        # all-reduce runs on the communication stream while the GEMMs of the next bucket are computed.
+        first_lstm = 6 if self.batch_norm else 4          # index of weight_ih_l0 in `params`
+        off_l0, off_l1 = sum(sizes[:first_lstm]), sum(sizes[:first_lstm + 4])
+        bucket_end = off_l0
+        overlap = self.comm is not None and not need_dx
+
+        def bucket(lo, hi):
+            if overlap:
+                self.comm.all_reduce(flat[lo:hi], wait=False)
+
         g = dict(zip(["bn_w", "bn_b"] if self.batch_norm else [], grads[:2]))
         names = ["W1", "b1", "W2", "b2", "Wih0", "Whh0", "bih0", "bhh0", "Wih1", "Whh1", "bih1", "bhh1", "Wp", "bp"]
         g.update(zip(names, grads[2 if self.batch_norm else 0:]))
@@ -395,6 +408,10 @@ class PolicyNet(nn.Module):
             # dW = dG^T X with dG (M, 4H) and X (M, H) as they sit in memory: MN-major tensor-core operands
             gemm(dG, ws.hm[l], g[f"Whh{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)
             gemm(dG, below[l], g[f"Wih{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)
+            if l == 1:
+                bucket(off_l1, flat.numel())
+            else:
+                bucket(off_l0, off_l1)
         # through ReLU of fc2: dZ2 = (dG0 W_ih0) * (H2 > 0)
         gemm(ws.dG[0], w["WihT"][0], ws.dZ2, M, H, 4 * H, res=ws.H2, res_mode=1)
         colsum(ws.dZ2, H, g["b2"])
@@ -420,8 +437,8 @@ class PolicyNet(nn.Module):
             if self.batch_norm:
                 count = float(M)
                 sums = torch.stack([g["bn_w"], g["bn_b"]])  # sum dy*xhat, sum dy of THIS rank
-                if self.process_group is not None:
-                    torch.distributed.all_reduce(sums, group=self.process_group)
+                if self.comm is not None:
+                    self.comm.all_reduce(sums)
                     count = float(self.global_rows)
                 bn = self.fc[0]
                 _lib.check(lib.pvr_bn1d_backward_dx(ws.dX0.data_ptr(), ws.dX0.stride(0), x.data_ptr(), x.stride(0), M,
@@ -432,9 +449,11 @@ class PolicyNet(nn.Module):
                 _lib.check(lib.pvr_bf16_rows_to_f32(ws.dX0.data_ptr(), ws.dX0.stride(0), M, D, dx.data_ptr(), D,
                                                     _stream()), "pvr_bf16_rows_to_f32")
         self._pending_flat = flat
-        if not need_dx and self.process_group is not None:
-            # data parallel: SUM over ranks (the loss is pre-scaled by 1/global rows)
-            torch.distributed.all_reduce(flat, group=self.process_group)
+        if not need_dx and self.comm is not None:
+            # data parallel: SUM over ranks (the loss is pre-scaled by 1/global rows). The two LSTM buckets went out
+            # while the backward continued (see `bucket` above); what is left is the trunk (BN, fc1, fc2).
+            self.comm.all_reduce(flat[:bucket_end], wait=False)
+            self.comm.join()
         return (grads, dx) if need_dx else grads
 
     # ------------------------------------------------------------------------------------------ public forward
@@ -674,10 +693,10 @@ class PolicyNetWithConv(PolicyNet):
                 dy = torch.empty(F * hi * hi, 32, dtype=f32, device=dev)
                 _lib.check(lib.pvr_col2im(dcol.data_ptr(), Kp, F, hi, hi, 32, ho, ho, dy.data_ptr(), _stream()),
                            "pvr_col2im")
-        if self.process_group is not None:
-            torch.distributed.all_reduce(self._pending_flat, group=self.process_group)
+        if self.comm is not None:
+            self.comm.all_reduce(self._pending_flat, wait=False)
             flat_c = torch.cat([g.flatten() for g in gconv])
-            torch.distributed.all_reduce(flat_c, group=self.process_group)
+            self.comm.all_reduce(flat_c)
             off = 0
             for g in gconv:
                 g.copy_(flat_c[off:off + g.numel()].view_as(g))

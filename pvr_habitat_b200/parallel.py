@@ -7,7 +7,9 @@
   update equals the reference's mean over the global batch; BatchNorm1d statistics are computed from all-reduced
   per-feature sums (synchronised batch statistics, global count).
 """
+import ctypes
 import os
+import sys
 
 import torch
 
@@ -45,18 +47,111 @@ def resolve_group(process_group=None):
     return group if torch.distributed.get_world_size(group) > 1 else None
 
 
+class Comm:
+    """The collectives of the data-parallel BC path over one process group.
+
+    NCCL groups: a communicator of our own created through the C ABI (`pvr_comm_*`, csrc/comm.cu; the unique id travels
+    over the torch.distributed group once). Every collective is a plain launch on ONE communication stream — forked
+    from / joined to the caller's stream with events, so it can overlap the kernels issued after it and is captured
+    into the whole-step CUDA graph like any kernel. Other backends (gloo: the CPU-side tests, two ranks sharing one
+    GPU) go through torch.distributed on the caller's stream.
+    """
+    _DT = {torch.float32: 0, torch.float64: 1, torch.bfloat16: 2, torch.int64: 3}
+
+    def __init__(self, group):
+        from . import _lib
+        self.group = group
+        self.rank = torch.distributed.get_rank(group)
+        self.world = torch.distributed.get_world_size(group)
+        self.native = None
+        self._stream = None
+        self._pending = False
+        if torch.distributed.get_backend(group) == "nccl" and torch.cuda.is_available():
+            lib = _lib.lib()
+            path = next((os.path.join(p, "nvidia", "nccl", "lib", "libnccl.so.2") for p in sys.path
+                         if os.path.exists(os.path.join(p, "nvidia", "nccl", "lib", "libnccl.so.2"))), "")
+            _lib.check(lib.pvr_comm_load(path.encode()), "pvr_comm_load")
+            uid = (ctypes.c_char * 128)()
+            if self.rank == 0:
+                _lib.check(lib.pvr_comm_unique_id(uid), "pvr_comm_unique_id")
+            box = [bytes(uid)]
+            torch.distributed.broadcast_object_list(box, src=torch.distributed.get_global_rank(group, 0), group=group)
+            handle = ctypes.c_void_p()
+            _lib.check(lib.pvr_comm_init(self.rank, self.world, box[0], ctypes.byref(handle)), "pvr_comm_init")
+            self.native, self._lib = handle, lib
+            self._stream = torch.cuda.Stream()
+
+    @property
+    def capturable(self):
+        return self.native is not None
+
+    def all_reduce(self, t, wait=True):
+        """In-place SUM over the ranks. wait=False: the caller's stream does not wait for the result — call `join()`
+        before using it (gradient buckets all-reduced while the backward continues)."""
+        if self.native is None:
+            torch.distributed.all_reduce(t, group=self.group)
+            return t
+        from . import _lib
+        assert t.is_contiguous() and t.is_cuda
+        cur = torch.cuda.current_stream(t.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._stream.wait_event(ev)
+        _lib.check(self._lib.pvr_comm_allreduce(self.native, t.data_ptr(), t.numel(), self._DT[t.dtype],
+                                                ctypes.c_void_p(self._stream.cuda_stream)), "pvr_comm_allreduce")
+        self._pending = True
+        if wait:
+            self.join()
+        return t
+
+    def join(self):
+        """Make the caller's current stream wait for every collective issued so far."""
+        if self.native is not None and self._pending:
+            ev = torch.cuda.Event()
+            ev.record(self._stream)
+            torch.cuda.current_stream().wait_event(ev)
+            self._pending = False
+
+    def broadcast(self, t, root=0):
+        if self.native is None:
+            torch.distributed.broadcast(t, src=torch.distributed.get_global_rank(self.group, root), group=self.group)
+            return t
+        from . import _lib
+        cur = torch.cuda.current_stream(t.device)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._stream.wait_event(ev)
+        _lib.check(self._lib.pvr_comm_broadcast(self.native, t.data_ptr(), t.numel(), self._DT[t.dtype], root,
+                                                ctypes.c_void_p(self._stream.cuda_stream)), "pvr_comm_broadcast")
+        self._pending = True
+        self.join()
+        return t
+
+
+_COMMS = {}
+
+
+def comm_for(group):
+    """One Comm per process group (NCCL communicators are expensive and must be created collectively)."""
+    key = id(group)
+    if key not in _COMMS:
+        _COMMS[key] = Comm(group)
+    return _COMMS[key]
+
+
 def attach(policy, process_group, global_rows, broadcast=True):
     """Make `policy` (pvr_habitat_b200.models.PolicyNet) synchronise BatchNorm sums and gradients over the group.
     Parameters and buffers are broadcast from the group's first rank, so the replicas start identical whatever the
     seeds of the ranks were."""
     group = resolve_group(process_group)
     policy.process_group = group
+    policy.comm = comm_for(group) if group is not None else None
     policy.global_rows = global_rows if group is not None else None
     if group is not None and broadcast:
-        src = torch.distributed.get_global_rank(group, 0)
         with torch.no_grad():
             for t in list(policy.parameters()) + list(policy.buffers()):
-                torch.distributed.broadcast(t.data, src=src, group=group)
+                if t.is_floating_point() or t.dtype == torch.int64:
+                    policy.comm.broadcast(t.data, 0)
     return policy
 
 

@@ -72,7 +72,7 @@ def test_product_code_never_imports_the_oracle():
     for m in pat.finditer(src):
         func = src[:m.start()].rsplit("\ndef ", 1)[1].split("(", 1)[0]
         assert func in ("oracle_parts", "oracle_embed", "cpu_port_frames_per_s", "cpu_port_bc_steps_per_s",
-                        "run_reference"), func
+                        "cpu_port_finetune_steps_per_s", "run_reference"), func
 
 
 def test_bench_clock_sampler_counts_only_samples_of_the_timed_region():

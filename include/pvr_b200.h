@@ -52,6 +52,11 @@ int pvr_abi_version(void);
 #define PVR_FMT_NHWC4_BF16 1
 #define PVR_FMT_STEM_BF16 2
 #define PVR_FMT_NHWC4_F32 3 /* (n*N, crop, crop, 4) float32, RGB + zero pad: input of the fp32 parity mode */
+/* (n*N, crop, crop + 8, 4) bf16: NHWC4 rows with 3 zero pixels before column 0 and 5 after the last one (row pitch
+ * (crop + 8) * 8 bytes). The 7x7/2 stem reads it through a tensor map whose pixel dimension advances by TWO pixels
+ * (16 bytes) while each "pixel" spans 8 columns x 4 channels (64 bytes): the W-expansion of PVR_FMT_STEM_BF16 happens
+ * in the TMA addressing instead of in HBM — 0.42 MB per frame instead of 1.6 MB written here and read by the stem. */
+#define PVR_FMT_STEM_PAD_BF16 4
 /* OR-ed into out_fmt: Resize is bicubic (A = -0.75, no antialias, clamped to [0, 255] before the rounding cast) instead
  * of bilinear — T.Resize(256, interpolation=3) of the MAE encoders, src/embeddings.py:81. */
 #define PVR_RESIZE_BICUBIC 0x100
@@ -296,6 +301,21 @@ int pvr_transpose_bf16(const void* in, int64_t ldi, int rows, int cols, void* ou
 /* fp32 weight (rows x cols) -> bf16 copy and/or bf16 transposed copy (either may be NULL). */
 int pvr_cast_weight(const float* w, int rows, int cols, void* w_bf16, int64_t ldb, void* wt_bf16, int64_t ldt,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * fp32 parity mode of the ViT encoders (csrc/vit_f32.cu; CLIP `encode_image`, src/embeddings.py:375-376, and the MAE
+ * encoders, :377-379): float32 end to end on the CUDA cores — the north star's "<= 1e-5 in the fp32 mode". LayerNorm
+ * is pvr_layernorm_f32 above. Not a performance path.
+ */
+/* out (M x N) = act(a (M x K) w^T (N x K) + bias (+ res)), float32, w dense; act 0 none / 2 QuickGELU / 3 erf GELU;
+ * `res` may alias `out`. Blocked summation (16-deep slices summed on their own). */
+int pvr_gemm_f32(const float* a, int64_t lda, const float* w, const float* bias, const float* res, int64_t ldr,
+                 float* out, int64_t ldo, int64_t M, int N, int K, int act, void* stream);
+/* x = [cls | patches] + pos, LayerNorm'ed when gamma / beta are given (CLIP ln_pre); patches float32 (n*(tokens-1), W). */
+int pvr_vit_embed_f32(const float* patches, const float* cls, const float* pos, int n_img, int tokens, int width,
+                      const float* gamma, const float* beta, float eps, float* x_out, void* stream);
+/* softmax(q k^T / 8) v per (image, head), head_dim 64; qkv float32 (n*tokens, 3*width) -> out (n*tokens, width). */
+int pvr_attention_f32(const float* qkv, int n_img, int tokens, int width, int heads, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Data-parallel collectives (K12). The reference is single process (no DDP / NCCL

@@ -9,6 +9,7 @@ PVR_FMT_NCHW_F32 = 0
 PVR_FMT_NHWC4_BF16 = 1
 PVR_FMT_STEM_BF16 = 2
 PVR_FMT_NHWC4_F32 = 3
+PVR_FMT_STEM_PAD_BF16 = 4
 PVR_RESIZE_BICUBIC = 0x100
 PVR_COMM_F32, PVR_COMM_F64, PVR_COMM_BF16, PVR_COMM_I64 = 0, 1, 2, 3
 PVR_OP_FP32 = 2
@@ -115,6 +116,9 @@ _SIGNATURES = {
     "pvr_optim_step_dev": (ctypes.c_int, [_i, ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp),
                                           ctypes.POINTER(_vp), ctypes.POINTER(_i64), _i, _vp, _f, _f, _vp, _f, _f, _f, _i,
                                           _vp, _vp]),
+    "pvr_gemm_f32": (ctypes.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp]),
+    "pvr_vit_embed_f32": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp]),
+    "pvr_attention_f32": (ctypes.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "pvr_comm_load": (ctypes.c_int, [ctypes.c_char_p]),
     "pvr_comm_version": (ctypes.c_int, []),
     "pvr_comm_unique_id": (ctypes.c_int, [_vp]),

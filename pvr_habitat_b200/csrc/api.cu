@@ -216,7 +216,8 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
       continue;
     }
     if (o.c_in == 32 && o.r == 7 && o.s == 1 && o.stride_h == 2 && o.stride_w == 1 && o.lower_h == -3 &&
-        o.lower_w == 0 && o.c_out == 64 && o.n_pad == 64 && o.in_pitch == 32 && o.out_pitch == 64 && o.out_coff == 0 &&
+        o.lower_w == 0 && o.c_out == 64 && o.n_pad == 64 && (o.in_pitch == 32 || o.in_pitch == 8) && o.out_pitch == 64 &&
+        o.out_coff == 0 &&
         o.w_in == o.w_out && o.h_in == 2 * o.h_out && o.w_out % 8 == 0 && o.res_slot < 0 && o.act == 0 &&
         (o.relu_n == 0 || o.relu_n >= 64) && o.k_pad == 256 && o.block_n == 0) {
       // ResNet stem over the W-expanded input: patch-resident row taps (conv3x3_patch.cu, STEM)
@@ -242,7 +243,11 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
           slot_rev[mp.out_slot] = reverse;
         }
       }
-      if (!pvr::make_tmap_4d(&b.ta, enc->slot_ptr[o.in_slot], 32, 32, o.w_in, o.h_in, n_images, 8, 37, &err, 2) ||
+      // in_pitch 32: W-expanded input (PVR_FMT_STEM_BF16); in_pitch 8: compact padded rows, expanded by the tensor map
+      const bool a_ok = o.in_pitch == 8
+          ? pvr::make_tmap_stem_compact(&b.ta, enc->slot_ptr[o.in_slot], o.w_in, o.h_in, n_images, 8, 37, 2, &err)
+          : pvr::make_tmap_4d(&b.ta, enc->slot_ptr[o.in_slot], 32, 32, o.w_in, o.h_in, n_images, 8, 37, &err, 2);
+      if (!a_ok ||
           !pvr::make_tmap_2d_sw64(&b.tb, o.weight, 256, 64, 256, 64, &err) ||
           !pvr::make_tmap_4d(&b.to, enc->slot_ptr[o.out_slot], 64, 64, o.w_out, o.h_out, n_images, 8, 16, &err)) {
         pvr_set_error("pvr_encoder_bind: op %zu: stem patch tensor maps: %s", i, err);

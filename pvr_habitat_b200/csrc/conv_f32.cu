@@ -84,7 +84,9 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(ConvF32Params p) {
       float v = fmaf(acc[i][j], p.scale[co], p.bias[co]);
       if (p.res) v += p.res[m * p.res_pitch + p.res_coff + co];
       if (co < p.relu_n) v = fmaxf(v, 0.f);
-      if (p.elu) v = v > 0.f ? v : expm1f(v);
+      if (p.elu == 1) v = v > 0.f ? v : expm1f(v);
+      else if (p.elu == 2) v = v / (1.f + expf(-1.702f * v));               // QuickGELU (CLIP MLP)
+      else if (p.elu == 3) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752f));  // erf GELU (timm / MAE MLP)
       p.out[m * p.out_pitch + p.out_coff + co] = v;
     }
   }

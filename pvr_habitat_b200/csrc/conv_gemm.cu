@@ -889,6 +889,25 @@ bool make_tmap_4d(CUtensorMap* out, const void* base, int c, int pitch, int w, i
   return true;
 }
 
+// Stem input in the compact padded layout (PVR_FMT_STEM_PAD_BF16): rows of (2 w_out + 8) NHWC4 pixels. Dimension 1
+// (output column q) advances by 16 bytes = two pixels while the innermost dimension spans 32 elements = 8 columns x
+// 4 channels: overlapping 64-byte windows, the W-expansion done by the TMA addressing.
+bool make_tmap_stem_compact(CUtensorMap* out, const void* base, int w_out, int h_in, int n, int box_w, int box_h,
+                            int stride_h, const char** err) {
+  static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
+  if (!fn) { *err = "cuTensorMapEncodeTiled not available"; return false; }
+  const cuuint64_t row_bytes = (cuuint64_t)(2 * w_out + 8) * 8;
+  cuuint64_t dims[4] = {32, (cuuint64_t)w_out, (cuuint64_t)h_in, (cuuint64_t)n};
+  cuuint64_t strides[3] = {16, row_bytes, row_bytes * h_in};
+  cuuint32_t box[4] = {32, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, (cuuint32_t)stride_h, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled (compact stem input) failed"; return false; }
+  return true;
+}
+
 bool make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t ld,
                       uint32_t box_rows, const char** err) {
   static EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));

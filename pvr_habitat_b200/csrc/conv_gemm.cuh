@@ -76,6 +76,9 @@ bool make_tmap_2d_sw64(CUtensorMap* out, const void* base, uint64_t k, uint64_t 
 // 128B swizzle (patch-resident 3x3 convolution, conv3x3_patch.cu).
 bool make_tmap_4d(CUtensorMap* out, const void* base, int c, int pitch, int w, int h, int n, int box_w, int box_h,
                   const char** err, int stride_h = 1);
+// Stem input in the compact padded layout (PVR_FMT_STEM_PAD_BF16): overlapping 64-byte windows, 16 bytes apart.
+bool make_tmap_stem_compact(CUtensorMap* out, const void* base, int w_out, int h_in, int n, int box_w, int box_h,
+                            int stride_h, const char** err);
 // 3x3 / stride 1 / pad 1 convolution, C_in = C_out = 64, W % 8 == 0, with the input patch resident in shared memory
 // (three column-shifted copies; the nine taps are UMMA descriptor offsets) and the weights resident for the whole
 // kernel. Same epilogue contract as conv_gemm (scale/bias/ReLU, bf16 NHWC out).

@@ -28,7 +28,8 @@ struct ConvF32Params {
   float* out;          // (M, out_pitch), channel offset out_coff
   long long M;         // n_images * P * Q
   int N, C, H, W, P, Q, R, S, stride_h, stride_w, lower_h, lower_w;
-  int in_pitch, out_pitch, out_coff, res_pitch, res_coff, relu_n, elu;
+  int in_pitch, out_pitch, out_coff, res_pitch, res_coff, relu_n;
+  int elu;             // activation after bias / residual: 0 none, 1 ELU, 2 QuickGELU, 3 erf GELU
 };
 cudaError_t launch_conv_f32(const ConvF32Params& p, cudaStream_t stream);
 cudaError_t launch_maxpool_f32(const float* in, float* out, int n_img, int H, int W, int C, int P, int Q,

@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
   const uint8_t* s = stage + head;
   const int npix = y_count * p.crop;
   const long long plane = (long long)p.crop * p.crop;
-  if (p.fmt == PVR_FMT_STEM_BF16) {
+  if (p.fmt == PVR_FMT_STEM_BF16 || p.fmt == PVR_FMT_STEM_PAD_BF16) {
     // W-expanded stem input: out[image][y][q][8 columns 2q-3..2q+4][4 ch] bf16 (64 B per output column of the 7x7/2
     // stem), so that the stem conv is a 7x1-tap implicit GEMM with 64-byte TMA rows. Pixels are first written to a
     // zero-margined bf16 row buffer in smem, then copied out 16 B per thread, fully coalesced.
@@ -193,6 +193,20 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
       }
       __syncthreads();
       const long long image = p.sample_major ? (long long)img * p.nf + f : (long long)f * p.N + img;
+      if (p.fmt == PVR_FMT_STEM_PAD_BF16) {
+        // compact variant: the padded NHWC4 row itself (buffer pixel j = column j - 3 = row-buffer entry j + 1),
+        // 16 B (two pixels) per thread; the stem's tensor map does the W-expansion (include/pvr_b200.h)
+        const int R = prow >> 1;  // uint4 per row
+        uint4* dst = reinterpret_cast<uint4*>(p.out) + (image * p.crop + y_first) * (long long)R;
+        for (int t = threadIdx.x; t < y_count * R; t += blockDim.x) {
+          const int yy = t / R, k = t - yy * R;
+          const uint2 e0 = pix[yy * prow + 2 * k + 1];
+          const uint2 e1 = 2 * k + 2 < prow ? pix[yy * prow + 2 * k + 2] : make_uint2(0u, 0u);
+          dst[t] = make_uint4(e0.x, e0.y, e1.x, e1.y);
+        }
+        __syncthreads();
+        continue;
+      }
       uint4* dst = reinterpret_cast<uint4*>(p.out) + (image * p.crop + y_first) * (long long)Q * 4;
       for (int t = threadIdx.x; t < y_count * Q * 4; t += blockDim.x) {
         const int yy = t / (Q * 4);
@@ -274,8 +288,8 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   if (!in || !out || N <= 0 || H <= 0 || W <= 0 || n_frames <= 0 || rh <= 0 || rw <= 0 || crop <= 0 || top < 0 ||
       left < 0 || top + crop > rh || left + crop > rw || !mean || !stdv ||
       (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16 && out_fmt != PVR_FMT_STEM_BF16 &&
-       out_fmt != PVR_FMT_NHWC4_F32) ||
-      (out_fmt == PVR_FMT_STEM_BF16 && (crop & 1))) {
+       out_fmt != PVR_FMT_NHWC4_F32 && out_fmt != PVR_FMT_STEM_PAD_BF16) ||
+      ((out_fmt == PVR_FMT_STEM_BF16 || out_fmt == PVR_FMT_STEM_PAD_BF16) && (crop & 1))) {
     pvr_set_error("pvr_preprocess_u8: invalid argument");
     return PVR_ERR_ARG;
   }
@@ -301,7 +315,7 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   while (rows > 1 && stage_bytes(rows) > 48 * 1024) rows >>= 1;
   long long smem = 16 + 3072 + stage_bytes(rows);
   p.pix_off = 0;
-  if (out_fmt == PVR_FMT_STEM_BF16) {
+  if (out_fmt == PVR_FMT_STEM_BF16 || out_fmt == PVR_FMT_STEM_PAD_BF16) {
     p.pix_off = (int)((smem + 15) & ~15ll);
     smem = p.pix_off + (long long)rows * (crop + 8) * 8;
   }

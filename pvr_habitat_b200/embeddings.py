@@ -55,7 +55,8 @@ class Transforms(nn.Module):
         """HBM bytes one frame costs in output format `fmt` (uint8 frame read + formatted frame written)."""
         c = self.crop
         out = {_lib.PVR_FMT_NCHW_F32: 3 * c * c * 4, _lib.PVR_FMT_NHWC4_BF16: c * c * 4 * 2,
-               _lib.PVR_FMT_STEM_BF16: c * (c // 2) * 32 * 2, _lib.PVR_FMT_NHWC4_F32: c * c * 4 * 4}[fmt & 0xff]
+               _lib.PVR_FMT_STEM_BF16: c * (c // 2) * 32 * 2, _lib.PVR_FMT_NHWC4_F32: c * c * 4 * 4,
+               _lib.PVR_FMT_STEM_PAD_BF16: c * (c + 8) * 4 * 2}[fmt & 0xff]
         return h * w * 3 + out
 
     def run(self, obs_nhwc_u8, n_frames, out_ptr, fmt, sample_major):
@@ -271,18 +272,22 @@ def build_encoder(model, device, hw=224, precision='bf16'):
         enc = prog.finish(device)
         enc.input_format = _lib.PVR_FMT_NHWC4_BF16
         return enc
-    in_slot = prog.new_slot(hw * (hw // 2) * 32)  # slot 0: W-expanded bf16 frames from the preprocessing kernel
+    # slot 0: the stem's input from the preprocessing kernel. Default: padded NHWC4 rows (PVR_FMT_STEM_PAD_BF16,
+    # (hw + 8) * 4 elements per row) that the stem's tensor map expands into its 8-column windows; PVR_STEM_EXPANDED=1
+    # (A/B switch) or a frame size the patch-resident stem does not take: the materialised W-expanded layout.
+    compact = hw % 32 == 0 and os.environ.get("PVR_STEM_EXPANDED") != "1"
+    in_slot = prog.new_slot(hw * (hw + 8) * 4 if compact else hw * (hw // 2) * 32)
     parts = model.models if isinstance(model, UberModel) else [model]
     off = 0
     for m in parts:
         sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
         if isinstance(m, ResNetBasicParams):
-            off += prg.add_resnet_basic(prog, sd, m.LAYERS[m.name], in_slot, off, hw)
+            off += prg.add_resnet_basic(prog, sd, m.LAYERS[m.name], in_slot, off, hw, compact_stem=compact)
         else:
-            off += prg.add_resnet50(prog, sd, m.variant, in_slot, off, hw)
+            off += prg.add_resnet50(prog, sd, m.variant, in_slot, off, hw, compact_stem=compact)
     prog.emb_width = off
     enc = prog.finish(device)
-    enc.input_format = _lib.PVR_FMT_STEM_BF16
+    enc.input_format = _lib.PVR_FMT_STEM_PAD_BF16 if compact else _lib.PVR_FMT_STEM_BF16
     return enc
 
 
@@ -313,12 +318,10 @@ class EmbeddingNet(nn.Module):
         self.precision = 'bf16'
 
     def set_precision(self, precision):
-        """'bf16' (default, tensor cores) or 'fp32' (parity mode: float32 end to end on the CUDA cores; ResNet and
-        small-conv encoders). The constructor signature stays the reference's, hence a setter."""
+        """'bf16' (default, tensor cores) or 'fp32' (parity mode: float32 end to end on the CUDA cores, every encoder:
+        ResNets, small conv, CLIP / MAE ViTs). The constructor signature stays the reference's, hence a setter."""
         if precision not in ('bf16', 'fp32'):
             raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
-        if precision == 'fp32' and isinstance(self.embedding, (clip_vit.CLIPImageModel, mae_vit.MAEParams)):
-            raise NotImplementedError("the fp32 parity mode covers the ResNet / small-conv encoders, not the ViTs")
         if precision != self.precision:
             self.precision = precision
             self._encoder = None
@@ -354,7 +357,7 @@ class EmbeddingNet(nn.Module):
         if self._encoder is None:
             if isinstance(self.embedding, (clip_vit.CLIPImageModel, mae_vit.MAEParams)):
                 self.embedding.invalidate()
-                self._encoder = self.embedding.runner(self.device)
+                self._encoder = self.embedding.runner(self.device, self.precision)
             else:
                 self._encoder = build_encoder(self.embedding, self.device, self.transforms.crop, self.precision)
         return self._encoder

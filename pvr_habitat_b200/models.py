@@ -620,21 +620,33 @@ class PolicyNetWithConv(PolicyNet):
                 sizes.append(hw)
             st["sizes"] = sizes
             st["tf"] = Transforms([0.0, 0.0, 0.0], [1.0, 1.0, 1.0], size=H, crop=H)  # x / 255 only
-        # weights change every step: rebuild the (tiny) program with the current values, keeping every activation
-        sd = {}
-        for i in (0, 2, 4, 6, 8):
-            sd[f"{i}.weight"] = self.feat_extract[i].weight.detach().float().cpu().transpose(2, 3).contiguous()
-            sd[f"{i}.bias"] = self.feat_extract[i].bias.detach().float().cpu()
-        prog = prg.Program()
-        in_slot = prog.new_slot(H * H * 4)
-        prog.emb_width = prg.add_small_conv(prog, sd, in_slot, 0, hw=H, keep_activations=True)
-        enc = prog.finish(dev)
-        enc.bind(F)
-        st["enc"], st["slots"] = enc, [in_slot] + prog.kept_slots
+        # The (tiny) program is compiled once per batch shape with every activation kept for the backward. The weights
+        # change every step: their packed bf16 copies are rewritten in place ON THE DEVICE (no host round trip, no
+        # synchronisation), H and W swapped instead of transposing the frames (src/models.py:169).
+        if "enc" not in st:
+            sd = {}
+            for i in (0, 2, 4, 6, 8):
+                sd[f"{i}.weight"] = self.feat_extract[i].weight.detach().float().cpu().transpose(2, 3).contiguous()
+                sd[f"{i}.bias"] = self.feat_extract[i].bias.detach().float().cpu()
+            prog = prg.Program()
+            in_slot = prog.new_slot(H * H * 4)
+            prog.emb_width = prg.add_small_conv(prog, sd, in_slot, 0, hw=H, keep_activations=True)
+            enc = prog.finish(dev)
+            enc.bind(F)
+            st["enc"], st["slots"], st["emb_width"] = enc, [in_slot] + prog.kept_slots, prog.emb_width
+            st["conv_ops"] = [i for i, m in enumerate(enc.op_meta) if m["kind"] == 1]
+        enc = st["enc"]
+        with torch.no_grad():
+            for j, (i, op) in enumerate(zip((0, 2, 4, 6, 8), st["conv_ops"])):
+                w = self.feat_extract[i].weight.detach().float().transpose(2, 3)
+                packed = prg.pack_first_small_conv(w, 32) if j == 0 else prg.pack_small_conv(w, 32)
+                t = enc.op_tensors[op]
+                t["weight"][:packed.shape[0]].copy_(packed)
+                t["bias"][:32].copy_(self.feat_extract[i].bias.detach().float())
         st["tf"].run(obs_u8, N, enc.slot0, _lib.PVR_FMT_NHWC4_BF16, True)
         if st.get("emb") is None or st["emb"].shape[0] != F:
-            st["emb"] = torch.empty(F, prog.emb_width, dtype=torch.float32, device=dev)
-        enc.forward(st["emb"], prog.emb_width)
+            st["emb"] = torch.empty(F, st["emb_width"], dtype=torch.float32, device=dev)
+        enc.forward(st["emb"], st["emb_width"])
         hc = self.conv_hw
         feat = torch.empty(TB, 32 * hc * hc * N, dtype=torch.float32, device=dev)
         _lib.check(lib.pvr_convfeat_gather(enc.slot_ptr(st["slots"][5]), 32, TB, N, hc, hc, 32, feat.data_ptr(),

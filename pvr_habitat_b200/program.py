@@ -185,6 +185,15 @@ class Encoder:
         self.workspace = None
         self.slot0 = None
         self.op_meta = [{k: v for k, v in d.items() if not k.startswith("_")} for d in prog.ops]
+        # device tensors of every op, by op index: lets a training loop overwrite packed weights / biases in place
+        self.op_tensors, k = [], 0
+        for d in prog.ops:
+            ent = {}
+            for key in ("_weight", "_scale", "_bias", "_aux"):
+                if key in d:
+                    ent[key[1:]] = self._keep[k]
+                    k += 1
+            self.op_tensors.append(ent)
 
     def bind(self, n_images):
         if n_images == self.n_images:
@@ -335,7 +344,7 @@ def _compress_head(prog, sd, prefix, x_slot, x_chw, emb_offset):
     return c * h * w
 
 
-def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
+def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224, compact_stem=False):
     """Append one ResNet-50 trunk reading the W-expanded bf16 frames (PVR_FMT_STEM_BF16) in `in_slot`.
 
     variant: 'conv5' (moco_conv5 / resnet50: avg-pooled 2048), 'l4' (moco_conv4_compressed: 42*7*7 = 2058),
@@ -345,8 +354,11 @@ def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
     # stem: 7x7/2 as a 7x1-tap conv over the W-expanded input (see pack_stem_weight)
     scale, bias = fold_bn(sd, "bn1")
     p = (hw + 6 - 7) // 2 + 1
+    # compact_stem: `in_slot` holds padded NHWC4 rows (PVR_FMT_STEM_PAD_BF16); the 8-column windows are formed by the
+    # stem's tensor map (pixel pitch 8 elements = 2 columns) instead of being materialised (pixel pitch 32)
     stem = prog.conv(in_slot, (32, hw, hw // 2), pack_stem_weight(sd["conv1.weight"].float(), 64), 256, 64, 7, 1,
-                     (2, 1), (-3, 0), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147)
+                     (2, 1), (-3, 0), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147,
+                     in_pitch=8 if compact_stem else None)
     x, h, w = prog.maxpool(stem, 64, p, p)
     prog.release(stem)
     chw = (64, h, w)
@@ -370,13 +382,16 @@ def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224):
     return n
 
 
-def add_resnet_basic(prog, sd, layers, in_slot, emb_offset, hw=224):
+def add_resnet_basic(prog, sd, layers, in_slot, emb_offset, hw=224, compact_stem=False):
     """Append a BasicBlock ResNet (resnet18: layers (2,2,2,2); resnet34: (3,4,6,3); tv:models/resnet.py:59-101) with
     fc = Identity (src/embeddings.py:112-117), reading the W-expanded frames in `in_slot`. Writes 512 columns."""
     scale, bias = fold_bn(sd, "bn1")
     p = (hw + 6 - 7) // 2 + 1
+    # compact_stem: `in_slot` holds padded NHWC4 rows (PVR_FMT_STEM_PAD_BF16); the 8-column windows are formed by the
+    # stem's tensor map (pixel pitch 8 elements = 2 columns) instead of being materialised (pixel pitch 32)
     stem = prog.conv(in_slot, (32, hw, hw // 2), pack_stem_weight(sd["conv1.weight"].float(), 64), 256, 64, 7, 1,
-                     (2, 1), (-3, 0), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147)
+                     (2, 1), (-3, 0), (p, p), scale, bias, 64, flops=2 * p * p * 64 * 147,
+                     in_pitch=8 if compact_stem else None)
     x, h, w = prog.maxpool(stem, 64, p, p)
     prog.release(stem)
     chw = (64, h, w)
@@ -532,20 +547,18 @@ def pack_first_small_conv(w, n_pad):
     K index = (r*2 + sp)*8 + e*4 + c with filter column j = 2*sp + e - 1."""
     co, ci, r, s = w.shape
     assert (ci, r, s) == (3, 3, 3)
-    out = torch.zeros(n_pad, 8, 2, 4, dtype=torch.float32)  # (co, tap, e, c); taps 6, 7 are padding
-    for rr in range(3):
-        for sp in range(2):
-            for e in range(2):
-                j = 2 * sp + e - 1
-                if 0 <= j < 3:
-                    out[:co, rr * 2 + sp, e, :3] = w[:, :, rr, j]
+    # (co, r (4: the last is padding), sp, e, c); tap = r*2 + sp. Works on any device (the finetuning path repacks
+    # the weights on the GPU every step, without a host round trip).
+    out = torch.zeros(n_pad, 4, 2, 2, 4, dtype=torch.float32, device=w.device)
+    for (sp, e), j in (((0, 1), 0), ((1, 0), 1), ((1, 1), 2)):
+        out[:co, :3, sp, e, :3] = w[:, :, :, j].permute(0, 2, 1)
     return out.reshape(n_pad, 64).to(torch.bfloat16)
 
 
 def pack_small_conv(w, n_pad):
     """(32, 32, 3, 3) -> bf16 (n_pad, 320): K = (r, s, c) over 9 taps of 32 channels, padded to 10 taps."""
     co, ci, r, s = w.shape
-    out = torch.zeros(n_pad, 10, ci, dtype=torch.float32)
+    out = torch.zeros(n_pad, 10, ci, dtype=torch.float32, device=w.device)
     out[:co, :9] = w.permute(0, 2, 3, 1).reshape(co, 9, ci)
     return out.reshape(n_pad, 10 * ci).to(torch.bfloat16)
 

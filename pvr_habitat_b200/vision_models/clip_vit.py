@@ -103,9 +103,10 @@ class CLIPImageModel(nn.Module):
     def invalidate(self):
         self._runner = None
 
-    def runner(self, device):
-        if self._runner is None or self._runner.device != torch.device(device):
-            self._runner = ViTRunner(self.visual, device)
+    def runner(self, device, precision='bf16'):
+        cls = ViTRunnerF32 if precision == 'fp32' else ViTRunner
+        if type(self._runner) is not cls or self._runner.device != torch.device(device):
+            self._runner = cls(self.visual, device)
         return self._runner
 
 
@@ -129,12 +130,12 @@ def load(name, device="cpu", checkpoint_path=None):
     return model.to(device), None
 
 
-def pack_patch_weight(w):
-    """(width, 3, p, p) -> bf16 (width, p * p * 4): K ordered (patch row, pixel, channel padded to 4)."""
+def pack_patch_weight(w, dtype=torch.bfloat16):
+    """(width, 3, p, p) -> (width, p * p * 4): K ordered (patch row, pixel, channel padded to 4)."""
     co, ci, p, _ = w.shape
     out = torch.zeros(co, p, p, 4, dtype=torch.float32)
     out[..., :3] = w.permute(0, 2, 3, 1)
-    return out.reshape(co, p * p * 4).to(torch.bfloat16)
+    return out.reshape(co, p * p * 4).to(dtype)
 
 
 def clip_spec(vis):
@@ -260,3 +261,108 @@ class ViTRunner:
             d.out, d.ldo = out.data_ptr(), ld
             d.m, d.n, d.n_pad, d.k, d.out_f32, d.split_k = n, self.O, self.O, W, 1, 1
             _lib.check(lib.pvr_gemm(ctypes.byref(d), st()), "pvr_gemm")
+
+
+class ViTRunnerF32:
+    """fp32 parity mode of ViTRunner (north star: embeddings within 1e-5 relative L2 "in the fp32 mode"): the same
+    launch sequence with float32 weights, activations and accumulation on the CUDA cores (csrc/vit_f32.cu, conv_f32.cu).
+    Frames arrive as PVR_FMT_NHWC4_F32. A checking mode, not a performance path."""
+
+    def __init__(self, spec, device):
+        if not isinstance(spec, dict):
+            spec = clip_spec(spec)
+        self.device = torch.device(device)
+        self.lib = _lib.lib()
+        self.input_format = _lib.PVR_FMT_NHWC4_F32
+        self.p, self.W, self.heads = spec["patch"], spec["width"], spec["heads"]
+        self.L = len(spec["blocks"])
+        self.res = spec["resolution"]
+        self.eps, self.act = float(spec["eps"]), int(spec["act"])
+        self.grid = self.res // self.p
+        self.S = self.grid * self.grid + 1
+        dev = self.device
+        f = lambda t: t.detach().to(dev, torch.float32).contiguous()  # noqa: E731
+        prog = prg.Program()
+        cpp = self.p * 4
+        self.in_slot = prog.new_slot(self.p * self.grid * cpp * 2)  # float32 values: two bf16 elements each
+        pbias = spec["patch_bias"]
+        pbias = torch.zeros(self.W) if pbias is None else pbias.detach().cpu().float()
+        self.patch_slot = prog.alloc(self.grid * self.W * 2)
+        prog.conv(self.in_slot, (cpp, self.p, self.grid),
+                  pack_patch_weight(spec["patch_weight"].detach().cpu().float(), torch.float32), self.p * cpp, self.W,
+                  self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), pbias, 0, out_slot=self.patch_slot,
+                  out_pitch=self.W, flags=prg.F32)
+        prog.emb_width = 1
+        self.patch_enc = prog.finish(dev)
+        self.cls, self.pos = f(spec["cls"].reshape(-1)), f(spec["pos"].reshape(self.S, self.W))
+        self.ln_pre = tuple(f(t) for t in spec["ln_pre"]) if spec["ln_pre"] is not None else None
+        self.ln_post = tuple(f(t) for t in spec["ln_post"])
+        self.blocks = [{k: (tuple(f(t) for t in v) if isinstance(v, tuple) else f(v)) for k, v in blk.items()}
+                       for blk in spec["blocks"]]
+        self.proj_t = f(spec["proj"].t()) if spec["proj"] is not None else None
+        self.O = self.proj_t.shape[0] if self.proj_t is not None else self.W
+        self.zero_bias = torch.zeros(max(self.O, 1), device=dev)
+        self.n = 0
+        self.flops_per_image = 0
+
+    def bind(self, n):
+        if n == self.n:
+            return
+        dev, M, W = self.device, n * self.S, self.W
+        self.patch_enc.bind(n * self.grid)
+        f32 = torch.float32
+        self.x = torch.empty(M, W, dtype=f32, device=dev)
+        self.y = torch.empty(M, W, dtype=f32, device=dev)
+        self.qkv = torch.empty(M, 3 * W, dtype=f32, device=dev)
+        self.att = torch.empty(M, W, dtype=f32, device=dev)
+        self.h = torch.empty(M, 4 * W, dtype=f32, device=dev)
+        self.clsy = torch.empty(n, W, dtype=f32, device=dev)
+        self.dummy = torch.zeros(n * self.grid, 1, device=dev)
+        self.n = n
+
+    @property
+    def slot0(self):
+        return self.patch_enc.slot0
+
+    def launches_per_forward(self):
+        return 2 + 7 * self.L + 2
+
+    def _gemm(self, a, w, bias, out, M, N, K, res=None, act=0):
+        _lib.check(self.lib.pvr_gemm_f32(a.data_ptr(), a.stride(0), w.data_ptr(), bias.data_ptr(),
+                                         res.data_ptr() if res is not None else None,
+                                         res.stride(0) if res is not None else 0, out.data_ptr(), out.stride(0), M, N, K,
+                                         act, _lib.current_stream_ptr()), "pvr_gemm_f32")
+
+    def _ln(self, x, row_step, rows, gb, out):
+        _lib.check(self.lib.pvr_layernorm_f32(x.data_ptr(), row_step, rows, self.W, gb[0].data_ptr(), gb[1].data_ptr(),
+                                              self.eps, out.data_ptr(), self.W, _lib.current_stream_ptr()),
+                   "pvr_layernorm_f32")
+
+    def forward(self, out, out_ld=None):
+        lib, n, S, W, M = self.lib, self.n, self.S, self.W, self.n * self.S
+        ld = out_ld if out_ld is not None else out.stride(0)
+        with torch.cuda.device(self.device):
+            self.patch_enc.forward(self.dummy, 1)
+            patches = self.patch_enc.slot_ptr(self.patch_slot)
+            g, bta = (self.ln_pre[0].data_ptr(), self.ln_pre[1].data_ptr()) if self.ln_pre is not None else (None, None)
+            _lib.check(lib.pvr_vit_embed_f32(patches, self.cls.data_ptr(), self.pos.data_ptr(), n, S, W, g, bta,
+                                             self.eps, self.x.data_ptr(), _lib.current_stream_ptr()),
+                       "pvr_vit_embed_f32")
+            for blk in self.blocks:
+                self._ln(self.x, 1, M, blk["ln1"], self.y)
+                self._gemm(self.y, blk["wqkv"], blk["bqkv"], self.qkv, M, 3 * W, W)
+                _lib.check(lib.pvr_attention_f32(self.qkv.data_ptr(), n, S, W, self.heads, self.att.data_ptr(),
+                                                 _lib.current_stream_ptr()), "pvr_attention_f32")
+                self._gemm(self.att, blk["wo"], blk["bo"], self.x, M, W, W, res=self.x)
+                self._ln(self.x, 1, M, blk["ln2"], self.y)
+                self._gemm(self.y, blk["w1"], blk["b1"], self.h, M, 4 * W, W, act=self.act)
+                self._gemm(self.h, blk["w2"], blk["b2"], self.x, M, W, 4 * W, res=self.x)
+            if self.proj_t is None:  # MAE: the normalised class token is the embedding
+                if ld != W:
+                    raise _lib.PvrError("ViTRunnerF32: the embedding rows must be dense (ld == width)")
+                self._ln(self.x, S, n, self.ln_post, out)
+                return
+            self._ln(self.x, S, n, self.ln_post, self.clsy)
+            _lib.check(lib.pvr_gemm_f32(self.clsy.data_ptr(), W, self.proj_t.data_ptr(), self.zero_bias.data_ptr(), None,
+                                        0, out.data_ptr(), ld, n, self.O, W, 0, _lib.current_stream_ptr()),
+                       "pvr_gemm_f32")

@@ -22,7 +22,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from .clip_vit import ViTRunner
+from .clip_vit import ViTRunner, ViTRunnerF32
 from .moco import _ALLOW_RANDOM_INIT
 
 _CONFIGS = {  # mae.py:275-298
@@ -124,9 +124,10 @@ class MAEParams(nn.Module):
     def invalidate(self):
         self._runner = None
 
-    def runner(self, device):
-        if self._runner is None or self._runner.device != torch.device(device):
-            self._runner = ViTRunner(mae_spec(self), device)
+    def runner(self, device, precision='bf16'):
+        cls = ViTRunnerF32 if precision == 'fp32' else ViTRunner
+        if type(self._runner) is not cls or self._runner.device != torch.device(device):
+            self._runner = cls(mae_spec(self), device)
         return self._runner
 
 

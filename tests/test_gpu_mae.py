@@ -143,6 +143,19 @@ def test_mae_embedding_vs_reference_golden(gold, name):
         print(f"{name} {tag}: rel-L2 {r:.2e}")
 
 
+@pytest.mark.parametrize("name", ["mae_base", "mae_large"])
+def test_mae_embedding_fp32_mode_vs_reference_golden(gold, name):
+    """North star: embeddings within relative L2 <= 1e-5 "in the fp32 mode" (net.set_precision('fp32'): float32
+    weights, activations and accumulation on the CUDA cores, csrc/vit_f32.cu)."""
+    net = make_net(name, int(gold[f"seed_{name}"])).set_precision('fp32')
+    for tag in ("64", "224"):
+        got = net(torch.from_numpy(gold["frames" + tag])).astype(np.float64)
+        ref = gold[f"emb{tag}_{name}"].astype(np.float64)
+        r = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        print(f"{name} {tag} fp32 mode: rel-L2 {r:.2e}")
+        assert r <= 1e-5, r
+
+
 def test_mae_two_frame_observation_and_batch_independence(gold):
     net = make_net("mae_base", int(gold["seed_mae_base"]))
     obs = restate.structured_frames(5, 64, 64, 6, 61)

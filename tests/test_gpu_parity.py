@@ -95,6 +95,32 @@ def test_preprocess_stem_layout_sample_major():
     assert torch.equal(out.cpu(), expand_stem_input(ref4))
 
 
+def test_preprocess_compact_stem_layout_and_bitwise_equal_embeddings(emb, monkeypatch):
+    """PVR_FMT_STEM_PAD_BF16: padded NHWC4 rows (3 zero pixels before column 0, 5 after the last), which the stem's
+    tensor map expands into the 8-column windows of PVR_FMT_STEM_BF16 (overlapping 64-byte boxes 16 bytes apart).
+    (1) the layout, (2) embeddings bitwise equal to the ones computed from the materialised W-expanded input."""
+    obs = restate.structured_frames(3, 64, 64, 6, 6)
+    t = Transforms()
+    out = torch.full((6, 224, 232, 4), float("nan"), dtype=torch.bfloat16, device="cuda")
+    t.run(torch.from_numpy(obs).cuda(), 2, out.data_ptr(), _lib.PVR_FMT_STEM_PAD_BF16, True)
+    nhwc = torch.full((6, 224, 224, 4), float("nan"), dtype=torch.bfloat16, device="cuda")
+    t.run(torch.from_numpy(obs).cuda(), 2, nhwc.data_ptr(), _lib.PVR_FMT_NHWC4_BF16, True)
+    assert torch.equal(out[:, :, 3:227], nhwc)
+    assert float(out[:, :, :3].abs().max()) == 0 and float(out[:, :, 227:].abs().max()) == 0
+    frames = restate.structured_frames(5, 224, 224, 3, 23)
+    net = make_net("moco_aug_uber_34", emb["weight_seeds"])
+    assert net.encoder().input_format == _lib.PVR_FMT_STEM_PAD_BF16
+    compact = net.embed(torch.from_numpy(frames)).cpu().numpy()
+    monkeypatch.setenv("PVR_STEM_EXPANDED", "1")
+    net2 = make_net("moco_aug_uber_34", emb["weight_seeds"])
+    assert net2.encoder().input_format == _lib.PVR_FMT_STEM_BF16
+    assert np.array_equal(compact, net2.embed(torch.from_numpy(frames)).cpu().numpy())
+    monkeypatch.setenv("PVR_NO_POOL_FUSION", "1")  # the un-fused stem (tile origin without the pooling halo)
+    monkeypatch.delenv("PVR_STEM_EXPANDED")
+    net3 = make_net("moco_aug_uber_34", emb["weight_seeds"])
+    assert np.array_equal(compact, net3.embed(torch.from_numpy(frames)).cpu().numpy())
+
+
 def test_transforms_module_keeps_reference_calling_convention(tf):
     frames = tf["in_structured_64"]
     x = torch.from_numpy(frames).permute(0, 3, 1, 2).contiguous().cuda()  # NCHW uint8, as src/embeddings.py:392-393

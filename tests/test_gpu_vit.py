@@ -94,6 +94,26 @@ def test_clip_embedding_vs_oracle(name, patch):
     assert np.array_equal(two[:, :512], got[:2]) and np.array_equal(two[:, 512:], got[2:4])
 
 
+@pytest.mark.parametrize("name,patch,hw", [("clip_vit", 32, (224, 224)), ("clip_vit_b16", 16, (224, 224)),
+                                           ("clip_vit", 32, (64, 64))])
+def test_clip_embedding_fp32_mode_vs_oracle(name, patch, hw):
+    """North star: embeddings within relative L2 <= 1e-5 "in the fp32 mode" (net.set_precision('fp32'))."""
+    net, sd = make_clip(name, patch, 5)
+    net.set_precision('fp32')
+    frames = restate.structured_frames(4, hw[0], hw[1], 3, 41)
+    got = net(torch.from_numpy(frames)).astype(np.float64)
+    ref = rv.embedding_forward(sd, frames).astype(np.float64)
+    relerr = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+    print(f"{name} {hw} fp32 mode: rel-L2 {relerr:.2e}")
+    assert relerr <= 1e-5, relerr
+    # 2-frame observations through the fused path, and back to bf16
+    obs2 = np.concatenate([frames[:2], frames[2:4]], axis=3)
+    two = net.embed(torch.from_numpy(obs2), 2).cpu().numpy()
+    assert np.array_equal(two[:, :512], got[:2].astype(np.float32)) and np.array_equal(two[:, 512:], got[2:4].astype(np.float32))
+    net.set_precision('bf16')
+    assert np.linalg.norm(net(torch.from_numpy(frames)) - ref) / np.linalg.norm(ref) <= 1e-2
+
+
 def test_clip_embedding_stress_weights():
     """Transformer matrices at twice CLIP's init scale: rounding the WEIGHTS to bf16 alone costs 0.73 % relative L2
     (CPU emulation), every other bf16 operand adds in quadrature -> 1.06 %. Recorded, not hidden."""

@@ -149,8 +149,8 @@ def test_policy_forward_backward_vs_reference_golden(gold):
             assert abs(float(g.norm()) - ref_norm) <= 0.02 * ref_norm + 1e-7, (name, float(g.norm()), ref_norm)
     assert rel(net.core.bias_ih_l1.grad, torch.from_numpy(gold["fb_grad_bias_ih_l1"])) < 2e-2
     assert rel(net.policy.weight.grad, torch.from_numpy(gold["fb_grad_policy_w"])) < 2e-2
-    # d(gamma) = sum dy * xhat is a sum of cancelling terms: bf16 rounding of dy shows up amplified
-    assert rel(net.fc[0].weight.grad, torch.from_numpy(gold["fb_grad_bn_w"])) < 0.12
+    # trunk gradients: see test_policy_vs_oracle_other_shapes for where their ~6 % comes from
+    assert rel(net.fc[0].weight.grad, torch.from_numpy(gold["fb_grad_bn_w"])) < 0.08
 
 
 def test_policy_eval_mode_argmax_and_no_grad(gold):
@@ -186,9 +186,13 @@ def test_policy_vs_oracle_other_shapes(T, B, D, bn):
     for k, p in net.named_parameters():
         if k.startswith("baseline."):
             continue
-        # bf16 operands in the backward GEMMs: weight gradients are sums of cancelling per-sample terms, so their
-        # relative L2 error vs fp32 is a few percent (largest for the deepest layer); the loss curve is the criterion
-        assert rel(p.grad, sd[k].grad) < (0.12 if k.startswith("fc.0.") and bn else 0.1), k
+        # Measured (profiles/r02_grad_error_table.txt): LSTM / head gradients within 0.65 %, the BN / fc trunk's
+        # within 6.2 %. A CPU emulation that rounds ONE class of tensors at a time (tools/grad_budget_cpu.py,
+        # profiles/r02_grad_budget_cpu.txt) reproduces these numbers to three digits and attributes them: bf16 weights
+        # alone 5 %, bf16 forward activations alone 4.8 % on the trunk (0.4 % on the LSTM) — the gradient of the bf16
+        # FUNCTION differs from the fp32 one's, amplified through the recurrence on the way down to the trunk — while
+        # the backward roundings (dG, dZ, dX0 in bf16) cost 0.2 % each. No backward precision would change that.
+        assert rel(p.grad, sd[k].grad) < (0.08 if k.startswith("fc.") else 0.012), k
 
 
 def test_bc_training_trace_vs_unmodified_reference(gold):

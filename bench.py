@@ -266,7 +266,7 @@ def cpu_port_bc_steps_per_s(threads):
 
 
 CLIP_B16_IMAGES = 1024     # BASELINE configs[2]: batch 1024 per GPU
-FT_CFG = dict(T=100, B=16, hw=64, n_frames=2, n=4096)  # BASELINE configs[3]: obs (T=100, B=16*G, 64, 64, 6) uint8
+FT_CFG = dict(T=100, B=16, hw=64, n_frames=2, n=16384)  # n >= B_global + (B_global - 1)(T - 1) at 8 GPUs  # BASELINE configs[3]: obs (T=100, B=16*G, 64, 64, 6) uint8
 # conv trunk 8.04 MFLOP/frame forward (5 x 3x3/s2 convs on 64x64), policy trunk at D = 256: 36.2 MFLOP/sample forward;
 # forward + backward = 3 x forward
 FT_GFLOP_PER_STEP_PER_SEQ = 3 * (2 * 8.04 + 36.2) * 100 / 1e3

@@ -65,6 +65,15 @@ def _device(flags):
     return torch.device('cuda', local if world > 1 else torch.cuda.current_device())
 
 
+def init_distributed_from_env():
+    """Under torchrun (WORLD_SIZE > 1) join the NCCL process group, one rank per GPU; no-op for a single process."""
+    rank, world, local = parallel.env_world()
+    if world > 1 and not (torch.distributed.is_available() and torch.distributed.is_initialized()):
+        torch.cuda.set_device(local)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world
+
+
 def _is_writer():
     return not (torch.distributed.is_available() and torch.distributed.is_initialized()) or \
         torch.distributed.get_rank() == 0

@@ -13,25 +13,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libpvr_b200.so")
 OBJ = os.path.join(HERE, "lib", "obj")
 SOURCES = ["api.cu", "conv_gemm.cu", "preprocess.cu", "preprocess_aa.cu", "pool_head.cu", "policy.cu", "vit.cu",
-           "conv3x3_patch.cu", "conv_b2b.cu", "conv_f32.cu", "policy_conv.cu", "lstm_persist.cu", "policy_step.cu",
-           "comm.cu", "vit_f32.cu"]
-NCCL_DIRS = None
-
-
-def _nccl():
-    """(include dir, library file) of the NCCL that ships with torch (header + libnccl.so.2); (None, None) if absent.
-    comm.cu binds NCCL at run time with dlopen, so only the header is needed to build."""
-    global NCCL_DIRS
-    if NCCL_DIRS is None:
-        inc = lib = None
-        for p in sys.path:
-            cand = os.path.join(p, "nvidia", "nccl")
-            if os.path.exists(os.path.join(cand, "include", "nccl.h")):
-                inc = os.path.join(cand, "include")
-                lib = os.path.join(cand, "lib", "libnccl.so.2")
-                break
-        NCCL_DIRS = (inc, lib)
-    return NCCL_DIRS
+           "conv3x3_patch.cu", "conv_b2b.cu", "conv_f32.cu", "policy_conv.cu", "lstm_persist.cu", "comm.cu",
+           "vit_f32.cu"]
 
 
 def _headers():
@@ -44,9 +27,6 @@ def _compile(nvcc, src, obj, verbose):
     cmd = [nvcc, "-c", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", obj, src]
-    inc, _ = _nccl()
-    if inc:
-        cmd += ["-I", inc]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

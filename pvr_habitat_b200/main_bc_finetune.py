@@ -2,7 +2,7 @@
 raw frames -> PolicyNetWithConv trained end to end (main_bc_finetune.py:167-208). The loop, file names, statistics and checkpoint
 schema are in pvr_habitat_b200.bc_run; the simulator hooks (`make_environment`, `test`) are optional arguments."""
 from .arguments import parser
-from .bc_run import run_bc
+from .bc_run import init_distributed_from_env, run_bc
 
 
 def run(flags, make_environment=None, test=None, **trainer_kwargs):
@@ -10,4 +10,5 @@ def run(flags, make_environment=None, test=None, **trainer_kwargs):
 
 
 if __name__ == '__main__':
+    init_distributed_from_env()  # torchrun: one rank per GPU, sequences of the global batch split over the ranks
     run(parser.parse_args())

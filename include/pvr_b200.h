@@ -357,6 +357,11 @@ int pvr_convfeat_gather(const void* y_bf16, int pitch, int TB, int N, int h, int
 int pvr_convfeat_scatter(const float* dfeat, int64_t ld, int TB, int N, int h, int w, int C, float* dy, void* stream);
 /* dz (M, 64) bf16 = dy (M, C) * ELU'(z), ELU' from the saved output y (1 if y > 0 else y + 1); columns >= C zero. */
 int pvr_elu_backward(const float* dy, const void* y_bf16, int pitch, int64_t M, int C, void* dz_bf16, void* stream);
+/* The same in one pass with what its consumers need: dz (M, 64) bf16, its transpose dzt (64, Mp) bf16 (K-major operand
+ * of the weight-gradient GEMM; columns >= M are left untouched) and colsum[c] += sum_m dz[m][c] (bias gradient; may be
+ * NULL). C a multiple of 16, Mp a multiple of 16. */
+int pvr_elu_backward_fused(const float* dy, const void* y_bf16, int pitch, int64_t M, int C, void* dz_bf16,
+                           void* dzt_bf16, int64_t Mp, float* colsum, void* stream);
 /* colT ((9*Ci), Mp) bf16: transposed im2col of A (F, Hi, Wi, pitch) for a 3x3/s2/p1 conv, Ci = 4 or 32. */
 int pvr_im2col_t(const void* a_bf16, int pitch, int F, int Hi, int Wi, int Ci, int Ho, int Wo, int64_t Mp,
                  void* colT_bf16, void* stream);

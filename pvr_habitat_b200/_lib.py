@@ -104,6 +104,7 @@ _SIGNATURES = {
     "pvr_convfeat_gather": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pvr_convfeat_scatter": (ctypes.c_int, [_vp, _i64, _i, _i, _i, _i, _i, _vp, _vp]),
     "pvr_elu_backward": (ctypes.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp]),
+    "pvr_elu_backward_fused": (ctypes.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
     "pvr_im2col_t": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _i64, _vp, _vp]),
     "pvr_col2im": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "pvr_bn1d_backward_dx": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_double,

@@ -669,40 +669,50 @@ class PolicyNetWithConv(PolicyNet):
         _lib.check(lib.pvr_convfeat_scatter(dx.data_ptr(), dx.stride(0), TB, N, hc, hc, 32, dy.data_ptr(), _stream()),
                    "pvr_convfeat_scatter")
         in_hw = [H] + sizes[:-1]
+        # per-layer buffers of the backward, allocated once per batch shape: the padding of dzt (columns >= M) and of
+        # colt (tap rows >= 9 Ci, columns >= M) is zeroed here and never written afterwards
+        bufs = st.get("bwd_bufs")
+        if bufs is None:
+            bufs = st["bwd_bufs"] = []
+            for l in range(5):
+                M = F * sizes[l] * sizes[l]
+                Mp = (M + 511) // 512 * 512
+                Kp = 64 if l == 0 else 320
+                bufs.append(dict(dz=torch.empty(M, 64, dtype=bf, device=dev), dzt=torch.zeros(64, Mp, dtype=bf, device=dev),
+                                 colt=torch.zeros(Kp, Mp, dtype=bf, device=dev), dw=torch.zeros(64, Kp, dtype=f32, device=dev),
+                                 wt=torch.zeros(Kp, 64, dtype=bf, device=dev) if l > 0 else None,
+                                 dcol=torch.empty(M, Kp, dtype=bf, device=dev) if l > 0 else None,
+                                 dy_in=torch.empty(F * in_hw[l] * in_hw[l], 32, dtype=f32, device=dev) if l > 0 else None))
         for l in range(4, -1, -1):
             ho, hi = sizes[l], in_hw[l]
             ci = 4 if l == 0 else 32
             M = F * ho * ho
             Mp = (M + 511) // 512 * 512
             Kp = 64 if l == 0 else 320
+            b = bufs[l]
             y_ptr, a_ptr = enc.slot_ptr(slots[l + 1]), enc.slot_ptr(slots[l])
-            dz = torch.empty(M, 64, dtype=bf, device=dev)
-            _lib.check(lib.pvr_elu_backward(dy.data_ptr(), y_ptr, 32, M, 32, dz.data_ptr(), _stream()),
-                       "pvr_elu_backward")
-            _lib.check(lib.pvr_colsum_bf16(dz.data_ptr(), 64, M, 32, gconv[2 * l + 1].data_ptr(), _stream()),
-                       "pvr_colsum_bf16")
-            dzt = torch.zeros(64, Mp, dtype=bf, device=dev)
-            _lib.check(lib.pvr_transpose_bf16(dz.data_ptr(), 64, M, 64, dzt.data_ptr(), Mp, _stream()),
-                       "pvr_transpose_bf16")
-            colt = torch.zeros(Kp, Mp, dtype=bf, device=dev)
+            # ELU backward + bias gradient + the transposed copy for the weight-gradient GEMM, one pass over dy
+            dz, dzt, colt, dw = b["dz"], b["dzt"], b["colt"], b["dw"]
+            _lib.check(lib.pvr_elu_backward_fused(dy.data_ptr(), y_ptr, 32, M, 32, dz.data_ptr(), dzt.data_ptr(), Mp,
+                                                  gconv[2 * l + 1].data_ptr(), _stream()), "pvr_elu_backward_fused")
             _lib.check(lib.pvr_im2col_t(a_ptr, ci, F, hi, hi, ci, ho, ho, Mp, colt.data_ptr(), _stream()),
                        "pvr_im2col_t")
             chunks = Mp // 64
             split = 1
             while split < 64 and chunks % (split * 2) == 0:
                 split *= 2
-            dw = torch.zeros(64, Kp, dtype=f32, device=dev)  # rows 32..63 unused (dZ^T padding)
+            dw.zero_()  # rows 32..63 unused (dZ^T padding); split-K slices accumulate into it
             gemm(dzt, colt, dw, 64, Kp, Mp, out_f32=2, split_k=split, n_pad=Kp)
             # natural layout (co, a, b, ci) -> parameter layout (co, ci, b, a): the conv runs on un-transposed frames
             w_nat = dw[:32, :9 * ci].view(32, 3, 3, ci)[..., :conv_params[2 * l].shape[1]]
             gconv[2 * l].copy_(w_nat.permute(0, 3, 2, 1))
             if l > 0:
-                wt = torch.zeros(Kp, 64, dtype=bf, device=dev)  # (k = (a, b, ci), co)
+                wt = b["wt"]  # (k = (a, b, ci), co); rows >= 288 and columns >= 32 stay zero
                 w_t = conv_params[2 * l].detach().transpose(2, 3).permute(2, 3, 1, 0).reshape(9 * 32, 32)
                 wt[:288, :32] = w_t.to(bf)
-                dcol = torch.empty(M, Kp, dtype=bf, device=dev)
+                dcol = b["dcol"]
                 gemm(dz, wt, dcol, M, Kp, 64, n_pad=Kp)
-                dy = torch.empty(F * hi * hi, 32, dtype=f32, device=dev)
+                dy = b["dy_in"]
                 _lib.check(lib.pvr_col2im(dcol.data_ptr(), Kp, F, hi, hi, 32, ho, ho, dy.data_ptr(), _stream()),
                            "pvr_col2im")
         if self.comm is not None:

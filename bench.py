@@ -227,6 +227,8 @@ def bench_bc(steps, warmup, world, dist, host_batches, batch_size=None):
     obs, action, done, _ = bc_dataset()
     torch.manual_seed(1)
     random.seed(1)
+    if host_batches and world > 1:  # the host-side gather of every rank is multi-threaded: share the cores
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
     net = PolicyNet((BC_CFG["D"],), BC_CFG["A"], batch_norm=True).cuda().train()
     tr = BCTrainer(net, obs, action, done, batch_size or BC_CFG["B"], BC_CFG["T"], 10 ** 9, host_batches=host_batches)
     for _ in range(warmup):

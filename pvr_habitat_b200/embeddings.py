@@ -403,27 +403,51 @@ class EmbeddingNet(nn.Module):
         return out.view(-1, self.out_size).squeeze().cpu().numpy()
 
 
-try:  # the gym adaptor exists only where gym does (simulator side; not on the embedding/BC hot path)
+try:  # gym is the simulator side's dependency; without it the adaptor keeps working on any object with the same duck type
     import gym
     from gym.spaces.box import Box
+    _ObservationWrapper = gym.ObservationWrapper
+except ImportError:
+    class Box(object):
+        """Minimal stand-in for gym.spaces.Box (shape / bounds only)."""
 
-    class EmbeddingWrapper(gym.ObservationWrapper):
-        """src/embeddings.py:409-444: (H, W, 3n) frames -> flat (n*O,) embedding."""
+        def __init__(self, low=None, high=None, shape=None, dtype=None):
+            self.low, self.high, self.shape, self.dtype = low, high, tuple(shape), dtype
 
-        def __init__(self, env, embedding):
-            gym.ObservationWrapper.__init__(self, env)
-            in_channels = env.observation_space.shape[2]
-            assert in_channels % 3 == 0, "Only RGB images are supported."
-            self.in_channels = 3
-            self.n_frames = in_channels // 3
-            self.embedding = embedding
-            self.observation_space = Box(low=-np.inf, high=np.inf,
-                                         shape=(self.embedding.out_size * self.n_frames,))
+    class _ObservationWrapper(object):
+        """Minimal stand-in for gym.ObservationWrapper: reset / step pass observations through `observation`."""
 
-        def observation(self, observation):
-            obs = torch.from_numpy(np.ascontiguousarray(observation))[None]
-            return self.embedding.embed(obs, self.n_frames).flatten().cpu().numpy()
-except ImportError:  # pragma: no cover
-    class EmbeddingWrapper(object):
-        def __init__(self, *a, **k):
-            raise ImportError("EmbeddingWrapper needs `gym` (the reference's simulator stack)")
+        def __init__(self, env):
+            self.env = env
+            self.observation_space = getattr(env, "observation_space", None)
+            self.action_space = getattr(env, "action_space", None)
+
+        def reset(self, **kwargs):
+            return self.observation(self.env.reset(**kwargs))
+
+        def step(self, action):
+            observation, reward, done, info = self.env.step(action)
+            return self.observation(observation), reward, done, info
+
+        def __getattr__(self, name):
+            return getattr(self.env, name)
+
+
+class EmbeddingWrapper(_ObservationWrapper):
+    """src/embeddings.py:409-444: (H, W, 3n) uint8 frames of one environment step -> flat (n*O,) float32 embedding
+    (frame f in columns [f*O, (f+1)*O), `src/embeddings.py:441-444`). Batches of <= 8 images replay from a CUDA graph
+    (pvr_encoder_forward), which is what makes the per-step latency of a rollout."""
+
+    def __init__(self, env, embedding):
+        _ObservationWrapper.__init__(self, env)
+        in_channels = env.observation_space.shape[2]
+        assert in_channels % 3 == 0, "Only RGB images are supported."
+        self.in_channels = 3
+        self.n_frames = in_channels // 3
+        self.embedding = embedding
+        self.observation_space = Box(low=-np.inf, high=np.inf,
+                                     shape=(self.embedding.out_size * self.n_frames,))
+
+    def observation(self, observation):
+        obs = torch.from_numpy(np.ascontiguousarray(observation))[None]
+        return self.embedding.embed(obs, self.n_frames).flatten().cpu().numpy()

@@ -321,3 +321,35 @@ def test_every_reference_embedding_name_is_accounted_for():
             assert not model.training and all(not p.requires_grad for p in model.parameters()), name
     with pytest.raises(NotImplementedError):
         _get_embedding("no_such_model")
+
+
+def test_embedding_wrapper_without_gym():
+    """EmbeddingWrapper (src/embeddings.py:409-444) works on a duck-typed environment when gym is not installed: the
+    observation space becomes (n_frames * out_size,), reset / step route observations through the encoder."""
+    import types
+    from pvr_habitat_b200.embeddings import EmbeddingWrapper
+
+    class Enc:
+        out_size = 5
+        calls = []
+
+        def embed(self, obs, n_frames):
+            Enc.calls.append((tuple(obs.shape), obs.dtype, n_frames))
+            return torch.arange(n_frames * 5, dtype=torch.float32).reshape(1, -1)
+
+    class Env:
+        observation_space = types.SimpleNamespace(shape=(64, 64, 6))
+        action_space = types.SimpleNamespace(n=3)
+
+        def reset(self):
+            return np.zeros((64, 64, 6), np.uint8)
+
+        def step(self, a):
+            return np.ones((64, 64, 6), np.uint8), 1.0, False, {}
+
+    w = EmbeddingWrapper(Env(), Enc())
+    assert w.n_frames == 2 and tuple(w.observation_space.shape) == (10,)
+    o = w.reset()
+    assert o.shape == (10,) and o.dtype == np.float32 and Enc.calls[-1] == ((1, 64, 64, 6), torch.uint8, 2)
+    o, r, d, info = w.step(0)
+    assert o.shape == (10,) and r == 1.0 and d is False and w.action_space.n == 3

@@ -187,12 +187,13 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // The CTAs of a batch tile all stream the same operand chunks: each starts at a different chunk so that they do not
   // all request the same L2 lines at the same moment (forward: 64 CTAs share the 16 chunks; backward: the 16 CTAs of
   // a K slice do).
-  const int rot = (BWD ? J : (J + 4 * (int)q)) & (NG - 1);
+  // (forward: the order is the same for the four CTAs of a cluster, which share the operand through multicast)
+  const int rot = J & (NG - 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], BWD ? 1 : 4);  // forward: freed by the MMAs of all four CTAs (multicast commit)
     }
     mbar_init(w_full, 1);
     mbar_init(acc_full, 1);
@@ -225,13 +226,58 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     __syncwarp();
     int it = 0;
-    for (int s = BWD ? 1 : 0; s < T; ++s) {
-      const int t = BWD ? T - 1 - s : s;
-      const int src_t = BWD ? t + 1 : t;  // time index of the operand rows (dG_{t+1} / hm_t)
-      const bool gated = BWD ? true : (t > 0);
+    if (!BWD) {
+      // Forward: the four CTAs of a cluster need the SAME operand rows (all 16 chunks of their batch tile). Each CTA
+      // loads one group per step — the k-th group of the step is issued by CTA k — and multicasts it to all four, so
+      // the L2 sees a quarter of the requests. A stage is reused when the MMAs of all four CTAs have released it
+      // (count-4 `empty` barrier, multicast commit); every CTA arms its own `full` barrier.
+      static_assert(NG == 4, "one group per CTA of the cluster");
+      for (int s = 0; s < T; ++s) {
+        const unsigned int* flags = p.ready + ((size_t)s * nbt + bt) * 16;
+        const int a_row = s * B + 64 * bt;
+        for (int k = 0; k < NG; ++k, ++it) {
+          const int st = it % NST;
+          const uint32_t ph = (uint32_t)(it / NST) & 1u;
+          mbar_wait(&empty[st], ph ^ 1u);
+          if (elect_one()) mbar_expect_tx(&full[st], STAGE_BYTES);
+          __syncwarp();
+          if (k != (int)q) continue;
+          const int g = (k + rot) & (NG - 1);
+          if (s > 0) {  // the group's four chunks must have been written by their 16 producer CTAs
+            uint32_t polls = 0;
+            uint64_t t0 = 0;
+            for (;;) {
+              unsigned int v = 4;
+              if (lane < CPI) v = ld_acquire_gpu(flags + CPI * g + lane);
+              if (__all_sync(0xffffffffu, v >= 4u)) break;
+              if ((++polls & 63u) == 0) {
+                const uint64_t now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > 4000000000ull) {
+                  if (lane == 0)
+                    printf("pvr: lstm_persist forward step %d group %d never became ready (block %d)\n", s, g,
+                           (int)blockIdx.x);
+                  __trap();
+                }
+              }
+            }
+          }
+          if (lane == 0 && k == 0) PROF(0);
+          fence_proxy_async_global();  // rows written with st.global by other SMs; TMA reads them next
+          if (elect_one())
+            tma_load_3d_multicast(&tmap_a, &full[st], sA + st * STAGE_BYTES, 0, a_row, CPI * g, (uint16_t)0xF);
+          __syncwarp();
+          if (lane == 0) PROF(2);
+        }
+      }
+    }
+    for (int s = 1; BWD && s < T; ++s) {
+      const int t = T - 1 - s;
+      const int src_t = t + 1;  // time index of the operand rows (dG_{t+1})
+      const bool gated = true;
       const unsigned int* flags = p.ready + ((size_t)src_t * nbt + bt) * 16;
       const int a_row = src_t * B + 64 * bt;
-      const int a_c0 = BWD ? (int)q * 16 : 0;  // first K chunk of this CTA's slice (dG: gate q's 1024 columns)
+      const int a_c0 = (int)q * 16;  // first K chunk of this CTA's slice (dG: gate q's 1024 columns)
       int next = 0;  // next chunk GROUP (CPI chunks = one TMA instruction = one ring stage), in this CTA's order
       uint32_t polls = 0;
       uint64_t t0 = 0;
@@ -302,7 +348,8 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem, ad + 2 * k, bd + 2 * k, idesc, ((g * CPI + c) | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[st]);
+          if (BWD) umma_commit(&empty[st]);
+          else umma_commit_multicast(&empty[st], (uint16_t)0xF);  // the stage is shared by the cluster's loads
           if (g == NG - 1) umma_commit(acc_full);
         }
         __syncwarp();

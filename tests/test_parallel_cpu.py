@@ -92,3 +92,44 @@ def test_two_rank_data_parallel_equals_global_batch(tmp_path):
     torch.testing.assert_close(got["flat"], flat, atol=1e-7, rtol=1e-4)
     x = torch.from_numpy(o).flatten(0, 1).double()
     torch.testing.assert_close(got["sums"], torch.stack([x.sum(0), (x * x).sum(0)]))
+
+
+# ------------------------------------------------------------------------------------------------ product plumbing
+def _attach_worker(rank, world, port, out):
+    """The product's attach / Comm path on gloo (CPU tensors): the normal torchrun idiom — torch.distributed is
+    initialised and NO process group is passed."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pvr_habitat_b200.models import PolicyNet
+    torch.manual_seed(100 + rank)  # different seeds: the replicas must be made identical by the broadcast
+    net = PolicyNet((16,), 3, batch_norm=True)
+    before = float(net.policy.weight.double().sum())
+    group = parallel.resolve_group(None)
+    assert group is not None and dist.get_world_size(group) == world
+    parallel.attach(net, None, global_rows=48)
+    assert net.process_group is not None and net.comm is not None and net.global_rows == 48
+    assert net.comm.world == world and not net.comm.capturable  # gloo: torch.distributed fallback, never captured
+    t = torch.full((5,), float(rank + 1), dtype=torch.float64)
+    net.comm.all_reduce(t)
+    sums = {k: float(v.double().sum()) for k, v in net.state_dict().items() if v.is_floating_point()}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (before, sums, t.tolist()))
+    if rank == 0:
+        torch.save(gathered, out)
+    dist.destroy_process_group()
+
+
+def test_attach_resolves_the_default_group_and_broadcasts(tmp_path):
+    """Round-1 advisor finding: with process_group=None under an initialised torch.distributed the collectives were
+    skipped and every rank trained alone. `attach` must pick WORLD, create the Comm and make the replicas identical."""
+    out = str(tmp_path / "attach.pt")
+    mp.spawn(_attach_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    (b0, s0, t0), (b1, s1, t1) = torch.load(out)
+    assert b0 != b1                      # the ranks started from different initialisations ...
+    assert s0 == s1                      # ... and hold rank 0's parameters / buffers after attach
+    assert abs(s0["policy.weight"] - b0) < 1e-12
+    assert t0 == t1 == [3.0] * 5         # all_reduce is a SUM over the ranks
+
+
+def test_resolve_group_single_process():
+    assert parallel.resolve_group(None) is None  # no torch.distributed: one process, no collectives

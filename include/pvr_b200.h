@@ -280,6 +280,7 @@ typedef struct pvr_lstm_bwd {
   float* dh_rec;        /* (B, H) fp32: gradient of the final hidden state on entry (zeros in BC) */
   float* dc_rec;        /* (B, H) fp32: gradient of the final cell state on entry (zeros in BC) */
   void* dG;             /* bf16 (T*B, 4H) out: gradient w.r.t. the gate pre-activations */
+  float* dbias;         /* optional (4H) fp32: += sum over t, b of dG — the gradient of bias_ih (= that of bias_hh) */
 } pvr_lstm_bwd;
 int pvr_lstm_backward(const pvr_lstm_bwd* layer, void* stream);
 

@@ -48,7 +48,7 @@ class pvr_lstm_fwd(ctypes.Structure):
 
 class pvr_lstm_bwd(ctypes.Structure):
     _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("flags", ctypes.c_int32)] + [
-        (n, ctypes.c_void_p) for n in ("w_hh_t", "nd", "gates", "c_all", "dh_out", "dh_rec", "dc_rec", "dG")]
+        (n, ctypes.c_void_p) for n in ("w_hh_t", "nd", "gates", "c_all", "dh_out", "dh_rec", "dc_rec", "dG", "dbias")]
 
 
 class pvr_slot(ctypes.Structure):

@@ -74,6 +74,7 @@ struct PersistParams {
   float* dh_rec;         // (B, H): in = gradient of the final hidden state, out = gradient of the initial one
   float* dc_rec;         // (B, H): same for the cell state
   __nv_bfloat16* dG;     // (T B, 4H)
+  float* dbias;          // optional (4H): += sum over t, b of dG
   unsigned int* ready;   // ((T+1) * nbt * 16) arrival counters, zeroed before the launch
   long long* prof;       // optional (PVR_LSTM_PROF): [block][step < 64][16] clock64 stamps of the phases of a step
 };
@@ -379,6 +380,9 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         ld8_coherent(p.dh_rec + (size_t)b * HID + j0, dh_last);
       }
     }
+    float bsum[BWD ? 32 : 1];  // backward: this thread's share of the bias gradient, summed over the time steps
+#pragma unroll
+    for (int i = 0; i < (BWD ? 32 : 1); ++i) bsum[i] = 0.f;
     uint32_t xphase = 0;
     int gi = 0;
     for (int s = 0; s < T; ++s) {
@@ -495,6 +499,9 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             o2[u] = dc * i * (1.f - g * g);
             o3[u] = dh * tc * o * (1.f - o);
             state[u] = dc * f * nd_t;
+            if (BWD) {
+              bsum[u] += o0[u]; bsum[8 + u] += o1[u]; bsum[16 + u] += o2[u]; bsum[24 + u] += o3[u];
+            }
           }
           __nv_bfloat16* dp = p.dG + row_t * (4 * HID) + j0;
           st8_bf16(dp, o0);
@@ -528,6 +535,16 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
         st8(p.c_all + (row_t + B) * HID + j0, state);
         st8_bf16(p.h_out + row_t * HID + j0, hv);
         if (t + 1 >= T) st8(p.h_last + (size_t)b * HID + j0, hv);
+      }
+    }
+    if (BWD && p.dbias) {
+      // bias gradient: the 32 rows a warp holds share `half`, so the rows are summed by shuffles first
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = bsum[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(p.dbias + (i >> 3) * HID + j0 + (i & 7), v);
       }
     }
     if (BWD && row_ok) {
@@ -672,6 +689,7 @@ int lstm_persist_backward(const pvr_lstm_bwd* L, cudaStream_t st) {
   p.nd = L->nd; p.c_all = const_cast<float*>(L->c_all); p.gates = const_cast<float*>(L->gates);
   p.dh_out = L->dh_out; p.dh_rec = L->dh_rec; p.dc_rec = L->dc_rec;
   p.dG = static_cast<__nv_bfloat16*>(L->dG);
+  p.dbias = L->dbias;
   CUtensorMap ta, tw;
   const char* err = nullptr;
   if (!make_tmap_kchunks(&ta, L->dG, 4 * HID, (uint64_t)T * B, 4 * HID, 64, CPI, &err) ||

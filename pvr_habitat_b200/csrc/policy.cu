@@ -972,6 +972,9 @@ extern "C" int pvr_lstm_backward(const pvr_lstm_bwd* L, void* stream_) {
     return PVR_ERR_ARG;
   }
   if (L->flags == 0 && pvr::lstm_persist_supported(L->T, L->B, L->H))
-    return pvr::lstm_persist_backward(L, static_cast<cudaStream_t>(stream_));
-  return run_cached(L, static_cast<cudaStream_t>(stream_), lstm_backward_issue, "pvr_lstm_backward");
+    return pvr::lstm_persist_backward(L, static_cast<cudaStream_t>(stream_));  // accumulates dbias itself
+  int rc = run_cached(L, static_cast<cudaStream_t>(stream_), lstm_backward_issue, "pvr_lstm_backward");
+  if (rc == PVR_OK && L->dbias)  // per-step kernels: the bias gradient is a column sum over this call's dG rows
+    rc = pvr_colsum_bf16(L->dG, 4 * L->H, L->T * L->B, 4 * L->H, L->dbias, stream_);
+  return rc;
 }

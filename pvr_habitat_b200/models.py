@@ -233,12 +233,13 @@ class PolicyNet(nn.Module):
                          h_last=ws.h_last[l].data_ptr())
         _lib.check(_lib.lib().pvr_lstm_forward(ctypes.byref(L), _stream()), "pvr_lstm_forward")
 
-    def _lstm_bwd_chunk(self, ws, w, l, t0, Tc, flags):
+    def _lstm_bwd_chunk(self, ws, w, l, t0, Tc, flags, dbias=None):
         B, H, r0 = ws.B, ws.H, t0 * ws.B
         L = pvr_lstm_bwd(T=Tc, B=B, H=H, flags=flags, w_hh_t=w["WhhT"][l].data_ptr(), nd=ws.nd[t0:].data_ptr(),
                          gates=ws.gates[l][r0:].data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
                          dh_out=ws.dHL[l][r0:].data_ptr(), dh_rec=ws.dh_rec[l].data_ptr(),
-                         dc_rec=ws.dc_rec[l].data_ptr(), dG=ws.dG[l][r0:].data_ptr())
+                         dc_rec=ws.dc_rec[l].data_ptr(), dG=ws.dG[l][r0:].data_ptr(),
+                         dbias=dbias.data_ptr() if dbias is not None else None)
         _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(L), _stream()), "pvr_lstm_backward")
 
     def _check_generation(self, generation):
@@ -387,7 +388,7 @@ class PolicyNet(nn.Module):
         for c in reversed(range(C)):
             flags = (_lib.PVR_LSTM_CONT_PREV if c > 0 else 0) | (_lib.PVR_LSTM_CONT_NEXT if c < C - 1 else 0)
             r0, rows = c * Tc * B, Tc * B
-            self._lstm_bwd_chunk(ws, w, 1, c * Tc, Tc, flags)
+            self._lstm_bwd_chunk(ws, w, 1, c * Tc, Tc, flags, g["bih1"])  # (+ the layer's bias gradient)
             # gradient w.r.t. layer-0 outputs (fp32, consumed by the layer-0 cell backward)
             gemm(ws.dG[1][r0:r0 + rows], w["WihT"][1], ws.dHL[0][r0:r0 + rows], rows, H, 4 * H, out_f32=1)
             if C > 1:
@@ -395,7 +396,7 @@ class PolicyNet(nn.Module):
                 ev.record(cur)
                 side.wait_event(ev)
             with torch.cuda.stream(side):
-                self._lstm_bwd_chunk(ws, w, 0, c * Tc, Tc, flags)
+                self._lstm_bwd_chunk(ws, w, 0, c * Tc, Tc, flags, g["bih0"])
         below = [ws.H2, ws.HL[0]]  # input of LSTM layer l
         for l in (1, 0):
             if l == 0 and C > 1:  # layer 1's weight gradients above overlap the tail of layer 0's recurrence
@@ -403,8 +404,7 @@ class PolicyNet(nn.Module):
                 ev.record(side)
                 cur.wait_event(ev)
             dG = ws.dG[l]
-            colsum(dG, 4 * H, g[f"bih{l}"])
-            g[f"bhh{l}"].copy_(g[f"bih{l}"])
+            g[f"bhh{l}"].copy_(g[f"bih{l}"])  # (accumulated by pvr_lstm_backward; both biases enter as their sum)
             # dW = dG^T X with dG (M, 4H) and X (M, H) as they sit in memory: MN-major tensor-core operands
             gemm(dG, ws.hm[l], g[f"Whh{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)
             gemm(dG, below[l], g[f"Wih{l}"], 4 * H, H, M, out_f32=1, n_pad=H, mn=True)

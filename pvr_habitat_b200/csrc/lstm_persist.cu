@@ -6,10 +6,13 @@
 //
 //   * W_hh (8 MB bf16) is cut into 64 x 1024 slices that stay RESIDENT in shared memory (128 KB per CTA) for the whole
 //     sequence: 64 slices x ceil(B / 64) batch tiles = 128 CTAs at B = 128, one per SM;
-//   * a step's operand (the masked h_{t-1}, or dG_{t+1} in the backward pass) streams through a 5-stage TMA ring as 16
-//     (64 rows x 64 K) chunks, each gated by a per-chunk arrival counter in global memory that the producing CTAs
-//     bump when their part of the previous step is written — a dataflow barrier instead of a kernel boundary
-//     (ld.acquire.gpu poll of 16 counters in one 64-byte line, fence.proxy.async, TMA);
+//   * a step's operand (the masked h_{t-1}, or dG_{t+1} in the backward pass; 64 rows x 1024) streams through a TMA
+//     ring as 4 groups of 4 (64 x 64) K chunks — one 32 KB box per instruction: the SM's TMA pipe serves its
+//     instructions one after the other at ~400 cycles + 2.3 cycles per 128-byte line, so 8 KB boxes cost 40 % more
+//     time per step — each group gated by per-chunk arrival counters in global memory that the producing CTAs bump
+//     when their part of the previous step is written: a dataflow barrier instead of a kernel boundary
+//     (ld.acquire.gpu poll of one 64-byte line, fence.proxy.async, TMA). In the forward pass the four CTAs of a
+//     cluster need the same rows: each loads one group and multicasts it (L2 requests / 4);
 //   * the (64 x 64) fp32 accumulator lives in TMEM (tcgen05.mma M = 64, N = 64, K = 16 x 64 per step);
 //   * clusters of 4 CTAs: CTA q of cluster (batch tile, hidden block J) owns gate q in the forward pass (rows
 //     q * 1024 + 64 J.. of W_hh) and K slice q (gate q's rows of W_hh^T) in the backward pass. After the MMAs the four
@@ -185,10 +188,9 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   const int cl = blockIdx.x >> 2;
   const int bt = cl / 16, J = cl % 16;
   const int T = p.T, B = p.B, nbt = p.nbt;
-  // The CTAs of a batch tile all stream the same operand chunks: each starts at a different chunk so that they do not
-  // all request the same L2 lines at the same moment (forward: 64 CTAs share the 16 chunks; backward: the 16 CTAs of
-  // a K slice do).
-  // (forward: the order is the same for the four CTAs of a cluster, which share the operand through multicast)
+  // Clusters walk the chunk groups in rotated order, so that the 16 clusters of a batch tile do not all request the
+  // same L2 lines at the same moment. The order is the same for the four CTAs of a cluster (forward: they share the
+  // operand through multicast).
   const int rot = J & (NG - 1);
 
   if (threadIdx.x == 0) {

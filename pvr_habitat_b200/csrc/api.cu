@@ -178,7 +178,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
   // layer2 variant with streamed weights: correct and bit-identical, but measured neutral (133 us against 86 + 51 us
   // per 256 frames: the 256 KB of weights per tile go through two-slot rings) -> opt-in
   const bool b2b_stream_on = b2b_on && getenv("PVR_B2B_STREAM") != nullptr;
-  const int pair_mode = getenv("PVR_CTA2") ? atoi(getenv("PVR_CTA2")) : 1;  // 0 off, 1: 256-wide pair tiles; 2: + 128-wide (no residual); 3: + residual layers
+  const int pair_mode = getenv("PVR_CTA2") ? atoi(getenv("PVR_CTA2")) : 2;  // 0 off, 1: 256-wide pair tiles; 2 (default since round 2: the N = 128 3x3 convs of layer2 gain 8 %: a single CTA reads A + W at the shared-memory port limit there): + 128-wide (no residual); 3: + residual layers
   for (size_t i = 0; i < enc->ops.size(); ++i) {
     const pvr_op& o = enc->ops[i];
     if (o.kind != PVR_OP_CONV) {

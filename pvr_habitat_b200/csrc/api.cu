@@ -737,6 +737,12 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   p.num_m_tiles = (d->m + 127) / 128;
   int block_n = pick_block_n(d->n_pad, (long long)p.num_m_tiles * split_k, sms, 0, d->res != nullptr);
   if (d->out_f32 == 2 && block_n > 128) block_n = 128;
+  // Weight-gradient GEMMs (MN-major operands, e.g. 4096 x 1024 outputs over K = T*B): 256-wide tiles even when they
+  // leave a few SMs idle (128 tiles on 148 SMs) — at N = 128 a single CTA reads A + W at the shared-memory port limit
+  // (128 B/clk), at N = 256 it does not.
+  if (mn && block_n == 128 && d->n_pad % 256 == 0 && (long long)p.num_m_tiles * (d->n_pad / 256) * 5 >= (long long)sms * 4 &&
+      !getenv("PVR_WGRAD_N128"))
+    block_n = 256;
   // CTA pairs (cta_group::2, 256 x 256 tiles) for wide bf16-output GEMMs with enough K: ViT QKV / fc1
   static const bool pair_ok = !(getenv("PVR_CTA2") && atoi(getenv("PVR_CTA2")) == 0);
   static const int pair_f32 = getenv("PVR_PAIR_F32") ? atoi(getenv("PVR_PAIR_F32")) : 1;

@@ -565,6 +565,257 @@ lstm_persist_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   if (warp == 1) tmem_dealloc(tmem, 64);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Forward recurrence, second form: the W_hh slice lives in TENSOR MEMORY.
+//
+// The kernel above is bound by what an SM can pull in per step (128 KB of h_{t-1} per CTA at ~32 B/clk, plus the
+// exchange of accumulator pieces through DSMEM). Here the roles of the operands are swapped: a CTA owns 32 hidden
+// units x 4 gates = 128 rows of W_hh as the A operand of an M = 128 MMA, held in TMEM as packed bf16 (128 lanes x 480
+// columns = K 0..959; the last K chunk sits in shared memory — TMEM has 512 columns and the accumulator needs 32), and
+// the B operand is a batch tile of 32 rows of h_{t-1} (64 KB per step: half the ingest, all four gates of a unit in
+// the same CTA, so no exchange and no cluster). TMEM lane r = 4 u + g holds gate g of unit 32 c + u. 32 CTAs per batch
+// tile x ceil(B / 32) tiles = 128 CTAs at B = 128. After the MMAs the (128 x 32) accumulator is transposed through
+// shared memory so that a thread owns (batch row, 8 units, 4 gates) — the cell code and every saved tensor are the
+// ones of the kernel above.
+constexpr int F2_NB = 32;                            // batch rows per tile = MMA N
+#ifndef PVR_F2_CPI
+#define PVR_F2_CPI 8
+#endif
+constexpr int F2_CPI = PVR_F2_CPI;                   // K chunks per TMA instruction
+constexpr int F2_NG = CHUNKS / F2_CPI;
+constexpr int F2_CHUNK_BYTES = F2_NB * 128;          // 4096
+constexpr int F2_SMEM_B = CHUNKS * F2_CHUNK_BYTES;   // 65536: one step's operand, every group its own slot
+constexpr int F2_KT = 15;                            // K chunks of the W slice held in TMEM (columns 32 .. 511)
+constexpr int F2_SMEM_WT = 128 * 128;                // the 16th chunk: (128 rows x 64) bf16, 128B-swizzled
+constexpr int F2_XPITCH = 33;
+constexpr int F2_SMEM_X = 128 * F2_XPITCH * 4;       // accumulator transpose
+constexpr int F2_SMEM_TOTAL = F2_SMEM_B + F2_SMEM_WT + F2_SMEM_X + 256 + 1024;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __nv_bfloat16* __restrict__ w_hh,
+                 const PersistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sWt = smem + F2_SMEM_B;
+  float* sX = reinterpret_cast<float*>(sWt + F2_SMEM_WT);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sX) + F2_SMEM_X);
+  uint64_t* full = bars;             // [F2_NG]
+  uint64_t* empty = bars + F2_NG;    // [F2_NG]
+  uint64_t* acc_full = bars + 2 * F2_NG;
+  uint64_t* acc_empty = acc_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bt = blockIdx.x >> 5, c = blockIdx.x & 31;
+  const int T = p.T, B = p.B, nbt = p.nbt;
+  const int rot = c & (F2_NG - 1);  // the CTAs of a tile walk the groups in rotated order (spreads the L2 requests)
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < F2_NG; ++g) {
+      mbar_init(&full[g], 1);
+      mbar_init(&empty[g], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    fence_barrier_init();
+    prefetch_tmap(&tmap_a);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp >= 2) {
+    // ---- W slice -> TMEM (packed bf16 pairs, the A-operand layout of tcgen05.mma with A in tensor memory) + the
+    // last chunk -> shared memory. Row r of the slice is W_hh row (r & 3) * 1024 + 32 c + (r >> 2).
+    const int ew = warp & 3;
+    const int r = 32 * ew + lane;
+    const __nv_bfloat16* wrow = w_hh + ((size_t)(r & 3) * HID + 32 * c + (r >> 2)) * HID;
+    const uint32_t ta = tmem + ((uint32_t)(32 * ew) << 16) + 32;
+#pragma unroll 6
+    for (int ks = 0; ks < F2_KT * 4; ++ks) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(wrow + 16 * ks));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(wrow + 16 * ks) + 1);
+      const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      tmem_st_32x32b_x8(ta + 8 * ks, pk);
+    }
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + 64 * F2_KT) + q8);
+      *reinterpret_cast<uint4*>(sWt + r * 128 + ((q8 ^ (r & 7)) << 4)) = v;
+    }
+    tmem_wait_st();
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    for (int s = 0; s < T; ++s) {
+      const unsigned int* flags = p.ready + ((size_t)s * nbt + bt) * 16;
+      const int a_row = s * B + F2_NB * bt;
+      for (int k = 0; k < F2_NG; ++k) {
+        const int g = (k + rot) & (F2_NG - 1);
+        mbar_wait(&empty[g], ((uint32_t)s & 1u) ^ 1u);
+        if (s > 0) {  // the group's chunks must have been written by their producers (2 CTAs per chunk of 64 units)
+          uint32_t polls = 0;
+          uint64_t t0 = 0;
+          for (;;) {
+            unsigned int v = 2;
+            if (lane < F2_CPI) v = ld_acquire_gpu(flags + F2_CPI * g + lane);
+            if (__all_sync(0xffffffffu, v >= 2u)) break;
+            if ((++polls & 63u) == 0) {
+              const uint64_t now = globaltimer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > 4000000000ull) {
+                if (lane == 0)
+                  printf("pvr: lstm_fwd2 step %d group %d never became ready (block %d)\n", s, g, (int)blockIdx.x);
+                __trap();
+              }
+            }
+          }
+        }
+        if (lane == 0 && k == 0) PROF(0);
+        fence_proxy_async_global();  // rows written with st.global by other SMs; TMA reads them next
+        if (elect_one()) {
+          mbar_expect_tx(&full[g], F2_CPI * F2_CHUNK_BYTES);
+          tma_load_3d(&tmap_a, &full[g], sB + g * F2_CPI * F2_CHUNK_BYTES, 0, a_row, F2_CPI * g);
+        }
+        __syncwarp();
+        if (lane == 0 && k == F2_NG - 1) PROF(2);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, F2_NB);
+    const uint64_t wt_desc = umma_desc_sw128(smem_u32(sWt));
+    for (int s = 0; s < T; ++s) {
+      mbar_wait(acc_empty, ((uint32_t)s & 1u) ^ 1u);  // the previous step's accumulator has been read
+      tc_fence_after();
+      for (int k = 0; k < F2_NG; ++k) {
+        const int g = (k + rot) & (F2_NG - 1);
+        mbar_wait(&full[g], (uint32_t)s & 1u);
+        tc_fence_after();
+        if (lane == 0 && k == 0) PROF(3);
+        if (lane == 0 && k == F2_NG - 1) PROF(4);
+        if (elect_one()) {
+#pragma unroll
+          for (int cc = 0; cc < F2_CPI; ++cc) {
+            const int kc = F2_CPI * g + cc;
+            const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * F2_CHUNK_BYTES));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t acc = (k | cc | kk) != 0 ? 1u : 0u;
+              if (kc < F2_KT) umma_bf16_ts(tmem, tmem + 32 + 8 * (4 * kc + kk), bd + 2 * kk, idesc, acc);
+              else umma_bf16(tmem, wt_desc + 2 * kk, bd + 2 * kk, idesc, acc);
+            }
+          }
+          umma_commit(&empty[g]);
+          if (k == F2_NG - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ cell (128 threads)
+    const int e = threadIdx.x - 64;
+    const int ew = warp & 3;            // TMEM lane quadrant of this warp: rows 32 ew .. 32 ew + 31 of the slice
+    const int crow = e >> 2, ug = e & 3;
+    const int b = F2_NB * bt + crow;
+    const bool row_ok = b < B;
+    const int j0 = 32 * c + 8 * ug;     // first of this thread's 8 hidden units
+    float state[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) state[u] = 0.f;
+    if (row_ok) ld8_coherent(p.c_all + (size_t)b * HID + j0, state);
+    for (int s = 0; s < T; ++s) {
+      const int t = s;
+      const size_t row_t = (size_t)t * B + b;
+      float op[32];
+      float nd_t = 0.f, nd_n = 0.f;
+      if (row_ok) {
+        nd_t = __ldg(p.nd + row_t);
+        if (t + 1 < T) nd_n = __ldg(p.nd + row_t + B);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ld8(p.xp + row_t * (4 * HID) + g * HID + j0, op + 8 * g);
+      }
+      mbar_wait(acc_full, (uint32_t)s & 1u);
+      tc_fence_after();
+      if (e == 0) PROF(5);
+      {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem + ((uint32_t)(32 * ew) << 16), v);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty);
+        // row r = 32 ew + lane, column n (batch row of the tile) -> sX[r][(n + 8 ew) & 31]: conflict free both ways
+        float* xr = sX + (32 * ew + lane) * F2_XPITCH;
+#pragma unroll
+        for (int n = 0; n < 32; ++n) xr[(n + 8 * ew) & 31] = __uint_as_float(v[n]);
+      }
+      named_bar_sync(2, 128);
+      float G[32];
+      {
+        const float* xc = sX + (32 * ug) * F2_XPITCH + ((crow + 8 * ug) & 31);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+          for (int g = 0; g < 4; ++g) G[8 * g + u] = xc[(4 * u + g) * F2_XPITCH];
+      }
+      const bool publish = t + 1 < T;
+      float o0[8], o1[8], o2[8], o3[8], hv[8];
+      if (row_ok) {
+        float hmv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float i = sigmoid_fast(G[u] + op[u]);
+          const float f = sigmoid_fast(G[8 + u] + op[8 + u]);
+          const float g = tanh_fast(G[16 + u] + op[16 + u]);
+          const float o = sigmoid_fast(G[24 + u] + op[24 + u]);
+          const float cv = f * (nd_t * state[u]) + i * g;
+          const float h = o * tanh_fast(cv);
+          state[u] = cv;
+          o0[u] = i; o1[u] = f; o2[u] = g; o3[u] = o;
+          hv[u] = h;
+          hmv[u] = h * nd_n;
+        }
+        if (publish) st8_bf16(p.hm + (row_t + B) * HID + j0, hmv);
+      }
+      if (e == 0) PROF(8);
+      if (publish) {
+        fence_proxy_async_global();
+        named_bar_sync(1, 128);
+        if (e == 0) {
+          PROF(9);
+          red_release_gpu_add(p.ready + ((size_t)(t + 1) * nbt + bt) * 16 + (c >> 1), 1u);
+          PROF(11);
+        }
+        named_bar_sync(3, 128);  // the stores below must not be in flight when the release drains the SM's stores
+      }
+      if (row_ok) {
+        float* gp = p.gates + row_t * (4 * HID) + j0;
+        st8(gp, o0);
+        st8(gp + HID, o1);
+        st8(gp + 2 * HID, o2);
+        st8(gp + 3 * HID, o3);
+        st8(p.c_all + (row_t + B) * HID + j0, state);
+        st8_bf16(p.h_out + row_t * HID + j0, hv);
+        if (t + 1 >= T) st8(p.h_last + (size_t)b * HID + j0, hv);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 long long* g_prof = nullptr;      // set by pvr_lstm_persist_profile()
 unsigned int* g_ready = nullptr;  // arrival counters (one launch at a time per process: stream ordered)
 size_t g_ready_words = 0;
@@ -595,12 +846,27 @@ int max_active_clusters(int grid) {
   return n;
 }
 
+int g_fwd2_blocks = -1;
+int fwd2_max_blocks() {
+  if (g_fwd2_blocks >= 0) return g_fwd2_blocks;
+  cudaFuncSetAttribute(lstm_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F2_SMEM_TOTAL);
+  int per_sm = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_fwd2_kernel, NTHREADS, F2_SMEM_TOTAL) !=
+      cudaSuccess) {
+    cudaGetLastError();
+    per_sm = 0;
+  }
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // one CTA per SM: each allocates all 512 TMEM columns
+  g_fwd2_blocks = per_sm > 0 ? sms : 0;
+  return g_fwd2_blocks;
+}
+
 bool shape_ok(int T, int B, int H) { return H == HID && T >= 1 && B >= 1 && B <= 128 && T <= 4096; }
 
-template <int BWD>
-int launch(const CUtensorMap& ta, const CUtensorMap& tw, const PersistParams& p, cudaStream_t st) {
-  const int grid = p.nbt * 16 * 4;
-  const size_t words = (size_t)(p.T + 1) * p.nbt * 16;
+// Arrival counters: grown on first use (never inside a stream capture), zeroed on the stream before every launch.
+int ensure_ready(size_t words, cudaStream_t st) {
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cap);
   if (words > g_ready_words) {
@@ -617,10 +883,18 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tw, const PersistParams& p,
       return PVR_ERR_CUDA;
     }
   }
+  cudaMemsetAsync(g_ready, 0, words * sizeof(unsigned int), st);
+  return PVR_OK;
+}
+
+template <int BWD>
+int launch(const CUtensorMap& ta, const CUtensorMap& tw, const PersistParams& p, cudaStream_t st) {
+  const int grid = p.nbt * 16 * 4;
+  const int rc = ensure_ready((size_t)(p.T + 1) * p.nbt * 16, st);
+  if (rc != PVR_OK) return rc;
   PersistParams q = p;
   q.ready = g_ready;
   q.prof = g_prof;
-  cudaMemsetAsync(g_ready, 0, words * sizeof(unsigned int), st);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
@@ -663,6 +937,16 @@ int lstm_persist_supported(int T, int B, int H) {
   return max_active_clusters<0>(clusters * 4) >= clusters && max_active_clusters<1>(clusters * 4) >= clusters;
 }
 
+// PVR_LSTM_FWD2=0 keeps the forward pass on the cluster kernel (A/B measurements).
+bool use_fwd2(int B) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("PVR_LSTM_FWD2");
+    off = (e && e[0] == '0') ? 1 : 0;
+  }
+  return !off && ((B + F2_NB - 1) / F2_NB) * 32 <= fwd2_max_blocks();
+}
+
 int lstm_persist_forward(const pvr_lstm_fwd* L, cudaStream_t st) {
   const int T = L->T, B = L->B;
   PersistParams p;
@@ -674,6 +958,25 @@ int lstm_persist_forward(const pvr_lstm_fwd* L, cudaStream_t st) {
   p.h_last = L->h_last;
   CUtensorMap ta, tw;
   const char* err = nullptr;
+  if (use_fwd2(B)) {
+    p.nbt = (B + F2_NB - 1) / F2_NB;
+    if (!make_tmap_kchunks(&ta, L->hm, HID, (uint64_t)T * B, HID, F2_NB, F2_CPI, &err)) {
+      pvr_set_error("pvr_lstm_persist_forward: tensor map: %s", err ? err : "?");
+      return PVR_ERR_CUDA;
+    }
+    const int rc = ensure_ready((size_t)(T + 1) * p.nbt * 16, st);
+    if (rc != PVR_OK) return rc;
+    p.ready = g_ready;
+    p.prof = g_prof;
+    mask_state_bf16_kernel<<<(B * HID + 255) / 256, 256, 0, st>>>(L->h0, L->nd, B, HID, p.hm);
+    lstm_fwd2_kernel<<<p.nbt * 32, NTHREADS, F2_SMEM_TOTAL, st>>>(ta, static_cast<const __nv_bfloat16*>(L->w_hh), p);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      pvr_set_error("pvr_lstm_fwd2 launch: %s", cudaGetErrorString(e));
+      return PVR_ERR_CUDA;
+    }
+    return PVR_OK;
+  }
   if (!make_tmap_kchunks(&ta, L->hm, HID, (uint64_t)T * B, HID, 64, CPI, &err) ||
       !make_tmap_2d(&tw, L->w_hh, HID, 4 * HID, HID, 64, &err)) {
     pvr_set_error("pvr_lstm_persist_forward: tensor map: %s", err ? err : "?");

@@ -816,6 +816,301 @@ lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __nv_bfloat16
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward recurrence, second form: dh_{t}[b, j] = sum_k dG_{t+1}[b, k] W_hh[k, j] with W_hh^T in tensor memory.
+//
+// CTA (J, q) of a cluster of 4 owns hidden units 128 J .. + 128 as the M = 128 rows of the A operand and gate q's 1024
+// columns of dG as its K slice (960 in TMEM + 64 in shared memory, as in the forward kernel); the B operand is a batch
+// tile of 32 rows of dG_{t+1} (64 KB per step instead of 128). The four partial (128 x 32) sums of a cluster are
+// reduce-scattered through distributed shared memory: TMEM lane quadrant w (units 32 w .. + 32) goes to CTA w, which
+// adds the four pieces and runs the cell update for those 32 units x 32 batch rows. 8 J x 4 q = 32 CTAs per batch tile.
+constexpr int B2_PITCH = 33;
+constexpr int B2_PIECE_BYTES = 32 * B2_PITCH * 4;    // (32 units x 32 batch rows) fp32, padded rows: 4224
+constexpr int B2_SMEM_RECV = 4 * B2_PIECE_BYTES;     // [source CTA][unit][batch row]
+constexpr int B2_SMEM_STAGE = 4 * B2_PIECE_BYTES;    // [destination CTA][unit][batch row]
+constexpr int B2_SMEM_TOTAL = F2_SMEM_B + F2_SMEM_WT + B2_SMEM_RECV + B2_SMEM_STAGE + 256 + 1024;
+static_assert(B2_PIECE_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __nv_bfloat16* __restrict__ w_hh_t,
+                 const PersistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;
+  uint8_t* sWt = smem + F2_SMEM_B;
+  float* sRecv = reinterpret_cast<float*>(sWt + F2_SMEM_WT);
+  float* sStage = reinterpret_cast<float*>(sWt + F2_SMEM_WT + B2_SMEM_RECV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sWt + F2_SMEM_WT + B2_SMEM_RECV + B2_SMEM_STAGE);
+  uint64_t* full = bars;             // [F2_NG]
+  uint64_t* empty = bars + F2_NG;    // [F2_NG]
+  uint64_t* acc_full = bars + 2 * F2_NG;
+  uint64_t* acc_empty = acc_full + 1;
+  uint64_t* xchg = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t q = cluster_ctarank();
+  const int cl = blockIdx.x >> 2;
+  const int bt = cl >> 3, J = cl & 7;
+  const int T = p.T, B = p.B, nbt = p.nbt;
+  const int rot = J & (F2_NG - 1);
+
+  if (threadIdx.x == 0) {
+    for (int g = 0; g < F2_NG; ++g) {
+      mbar_init(&full[g], 1);
+      mbar_init(&empty[g], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    mbar_init(xchg, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmap_a);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp >= 2) {
+    // row r of the slice = row 128 J + r of W_hh^T (4096 columns), columns 1024 q .. + 1024
+    const int ew = warp & 3;
+    const int r = 32 * ew + lane;
+    const __nv_bfloat16* wrow = w_hh_t + (size_t)(128 * J + r) * (4 * HID) + 1024 * (int)q;
+    const uint32_t ta = tmem + ((uint32_t)(32 * ew) << 16) + 32;
+#pragma unroll 6
+    for (int ks = 0; ks < F2_KT * 4; ++ks) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(wrow + 16 * ks));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(wrow + 16 * ks) + 1);
+      const uint32_t pk[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      tmem_st_32x32b_x8(ta + 8 * ks, pk);
+    }
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(wrow + 64 * F2_KT) + q8);
+      *reinterpret_cast<uint4*>(sWt + r * 128 + ((q8 ^ (r & 7)) << 4)) = v;
+    }
+    tmem_wait_st();
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();  // the peers' barriers exist before anything arrives on them remotely
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    for (int s = 1; s < T; ++s) {
+      const int src_t = T - s;  // time index of the operand rows (dG_{t+1}, t = T - 1 - s)
+      const unsigned int* flags = p.ready + ((size_t)src_t * nbt + bt) * 16;
+      const int a_row = src_t * B + F2_NB * bt;
+      for (int k = 0; k < F2_NG; ++k) {
+        const int g = (k + rot) & (F2_NG - 1);
+        mbar_wait(&empty[g], ((uint32_t)s & 1u));  // step s = 1 is the first use (parity 1 passes at once)
+        {
+          uint32_t polls = 0;
+          uint64_t t0 = 0;
+          for (;;) {
+            unsigned int v = 2;
+            if (lane < F2_CPI) v = ld_acquire_gpu(flags + F2_CPI * g + lane);
+            if (__all_sync(0xffffffffu, v >= 2u)) break;
+            if ((++polls & 63u) == 0) {
+              const uint64_t now = globaltimer_ns();
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > 4000000000ull) {
+                if (lane == 0)
+                  printf("pvr: lstm_bwd2 step %d group %d never became ready (block %d)\n", s, g, (int)blockIdx.x);
+                __trap();
+              }
+            }
+          }
+        }
+        if (lane == 0 && k == 0) PROF(0);
+        fence_proxy_async_global();
+        if (elect_one()) {
+          mbar_expect_tx(&full[g], F2_CPI * F2_CHUNK_BYTES);
+          tma_load_3d(&tmap_a, &full[g], sB + g * F2_CPI * F2_CHUNK_BYTES, 0, a_row, 16 * (int)q + F2_CPI * g);
+        }
+        __syncwarp();
+        if (lane == 0 && k == F2_NG - 1) PROF(2);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, F2_NB);
+    const uint64_t wt_desc = umma_desc_sw128(smem_u32(sWt));
+    for (int s = 1; s < T; ++s) {
+      mbar_wait(acc_empty, (uint32_t)s & 1u);  // the previous step's accumulator has been read
+      tc_fence_after();
+      for (int k = 0; k < F2_NG; ++k) {
+        const int g = (k + rot) & (F2_NG - 1);
+        mbar_wait(&full[g], ((uint32_t)s & 1u) ^ 1u);
+        tc_fence_after();
+        if (lane == 0 && k == 0) PROF(3);
+        if (lane == 0 && k == F2_NG - 1) PROF(4);
+        if (elect_one()) {
+#pragma unroll
+          for (int cc = 0; cc < F2_CPI; ++cc) {
+            const int kc = F2_CPI * g + cc;
+            const uint64_t bd = umma_desc_sw128(smem_u32(sB + kc * F2_CHUNK_BYTES));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t acc = (k | cc | kk) != 0 ? 1u : 0u;
+              if (kc < F2_KT) umma_bf16_ts(tmem, tmem + 32 + 8 * (4 * kc + kk), bd + 2 * kk, idesc, acc);
+              else umma_bf16(tmem, wt_desc + 2 * kk, bd + 2 * kk, idesc, acc);
+            }
+          }
+          umma_commit(&empty[g]);
+          if (k == F2_NG - 1) umma_commit(acc_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ exchange + cell (128 threads)
+    const int e = threadIdx.x - 64;
+    const int ew = warp & 3;            // TMEM lane quadrant of this warp = the cluster rank its piece goes to
+    const int crow = e >> 2, ug = e & 3;
+    const int b = F2_NB * bt + crow;
+    const bool row_ok = b < B;
+    const int j0 = 128 * J + 32 * (int)q + 8 * ug;  // first of this thread's 8 hidden units
+    const uint32_t recv_base = smem_u32(sRecv);
+    const uint32_t xchg_addr = smem_u32(xchg);
+    float state[8], dh_last[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) state[u] = dh_last[u] = 0.f;
+    if (row_ok) {
+      ld8_coherent(p.dc_rec + (size_t)b * HID + j0, state);
+      ld8_coherent(p.dh_rec + (size_t)b * HID + j0, dh_last);
+    }
+    float bsum[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bsum[i] = 0.f;
+    uint32_t xphase = 0;
+    for (int s = 0; s < T; ++s) {
+      const int t = T - 1 - s;
+      const bool has_gemm = s > 0;
+      const size_t row_t = (size_t)t * B + b;
+      float op[32], cp[8], cc[8], dho[8];
+      float nd_t = 0.f, nd_n = 0.f;
+      if (row_ok) {
+        nd_t = __ldg(p.nd + row_t);
+        if (t + 1 < T) nd_n = __ldg(p.nd + row_t + B);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ld8(p.gates + row_t * (4 * HID) + g * HID + j0, op + 8 * g);
+        ld8(p.c_all + row_t * HID + j0, cp);
+        ld8(p.c_all + (row_t + B) * HID + j0, cc);
+        if (p.dh_out) ld8(p.dh_out + row_t * HID + j0, dho);
+        else {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dho[u] = 0.f;
+        }
+      }
+      float G[32];
+      if (has_gemm) {
+        mbar_wait(acc_full, ((uint32_t)s & 1u) ^ 1u);
+        tc_fence_after();
+        if (e == 0) PROF(5);
+        {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem + ((uint32_t)(32 * ew) << 16), v);
+          tmem_wait_ld();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+          // this warp's (32 units x 32 batch rows) piece belongs to CTA ew: straight into the own receive buffer, or
+          // staged for the copy
+          float* dstp = (ew == (int)q ? sRecv + (int)q * (32 * B2_PITCH) : sStage + ew * (32 * B2_PITCH)) +
+                        lane * B2_PITCH;
+#pragma unroll
+          for (int n = 0; n < 32; ++n) dstp[n] = __uint_as_float(v[n]);
+        }
+        fence_proxy_async();  // generic-proxy writes to shared memory -> visible to the bulk-copy engine
+        __syncwarp();
+        if (lane == 0 && ew != (int)q)
+          bulk_copy_to_peer(mapa(recv_base + q * B2_PIECE_BYTES, (uint32_t)ew),
+                            smem_u32(sStage) + (uint32_t)ew * B2_PIECE_BYTES, B2_PIECE_BYTES,
+                            mapa(xchg_addr, (uint32_t)ew));
+        if (e == 0) {
+          mbar_expect_tx(xchg, 3 * B2_PIECE_BYTES);
+          PROF(6);
+        }
+        named_bar_sync(2, 128);  // the own piece is in sRecv (written by warp quadrant q)
+        mbar_wait_cluster(xchg, xphase);
+        if (e == 0) PROF(7);
+        xphase ^= 1u;
+#pragma unroll
+        for (int src = 0; src < 4; ++src) {
+          const float* rp = sRecv + src * (32 * B2_PITCH) + (8 * ug) * B2_PITCH + crow;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) G[8 * src + u] = rp[u * B2_PITCH];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) G[i] = 0.f;
+      }
+      const bool publish = t > 0;
+      if (row_ok) {
+        float o0[8], o1[8], o2[8], o3[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float rec = has_gemm ? nd_n * ((G[u] + G[8 + u]) + (G[16 + u] + G[24 + u])) : dh_last[u];
+          const float dh = dho[u] + rec;
+          const float i = op[u], f = op[8 + u], g = op[16 + u], o = op[24 + u];
+          const float tc = tanh_fast(cc[u]);
+          const float dc = state[u] + dh * o * (1.f - tc * tc);
+          const float cpm = nd_t * cp[u];
+          o0[u] = dc * g * i * (1.f - i);
+          o1[u] = dc * cpm * f * (1.f - f);
+          o2[u] = dc * i * (1.f - g * g);
+          o3[u] = dh * tc * o * (1.f - o);
+          state[u] = dc * f * nd_t;
+          bsum[u] += o0[u]; bsum[8 + u] += o1[u]; bsum[16 + u] += o2[u]; bsum[24 + u] += o3[u];
+        }
+        __nv_bfloat16* dp = p.dG + row_t * (4 * HID) + j0;
+        st8_bf16(dp, o0);
+        st8_bf16(dp + HID, o1);
+        st8_bf16(dp + 2 * HID, o2);
+        st8_bf16(dp + 3 * HID, o3);
+      }
+      if (e == 0) PROF(8);
+      if (publish) {
+        fence_proxy_async_global();
+        named_bar_sync(1, 128);
+        if (e == 0) {
+          PROF(9);
+          // 64-unit chunk 2 J + (q >> 1) of time t: written by this CTA and its neighbour of the cluster
+          red_release_gpu_add(p.ready + ((size_t)t * nbt + bt) * 16 + 2 * J + ((int)q >> 1), 1u);
+          PROF(11);
+        }
+      }
+    }
+    if (p.dbias) {
+      // bias gradient: lanes with the same (lane & 3) hold the same 8 units for 8 different batch rows
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float v = bsum[i];
+#pragma unroll
+        for (int o = 16; o >= 4; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane < 4) atomicAdd(p.dbias + (i >> 3) * HID + j0 + (i & 7), v);
+      }
+    }
+    if (row_ok) {
+      st8(p.dc_rec + (size_t)b * HID + j0, state);
+      float z[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) z[u] = 0.f;
+      st8(p.dh_rec + (size_t)b * HID + j0, z);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves while a peer may still write into its shared memory
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 long long* g_prof = nullptr;      // set by pvr_lstm_persist_profile()
 unsigned int* g_ready = nullptr;  // arrival counters (one launch at a time per process: stream ordered)
 size_t g_ready_words = 0;
@@ -861,6 +1156,35 @@ int fwd2_max_blocks() {
   // one CTA per SM: each allocates all 512 TMEM columns
   g_fwd2_blocks = per_sm > 0 ? sms : 0;
   return g_fwd2_blocks;
+}
+
+int g_bwd2_clusters = -1;
+void bwd2_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* attr, int grid, cudaStream_t st) {
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->gridDim = dim3(grid);
+  cfg->blockDim = dim3(NTHREADS);
+  cfg->dynamicSmemBytes = B2_SMEM_TOTAL;
+  cfg->stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 4;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg->attrs = attr;
+  cfg->numAttrs = 1;
+}
+int bwd2_max_clusters() {
+  if (g_bwd2_clusters >= 0) return g_bwd2_clusters;
+  cudaFuncSetAttribute(lstm_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, B2_SMEM_TOTAL);
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  bwd2_config(&cfg, attr, 128, 0);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, lstm_bwd2_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  g_bwd2_clusters = n;
+  return n;
 }
 
 bool shape_ok(int T, int B, int H) { return H == HID && T >= 1 && B >= 1 && B <= 128 && T <= 4096; }
@@ -986,6 +1310,16 @@ int lstm_persist_forward(const pvr_lstm_fwd* L, cudaStream_t st) {
   return launch<0>(ta, tw, p, st);
 }
 
+// PVR_LSTM_BWD2=0 keeps the backward pass on the first cluster kernel (A/B measurements).
+bool use_bwd2(int B) {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("PVR_LSTM_BWD2");
+    off = (e && e[0] == '0') ? 1 : 0;
+  }
+  return !off && ((B + F2_NB - 1) / F2_NB) * 8 <= bwd2_max_clusters();
+}
+
 int lstm_persist_backward(const pvr_lstm_bwd* L, cudaStream_t st) {
   const int T = L->T, B = L->B;
   PersistParams p;
@@ -997,6 +1331,27 @@ int lstm_persist_backward(const pvr_lstm_bwd* L, cudaStream_t st) {
   p.dbias = L->dbias;
   CUtensorMap ta, tw;
   const char* err = nullptr;
+  if (use_bwd2(B)) {
+    p.nbt = (B + F2_NB - 1) / F2_NB;
+    if (!make_tmap_kchunks(&ta, L->dG, 4 * HID, (uint64_t)T * B, 4 * HID, F2_NB, F2_CPI, &err)) {
+      pvr_set_error("pvr_lstm_persist_backward: tensor map: %s", err ? err : "?");
+      return PVR_ERR_CUDA;
+    }
+    const int rc = ensure_ready((size_t)(T + 1) * p.nbt * 16, st);
+    if (rc != PVR_OK) return rc;
+    p.ready = g_ready;
+    p.prof = g_prof;
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    bwd2_config(&cfg, attr, p.nbt * 32, st);
+    const cudaError_t e =
+        cudaLaunchKernelEx(&cfg, lstm_bwd2_kernel, ta, static_cast<const __nv_bfloat16*>(L->w_hh_t), p);
+    if (e != cudaSuccess) {
+      pvr_set_error("pvr_lstm_bwd2 launch: %s", cudaGetErrorString(e));
+      return PVR_ERR_CUDA;
+    }
+    return PVR_OK;
+  }
   if (!make_tmap_kchunks(&ta, L->dG, 4 * HID, (uint64_t)T * B, 4 * HID, 64, CPI, &err) ||
       !make_tmap_2d(&tw, L->w_hh_t, 4 * HID, HID, 4 * HID, 64, &err)) {
     pvr_set_error("pvr_lstm_persist_backward: tensor map: %s", err ? err : "?");

@@ -93,6 +93,23 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Wait until the `n` (<= 32) arrival counters at `flags` have all reached `need`: one ld.acquire.gpu per lane and
+// round trip. (Measured alternatives, both slower by ~1000 cycles per step: relaxed polls + one fence.acq_rel.gpu — the
+// fence drains every store the SM has in flight — and several acquire polls in flight per lane.)
+__device__ __forceinline__ bool wait_flags(const unsigned int* flags, int n, unsigned int need, int lane) {
+  uint64_t t0 = 0;
+  uint32_t polls = 0;
+  for (;;) {
+    unsigned int v = need;
+    if (lane < n) v = ld_acquire_gpu(flags + lane);
+    if (__all_sync(0xffffffffu, v >= need)) return true;
+    if ((++polls & 63u) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) return false;
+    }
+  }
+}
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   uint32_t r;
@@ -663,23 +680,10 @@ lstm_fwd2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __nv_bfloat16
       for (int k = 0; k < F2_NG; ++k) {
         const int g = (k + rot) & (F2_NG - 1);
         mbar_wait(&empty[g], ((uint32_t)s & 1u) ^ 1u);
-        if (s > 0) {  // the group's chunks must have been written by their producers (2 CTAs per chunk of 64 units)
-          uint32_t polls = 0;
-          uint64_t t0 = 0;
-          for (;;) {
-            unsigned int v = 2;
-            if (lane < F2_CPI) v = ld_acquire_gpu(flags + F2_CPI * g + lane);
-            if (__all_sync(0xffffffffu, v >= 2u)) break;
-            if ((++polls & 63u) == 0) {
-              const uint64_t now = globaltimer_ns();
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > 4000000000ull) {
-                if (lane == 0)
-                  printf("pvr: lstm_fwd2 step %d group %d never became ready (block %d)\n", s, g, (int)blockIdx.x);
-                __trap();
-              }
-            }
-          }
+        // the group's chunks must have been written by their producers (2 CTAs per chunk of 64 units)
+        if (s > 0 && !wait_flags(flags + F2_CPI * g, F2_CPI, 2u, lane)) {
+          if (lane == 0) printf("pvr: lstm_fwd2 step %d group %d never became ready (block %d)\n", s, g, (int)blockIdx.x);
+          __trap();
         }
         if (lane == 0 && k == 0) PROF(0);
         fence_proxy_async_global();  // rows written with st.global by other SMs; TMA reads them next
@@ -909,23 +913,9 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __nv_bfloat16
       for (int k = 0; k < F2_NG; ++k) {
         const int g = (k + rot) & (F2_NG - 1);
         mbar_wait(&empty[g], ((uint32_t)s & 1u));  // step s = 1 is the first use (parity 1 passes at once)
-        {
-          uint32_t polls = 0;
-          uint64_t t0 = 0;
-          for (;;) {
-            unsigned int v = 2;
-            if (lane < F2_CPI) v = ld_acquire_gpu(flags + F2_CPI * g + lane);
-            if (__all_sync(0xffffffffu, v >= 2u)) break;
-            if ((++polls & 63u) == 0) {
-              const uint64_t now = globaltimer_ns();
-              if (t0 == 0) t0 = now;
-              else if (now - t0 > 4000000000ull) {
-                if (lane == 0)
-                  printf("pvr: lstm_bwd2 step %d group %d never became ready (block %d)\n", s, g, (int)blockIdx.x);
-                __trap();
-              }
-            }
-          }
+        if (!wait_flags(flags + F2_CPI * g, F2_CPI, 2u, lane)) {
+          if (lane == 0) printf("pvr: lstm_bwd2 step %d group %d never became ready (block %d)\n", s, g, (int)blockIdx.x);
+          __trap();
         }
         if (lane == 0 && k == 0) PROF(0);
         fence_proxy_async_global();

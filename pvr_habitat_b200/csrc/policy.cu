@@ -300,6 +300,54 @@ __global__ void __launch_bounds__(256) heads_fwd_kernel(const __nv_bfloat16* __r
   }
 }
 
+// Same product with the (A + 1) weight rows staged in shared memory and 16-byte loads of h: a warp walks rows with a
+// grid stride, a lane owns 8 consecutive k per 256. K % 8 == 0.
+template <int MAXA>
+__global__ void __launch_bounds__(256) heads_fwd_staged_kernel(const __nv_bfloat16* __restrict__ h, int m, int K,
+                                                                const float* __restrict__ Wp,
+                                                                const float* __restrict__ bp,
+                                                                const float* __restrict__ Wb,
+                                                                const float* __restrict__ bb, int A,
+                                                                float* __restrict__ logits,
+                                                                float* __restrict__ baseline) {
+  extern __shared__ float sw[];  // [(A + 1)][K]: policy rows, then the baseline row
+  for (int i = threadIdx.x; i < (A + 1) * K; i += 256) sw[i] = i < A * K ? Wp[i] : Wb[i - A * K];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int row = blockIdx.x * 8 + (threadIdx.x >> 5); row < m; row += gridDim.x * 8) {
+    float acc[MAXA + 1];
+#pragma unroll
+    for (int a = 0; a <= MAXA; ++a) acc[a] = 0.f;
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(h + (long long)row * K + k);
+      float hv[8];
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hv[2 * j] = __uint_as_float(w4[j] << 16);
+        hv[2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int a = 0; a <= MAXA; ++a) {
+        const int ra = a < MAXA ? a : A;  // slot MAXA = the baseline row
+        if (a < MAXA && a >= A) continue;
+        const float4 w0 = *reinterpret_cast<const float4*>(sw + ra * K + k);
+        const float4 w1 = *reinterpret_cast<const float4*>(sw + ra * K + k + 4);
+        acc[a] += hv[0] * w0.x + hv[1] * w0.y + hv[2] * w0.z + hv[3] * w0.w + hv[4] * w1.x + hv[5] * w1.y +
+                  hv[6] * w1.z + hv[7] * w1.w;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a <= MAXA; ++a) acc[a] = warp_sum(acc[a]);
+    if (lane == 0) {
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < A) logits[(long long)row * A + a] = acc[a] + bp[a];
+      baseline[row] = acc[MAXA] + bb[0];
+    }
+  }
+}
+
 // Mean softmax cross-entropy over rows (main_bc_2.py:211-214) and its gradient. One thread per row for the softmax
 // over A actions, warp-shuffle + one atomic per warp for the loss sum.
 __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ logits, const long long* __restrict__ tgt,
@@ -377,6 +425,64 @@ __global__ void __launch_bounds__(256) heads_bwd_dw_kernel(const float* __restri
   }
 }
 
+// Same sums with 16-byte loads of h: a thread owns 8 consecutive k, a block 128 such threads (1024 k) x 2 row lanes.
+// grid (ceil(K / 1024), row chunks). K % 8 == 0.
+template <int MAXA>
+__global__ void __launch_bounds__(256) heads_bwd_dw8_kernel(const float* __restrict__ dl,
+                                                             const __nv_bfloat16* __restrict__ h, int m, int K, int A,
+                                                             int rows_per_block, float scale, float* __restrict__ dWp,
+                                                             float* __restrict__ dbp) {
+  __shared__ float sh[128][8 * MAXA + 1];
+  const int kt = threadIdx.x & 127, rl = threadIdx.x >> 7;
+  const int k = blockIdx.x * 1024 + kt * 8;
+  const int r0 = blockIdx.y * rows_per_block, r1 = min(m, r0 + rows_per_block);
+  float acc[MAXA][8];
+  float bacc = 0.f;
+#pragma unroll
+  for (int a = 0; a < MAXA; ++a)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+  if (k < K) {
+#pragma unroll 4
+    for (int r = r0 + rl; r < r1; r += 2) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(h + (long long)r * K + k);
+      const uint32_t w4[4] = {raw.x, raw.y, raw.z, raw.w};
+      float hv[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hv[2 * j] = __uint_as_float(w4[j] << 16);
+        hv[2 * j + 1] = __uint_as_float(w4[j] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int a = 0; a < MAXA; ++a)
+        if (a < A) {
+          const float g = __ldg(dl + (long long)r * A + a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[a][j] += g * hv[j];
+          if (blockIdx.x == 0 && kt == a) bacc += g;  // bias gradient, once
+        }
+    }
+  }
+  if (rl == 1) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sh[kt][a * 8 + j] = acc[a][j];
+    sh[kt][8 * MAXA] = bacc;
+  }
+  __syncthreads();
+  if (rl == 0 && k < K) {
+#pragma unroll
+    for (int a = 0; a < MAXA; ++a)
+      if (a < A) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          atomicAdd(&dWp[(long long)a * K + k + j], (acc[a][j] + sh[kt][a * 8 + j]) * scale);
+      }
+    if (blockIdx.x == 0 && kt < A) atomicAdd(&dbp[kt], (bacc + sh[kt][8 * MAXA]) * scale);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- reductions / layout
 // out[n] += sum_m y[m][n]  (bias gradients), y bf16.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ y, long long ldy, int m,
@@ -429,6 +535,44 @@ __global__ void __launch_bounds__(256) cast_weight_kernel(const float* __restric
     if (c0 + i < cols && r0 + tx < rows) wt[(long long)(c0 + i) * ldt + r0 + tx] = __float2bfloat16_rn(t[tx][i]);
 }
 
+// Same copies on 64 x 64 tiles with 16-byte loads and 8-byte stores (rows, cols, ldb, ldt multiples of 4).
+__global__ void __launch_bounds__(256) cast_weight64_kernel(const float* __restrict__ w, int rows, int cols,
+                                                             __nv_bfloat16* __restrict__ wb, long long ldb,
+                                                             __nv_bfloat16* __restrict__ wt, long long ldt) {
+  __shared__ float t[64][65];
+  const int c0 = blockIdx.x * 64, r0 = blockIdx.y * 64;
+  const int q = (threadIdx.x & 15) * 4, l = threadIdx.x >> 4;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int r = r0 + it * 16 + l, c = c0 + q;
+    if (r < rows && c < cols) {
+      const float4 v = *reinterpret_cast<const float4*>(w + (long long)r * cols + c);
+      t[it * 16 + l][q] = v.x; t[it * 16 + l][q + 1] = v.y; t[it * 16 + l][q + 2] = v.z; t[it * 16 + l][q + 3] = v.w;
+      if (wb) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&a);
+        o.y = *reinterpret_cast<const uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(wb + (long long)r * ldb + c) = o;
+      }
+    }
+  }
+  if (!wt) return;
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int cc = it * 16 + l;  // column of w = row of the transposed copy
+    if (c0 + cc < cols && r0 + q < rows) {
+      const __nv_bfloat162 a = __floats2bfloat162_rn(t[q][cc], t[q + 1][cc]);
+      const __nv_bfloat162 b = __floats2bfloat162_rn(t[q + 2][cc], t[q + 3][cc]);
+      uint2 o;
+      o.x = *reinterpret_cast<const uint32_t*>(&a);
+      o.y = *reinterpret_cast<const uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(wt + (long long)(c0 + cc) * ldt + r0 + q) = o;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- optimizer
 struct TensorList {
   float* p[32];
@@ -444,10 +588,21 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const TensorList tl, double*
   const int t = blockIdx.y;
   const float* g = tl.g[t];
   const long long n = tl.n[t];
+  const bool vec = (reinterpret_cast<uintptr_t>(g) & 15) == 0;
+  if ((long long)blockIdx.x * blockDim.x * (vec ? 4 : 1) >= n) return;  // small tensors: no idle blocks / atomics
   double s = 0.0;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const double v = (double)g[i];
-    s += v * v;
+  const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    // 16-byte loads, squares and sums in double as in the scalar loop
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+#pragma unroll 4
+    for (long long i = i0; i < (n >> 2); i += stride) {
+      const float4 v = g4[i];
+      s += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    for (long long i = (n & ~3ll) + i0; i < n; i += stride) s += (double)g[i] * g[i];
+  } else {
+    for (long long i = i0; i < n; i += stride) s += (double)g[i] * g[i];
   }
   s = warp_sum_d(s);
   __shared__ double sh[8];
@@ -648,8 +803,15 @@ extern "C" int pvr_heads_forward(const void* h_bf16, int m, int K, const float* 
     pvr_set_error("pvr_heads_forward: invalid argument (A <= 8, K %% 64 == 0)");
     return PVR_ERR_ARG;
   }
-  heads_fwd_kernel<8><<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      static_cast<const __nv_bfloat16*>(h_bf16), m, K, Wp, bp, Wb, bb, A, logits, baseline);
+  const size_t stage_bytes = (size_t)(A + 1) * K * sizeof(float);
+  if (stage_bytes <= 48 * 1024 && (reinterpret_cast<uintptr_t>(h_bf16) & 15) == 0) {
+    const int blocks = (m + 7) / 8 < 296 ? (m + 7) / 8 : 296;
+    heads_fwd_staged_kernel<8><<<blocks, 256, stage_bytes, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const __nv_bfloat16*>(h_bf16), m, K, Wp, bp, Wb, bb, A, logits, baseline);
+  } else {
+    heads_fwd_kernel<8><<<(m + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        static_cast<const __nv_bfloat16*>(h_bf16), m, K, Wp, bp, Wb, bb, A, logits, baseline);
+  }
   PVR_LAUNCH_CHECK("pvr_heads_forward");
   return PVR_OK;
 }
@@ -677,10 +839,20 @@ extern "C" int pvr_heads_backward(const float* dlogits, const void* h_bf16, cons
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   heads_bwd_dh_kernel<<<148 * 8, 256, 0, st>>>(dlogits, Wp, m, K, A, scale, dh);
   PVR_LAUNCH_CHECK("pvr_heads_backward(dh)");
-  const int rpb = rows_per_block_for(m);
-  dim3 grid((K + 31) / 32, (m + rpb - 1) / rpb);
-  heads_bwd_dw_kernel<8><<<grid, 256, 0, st>>>(dlogits, static_cast<const __nv_bfloat16*>(h_bf16), m, K, A, rpb, scale,
-                                               dWp, dbp);
+  if (K % 8 == 0 && (reinterpret_cast<uintptr_t>(h_bf16) & 15) == 0) {
+    const int kblocks = (K + 1023) / 1024;
+    int chunks = 296 / kblocks;
+    if (chunks > (m + 15) / 16) chunks = (m + 15) / 16;
+    const int rpb = (m + chunks - 1) / chunks;
+    dim3 grid(kblocks, (m + rpb - 1) / rpb);
+    heads_bwd_dw8_kernel<8><<<grid, 256, 0, st>>>(dlogits, static_cast<const __nv_bfloat16*>(h_bf16), m, K, A, rpb,
+                                                  scale, dWp, dbp);
+  } else {
+    const int rpb = rows_per_block_for(m);
+    dim3 grid((K + 31) / 32, (m + rpb - 1) / rpb);
+    heads_bwd_dw_kernel<8><<<grid, 256, 0, st>>>(dlogits, static_cast<const __nv_bfloat16*>(h_bf16), m, K, A, rpb,
+                                                 scale, dWp, dbp);
+  }
   PVR_LAUNCH_CHECK("pvr_heads_backward(dW)");
   return PVR_OK;
 }
@@ -717,9 +889,18 @@ extern "C" int pvr_cast_weight(const float* w, int rows, int cols, void* w_bf16,
     pvr_set_error("pvr_cast_weight: invalid argument");
     return PVR_ERR_ARG;
   }
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
-  cast_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
-      w, rows, cols, static_cast<__nv_bfloat16*>(w_bf16), ldb, static_cast<__nv_bfloat16*>(wt_bf16), ldt);
+  const bool vec = rows % 4 == 0 && cols % 4 == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                   (!w_bf16 || (ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(w_bf16) & 7) == 0)) &&
+                   (!wt_bf16 || (ldt % 4 == 0 && (reinterpret_cast<uintptr_t>(wt_bf16) & 7) == 0));
+  if (vec) {
+    dim3 grid((cols + 63) / 64, (rows + 63) / 64);
+    cast_weight64_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        w, rows, cols, static_cast<__nv_bfloat16*>(w_bf16), ldb, static_cast<__nv_bfloat16*>(wt_bf16), ldt);
+  } else {
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+    cast_weight_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        w, rows, cols, static_cast<__nv_bfloat16*>(w_bf16), ldb, static_cast<__nv_bfloat16*>(wt_bf16), ldt);
+  }
   PVR_LAUNCH_CHECK("pvr_cast_weight");
   return PVR_OK;
 }
@@ -738,7 +919,7 @@ extern "C" int pvr_optim_sumsq(const float* const* grads, const int64_t* sizes, 
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   cudaMemsetAsync(sumsq, 0, sizeof(double), st);
-  sumsq_kernel<<<dim3(64, count), 256, 0, st>>>(tl, sumsq);
+  sumsq_kernel<<<dim3(148, count), 256, 0, st>>>(tl, sumsq);
   PVR_LAUNCH_CHECK("pvr_optim_sumsq");
   return PVR_OK;
 }

@@ -735,7 +735,11 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   p.M = d->m;
   p.pdl = (d->flags & PVR_GEMM_PDL) != 0;
   p.num_m_tiles = (d->m + 127) / 128;
-  int block_n = pick_block_n(d->n_pad, (long long)p.num_m_tiles * split_k, sms, 0, d->res != nullptr);
+  // (ResNet's residual layers are HBM-bound and stay at N <= 128; a long-K GEMM with a mask / residual operand — the
+  // policy's dZ = (dG W^T) * (H > 0), K = 4096 — is tensor-bound and takes the 256-wide tile)
+  static const int res256 = getenv("PVR_RES_N256") ? atoi(getenv("PVR_RES_N256")) : 1;
+  const bool narrow_res = d->res != nullptr && !(res256 && d->k >= 2048 && d->out_f32 == 0);
+  int block_n = pick_block_n(d->n_pad, (long long)p.num_m_tiles * split_k, sms, 0, narrow_res);
   if (d->out_f32 == 2 && block_n > 128) block_n = 128;
   // Weight-gradient GEMMs (MN-major operands, e.g. 4096 x 1024 outputs over K = T*B): 256-wide tiles even when they
   // leave a few SMs idle (128 tiles on 148 SMs) — at N = 128 a single CTA reads A + W at the shared-memory port limit
@@ -743,6 +747,11 @@ extern "C" int pvr_gemm(const pvr_gemm_desc* d, void* stream) {
   if (mn && block_n == 128 && d->n_pad % 256 == 0 && (long long)p.num_m_tiles * (d->n_pad / 256) * 5 >= (long long)sms * 4 &&
       !getenv("PVR_WGRAD_N128"))
     block_n = 256;
+  // ... and 128-wide ones rather than 64 when they fill >= 80 % of the SMs in one wave (dW1: 8 x 16 tiles): a 64-wide
+  // tile is bound by the shared-memory port at 2/3 of the tensor rate
+  if (mn && block_n == 64 && d->n_pad % 128 == 0 && (long long)p.num_m_tiles * (d->n_pad / 128) * 5 >= (long long)sms * 4 &&
+      !getenv("PVR_WGRAD_N128"))
+    block_n = 128;
   // CTA pairs (cta_group::2, 256 x 256 tiles) for wide bf16-output GEMMs with enough K: ViT QKV / fc1
   static const bool pair_ok = !(getenv("PVR_CTA2") && atoi(getenv("PVR_CTA2")) == 0);
   static const int pair_f32 = getenv("PVR_PAIR_F32") ? atoi(getenv("PVR_PAIR_F32")) : 1;

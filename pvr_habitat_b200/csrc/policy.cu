@@ -841,7 +841,8 @@ extern "C" int pvr_heads_backward(const float* dlogits, const void* h_bf16, cons
   PVR_LAUNCH_CHECK("pvr_heads_backward(dh)");
   if (K % 8 == 0 && (reinterpret_cast<uintptr_t>(h_bf16) & 15) == 0) {
     const int kblocks = (K + 1023) / 1024;
-    int chunks = 296 / kblocks;
+    // few row chunks: every block ends with 8 A atomics per thread, which cost more than its share of the rows
+    int chunks = 64 / kblocks > 0 ? 64 / kblocks : 1;
     if (chunks > (m + 15) / 16) chunks = (m + 15) / 16;
     const int rpb = (m + chunks - 1) / chunks;
     dim3 grid(kblocks, (m + rpb - 1) / rpb);

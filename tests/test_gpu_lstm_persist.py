@@ -58,7 +58,7 @@ def _forward_ref(w_hh, xp, nd, h0, c0, T, B):
     return torch.cat(gates), torch.cat(cs), torch.cat(hs)
 
 
-@pytest.mark.parametrize("T,B", [(3, 128), (64, 128), (16, 64), (20, 16), (7, 40), (5, 100)])
+@pytest.mark.parametrize("T,B", [(3, 128), (64, 128), (16, 64), (20, 16), (7, 40), (5, 100), (1, 16), (2, 33)])
 def test_persistent_forward_vs_torch(T, B):
     assert _lib.lib().pvr_lstm_persist_supported(T, B, H) == 1, "persistent kernels not available on this device"
     w_hh, xp, nd, h0, c0 = _problem(T, B, 100 * T + B)
@@ -75,14 +75,14 @@ def test_persistent_forward_vs_torch(T, B):
         assert float((out["hm"][B:].float() - want).abs().max()) < 1e-2
 
 
-def _backward_cuda(w_hh, nd, gates, c_all, dh_out, T, B, flags=0):
+def _backward_cuda(w_hh, nd, gates, c_all, dh_out, T, B, flags=0, dbias=None):
     f32, bf = torch.float32, torch.bfloat16
     w_hh_t = w_hh.t().contiguous()
     dh_rec, dc_rec = torch.zeros(B, H, device="cuda"), torch.zeros(B, H, device="cuda")
     dG = torch.zeros(T * B, 4 * H, dtype=bf, device="cuda")
     L = pvr_lstm_bwd(T=T, B=B, H=H, flags=flags, w_hh_t=w_hh_t.data_ptr(), nd=nd.data_ptr(), gates=gates.data_ptr(),
                      c_all=c_all.data_ptr(), dh_out=dh_out.data_ptr(), dh_rec=dh_rec.data_ptr(),
-                     dc_rec=dc_rec.data_ptr(), dG=dG.data_ptr())
+                     dc_rec=dc_rec.data_ptr(), dG=dG.data_ptr(), dbias=dbias.data_ptr() if dbias is not None else None)
     _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(L), _lib.current_stream_ptr()), "pvr_lstm_backward")
     torch.cuda.synchronize()
     return dG
@@ -106,16 +106,20 @@ def _backward_ref(w_hh, nd, gates, c_all, dh_out, T, B):
     return torch.cat(out)
 
 
-@pytest.mark.parametrize("T,B", [(3, 128), (64, 128), (16, 64), (20, 16), (7, 40)])
+@pytest.mark.parametrize("T,B", [(3, 128), (64, 128), (16, 64), (20, 16), (7, 40), (5, 100), (1, 16), (2, 33)])
 def test_persistent_backward_vs_torch(T, B):
     w_hh, xp, nd, h0, c0 = _problem(T, B, 7 * T + B)
     gates, cs, hs = _forward_ref(w_hh, xp, nd, h0, c0, T, B)
     g = torch.Generator(device="cuda").manual_seed(5)
     dh_out = torch.randn(T * B, H, generator=g, device="cuda") * 0.1
-    dG = _backward_cuda(w_hh, nd, gates.contiguous(), cs.contiguous(), dh_out, T, B).float()
+    dbias = torch.full((4 * H,), 0.25, device="cuda")  # accumulated into: the kernel adds the sum over (t, b) of dG
+    dG = _backward_cuda(w_hh, nd, gates.contiguous(), cs.contiguous(), dh_out, T, B, dbias=dbias).float()
     ref = _backward_ref(w_hh, nd, gates, cs, dh_out, T, B)
     rel = float((dG - ref).norm() / ref.norm())
     assert rel < 6e-3, rel  # bf16 rounding of the stored dG (2^-9 relative) dominates
+    ref_b = ref.double().sum(0)
+    rel_b = float(((dbias.double() - 0.25) - ref_b).norm() / ref_b.norm())
+    assert rel_b < 2e-3, rel_b  # summed in fp32 before the bf16 rounding of dG
 
 
 def test_persistent_equals_per_step_kernels():
@@ -162,4 +166,27 @@ def test_persistent_is_deterministic_and_fast():
     torch.cuda.synchronize()
     us_per_step = ev[0].elapsed_time(ev[1]) * 1e3 / 10 / T
     print(f"persistent forward: {us_per_step:.2f} us per time step (T = {T}, B = {B})")
-    assert us_per_step < 9.5  # the per-step kernels take 13 us (GEMM 8.5 + cell 4.5); measured 7.6 us (round 2)
+    # per-step kernels: 13 us (GEMM 8.5 + cell 4.5); cluster kernel with W_hh in shared memory: 7.6 us; W_hh in tensor
+    # memory: 4.5 us
+    assert us_per_step < 6.0
+    gates, c_all = a["gates"], a["c_all"]
+    dh_out = torch.randn(T * B, H, device="cuda") * 0.1
+    w_hh_t = w_hh.t().contiguous()
+    dh_rec, dc_rec = torch.zeros(B, H, device="cuda"), torch.zeros(B, H, device="cuda")
+    dG = torch.zeros(T * B, 4 * H, dtype=bf, device="cuda")
+    Lb = pvr_lstm_bwd(T=T, B=B, H=H, flags=0, w_hh_t=w_hh_t.data_ptr(), nd=nd.data_ptr(), gates=gates.data_ptr(),
+                      c_all=c_all.data_ptr(), dh_out=dh_out.data_ptr(), dh_rec=dh_rec.data_ptr(),
+                      dc_rec=dc_rec.data_ptr(), dG=dG.data_ptr(), dbias=None)
+    _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(Lb), _lib.current_stream_ptr()), "pvr_lstm_backward")
+    first = dG.clone()
+    ev[0].record()
+    for _ in range(10):
+        dh_rec.zero_()
+        dc_rec.zero_()
+        _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(Lb), _lib.current_stream_ptr()), "pvr_lstm_backward")
+    ev[1].record()
+    torch.cuda.synchronize()
+    assert torch.equal(first, dG)
+    us_per_step = ev[0].elapsed_time(ev[1]) * 1e3 / 10 / T
+    print(f"persistent backward: {us_per_step:.2f} us per time step (T = {T}, B = {B})")
+    assert us_per_step < 6.0  # 7.1 us with W_hh^T in shared memory, 4.5 us in tensor memory

@@ -129,7 +129,9 @@ class BCTrainer:
     def _step_body(self, o, a, d, n_mine, lr_tensor, state=None):
         if state is None:
             state = tuple(s.to(self.device) for s in self.model.initial_state(batch_size=n_mine))
-        output, _ = self.model(dict(obs=o, done=d), state)
+        # (the action sampled in training mode is unused here: our policies can skip the draw)
+        kw = {"sample_action": False} if getattr(self.model, "accepts_sample_action", False) else {}
+        output, _ = self.model(dict(obs=o, done=d), state, **kw)
         loss = bc_loss(output['policy_logits'], a, global_rows=self.global_rows)
         if lr_tensor is None:
             self.scheduler.step()

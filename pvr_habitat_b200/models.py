@@ -457,7 +457,12 @@ class PolicyNet(nn.Module):
         return (grads, dx) if need_dx else grads
 
     # ------------------------------------------------------------------------------------------ public forward
-    def forward(self, inputs, core_state=()):
+    accepts_sample_action = True
+
+    def forward(self, inputs, core_state=(), sample_action=True):
+        """src/models.py:59-82. `sample_action=False` (not in the reference) skips the multinomial draw of the training
+        mode, whose result the BC loops never read (main_bc_2.py:206-214 uses `policy_logits` only): ~15 small launches
+        per step; the output's `action` is then None and the CUDA RNG is not advanced."""
         x = inputs['obs']  # (unroll_length, batch_size, obs_size)
         T, B, *_ = x.shape
         dev = self.device
@@ -478,11 +483,11 @@ class PolicyNet(nn.Module):
             else:
                 logits, baseline, hn, cn = self._forward_cuda(x, notdone, h0, c0)
         if self.training:
-            action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1)
+            action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1) if sample_action else None
         elif action is None:
             action = torch.argmax(logits, dim=1)
         return dict(policy_logits=logits.view(T, B, -1), baseline=baseline.view(T, B),
-                    action=action.view(T, B)), (hn, cn)
+                    action=action.view(T, B) if action is not None else None), (hn, cn)
 
     # ------------------------------------------------------------------------------------------ online rollout
     def _rollout_step(self, x, notdone, h0, c0):
@@ -726,7 +731,9 @@ class PolicyNetWithConv(PolicyNet):
         return list(gconv) + list(grads_policy)
 
     # ------------------------------------------------------------------------------------------ public forward
-    def forward(self, inputs, core_state=()):
+    accepts_sample_action = True
+
+    def forward(self, inputs, core_state=(), sample_action=True):
         x = inputs['obs']  # (unroll_length, batch_size, H, W, 3 * n_frames) uint8
         T, B, *_, CN = x.shape
         dev = self.device
@@ -746,8 +753,8 @@ class PolicyNetWithConv(PolicyNet):
             else:
                 logits, baseline, hn, cn = self._forward_conv_cuda(obs, notdone, h0, c0)
         if self.training:
-            action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1)
+            action = torch.multinomial(F.softmax(logits, dim=1), num_samples=1) if sample_action else None
         else:
             action = torch.argmax(logits, dim=1)
         return dict(policy_logits=logits.view(T, B, -1), baseline=baseline.view(T, B),
-                    action=action.view(T, B)), (hn, cn)
+                    action=action.view(T, B) if action is not None else None), (hn, cn)

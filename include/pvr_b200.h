@@ -260,9 +260,15 @@ typedef struct pvr_lstm_fwd {
   float* gates;       /* (T*B, 4H) fp32 activated gates, saved for backward */
   float* g_tmp;       /* (B, 4H) fp32 scratch */
   float* h_last;      /* (B, H) fp32: h_{T-1} */
+  /* Optional arrival counters of the persistent kernel: a device buffer of at least PVR_LSTM_COUNTER_BYTES(T, B) that
+   * belongs to this sequence (zeroed by the call). NULL: a process-wide buffer is used, which serialises nothing by
+   * itself — callers that run recurrences of DIFFERENT sequences concurrently on several streams must pass their own. */
+  void* counters;
+  int64_t counters_bytes;
 } pvr_lstm_fwd;
+#define PVR_LSTM_COUNTER_BYTES(T, B) ((int64_t)((T) + 1) * (((B) + 31) / 32) * 16 * 4)
 int pvr_lstm_forward(const pvr_lstm_fwd* layer, void* stream);
-/* 1 if the whole-sequence persistent kernels (csrc/lstm_persist.cu: W_hh resident in shared memory, one launch for all
+/* 1 if the whole-sequence persistent kernels (csrc/lstm_persist.cu: W_hh resident in tensor / shared memory, one launch for all
  * T steps) serve this shape on the current device: H = 1024, B <= 128, all CTAs co-resident. pvr_lstm_forward /
  * pvr_lstm_backward use them when `flags == 0`; otherwise (and with PVR_LSTM_PERSIST=0) the per-step kernels run. */
 int pvr_lstm_persist_supported(int T, int B, int H);
@@ -281,6 +287,8 @@ typedef struct pvr_lstm_bwd {
   float* dc_rec;        /* (B, H) fp32: gradient of the final cell state on entry (zeros in BC) */
   void* dG;             /* bf16 (T*B, 4H) out: gradient w.r.t. the gate pre-activations */
   float* dbias;         /* optional (4H) fp32: += sum over t, b of dG — the gradient of bias_ih (= that of bias_hh) */
+  void* counters;       /* optional, as in pvr_lstm_fwd */
+  int64_t counters_bytes;
 } pvr_lstm_bwd;
 int pvr_lstm_backward(const pvr_lstm_bwd* layer, void* stream);
 

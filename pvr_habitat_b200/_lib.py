@@ -43,12 +43,19 @@ class pvr_gemm_desc(ctypes.Structure):
 
 class pvr_lstm_fwd(ctypes.Structure):
     _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("flags", ctypes.c_int32)] + [
-        (n, ctypes.c_void_p) for n in ("w_hh", "xp", "nd", "h0", "c_all", "hm", "h_out", "gates", "g_tmp", "h_last")]
+        (n, ctypes.c_void_p) for n in ("w_hh", "xp", "nd", "h0", "c_all", "hm", "h_out", "gates", "g_tmp", "h_last",
+                                       "counters")] + [("counters_bytes", ctypes.c_int64)]
 
 
 class pvr_lstm_bwd(ctypes.Structure):
     _fields_ = [("T", ctypes.c_int32), ("B", ctypes.c_int32), ("H", ctypes.c_int32), ("flags", ctypes.c_int32)] + [
-        (n, ctypes.c_void_p) for n in ("w_hh_t", "nd", "gates", "c_all", "dh_out", "dh_rec", "dc_rec", "dG", "dbias")]
+        (n, ctypes.c_void_p) for n in ("w_hh_t", "nd", "gates", "c_all", "dh_out", "dh_rec", "dc_rec", "dG", "dbias",
+                                       "counters")] + [("counters_bytes", ctypes.c_int64)]
+
+
+def lstm_counter_bytes(T, B):
+    """PVR_LSTM_COUNTER_BYTES of include/pvr_b200.h"""
+    return (T + 1) * ((B + 31) // 32) * 16 * 4
 
 
 class pvr_slot(ctypes.Structure):

@@ -24,7 +24,7 @@ void pvr_set_error(const char* fmt, ...) {
 }
 
 extern "C" const char* pvr_last_error(void) { return g_err; }
-extern "C" int pvr_abi_version(void) { return 2; }
+extern "C" int pvr_abi_version(void) { return 3; }
 
 namespace {
 

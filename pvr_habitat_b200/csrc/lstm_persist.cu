@@ -1102,7 +1102,7 @@ lstm_bwd2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __nv_bfloat16
 }
 
 long long* g_prof = nullptr;      // set by pvr_lstm_persist_profile()
-unsigned int* g_ready = nullptr;  // arrival counters (one launch at a time per process: stream ordered)
+unsigned int* g_ready = nullptr;  // process-wide arrival counters, used when the caller passes none (stream ordered)
 size_t g_ready_words = 0;
 int g_max_clusters[2] = {-1, -1};
 
@@ -1180,7 +1180,12 @@ int bwd2_max_clusters() {
 bool shape_ok(int T, int B, int H) { return H == HID && T >= 1 && B >= 1 && B <= 128 && T <= 4096; }
 
 // Arrival counters: grown on first use (never inside a stream capture), zeroed on the stream before every launch.
-int ensure_ready(size_t words, cudaStream_t st) {
+int ensure_ready(size_t words, cudaStream_t st, void* user, int64_t user_bytes, unsigned int** out) {
+  if (user && user_bytes >= (int64_t)(words * sizeof(unsigned int))) {  // the caller's own counters
+    *out = static_cast<unsigned int*>(user);
+    cudaMemsetAsync(user, 0, words * sizeof(unsigned int), st);
+    return PVR_OK;
+  }
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(st, &cap);
   if (words > g_ready_words) {
@@ -1198,16 +1203,19 @@ int ensure_ready(size_t words, cudaStream_t st) {
     }
   }
   cudaMemsetAsync(g_ready, 0, words * sizeof(unsigned int), st);
+  *out = g_ready;
   return PVR_OK;
 }
 
 template <int BWD>
-int launch(const CUtensorMap& ta, const CUtensorMap& tw, const PersistParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tw, const PersistParams& p, cudaStream_t st, void* user,
+           int64_t user_bytes) {
   const int grid = p.nbt * 16 * 4;
-  const int rc = ensure_ready((size_t)(p.T + 1) * p.nbt * 16, st);
+  unsigned int* ready = nullptr;
+  const int rc = ensure_ready((size_t)(p.T + 1) * p.nbt * 16, st, user, user_bytes, &ready);
   if (rc != PVR_OK) return rc;
   PersistParams q = p;
-  q.ready = g_ready;
+  q.ready = ready;
   q.prof = g_prof;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -1278,9 +1286,8 @@ int lstm_persist_forward(const pvr_lstm_fwd* L, cudaStream_t st) {
       pvr_set_error("pvr_lstm_persist_forward: tensor map: %s", err ? err : "?");
       return PVR_ERR_CUDA;
     }
-    const int rc = ensure_ready((size_t)(T + 1) * p.nbt * 16, st);
+    const int rc = ensure_ready((size_t)(T + 1) * p.nbt * 16, st, L->counters, L->counters_bytes, &p.ready);
     if (rc != PVR_OK) return rc;
-    p.ready = g_ready;
     p.prof = g_prof;
     mask_state_bf16_kernel<<<(B * HID + 255) / 256, 256, 0, st>>>(L->h0, L->nd, B, HID, p.hm);
     lstm_fwd2_kernel<<<p.nbt * 32, NTHREADS, F2_SMEM_TOTAL, st>>>(ta, static_cast<const __nv_bfloat16*>(L->w_hh), p);
@@ -1297,7 +1304,7 @@ int lstm_persist_forward(const pvr_lstm_fwd* L, cudaStream_t st) {
     return PVR_ERR_CUDA;
   }
   mask_state_bf16_kernel<<<(B * HID + 255) / 256, 256, 0, st>>>(L->h0, L->nd, B, HID, p.hm);
-  return launch<0>(ta, tw, p, st);
+  return launch<0>(ta, tw, p, st, L->counters, L->counters_bytes);
 }
 
 // PVR_LSTM_BWD2=0 keeps the backward pass on the first cluster kernel (A/B measurements).
@@ -1327,9 +1334,8 @@ int lstm_persist_backward(const pvr_lstm_bwd* L, cudaStream_t st) {
       pvr_set_error("pvr_lstm_persist_backward: tensor map: %s", err ? err : "?");
       return PVR_ERR_CUDA;
     }
-    const int rc = ensure_ready((size_t)(T + 1) * p.nbt * 16, st);
+    const int rc = ensure_ready((size_t)(T + 1) * p.nbt * 16, st, L->counters, L->counters_bytes, &p.ready);
     if (rc != PVR_OK) return rc;
-    p.ready = g_ready;
     p.prof = g_prof;
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
@@ -1347,7 +1353,7 @@ int lstm_persist_backward(const pvr_lstm_bwd* L, cudaStream_t st) {
     pvr_set_error("pvr_lstm_persist_backward: tensor map: %s", err ? err : "?");
     return PVR_ERR_CUDA;
   }
-  return launch<1>(ta, tw, p, st);
+  return launch<1>(ta, tw, p, st, L->counters, L->counters_bytes);
 }
 
 }  // namespace pvr

@@ -73,6 +73,10 @@ class _Workspace:
         self.gates = [z(M, 4 * H), z(M, 4 * H)]
         self.c_all = [z(M + B, H), z(M + B, H)]
         self.g_tmp = [z(B, 4 * H), z(B, 4 * H)]  # per layer: the two layers run concurrently (wavefront)
+        # arrival counters of the persistent recurrence kernels, one buffer per layer of THIS workspace (never shared
+        # with another sequence that may run on another stream)
+        self.lstm_counters = [torch.zeros(_lib.lstm_counter_bytes(T, B) // 4, dtype=torch.int32, device=device)
+                              for _ in range(2)]
         self.h_last = [z(B, H), z(B, H)]
         self.h0 = [z(B, H), z(B, H)]          # persistent copies: stable pointers keep the CUDA-graph cache warm
         self.nd = z(T, B)
@@ -230,7 +234,8 @@ class PolicyNet(nn.Module):
                          nd=ws.nd[t0:].data_ptr(), h0=ws.h0[l].data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
                          hm=ws.hm[l][r0:].data_ptr(), h_out=ws.HL[l][r0:].data_ptr(),
                          gates=ws.gates[l][r0:].data_ptr(), g_tmp=ws.g_tmp[l].data_ptr(),
-                         h_last=ws.h_last[l].data_ptr())
+                         h_last=ws.h_last[l].data_ptr(), counters=ws.lstm_counters[l].data_ptr(),
+                         counters_bytes=ws.lstm_counters[l].numel() * 4)
         _lib.check(_lib.lib().pvr_lstm_forward(ctypes.byref(L), _stream()), "pvr_lstm_forward")
 
     def _lstm_bwd_chunk(self, ws, w, l, t0, Tc, flags, dbias=None):
@@ -239,7 +244,8 @@ class PolicyNet(nn.Module):
                          gates=ws.gates[l][r0:].data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
                          dh_out=ws.dHL[l][r0:].data_ptr(), dh_rec=ws.dh_rec[l].data_ptr(),
                          dc_rec=ws.dc_rec[l].data_ptr(), dG=ws.dG[l][r0:].data_ptr(),
-                         dbias=dbias.data_ptr() if dbias is not None else None)
+                         dbias=dbias.data_ptr() if dbias is not None else None,
+                         counters=ws.lstm_counters[l].data_ptr(), counters_bytes=ws.lstm_counters[l].numel() * 4)
         _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(L), _stream()), "pvr_lstm_backward")
 
     def _check_generation(self, generation):

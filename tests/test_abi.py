@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(built):
 
 
 def test_abi_version_and_error_string(built):
-    assert built.pvr_abi_version() == 2
+    assert built.pvr_abi_version() == 3
     assert isinstance(built.pvr_last_error(), bytes)
 
 

@@ -204,9 +204,19 @@ int pvr_layernorm_f32(const float* x, int64_t row_step, int64_t rows, int width,
  * no LayerNorm (MAE: cls_token + pos_embed[0] | patches + pos_embed[1:], src/vision_models/mae.py:206-217). */
 int pvr_vit_embed(const void* patches_bf16, const float* cls, const float* pos, int n_img, int tokens, int width,
                   const float* gamma, const float* beta, float eps, float* x_out, void* stream);
-/* out (n_img*tokens, width) bf16 = softmax(q k^T / sqrt(64)) v per image and head; qkv (n_img*tokens, 3*width) bf16
+/* out (n_img*tokens, width) bf16 = softmax(q k^T / sqrt(head_dim)) v per image and head; qkv (n_img*tokens, 3*width) bf16
  * laid out [q | k | v] with heads contiguous inside each (nn.MultiheadAttention in_proj order). tcgen05 kernel. */
 int pvr_attention(const void* qkv_bf16, int n_img, int tokens, int width, int heads, void* out_bf16, void* stream);
+/* Same contract for any head_dim in {64, 80, 96, 128} and any sequence whose K / V fit shared memory (mae_huge,
+ * src/vision_models/mae.py:291-296: 257 tokens, 16 heads of 80): warp-level mma.sync kernel with online softmax
+ * (csrc/attention_mma.cu). pvr_attention forwards here for the shapes its tcgen05 kernel does not cover. */
+int pvr_attention_mma(const void* qkv_bf16, int n_img, int tokens, int width, int heads, void* out_bf16, void* stream);
+/* im2col of non-overlapping p x p patches (timm PatchEmbed, Conv2d(3, width, p, stride p), for patch sizes whose rows
+ * are not a whole number of 128-byte TMA rows: mae_huge, p = 14): col (n_img * grid * grid, k_pad) with
+ * col[(img, gy, gx)][c * p * p + py * p + px] = x[img][gy * p + py][gx * p + px][c], zero beyond 3 p^2. x is NHWC4;
+ * f32 = 0: bf16 in / bf16 out, f32 = 1: float32 in / float32 out (fp32 parity mode). The patch embedding is then one
+ * GEMM against the (width, 3 p^2) weight in its natural torch layout, zero padded to k_pad. */
+int pvr_vit_patchify(const void* x_nhwc4, int n_img, int res, int patch, int k_pad, int f32, void* col, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * BC policy network pieces (src/models.py:13-89 PolicyNet, main_bc_2.py:206-227 loss / clip / RMSprop).
@@ -374,6 +384,13 @@ int pvr_elu_backward_fused(const float* dy, const void* y_bf16, int pitch, int64
 /* colT ((9*Ci), Mp) bf16: transposed im2col of A (F, Hi, Wi, pitch) for a 3x3/s2/p1 conv, Ci = 4 or 32. */
 int pvr_im2col_t(const void* a_bf16, int pitch, int F, int Hi, int Wi, int Ci, int Ho, int Wo, int64_t Mp,
                  void* colT_bf16, void* stream);
+/* Weight / bias gradient of the FIRST layer of the small-conv trunk (src/models.py:108: Conv2d(3, 32, 3x3, stride 2,
+ * padding 1) + ELU) in one pass, no im2col and no GEMM: dz = bf16(dy * ELU'(y));
+ * dw[co][a][b][c] += sum_px dz[px][co] x[2 oy - 1 + a][2 ox - 1 + b][c] (fp32, (32, 3, 3, 4), zeroed by the caller; the
+ * 4th channel is the padding of the NHWC4 frames and stays 0), dbias[co] += sum_px dz[px][co].
+ * dy fp32 (F*Ho*Wo, 32); y bf16 with `y_pitch` elements per pixel; x bf16 (F, Hi, Wi, 4). */
+int pvr_small_conv1_wgrad(const float* dy, const void* y_bf16, int y_pitch, const void* x_nhwc4_bf16, int F, int Hi,
+                          int Wi, int Ho, int Wo, float* dw, float* dbias, void* stream);
 /* dA (F, Hi, Wi, Ci) fp32 = col2im of dcol (F*Ho*Wo, Kp) bf16 (input gradient of the layer), Ci = 32. */
 int pvr_col2im(const void* dcol_bf16, int Kp, int F, int Hi, int Wi, int Ci, int Ho, int Wo, float* dA, void* stream);
 /* BatchNorm1d input gradient from dy (bf16), the saved statistics and the (all-reduced) sums of pvr_bn1d_backward. */

@@ -284,6 +284,28 @@ def golden_mae(E):
     np.savez_compressed(os.path.join(GOLDEN, "mae.npz"), **out)
 
 
+def golden_mae_huge(E):
+    """EmbeddingNet('mae_huge') of the reference (src/embeddings.py:145-148: mae_vit_huge_patch14, 257 tokens, 16 heads
+    of 80) on a synthetic checkpoint, in its own file so that mae.npz stays as generated. One frame of each of the
+    frame sets of golden_mae (632 M parameters: 0.33 TFLOP per frame on the CPU)."""
+    from oracle import restate_mae
+    name, seed = "mae_huge", 203
+    frames224 = restate.structured_frames(2, 224, 224, 3, 45)[:1]
+    frames64 = restate.structured_frames(3, 64, 64, 3, 46)[:1]
+    sd = restate_mae.mae_state(name, seed)
+    with tempfile.TemporaryDirectory() as d, refshim.chdir(d):
+        torch.save({"model": sd}, os.path.join(d, restate_mae.CHECKPOINTS[name]))
+        torch.manual_seed(7)
+        net = E.EmbeddingNet(name, pretrained=True, train=False, disable_cuda=True)
+    net.transforms[0].antialias = False  # torchvision 0.10 semantics, see golden_mae
+    out = {"frames224": frames224, "frames64": frames64, f"seed_{name}": np.array(seed),
+           f"out_size_{name}": np.array(int(net.out_size)),
+           f"emb224_{name}": np.atleast_2d(net(torch.from_numpy(frames224))),
+           f"emb64_{name}": np.atleast_2d(net(torch.from_numpy(frames64)))}
+    print(name, out[f"out_size_{name}"], np.abs(out[f"emb224_{name}"]).mean())
+    np.savez_compressed(os.path.join(GOLDEN, "mae_huge.npz"), **out)
+
+
 def golden_clip_transforms(E):
     """The `transforms` the reference builds for 'clip_vit' (src/embeddings.py:309-314: antialiased bicubic Resize(224)
     -> CenterCrop(224) -> float -> CLIP Normalize), run on frames that are not 224x224 (Habitat renders 64x64). The
@@ -392,7 +414,7 @@ def main():
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
     if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which or \
-            "mae" in which or "save_embedded" in which or "clip_transforms" in which:
+            "mae" in which or "mae_huge" in which or "save_embedded" in which or "clip_transforms" in which:
         E = refshim.reference_embeddings()
         if "clip_transforms" in which:
             golden_clip_transforms(E)
@@ -400,6 +422,8 @@ def main():
             golden_save_embedded(E)
         if "mae" in which:
             golden_mae(E)
+        if "mae_huge" in which:
+            golden_mae_huge(E)
         if "resnet_basic" in which:
             golden_resnet_basic(E)
         if "transforms" in which:

@@ -18,8 +18,10 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-CONFIGS = {"mae_base": dict(dim=768, depth=12, heads=12, patch=16), "mae_large": dict(dim=1024, depth=24, heads=16, patch=16)}
-CHECKPOINTS = {"mae_base": "mae_pretrain_vit_base.pth", "mae_large": "mae_pretrain_vit_large.pth"}  # embeddings.py:139,143
+CONFIGS = {"mae_base": dict(dim=768, depth=12, heads=12, patch=16), "mae_large": dict(dim=1024, depth=24, heads=16, patch=16),
+           "mae_huge": dict(dim=1280, depth=32, heads=16, patch=14)}  # mae.py:275-296
+CHECKPOINTS = {"mae_base": "mae_pretrain_vit_base.pth", "mae_large": "mae_pretrain_vit_large.pth",
+               "mae_huge": "mae_pretrain_vit_huge.pth"}  # embeddings.py:139,143,147
 
 
 # ---------------------------------------------------------------------------- timm 0.5.4, restated (see header)

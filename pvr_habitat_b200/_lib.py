@@ -90,6 +90,8 @@ _SIGNATURES = {
     "pvr_layernorm_f32": (ctypes.c_int, [_vp, _i64, _i64, _i, _vp, _vp, _f, _vp, _i64, _vp]),
     "pvr_vit_embed": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "pvr_attention": (ctypes.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "pvr_attention_mma": (ctypes.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "pvr_vit_patchify": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pvr_bn1d_stats": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp]),
     "pvr_bn1d_normalize": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, ctypes.c_double, _f, _f, _vp, _vp, _vp, _vp, _vp,
                                           _vp, _vp, _i64, _vp]),
@@ -114,6 +116,7 @@ _SIGNATURES = {
     "pvr_elu_backward_fused": (ctypes.c_int, [_vp, _vp, _i, _i64, _i, _vp, _vp, _i64, _vp, _vp]),
     "pvr_im2col_t": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _i64, _vp, _vp]),
     "pvr_col2im": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "pvr_small_conv1_wgrad": (ctypes.c_int, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "pvr_bn1d_backward_dx": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_double,
                                             _vp, _i64, _vp]),
     "pvr_bf16_rows_to_f32": (ctypes.c_int, [_vp, _i64, _i64, _i, _vp, _i64, _vp]),

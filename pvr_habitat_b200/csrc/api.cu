@@ -58,6 +58,7 @@ struct BoundConv {
   int block_n, a_mode;
   bool epi_tma;
   bool patch;  // patch-resident 3x3 kernel (conv3x3_patch.cu)
+  bool direct;  // first layer of the small-conv trunk: warp-level mma.sync kernel (small_conv.cu)
 };
 
 }  // namespace
@@ -197,6 +198,7 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     b.pp.pdl = pdl;
     const long long M = (long long)n_images * o.h_out * o.w_out;
     b.patch = false;
+    b.direct = false;
     if (o.r == 3 && o.s == 3 && o.stride_h == 1 && o.stride_w == 1 && o.lower_h == -1 && o.lower_w == -1 &&
         o.c_in == 64 && o.c_out == 64 && o.n_pad == 64 && o.in_pitch == 64 && o.out_pitch == 64 && o.out_coff == 0 &&
         o.h_in == o.h_out && o.w_in == o.w_out && o.w_out % 8 == 0 && o.res_slot < 0 && o.act == 0 &&
@@ -410,6 +412,14 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
     } else {
       const int upper_w = o.lower_w + (o.w_out - 1) * o.stride_w - (o.w_in - 1);
       const int upper_h = o.lower_h + (o.h_out - 1) * o.stride_h - (o.h_in - 1);
+      // 3 -> 32 channels, 3x3 stride 2 over NHWC4 pixel pairs + ELU (program.add_small_conv, first layer): K = 27 is
+      // not a tensor-core problem (see small_conv.cu); PVR_SMALL_CONV_GEMM=1 keeps it on the implicit-GEMM kernel
+      static const bool direct_ok = !(getenv("PVR_SMALL_CONV_GEMM") && atoi(getenv("PVR_SMALL_CONV_GEMM")) != 0);
+      b.direct = direct_ok && o.c_in == 8 && o.in_pitch == 8 && o.r == 3 && o.s == 2 && o.stride_h == 2 &&
+                 o.stride_w == 1 && o.lower_h == -1 && o.lower_w == -1 && o.k_pad == 64 && o.n_pad == 32 &&
+                 o.c_out == 32 && o.out_pitch == 32 && o.out_coff == 0 && o.act == 3 && o.res_slot < 0 &&
+                 o.relu_n == 0 && !(o.flags & PVR_CONV_OUT_F32) && o.h_out == (o.h_in - 1) / 2 + 1 &&
+                 o.w_out == (2 * o.w_in - 1) / 2 + 1;
       if (o.c_in == 8) {
         b.a_mode = pvr::A_IM2COL8;
         if (o.k_pad < o.r * o.s * 8) {
@@ -533,7 +543,9 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
     switch (o.kind) {
       case PVR_OP_CONV: {
         const BoundConv& b = enc->bound[i];
-        e = b.b2b   ? pvr::launch_conv_b2b(b.ta, b.ta2, b.tb, b.tr, b.to, b.tw1, b.to2, b.bp, enc->sms, stream)
+        e = b.direct ? pvr::launch_small_conv1(enc->slot_ptr[o.in_slot], n, o.h_in, 2 * o.w_in, o.h_out, o.w_out,
+                                               o.weight, o.scale, o.bias, enc->slot_ptr[o.out_slot], stream)
+            : b.b2b   ? pvr::launch_conv_b2b(b.ta, b.ta2, b.tb, b.tr, b.to, b.tw1, b.to2, b.bp, enc->sms, stream)
             : b.patch ? pvr::launch_conv3x3_patch(b.ta, b.tb, b.to, b.pp, enc->sms, stream)
                       : pvr::launch_conv_gemm(b.block_n, b.a_mode, b.epi_tma, b.ta, b.tb, b.to, b.tr, b.p, enc->sms,
                                             stream, &b.ta2);

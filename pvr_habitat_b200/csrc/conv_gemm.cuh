@@ -119,4 +119,9 @@ bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int 
                       int lower_h, int upper_w, int upper_h, int stride_w, int stride_h, int channels_per_pixel,
                       int pixels_per_column, int swizzle_bytes, const char** err);
 
+// First layer of the small-conv trunk (3 -> 32 channels, 3x3 stride 2, ELU) with register-resident mma.sync fragments (small_conv.cu). `x` is
+// (F, Hi, Wi, 4) bf16, `wpk` the packed weight of program.pack_first_small_conv, `y` (F, Ho, Wo, 32) bf16.
+cudaError_t launch_small_conv1(const void* x, int F, int Hi, int Wi, int Ho, int Wo, const void* wpk, const float* scale,
+                               const float* bias, void* y, cudaStream_t stream);
+
 }  // namespace pvr

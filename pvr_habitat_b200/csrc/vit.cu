@@ -367,12 +367,17 @@ cudaError_t launch_ln(const float* src, long long row_step, const __nv_bfloat16*
                                                                           beta, eps, rows, out_f32, out_bf16, mode);
   return cudaGetLastError();
 }
-// widths: 768 (ViT-B: CLIP, mae_base), 1024 (ViT-L: mae_large)
+// widths: 768 (ViT-B: CLIP, mae_base), 1024 (ViT-L: mae_large), 1280 (ViT-H: mae_huge)
+}  // namespace
+inline bool ln_width_ok(int width) { return width == 768 || width == 1024 || width == 1280; }
+namespace {
 cudaError_t dispatch_ln(int width, const float* src, long long row_step, const __nv_bfloat16* patches, const float* cls,
                         const float* pos, int tokens, const float* gamma, const float* beta, float eps, long long rows,
                         float* out_f32, __nv_bfloat16* out_bf16, int mode, cudaStream_t stream) {
   if (width == 768)
     return launch_ln<768>(src, row_step, patches, cls, pos, tokens, gamma, beta, eps, rows, out_f32, out_bf16, mode, stream);
+  if (width == 1280)
+    return launch_ln<1280>(src, row_step, patches, cls, pos, tokens, gamma, beta, eps, rows, out_f32, out_bf16, mode, stream);
   return launch_ln<1024>(src, row_step, patches, cls, pos, tokens, gamma, beta, eps, rows, out_f32, out_bf16, mode, stream);
 }
 }  // namespace
@@ -380,8 +385,8 @@ cudaError_t dispatch_ln(int width, const float* src, long long row_step, const _
 
 extern "C" int pvr_layernorm(const float* x, int64_t row_step, int64_t rows, int width, const float* gamma,
                              const float* beta, float eps, void* y_bf16, void* stream) {
-  if (!x || !gamma || !beta || !y_bf16 || rows <= 0 || (width != 768 && width != 1024) || row_step <= 0) {
-    pvr_set_error("pvr_layernorm: invalid argument (width must be 768 or 1024)");
+  if (!x || !gamma || !beta || !y_bf16 || rows <= 0 || !pvr::ln_width_ok(width) || row_step <= 0) {
+    pvr_set_error("pvr_layernorm: invalid argument (width must be 768, 1024 or 1280)");
     return PVR_ERR_ARG;
   }
   cudaError_t e = pvr::dispatch_ln(width, x, row_step, nullptr, nullptr, nullptr, 1, gamma, beta, eps, rows, nullptr,
@@ -392,8 +397,8 @@ extern "C" int pvr_layernorm(const float* x, int64_t row_step, int64_t rows, int
 
 extern "C" int pvr_layernorm_f32(const float* x, int64_t row_step, int64_t rows, int width, const float* gamma,
                                  const float* beta, float eps, float* y, int64_t ldy, void* stream) {
-  if (!x || !gamma || !beta || !y || rows <= 0 || (width != 768 && width != 1024) || row_step <= 0 || ldy != width) {
-    pvr_set_error("pvr_layernorm_f32: invalid argument (width must be 768 or 1024, dense output rows)");
+  if (!x || !gamma || !beta || !y || rows <= 0 || !pvr::ln_width_ok(width) || row_step <= 0 || ldy != width) {
+    pvr_set_error("pvr_layernorm_f32: invalid argument (width must be 768, 1024 or 1280, dense output rows)");
     return PVR_ERR_ARG;
   }
   cudaError_t e = pvr::dispatch_ln(width, x, row_step, nullptr, nullptr, nullptr, 1, gamma, beta, eps, rows, y, nullptr,
@@ -405,8 +410,8 @@ extern "C" int pvr_layernorm_f32(const float* x, int64_t row_step, int64_t rows,
 extern "C" int pvr_vit_embed(const void* patches_bf16, const float* cls, const float* pos, int n_img, int tokens,
                              int width, const float* gamma, const float* beta, float eps, float* x_out, void* stream) {
   if (!patches_bf16 || !cls || !pos || (!gamma != !beta) || !x_out || n_img <= 0 || tokens <= 1 ||
-      (width != 768 && width != 1024)) {
-    pvr_set_error("pvr_vit_embed: invalid argument (width must be 768 or 1024)");
+      !pvr::ln_width_ok(width)) {
+    pvr_set_error("pvr_vit_embed: invalid argument (width must be 768, 1024 or 1280)");
     return PVR_ERR_ARG;
   }
   const long long rows = (long long)n_img * tokens;
@@ -420,10 +425,14 @@ extern "C" int pvr_vit_embed(const void* patches_bf16, const float* cls, const f
 extern "C" int pvr_attention(const void* qkv_bf16, int n_img, int tokens, int width, int heads, void* out_bf16,
                              void* stream) {
   using namespace pvr;
-  if (!qkv_bf16 || !out_bf16 || n_img <= 0 || tokens <= 0 || tokens > 256 || heads <= 0 || width != heads * 64) {
-    pvr_set_error("pvr_attention: invalid argument (head_dim must be 64, at most 256 tokens)");
+  if (!qkv_bf16 || !out_bf16 || n_img <= 0 || tokens <= 0 || heads <= 0 || width <= 0 || width % heads) {
+    pvr_set_error("pvr_attention: invalid argument");
     return PVR_ERR_ARG;
   }
+  // the tensor-memory kernel below is built for head_dim 64 and at most 256 keys (one TMEM buffer per query tile);
+  // everything else (mae_huge: 257 tokens, head_dim 80) takes the register-level kernel of attention_mma.cu
+  if (tokens > 256 || width != heads * 64)
+    return pvr_attention_mma(qkv_bf16, n_img, tokens, width, heads, out_bf16, stream);
   AttnParams p;
   p.n_img = n_img; p.S = tokens; p.W = width; p.heads = heads;
   p.KP = (tokens + 15) / 16 * 16;

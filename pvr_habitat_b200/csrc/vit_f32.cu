@@ -58,17 +58,20 @@ __global__ void __launch_bounds__(256) vit_embed_f32_kernel(const float* __restr
 }
 
 // One block per (image, head): K and V of the head staged in shared memory, one warp per query row at a time.
-// head_dim = 64 (two values per lane).
+// head_dim D <= 128: lane l owns dimensions l, l + 32, ... (2 values at D = 64; 3 with the last one guarded at the
+// D = 80 of mae_huge).
+template <int D>
 __global__ void __launch_bounds__(256) vit_attention_f32_kernel(const float* __restrict__ qkv, int S, int W, int heads,
                                                                  float scale, float* __restrict__ out) {
+  constexpr int PER = (D + 31) / 32;
   extern __shared__ float sm[];
-  float* Ks = sm;                 // (S, 64)
-  float* Vs = sm + (size_t)S * 64;
-  float* Ps = Vs + (size_t)S * 64;  // (8 warps, S) probabilities of the row a warp is working on
+  float* Ks = sm;                 // (S, D)
+  float* Vs = sm + (size_t)S * D;
+  float* Ps = Vs + (size_t)S * D;  // (8 warps, S) probabilities of the row a warp is working on
   const int img = blockIdx.x / heads, head = blockIdx.x % heads;
-  const float* base = qkv + (long long)img * S * 3 * W + head * 64;
-  for (int i = threadIdx.x; i < S * 64; i += blockDim.x) {
-    const int t = i >> 6, d = i & 63;
+  const float* base = qkv + (long long)img * S * 3 * W + head * D;
+  for (int i = threadIdx.x; i < S * D; i += blockDim.x) {
+    const int t = i / D, d = i - t * D;
     Ks[i] = base[(long long)t * 3 * W + W + d];
     Vs[i] = base[(long long)t * 3 * W + 2 * W + d];
   }
@@ -76,10 +79,16 @@ __global__ void __launch_bounds__(256) vit_attention_f32_kernel(const float* __r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* P = Ps + (size_t)warp * S;
   for (int r = warp; r < S; r += 8) {
-    const float q0 = base[(long long)r * 3 * W + lane] * scale, q1 = base[(long long)r * 3 * W + 32 + lane] * scale;
+    float q[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) q[k] = lane + 32 * k < D ? base[(long long)r * 3 * W + lane + 32 * k] * scale : 0.f;
     float mx = -INFINITY;
     for (int j = 0; j < S; ++j) {
-      const float s = warp_sum(q0 * Ks[j * 64 + lane] + q1 * Ks[j * 64 + 32 + lane]);
+      float part = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+        if (lane + 32 * k < D) part = fmaf(q[k], Ks[j * D + lane + 32 * k], part);
+      const float s = warp_sum(part);
       if (lane == 0) P[j] = s;
       mx = fmaxf(mx, s);
     }
@@ -92,17 +101,41 @@ __global__ void __launch_bounds__(256) vit_attention_f32_kernel(const float* __r
     }
     sum = warp_sum(sum);
     __syncwarp();
-    float o0 = 0.f, o1 = 0.f;
+    float o[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) o[k] = 0.f;
     for (int j = 0; j < S; ++j) {
       const float pj = P[j];
-      o0 = fmaf(pj, Vs[j * 64 + lane], o0);
-      o1 = fmaf(pj, Vs[j * 64 + 32 + lane], o1);
+#pragma unroll
+      for (int k = 0; k < PER; ++k)
+        if (lane + 32 * k < D) o[k] = fmaf(pj, Vs[j * D + lane + 32 * k], o[k]);
     }
-    float* dst = out + ((long long)img * S + r) * W + head * 64;
-    dst[lane] = o0 / sum;
-    dst[32 + lane] = o1 / sum;
+    float* dst = out + ((long long)img * S + r) * W + head * D;
+#pragma unroll
+    for (int k = 0; k < PER; ++k)
+      if (lane + 32 * k < D) dst[lane + 32 * k] = o[k] / sum;
     __syncwarp();
   }
+}
+
+template <int D>
+int launch_attention_f32(const float* qkv, int n_img, int tokens, int width, int heads, float* out, cudaStream_t stream) {
+  const size_t smem = ((size_t)tokens * 2 * D + 8 * (size_t)tokens) * sizeof(float);
+  if (smem > 200 * 1024) {
+    pvr_set_error("pvr_attention_f32: sequence too long for shared-memory staging (%d tokens)", tokens);
+    return PVR_ERR_ARG;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(vit_attention_f32_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024);
+    if (e != cudaSuccess) { pvr_set_error("pvr_attention_f32: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
+    attr = true;
+  }
+  vit_attention_f32_kernel<D><<<n_img * heads, 256, smem, stream>>>(qkv, tokens, width, heads, 1.f / sqrtf((float)D), out);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { pvr_set_error("pvr_attention_f32: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
+  return PVR_OK;
 }
 
 }  // namespace
@@ -168,25 +201,16 @@ extern "C" int pvr_vit_embed_f32(const float* patches, const float* cls, const f
 
 extern "C" int pvr_attention_f32(const float* qkv, int n_img, int tokens, int width, int heads, float* out,
                                  void* stream) {
-  if (!qkv || !out || n_img <= 0 || tokens <= 0 || heads <= 0 || width != heads * 64) {
-    pvr_set_error("pvr_attention_f32: invalid argument (head_dim must be 64)");
+  if (!qkv || !out || n_img <= 0 || tokens <= 0 || heads <= 0 || width <= 0 || width % heads) {
+    pvr_set_error("pvr_attention_f32: invalid argument");
     return PVR_ERR_ARG;
   }
-  const size_t smem = ((size_t)tokens * 128 + 8 * (size_t)tokens) * sizeof(float);
-  if (smem > 200 * 1024) {
-    pvr_set_error("pvr_attention_f32: sequence too long for shared-memory staging (%d tokens)", tokens);
-    return PVR_ERR_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  switch (width / heads) {
+    case 64: return pvr::launch_attention_f32<64>(qkv, n_img, tokens, width, heads, out, st);
+    case 80: return pvr::launch_attention_f32<80>(qkv, n_img, tokens, width, heads, out, st);
+    default:
+      pvr_set_error("pvr_attention_f32: head_dim %d is not built (64, 80)", width / heads);
+      return PVR_ERR_ARG;
   }
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(pvr::vit_attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         200 * 1024);
-    if (e != cudaSuccess) { pvr_set_error("pvr_attention_f32: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
-    attr = true;
-  }
-  pvr::vit_attention_f32_kernel<<<n_img * heads, 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      qkv, tokens, width, heads, 0.125f, out);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { pvr_set_error("pvr_attention_f32: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
-  return PVR_OK;
 }

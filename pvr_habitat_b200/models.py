@@ -607,6 +607,8 @@ class PolicyNetWithConv(PolicyNet):
         self._build_trunk(conv_out_size * n_frames, num_actions, batch_norm)
         self._needs_input_grad = True
         self._conv = None
+        # PVR_SMALL_CONV_GEMM=1: the first conv layer (forward and weight gradient) stays on the implicit-GEMM path
+        self._direct_first_layer = os.environ.get("PVR_SMALL_CONV_GEMM", "0") in ("", "0")
 
     def _conv_params(self):
         ps = []
@@ -689,6 +691,9 @@ class PolicyNetWithConv(PolicyNet):
                 M = F * sizes[l] * sizes[l]
                 Mp = (M + 511) // 512 * 512
                 Kp = 64 if l == 0 else 320
+                if l == 0 and self._direct_first_layer:
+                    bufs.append(dict(dw_nat=torch.zeros(32, 3, 3, 4, dtype=f32, device=dev)))
+                    continue
                 bufs.append(dict(dz=torch.empty(M, 64, dtype=bf, device=dev), dzt=torch.zeros(64, Mp, dtype=bf, device=dev),
                                  colt=torch.zeros(Kp, Mp, dtype=bf, device=dev), dw=torch.zeros(64, Kp, dtype=f32, device=dev),
                                  wt=torch.zeros(Kp, 64, dtype=bf, device=dev) if l > 0 else None,
@@ -702,6 +707,15 @@ class PolicyNetWithConv(PolicyNet):
             Kp = 64 if l == 0 else 320
             b = bufs[l]
             y_ptr, a_ptr = enc.slot_ptr(slots[l + 1]), enc.slot_ptr(slots[l])
+            if l == 0 and self._direct_first_layer:
+                # first layer (3 input channels, no input gradient needed): one mma.sync pass over dy / y / the frames
+                # instead of ELU backward + im2col^T + a K = 3.3 M GEMM (csrc/small_conv.cu)
+                dwn = b["dw_nat"]
+                dwn.zero_()
+                _lib.check(lib.pvr_small_conv1_wgrad(dy.data_ptr(), y_ptr, 32, a_ptr, F, hi, hi, ho, ho, dwn.data_ptr(),
+                                                     gconv[1].data_ptr(), _stream()), "pvr_small_conv1_wgrad")
+                gconv[0].copy_(dwn[..., :conv_params[0].shape[1]].permute(0, 3, 2, 1))
+                continue
             # ELU backward + bias gradient + the transposed copy for the weight-gradient GEMM, one pass over dy
             dz, dzt, colt, dw = b["dz"], b["dzt"], b["colt"], b["dw"]
             _lib.check(lib.pvr_elu_backward_fused(dy.data_ptr(), y_ptr, 32, M, 32, dz.data_ptr(), dzt.data_ptr(), Mp,

@@ -177,17 +177,28 @@ class ViTRunner:
         # is expressed on a reshaped view of the NHWC4 frames: (N*grid, p, grid, p*4) = (patch row, row inside the
         # patch, patch column, one patch row of pixels). One "image" of the program is one row of patches, the filter
         # is p x 1 taps over the "row inside the patch" axis and every stride is 1.
+        # Patch sizes whose rows are not whole 128-byte TMA rows (mae_huge: p = 14) gather their patches with
+        # pvr_vit_patchify and multiply them by the weight in its torch layout (K = 3 p^2 padded to a multiple of 64).
         prog = prg.Program()
         cpp = self.p * 4
-        self.in_slot = prog.new_slot(self.p * self.grid * cpp)
         pbias = spec["patch_bias"]
         pbias = torch.zeros(self.W) if pbias is None else pbias.detach().cpu().float()
-        self.patch_slot = prog.conv(self.in_slot, (cpp, self.p, self.grid),
-                                    pack_patch_weight(spec["patch_weight"].detach().cpu().float()), self.p * cpp, self.W,
-                                    self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), pbias, 0,
-                                    flops=2 * self.grid * self.W * 3 * self.p * self.p)
-        prog.emb_width = 1
-        self.patch_enc = prog.finish(dev)
+        self.gather_patches = (cpp * 2) % 128 != 0
+        if self.gather_patches:
+            self.patch_enc = None  # the frames live in a plain buffer (bind), no encoder program
+            k = 3 * self.p * self.p
+            self.patch_k = (k + 63) // 64 * 64
+            wp = torch.zeros(self.W, self.patch_k)
+            wp[:, :k] = spec["patch_weight"].detach().cpu().float().reshape(self.W, k)
+            self.patch_w, self.patch_b = wp.to(dev, bf).contiguous(), pbias.to(dev)
+        else:
+            self.in_slot = prog.new_slot(self.p * self.grid * cpp)
+            self.patch_slot = prog.conv(self.in_slot, (cpp, self.p, self.grid),
+                                        pack_patch_weight(spec["patch_weight"].detach().cpu().float()), self.p * cpp,
+                                        self.W, self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), pbias, 0,
+                                        flops=2 * self.grid * self.W * 3 * self.p * self.p)
+            prog.emb_width = 1
+            self.patch_enc = prog.finish(dev)
         self.cls, self.pos = f(spec["cls"].reshape(-1)), f(spec["pos"].reshape(self.S, self.W))
         self.ln_pre = tuple(f(t) for t in spec["ln_pre"]) if spec["ln_pre"] is not None else None
         self.ln_post = tuple(f(t) for t in spec["ln_post"])
@@ -208,7 +219,10 @@ class ViTRunner:
         if n == self.n:
             return
         dev, bf, M, W = self.device, torch.bfloat16, n * self.S, self.W
-        self.patch_enc.bind(n * self.grid)
+        if self.gather_patches:
+            self.frames = torch.empty(n, self.res, self.res, 4, dtype=bf, device=dev)
+        else:
+            self.patch_enc.bind(n * self.grid)
         self.x = torch.empty(M, W, dtype=torch.float32, device=dev)
         self.y = torch.empty(M, W, dtype=bf, device=dev)
         self.qkv = torch.empty(M, 3 * W, dtype=bf, device=dev)
@@ -216,14 +230,17 @@ class ViTRunner:
         self.h = torch.empty(M, 4 * W, dtype=bf, device=dev)
         self.clsy = torch.empty(n, W, dtype=bf, device=dev)
         self.dummy = torch.zeros(n * self.grid, 1, device=dev)
+        if self.gather_patches:
+            self.col = torch.empty(n * self.grid ** 2, self.patch_k, dtype=bf, device=dev)
+            self.patches = torch.empty(n * self.grid ** 2, W, dtype=bf, device=dev)
         self.n = n
 
     @property
     def slot0(self):
-        return self.patch_enc.slot0
+        return self.frames.data_ptr() if self.gather_patches else self.patch_enc.slot0
 
     def launches_per_forward(self):
-        return 2 + 7 * self.L + (2 if self.proj_t is not None else 1)
+        return (3 if self.gather_patches else 2) + 7 * self.L + (2 if self.proj_t is not None else 1)
 
     def forward(self, out, out_ld=None):
         """Frames must already be in slot0 (NHWC4 bf16). Writes (n, O) fp32 rows into `out`."""
@@ -231,8 +248,14 @@ class ViTRunner:
         st = _lib.current_stream_ptr
         ld = out_ld if out_ld is not None else out.stride(0)
         with torch.cuda.device(self.device):
-            self.patch_enc.forward(self.dummy, 1)
-            patches = self.patch_enc.slot_ptr(self.patch_slot)
+            if self.gather_patches:
+                _lib.check(lib.pvr_vit_patchify(self.frames.data_ptr(), n, self.res, self.p, self.patch_k, 0,
+                                                self.col.data_ptr(), st()), "pvr_vit_patchify")
+                gemm(self.col, self.patch_w, self.patches, n * self.grid ** 2, W, self.patch_k, bias=self.patch_b)
+                patches = self.patches.data_ptr()
+            else:
+                self.patch_enc.forward(self.dummy, 1)
+                patches = self.patch_enc.slot_ptr(self.patch_slot)
             g, bta = (self.ln_pre[0].data_ptr(), self.ln_pre[1].data_ptr()) if self.ln_pre is not None else (None, None)
             _lib.check(lib.pvr_vit_embed(patches, self.cls.data_ptr(), self.pos.data_ptr(), n, S, W, g, bta, eps,
                                          self.x.data_ptr(), st()), "pvr_vit_embed")
@@ -287,13 +310,22 @@ class ViTRunnerF32:
         self.in_slot = prog.new_slot(self.p * self.grid * cpp * 2)  # float32 values: two bf16 elements each
         pbias = spec["patch_bias"]
         pbias = torch.zeros(self.W) if pbias is None else pbias.detach().cpu().float()
-        self.patch_slot = prog.alloc(self.grid * self.W * 2)
-        prog.conv(self.in_slot, (cpp, self.p, self.grid),
-                  pack_patch_weight(spec["patch_weight"].detach().cpu().float(), torch.float32), self.p * cpp, self.W,
-                  self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), pbias, 0, out_slot=self.patch_slot,
-                  out_pitch=self.W, flags=prg.F32)
-        prog.emb_width = 1
-        self.patch_enc = prog.finish(dev)
+        self.gather_patches = (cpp * 2) % 128 != 0  # same split as ViTRunner (mae_huge: p = 14)
+        if self.gather_patches:
+            self.patch_enc = None
+            k = 3 * self.p * self.p
+            self.patch_k = (k + 63) // 64 * 64
+            wp = torch.zeros(self.W, self.patch_k)
+            wp[:, :k] = spec["patch_weight"].detach().cpu().float().reshape(self.W, k)
+            self.patch_w, self.patch_b = wp.to(dev).contiguous(), pbias.to(dev)
+        else:
+            self.patch_slot = prog.alloc(self.grid * self.W * 2)
+            prog.conv(self.in_slot, (cpp, self.p, self.grid),
+                      pack_patch_weight(spec["patch_weight"].detach().cpu().float(), torch.float32), self.p * cpp,
+                      self.W, self.p, 1, (1, 1), (0, 0), (1, self.grid), torch.ones(self.W), pbias, 0,
+                      out_slot=self.patch_slot, out_pitch=self.W, flags=prg.F32)
+            prog.emb_width = 1
+            self.patch_enc = prog.finish(dev)
         self.cls, self.pos = f(spec["cls"].reshape(-1)), f(spec["pos"].reshape(self.S, self.W))
         self.ln_pre = tuple(f(t) for t in spec["ln_pre"]) if spec["ln_pre"] is not None else None
         self.ln_post = tuple(f(t) for t in spec["ln_post"])
@@ -309,7 +341,10 @@ class ViTRunnerF32:
         if n == self.n:
             return
         dev, M, W = self.device, n * self.S, self.W
-        self.patch_enc.bind(n * self.grid)
+        if self.gather_patches:
+            self.frames = torch.empty(n, self.res, self.res, 4, dtype=torch.float32, device=dev)
+        else:
+            self.patch_enc.bind(n * self.grid)
         f32 = torch.float32
         self.x = torch.empty(M, W, dtype=f32, device=dev)
         self.y = torch.empty(M, W, dtype=f32, device=dev)
@@ -318,14 +353,17 @@ class ViTRunnerF32:
         self.h = torch.empty(M, 4 * W, dtype=f32, device=dev)
         self.clsy = torch.empty(n, W, dtype=f32, device=dev)
         self.dummy = torch.zeros(n * self.grid, 1, device=dev)
+        if self.gather_patches:
+            self.col = torch.empty(n * self.grid ** 2, self.patch_k, dtype=f32, device=dev)
+            self.patches = torch.empty(n * self.grid ** 2, W, dtype=f32, device=dev)
         self.n = n
 
     @property
     def slot0(self):
-        return self.patch_enc.slot0
+        return self.frames.data_ptr() if self.gather_patches else self.patch_enc.slot0
 
     def launches_per_forward(self):
-        return 2 + 7 * self.L + 2
+        return (3 if self.gather_patches else 2) + 7 * self.L + 2
 
     def _gemm(self, a, w, bias, out, M, N, K, res=None, act=0):
         _lib.check(self.lib.pvr_gemm_f32(a.data_ptr(), a.stride(0), w.data_ptr(), bias.data_ptr(),
@@ -342,8 +380,14 @@ class ViTRunnerF32:
         lib, n, S, W, M = self.lib, self.n, self.S, self.W, self.n * self.S
         ld = out_ld if out_ld is not None else out.stride(0)
         with torch.cuda.device(self.device):
-            self.patch_enc.forward(self.dummy, 1)
-            patches = self.patch_enc.slot_ptr(self.patch_slot)
+            if self.gather_patches:
+                _lib.check(lib.pvr_vit_patchify(self.frames.data_ptr(), n, self.res, self.p, self.patch_k, 1,
+                                                self.col.data_ptr(), _lib.current_stream_ptr()), "pvr_vit_patchify")
+                self._gemm(self.col, self.patch_w, self.patch_b, self.patches, n * self.grid ** 2, W, self.patch_k)
+                patches = self.patches.data_ptr()
+            else:
+                self.patch_enc.forward(self.dummy, 1)
+                patches = self.patch_enc.slot_ptr(self.patch_slot)
             g, bta = (self.ln_pre[0].data_ptr(), self.ln_pre[1].data_ptr()) if self.ln_pre is not None else (None, None)
             _lib.check(lib.pvr_vit_embed_f32(patches, self.cls.data_ptr(), self.pos.data_ptr(), n, S, W, g, bta,
                                              self.eps, self.x.data_ptr(), _lib.current_stream_ptr()),

@@ -28,6 +28,8 @@ from .moco import _ALLOW_RANDOM_INIT
 _CONFIGS = {  # mae.py:275-298
     "mae_base": dict(patch_size=16, embed_dim=768, depth=12, num_heads=12, checkpoint="mae_pretrain_vit_base.pth"),
     "mae_large": dict(patch_size=16, embed_dim=1024, depth=24, num_heads=16, checkpoint="mae_pretrain_vit_large.pth"),
+    # 16 x 16 patches of 14 x 14 + class token = 257 tokens, 16 heads of 80: attention_mma.cu, vit_patchify.cu
+    "mae_huge": dict(patch_size=14, embed_dim=1280, depth=32, num_heads=16, checkpoint="mae_pretrain_vit_huge.pth"),
 }
 
 
@@ -142,9 +144,7 @@ def mae_spec(m):
 
 
 def load(name, checkpoint_path=None):
-    """`mae_vit_*_patch16()` + `load_state_dict(torch.load(path)['model'], strict=False)` of src/embeddings.py:137-144."""
-    if name == "mae_huge":
-        raise NotImplementedError("mae_huge (patch 14, head_dim 80) is not built: the attention kernel is head_dim 64")
+    """`mae_vit_*_patch1x()` + `load_state_dict(torch.load(path)['model'], strict=False)` of src/embeddings.py:137-148."""
     if name not in _CONFIGS:
         raise NotImplementedError("Requested model not available.")
     model = MAEParams(name)

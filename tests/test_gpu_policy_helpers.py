@@ -83,3 +83,34 @@ def test_sumsq_matches_double_sum():
             "pvr_optim_sumsq")
     ref = sum(float((t.double() ** 2).sum()) for t in ts)
     assert abs(float(out) - ref) <= 1e-10 * ref
+
+
+@pytest.mark.parametrize("F,H", [(6, 64), (3, 30), (2, 17)])
+def test_small_conv1_wgrad_vs_torch(F, H):
+    """First-layer weight / bias gradient of the small-conv trunk (src/models.py:108) against torch autograd on the
+    same bf16-rounded operands: dz = bf16(dy * ELU'(y)), products accumulated in fp32."""
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(F * 100 + H)
+    Ho = (H - 1) // 2 + 1
+    x = torch.zeros(F, H, H, 4, device="cuda")
+    x[..., :3] = torch.rand(F, H, H, 3, device="cuda", generator=g)
+    xb = x.bfloat16()
+    y = (torch.randn(F, Ho, Ho, 32, device="cuda", generator=g) * 0.7).bfloat16()  # ELU output: > -1
+    y = torch.where(y.float() < -0.99, torch.full_like(y, -0.5), y)
+    dy = torch.randn(F * Ho * Ho, 32, device="cuda", generator=g)
+    dw = torch.zeros(32, 3, 3, 4, device="cuda")
+    db = torch.zeros(32, device="cuda")
+    L.check(lib.pvr_small_conv1_wgrad(dy.data_ptr(), y.data_ptr(), 32, xb.data_ptr(), F, H, H, Ho, Ho, dw.data_ptr(),
+                                      db.data_ptr(), _stream()), "pvr_small_conv1_wgrad")
+    yf = y.float().reshape(-1, 32)
+    dz = (dy * torch.where(yf > 0, torch.ones_like(yf), yf + 1)).bfloat16().double()
+    xin = xb.double().permute(0, 3, 1, 2)[:, :3].contiguous().requires_grad_(False)
+    w = torch.zeros(32, 3, 3, 3, device="cuda", dtype=torch.float64, requires_grad=True)
+    out = torch.nn.functional.conv2d(xin, w, stride=2, padding=1)  # (F, 32, Ho, Ho)
+    out.backward(dz.reshape(F, Ho, Ho, 32).permute(0, 3, 1, 2))
+    ref = w.grad.permute(0, 2, 3, 1)  # (co, a, b, c)
+    scale = float(ref.abs().max())
+    assert float((dw[..., :3].double() - ref).abs().max()) < 2e-5 * scale + 1e-6
+    assert not dw[..., 3].any()
+    ref_b = dz.sum(0)
+    assert float((db.double() - ref_b).abs().max()) < 2e-5 * float(ref_b.abs().max()) + 1e-6

@@ -60,6 +60,15 @@ int pvr_abi_version(void);
 /* OR-ed into out_fmt: Resize is bicubic (A = -0.75, no antialias, clamped to [0, 255] before the rounding cast) instead
  * of bilinear — T.Resize(256, interpolation=3) of the MAE encoders, src/embeddings.py:81. */
 #define PVR_RESIZE_BICUBIC 0x100
+/* OR-ed into out_fmt (bilinear only) — the 'maskrcnn_l3' transforms of src/embeddings.py:283-294, which resize a FLOAT
+ * image: the bilinear interpolant is not rounded back to uint8 and not divided by 255; out = (v - mean) / stdv with
+ * mean = (103.530, 116.280, 123.675), stdv = 1 on values in [0, 255]. */
+#define PVR_RESIZE_FLOAT 0x200
+/* OR-ed into out_fmt: rows 0 and 2 of every image trade places before the resize. That is what the reference's
+ * `_rgb_to_bgr` does (src/embeddings.py:285-288): `x[:,:,[0,1,2]] = x[:,:,[2,1,0]]` indexes dimension 2 of the NCHW
+ * tensor — the rows — so the channels stay RGB and three rows are permuted; reproduced as is for parity (with
+ * CenterCrop(224) of a 256-row resize the rows only reach the output for frames of fewer than 54 rows). */
+#define PVR_SWAP_ROWS_0_2 0x400
 int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_frames, int rh, int rw, int top, int left,
                       int crop, const float* mean, const float* stdv, void* out, int out_fmt, int sample_major,
                       void* stream);

@@ -306,6 +306,42 @@ def golden_mae_huge(E):
     np.savez_compressed(os.path.join(GOLDEN, "mae_huge.npz"), **out)
 
 
+def golden_maskrcnn(E):
+    """EmbeddingNet('maskrcnn_l3') of the reference (src/embeddings.py:283-295, :380-383; src/vision_models/maskrcnn.py)
+    on a synthetic checkpoint: its transforms (torchvision) and model surgery run unmodified; detectron2's backbone
+    classes come from the restatement in oracle/restate_maskrcnn.py (detectron2 is not installed).
+    torchvision 0.26 would route the float Resize through the antialiased kernel (same weights when up-scaling, another
+    summation order); the reference pins torchvision 0.10: `antialias = False` on the constructed Resize object."""
+    from oracle import restate_maskrcnn
+    seed = 301
+    sd = restate_maskrcnn.maskrcnn_state(seed)
+    full = {"backbone." + k: v for k, v in sd.items()}
+    g = torch.Generator().manual_seed(seed)
+    for k, v in restate_maskrcnn.BasicBlock(11, 1024).state_dict().items():  # res4[7]: loaded strictly, then dropped
+        full["backbone.res4.7." + k] = torch.randn(v.shape, generator=g) if v.dtype.is_floating_point else v
+    with tempfile.TemporaryDirectory() as d, refshim.chdir(d):
+        torch.save({"model": full}, os.path.join(d, "maskrcnn_l3.pth"))
+        net = E.EmbeddingNet("maskrcnn_l3", pretrained=True, train=False, disable_cuda=True)
+    net.transforms[1].antialias = False
+    cases = {
+        "structured_64": restate.structured_frames(2, 64, 64, 3, 71),
+        "structured_224": restate.structured_frames(1, 224, 224, 3, 72),
+        "small_40x48": restate.structured_frames(1, 40, 48, 3, 73),   # < 54 rows: the permuted rows 0 / 2 reach the crop
+        "adversarial_64": restate.adversarial_frames(64, 64)[:2],
+    }
+    out = {"seed": np.array(seed), "out_size": np.array(int(net.out_size)),
+           "state_keys": np.array(sorted(net.state_dict().keys()))}
+    for name, frames in cases.items():
+        x = torch.from_numpy(frames).permute(0, 3, 1, 2).contiguous()
+        t = net.transforms(x.clone()).numpy()
+        out["in_" + name] = frames
+        out["t_top_" + name] = t[:, :, :12]          # the rows the reference's row permutation can reach
+        out["t_sub_" + name] = t[:, :, ::7, ::5]
+        out["emb_" + name] = np.atleast_2d(net(torch.from_numpy(frames)))
+        print(name, t.shape, float(np.abs(out["emb_" + name]).mean()))
+    np.savez_compressed(os.path.join(GOLDEN, "maskrcnn.npz"), **out)
+
+
 def golden_clip_transforms(E):
     """The `transforms` the reference builds for 'clip_vit' (src/embeddings.py:309-314: antialiased bicubic Resize(224)
     -> CenterCrop(224) -> float -> CLIP Normalize), run on frames that are not 224x224 (Habitat renders 64x64). The
@@ -414,7 +450,7 @@ def main():
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
     if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which or \
-            "mae" in which or "mae_huge" in which or "save_embedded" in which or "clip_transforms" in which:
+            "mae" in which or "mae_huge" in which or "maskrcnn" in which or "save_embedded" in which or "clip_transforms" in which:
         E = refshim.reference_embeddings()
         if "clip_transforms" in which:
             golden_clip_transforms(E)
@@ -424,6 +460,8 @@ def main():
             golden_mae(E)
         if "mae_huge" in which:
             golden_mae_huge(E)
+        if "maskrcnn" in which:
+            golden_maskrcnn(E)
         if "resnet_basic" in which:
             golden_resnet_basic(E)
         if "transforms" in which:

@@ -1,8 +1,9 @@
 """ORACLE (build container only) — import the UNMODIFIED reference from /root/reference.
 
 The reference needs gym / detectron2 / timm / habitat at import time (src/embeddings.py:2-3,
-src/vision_models/maskrcnn.py:2-20, src/vision_models/mae.py:20); none is installed. gym / detectron2 are not on the
-hot path and are replaced by inert stub modules; `timm.models.vision_transformer` (mae.py:20 needs PatchEmbed and Block
+src/vision_models/maskrcnn.py:2-20, src/vision_models/mae.py:20); none is installed. gym is not on the hot path and is replaced by an inert stub
+module; detectron2's ResNet backbone classes (maskrcnn.py builds `maskrcnn_l3` from them) are served by the restatement
+in oracle/restate_maskrcnn.py, the rest of detectron2 by inert classes; `timm.models.vision_transformer` (mae.py:20 needs PatchEmbed and Block
 to build the MAE encoders) is served by the restatement of timm 0.5.4 in oracle/restate_mae.py. `np.float`, which
 mae.py:58 still uses, left numpy in 1.24: it is restored as the alias of `float` it used to be.
 Checkpoint-backed encoders (src/embeddings.py:151-236) read hard-coded relative paths: `write_checkpoints` writes synthetic checkpoints under those names into a scratch directory and the
@@ -46,11 +47,12 @@ def install_stubs():
         gym.spaces = spaces
         spaces.box = box
         sys.modules.update({"gym": gym, "gym.spaces": spaces, "gym.spaces.box": box})
-    for name in ("detectron2", "detectron2.layers", "detectron2.config", "detectron2.modeling",
-                 "detectron2.modeling.meta_arch", "detectron2.modeling.anchor_generator",
-                 "detectron2.modeling.backbone", "detectron2.modeling.backbone.resnet",
-                 "detectron2.modeling.box_regression", "detectron2.modeling.matcher", "detectron2.modeling.poolers",
-                 "detectron2.modeling.proposal_generator", "detectron2.modeling.roi_heads", "timm", "timm.models"):
+    if "detectron2" not in sys.modules:
+        # the backbone classes mask_rcnn_model builds are served by the restatement of detectron2 in
+        # oracle/restate_maskrcnn.py; everything else in the package (RPN, ROI heads, ...) is an inert class
+        from oracle import restate_maskrcnn
+        restate_maskrcnn.install_detectron2()
+    for name in ("timm", "timm.models"):
         sys.modules.setdefault(name, _Anything(name))
     if "timm.models.vision_transformer" not in sys.modules:
         import numpy as np

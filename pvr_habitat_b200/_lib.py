@@ -11,6 +11,8 @@ PVR_FMT_STEM_BF16 = 2
 PVR_FMT_NHWC4_F32 = 3
 PVR_FMT_STEM_PAD_BF16 = 4
 PVR_RESIZE_BICUBIC = 0x100
+PVR_RESIZE_FLOAT = 0x200
+PVR_SWAP_ROWS_0_2 = 0x400
 PVR_COMM_F32, PVR_COMM_F64, PVR_COMM_BF16, PVR_COMM_I64 = 0, 1, 2, 3
 PVR_OP_FP32 = 2
 PVR_CONV_OUT_F32 = 1

@@ -29,7 +29,20 @@ struct PreParams {
   int fmt;
   int sample_major;  // image index of (sample i, frame f): i*nf + f instead of f*N + i
   int pix_off;       // byte offset of the bf16 pixel buffer inside dynamic smem (PVR_FMT_STEM_BF16)
+  int flt;           // PVR_RESIZE_FLOAT: no rounding back to uint8, no /255: (v - mean) / std on the fp32 interpolant
+  int swap02;        // PVR_SWAP_ROWS_0_2: image rows 0 and 2 trade places before the resize
 };
+
+// bilinear interpolant v of channel c -> output value
+__device__ __forceinline__ float finish_bilinear(const PreParams& p, float v, int c, const float* lut) {
+  if (p.flt) return __fdiv_rn(__fsub_rn(v, p.mean[c]), p.stdv[c]);  // Normalize: sub_(mean).div_(std)
+  int u = (int)rintf(v);  // half to even, as torch.round
+  u = min(max(u, 0), 255);
+  return lut[c * 256 + u];
+}
+__device__ __forceinline__ int swap_row(const PreParams& p, int r) {
+  return p.swap02 ? (r == 0 ? 2 : (r == 2 ? 0 : r)) : r;
+}
 
 __device__ __forceinline__ void src_index(float scale, int dst, int size, int& i0, int& i1, float& l) {
   // ATen area_pixel_compute_source_index(align_corners=false) + guard_index_and_lambda. The x86 build of ATen
@@ -116,6 +129,10 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
   } else {
     src_index(p.scale_y, y_first + p.top, p.H, r_lo, tmp, lf);
     src_index(p.scale_y, y_first + y_count - 1 + p.top, p.H, tmp, r_hi, lf);
+    if (p.swap02 && r_lo <= 2) {  // a band that touches rows 0..2 stages all three
+      r_lo = 0;
+      r_hi = max(r_hi, 2);
+    }
   }
   const long long row_bytes = (long long)p.W * p.CH;
   const long long g0 = (long long)img * p.H * row_bytes + (long long)r_lo * row_bytes;
@@ -172,6 +189,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
           float ly, lx;
           src_index(p.scale_y, y_first + yy + p.top, p.H, r0, r1, ly);
           src_index(p.scale_x, x + p.left, p.W, c0, c1, lx);
+          r0 = swap_row(p, r0);
+          r1 = swap_row(p, r1);
           const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
           const uint8_t* q00 = s + (long long)(r0 - r_lo) * row_bytes + c0 * p.CH + 3 * f;
           const uint8_t* q01 = s + (long long)(r0 - r_lo) * row_bytes + c1 * p.CH + 3 * f;
@@ -182,9 +201,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
             const float top = __fmaf_rn((float)q00[c], hx, __fmul_rn((float)q01[c], lx));
             const float bot = __fmaf_rn((float)q10[c], hx, __fmul_rn((float)q11[c], lx));
             const float v = __fmaf_rn(top, hy, __fmul_rn(bot, ly));
-            int u = (int)rintf(v);
-            u = min(max(u, 0), 255);
-            o[c] = lut[c * 256 + u];
+            o[c] = finish_bilinear(p, v, c, lut);
           }
         }
         __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]);
@@ -232,6 +249,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
     } else {
       src_index(p.scale_y, y + p.top, p.H, r0, r1, ly);
       src_index(p.scale_x, x + p.left, p.W, c0, c1, lx);
+      r0 = swap_row(p, r0);
+      r1 = swap_row(p, r1);
     }
     const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
     const uint8_t* q00 = s + (long long)(r0 - r_lo) * row_bytes + c0 * p.CH;
@@ -248,9 +267,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PreParams p) {
         const float top = __fmaf_rn((float)q00[ch], hx, __fmul_rn((float)q01[ch], lx));
         const float bot = __fmaf_rn((float)q10[ch], hx, __fmul_rn((float)q11[ch], lx));
         const float v = __fmaf_rn(top, hy, __fmul_rn(bot, ly));
-        int u = (int)rintf(v);  // half to even, as torch.round
-        u = min(max(u, 0), 255);
-        o[c] = lut[c * 256 + u];
+        o[c] = finish_bilinear(p, v, c, lut);
       }
       // frame-major is the reference's np.concatenate(np.split(o, n, 3), 0) order
       const long long image = p.sample_major ? (long long)img * p.nf + f : (long long)f * p.N + img;
@@ -284,7 +301,12 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
                                  int sample_major, void* stream) {
   using namespace pvr;
   const bool cubic = (out_fmt & PVR_RESIZE_BICUBIC) != 0;
-  out_fmt &= ~PVR_RESIZE_BICUBIC;
+  const bool flt = (out_fmt & PVR_RESIZE_FLOAT) != 0, swap02 = (out_fmt & PVR_SWAP_ROWS_0_2) != 0;
+  out_fmt &= ~(PVR_RESIZE_BICUBIC | PVR_RESIZE_FLOAT | PVR_SWAP_ROWS_0_2);
+  if ((flt || swap02) && (cubic || H < 3)) {
+    pvr_set_error("pvr_preprocess_u8: PVR_RESIZE_FLOAT / PVR_SWAP_ROWS_0_2 are bilinear-only and need >= 3 rows");
+    return PVR_ERR_ARG;
+  }
   if (!in || !out || N <= 0 || H <= 0 || W <= 0 || n_frames <= 0 || rh <= 0 || rw <= 0 || crop <= 0 || top < 0 ||
       left < 0 || top + crop > rh || left + crop > rw || !mean || !stdv ||
       (out_fmt != PVR_FMT_NCHW_F32 && out_fmt != PVR_FMT_NHWC4_BF16 && out_fmt != PVR_FMT_STEM_BF16 &&
@@ -308,10 +330,12 @@ extern "C" int pvr_preprocess_u8(const uint8_t* in, int N, int H, int W, int n_f
   for (int c = 0; c < 3; ++c) { p.mean[c] = mean[c]; p.stdv[c] = stdv[c]; }
   p.fmt = out_fmt;
   p.sample_major = sample_major ? 1 : 0;
+  p.flt = flt ? 1 : 0;
+  p.swap02 = swap02 ? 1 : 0;
   // rows per band: keep the staged input under ~48 KiB so several CTAs share an SM
   const long long row_bytes = (long long)W * p.CH;
   int rows = 16;
-  auto stage_bytes = [&](int r) { return ((long long)(p.scale_y * r) + (cubic ? 5 : 3)) * row_bytes + 48; };
+  auto stage_bytes = [&](int r) { return ((long long)(p.scale_y * r) + (cubic ? 5 : (swap02 ? 6 : 3))) * row_bytes + 48; };
   while (rows > 1 && stage_bytes(rows) > 48 * 1024) rows >>= 1;
   long long smem = 16 + 3072 + stage_bytes(rows);
   p.pix_off = 0;

@@ -16,6 +16,7 @@ from . import _lib
 from . import program as prg
 from .vision_models import clip_vit
 from .vision_models import mae as mae_vit
+from .vision_models import maskrcnn
 from .vision_models.moco import moco_conv3_compressed, moco_conv4_compressed, moco_conv5, random_init_allowed
 from .vision_models.resnet import resnet_conv3_compressed, resnet_conv4_compressed, resnet_conv5
 from .vision_models.resnet_params import ResNet50Params, ResNetBasicParams
@@ -45,9 +46,11 @@ class Transforms(nn.Module):
     def __init__(self, mean=IMAGENET_MEAN, std=IMAGENET_STD, size=256, crop=224, interpolation='bilinear'):
         super().__init__()
         self.mean, self.std, self.size, self.crop = list(mean), list(std), size, crop
-        assert interpolation in ('bilinear', 'bicubic', 'bicubic_aa')
+        assert interpolation in ('bilinear', 'bicubic', 'bicubic_aa', 'bilinear_float_rows02')
         # 'bicubic': T.Resize(256, interpolation=3) of the MAE encoders; 'bicubic_aa': CLIP's antialiased bicubic Resize
-        # (pvr_preprocess_u8_aa, csrc/preprocess_aa.cu)
+        # (pvr_preprocess_u8_aa, csrc/preprocess_aa.cu); 'bilinear_float_rows02': the maskrcnn_l3 transforms
+        # (src/embeddings.py:283-294) — `_rgb_to_bgr` (which permutes ROWS 0 and 2, not channels), `.float()`, Resize of
+        # the float image (no uint8 rounding), CenterCrop, Normalize on the 0..255 scale
         self.interpolation = interpolation
         self.identity_resize_only = False  # debugging aid: reject frames that would need an actual resize
 
@@ -72,6 +75,8 @@ class Transforms(nn.Module):
         fn, name = _lib.lib().pvr_preprocess_u8, "pvr_preprocess_u8"
         if self.interpolation == 'bicubic':
             fmt |= _lib.PVR_RESIZE_BICUBIC
+        elif self.interpolation == 'bilinear_float_rows02':
+            fmt |= _lib.PVR_RESIZE_FLOAT | _lib.PVR_SWAP_ROWS_0_2
         elif self.interpolation == 'bicubic_aa' and (rh, rw) != (h, w):
             # (torchvision leaves an image whose short side already has the requested size untouched,
             # tv:transforms/functional.py:468-471: that case is the scale-1 path of the bilinear kernel = a copy)
@@ -227,10 +232,15 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
             raise NotImplementedError("Requested model not available.")
         transforms = Transforms(CLIP_MEAN, CLIP_STD, size=model.visual.input_resolution,
                                 crop=model.visual.input_resolution, interpolation='bicubic_aa')
+    elif embedding_name == 'maskrcnn_l3':
+        # src/embeddings.py:283-295: detectron2 R50-C4 backbone through res4 + the 1024 -> 11 compression block; the
+        # frames stay on the 0..255 scale (Normalize with detectron2's pixel means, std 1) and are resized as floats
+        model = maskrcnn.mask_rcnn_model(checkpoint_path='maskrcnn_l3.pth')
+        transforms = Transforms(maskrcnn.PIXEL_MEAN, [1.0, 1.0, 1.0], interpolation='bilinear_float_rows02')
     elif embedding_name == 'true_state':
         return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
     else:
-        # clip_rn50, maskrcnn_l3: not built yet (see DESIGN.md scope table)
+        # clip_rn50: not built (see DESIGN.md scope table)
         raise NotImplementedError("Requested model not available.")
 
     if train:
@@ -239,6 +249,12 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
     for p in model.parameters():
         p.requires_grad = False
     return model, transforms
+
+
+def _program_sd(m, sd):
+    """Containers whose keys are not torchvision's (maskrcnn.MaskRCNNBackboneParams: detectron2 names) translate
+    their state_dict into the naming program.add_resnet50 reads."""
+    return m.program_state_dict(sd) if hasattr(m, 'program_state_dict') else sd
 
 
 def build_encoder(model, device, hw=224, precision='bf16'):
@@ -258,7 +274,8 @@ def build_encoder(model, device, hw=224, precision='bf16'):
             elif isinstance(m, ResNetBasicParams):
                 off += prg.add_resnet_basic_f32(prog, sd, m.LAYERS[m.name], in_slot, off, hw)
             else:
-                off += prg.add_resnet50_f32(prog, sd, m.variant, in_slot, off, hw)
+                off += prg.add_resnet50_f32(prog, _program_sd(m, sd), m.variant, in_slot, off, hw,
+                                            stride_in_1x1=getattr(m, 'stride_in_1x1', False))
         prog.emb_width = off
         enc = prog.finish(device)
         enc.input_format = _lib.PVR_FMT_NHWC4_F32
@@ -284,7 +301,8 @@ def build_encoder(model, device, hw=224, precision='bf16'):
         if isinstance(m, ResNetBasicParams):
             off += prg.add_resnet_basic(prog, sd, m.LAYERS[m.name], in_slot, off, hw, compact_stem=compact)
         else:
-            off += prg.add_resnet50(prog, sd, m.variant, in_slot, off, hw, compact_stem=compact)
+            off += prg.add_resnet50(prog, _program_sd(m, sd), m.variant, in_slot, off, hw, compact_stem=compact,
+                                    stride_in_1x1=getattr(m, 'stride_in_1x1', False))
     prog.emb_width = off
     enc = prog.finish(device)
     enc.input_format = _lib.PVR_FMT_STEM_PAD_BF16 if compact else _lib.PVR_FMT_STEM_BF16

@@ -267,14 +267,16 @@ def _conv_bn(prog, sd, conv_key, bn_key, in_slot, in_chw, stride, pad, relu, res
     return out, (co, p, q)
 
 
-def _bottleneck(prog, sd, prefix, x_slot, x_chw, stride, has_ds):
-    """torchvision Bottleneck (resnet.py:143-166), stride on the 3x3 conv (v1.5).
+def _bottleneck(prog, sd, prefix, x_slot, x_chw, stride, has_ds, stride_in_1x1=False):
+    """torchvision Bottleneck (resnet.py:143-166), stride on the 3x3 conv (v1.5); `stride_in_1x1`: on conv1 instead
+    (detectron2's BottleneckBlock as src/vision_models/maskrcnn.py:52-56 configures it, the MSRA / Caffe layout).
 
     Blocks with a projection shortcut compute `relu(bn3(conv3(t2)) + bn_d(conv_d(x)))` as ONE GEMM over the
     concatenated K = [t2 channels | x channels]: both BN scales are folded into the weight rows, the bias is b3 + b_d.
     The shortcut tensor is neither written nor re-read (layer1.0: 411 MB + 411 MB per 256 frames)."""
-    t1, s1 = _conv_bn(prog, sd, prefix + ".conv1", prefix + ".bn1", x_slot, x_chw, 1, 0, True)
-    t2, s2 = _conv_bn(prog, sd, prefix + ".conv2", prefix + ".bn2", t1, s1, stride, 1, True)
+    st1, st2 = (stride, 1) if stride_in_1x1 else (1, stride)
+    t1, s1 = _conv_bn(prog, sd, prefix + ".conv1", prefix + ".bn1", x_slot, x_chw, st1, 0, True)
+    t2, s2 = _conv_bn(prog, sd, prefix + ".conv2", prefix + ".bn2", t1, s1, st2, 1, True)
     prog.release(t1)
     if has_ds and x_chw[0] % 64 == 0 and s2[0] % 64 == 0:
         w3 = sd[prefix + ".conv3.weight"].float()
@@ -344,7 +346,7 @@ def _compress_head(prog, sd, prefix, x_slot, x_chw, emb_offset):
     return c * h * w
 
 
-def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224, compact_stem=False):
+def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224, compact_stem=False, stride_in_1x1=False):
     """Append one ResNet-50 trunk reading the W-expanded bf16 frames (PVR_FMT_STEM_BF16) in `in_slot`.
 
     variant: 'conv5' (moco_conv5 / resnet50: avg-pooled 2048), 'l4' (moco_conv4_compressed: 42*7*7 = 2058),
@@ -371,7 +373,7 @@ def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224, compact_stem=Fa
         elif name == "layer4":
             key = pre[1]
         for b in range(blocks):
-            x, chw = _bottleneck(prog, sd, f"{key}{b}", x, chw, stride if b == 0 else 1, b == 0)
+            x, chw = _bottleneck(prog, sd, f"{key}{b}", x, chw, stride if b == 0 else 1, b == 0, stride_in_1x1)
     if variant == "conv5":
         prog.avgpool(x, chw[0], chw[1], chw[2], emb_offset)
         prog.release(x)
@@ -459,7 +461,7 @@ def _stem_f32(prog, sd, in_slot, hw):
     return x, (64, h, w)
 
 
-def add_resnet50_f32(prog, sd, variant, in_slot, emb_offset, hw=224):
+def add_resnet50_f32(prog, sd, variant, in_slot, emb_offset, hw=224, stride_in_1x1=False):
     """fp32 counterpart of add_resnet50 (same variants, same embedding columns)."""
     pre = {"conv5": ("layer3.", "layer4."), "l4": ("layer3.", "layer4.0."), "l3": ("layer3.0.", None)}[variant]
     x, chw = _stem_f32(prog, sd, in_slot, hw)
@@ -469,8 +471,9 @@ def add_resnet50_f32(prog, sd, variant, in_slot, emb_offset, hw=224):
         key = {"layer3": pre[0], "layer4": pre[1]}.get(name, name + ".")
         for b in range(blocks):
             px, st = f"{key}{b}", (stride if b == 0 else 1)
-            t1, s1 = _conv_bn_f32(prog, sd, px + ".conv1", px + ".bn1", x, chw, 1, 0, True)
-            t2, s2 = _conv_bn_f32(prog, sd, px + ".conv2", px + ".bn2", t1, s1, st, 1, True)
+            st1, st2 = (st, 1) if stride_in_1x1 else (1, st)
+            t1, s1 = _conv_bn_f32(prog, sd, px + ".conv1", px + ".bn1", x, chw, st1, 0, True)
+            t2, s2 = _conv_bn_f32(prog, sd, px + ".conv2", px + ".bn2", t1, s1, st2, 1, True)
             prog.release(t1)
             if b == 0:
                 idn, sidn = _conv_bn_f32(prog, sd, px + ".downsample.0", px + ".downsample.1", x, chw, st, 0, False)

@@ -94,6 +94,8 @@ int pvr_preprocess_u8_aa(const uint8_t* in, int N, int H, int W, int n_frames, i
                              act == 0: input = bf16 (2c) per pixel [relu(bn1(conv1 x)) | bn_d(conv_d x)];
                              act == 1: input = float32 per-tap partial sums, 9 x 2c per pixel (pitch in floats): the op
                              first forms sum_tap Z[p + tap - 1][tap], applies scale1/bias1 (+ ReLU on the first c) */
+#define PVR_OP_AVGPOOL2 6 /* 2x2 stride-2 average pool NHWC -> NHWC (nn.AvgPool2d(2) of CLIP's ModifiedResNet); bf16 or,
+                           * with PVR_OP_FP32 in flags, float32 */
 #define PVR_OP_FLATTEN 5  /* NHWC bf16 slot -> NCHW-flattened float32 embedding columns (`out.view(-1, out_size)`) */
 
 /* CONV flag: the output slot holds float32 values (out_pitch floats per pixel; the slot is sized as 2*out_pitch bf16
@@ -219,6 +221,11 @@ int pvr_attention(const void* qkv_bf16, int n_img, int tokens, int width, int he
 /* Same contract for any head_dim in {64, 80, 96, 128} and any sequence whose K / V fit shared memory (mae_huge,
  * src/vision_models/mae.py:291-296: 257 tokens, 16 heads of 80): warp-level mma.sync kernel with online softmax
  * (csrc/attention_mma.cu). pvr_attention forwards here for the shapes its tcgen05 kernel does not cover. */
+/* Token assembly of CLIP's AttentionPool2d (openai/CLIP clip/model.py; `clip.load("RN50")`, src/embeddings.py:305-306):
+ * tokens (n_img, hw + 1, width) with tokens[i][0] = mean_j x[i][j] + pos[0], tokens[i][j + 1] = x[i][j] + pos[j + 1];
+ * x (n_img, hw, width) is the NHWC output of layer4. f32 = 0: bf16 in / out; f32 = 1: float32 in / out. */
+int pvr_attnpool_tokens(const void* x, int n_img, int hw, int width, const float* pos, int f32, void* tokens,
+                        void* stream);
 int pvr_attention_mma(const void* qkv_bf16, int n_img, int tokens, int width, int heads, void* out_bf16, void* stream);
 /* im2col of non-overlapping p x p patches (timm PatchEmbed, Conv2d(3, width, p, stride p), for patch sizes whose rows
  * are not a whole number of 128-byte TMA rows: mae_huge, p = 14): col (n_img * grid * grid, k_pad) with

@@ -342,6 +342,42 @@ def golden_maskrcnn(E):
     np.savez_compressed(os.path.join(GOLDEN, "maskrcnn.npz"), **out)
 
 
+def golden_clip_rn50(E):
+    """EmbeddingNet('clip_rn50') of the reference (src/embeddings.py:305-314, 375-376): its transforms, `encode_image`
+    dispatch and output handling run unmodified; `clip.load("RN50")` is served by the restatement of openai/CLIP's
+    ModifiedResNet in oracle/restate_clip_rn.py (the `clip` package is not installed)."""
+    import types
+    from oracle import restate_clip_rn
+    seed = 401
+    sd = restate_clip_rn.clip_rn50_state(seed)
+
+    def load(name, device="cpu"):
+        assert name == "RN50"
+        m = restate_clip_rn.FakeClip()
+        m.load_state_dict(sd, strict=True)
+        return m.to(device), None
+
+    fake = types.ModuleType("clip")
+    fake.load = load
+    old = getattr(E, "clip", None)
+    E.clip = fake
+    try:
+        net = E.EmbeddingNet("clip_rn50", pretrained=True, train=False, disable_cuda=True)
+    finally:
+        if old is not None:
+            E.clip = old
+    cases = {"structured_64": restate.structured_frames(2, 64, 64, 3, 81),
+             "structured_224": restate.structured_frames(1, 224, 224, 3, 82),
+             "structured_96x128": restate.structured_frames(1, 96, 128, 3, 83)}
+    out = {"seed": np.array(seed), "out_size": np.array(int(net.out_size)),
+           "visual_keys": np.array(sorted(k for k in net.state_dict() if k.startswith("embedding.visual.")))}
+    for name, frames in cases.items():
+        out["in_" + name] = frames
+        out["emb_" + name] = np.atleast_2d(net(torch.from_numpy(frames)))
+        print(name, out["emb_" + name].shape, float(np.abs(out["emb_" + name]).mean()))
+    np.savez_compressed(os.path.join(GOLDEN, "clip_rn50.npz"), **out)
+
+
 def golden_clip_transforms(E):
     """The `transforms` the reference builds for 'clip_vit' (src/embeddings.py:309-314: antialiased bicubic Resize(224)
     -> CenterCrop(224) -> float -> CLIP Normalize), run on frames that are not 224x224 (Habitat renders 64x64). The
@@ -450,7 +486,7 @@ def main():
     torch.set_num_threads(8)
     which = sys.argv[1:] or ["transforms", "embeddings", "policy", "small_conv"]
     if "transforms" in which or "embeddings" in which or "small_conv" in which or "resnet_basic" in which or \
-            "mae" in which or "mae_huge" in which or "maskrcnn" in which or "save_embedded" in which or "clip_transforms" in which:
+            "mae" in which or "mae_huge" in which or "maskrcnn" in which or "clip_rn50" in which or "save_embedded" in which or "clip_transforms" in which:
         E = refshim.reference_embeddings()
         if "clip_transforms" in which:
             golden_clip_transforms(E)
@@ -462,6 +498,8 @@ def main():
             golden_mae_huge(E)
         if "maskrcnn" in which:
             golden_maskrcnn(E)
+        if "clip_rn50" in which:
+            golden_clip_rn50(E)
         if "resnet_basic" in which:
             golden_resnet_basic(E)
         if "transforms" in which:

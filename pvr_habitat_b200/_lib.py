@@ -18,7 +18,7 @@ PVR_OP_FP32 = 2
 PVR_CONV_OUT_F32 = 1
 PVR_GEMM_PDL, PVR_GEMM_MN = 1, 2
 PVR_LSTM_CONT_PREV, PVR_LSTM_CONT_NEXT = 1, 2
-PVR_OP_CONV, PVR_OP_MAXPOOL, PVR_OP_AVGPOOL, PVR_OP_HEAD, PVR_OP_FLATTEN = 1, 2, 3, 4, 5
+PVR_OP_CONV, PVR_OP_MAXPOOL, PVR_OP_AVGPOOL, PVR_OP_HEAD, PVR_OP_FLATTEN, PVR_OP_AVGPOOL2 = 1, 2, 3, 4, 5, 6
 
 
 class PvrError(RuntimeError):
@@ -93,6 +93,7 @@ _SIGNATURES = {
     "pvr_vit_embed": (ctypes.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _f, _vp, _vp]),
     "pvr_attention": (ctypes.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
     "pvr_attention_mma": (ctypes.c_int, [_vp, _i, _i, _i, _i, _vp, _vp]),
+    "pvr_attnpool_tokens": (ctypes.c_int, [_vp, _i, _i, _i, _vp, _i, _vp, _vp]),
     "pvr_vit_patchify": (ctypes.c_int, [_vp, _i, _i, _i, _i, _i, _vp, _vp]),
     "pvr_bn1d_stats": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, _vp]),
     "pvr_bn1d_normalize": (ctypes.c_int, [_vp, _i64, _i, _i, _vp, ctypes.c_double, _f, _f, _vp, _vp, _vp, _vp, _vp,

@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "lib", "libpvr_b200.so")
 OBJ = os.path.join(HERE, "lib", "obj")
 SOURCES = ["api.cu", "conv_gemm.cu", "preprocess.cu", "preprocess_aa.cu", "pool_head.cu", "policy.cu", "vit.cu",
            "conv3x3_patch.cu", "conv_b2b.cu", "conv_f32.cu", "policy_conv.cu", "lstm_persist.cu", "comm.cu",
-           "vit_f32.cu", "small_conv.cu", "attention_mma.cu", "vit_patchify.cu"]
+           "vit_f32.cu", "small_conv.cu", "attention_mma.cu", "vit_patchify.cu", "clip_rn.cu"]
 
 
 def _headers():

@@ -114,6 +114,12 @@ extern "C" int pvr_encoder_create(const pvr_op* ops, int n_ops, const pvr_slot* 
         pvr_set_error("pvr_encoder_create: op %d: c_in must be 8, 32 or a multiple of 64 (got %d)", i, o.c_in);
         return PVR_ERR_ARG;
       }
+    } else if (o.kind == PVR_OP_AVGPOOL2) {
+      if (o.h_in < 2 || o.w_in < 2 || o.h_out != o.h_in / 2 || o.w_out != o.w_in / 2 || o.in_pitch != o.c_in ||
+          o.out_pitch != o.c_in || o.c_in % 8) {
+        pvr_set_error("pvr_encoder_create: op %d has an invalid 2x2 average-pool description", i);
+        return PVR_ERR_ARG;
+      }
     } else if (o.kind != PVR_OP_MAXPOOL && o.kind != PVR_OP_AVGPOOL && o.kind != PVR_OP_HEAD &&
                o.kind != PVR_OP_FLATTEN) {
       pvr_set_error("pvr_encoder_create: op %d has unknown kind %d", i, o.kind);
@@ -526,6 +532,9 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
         case PVR_OP_AVGPOOL:
           e = pvr::launch_avgpool_f32(in, emb, emb_ld, o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
           break;
+        case PVR_OP_AVGPOOL2:
+          e = pvr::launch_avgpool2(in, enc->slot_ptr[o.out_slot], n, o.h_in, o.w_in, o.c_in, 1, stream);
+          break;
         case PVR_OP_FLATTEN:
           e = pvr::launch_flatten_f32(in, o.in_pitch, emb, emb_ld, o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
           break;
@@ -559,6 +568,10 @@ static int encoder_run(pvr_encoder* enc, float* emb, int64_t emb_ld, cudaStream_
       case PVR_OP_AVGPOOL:
         e = pvr::launch_avgpool(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), emb, emb_ld,
                                 o.emb_offset, n, o.h_in * o.w_in, o.c_in, stream);
+        break;
+      case PVR_OP_AVGPOOL2:
+        e = pvr::launch_avgpool2(enc->slot_ptr[o.in_slot], enc->slot_ptr[o.out_slot], n, o.h_in, o.w_in, o.c_in, 0,
+                                 stream);
         break;
       case PVR_OP_FLATTEN:
         e = pvr::launch_flatten(reinterpret_cast<const __nv_bfloat16*>(enc->slot_ptr[o.in_slot]), o.in_pitch, emb,

@@ -124,4 +124,7 @@ bool make_tmap_im2col(CUtensorMap* out, const void* base, int c, int pitch, int 
 cudaError_t launch_small_conv1(const void* x, int F, int Hi, int Wi, int Ho, int Wo, const void* wpk, const float* scale,
                                const float* bias, void* y, cudaStream_t stream);
 
+// 2x2 / stride 2 average pool NHWC -> NHWC (clip_rn.cu); f32 != 0: float32 tensors (parity mode), else bf16.
+cudaError_t launch_avgpool2(const void* in, void* out, int n_img, int H, int W, int C, int f32, cudaStream_t stream);
+
 }  // namespace pvr

@@ -14,6 +14,7 @@ from torch import nn
 
 from . import _lib
 from . import program as prg
+from .vision_models import clip_rn
 from .vision_models import clip_vit
 from .vision_models import mae as mae_vit
 from .vision_models import maskrcnn
@@ -228,6 +229,8 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
             model, _ = clip_vit.load("ViT-B/32", device='cpu')
         elif embedding_name == 'clip_vit_b16':  # BASELINE configs[2] geometry (CLIP block structure, patch 16)
             model, _ = clip_vit.load("ViT-B/16", device='cpu')
+        elif embedding_name == 'clip_rn50':  # src/embeddings.py:305-306
+            model, _ = clip_rn.load("RN50", device='cpu')
         else:
             raise NotImplementedError("Requested model not available.")
         transforms = Transforms(CLIP_MEAN, CLIP_STD, size=model.visual.input_resolution,
@@ -240,7 +243,6 @@ def _get_embedding(embedding_name='random', in_channels=3, pretrained=True, trai
     elif embedding_name == 'true_state':
         return nn.Sequential(nn.Identity()), nn.Sequential(nn.Identity())
     else:
-        # clip_rn50: not built (see DESIGN.md scope table)
         raise NotImplementedError("Requested model not available.")
 
     if train:
@@ -373,7 +375,7 @@ class EmbeddingNet(nn.Module):
     def encoder(self):
         self._require_cuda()
         if self._encoder is None:
-            if isinstance(self.embedding, (clip_vit.CLIPImageModel, mae_vit.MAEParams)):
+            if isinstance(self.embedding, (clip_vit.CLIPImageModel, clip_rn.CLIPResNetModel, mae_vit.MAEParams)):
                 self.embedding.invalidate()
                 self._encoder = self.embedding.runner(self.device, self.precision)
             else:

@@ -135,6 +135,14 @@ class Program:
                              h_in=h, w_in=w, in_pitch=c, c_out=c, h_out=p, w_out=q, out_pitch=c, flags=flags))
         return out_slot, p, q
 
+    def avgpool2(self, in_slot, c, h, w, flags=0):
+        """nn.AvgPool2d(2) on an NHWC slot (CLIP's ModifiedResNet); returns (slot, h // 2, w // 2)."""
+        p, q = h // 2, w // 2
+        out_slot = self.alloc(p * q * c * (2 if flags & _lib.PVR_OP_FP32 else 1))
+        self.ops.append(dict(kind=_lib.PVR_OP_AVGPOOL2, in_slot=in_slot, out_slot=out_slot, res_slot=-1, c_in=c,
+                             h_in=h, w_in=w, in_pitch=c, c_out=c, h_out=p, w_out=q, out_pitch=c, flags=flags))
+        return out_slot, p, q
+
     def flatten(self, in_slot, c, h, w, pitch, emb_offset, flags=0):
         self.ops.append(dict(kind=_lib.PVR_OP_FLATTEN, in_slot=in_slot, out_slot=-1, res_slot=-1, c_in=c, h_in=h,
                              w_in=w, in_pitch=pitch, c_out=c, emb_offset=emb_offset, flags=flags))
@@ -382,6 +390,101 @@ def add_resnet50(prog, sd, variant, in_slot, emb_offset, hw=224, compact_stem=Fa
     n = _compress_head(prog, sd, head_prefix, x, chw, emb_offset)
     prog.release(x)
     return n
+
+
+# ------------------------------------------------------------------------------------------------ CLIP ModifiedResNet
+def _clip_down_block(prog, sd, prefix, x_slot, x_chw):
+    """First block of layer2-4 of CLIP's ModifiedResNet (openai/CLIP clip/model.py Bottleneck with stride 2): every conv
+    has stride 1; `avgpool(2)` follows conv2 and precedes the shortcut's 1x1 conv. conv3 and the shortcut conv then run
+    as ONE GEMM over K = [pooled t2 | pooled x] like torchvision's projection blocks (_bottleneck)."""
+    t1, s1 = _conv_bn(prog, sd, prefix + ".conv1", prefix + ".bn1", x_slot, x_chw, 1, 0, True)
+    t2, s2 = _conv_bn(prog, sd, prefix + ".conv2", prefix + ".bn2", t1, s1, 1, 1, True)
+    prog.release(t1)
+    t2p, p, q = prog.avgpool2(t2, s2[0], s2[1], s2[2])
+    prog.release(t2)
+    xp, _, _ = prog.avgpool2(x_slot, x_chw[0], x_chw[1], x_chw[2])
+    prog.release(x_slot)
+    w3 = sd[prefix + ".conv3.weight"].float()
+    wd = sd[prefix + ".downsample.0.weight"].float()
+    co = w3.shape[0]
+    sc3, b3 = fold_bn(sd, prefix + ".bn3")
+    scd, bd = fold_bn(sd, prefix + ".downsample.1")
+    wcat = torch.cat([w3.reshape(co, -1) * sc3[:, None], wd.reshape(co, -1) * scd[:, None]], 1)
+    k = wcat.shape[1]
+    packed = torch.zeros(_round_up(co, 64), k, dtype=torch.bfloat16)
+    packed[:co] = wcat.to(torch.bfloat16)
+    y = prog.conv(t2p, (s2[0], p, q), packed, k, co, 1, 1, (1, 1), (0, 0), (p, q), torch.ones(co), b3 + bd, co,
+                  in2=(xp, (x_chw[0], p, q), x_chw[0], 1), flops=2 * p * q * co * (s2[0] + x_chw[0]))
+    prog.release_after_next_conv(t2p)
+    prog.release_after_next_conv(xp)
+    return y, (co, p, q)
+
+
+def add_clip_resnet(prog, sd, in_slot, hw=224, layers=(3, 4, 6, 3)):
+    """The convolutional trunk of CLIP's ModifiedResNet (`clip.load("RN50").visual` without its attention pool):
+    3-conv stem (3 -> 32 /2, 32 -> 32, 32 -> 64, each + BN + ReLU) -> avgpool(2) -> layer1..4 (Bottlenecks with the
+    stride replaced by average pooling). `in_slot` holds NHWC4 bf16 frames. Returns (slot, (2048, hw/32, hw/32)) of the
+    NHWC bf16 feature map the attention pool reads; nothing is written to the embedding row."""
+    h = hw
+    p = (h + 2 - 3) // 2 + 1
+    sc, bi = fold_bn(sd, "bn1")
+    x = prog.conv(in_slot, (8, h, h // 2), pack_first_small_conv(sd["conv1.weight"].float(), 32), 64, 32, 3, 2, (2, 1),
+                  (-1, -1), (p, p), sc, bi, 32, out_pitch=32, flops=2 * p * p * 32 * 27)
+    for i, co in ((2, 32), (3, 64)):
+        sc, bi = fold_bn(sd, f"bn{i}")
+        y = prog.conv(x, (32, p, p), pack_small_conv(sd[f"conv{i}.weight"].float(), _round_up(co, 32)), 320, co, 3, 3,
+                      (1, 1), (-1, -1), (p, p), sc, bi, co, out_pitch=co, flops=2 * p * p * co * 288)
+        prog.release(x)
+        x = y
+    y, h, w = prog.avgpool2(x, 64, p, p)
+    prog.release(x)
+    x, chw = y, (64, h, w)
+    for li, blocks in enumerate(layers):
+        for b in range(blocks):
+            prefix = f"layer{li + 1}.{b}"
+            if b == 0 and li > 0:
+                x, chw = _clip_down_block(prog, sd, prefix, x, chw)
+            else:
+                x, chw = _bottleneck(prog, sd, prefix, x, chw, 1, b == 0)
+    return x, chw
+
+
+def add_clip_resnet_f32(prog, sd, in_slot, hw=224, layers=(3, 4, 6, 3)):
+    """fp32 counterpart of add_clip_resnet (float32 NHWC4 frames in, float32 NHWC feature map out)."""
+    x, chw = in_slot, (4, hw, hw)
+    for i, (stride, w) in enumerate(((2, _pad_rgb_weight(sd["conv1.weight"].float())), (1, sd["conv2.weight"].float()),
+                                     (1, sd["conv3.weight"].float())), 1):
+        sc, bi = fold_bn(sd, f"bn{i}")
+        y, sy = _conv_f32(prog, w, sc, bi, x, chw, stride, 1, w.shape[0])
+        if i > 1:
+            prog.release(x)
+        x, chw = y, sy
+    y, h, w = prog.avgpool2(x, chw[0], chw[1], chw[2], flags=F32)
+    prog.release(x)
+    x, chw = y, (chw[0], h, w)
+    for li, blocks in enumerate(layers):
+        for b in range(blocks):
+            px = f"layer{li + 1}.{b}"
+            t1, s1 = _conv_bn_f32(prog, sd, px + ".conv1", px + ".bn1", x, chw, 1, 0, True)
+            t2, s2 = _conv_bn_f32(prog, sd, px + ".conv2", px + ".bn2", t1, s1, 1, 1, True)
+            prog.release(t1)
+            if b == 0 and li > 0:
+                t2p, h, w = prog.avgpool2(t2, s2[0], s2[1], s2[2], flags=F32)
+                prog.release(t2)
+                t2, s2 = t2p, (s2[0], h, w)
+                xp, _, _ = prog.avgpool2(x, chw[0], chw[1], chw[2], flags=F32)
+                prog.release(x)
+                x, chw = xp, (chw[0], h, w)
+            if b == 0:
+                idn, sidn = _conv_bn_f32(prog, sd, px + ".downsample.0", px + ".downsample.1", x, chw, 1, 0, False)
+                prog.release(x)
+            else:
+                idn, sidn = x, chw
+            y, sy = _conv_bn_f32(prog, sd, px + ".conv3", px + ".bn3", t2, s2, 1, 0, True, res=(idn, sidn[0], 0))
+            prog.release(t2)
+            prog.release(idn)
+            x, chw = y, sy
+    return x, chw
 
 
 def add_resnet_basic(prog, sd, layers, in_slot, emb_offset, hw=224, compact_stem=False):

@@ -292,12 +292,12 @@ moco_croponly_mujoco moco_croponly_places moco_croponly_places_l3 moco_croponly_
 moco_croponly_places_uber_345 moco_croponly_places_uber_35 moco_croponly_places_uber_45 moco_croponly_uber
 moco_croponly_uber_34 moco_croponly_uber_345 moco_croponly_uber_35 moco_croponly_uber_45 random resnet18 resnet34 resnet50
 resnet50_l3 resnet50_l4 resnet50_places resnet50_places_l3 resnet50_places_l4 true_state""".split()
-NOT_BUILT = {"clip_rn50"}  # DESIGN.md §6
+NOT_BUILT = set()  # every name of the reference builds
 
 
 def test_every_reference_embedding_name_is_accounted_for():
     """The 52 names `_get_embedding` accepts in the reference (every `embedding_name == '...'` of src/embeddings.py:
-    88-318): 51 build here with the reference's output width, 1 raises NotImplementedError like an unknown name."""
+    88-318): all 52 build here with the reference's output width; an unknown name raises NotImplementedError like an unknown name."""
     widths = {"conv5": 2048, "l4": 2058, "l3": 2156}
     assert len(REFERENCE_NAMES) == 52
     with allow_random_init():
@@ -314,7 +314,7 @@ def test_every_reference_embedding_name_is_accounted_for():
             elif name.endswith(("_l3", "_l4")):  # maskrcnn_l3 included: (11, 14, 14)
                 want = widths[name[-2:]]
             else:
-                want = {"random": 1568, "resnet18": 512, "resnet34": 512, "clip_vit": 512, "mae_base": 768,
+                want = {"random": 1568, "resnet18": 512, "resnet34": 512, "clip_vit": 512, "clip_rn50": 1024, "mae_base": 768,
                         "mae_large": 1024, "mae_huge": 1280}.get(name, 2048)
             assert int(model.out_size) == want, name
             assert not model.training and all(not p.requires_grad for p in model.parameters()), name

@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload uber34x3|conv5]
 
-One step = the embedding hot path over one batch of synthetic observations, `--passes` (default 8) encoder passes of
-`obs_per_pass` observations each, so that the K timed steps last >= 2 s (one pass is 13 ms):
+One step = the embedding hot path over one batch of synthetic observations, `--passes` (default 2) encoder passes of
+`obs_per_pass` observations each, so that the K timed steps last >= 2 s (one pass of 768 observations is 52 ms):
 uint8 (B, 224, 224, 3n) -> fused preprocessing kernel -> ResNet-50 trunk(s) (tcgen05 implicit GEMM) -> (B, n*O) fp32.
 Default workload = BASELINE.json configs[1]: moco_aug_uber_34 (layer3 + layer4 compressed taps, two independent
 ResNet-50 trunks as the reference computes them, src/embeddings.py:44-57,225-229), 3-frame observations, bf16.
@@ -38,20 +38,29 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (embedding name, frames per observation, observations per step per GPU)
-    "uber34x3": ("moco_aug_uber_34", 3, 192),
+    # 768 observations = 2304 frames per encoder pass: larger passes amortise the per-launch cost of the 91 conv
+    # kernels (profiles/r02_sweep_pass_size_conv5.txt; 192 -> 768: +2 % at the power-capped clock of this pool)
+    "uber34x3": ("moco_aug_uber_34", 3, 768),
     "conv5": ("moco_aug", 1, 512),
     "clip_b16": ("clip_vit_b16", 1, 1024),  # BASELINE configs[2]: CLIP-architecture ViT-B/16, batch 1024 per GPU
     "clip_b32": ("clip_vit", 1, 1024),      # the reference's actual `clip_vit` (ViT-B/32)
     "mae_base": ("mae_base", 1, 1024),      # MAE ViT-B/16 (bicubic preprocessing, erf GELU)
     "mae_large": ("mae_large", 1, 512),     # MAE ViT-L/16
+    # SURVEY §8(f)-4, measured for DESIGN.md only (no BASELINE config names them)
+    "mae_huge": ("mae_huge", 1, 256),       # MAE ViT-H/14: 257 tokens, 16 heads of 80 (attention_mma.cu)
+    "clip_rn50": ("clip_rn50", 1, 512),     # CLIP ModifiedResNet + attention pool
+    "maskrcnn_l3": ("maskrcnn_l3", 1, 512), # detectron2 R50-C4 through res4 + 1024 -> 11 compression block
 }
 VARIANTS = {"moco_aug": ["conv5"], "moco_aug_uber_34": ["l3", "l4"]}
 CLIP_PATCH = {"clip_vit_b16": 16, "clip_vit": 32}
-MAE_NAMES = ("mae_base", "mae_large")
-VIT_NAMES = tuple(CLIP_PATCH) + MAE_NAMES   # encoders run by ViTRunner (whole forward timed as one unit)
+MAE_NAMES = ("mae_base", "mae_large", "mae_huge")
+# encoders driven by a runner object (whole forward timed as one unit): ViTRunner, CLIPRNRunner
+VIT_NAMES = tuple(CLIP_PATCH) + MAE_NAMES + ("clip_rn50",)
 GFLOP_PER_FRAME = {"moco_aug": 8.174, "moco_aug_uber_34": 14.96,  # SURVEY.md §8(d), convs only
                    "clip_vit_b16": 35.13, "clip_vit": 8.818,
-                   "mae_base": 35.13, "mae_large": 123.1}  # 2 x (patch embed + 12W^2 S + 2 S^2 W per layer) MACs
+                   "mae_base": 35.13, "mae_large": 123.1,  # 2 x (patch embed + 12W^2 S + 2 S^2 W per layer) MACs
+                   "mae_huge": 334.6, "clip_rn50": 12.02,  # runner.flops_per_image
+                   "maskrcnn_l3": 6.636}                   # same convolutions as the MoCo layer-3 variant
 
 
 def load_peaks():
@@ -452,7 +461,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="uber34x3", choices=list(WORKLOADS))
     ap.add_argument("--obs-per-step", type=int, default=0, help="observations per encoder PASS (per GPU)")
-    ap.add_argument("--passes", type=int, default=8, help="encoder passes per step (timed region >= 2 s)")
+    ap.add_argument("--passes", type=int, default=2, help="encoder passes per step (timed region >= 2 s)")
     ap.add_argument("--no-extra", action="store_true", help="skip the clip_b16 / finetune measurements")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bc", action="store_true", help="skip the BC steps/s measurement")
@@ -732,9 +741,9 @@ def finish(args, world, rank, dist, name, n_frames, obs_per_step, frames_per_ste
             if args.workload == "uber34x3" else
             (f"{name}: CLIP-architecture ViT-B/{CLIP_PATCH[name]}, 224x224 uint8 frames, random-init weights"
              if name in CLIP_PATCH else
-             (f"{name}: MAE ViT-{'B' if name == 'mae_base' else 'L'}/16 encoder, bicubic Resize(256)+CenterCrop(224) of "
-              "224x224 uint8 frames, random-init weights" if name in MAE_NAMES else
-              f"{name}: ResNet-50 conv5, 224x224 uint8 frames, random-init weights")),
+             (f"{name}: MAE ViT-{dict(mae_base='B/16', mae_large='L/16', mae_huge='H/14')[name]} encoder, bicubic "
+              "Resize(256)+CenterCrop(224) of 224x224 uint8 frames, random-init weights" if name in MAE_NAMES else
+              f"{name}: 224x224 uint8 frames, random-init weights")),
             "obs_per_step_per_gpu": obs_per_step, "frames_per_step_per_gpu": frames_per_step,
             "passes_per_step": passes, "obs_per_pass": obs_per_step // passes,
             "embedding_width": width, "sharding": "observations split over ranks, no data-path collective",

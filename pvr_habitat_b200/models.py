@@ -217,7 +217,16 @@ class PolicyNet(nn.Module):
         where the step is bound by the host's launch rate and more launches would only slow it down."""
         env = os.environ.get("PVR_LSTM_CHUNKS")
         if not env and B is not None and _lib.lib().pvr_lstm_persist_supported(T, B, 1024):
-            return 1
+            # The persistent kernels occupy 32 CTAs per batch tile of 32 rows: at B <= 32 (finetuning: B = 16) two of
+            # them fit side by side, so the layers run as a wavefront over `c` chunks, each chunk one persistent launch
+            # (state handed over through h_last / c_all / dh_rec / dc_rec, see _lstm_fwd_chunk / _lstm_bwd_chunk).
+            # At B = 128 a layer fills 128 SMs and chunking only adds launches.
+            c = int(os.environ.get("PVR_LSTM_PERSIST_CHUNKS", "2")) if B <= 32 else 1
+            while c > 1 and (T % c or T // c < 8 or not _lib.lib().pvr_lstm_persist_supported(T // c, B, 1024)):
+                c //= 2
+            self._persist_chunks = True
+            return max(c, 1)
+        self._persist_chunks = False
         c = int(env) if env else (8 if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing() else 1)
         while c > 1 and (T % c or T // c < 2):
             c //= 2
@@ -230,8 +239,16 @@ class PolicyNet(nn.Module):
 
     def _lstm_fwd_chunk(self, ws, w, l, t0, Tc, flags):
         B, H, r0 = ws.B, ws.H, t0 * ws.B
+        h0 = ws.h0[l]
+        if getattr(self, "_persist_chunks", False):
+            # chunk of a persistent-kernel wavefront: an ordinary sequence (flags 0) whose initial state is the previous
+            # chunk's final one — h_{t0-1} in h_last (fp32, masked and rounded to the bf16 operand exactly as the
+            # unchunked kernel does between steps), c_{t0-1} already in c_all[t0]
+            flags = 0
+            if t0 > 0:
+                h0 = ws.h_last[l]
         L = pvr_lstm_fwd(T=Tc, B=B, H=H, flags=flags, w_hh=w["Whh"][l].data_ptr(), xp=ws.XP[l][r0:].data_ptr(),
-                         nd=ws.nd[t0:].data_ptr(), h0=ws.h0[l].data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
+                         nd=ws.nd[t0:].data_ptr(), h0=h0.data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
                          hm=ws.hm[l][r0:].data_ptr(), h_out=ws.HL[l][r0:].data_ptr(),
                          gates=ws.gates[l][r0:].data_ptr(), g_tmp=ws.g_tmp[l].data_ptr(),
                          h_last=ws.h_last[l].data_ptr(), counters=ws.lstm_counters[l].data_ptr(),
@@ -240,6 +257,9 @@ class PolicyNet(nn.Module):
 
     def _lstm_bwd_chunk(self, ws, w, l, t0, Tc, flags, dbias=None):
         B, H, r0 = ws.B, ws.H, t0 * ws.B
+        persist = getattr(self, "_persist_chunks", False)
+        if persist:
+            flags = 0  # dh_rec / dc_rec carry the state between the chunks (read on entry, dc_rec written on exit)
         L = pvr_lstm_bwd(T=Tc, B=B, H=H, flags=flags, w_hh_t=w["WhhT"][l].data_ptr(), nd=ws.nd[t0:].data_ptr(),
                          gates=ws.gates[l][r0:].data_ptr(), c_all=ws.c_all[l][r0:].data_ptr(),
                          dh_out=ws.dHL[l][r0:].data_ptr(), dh_rec=ws.dh_rec[l].data_ptr(),
@@ -247,6 +267,11 @@ class PolicyNet(nn.Module):
                          dbias=dbias.data_ptr() if dbias is not None else None,
                          counters=ws.lstm_counters[l].data_ptr(), counters_bytes=ws.lstm_counters[l].numel() * 4)
         _lib.check(_lib.lib().pvr_lstm_backward(ctypes.byref(L), _stream()), "pvr_lstm_backward")
+        if persist and t0 > 0:
+            # gradient flowing into h_{t0-1}: nd[t0] * (dG_{t0} W_hh) — the product the kernel leaves out at the first
+            # step of its sequence (training starts from a constant state); same bf16 operands / fp32 sum as in-kernel
+            gemm(ws.dG[l][r0:r0 + B], w["WhhT"][l], ws.dh_rec[l], B, H, 4 * H, out_f32=1)
+            ws.dh_rec[l].mul_(ws.nd[t0].unsqueeze(1))
 
     def _check_generation(self, generation):
         if generation != self._generation:

@@ -491,6 +491,21 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
         pvr_set_error("pvr_encoder_bind: op %zu: output/residual tensor map: %s", i, err);
         return PVR_ERR_CUDA;
       }
+      // A-stationary tile order (ConvGemmParams::astat): plain 1x1 layers whose K chunks exactly fill the stage ring
+      // and that have several N tiles per M tile — layer3's 256 -> 1024 + residual (K = 4 chunks, 8 N tiles), which
+      // takes in 160 KB per 128 x 128 tile at ~32 B/clk and is bound by neither HBM nor the tensor pipe. M tiles are
+      // padded to a multiple of the grid (<= 4 % more tiles; the padding tiles read zeros and store nothing).
+      // PVR_ASTAT: 0 = off, 1 (default) = when the padding costs <= 4 %, 2 = always (tests: small batches)
+      const int astat_mode = getenv("PVR_ASTAT") ? atoi(getenv("PVR_ASTAT")) : 1;
+      if (astat_mode && b.a_mode == pvr::A_TILED && !p.cta2 && p.kc_split == 0 && p.split_k == 1 &&
+          p.num_k_chunks == pvr::conv_gemm_stages(b.block_n, true) && p.num_n_tiles >= 2 &&
+          (p.num_n_tiles & (p.num_n_tiles - 1)) == 0) {
+        const int padded = (p.num_m_tiles + enc->sms - 1) / enc->sms * enc->sms;
+        if (astat_mode >= 2 || (long long)padded * 100 <= (long long)p.num_m_tiles * 104) {
+          p.num_m_tiles = padded;
+          p.astat = 1;
+        }
+      }
     }
   }
   enc->n_images = n_images;

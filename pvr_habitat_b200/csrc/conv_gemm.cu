@@ -134,6 +134,14 @@ __device__ __forceinline__ int tile_mn(const ConvGemmParams& p, int tile) {
 // (m_tile, n_tile) without an integer division when the number of N tiles is a power of two (every ResNet layer):
 // the epilogue threads evaluate this per sub-tile.
 __device__ __forceinline__ void tile_coords(const ConvGemmParams& p, int tile, int& m_tile, int& n_tile) {
+  if (p.astat) {  // A-stationary order (ConvGemmParams::astat): iteration `it` of CTA w = (m-tile w + (it / Nn) grid, it % Nn)
+    const int ws = (int)gridDim.x;
+    const int it = tile / ws, w = tile - it * ws;
+    m_tile = w + (it >> p.n_tiles_shift) * ws;
+    n_tile = it & (p.num_n_tiles - 1);
+    if (p.reverse) m_tile = p.num_m_tiles - 1 - m_tile;
+    return;
+  }
   const int mn = tile_mn(p, tile);
   if (p.n_tiles_shift >= 0) {
     m_tile = mn >> p.n_tiles_shift;
@@ -287,10 +295,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int i = 0; i < BLOCK_M / 64; ++i)
               tma_load_2d(&tmap_a, &full_bar[stage], a_dst + i * 8192, m0 + 64 * i, kc * BLOCK_K);
           } else {
-          mbar_expect_tx(&full_bar[stage], A_STAGE_BYTES + C::B_STAGE_BYTES);
+          // A-stationary order: from the second n-tile of an m-tile on, stage kc still holds A's K chunk kc
+          const bool a_resident = A_MODE == A_TILED && p.astat && n_tile != 0;
+          mbar_expect_tx(&full_bar[stage], (a_resident ? 0u : A_STAGE_BYTES) + C::B_STAGE_BYTES);
           tma_load_2d(&tmap_b, &full_bar[stage], sB + stage * C::B_STAGE_BYTES, kc * BLOCK_K, n0);
           if (A_MODE == A_TILED) {
-            if (kc < p.kc_split || p.kc_split == 0)
+            if (a_resident) {
+            } else if (kc < p.kc_split || p.kc_split == 0)
               tma_load_2d(&tmap_a, &full_bar[stage], a_dst, kc * BLOCK_K, m0);
             else if (p.a2_im2col)  // second K range: the shortcut's input, 1x1 taps with a stride
               tma_load_im2col_4d(&tmap_a2, &full_bar[stage], a_dst, (kc - p.kc_split) * BLOCK_K, w0, h0, img,
@@ -735,11 +746,25 @@ cudaError_t launch_mode(int a_mode, const CUtensorMap& ta, const CUtensorMap& tb
 
 }  // namespace
 
+int conv_gemm_stages(int block_n, bool epi_tma) {
+  switch (block_n) {
+    case 32: return epi_tma ? Cfg<32, true>::STAGES : Cfg<32, false>::STAGES;
+    case 64: return epi_tma ? Cfg<64, true>::STAGES : Cfg<64, false>::STAGES;
+    case 128: return epi_tma ? Cfg<128, true>::STAGES : Cfg<128, false>::STAGES;
+    case 256: return epi_tma ? Cfg<256, true>::STAGES : Cfg<256, false>::STAGES;
+    default: return 0;
+  }
+}
+
 cudaError_t launch_conv_gemm(int block_n, int a_mode, bool epi_tma, const CUtensorMap& tmap_a,
                              const CUtensorMap& tmap_b, const CUtensorMap& tmap_out, const CUtensorMap& tmap_res,
                              const ConvGemmParams& p_in, int num_sms, cudaStream_t stream,
                              const CUtensorMap* tmap_a2) {
   if (p_in.split_k < 1) return cudaErrorInvalidValue;
+  if (p_in.astat && (a_mode != A_TILED || p_in.cta2 || p_in.mn || p_in.split_k != 1 || p_in.kc_split ||
+                     p_in.num_k_chunks != conv_gemm_stages(block_n, epi_tma) || p_in.num_m_tiles % num_sms ||
+                     (p_in.num_n_tiles & (p_in.num_n_tiles - 1))))
+    return cudaErrorInvalidValue;
   if (p_in.kc_split && (a_mode != A_TILED || !tmap_a2)) return cudaErrorInvalidValue;
   const CUtensorMap& ta2 = tmap_a2 ? *tmap_a2 : tmap_a;
   ConvGemmParams p = p_in;

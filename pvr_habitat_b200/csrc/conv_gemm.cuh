@@ -50,7 +50,16 @@ struct ConvGemmParams {
   const __nv_bfloat16* res;  // may be null
   const float* scale;        // (n_pad)
   const float* bias;         // (n_pad)
+  // 1: A-stationary tile order (plain 1x1 layers whose K chunks exactly fill the stage ring, e.g. 256 -> 1024 +
+  // residual of layer3): CTA w walks m-tiles w, w + grid, ... and ALL n-tiles of one m-tile back to back, so K chunk
+  // kc of the A tile is already in stage kc from the previous n-tile and only the W chunk is reloaded — 96 KB instead
+  // of 160 KB taken in per 128 x 128 tile by a kernel that is bound by the SM's ingest rate. num_m_tiles is padded to
+  // a multiple of the grid; rows past M are zero-filled by the TMA loads and clipped by the TMA stores.
+  int astat;
 };
+
+// Stages of the TMA ring of the single-CTA kernel (host-side twin of Cfg<BLOCK_N, EPI_TMA>::STAGES).
+int conv_gemm_stages(int block_n, bool epi_tma);
 
 // Launch on `stream`; block_n in {32, 64, 128, 256}. Returns cudaError_t of the launch.
 // epi_tma: stage the output through shared memory + TMA store (needs n_valid % 64 == 0, block_n >= 64); tmap_out /

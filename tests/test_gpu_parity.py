@@ -390,3 +390,21 @@ def test_fp32_mode_small_conv_vs_reference_golden(golden_dir):
     net.set_precision("fp32")
     for key in ("64", "224"):
         check_embedding_fp32(net(torch.from_numpy(gold["frames" + key])), gold["emb" + key])
+
+
+def test_a_stationary_tile_order_is_bitwise_neutral(monkeypatch):
+    """ConvGemmParams::astat (layer3's 256 -> 1024 + residual convs walk all N tiles of an M tile back to back and reload
+    only the weight chunks): another tile ORDER of the same arithmetic, so the embeddings are bit-identical. PVR_ASTAT=2
+    forces it at a batch where the M-tile padding would normally rule it out (it is on by default from ~1200 frames)."""
+    from pvr_habitat_b200.embeddings import EmbeddingNet
+    from pvr_habitat_b200.vision_models.moco import allow_random_init
+    frames = torch.from_numpy(restate.structured_frames(16, 64, 64, 3, 17))  # >= 13 frames: 128-wide tiles at layer3
+    outs = []
+    for mode in ("0", "2"):
+        monkeypatch.setenv("PVR_ASTAT", mode)
+        torch.manual_seed(4)
+        with allow_random_init():
+            net = EmbeddingNet("moco_aug_uber_34")
+        outs.append(net(frames))
+    assert outs[0].shape == (16, 4214) and np.isfinite(outs[0]).all()
+    assert np.array_equal(outs[0], outs[1])

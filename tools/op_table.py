@@ -12,6 +12,7 @@ name = sys.argv[1] if len(sys.argv) > 1 else "moco_aug"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 net = bench.build_net(name, torch.device("cuda", 0))
+net.max_images_per_pass = n  # one pass: the encoder stays bound to all n frames for the timed forwards below
 obs = torch.from_numpy(bench.make_observations(n, 1, 3)).cuda()
 out = net.embed(obs, 1)
 enc = net.encoder()

@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b, float& sum) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(320) vit_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int W,
+__global__ void __launch_bounds__(256, 2) vit_attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, int S, int W,
                                                                  int heads, float scale_log2e,
                                                                  __nv_bfloat16* __restrict__ out) {
   static_assert(D % 16 == 0 && D <= 128, "head_dim");
@@ -193,15 +193,21 @@ int launch(const void* qkv, int n_img, int tokens, int width, int heads, void* o
   }
   static size_t configured = 0;
   if (smem > configured) {
-    const cudaError_t e = cudaFuncSetAttribute(vit_attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(vit_attention_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    // two blocks per SM (2 x 101 KB at mae_huge's shape) need the full shared-memory carve-out: with the default one
+    // the driver sized it for ONE block (ncu: "Block Limit Shared Mem 1", 12 % occupancy, 68 % of the issue slots idle)
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(vit_attention_mma_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                               cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) { pvr_set_error("pvr_attention_mma: %s", cudaGetErrorString(e)); return PVR_ERR_CUDA; }
     configured = smem;
   }
-  // as many warps (<= 10) as keep the 16-row tiles evenly spread: 257 tokens = 17 tiles -> 9 warps x 2 rounds
-  // (first version: 6 warps x 3 rounds, 467 us per layer of mae_huge at 256 images)
+  // as many warps (<= 8) as keep the 16-row tiles evenly spread: 257 tokens = 17 tiles -> 6 warps x 3 rounds. (Registers
+  // are allocated per 4 warps: 9 warps x 2 rounds was tried and is slower, 587 vs 467 us per layer of mae_huge at 256
+  // images, because it costs the second block per SM — profiles/r02_ncu_full_attention_mma.txt.)
   const int rtiles = (tokens + 15) / 16;
-  const int rounds = (rtiles + 9) / 10;
+  const int rounds = (rtiles + 7) / 8;
   const int warps = (rtiles + rounds - 1) / rounds;
   vit_attention_mma_kernel<D><<<n_img * heads, 32 * warps, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(qkv), tokens, width, heads, 1.4426950408889634f / sqrtf((float)D),

@@ -55,13 +55,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// ELU for v <= 0: expm1f costs ~35 instructions per value and was the largest item of the first version; the result is
-// rounded to bf16 (2^-9 relative), so a degree-5 Taylor polynomial below |v| = 1/8 (relative error < 5e-8) and
-// __expf(v) - 1 above it (absolute error ~1e-7 on a magnitude >= 0.117) are exact for this purpose.
+// ELU for v <= 0: expm1f costs ~35 instructions per value and was the largest item of the first version (the kernel is
+// issue bound: ncu, profiles/r02_ncu_full_small_conv.txt). The result is rounded to bf16 (relative 2^-9), so
+// ex2.approx(v log2 e) - 1 is exact for this purpose: its absolute error (~1.2e-7) is below half a bf16 ulp of the
+// result for |v| > 6e-5 and below 1.2e-7 in absolute terms everywhere.
 __device__ __forceinline__ float elu_neg(float v) {
-  const float t = v * fmaf(v, fmaf(v, fmaf(v, fmaf(v, 1.f / 120.f, 1.f / 24.f), 1.f / 6.f), 0.5f), 1.f);
-  const float e = __expf(v) - 1.f;
-  return v > -0.125f ? t : e;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+  return e - 1.f;
 }
 
 // ---------------------------------------------------------------------------------------------- forward
@@ -74,7 +75,7 @@ __device__ __forceinline__ float elu_neg(float v) {
 // that a thread's 8 results of one pixel are the 8 consecutive channels 8 tg .. 8 tg + 7: one 16-byte store per pixel.
 // `wpk` is the packed weight of program.pack_first_small_conv: bf16 (32, 64), K index 16 r + 4 + 4 j + c for filter
 // tap (row r, column j) and input channel c.
-__global__ void __launch_bounds__(256) small_conv1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int F, int Hi, int Wi,
+__global__ void __launch_bounds__(256, 3) small_conv1_fwd_kernel(const __nv_bfloat16* __restrict__ x, int F, int Hi, int Wi,
                                                               int Ho, int Wo, const __nv_bfloat16* __restrict__ wpk,
                                                               const float* __restrict__ scale,
                                                               const float* __restrict__ bias,

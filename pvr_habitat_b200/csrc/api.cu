@@ -182,9 +182,12 @@ extern "C" int pvr_encoder_bind(pvr_encoder* enc, int n_images, void* workspace,
   const bool zigzag = getenv("PVR_NO_ZIGZAG") == nullptr;
   const int pdl = getenv("PVR_NO_PDL") == nullptr;
   const bool b2b_on = getenv("PVR_NO_B2B") == nullptr;
-  // layer2 variant with streamed weights: correct and bit-identical, but measured neutral (133 us against 86 + 51 us
-  // per 256 frames: the 256 KB of weights per tile go through two-slot rings) -> opt-in
-  const bool b2b_stream_on = b2b_on && getenv("PVR_B2B_STREAM") != nullptr;
+  // layer2 variant with streamed weights (256 KB of weights per tile go through two-slot rings): bit-identical, and
+  // kernel by kernel as fast as the two launches it replaces (133 us against 86 + 51 us per 256 frames) — but it keeps
+  // the 512-channel tensor from being re-read by the next conv1 (0.8 MB per frame and block), and on the power-capped
+  // B200s of this pool fewer HBM bytes are worth +1.2 % on the whole default step (A/B in one job, twice:
+  // 45.02 / 45.29 k -> 45.68 / 45.77 k frames/s). On by default since the end of round 2; PVR_B2B_STREAM=0 turns it off.
+  const bool b2b_stream_on = b2b_on && !(getenv("PVR_B2B_STREAM") && atoi(getenv("PVR_B2B_STREAM")) == 0);
   const int pair_mode = getenv("PVR_CTA2") ? atoi(getenv("PVR_CTA2")) : 2;  // 0 off, 1: 256-wide pair tiles; 2 (default since round 2: the N = 128 3x3 convs of layer2 gain 8 %: a single CTA reads A + W at the shared-memory port limit there): + 128-wide (no residual); 3: + residual layers
   for (size_t i = 0; i < enc->ops.size(); ++i) {
     const pvr_op& o = enc->ops[i];

@@ -298,14 +298,16 @@ def test_fused_kernels_bit_identical_on_ragged_tiles(emb, monkeypatch):
 
 def test_streamed_back_to_back_kernel_is_bit_identical(emb, monkeypatch):
     """conv_b2b_stream_kernel (layer2: 128 -> 512 + residual fused with the next 512 -> 128, weights streamed through
-    rings) is opt-in (PVR_B2B_STREAM); its embeddings are bitwise those of the default schedule."""
+    rings; the default since the end of round 2, PVR_B2B_STREAM=0 turns it off): its embeddings are bitwise those of
+    the two separate kernels."""
     frames = restate.structured_frames(6, 224, 224, 3, 17)
+    monkeypatch.setenv("PVR_B2B_STREAM", "0")
     net = make_net("moco_aug", emb["weight_seeds"])
-    default = net.embed(torch.from_numpy(frames)).cpu().numpy()
-    monkeypatch.setenv("PVR_B2B_STREAM", "1")
+    separate = net.embed(torch.from_numpy(frames)).cpu().numpy()
+    monkeypatch.delenv("PVR_B2B_STREAM")
     net2 = make_net("moco_aug", emb["weight_seeds"])
     streamed = net2.embed(torch.from_numpy(frames)).cpu().numpy()
-    assert np.array_equal(default, streamed)
+    assert np.array_equal(separate, streamed)
     assert net2.encoder().lib.pvr_encoder_launch_count(net2.encoder().handle) < \
         net.encoder().lib.pvr_encoder_launch_count(net.encoder().handle)
 

@@ -119,3 +119,23 @@ def test_embedding_fp32_mode_vs_reference_golden(gold):
         r = np.linalg.norm(got - ref) / np.linalg.norm(ref)
         print(f"clip_rn50 {case} fp32 mode: rel-L2 {r:.2e}")
         assert r <= 1e-5, r
+
+
+@pytest.mark.parametrize("name", ["clip_rn50", "maskrcnn_l3", "mae_huge"])
+def test_two_frame_observations_and_pass_splitting(name):
+    """`embed` with 6-channel observations (frame split / regroup of main_bc_1.py:128-136 inside the kernels) and a batch
+    cut into several encoder passes give exactly the per-frame calls' rows, for the encoders added last."""
+    from oracle import restate
+    with allow_random_init():
+        net = EmbeddingNet(name)
+    obs = restate.structured_frames(5, 64, 64, 6, 61)
+    fused = net.embed(torch.from_numpy(obs), n_frames=2).cpu().numpy()
+    O = net.out_size
+    assert fused.shape == (5, 2 * O) and np.isfinite(fused).all()
+    frames, _ = restate.split_frames(obs)
+    host = restate.regroup_frames(np.atleast_2d(net(torch.from_numpy(frames))), 2)
+    assert np.array_equal(host, fused)
+    net.max_images_per_pass = 4  # 10 frames -> passes of 2 observations
+    assert np.array_equal(net.embed(torch.from_numpy(obs), n_frames=2).cpu().numpy(), fused)
+    single = net(torch.from_numpy(frames[:1]))
+    assert single.shape == (O,)  # squeezed like the reference (src/embeddings.py:402)

@@ -9,8 +9,9 @@ import torch.nn.functional as F
 from pvr_habitat_b200 import _lib
 
 
-def emulate(prog, frames_nhwc4, round_bf16=True):
-    """frames_nhwc4: slot-0 contents, (N, H, W/2, 32) W-expanded frames (program.expand_stem_input). Returns (N, emb_width)."""
+def emulate(prog, frames_nhwc4, round_bf16=True, return_slots=False):
+    """frames_nhwc4: slot-0 contents, (N, H, W/2, 32) W-expanded frames (program.expand_stem_input). Returns (N, emb_width);
+    with `return_slots` also the final contents of every slot (programs that leave a feature map for a runner)."""
     n = frames_nhwc4.shape[0]
     slots = {0: frames_nhwc4.reshape(n, -1).float()}
     emb = torch.zeros(n, prog.emb_width)
@@ -69,6 +70,11 @@ def emulate(prog, frames_nhwc4, round_bf16=True):
             x = slots[op["in_slot"]][:, :h * w * c].reshape(n, h, w, c).permute(0, 3, 1, 2)
             y = F.max_pool2d(x, 3, 2, 1)
             slots[op["out_slot"]] = y.permute(0, 2, 3, 1).reshape(n, -1).contiguous()
+        elif k == _lib.PVR_OP_AVGPOOL2:
+            c, h, w = op["c_in"], op["h_in"], op["w_in"]
+            x = slots[op["in_slot"]][:, :h * w * c].reshape(n, h, w, c).permute(0, 3, 1, 2)
+            y = rb(F.avg_pool2d(x, 2))
+            slots[op["out_slot"]] = y.permute(0, 2, 3, 1).reshape(n, -1).contiguous()
         elif k == _lib.PVR_OP_FLATTEN:
             c, h, w, pitch = op["c_in"], op["h_in"], op["w_in"], op["in_pitch"]
             x = slots[op["in_slot"]][:, :h * w * pitch].reshape(n, h * w, pitch)[..., :c]
@@ -99,4 +105,4 @@ def emulate(prog, frames_nhwc4, round_bf16=True):
             s2, b2 = aux[base:base + c], aux[base + c:base + 2 * c]
             y = F.conv2d(a, w2, padding=1) * s2[None, :, None, None] + b2[None, :, None, None] + idn
             emb[:, op["emb_offset"]:op["emb_offset"] + c * h * w] = y.relu().reshape(n, -1)
-    return emb
+    return (emb, slots) if return_slots else emb

@@ -352,3 +352,68 @@ def test_embedding_wrapper_without_gym():
     assert o.shape == (10,) and o.dtype == np.float32 and Enc.calls[-1] == ((1, 64, 64, 6), torch.uint8, 2)
     o, r, d, info = w.step(0)
     assert o.shape == (10,) and r == 1.0 and d is False and w.action_space.n == 3
+
+
+# ------------------------------------------------------------------------------------------------ encoders of §8(f)-4
+def test_maskrcnn_program_equals_oracle_backbone():
+    """detectron2-named weights -> program_state_dict -> add_resnet50(variant='l3', stride_in_1x1=True), emulated on the
+    CPU, against the restated detectron2 backbone (stride on the first 1x1, 1x1 shortcut of the compression block as the
+    centre tap of a 3x3 kernel)."""
+    from oracle import restate_maskrcnn as rm
+    from pvr_habitat_b200.vision_models.maskrcnn import MaskRCNNBackboneParams
+    sd = rm.maskrcnn_state(5)
+    sd = {k: (v.to(torch.bfloat16).float() if v.dim() == 4 else v) for k, v in sd.items()}
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 32 * 32)
+    prog.emb_width = prg.add_resnet50(prog, MaskRCNNBackboneParams.program_state_dict(sd), "l3", s0, 0, hw=64,
+                                      stride_in_1x1=True)
+    assert prog.emb_width == 11 * 4 * 4
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1)) * 40
+    x4 = torch.zeros(2, 64, 64, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    got = emulate(prog, prg.expand_stem_input(x4), round_bf16=False)
+    net = rm.build_backbone()
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        ref = net(x)["res4"].reshape(2, -1)
+    assert float((got - ref).abs().max()) <= 3e-3 * float(ref.abs().max())
+
+
+def test_clip_resnet_program_equals_oracle_trunk():
+    """add_clip_resnet (3-conv stem, PVR_OP_AVGPOOL2, pooled projection blocks as one GEMM over [t2 | x]) emulated on the
+    CPU against the restated ModifiedResNet up to its attention pool; the slot planner must keep the feature map the
+    runner reads alive."""
+    from oracle import restate_clip_rn as rc
+    sd = {k[len("visual."):]: v for k, v in rc.clip_rn50_state(3).items() if k.startswith("visual.")}
+    sd = {k: (v.to(torch.bfloat16).float() if v.dim() == 4 else v) for k, v in sd.items()}
+    prog = prg.Program()
+    s0 = prog.new_slot(64 * 64 * 4)
+    feat, chw = prg.add_clip_resnet(prog, sd, s0, hw=64)
+    prog.emb_width = 1
+    assert chw == (2048, 2, 2)
+    kinds = [op["kind"] for op in prog.ops]
+    assert kinds.count(_lib_kinds()["avgpool2"]) == 1 + 2 * 3  # stem + (t2, x) of layer2.0 / layer3.0 / layer4.0
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    x4 = torch.zeros(2, 64, 64, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    _, slots = emulate(prog, x4, round_bf16=False, return_slots=True)
+    got = slots[feat][:, :2 * 2 * 2048].reshape(2, 2, 2, 2048).permute(0, 3, 1, 2)
+    m = rc.ModifiedResNet().eval()
+    m.load_state_dict({k: v for k, v in sd.items()}, strict=True)
+    with torch.no_grad():
+        t = x
+        for conv, bn in ((m.conv1, m.bn1), (m.conv2, m.bn2), (m.conv3, m.bn3)):
+            t = torch.relu(bn(conv(t)))
+        ref = m.layer4(m.layer3(m.layer2(m.layer1(m.avgpool(t)))))
+    assert float((got - ref).abs().max()) <= 3e-3 * float(ref.abs().max())
+    # no conv writes into a slot it (or its residual / second input) still reads
+    for op in prog.ops:
+        if op["kind"] == 1:
+            assert op["out_slot"] not in (op["in_slot"], 0)
+            if op.get("in2_c", 0):
+                assert op["in2_slot"] not in (op["out_slot"], op["in_slot"])
+
+
+def _lib_kinds():
+    from pvr_habitat_b200 import _lib
+    return {"avgpool2": _lib.PVR_OP_AVGPOOL2}

@@ -9,9 +9,10 @@
 // version (fp32 FMA from shared-memory weights) measured 386 us forward / 1043 us weight gradient
 // (profiles/r02_launches_finetune_direct_v0.csv): shared-memory and latency bound. These kernels keep the operands in
 // registers and issue warp-level mma.sync m16n8k16 (bf16 x bf16 -> fp32) instead, which takes the arithmetic off the
-// critical path and leaves the memory system as the only bound. Same arithmetic as the GEMM path they replace: bf16
-// inputs and weights, fp32 accumulation, fp32 bias, ELU (expm1f), bf16 output; the backward rounds
-// dz = dy * ELU'(y) to bf16 before it is multiplied, as the GEMM path's operand was.
+// critical path: measured 155 us forward (issue bound at IPC 2.2) / 171 us weight gradient (4.3 TB/s),
+// profiles/r02_ncu_full_small_conv.txt. Same arithmetic as the GEMM path they replace: bf16 inputs and weights, fp32
+// accumulation, fp32 bias, ELU (ex2-based, see elu_neg), bf16 output; the backward rounds dz = dy * ELU'(y) to bf16
+// before it is multiplied, as the GEMM path's operand was.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
